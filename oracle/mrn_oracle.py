@@ -276,8 +276,8 @@ def ctc_nll_and_grad(logits: torch.Tensor, targets: torch.Tensor, target_lengths
             alpha[0, 1] = lpe[0, 1]
         for t in range(1, T):
             a = alpha[t - 1]
-            a1 = torch.cat([torch.full((1,), NEG_INF, dtype=dt), a[:-1]])
-            a2 = torch.cat([torch.full((2,), NEG_INF, dtype=dt), a[:-2]])
+            a1 = torch.cat([torch.full((1,), NEG_INF, dtype=dt), a])[:S]
+            a2 = torch.cat([torch.full((2,), NEG_INF, dtype=dt), a])[:S]
             a2 = torch.where(can_skip, a2, torch.full_like(a2, NEG_INF))
             alpha[t] = torch.logsumexp(torch.stack([a, a1, a2]), 0) + lpe[t]
         tail = alpha[T - 1, S - 1:S] if S == 1 else alpha[T - 1, S - 2:S]
@@ -293,8 +293,8 @@ def ctc_nll_and_grad(logits: torch.Tensor, targets: torch.Tensor, target_lengths
             beta[T - 1, S - 2] = lpe[T - 1, S - 2]
         for t in range(T - 2, -1, -1):
             bt = beta[t + 1]
-            b1 = torch.cat([bt[1:], torch.full((1,), NEG_INF, dtype=dt)])
-            b2 = torch.cat([bt[2:], torch.full((2,), NEG_INF, dtype=dt)])
+            b1 = torch.cat([bt, torch.full((1,), NEG_INF, dtype=dt)])[1:S + 1]
+            b2 = torch.cat([bt, torch.full((2,), NEG_INF, dtype=dt)])[2:S + 2]
             skip_from = torch.zeros(S, dtype=torch.bool)
             if S > 2:
                 skip_from[:-2] = can_skip[2:]
