@@ -1,0 +1,197 @@
+/* mrn_b200 -- C ABI of the B200-native MRN multiplexed-routing train / infer step.
+ *
+ * The reference (simplify23/MRN) is pure Python/PyTorch and has no FFI of its own; its boundary for this path
+ * is the nn.Module / learner API of modules/model.py, modules/dm_router.py and il_modules/mrn.py.  Every entry
+ * point below names the reference code (file:line, relative to the reference root) it replaces.  The Python
+ * mirror of that API (mrn_b200/modules/*.py, mrn_b200/il_modules/mrn.py) binds these symbols through ctypes
+ * (mrn_b200/_lib.py); INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it is documented as a host array
+ *     (pointer tables `const T* const*`, `ld`, `Ci` arrays and the MrnbSvtrPack struct live on the host);
+ *   - the caller owns all memory (inputs, outputs, workspace); nothing is allocated or freed, nothing
+ *     synchronises; every kernel is enqueued on `stream` (a cudaStream_t passed as void*-compatible handle);
+ *   - return value: 0 = MRNB_OK, negative = error; mrnb_last_error() returns a thread-local message;
+ *   - there is no CPU fallback and no alternative backend: the library is sm_100a code only.
+ */
+#ifndef MRN_B200_H
+#define MRN_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define MRNB_OK 0
+#define MRNB_ERR_ARG (-1)
+#define MRNB_ERR_WORKSPACE (-2)
+#define MRNB_ERR_LAUNCH (-3)
+#define MRNB_ERR_UNSUPPORTED (-4)
+
+#define MRNB_MAX_EXPERTS 8
+#define MRNB_PREC_FP32 0 /* CUDA-core fp32 contractions (parity mode, 1e-4 tolerance) */
+#define MRNB_PREC_BF16 1 /* tcgen05 bf16 operands, fp32 accumulate in TMEM (2e-2 tolerance) */
+
+int mrnb_version(void);
+const char* mrnb_last_error(void);
+/* kernels launched by this library since the last reset (bench.py "gpu_launches") */
+long mrnb_launch_count(void);
+void mrnb_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * SVTR expert recognisers, grouped over experts.
+ * Replaces  modules/model.py:82-101 (Model_Extractor.forward), :133-148 (Model.forward),
+ *           modules/svtr.py:500-528 (SVTR.forward_features) and everything below it,
+ *           torch.stack(features, 1) at modules/model.py:400 / :369.
+ *
+ * Parameter slots (MrnbSvtrPack.p[slot]): fp32 device tensors STACKED over experts, [I, ...reference shape...],
+ * except the two layouts marked (*) which are re-laid once at load time (kh,kw before Cin):
+ */
+enum {
+  MRNB_P_POS_EMBED = 0, /* [I,512,64]        ConvNet.pos_embed */
+  MRNB_P_CONV0_W,       /* [I,32,4,3,3]      patch_embed.proj.0.weight */
+  MRNB_P_CONV0_B,       /* [I,32] */
+  MRNB_P_BN0_W, MRNB_P_BN0_B, MRNB_P_BN0_MEAN, MRNB_P_BN0_VAR, /* [I,32] patch_embed.proj.1.* (mean/var are updated in train mode) */
+  MRNB_P_CONV1_W,       /* [I,64,3,3,32] (*) patch_embed.proj.3.weight permuted (0,2,3,1) */
+  MRNB_P_CONV1_B,       /* [I,64] */
+  MRNB_P_BN1_W, MRNB_P_BN1_B, MRNB_P_BN1_MEAN, MRNB_P_BN1_VAR, /* [I,64] patch_embed.proj.4.* */
+  MRNB_P_BLOCK0 = 13,   /* 12 blocks x MRNB_PB_COUNT slots: blocks1.0-2, blocks2.0-5, blocks3.0-2 */
+  MRNB_P_SUB0 = 13 + 12 * 12, /* 3 merges x MRNB_PS_COUNT slots: sub_sample1..3 */
+  MRNB_P_SEQ_W = 13 + 12 * 12 + 3 * 4, /* [I,256,512] model.SequenceModeling.0.weight */
+  MRNB_P_SEQ_B,         /* [I,256] */
+  MRNB_P_COUNT
+};
+enum { /* per block, d = 64/128/256 */
+  MRNB_PB_NORM1_W = 0, MRNB_PB_NORM1_B, /* [I,d] */
+  MRNB_PB_QKV_W, MRNB_PB_QKV_B,         /* [I,3d,d], [I,3d] */
+  MRNB_PB_PROJ_W, MRNB_PB_PROJ_B,       /* [I,d,d], [I,d] */
+  MRNB_PB_NORM2_W, MRNB_PB_NORM2_B,
+  MRNB_PB_FC1_W, MRNB_PB_FC1_B,         /* [I,4d,d], [I,4d] */
+  MRNB_PB_FC2_W, MRNB_PB_FC2_B,         /* [I,d,4d], [I,d] */
+  MRNB_PB_COUNT
+};
+enum { /* per merge, Cin -> Cout = 64->128, 128->256, 256->512 */
+  MRNB_PS_CONV_W = 0, /* [I,Cout,3,3,Cin] (*) sub_sampleK.conv.weight permuted (0,2,3,1) */
+  MRNB_PS_CONV_B,     /* [I,Cout] */
+  MRNB_PS_NORM_W, MRNB_PS_NORM_B, /* [I,Cout] */
+  MRNB_PS_COUNT
+};
+
+typedef struct MrnbSvtrPack {
+  int n_experts;
+  const float* p[MRNB_P_COUNT]; /* fp32 parameters (always required) */
+  const void* h[MRNB_P_COUNT];  /* bf16 copies of the GEMM weight slots (*_W of qkv/proj/fc1/fc2/conv/seq); MRNB_PREC_BF16 only */
+  const float* fc_w[MRNB_MAX_EXPERTS];  /* [C_i,256] model.{i}.fc.weight (ragged over experts) */
+  const void* fc_w16[MRNB_MAX_EXPERTS]; /* bf16 copy; MRNB_PREC_BF16 only */
+  const float* fc_b[MRNB_MAX_EXPERTS];  /* [C_i] */
+  int n_class[MRNB_MAX_EXPERTS];
+} MrnbSvtrPack;
+
+size_t mrnb_svtr_workspace_bytes(int n_experts, int B, int chunk, int prec);
+
+/* image [B,4,32,256] fp32 NCHW.  chunk: samples processed together after the patch embedding (0 = all).
+ * bn_batch_stats = 1: nn.BatchNorm2d in .train() (batch statistics; update_running = 1 also applies the momentum
+ * update, reference quirk il_modules/mrn.py:401); 0: running statistics.
+ * drop_scales: NULL or [I,12,2,B] DropPath multipliers (modules/svtr.py:7-22).
+ * features: NULL or [B,I,64,256] fp32 (router input).  logits: host array of I device pointers (NULL entries are
+ * skipped), logits[i] is [B,64,ld_logits[i]] fp32 with the first C_i columns written (model.{i} "predict"). */
+int mrnb_svtr_experts_forward(const MrnbSvtrPack* pack, const float* image, int B, int chunk, int prec,
+                              int bn_batch_stats, int update_running, const float* drop_scales, float* features,
+                              float* const* logits, const long* ld_logits, void* workspace, size_t workspace_bytes,
+                              cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * DM-Router + gate head.   Replaces modules/dm_router.py:50-67 (DM_Router.forward, both gating blocks) and
+ * modules/model.py:402-406 (train) / :371-377 (eval): rearrange -> channel_route -> route -> softmax / argmax.
+ *
+ * Router parameters live in ONE fp32 arena (also the gradient / Adam / NCCL all-reduce layout); offsets in floats
+ * are returned by mrnb_router_param_offsets in nn.Module.parameters() order (modules/model.py:437-452):
+ *   0 route.weight[T] 1 route.bias[1] 2 channel_route.weight[I,I*D] 3 channel_route.bias[I]
+ *   4 norm.weight[D] 5 norm.bias[D] 6 proj_1.weight[2D,D] 7 proj_1.bias[2D]
+ *   8 spatial_gating.norm.weight[D] 9 .bias[D] 10 spatial_gating.proj.weight[IT,IT] 11 .bias[IT]
+ *   12 channel_gating.norm.weight[T] 13 .bias[T] 14 channel_gating.proj.weight[ID,ID] 15 .bias[ID]
+ *   16 proj_2.weight[D,D] 17 proj_2.bias[D] 18 proj_3.weight[D,D] 19 proj_3.bias[D]
+ */
+#define MRNB_ROUTER_NPARAMS 20
+long mrnb_router_param_offsets(int n_experts, int T, int D, long* offsets /* host, [MRNB_ROUTER_NPARAMS+1] */);
+size_t mrnb_router_workspace_bytes(int B, int n_experts, int T, int D, int with_backward);
+
+/* x [B,I,T,D] fp32 -> out [B,I,T,D], scores r [B,I] (pre-softmax), gate = softmax(r) [B,I], index = argmax_j r (first max).
+ * The workspace keeps the activations the backward needs. */
+int mrnb_router_forward(const float* params, const float* x, int B, int n_experts, int T, int D, int prec,
+                        float* out, float* scores, float* gate, int* index, void* workspace, size_t workspace_bytes,
+                        cudaStream_t stream);
+
+/* Backward of the stage-1 objective w.r.t. every router parameter (il_modules/mrn.py:342,360,362):
+ *   loss = pi * CTC + CrossEntropy(gate, domain)   -- CE applied to the already softmaxed gate (reference quirk).
+ * dgate_ctc [B,I] is d(pi*CTC)/dgate from mrnb_ctc_lattice; domain [B] int64.  Writes grads (same arena layout,
+ * overwritten) and taski_loss (scalar, the CE term).  Must follow mrnb_router_forward with the same workspace. */
+int mrnb_router_backward(const float* params, const float* x, const float* gate, const float* dgate_ctc,
+                         const long long* domain, int B, int n_experts, int T, int D, int prec, float* grads,
+                         float* taski_loss, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* DM_Router alone with an explicit upstream gradient (tests): d_out [B,I,T,D] -> grads of the dm_router.0.*
+ * slots (4..19) and, if dx != NULL, the input gradient. */
+int mrnb_dm_router_backward(const float* params, const float* x, const float* d_out, int B, int n_experts, int T, int D,
+                            int prec, float* grads, float* dx, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Gated combine + log-softmax + CTC + greedy decode.
+ * Replaces modules/model.py:361-364,410-423 (pad with ONES, stack, gate-mul, sum), :383-393 (hard route = one-hot gate),
+ *          il_modules/mrn.py:251-252,345-346 + il_modules/base.py:131 (log_softmax + CTCLoss(mean, zero_infinity)),
+ *          test.py:211-221,257 + tools/utils.py:62-76 (argmax, collapse, confidence).
+ *
+ * mrnb_gate_combine: z[i] [B,T,ld[i]] (first Ci[i] columns valid; z, ld, Ci are HOST arrays), gate [B,I].
+ *   Always writes lse [B,T].  Optional outputs (NULL to skip): logits [B,T,ldo] (the combined union-charset
+ *   logits), E [B,T,I] = sum_c softmax(logits)[c] * pad_i[c], amax [B,T] (first maximal class), maxprob [B,T],
+ *   lpe [B,T,Lmax+1] log-probs of blank + each target label, zlab [B,T,Lmax+1,I] per-expert values at those columns.
+ *   targets [B,Lmax] int64 padded with 1, tlen [B] int32 (tools/utils.py:45-60). */
+int mrnb_gate_combine(const float* const* z, const long* ld, const int* Ci, int n_experts, const float* gate, int B,
+                      int T, float* logits, long ldo, float* lse, float* E, int* amax, float* maxprob,
+                      const long long* targets, const int* tlen, int Lmax, float* lpe, float* zlab, cudaStream_t stream);
+
+/* CTC alpha-beta over all T frames, blank 0.  nll [B] (0 where infeasible: zero_infinity), loss_mean = mean_b(nll_b /
+ * max(len_b,1)).  Optional: dgate [B,I] = grad_scale/max(len,1) * sum_t(E_i - sum_s occ_s * zlab_i[ext_s])  (pass
+ * grad_scale = pi / B), occ_col [B,T,Lmax+1] posterior mass per label column (for mrnb_ctc_dense_grad). */
+int mrnb_ctc_lattice(const float* lpe, const float* zlab, const float* E, const long long* targets, const int* tlen,
+                     int Lmax, int B, int T, int n_experts, float grad_scale, float* nll, float* loss_mean, float* dgate,
+                     float* occ_col, cudaStream_t stream);
+
+/* Dense gradient of the mean CTC loss w.r.t. logits [B,T,C] (expert-training stage, il_modules/mrn.py:251-260). */
+int mrnb_ctc_dense_grad(const float* logits, long ldl, const float* lse, const float* occ_col, const float* nll,
+                        const long long* targets, const int* tlen, int Lmax, int B, int T, int C, float grad_scale,
+                        float* grad, long ldg, cudaStream_t stream);
+
+/* ids [B,T] compacted (collapse repeats, drop blank 0; -1 padded), len [B], conf [B] = prod_t maxprob[b,t]. */
+int mrnb_greedy_decode(const int* amax, const float* maxprob, int B, int T, int* out_ids, int* out_len, float* conf,
+                       cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * clip_grad_norm_(5) + Adam on a flat arena.  Replaces il_modules/mrn.py:364-367 (torch foreach kernels).
+ * state: exp_avg, exp_avg_sq [n]; norm_out: device scalar receiving the pre-clip L2 norm.  step is 1-based. */
+int mrnb_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n, float lr, float beta1,
+                   float beta2, float eps, float max_norm, int step, float* norm_out, void* workspace /* >= 4 KiB */,
+                   cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Building blocks (used by the entry points above; exported for the parity tests). */
+int mrnb_linear_f32(const float* A, const float* W, const float* bias, const float* residual, float* out, int M, int N,
+                    int K, int act_gelu, cudaStream_t stream);
+/* tcgen05 / TMEM / TMA GEMM: A [M,K] bf16, W [N,K] bf16, out fp32 or bf16 [M,N]; K % 64 == 0. */
+int mrnb_linear_bf16(const void* A, const void* W, const float* bias, const float* residual, void* out, int out_is_f32,
+                     int M, int N, int K, int act_gelu, cudaStream_t stream);
+int mrnb_layernorm_f32(const float* x, float* y, const float* gamma, const float* beta, long rows, int D, float eps,
+                       cudaStream_t stream);
+int mrnb_svtr_attention_f32(const float* qkv, float* out, int groups, int N, int d, int heads, int H, int W, int local,
+                            cudaStream_t stream);
+int mrnb_cast_f32_to_bf16(const float* x, void* y, long n, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRN_B200_H */

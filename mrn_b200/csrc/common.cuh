@@ -1,0 +1,85 @@
+// Shared device/host helpers for the mrn_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#define MRNB_OK 0
+#define MRNB_ERR_ARG (-1)
+#define MRNB_ERR_WORKSPACE (-2)
+#define MRNB_ERR_LAUNCH (-3)
+#define MRNB_ERR_UNSUPPORTED (-4)
+
+#define MRNB_MAX_EXPERTS 8
+
+void mrnb_set_error(const char* fmt, ...);
+extern "C" void mrnb_count_launch(int n);   // launch counter (bench.py's gpu_launches)
+
+#define MRNB_CHECK_ARG(cond, ...)                        \
+  do {                                                   \
+    if (!(cond)) {                                       \
+      mrnb_set_error(__VA_ARGS__);                       \
+      return MRNB_ERR_ARG;                               \
+    }                                                    \
+  } while (0)
+
+#define MRNB_CHECK_LAUNCH(name)                                               \
+  do {                                                                        \
+    cudaError_t e__ = cudaGetLastError();                                     \
+    mrnb_count_launch(1);                                                     \
+    if (e__ != cudaSuccess) {                                                 \
+      mrnb_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+      return MRNB_ERR_LAUNCH;                                                 \
+    }                                                                         \
+  } while (0)
+
+#define MRNB_TRY(expr)            \
+  do {                            \
+    int rc__ = (expr);            \
+    if (rc__ != MRNB_OK) return rc__; \
+  } while (0)
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf(float x) {
+  // nn.GELU() exact form: 0.5 x (1 + erf(x / sqrt(2)))
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// log(exp(a)+exp(b)) with -inf handling
+__device__ __forceinline__ float log_add(float a, float b) {
+  const float m = fmaxf(a, b);
+  if (m == -INFINITY) return -INFINITY;
+  return m + log1pf(expf(-fabsf(a - b)));
+}

@@ -1,0 +1,618 @@
+// DM-Router + gate head: forward and the full parameter backward of the router-training stage.
+//
+// Reference (paths relative to /root/reference):
+//   modules/dm_router.py:50-67   DM_Router.forward          :11-17 SpatialDomainGating   :26-33 ChannelDomainGating
+//   modules/model.py:402-406     gate head (rearrange -> channel_route -> route -> softmax), :371-377 eval argmax
+//   il_modules/mrn.py:342,360    taski_loss = CrossEntropy(gate, domain); loss = 15*CTC + taski_loss
+//
+// Math, x in [B,I,T,D], rows m = (b,i,t), token n = i*T+t, channel k = i*D+c:
+//   xn = LN_D(x); a1 = xn W1^T + b1; [u|v] = GELU(a1); vn = LN_D(v)
+//   v2[b,n,:] = sum_m Ws[n,m] vn[b,m,:] + bs[n];  g1 = u*v2;  y = g1 W2^T + b2 + x
+//   gn[b,k,:] = LN_T(y[b,k,:]);  g2[b,k,t] = sum_j Wc[k,j] gn[b,j,t] + bc[k];  y2 = y*g2;  out = y2 W3^T + b3 + x
+//   s[b,t,j] = sum_k out[b,k,t] Wcr[j,k] + bcr[j];  r[b,j] = sum_t wr[t] s[b,t,j] + br;  gate = softmax(r)
+// Every rearrange/permute of the reference is a two-level stride of the GEMM descriptors (no copies).
+// v1 engine: fp32 CUDA-core GEMM (gemm_f32.cu) for both precisions -- gate weights are an fp32 quantity
+// (1e-4 tolerance); the tensor-core port of these contractions is tracked in DESIGN.md.
+#include "common.cuh"
+#include "gemm_f32.h"
+#include "../../include/mrn_b200.h"
+
+namespace {
+
+constexpr int RD = 256;   // router channel width (opt.hidden_size)
+
+enum { R_ROUTE_W, R_ROUTE_B, R_CR_W, R_CR_B, R_N_W, R_N_B, R_P1_W, R_P1_B, R_SN_W, R_SN_B, R_SP_W, R_SP_B,
+       R_CN_W, R_CN_B, R_CP_W, R_CP_B, R_P2_W, R_P2_B, R_P3_W, R_P3_B };
+
+long router_offsets(int I, int T, int D, long* off) {
+  const long sz[MRNB_ROUTER_NPARAMS] = {T, 1, (long)I * I * D, I, D, D, 2L * D * D, 2L * D, D, D,
+                                        (long)I * T * I * T, (long)I * T, T, T, (long)I * D * I * D, (long)I * D,
+                                        (long)D * D, D, (long)D * D, D};
+  long o = 0;
+  for (int k = 0; k < MRNB_ROUTER_NPARAMS; ++k) { off[k] = o; o += sz[k]; }
+  off[MRNB_ROUTER_NPARAMS] = o;
+  return o;
+}
+
+// ---- row LayerNorm over D=256 with saved statistics (warp per row) ------------------------------
+__global__ void __launch_bounds__(256)
+ln_rows_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float* __restrict__ y, float* __restrict__ stats, long rows, float eps) {
+  const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float v[8];
+  const float* xr = x + row * RD;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const float4 t = *reinterpret_cast<const float4*>(xr + c * 128 + lane * 4);
+    v[c * 4] = t.x; v[c * 4 + 1] = t.y; v[c * 4 + 2] = t.z; v[c * 4 + 3] = t.w;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += v[j];
+  const float mean = warp_sum(s) * (1.0f / RD);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / RD) + eps);
+  if (lane == 0) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int idx = (j / 4) * 128 + lane * 4 + (j % 4);
+    y[row * RD + idx] = (v[j] - mean) * rstd * gamma[idx] + beta[idx];
+  }
+}
+
+// a1 [rows, 2D] -> u = GELU(a1[:, :D]) ; vn = LN_D(GELU(a1[:, D:])) + stats
+__global__ void __launch_bounds__(256)
+gelu_ln_fwd_kernel(const float* __restrict__ a1, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float* __restrict__ u, float* __restrict__ vn, float* __restrict__ stats, long rows, float eps) {
+  const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* ar = a1 + row * 2 * RD;
+  float v[8];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const float4 tu = *reinterpret_cast<const float4*>(ar + c * 128 + lane * 4);
+    *reinterpret_cast<float4*>(u + row * RD + c * 128 + lane * 4) =
+        make_float4(gelu_erf(tu.x), gelu_erf(tu.y), gelu_erf(tu.z), gelu_erf(tu.w));
+    const float4 tv = *reinterpret_cast<const float4*>(ar + RD + c * 128 + lane * 4);
+    v[c * 4] = gelu_erf(tv.x); v[c * 4 + 1] = gelu_erf(tv.y); v[c * 4 + 2] = gelu_erf(tv.z); v[c * 4 + 3] = gelu_erf(tv.w);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += v[j];
+  const float mean = warp_sum(s) * (1.0f / RD);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / RD) + eps);
+  if (lane == 0) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int idx = (j / 4) * 128 + lane * 4 + (j % 4);
+    vn[row * RD + idx] = (v[j] - mean) * rstd * gamma[idx] + beta[idx];
+  }
+}
+
+__global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ c, long n4) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i];
+  reinterpret_cast<float4*>(c)[i] = make_float4(x.x * y.x, x.y * y.y, x.z * y.z, x.w * y.w);
+}
+// c = a*b ; d = a*e      (shared first factor)
+__global__ void mul2_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ e,
+                            float* __restrict__ c, float* __restrict__ d, long n4) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i],
+               z = reinterpret_cast<const float4*>(e)[i];
+  reinterpret_cast<float4*>(c)[i] = make_float4(x.x * y.x, x.y * y.y, x.z * y.z, x.w * y.w);
+  reinterpret_cast<float4*>(d)[i] = make_float4(x.x * z.x, x.y * z.y, x.z * z.z, x.w * z.w);
+}
+
+// LayerNorm over the patch axis T for every (b,i,c): block per (b,i), thread per c (ChannelDomainGating.norm)
+__global__ void __launch_bounds__(RD)
+lnT_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma /*[T]*/, const float* __restrict__ beta,
+               float* __restrict__ gn, float* __restrict__ stats /*[B*I, D, 2]*/, int T, float eps) {
+  const long bi = blockIdx.x;
+  const int c = threadIdx.x;
+  const float* yp = y + bi * T * RD + c;
+  float s = 0.f;
+  for (int t = 0; t < T; ++t) s += yp[(long)t * RD];
+  const float mean = s / T;
+  float q = 0.f;
+  for (int t = 0; t < T; ++t) { const float d = yp[(long)t * RD] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(q / T + eps);
+  stats[(bi * RD + c) * 2] = mean; stats[(bi * RD + c) * 2 + 1] = rstd;
+  float* gp = gn + bi * T * RD + c;
+  for (int t = 0; t < T; ++t) gp[(long)t * RD] = (yp[(long)t * RD] - mean) * rstd * gamma[t] + beta[t];
+}
+
+// backward of lnT: dy += rstd*(dxh - mean(dxh) - xh*mean(dxh*xh)), dgamma[t] += sum dgn*xh, dbeta[t] += sum dgn
+__global__ void __launch_bounds__(RD)
+lnT_bwd_kernel(const float* __restrict__ y, const float* __restrict__ stats, const float* __restrict__ gamma,
+               const float* __restrict__ dgn, float* __restrict__ dy /* accumulated */, float* __restrict__ dgamma,
+               float* __restrict__ dbeta, int T) {
+  extern __shared__ float sh[];        // [T][2] block partials
+  const long bi = blockIdx.x;
+  const int c = threadIdx.x, lane = c & 31;
+  for (int k = c; k < 2 * T; k += RD) sh[k] = 0.f;
+  __syncthreads();
+  const float mean = stats[(bi * RD + c) * 2], rstd = stats[(bi * RD + c) * 2 + 1];
+  const float* yp = y + bi * T * RD + c;
+  const float* dp = dgn + bi * T * RD + c;
+  float m1 = 0.f, m2 = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float xh = (yp[(long)t * RD] - mean) * rstd, d = dp[(long)t * RD];
+    const float dxh = d * gamma[t];
+    m1 += dxh; m2 = fmaf(dxh, xh, m2);
+    const float a = warp_sum(d * xh), b2 = warp_sum(d);
+    if (lane == 0) { atomicAdd(&sh[t * 2], a); atomicAdd(&sh[t * 2 + 1], b2); }
+  }
+  m1 /= T; m2 /= T;
+  float* op = dy + bi * T * RD + c;
+  for (int t = 0; t < T; ++t) {
+    const float xh = (yp[(long)t * RD] - mean) * rstd;
+    const float dxh = dp[(long)t * RD] * gamma[t];
+    op[(long)t * RD] += rstd * (dxh - m1 - xh * m2);
+  }
+  __syncthreads();
+  for (int k = c; k < T; k += RD) { atomicAdd(dgamma + k, sh[k * 2]); atomicAdd(dbeta + k, sh[k * 2 + 1]); }
+}
+
+// Row-LN backward (D=256, warp per row).  xin is the LN input (or its pre-GELU activation when GELU_IN):
+//   dxin = LNbwd(dyn) [* GELU'(pre)]  (+ add1 + add2);  dgamma/dbeta accumulated with block partials + atomics.
+template <bool GELU_IN>
+__global__ void __launch_bounds__(256)
+ln_rows_bwd_kernel(const float* __restrict__ xin, long ldx, const float* __restrict__ stats,
+                   const float* __restrict__ gamma, const float* __restrict__ dyn, float* __restrict__ dxin, long lddx,
+                   const float* __restrict__ add1, const float* __restrict__ add2, float* __restrict__ dgamma,
+                   float* __restrict__ dbeta, long rows) {
+  __shared__ float sg[RD], sb[RD];
+  for (int k = threadIdx.x; k < RD; k += 256) { sg[k] = 0.f; sb[k] = 0.f; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float ag[8], ab[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { ag[j] = 0.f; ab[j] = 0.f; }
+  for (long row = (long)blockIdx.x * 8 + w; row < rows; row += (long)gridDim.x * 8) {
+    const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
+    float xh[8], dxh[8], pre[8];
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = (j / 4) * 128 + lane * 4 + (j % 4);
+      pre[j] = xin[row * ldx + idx];
+      const float xv = GELU_IN ? gelu_erf(pre[j]) : pre[j];
+      xh[j] = (xv - mean) * rstd;
+      const float d = dyn[row * RD + idx];
+      dxh[j] = d * gamma[idx];
+      ag[j] = fmaf(d, xh[j], ag[j]); ab[j] += d;
+      m1 += dxh[j]; m2 = fmaf(dxh[j], xh[j], m2);
+    }
+    m1 = warp_sum(m1) * (1.0f / RD); m2 = warp_sum(m2) * (1.0f / RD);
+    if (dxin) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int idx = (j / 4) * 128 + lane * 4 + (j % 4);
+        float g = rstd * (dxh[j] - m1 - xh[j] * m2);
+        if (GELU_IN) g *= gelu_erf_grad(pre[j]);
+        if (add1) g += add1[row * RD + idx];
+        if (add2) g += add2[row * RD + idx];
+        dxin[row * lddx + idx] = g;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int idx = (j / 4) * 128 + lane * 4 + (j % 4);
+    atomicAdd(&sg[idx], ag[j]); atomicAdd(&sb[idx], ab[j]);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < RD; k += 256) { atomicAdd(dgamma + k, sg[k]); atomicAdd(dbeta + k, sb[k]); }
+}
+
+// da1[:, :D] = du * GELU'(a1[:, :D])
+__global__ void gelu_bwd_kernel(const float* __restrict__ a1, const float* __restrict__ du, float* __restrict__ da1, long rows) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * RD) return;
+  const long row = i / RD; const int c = (int)(i % RD);
+  da1[row * 2 * RD + c] = du[i] * gelu_erf_grad(a1[row * 2 * RD + c]);
+}
+
+// out[n] (+)= sum_m X(m, n) with two-level axes; grid (cdiv(N,32), msplit)
+__global__ void colsum_kernel(const float* __restrict__ X, MrnbAxis am, MrnbAxis an, int M, int N, float* __restrict__ out) {
+  __shared__ float sh[8][33];
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ty = threadIdx.x >> 5;
+  const int per = (M + gridDim.y - 1) / gridDim.y;
+  const int m0 = blockIdx.y * per, m1 = min(M, m0 + per);
+  float s = 0.f;
+  if (n < N) {
+    const long on = (long)(n / an.inner) * an.so + (long)(n % an.inner) * an.si;
+    for (int m = m0 + ty; m < m1; m += 8) s += X[(long)(m / am.inner) * am.so + (long)(m % am.inner) * am.si + on];
+  }
+  sh[ty][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x];
+    atomicAdd(out + n, t);
+  }
+}
+
+// gate head finish: r[b,j] = sum_t wr[t] s[b,t,j] + br ; gate = softmax(r) ; index = first argmax
+__global__ void gate_finish_kernel(const float* __restrict__ s, const float* __restrict__ wr, const float* __restrict__ br,
+                                   int B, int T, int I, float* __restrict__ r, float* __restrict__ gate,
+                                   int* __restrict__ index) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float rr[MRNB_MAX_EXPERTS];
+  float mx = -INFINITY; int am = 0;
+  for (int j = 0; j < I; ++j) {
+    float a = 0.f;
+    for (int t = 0; t < T; ++t) a = fmaf(wr[t], s[((long)b * T + t) * I + j], a);
+    a += br[0];
+    rr[j] = a;
+    if (a > mx) { mx = a; am = j; }
+  }
+  float sum = 0.f;
+  for (int j = 0; j < I; ++j) sum += expf(rr[j] - mx);
+  for (int j = 0; j < I; ++j) {
+    if (r) r[b * I + j] = rr[j];
+    if (gate) gate[b * I + j] = expf(rr[j] - mx) / sum;
+  }
+  if (index) index[b] = am;
+}
+
+// dL/dr from dL/dgate (CTC part) + CrossEntropy(gate, domain) applied to the softmaxed gate; also the CE loss.
+__global__ void gate_bwd_kernel(const float* __restrict__ gate, const float* __restrict__ dgate_ctc,
+                                const long long* __restrict__ domain, int B, int I, float* __restrict__ dr,
+                                float* __restrict__ ce_loss) {
+  __shared__ double sh[8];
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  double lossb = 0.0;
+  if (b < B) {
+    float g[MRNB_MAX_EXPERTS], dg[MRNB_MAX_EXPERTS];
+    float mx = -INFINITY;
+    for (int j = 0; j < I; ++j) { g[j] = gate[b * I + j]; mx = fmaxf(mx, g[j]); }
+    float sum = 0.f;
+    for (int j = 0; j < I; ++j) sum += expf(g[j] - mx);
+    const int dom = (int)domain[b];
+    float dot = 0.f;
+    for (int j = 0; j < I; ++j) {
+      const float sm = expf(g[j] - mx) / sum;
+      dg[j] = (dgate_ctc ? dgate_ctc[b * I + j] : 0.f) + (sm - (j == dom ? 1.f : 0.f)) / (float)B;
+      dot = fmaf(g[j], dg[j], dot);
+    }
+    lossb = -(double)(g[dom] - mx - logf(sum)) / (double)B;
+    for (int j = 0; j < I; ++j) dr[b * I + j] = g[j] * (dg[j] - dot);
+  }
+  lossb = warp_sum_d(lossb);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = lossb;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += sh[k];
+    atomicAdd(ce_loss, (float)t);
+  }
+}
+
+// ds[b,t,j] = dr[b,j]*wr[t];  dwr[t] = sum_{b,j} dr[b,j] s[b,t,j];  dbr = sum dr      (block per t)
+__global__ void route_bwd_kernel(const float* __restrict__ dr, const float* __restrict__ s, const float* __restrict__ wr,
+                                 int B, int T, int I, float* __restrict__ ds, float* __restrict__ dwr, float* __restrict__ dbr) {
+  __shared__ float sh[2][8];
+  const int t = blockIdx.x;
+  float a = 0.f, c = 0.f;
+  const float w = wr[t];
+  for (int k = threadIdx.x; k < B * I; k += blockDim.x) {
+    const int b = k / I, j = k % I;
+    const float d = dr[k];
+    ds[((long)b * T + t) * I + j] = d * w;
+    a = fmaf(d, s[((long)b * T + t) * I + j], a);
+    c += d;
+  }
+  a = warp_sum(a); c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ta = 0.f, tc = 0.f;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { ta += sh[0][k]; tc += sh[1][k]; }
+    dwr[t] = ta;
+    if (t == 0) dbr[0] = tc;
+  }
+}
+
+inline size_t al(size_t v) { return (v + 255) / 256 * 256; }
+
+struct RouterWs {
+  // forward (kept for backward)
+  float *stats1, *xn, *a1, *u, *vn, *stats2, *v2, *g1, *y, *statsT, *gn, *g2, *y2, *out, *s;
+  // backward temporaries
+  float *dr, *ds, *dout, *dy2, *dy, *dg2, *dgn, *dg1, *du, *dv2, *dvn, *da1, *dxn;
+  size_t bytes;
+};
+
+RouterWs carve(char* base, int B, int I, int T, int D, bool bwd) {
+  RouterWs w{};
+  size_t o = 0;
+  const size_t M = (size_t)B * I * T, MD = M * D;
+  auto take = [&](size_t n) { float* p = base ? (float*)(base + o) : nullptr; o = al(o + n * 4); return p; };
+  w.stats1 = take(M * 2); w.xn = take(MD); w.a1 = take(MD * 2); w.u = take(MD); w.vn = take(MD); w.stats2 = take(M * 2);
+  w.v2 = take(MD); w.g1 = take(MD); w.y = take(MD); w.statsT = take((size_t)B * I * D * 2); w.gn = take(MD);
+  w.g2 = take(MD); w.y2 = take(MD); w.out = take(MD); w.s = take((size_t)B * T * I);
+  if (bwd) {
+    w.dr = take((size_t)B * I); w.ds = take((size_t)B * T * I); w.dout = take(MD); w.dy2 = take(MD); w.dy = take(MD);
+    w.dg2 = take(MD); w.dgn = take(MD); w.dg1 = take(MD); w.du = take(MD); w.dv2 = take(MD); w.dvn = take(MD);
+    w.da1 = take(MD * 2); w.dxn = take(MD);
+  }
+  w.bytes = o + 256;
+  return w;
+}
+
+#define LAUNCH_EW(kernel, n, ...)                                      \
+  do {                                                                 \
+    kernel<<<cdiv((n), 256), 256, 0, st>>>(__VA_ARGS__);               \
+    MRNB_CHECK_LAUNCH(#kernel);                                        \
+  } while (0)
+
+int colsum(const float* X, MrnbAxis am, MrnbAxis an, int M, int N, float* out, cudaStream_t st) {
+  int msplit = M / 512; if (msplit < 1) msplit = 1; if (msplit > 64) msplit = 64;
+  colsum_kernel<<<dim3(cdiv(N, 32), msplit), 256, 0, st>>>(X, am, an, M, N, out);
+  MRNB_CHECK_LAUNCH("colsum_kernel");
+  return MRNB_OK;
+}
+
+int router_forward(const float* P, const float* x, int B, int I, int T, int D, float* out_user, float* scores,
+                   float* gate, int* index, RouterWs& w, cudaStream_t st) {
+  long off[MRNB_ROUTER_NPARAMS + 1];
+  router_offsets(I, T, D, off);
+  const long M = (long)B * I * T, IT = (long)I * T, ID = (long)I * D, TD = (long)T * D, ITD = IT * D;
+  float* out = w.out;   // kept in the workspace for the backward; copied to the caller's buffer at the end
+  ln_rows_fwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(x, P + off[R_N_W], P + off[R_N_B], w.xn, w.stats1, M, 1e-5f);
+  MRNB_CHECK_LAUNCH("ln_rows_fwd_kernel");
+  {  // a1 = xn W1^T + b1
+    MrnbGemm g = mrnb_gemm_nt(w.xn, D, P + off[R_P1_W], D, w.a1, 2 * D, (int)M, 2 * D, D);
+    g.bias_n = P + off[R_P1_B];
+    MRNB_TRY(mrnb_sgemm(g, st));
+  }
+  gelu_ln_fwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(w.a1, P + off[R_SN_W], P + off[R_SN_B], w.u, w.vn, w.stats2, M, 1e-5f);
+  MRNB_CHECK_LAUNCH("gelu_ln_fwd_kernel");
+  {  // v2[b] = Ws . vn[b] + bs  (token mixing over n = i*T+t)
+    MrnbGemm g{};
+    g.A = P + off[R_SP_W]; g.am = mrnb_axis(IT); g.ak = mrnb_axis(1); g.a_kfast = 1; g.sAb = 0;
+    g.B = w.vn; g.bk = mrnb_axis(D); g.bn = mrnb_axis(1); g.b_kfast = 0; g.sBb = ITD;
+    g.C = w.v2; g.cm = mrnb_axis(D); g.cn = mrnb_axis(1); g.sCb = ITD;
+    g.M = (int)IT; g.N = D; g.K = (int)IT; g.batch = B; g.splitk = 1; g.alpha = 1.f; g.rows_per_scale = 1;
+    g.bias_m = P + off[R_SP_B];
+    MRNB_TRY(mrnb_sgemm(g, st));
+  }
+  LAUNCH_EW(mul_kernel, M * D / 4, w.u, w.v2, w.g1, M * D / 4);
+  {  // y = g1 W2^T + b2 + x
+    MrnbGemm g = mrnb_gemm_nt(w.g1, D, P + off[R_P2_W], D, w.y, D, (int)M, D, D);
+    g.bias_n = P + off[R_P2_B]; g.res = x;
+    MRNB_TRY(mrnb_sgemm(g, st));
+  }
+  lnT_fwd_kernel<<<B * I, RD, 0, st>>>(w.y, P + off[R_CN_W], P + off[R_CN_B], w.gn, w.statsT, T, 1e-5f);
+  MRNB_CHECK_LAUNCH("lnT_fwd_kernel");
+  {  // g2[(b,t),(i,c)] = sum_(i',c') gn[(b,t),(i',c')] Wc[(i,c),(i',c')] + bc   (channel mixing over k = i*D+c)
+    MrnbGemm g{};
+    g.A = w.gn; g.am = mrnb_axis2(T, D, ITD); g.ak = mrnb_axis2(D, 1, TD); g.a_kfast = 1;
+    g.B = P + off[R_CP_W]; g.bn = mrnb_axis(ID); g.bk = mrnb_axis(1); g.b_kfast = 1;
+    g.C = w.g2; g.cm = mrnb_axis2(T, D, ITD); g.cn = mrnb_axis2(D, 1, TD);
+    g.M = B * T; g.N = (int)ID; g.K = (int)ID; g.batch = 1; g.splitk = 1; g.alpha = 1.f; g.rows_per_scale = 1;
+    g.bias_n = P + off[R_CP_B];
+    MRNB_TRY(mrnb_sgemm(g, st));
+  }
+  LAUNCH_EW(mul_kernel, M * D / 4, w.y, w.g2, w.y2, M * D / 4);
+  {  // out = y2 W3^T + b3 + x
+    MrnbGemm g = mrnb_gemm_nt(w.y2, D, P + off[R_P3_W], D, out, D, (int)M, D, D);
+    g.bias_n = P + off[R_P3_B]; g.res = x;
+    MRNB_TRY(mrnb_sgemm(g, st));
+  }
+  if (scores || gate || index) {
+    MrnbGemm g{};   // s[(b,t), j] = sum_(i,c) out[b,i,t,c] Wcr[j,(i,c)] + bcr[j]
+    g.A = out; g.am = mrnb_axis2(T, D, ITD); g.ak = mrnb_axis2(D, 1, TD); g.a_kfast = 1;
+    g.B = P + off[R_CR_W]; g.bn = mrnb_axis(ID); g.bk = mrnb_axis(1); g.b_kfast = 1;
+    g.C = w.s; g.cm = mrnb_axis(I); g.cn = mrnb_axis(1);
+    g.M = B * T; g.N = I; g.K = (int)ID; g.batch = 1; g.splitk = 1; g.alpha = 1.f; g.rows_per_scale = 1;
+    g.bias_n = P + off[R_CR_B];
+    MRNB_TRY(mrnb_sgemm(g, st));
+    gate_finish_kernel<<<cdiv(B, 128), 128, 0, st>>>(w.s, P + off[R_ROUTE_W], P + off[R_ROUTE_B], B, T, I, scores, gate, index);
+    MRNB_CHECK_LAUNCH("gate_finish_kernel");
+  }
+  if (out_user) cudaMemcpyAsync(out_user, out, (size_t)M * D * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  return MRNB_OK;
+}
+
+// Backward through DM_Router given d_out (in w.dout).  G = gradient arena (already zeroed).
+int dm_router_backward_core(const float* P, const float* x, const float* out_fwd, int B, int I, int T, int D, float* G,
+                            float* dx, RouterWs& w, cudaStream_t st) {
+  long off[MRNB_ROUTER_NPARAMS + 1];
+  router_offsets(I, T, D, off);
+  (void)out_fwd;
+  const long M = (long)B * I * T, IT = (long)I * T, ID = (long)I * D, TD = (long)T * D, ITD = IT * D;
+  const long n4 = M * D / 4;
+  auto dW_rows = [&](const float* dY, long ldy, int Nout, const float* Xin, long ldx, int Nin, float* dW) {
+    // dW[o,i] = sum_rows dY[row,o] * Xin[row,i]
+    MrnbGemm g{};
+    g.A = dY; g.am = mrnb_axis(1); g.ak = mrnb_axis(ldy); g.a_kfast = 0;
+    g.B = Xin; g.bk = mrnb_axis(ldx); g.bn = mrnb_axis(1); g.b_kfast = 0;
+    g.C = dW; g.cm = mrnb_axis(Nin); g.cn = mrnb_axis(1);
+    g.M = Nout; g.N = Nin; g.K = (int)M; g.batch = 1; g.alpha = 1.f; g.rows_per_scale = 1;
+    g.splitk = (int)((M + 2047) / 2048); if (g.splitk > 64) g.splitk = 64; if (g.splitk < 1) g.splitk = 1;
+    return mrnb_sgemm(g, st);
+  };
+  auto dX_rows = [&](const float* dY, long ldy, int Nout, const float* Wt, int Nin, float* dX, long lddx) {
+    // dX[row,i] = sum_o dY[row,o] * W[o,i]
+    MrnbGemm g{};
+    g.A = dY; g.am = mrnb_axis(ldy); g.ak = mrnb_axis(1); g.a_kfast = 1;
+    g.B = Wt; g.bk = mrnb_axis(Nin); g.bn = mrnb_axis(1); g.b_kfast = 0;
+    g.C = dX; g.cm = mrnb_axis(lddx); g.cn = mrnb_axis(1);
+    g.M = (int)M; g.N = Nin; g.K = Nout; g.batch = 1; g.splitk = 1; g.alpha = 1.f; g.rows_per_scale = 1;
+    return mrnb_sgemm(g, st);
+  };
+  // out = y2 W3^T + b3 + x
+  MRNB_TRY(dX_rows(w.dout, D, D, P + off[R_P3_W], D, w.dy2, D));
+  MRNB_TRY(dW_rows(w.dout, D, D, w.y2, D, D, G + off[R_P3_W]));
+  MRNB_TRY(colsum(w.dout, mrnb_axis(D), mrnb_axis(1), (int)M, D, G + off[R_P3_B], st));
+  // y2 = y * g2 : dy = dy2*g2 ; dg2 = dy2*y
+  LAUNCH_EW(mul2_kernel, n4, w.dy2, w.g2, w.y, w.dy, w.dg2, n4);
+  {  // dgn[(b,t), j] = sum_k dg2[(b,t),k] Wc[k,j]
+    MrnbGemm g{};
+    g.A = w.dg2; g.am = mrnb_axis2(T, D, ITD); g.ak = mrnb_axis2(D, 1, TD); g.a_kfast = 1;
+    g.B = P + off[R_CP_W]; g.bk = mrnb_axis(ID); g.bn = mrnb_axis(1); g.b_kfast = 0;
+    g.C = w.dgn; g.cm = mrnb_axis2(T, D, ITD); g.cn = mrnb_axis2(D, 1, TD);
+    g.M = B * T; g.N = (int)ID; g.K = (int)ID; g.batch = 1; g.splitk = 1; g.alpha = 1.f; g.rows_per_scale = 1;
+    MRNB_TRY(mrnb_sgemm(g, st));
+  }
+  {  // dWc[k,j] = sum_(b,t) dg2[(b,t),k] gn[(b,t),j]
+    MrnbGemm g{};
+    g.A = w.dg2; g.am = mrnb_axis2(D, 1, TD); g.ak = mrnb_axis2(T, D, ITD); g.a_kfast = 0;
+    g.B = w.gn; g.bk = mrnb_axis2(T, D, ITD); g.bn = mrnb_axis2(D, 1, TD); g.b_kfast = 0;
+    g.C = G + off[R_CP_W]; g.cm = mrnb_axis(ID); g.cn = mrnb_axis(1);
+    g.M = (int)ID; g.N = (int)ID; g.K = B * T; g.batch = 1; g.alpha = 1.f; g.rows_per_scale = 1;
+    const int tiles = cdiv(ID, 128) * cdiv(ID, 128);
+    g.splitk = tiles >= 120 ? 1 : (tiles >= 30 ? 4 : 16);
+    if ((long)B * T < 64L * g.splitk) g.splitk = 1;
+    MRNB_TRY(mrnb_sgemm(g, st));
+  }
+  MRNB_TRY(colsum(w.dg2, mrnb_axis2(T, D, ITD), mrnb_axis2(D, 1, TD), B * T, (int)ID, G + off[R_CP_B], st));
+  // gn = LN_T(y)
+  lnT_bwd_kernel<<<B * I, RD, 2 * T * sizeof(float), st>>>(w.y, w.statsT, P + off[R_CN_W], w.dgn, w.dy, G + off[R_CN_W],
+                                                            G + off[R_CN_B], T);
+  MRNB_CHECK_LAUNCH("lnT_bwd_kernel");
+  // y = g1 W2^T + b2 + x
+  MRNB_TRY(dX_rows(w.dy, D, D, P + off[R_P2_W], D, w.dg1, D));
+  MRNB_TRY(dW_rows(w.dy, D, D, w.g1, D, D, G + off[R_P2_W]));
+  MRNB_TRY(colsum(w.dy, mrnb_axis(D), mrnb_axis(1), (int)M, D, G + off[R_P2_B], st));
+  // g1 = u * v2 : du = dg1*v2 ; dv2 = dg1*u
+  LAUNCH_EW(mul2_kernel, n4, w.dg1, w.v2, w.u, w.du, w.dv2, n4);
+  {  // dvn[b,m,:] = sum_n Ws[n,m] dv2[b,n,:]
+    MrnbGemm g{};
+    g.A = P + off[R_SP_W]; g.am = mrnb_axis(1); g.ak = mrnb_axis(IT); g.a_kfast = 0; g.sAb = 0;
+    g.B = w.dv2; g.bk = mrnb_axis(D); g.bn = mrnb_axis(1); g.b_kfast = 0; g.sBb = ITD;
+    g.C = w.dvn; g.cm = mrnb_axis(D); g.cn = mrnb_axis(1); g.sCb = ITD;
+    g.M = (int)IT; g.N = D; g.K = (int)IT; g.batch = B; g.splitk = 1; g.alpha = 1.f; g.rows_per_scale = 1;
+    MRNB_TRY(mrnb_sgemm(g, st));
+  }
+  {  // dWs[n,m] = sum_(b,c) dv2[b,n,c] vn[b,m,c]
+    MrnbGemm g{};
+    g.A = w.dv2; g.am = mrnb_axis(D); g.ak = mrnb_axis2(D, 1, ITD); g.a_kfast = 1;
+    g.B = w.vn; g.bn = mrnb_axis(D); g.bk = mrnb_axis2(D, 1, ITD); g.b_kfast = 1;
+    g.C = G + off[R_SP_W]; g.cm = mrnb_axis(IT); g.cn = mrnb_axis(1);
+    g.M = (int)IT; g.N = (int)IT; g.K = B * D; g.batch = 1; g.alpha = 1.f; g.rows_per_scale = 1;
+    g.splitk = (B * D + 2047) / 2048; if (g.splitk > 32) g.splitk = 32; if (g.splitk < 1) g.splitk = 1;
+    MRNB_TRY(mrnb_sgemm(g, st));
+  }
+  // dbs[n] = sum_(b,c) dv2[b,n,c]
+  MRNB_TRY(colsum(w.dv2, mrnb_axis2(D, 1, ITD), mrnb_axis(D), B * D, (int)IT, G + off[R_SP_B], st));
+  // vn = LN_D(GELU(a1v)); u = GELU(a1u)
+  {
+    const int grid = (int)((M + 8 * 16 - 1) / (8 * 16));
+    ln_rows_bwd_kernel<true><<<grid > 0 ? grid : 1, 256, 0, st>>>(w.a1 + D, 2 * D, w.stats2, P + off[R_SN_W], w.dvn,
+                                                                    w.da1 + D, 2 * D, nullptr, nullptr, G + off[R_SN_W],
+                                                                    G + off[R_SN_B], M);
+    MRNB_CHECK_LAUNCH("ln_rows_bwd_kernel");
+  }
+  LAUNCH_EW(gelu_bwd_kernel, M * D, w.a1, w.du, w.da1, M);
+  // a1 = xn W1^T + b1
+  MRNB_TRY(dW_rows(w.da1, 2 * D, 2 * D, w.xn, D, D, G + off[R_P1_W]));
+  MRNB_TRY(colsum(w.da1, mrnb_axis(2 * D), mrnb_axis(1), (int)M, 2 * D, G + off[R_P1_B], st));
+  MRNB_TRY(dX_rows(w.da1, 2 * D, 2 * D, P + off[R_P1_W], D, w.dxn, D));
+  {  // xn = LN_D(x): dgamma/dbeta (+ dx = LNbwd + dy + dout when requested)
+    const int grid = (int)((M + 8 * 16 - 1) / (8 * 16));
+    ln_rows_bwd_kernel<false><<<grid > 0 ? grid : 1, 256, 0, st>>>(x, D, w.stats1, P + off[R_N_W], w.dxn, dx, D,
+                                                                     dx ? w.dy : nullptr, dx ? w.dout : nullptr,
+                                                                     G + off[R_N_W], G + off[R_N_B], M);
+    MRNB_CHECK_LAUNCH("ln_rows_bwd_kernel");
+  }
+  return MRNB_OK;
+}
+
+}  // namespace
+
+extern "C" long mrnb_router_param_offsets(int n_experts, int T, int D, long* offsets) {
+  long tmp[MRNB_ROUTER_NPARAMS + 1];
+  const long n = router_offsets(n_experts, T, D, tmp);
+  if (offsets) for (int k = 0; k <= MRNB_ROUTER_NPARAMS; ++k) offsets[k] = tmp[k];
+  return n;
+}
+
+extern "C" size_t mrnb_router_workspace_bytes(int B, int n_experts, int T, int D, int with_backward) {
+  return carve(nullptr, B, n_experts, T, D, with_backward != 0).bytes;
+}
+
+#define ROUTER_ARGCHECK(name)                                                                                   \
+  MRNB_CHECK_ARG(params && x && workspace && B > 0 && T > 0, name ": null/empty argument");                      \
+  MRNB_CHECK_ARG(n_experts >= 1 && n_experts <= MRNB_MAX_EXPERTS, name ": n_experts %d out of range", n_experts); \
+  MRNB_CHECK_ARG(D == RD, name ": only D == 256 (opt.hidden_size) is supported, got %d", D);                     \
+  MRNB_CHECK_ARG(prec == MRNB_PREC_FP32 || prec == MRNB_PREC_BF16, name ": unknown precision %d", prec);
+
+extern "C" int mrnb_router_forward(const float* params, const float* x, int B, int n_experts, int T, int D, int prec,
+                                   float* out, float* scores, float* gate, int* index, void* workspace,
+                                   size_t workspace_bytes, cudaStream_t stream) {
+  ROUTER_ARGCHECK("router_forward");
+  RouterWs w = carve((char*)workspace, B, n_experts, T, D, false);
+  MRNB_CHECK_ARG(workspace_bytes >= w.bytes, "router_forward: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+  return router_forward(params, x, B, n_experts, T, D, out, scores, gate, index, w, stream);
+}
+
+extern "C" int mrnb_router_backward(const float* params, const float* x, const float* gate, const float* dgate_ctc,
+                                    const long long* domain, int B, int n_experts, int T, int D, int prec, float* grads,
+                                    float* taski_loss, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  ROUTER_ARGCHECK("router_backward");
+  MRNB_CHECK_ARG(gate && domain && grads && taski_loss, "router_backward: null argument");
+  RouterWs w = carve((char*)workspace, B, n_experts, T, D, true);
+  MRNB_CHECK_ARG(workspace_bytes >= w.bytes, "router_backward: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+  const int I = n_experts;
+  cudaStream_t st = stream;
+  long off[MRNB_ROUTER_NPARAMS + 1];
+  const long nparam = router_offsets(I, T, D, off);
+  const long ID = (long)I * D, TD = (long)T * D, ITD = (long)I * T * D;
+  cudaMemsetAsync(grads, 0, nparam * sizeof(float), st);
+  cudaMemsetAsync(taski_loss, 0, sizeof(float), st);
+  gate_bwd_kernel<<<cdiv(B, 256), 256, 0, st>>>(gate, dgate_ctc, domain, B, I, w.dr, taski_loss);
+  MRNB_CHECK_LAUNCH("gate_bwd_kernel");
+  route_bwd_kernel<<<T, 256, 0, st>>>(w.dr, w.s, params + off[R_ROUTE_W], B, T, I, w.ds, grads + off[R_ROUTE_W],
+                                      grads + off[R_ROUTE_B]);
+  MRNB_CHECK_LAUNCH("route_bwd_kernel");
+  {  // dWcr[j,(i,c)] = sum_(b,t) ds[(b,t),j] out[b,i,t,c]
+    MrnbGemm g{};
+    g.A = w.ds; g.am = mrnb_axis(1); g.ak = mrnb_axis(I); g.a_kfast = 0;
+    g.B = w.out; g.bk = mrnb_axis2(T, D, ITD); g.bn = mrnb_axis2(D, 1, TD); g.b_kfast = 0;
+    g.C = grads + off[R_CR_W]; g.cm = mrnb_axis(ID); g.cn = mrnb_axis(1);
+    g.M = I; g.N = (int)ID; g.K = B * T; g.batch = 1; g.alpha = 1.f; g.rows_per_scale = 1;
+    g.splitk = (B * T + 1023) / 1024; if (g.splitk > 32) g.splitk = 32; if (g.splitk < 1) g.splitk = 1;
+    MRNB_TRY(mrnb_sgemm(g, st));
+  }
+  MRNB_TRY(colsum(w.ds, mrnb_axis(I), mrnb_axis(1), B * T, I, grads + off[R_CR_B], st));
+  {  // dout[b,i,t,c] = sum_j ds[(b,t),j] Wcr[j,(i,c)]
+    MrnbGemm g{};
+    g.A = w.ds; g.am = mrnb_axis(I); g.ak = mrnb_axis(1); g.a_kfast = 1;
+    g.B = params + off[R_CR_W]; g.bk = mrnb_axis(ID); g.bn = mrnb_axis(1); g.b_kfast = 0;
+    g.C = w.dout; g.cm = mrnb_axis2(T, D, ITD); g.cn = mrnb_axis2(D, 1, TD);
+    g.M = B * T; g.N = (int)ID; g.K = I; g.batch = 1; g.splitk = 1; g.alpha = 1.f; g.rows_per_scale = 1;
+    MRNB_TRY(mrnb_sgemm(g, st));
+  }
+  return dm_router_backward_core(params, x, w.out, B, I, T, D, grads, nullptr, w, st);
+}
+
+extern "C" int mrnb_dm_router_backward(const float* params, const float* x, const float* d_out, int B, int n_experts,
+                                       int T, int D, int prec, float* grads, float* dx, void* workspace,
+                                       size_t workspace_bytes, cudaStream_t stream) {
+  ROUTER_ARGCHECK("dm_router_backward");
+  MRNB_CHECK_ARG(d_out && grads, "dm_router_backward: null argument");
+  RouterWs w = carve((char*)workspace, B, n_experts, T, D, true);
+  MRNB_CHECK_ARG(workspace_bytes >= w.bytes, "dm_router_backward: workspace too small");
+  long off[MRNB_ROUTER_NPARAMS + 1];
+  const long nparam = router_offsets(n_experts, T, D, off);
+  cudaMemsetAsync(grads, 0, nparam * sizeof(float), stream);
+  cudaMemcpyAsync(w.dout, d_out, (size_t)B * n_experts * T * D * sizeof(float), cudaMemcpyDeviceToDevice, stream);
+  return dm_router_backward_core(params, x, w.out, B, n_experts, T, D, grads, dx, w, stream);
+}

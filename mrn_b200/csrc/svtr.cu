@@ -1,0 +1,684 @@
+// SVTR expert recogniser forward, grouped over the N per-task experts (one launch covers every expert).
+//
+// Reference (paths relative to /root/reference):
+//   modules/svtr.py:500-528   SVTR.forward_features        modules/svtr.py:200-204  Block.forward (pre-norm)
+//   modules/svtr.py:133-152   Attention.forward (Local mask :116-128)   modules/svtr.py:61-67  Mlp
+//   modules/svtr.py:246-254   PatchEmbed (conv-BN-GELU x2)  modules/svtr.py:285-312  SubSample (conv s(2,1) + LN)
+//   modules/model.py:82-101   Model_Extractor.forward (permute / avg-pool over H=1 / Linear 512->256)
+//   modules/model.py:133-148  Model.forward (CTC head fc)
+//
+// Layout: activations are token-major [expert][sample][token][channel]; the residual stream is fp32, GEMM operands
+// are AT (float in the fp32 parity mode, bf16 in the tensor-core mode).  Every dense contraction goes through
+// linear<AT>() -> gemm_f32.cu (CUDA cores) or gemm_tc.cu (tcgen05/TMEM/TMA).
+#include "common.cuh"
+#include "gemm_f32.h"
+#include "gemm_tc.h"
+#include "svtr.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the channel axis: one warp per row.  gamma/beta are [groups, D]; group = row / rows_per_group.
+// ------------------------------------------------------------------------------------------------
+template <typename OT, int D>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* x, long x_gs, OT* y, long y_gs, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, long rows, long rows_per_group, float eps) {
+  constexpr int VPT = D / 32;
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const long grp = row / rows_per_group;
+  const long rin = row % rows_per_group;
+  const float* xr = x + grp * x_gs + rin * D;
+  float v[VPT];
+  if constexpr (VPT >= 4) {
+#pragma unroll
+    for (int c = 0; c < VPT / 4; ++c) {
+      const float4 t = *reinterpret_cast<const float4*>(xr + c * 128 + lane * 4);
+      v[c * 4] = t.x; v[c * 4 + 1] = t.y; v[c * 4 + 2] = t.z; v[c * 4 + 3] = t.w;
+    }
+  } else {
+    const float2 t = *reinterpret_cast<const float2*>(xr + lane * 2);
+    v[0] = t.x; v[1] = t.y;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) s += v[j];
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) { const float d = v[j] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+  const float* g = gamma + grp * D;
+  const float* bt = beta + grp * D;
+  OT* yr = y + grp * y_gs + rin * D;
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const int idx = (VPT >= 4) ? ((j / 4) * 128 + lane * 4 + (j % 4)) : (lane * 2 + j);
+    yr[idx] = from_f32<OT>((v[j] - mean) * rstd * g[idx] + bt[idx]);
+  }
+}
+
+template <typename OT>
+int launch_layernorm(const float* x, long x_gs, OT* y, long y_gs, const float* gamma, const float* beta, long rows,
+                     long rows_per_group, int D, float eps, cudaStream_t st) {
+  const int grid = cdiv(rows, 8);
+  switch (D) {
+    case 64: layernorm_kernel<OT, 64><<<grid, 256, 0, st>>>(x, x_gs, y, y_gs, gamma, beta, rows, rows_per_group, eps); break;
+    case 128: layernorm_kernel<OT, 128><<<grid, 256, 0, st>>>(x, x_gs, y, y_gs, gamma, beta, rows, rows_per_group, eps); break;
+    case 256: layernorm_kernel<OT, 256><<<grid, 256, 0, st>>>(x, x_gs, y, y_gs, gamma, beta, rows, rows_per_group, eps); break;
+    case 512: layernorm_kernel<OT, 512><<<grid, 256, 0, st>>>(x, x_gs, y, y_gs, gamma, beta, rows, rows_per_group, eps); break;
+    default: mrnb_set_error("layernorm: unsupported D=%d", D); return MRNB_ERR_UNSUPPORTED;
+  }
+  MRNB_CHECK_LAUNCH("layernorm_kernel");
+  return MRNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Patch embedding.  conv0: 4->32, 3x3 s2 p1 on the NCHW image (shared by all experts) -> raw NHWC [I,B,16,128,32]
+// plus per-channel sum / sum-of-squares for train-mode BatchNorm.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+conv0_kernel(const float* __restrict__ img, const float* __restrict__ w /*[I,32,4,3,3]*/,
+             const float* __restrict__ bias /*[I,32]*/, float* __restrict__ out, double* __restrict__ stats /*[I,32,2]*/,
+             int B) {
+  // grid: (16 output rows, B, I); block: 128 threads = 128 output columns
+  const int oh = blockIdx.x, b = blockIdx.y, e = blockIdx.z, ow = threadIdx.x;
+  __shared__ float sw[32 * 36];
+  __shared__ float sb[32];
+  __shared__ float red[4][32][2];
+  for (int k = threadIdx.x; k < 32 * 36; k += 128) sw[k] = w[(long)e * 32 * 36 + k];
+  if (threadIdx.x < 32) sb[threadIdx.x] = bias[e * 32 + threadIdx.x];
+  __syncthreads();
+  float in[36];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ih = oh * 2 - 1 + kh, iw = ow * 2 - 1 + kw;
+        in[c * 9 + kh * 3 + kw] = (ih >= 0 && ih < 32 && iw >= 0 && iw < 256)
+                                      ? __ldg(img + (((long)b * 4 + c) * 32 + ih) * 256 + iw) : 0.f;
+      }
+  float* o = out + ((((long)e * B + b) * 16 + oh) * 128 + ow) * 32;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  for (int oc0 = 0; oc0 < 32; oc0 += 4) {
+    float r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float a = sb[oc0 + u];
+#pragma unroll
+      for (int k = 0; k < 36; ++k) a = fmaf(in[k], sw[(oc0 + u) * 36 + k], a);
+      r[u] = a;
+    }
+    *reinterpret_cast<float4*>(o + oc0) = make_float4(r[0], r[1], r[2], r[3]);
+    if (stats) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float s1 = warp_sum(r[u]), s2 = warp_sum(r[u] * r[u]);
+        if (lane == 0) { red[wp][oc0 + u][0] = s1; red[wp][oc0 + u][1] = s2; }
+      }
+    }
+  }
+  if (stats) {
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const int c = threadIdx.x >> 1, k = threadIdx.x & 1;
+      const double t = (double)red[0][c][k] + (double)red[1][c][k] + (double)red[2][c][k] + (double)red[3][c][k];
+      atomicAdd(stats + ((long)e * 32 + c) * 2 + k, t);
+    }
+  }
+}
+
+// BN finalize: scale/shift per (expert, channel) from batch statistics (train) or running statistics (eval);
+// in train mode also the running-stat update with momentum 0.1 and the unbiased variance (nn.BatchNorm2d).
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ run_mean,
+                                   float* __restrict__ run_var, float* __restrict__ scale_shift /*[I,C,2]*/, int I, int C,
+                                   double count, int use_batch_stats, int update_running, float eps) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= I * C) return;
+  float mean, var;
+  if (use_batch_stats) {
+    const double m = stats[idx * 2] / count;
+    double v = stats[idx * 2 + 1] / count - m * m;
+    if (v < 0) v = 0;
+    mean = (float)m; var = (float)v;
+    if (update_running) {
+      run_mean[idx] = 0.9f * run_mean[idx] + 0.1f * mean;
+      run_var[idx] = 0.9f * run_var[idx] + 0.1f * (float)(v * count / (count - 1.0));
+    }
+  } else {
+    mean = run_mean[idx]; var = run_var[idx];
+  }
+  const float sc = gamma[idx] * rsqrtf(var + eps);
+  scale_shift[idx * 2] = sc;
+  scale_shift[idx * 2 + 1] = beta[idx] - mean * sc;
+}
+
+// conv1: 32->64, 3x3 s2 p1 over GELU(BN(conv0)) (applied on load) -> raw NHWC [I,B,8,64,64] + BN statistics.
+// grid (8 output rows, B, I); block 256 = 64 output columns x 4 groups of 16 output channels.
+__global__ void __launch_bounds__(256)
+conv1_kernel(const float* __restrict__ in /*[I,B,16,128,32]*/, const float* __restrict__ ss0 /*[I,32,2]*/,
+             const float* __restrict__ w /*[I,64,3,3,32]*/, const float* __restrict__ bias /*[I,64]*/,
+             float* __restrict__ out, double* __restrict__ stats /*[I,64,2]*/, int B) {
+  extern __shared__ float sm[];
+  float* s_in = sm;                       // [3][130][33]  (column index iw+1, zero border)
+  float* s_w = sm + 12872;               // [288][64] (16B aligned)     k-major so a warp reads 16 consecutive oc (broadcast x4)
+  const int oh = blockIdx.x, b = blockIdx.y, e = blockIdx.z, tid = threadIdx.x;
+  for (int k = tid; k < 64 * 288; k += 256) {
+    const int oc = k / 288, kk = k % 288;
+    s_w[kk * 64 + oc] = w[(long)e * 64 * 288 + k];
+  }
+  for (int k = tid; k < 3 * 130 * 32; k += 256) {
+    const int c = k % 32, col = (k / 32) % 130, r = k / (32 * 130);
+    const int ih = oh * 2 - 1 + r, iw = col - 1;
+    float v = 0.f;
+    if (ih >= 0 && ih < 16 && iw >= 0 && iw < 128) {
+      const float raw = in[((((long)e * B + b) * 16 + ih) * 128 + iw) * 32 + c];
+      v = gelu_erf(fmaf(raw, ss0[(e * 32 + c) * 2], ss0[(e * 32 + c) * 2 + 1]));
+    }
+    s_in[(r * 130 + col) * 33 + c] = v;
+  }
+  __syncthreads();
+  const int ow = tid & 63, og = tid >> 6;   // og: which 16 output channels
+  float acc[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) acc[u] = bias[e * 64 + og * 16 + u];
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw) {
+      const float* ip = s_in + (kh * 130 + ow * 2 + kw) * 33;
+      const float* wp_ = s_w + ((kh * 3 + kw) * 32) * 64 + og * 16;
+#pragma unroll 8
+      for (int c = 0; c < 32; ++c) {
+        const float x = ip[c];
+        const float4* w4 = reinterpret_cast<const float4*>(wp_ + c * 64);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 ww = w4[u];
+          acc[u * 4] = fmaf(x, ww.x, acc[u * 4]); acc[u * 4 + 1] = fmaf(x, ww.y, acc[u * 4 + 1]);
+          acc[u * 4 + 2] = fmaf(x, ww.z, acc[u * 4 + 2]); acc[u * 4 + 3] = fmaf(x, ww.w, acc[u * 4 + 3]);
+        }
+      }
+    }
+  float* o = out + ((((long)e * B + b) * 8 + oh) * 64 + ow) * 64 + og * 16;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    *reinterpret_cast<float4*>(o + u * 4) = make_float4(acc[u * 4], acc[u * 4 + 1], acc[u * 4 + 2], acc[u * 4 + 3]);
+  if (stats) {
+    __shared__ float red[8][16][2];
+    const int lane = tid & 31, wp = tid >> 5;      // warps 2*og, 2*og+1 share a channel group
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const float s1 = warp_sum(acc[u]), s2 = warp_sum(acc[u] * acc[u]);
+      if (lane == 0) { red[wp][u][0] = s1; red[wp][u][1] = s2; }
+    }
+    __syncthreads();
+    if (tid < 128) {
+      const int c = tid >> 1, k = tid & 1, g = c >> 4, u = c & 15;
+      atomicAdd(stats + ((long)e * 64 + c) * 2 + k, (double)red[2 * g][u][k] + (double)red[2 * g + 1][u][k]);
+    }
+  }
+}
+
+// tokens: x[e,b,n,c] = GELU(BN(conv1 raw)) + pos_embed[e,n,c]      (svtr.py:246-254,511)
+__global__ void embed_kernel(const float* __restrict__ raw, const float* __restrict__ ss1 /*[I,64,2]*/,
+                             const float* __restrict__ pos /*[I,512,64]*/, float* __restrict__ x, long per_expert) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;     // float4 index
+  const int e = blockIdx.y;
+  if (i * 4 >= per_expert) return;
+  const long off = (long)e * per_expert + i * 4;
+  const int c = (int)((i * 4) % 64);
+  const long n = ((i * 4) / 64) % 512;
+  const float4 r = *reinterpret_cast<const float4*>(raw + off);
+  const float4 p = *reinterpret_cast<const float4*>(pos + ((long)e * 512 + n) * 64 + c);
+  const float* ss = ss1 + (e * 64 + c) * 2;
+  float4 o;
+  o.x = gelu_erf(fmaf(r.x, ss[0], ss[1])) + p.x;
+  o.y = gelu_erf(fmaf(r.y, ss[2], ss[3])) + p.y;
+  o.z = gelu_erf(fmaf(r.z, ss[4], ss[5])) + p.z;
+  o.w = gelu_erf(fmaf(r.w, ss[6], ss[7])) + p.w;
+  *reinterpret_cast<float4*>(x + off) = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Attention.  One CTA per (expert*sample, head); one thread per query; K/V of the head staged in shared memory
+// (row stride 36 floats: conflict-free LDS.128 both for broadcast (Global) and lane-distinct (Local) rows).
+// Local mixer: |dh| <= 3, |dw| <= 5 window as index bounds (svtr.py:116-128), no dense mask.
+// ------------------------------------------------------------------------------------------------
+constexpr int KV_LD = 36;
+
+template <typename AT, bool LOCAL>
+__global__ void __launch_bounds__(512)
+attention_kernel(const AT* __restrict__ qkv, AT* __restrict__ out, int N, int d, int heads, int H, int W) {
+  extern __shared__ float sm[];
+  float* sK = sm;
+  float* sV = sm + (size_t)N * KV_LD;
+  const int g = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  const AT* base = qkv + (long)g * N * 3 * d;
+  for (int k = tid; k < N * 32; k += blockDim.x) {
+    const int n = k >> 5, j = k & 31;
+    sK[n * KV_LD + j] = to_f32<AT>(base[(long)n * 3 * d + d + h * 32 + j]);
+    sV[n * KV_LD + j] = to_f32<AT>(base[(long)n * 3 * d + 2 * d + h * 32 + j]);
+  }
+  __syncthreads();
+  const int n = tid;
+  if (n >= N) return;
+  float q[32], acc[32];
+  const float scale = 0.17677669529663688110f;    // 32^-0.5 (head_dim = 32 for every stage)
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { q[j] = to_f32<AT>(base[(long)n * 3 * d + h * 32 + j]) * scale; acc[j] = 0.f; }
+  float m = -INFINITY, l = 0.f;
+
+  auto step = [&](int key, bool valid) {
+    const float4* kr = reinterpret_cast<const float4*>(sK + key * KV_LD);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 kk = kr[j];
+      s = fmaf(q[4 * j], kk.x, s); s = fmaf(q[4 * j + 1], kk.y, s);
+      s = fmaf(q[4 * j + 2], kk.z, s); s = fmaf(q[4 * j + 3], kk.w, s);
+    }
+    if (!valid) return;
+    float p;
+    if (s > m) {
+      const float corr = expf(m - s);
+      l *= corr;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] *= corr;
+      m = s;
+      p = 1.f;
+    } else {
+      p = expf(s - m);
+    }
+    l += p;
+    const float4* vr = reinterpret_cast<const float4*>(sV + key * KV_LD);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 vv = vr[j];
+      acc[4 * j] = fmaf(p, vv.x, acc[4 * j]); acc[4 * j + 1] = fmaf(p, vv.y, acc[4 * j + 1]);
+      acc[4 * j + 2] = fmaf(p, vv.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(p, vv.w, acc[4 * j + 3]);
+    }
+  };
+
+  if constexpr (LOCAL) {
+    const int qh = n / W, qw = n % W;
+    for (int dh = -3; dh <= 3; ++dh) {
+      const int kh = qh + dh;
+      if (kh < 0 || kh >= H) continue;
+      for (int dw = -5; dw <= 5; ++dw) {
+        const int kw = qw + dw;
+        const bool valid = kw >= 0 && kw < W;
+        step(kh * W + (valid ? kw : qw), valid);
+      }
+    }
+  } else {
+    for (int key = 0; key < N; ++key) step(key, true);
+  }
+  const float inv = 1.0f / l;
+  AT* o = out + ((long)g * N + n) * d + h * 32;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) o[j] = from_f32<AT>(acc[j] * inv);
+}
+
+// ------------------------------------------------------------------------------------------------
+// im2col for the SubSample conv (3x3, stride (2,1), pad 1) over token-major x[g, H, W, C]:
+//   col[(g, oh, w), (kh, kw, c)] ; the conv weight is packed as [Cout, kh, kw, Cin] to match.
+// ------------------------------------------------------------------------------------------------
+template <typename AT>
+__global__ void im2col_kernel(const float* __restrict__ x, long x_gs, int bc, AT* __restrict__ col, int H, int W, int C,
+                              long total4) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;    // one float4 of channels
+  if (i >= total4) return;
+  const int c4 = C / 4;
+  const int c = (int)(i % c4) * 4;
+  long r = i / c4;
+  const int tap = (int)(r % 9); r /= 9;
+  const int w = (int)(r % W); r /= W;
+  const int oh = (int)(r % (H / 2));
+  const long g = r / (H / 2);
+  const int ih = oh * 2 - 1 + tap / 3, iw = w - 1 + tap % 3;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+    v = *reinterpret_cast<const float4*>(x + (g / bc) * x_gs + (((g % bc) * H + ih) * W + iw) * C + c);
+  AT* o = col + i * 4;
+  o[0] = from_f32<AT>(v.x); o[1] = from_f32<AT>(v.y); o[2] = from_f32<AT>(v.z); o[3] = from_f32<AT>(v.w);
+}
+
+template <typename AT>
+__global__ void cast_kernel(const float* __restrict__ x, AT* __restrict__ y, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = from_f32<AT>(x[i]);
+}
+
+// features [I, Bc, T, D] (expert-major, AT) -> router layout [Bc, I, T, D] fp32   (torch.stack(...,1), model.py:400)
+__global__ void feature_scatter_kernel(const float* __restrict__ src, float* __restrict__ dst, int I, int Bc, long TD) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)I * Bc * TD / 4;
+  if (i >= total) return;
+  const long e4 = i * 4;
+  const long td = e4 % TD;
+  const long b = (e4 / TD) % Bc;
+  const long e = e4 / (TD * Bc);
+  *reinterpret_cast<float4*>(dst + (b * I + e) * TD + td) = *reinterpret_cast<const float4*>(src + e4);
+}
+
+// ------------------------------------------------------------------------------------------------
+// linear<AT>: grouped Linear over experts: out[g, m, :] = epi(A[g, m, :] . W[g]^T + b[g])
+// ------------------------------------------------------------------------------------------------
+struct LinearArgs {
+  const void* A; long lda; long a_gstride;       // AT
+  const float* W32; const void* W16; long w_gstride;   // [groups, N, K]
+  const float* bias; long bias_gstride;
+  void* out; long ldo; long o_gstride; int out_is_f32;   // out dtype: fp32 or AT
+  const float* res; const float* rowscale; int rows_per_scale; long rowscale_gstride;
+  int M, N, K, groups, gelu;
+};
+
+template <typename AT>
+int linear(const LinearArgs& a, cudaStream_t st);
+
+template <>
+int linear<float>(const LinearArgs& a, cudaStream_t st) {
+  MrnbGemm g = mrnb_gemm_nt((const float*)a.A, a.lda, a.W32, a.K, (float*)a.out, a.ldo, a.M, a.N, a.K);
+  g.batch = a.groups; g.sAb = a.a_gstride; g.sBb = a.w_gstride; g.sCb = a.o_gstride;
+  g.bias_n = a.bias; g.bias_bstride = a.bias_gstride;
+  g.res = a.res; g.rowscale = a.rowscale; g.rows_per_scale = a.rows_per_scale > 0 ? a.rows_per_scale : 1;
+  g.rowscale_bstride = a.rowscale_gstride;
+  g.act = a.gelu;
+  return mrnb_sgemm(g, st);
+}
+
+template <>
+int linear<__nv_bfloat16>(const LinearArgs& a, cudaStream_t st) {
+  MrnbTcGemm g{};
+  g.A = a.A; g.lda = a.lda; g.a_gstride = a.a_gstride;
+  g.W = a.W16; g.ldw = a.K; g.w_gstride = a.w_gstride;
+  g.bias = a.bias; g.bias_gstride = a.bias_gstride;
+  g.out = a.out; g.ldo = a.ldo; g.o_gstride = a.o_gstride; g.out_f32 = a.out_is_f32;
+  g.res = a.res; g.rowscale = a.rowscale; g.rows_per_scale = a.rows_per_scale > 0 ? a.rows_per_scale : 1;
+  g.rowscale_gstride = a.rowscale_gstride;
+  g.M = a.M; g.N = a.N; g.K = a.K; g.groups = a.groups; g.gelu = a.gelu;
+  return mrnb_tc_gemm(g, st);
+}
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+  char* base; size_t off, cap;
+  template <typename T> T* take(size_t n) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off = align_up(off + n * sizeof(T));
+    return p;
+  }
+};
+
+template <typename AT>
+size_t svtr_workspace_bytes_t(int I, int B, int Bc) {
+  size_t s = 0;
+  s += align_up((size_t)I * B * 16 * 128 * 32 * 4);        // conv0 raw
+  s += align_up((size_t)I * B * 8 * 64 * 64 * 4);          // conv1 raw
+  s += align_up((size_t)I * 96 * 2 * 8);                    // stats
+  s += align_up((size_t)I * 96 * 2 * 4);                    // scale/shift
+  s += align_up((size_t)I * B * 32768 * 4);                 // x (all samples)
+  const size_t u = (size_t)I * Bc * 32768;
+  s += align_up(u * 4);                                     // xb (subsample output / ping-pong)
+  s += align_up(u * sizeof(AT));                            // ln out
+  s += align_up(u * 3 * sizeof(AT));                        // qkv
+  s += align_up(u * sizeof(AT));                            // attention out
+  s += align_up(u * 9 / 2 * sizeof(AT));                    // mlp hidden (4u) / im2col (4.5u)
+  s += align_up((size_t)I * Bc * 64 * 256 * 4);             // features expert-major fp32
+  s += align_up((size_t)I * Bc * 64 * 256 * sizeof(AT));    // features AT (classifier operand)
+  return s + 4096;
+}
+
+template <typename AT>
+int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int bn_batch_stats, int update_running,
+                   const float* drop_scales /*[I,12,2,B] or null*/, float* features /*[B,I,T,256]*/,
+                   float* const* logits, const long* ld_logits, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int I = P.n_experts;
+  MRNB_CHECK_ARG(ws_bytes >= svtr_workspace_bytes_t<AT>(I, B, Bc), "svtr_forward: workspace too small (%zu < %zu)",
+                 ws_bytes, svtr_workspace_bytes_t<AT>(I, B, Bc));
+  Workspace W{(char*)ws, 0, ws_bytes};
+  float* conv0 = W.take<float>((size_t)I * B * 16 * 128 * 32);
+  float* conv1 = W.take<float>((size_t)I * B * 8 * 64 * 64);
+  double* stats = W.take<double>((size_t)I * 96 * 2);
+  float* ss = W.take<float>((size_t)I * 96 * 2);
+  float* xall = W.take<float>((size_t)I * B * 32768);
+  const size_t u = (size_t)I * Bc * 32768;
+  float* xb = W.take<float>(u);
+  AT* lnout = W.take<AT>(u);
+  AT* qkv = W.take<AT>(u * 3);
+  AT* att = W.take<AT>(u);
+  AT* big = W.take<AT>(u * 9 / 2);
+  float* feat32 = W.take<float>((size_t)I * Bc * 64 * 256);
+  AT* featat = W.take<AT>((size_t)I * Bc * 64 * 256);
+  constexpr bool F32 = sizeof(AT) == 4;
+
+  // ---- patch embedding on the full batch (train-mode BN needs whole-batch statistics)
+  double* st0 = stats; double* st1 = stats + (size_t)I * 32 * 2;
+  float* ss0 = ss; float* ss1 = ss + (size_t)I * 32 * 2;
+  if (bn_batch_stats) {
+    cudaMemsetAsync(stats, 0, (size_t)I * 96 * 2 * sizeof(double), st);
+  }
+  conv0_kernel<<<dim3(16, B, I), 128, 0, st>>>(image, P.p[MRNB_P_CONV0_W], P.p[MRNB_P_CONV0_B], conv0,
+                                                bn_batch_stats ? st0 : nullptr, B);
+  MRNB_CHECK_LAUNCH("conv0_kernel");
+  bn_finalize_kernel<<<cdiv(I * 32, 128), 128, 0, st>>>(st0, P.p[MRNB_P_BN0_W], P.p[MRNB_P_BN0_B],
+                                                        (float*)P.p[MRNB_P_BN0_MEAN], (float*)P.p[MRNB_P_BN0_VAR], ss0, I,
+                                                        32, (double)B * 16 * 128, bn_batch_stats, update_running, 1e-5f);
+  MRNB_CHECK_LAUNCH("bn_finalize_kernel");
+  {
+    const size_t smem = (12872 + 288 * 64) * sizeof(float);
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; }
+    conv1_kernel<<<dim3(8, B, I), 256, smem, st>>>(conv0, ss0, P.p[MRNB_P_CONV1_W], P.p[MRNB_P_CONV1_B], conv1,
+                                                    bn_batch_stats ? st1 : nullptr, B);
+    MRNB_CHECK_LAUNCH("conv1_kernel");
+  }
+  bn_finalize_kernel<<<cdiv(I * 64, 128), 128, 0, st>>>(st1, P.p[MRNB_P_BN1_W], P.p[MRNB_P_BN1_B],
+                                                        (float*)P.p[MRNB_P_BN1_MEAN], (float*)P.p[MRNB_P_BN1_VAR], ss1, I,
+                                                        64, (double)B * 8 * 64, bn_batch_stats, update_running, 1e-5f);
+  MRNB_CHECK_LAUNCH("bn_finalize_kernel");
+  {
+    const long per_expert = (long)B * 32768;
+    embed_kernel<<<dim3(cdiv(per_expert / 4, 256), I), 256, 0, st>>>(conv1, ss1, P.p[MRNB_P_POS_EMBED], xall, per_expert);
+    MRNB_CHECK_LAUNCH("embed_kernel");
+  }
+
+  static const int DIMS[3] = {64, 128, 256}, DEPTH[3] = {3, 6, 3}, HEADS[3] = {2, 4, 8}, GH[3] = {8, 4, 2};
+  static const int OUTS[3] = {128, 256, 512};
+  {
+    static bool set = false;
+    if (!set) {
+      const int mx = 2 * 512 * KV_LD * 4;
+      cudaFuncSetAttribute(attention_kernel<AT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+      cudaFuncSetAttribute(attention_kernel<AT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+      set = true;
+    }
+  }
+
+  for (int b0 = 0; b0 < B; b0 += Bc) {
+    const int bc = (B - b0 < Bc) ? (B - b0) : Bc;
+    // x for expert e, chunk: xall[e][b0 .. b0+bc) : group stride B*32768, rows contiguous inside a group
+    float* x = xall + (size_t)b0 * 32768;
+    long x_gs = (long)B * 32768;           // group (expert) stride of the current residual stream
+    int blk = 0;
+    for (int sidx = 0; sidx < 3; ++sidx) {
+      const int d = DIMS[sidx], N = 32768 / d, heads = HEADS[sidx], H = GH[sidx], Wd = 64;
+      const long rows_g = (long)bc * N;          // rows per expert in this chunk
+      for (int j = 0; j < DEPTH[sidx]; ++j, ++blk) {
+        const int pb = MRNB_P_BLOCK0 + blk * MRNB_PB_COUNT;
+        const bool local = blk < 6;
+        // LN1 (per expert: x groups are strided, outputs packed [I, rows_g, d])
+        MRNB_TRY(launch_layernorm<AT>(x, x_gs, lnout, rows_g * d, P.p[pb + MRNB_PB_NORM1_W], P.p[pb + MRNB_PB_NORM1_B],
+                                      rows_g * I, rows_g, d, 1e-6f, st));
+        LinearArgs a{};
+        a.A = lnout; a.lda = d; a.a_gstride = rows_g * d;
+        a.W32 = P.p[pb + MRNB_PB_QKV_W]; a.W16 = P.h[pb + MRNB_PB_QKV_W]; a.w_gstride = (long)3 * d * d;
+        a.bias = P.p[pb + MRNB_PB_QKV_B]; a.bias_gstride = 3 * d;
+        a.out = qkv; a.ldo = 3 * d; a.o_gstride = rows_g * 3 * d; a.out_is_f32 = F32;
+        a.M = (int)rows_g; a.N = 3 * d; a.K = d; a.groups = I;
+        MRNB_TRY(linear<AT>(a, st));
+        {
+          const size_t smem = (size_t)2 * N * KV_LD * sizeof(float);
+          dim3 grid(I * bc, heads);
+          if (local) attention_kernel<AT, true><<<grid, N, smem, st>>>(qkv, att, N, d, heads, H, Wd);
+          else attention_kernel<AT, false><<<grid, N, smem, st>>>(qkv, att, N, d, heads, H, Wd);
+          MRNB_CHECK_LAUNCH("attention_kernel");
+        }
+        // proj + DropPath scale + residual (in place on x)
+        LinearArgs pr{};
+        pr.A = att; pr.lda = d; pr.a_gstride = rows_g * d;
+        pr.W32 = P.p[pb + MRNB_PB_PROJ_W]; pr.W16 = P.h[pb + MRNB_PB_PROJ_W]; pr.w_gstride = (long)d * d;
+        pr.bias = P.p[pb + MRNB_PB_PROJ_B]; pr.bias_gstride = d;
+        pr.out = x; pr.ldo = d; pr.o_gstride = x_gs; pr.out_is_f32 = 1; pr.res = x;
+        if (drop_scales) {
+          pr.rowscale = drop_scales + ((size_t)blk * 2 + 0) * B + b0; pr.rows_per_scale = N;
+          pr.rowscale_gstride = (long)12 * 2 * B;
+        }
+        pr.M = (int)rows_g; pr.N = d; pr.K = d; pr.groups = I;
+        MRNB_TRY(linear<AT>(pr, st));
+        MRNB_TRY(launch_layernorm<AT>(x, x_gs, lnout, rows_g * d, P.p[pb + MRNB_PB_NORM2_W], P.p[pb + MRNB_PB_NORM2_B],
+                                      rows_g * I, rows_g, d, 1e-6f, st));
+        LinearArgs f1{};
+        f1.A = lnout; f1.lda = d; f1.a_gstride = rows_g * d;
+        f1.W32 = P.p[pb + MRNB_PB_FC1_W]; f1.W16 = P.h[pb + MRNB_PB_FC1_W]; f1.w_gstride = (long)4 * d * d;
+        f1.bias = P.p[pb + MRNB_PB_FC1_B]; f1.bias_gstride = 4 * d;
+        f1.out = big; f1.ldo = 4 * d; f1.o_gstride = rows_g * 4 * d; f1.out_is_f32 = F32; f1.gelu = 1;
+        f1.M = (int)rows_g; f1.N = 4 * d; f1.K = d; f1.groups = I;
+        MRNB_TRY(linear<AT>(f1, st));
+        LinearArgs f2{};
+        f2.A = big; f2.lda = 4 * d; f2.a_gstride = rows_g * 4 * d;
+        f2.W32 = P.p[pb + MRNB_PB_FC2_W]; f2.W16 = P.h[pb + MRNB_PB_FC2_W]; f2.w_gstride = (long)4 * d * d;
+        f2.bias = P.p[pb + MRNB_PB_FC2_B]; f2.bias_gstride = d;
+        f2.out = x; f2.ldo = d; f2.o_gstride = x_gs; f2.out_is_f32 = 1; f2.res = x;
+        if (drop_scales) {
+          f2.rowscale = drop_scales + ((size_t)blk * 2 + 1) * B + b0; f2.rows_per_scale = N;
+          f2.rowscale_gstride = (long)12 * 2 * B;
+        }
+        f2.M = (int)rows_g; f2.N = d; f2.K = 4 * d; f2.groups = I;
+        MRNB_TRY(linear<AT>(f2, st));
+      }
+      // SubSample: im2col -> conv GEMM (+bias) -> LN(eps 1e-5)
+      const int Co = OUTS[sidx];
+      const long orows_g = (long)bc * (H / 2) * Wd;
+      {
+        const long total4 = (long)I * orows_g * 9 * d / 4;
+        im2col_kernel<AT><<<cdiv(total4, 256), 256, 0, st>>>(x, x_gs, bc, big, H, Wd, d, total4);
+        MRNB_CHECK_LAUNCH("im2col_kernel");
+      }
+      const int ps = MRNB_P_SUB0 + sidx * MRNB_PS_COUNT;
+      float* cv = (x == xb) ? xall : xb;          // conv output buffer distinct from x
+      // (xall chunk region is free to reuse once x has moved to xb and vice versa)
+      float* cvx = (cv == xall) ? xall + (size_t)b0 * 32768 : xb;
+      const long cv_gs = (cv == xall) ? (long)B * 32768 : (long)bc * 32768;
+      LinearArgs cvl{};
+      cvl.A = big; cvl.lda = 9 * d; cvl.a_gstride = orows_g * 9 * d;
+      cvl.W32 = P.p[ps + MRNB_PS_CONV_W]; cvl.W16 = P.h[ps + MRNB_PS_CONV_W]; cvl.w_gstride = (long)Co * 9 * d;
+      cvl.bias = P.p[ps + MRNB_PS_CONV_B]; cvl.bias_gstride = Co;
+      cvl.out = cvx; cvl.ldo = Co; cvl.o_gstride = cv_gs; cvl.out_is_f32 = 1;
+      cvl.M = (int)orows_g; cvl.N = Co; cvl.K = 9 * d; cvl.groups = I;
+      MRNB_TRY(linear<AT>(cvl, st));
+      if (sidx < 2) {
+        // LN in place (fp32 -> fp32) : next stage's residual stream
+        MRNB_TRY(launch_layernorm<float>(cvx, cv_gs, cvx, cv_gs, P.p[ps + MRNB_PS_NORM_W], P.p[ps + MRNB_PS_NORM_B],
+                                         orows_g * I, orows_g, Co, 1e-5f, st));
+        x = cvx; x_gs = cv_gs;
+      } else {
+        // last merge: LN -> AT [I, bc*64, 512] visual feature (model.py:88-95 relabel), then Linear 512->256
+        MRNB_TRY(launch_layernorm<AT>(cvx, cv_gs, lnout, orows_g * Co, P.p[ps + MRNB_PS_NORM_W], P.p[ps + MRNB_PS_NORM_B],
+                                      orows_g * I, orows_g, Co, 1e-5f, st));
+        LinearArgs sq{};
+        sq.A = lnout; sq.lda = 512; sq.a_gstride = orows_g * 512;
+        sq.W32 = P.p[MRNB_P_SEQ_W]; sq.W16 = P.h[MRNB_P_SEQ_W]; sq.w_gstride = 256 * 512;
+        sq.bias = P.p[MRNB_P_SEQ_B]; sq.bias_gstride = 256;
+        sq.out = feat32; sq.ldo = 256; sq.o_gstride = orows_g * 256; sq.out_is_f32 = 1;
+        sq.M = (int)orows_g; sq.N = 256; sq.K = 512; sq.groups = I;
+        MRNB_TRY(linear<AT>(sq, st));
+      }
+    }
+    // features -> router layout; classifier heads (ragged N = C_i)
+    {
+      const long TD = 64 * 256;
+      const long total4 = (long)I * bc * TD / 4;
+      if (features) {
+        feature_scatter_kernel<<<cdiv(total4, 256), 256, 0, st>>>(feat32, features + (size_t)b0 * I * TD, I, bc, TD);
+        MRNB_CHECK_LAUNCH("feature_scatter_kernel");
+      }
+      const void* fa = feat32;
+      if (!F32) {
+        cast_kernel<AT><<<cdiv(total4 * 4, 256), 256, 0, st>>>(feat32, featat, total4 * 4);
+        MRNB_CHECK_LAUNCH("cast_kernel");
+        fa = featat;
+      }
+      if (logits) {
+        for (int e = 0; e < I; ++e) {
+          if (!logits[e]) continue;
+          LinearArgs fc{};
+          fc.A = (const char*)fa + (size_t)e * bc * TD * sizeof(AT); fc.lda = 256;
+          fc.W32 = P.fc_w[e]; fc.W16 = P.fc_w16[e]; fc.bias = P.fc_b[e];
+          fc.out = logits[e] + (size_t)b0 * 64 * ld_logits[e]; fc.ldo = ld_logits[e]; fc.out_is_f32 = 1;
+          fc.M = bc * 64; fc.N = P.n_class[e]; fc.K = 256; fc.groups = 1;
+          MRNB_TRY(linear<AT>(fc, st));
+        }
+      }
+    }
+  }
+  return MRNB_OK;
+}
+
+}  // namespace
+
+extern "C" size_t mrnb_svtr_workspace_bytes(int n_experts, int B, int chunk, int prec) {
+  if (chunk <= 0 || chunk > B) chunk = B;
+  return prec == MRNB_PREC_BF16 ? svtr_workspace_bytes_t<__nv_bfloat16>(n_experts, B, chunk)
+                                : svtr_workspace_bytes_t<float>(n_experts, B, chunk);
+}
+
+extern "C" int mrnb_svtr_experts_forward(const MrnbSvtrPack* pack, const float* image, int B, int chunk, int prec,
+                                         int bn_batch_stats, int update_running, const float* drop_scales,
+                                         float* features, float* const* logits, const long* ld_logits, void* workspace,
+                                         size_t workspace_bytes, cudaStream_t stream) {
+  MRNB_CHECK_ARG(pack && image && workspace && B > 0, "svtr_experts_forward: null/empty argument");
+  MRNB_CHECK_ARG(pack->n_experts >= 1 && pack->n_experts <= MRNB_MAX_EXPERTS, "svtr_experts_forward: n_experts out of range");
+  MRNB_CHECK_ARG(!bn_batch_stats || B * 16 * 128 > 1, "svtr_experts_forward: batch statistics need more than one value");
+  if (chunk <= 0 || chunk > B) chunk = B;
+  for (int k = 0; k < MRNB_P_COUNT; ++k) MRNB_CHECK_ARG(pack->p[k], "svtr_experts_forward: parameter slot %d is null", k);
+  if (prec == MRNB_PREC_BF16) {
+    return svtr_forward_t<__nv_bfloat16>(*pack, image, B, chunk, bn_batch_stats, update_running, drop_scales, features,
+                                         logits, ld_logits, workspace, workspace_bytes, stream);
+  } else if (prec == MRNB_PREC_FP32) {
+    return svtr_forward_t<float>(*pack, image, B, chunk, bn_batch_stats, update_running, drop_scales, features, logits,
+                                 ld_logits, workspace, workspace_bytes, stream);
+  }
+  mrnb_set_error("svtr_experts_forward: unknown precision %d", prec);
+  return MRNB_ERR_ARG;
+}
+
+// Stand-alone ops for the tests.
+extern "C" int mrnb_layernorm_f32(const float* x, float* y, const float* gamma, const float* beta, long rows, int D,
+                                  float eps, cudaStream_t stream) {
+  MRNB_CHECK_ARG(x && y && gamma && beta && rows > 0, "layernorm: bad argument");
+  return launch_layernorm<float>(x, 0, y, 0, gamma, beta, rows, rows, D, eps, stream);
+}
+
+extern "C" int mrnb_svtr_attention_f32(const float* qkv, float* out, int groups, int N, int d, int heads, int H, int W,
+                                       int local, cudaStream_t stream) {
+  MRNB_CHECK_ARG(qkv && out && groups > 0 && N > 0 && N <= 512 && d == heads * 32 && H * W == N, "svtr_attention: bad argument");
+  const size_t smem = (size_t)2 * N * KV_LD * sizeof(float);
+  static bool set = false;
+  if (!set) {
+    const int mx = 2 * 512 * KV_LD * 4;
+    cudaFuncSetAttribute(attention_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(attention_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    set = true;
+  }
+  dim3 grid(groups, heads);
+  if (local) attention_kernel<float, true><<<grid, N, smem, stream>>>(qkv, out, N, d, heads, H, W);
+  else attention_kernel<float, false><<<grid, N, smem, stream>>>(qkv, out, N, d, heads, H, W);
+  MRNB_CHECK_LAUNCH("attention_kernel");
+  return MRNB_OK;
+}

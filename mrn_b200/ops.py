@@ -1,0 +1,369 @@
+"""Thin Python wrappers over the C ABI (include/mrn_b200.h): torch tensors in, torch tensors out.
+
+torch is used for device memory, streams and (elsewhere) torch.distributed only; every FLOP on the path runs in
+libmrn_b200.so.  All wrappers require CUDA tensors and raise otherwise -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+T_FRAMES = 64      # MRNNet.patch for SVTR (modules/model.py:324)
+D_FEAT = 256       # opt.hidden_size
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return C.c_void_p(0)
+    if not t.is_cuda:
+        raise RuntimeError("mrn_b200 ops need CUDA tensors (no CPU fallback)")
+    return C.c_void_p(t.data_ptr())
+
+
+def _chk_f32(*ts):
+    for t in ts:
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+            raise RuntimeError("expected a contiguous float32 tensor, got %s contiguous=%s" % (t.dtype, t.is_contiguous()))
+
+
+def launch_count() -> int:
+    return int(L.load().mrnb_launch_count())
+
+
+def reset_launch_count() -> None:
+    L.load().mrnb_reset_launch_count()
+
+
+# ------------------------------------------------------------------------------------------------ building blocks
+def linear_f32(a, w, bias=None, residual=None, gelu=False):
+    _chk_f32(a, w, bias, residual)
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    L.check(L.load().mrnb_linear_f32(_p(a), _p(w), _p(bias), _p(residual), _p(out), M, N, K, int(gelu), _stream()), "linear_f32")
+    return out
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    _chk_f32(x)
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    L.check(L.load().mrnb_cast_f32_to_bf16(_p(x), _p(y), x.numel(), _stream()), "cast")
+    return y
+
+
+def linear_bf16(a, w, bias=None, residual=None, gelu=False, out_f32=True):
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.is_contiguous() and w.is_contiguous()
+    _chk_f32(bias, residual)
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, device=a.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    L.check(L.load().mrnb_linear_bf16(_p(a), _p(w), _p(bias), _p(residual), _p(out), int(out_f32), M, N, K, int(gelu),
+                                      _stream()), "linear_bf16")
+    return out
+
+
+def layernorm(x, gamma, beta, eps):
+    _chk_f32(x, gamma, beta)
+    y = torch.empty_like(x)
+    rows = x.numel() // x.shape[-1]
+    L.check(L.load().mrnb_layernorm_f32(_p(x), _p(y), _p(gamma), _p(beta), rows, x.shape[-1], float(eps), _stream()), "layernorm")
+    return y
+
+
+def svtr_attention(qkv, heads, H, W, local):
+    _chk_f32(qkv)
+    G, N, d3 = qkv.shape
+    out = torch.empty(G, N, d3 // 3, device=qkv.device, dtype=torch.float32)
+    L.check(L.load().mrnb_svtr_attention_f32(_p(qkv), _p(out), G, N, d3 // 3, heads, H, W, int(local), _stream()), "attention")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ SVTR experts
+_BLOCK_KEYS = ("norm1.weight", "norm1.bias", "mixer.qkv.weight", "mixer.qkv.bias", "mixer.proj.weight",
+               "mixer.proj.bias", "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight",
+               "mlp.fc2.bias")
+_BLOCK_NAMES = [f"blocks1.{j}" for j in range(3)] + [f"blocks2.{j}" for j in range(6)] + [f"blocks3.{j}" for j in range(3)]
+_GEMM_W_SLOTS = {L.PB_QKV_W, L.PB_PROJ_W, L.PB_FC1_W, L.PB_FC2_W}
+
+
+def round_up(v, a):
+    return (v + a - 1) // a * a
+
+
+class SvtrPack:
+    """Device-resident, expert-stacked copy of the SVTR expert parameters in the layout the kernels consume
+    (include/mrn_b200.h: MRNB_P_* slots).  Built from a reference-format state_dict; rebuilt when experts change
+    (experts are frozen during router training, il_modules/mrn.py:154-157)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], n_experts: int, device, prec: int, prefix: str = ""):
+        self.n_experts = n_experts
+        self.prec = prec
+        self.device = torch.device(device)
+        self.tensors: List[torch.Tensor] = []      # keep-alive
+        self.struct = L.MrnbSvtrPack()
+        self.struct.n_experts = n_experts
+        self.n_class: List[int] = []
+        self.slot_tensors: Dict[int, torch.Tensor] = {}
+        sd = state_dict
+
+        def conv(i):
+            return f"{prefix}model.{i}.model.FeatureExtraction.ConvNet."
+
+        def stack(suffix, permute=None):
+            ts = []
+            for i in range(n_experts):
+                t = sd[conv(i) + suffix].detach().to(self.device, torch.float32)
+                if permute is not None:
+                    t = t.permute(*permute)
+                ts.append(t.contiguous())
+            return torch.stack(ts, 0).contiguous()
+
+        def put(slot, t, gemm_weight=False):
+            self.tensors.append(t)
+            self.slot_tensors[slot] = t
+            self.struct.p[slot] = t.data_ptr()
+            if gemm_weight and prec == L.PREC_BF16:
+                h = cast_bf16(t)
+                self.tensors.append(h)
+                self.struct.h[slot] = h.data_ptr()
+
+        put(L.P_POS_EMBED, stack("pos_embed").reshape(n_experts, 512, 64).contiguous())
+        put(L.P_CONV0_W, stack("patch_embed.proj.0.weight"))
+        put(L.P_CONV0_B, stack("patch_embed.proj.0.bias"))
+        for base, idx in ((L.P_BN0_W, 1), (L.P_BN1_W, 4)):
+            for k, nm in enumerate(("weight", "bias", "running_mean", "running_var")):
+                put(base + k, stack(f"patch_embed.proj.{idx}.{nm}"))
+        put(L.P_CONV1_W, stack("patch_embed.proj.3.weight", permute=(0, 2, 3, 1)))
+        put(L.P_CONV1_B, stack("patch_embed.proj.3.bias"))
+        for b, name in enumerate(_BLOCK_NAMES):
+            for k, key in enumerate(_BLOCK_KEYS):
+                put(L.P_BLOCK0 + b * L.PB_COUNT + k, stack(f"{name}.{key}"), gemm_weight=k in _GEMM_W_SLOTS)
+        for s in range(3):
+            base = L.P_SUB0 + s * L.PS_COUNT
+            put(base + L.PS_CONV_W, stack(f"sub_sample{s + 1}.conv.weight", permute=(0, 2, 3, 1)), gemm_weight=True)
+            put(base + L.PS_CONV_B, stack(f"sub_sample{s + 1}.conv.bias"))
+            put(base + L.PS_NORM_W, stack(f"sub_sample{s + 1}.norm.weight"))
+            put(base + L.PS_NORM_B, stack(f"sub_sample{s + 1}.norm.bias"))
+        seq_w = torch.stack([sd[f"{prefix}model.{i}.model.SequenceModeling.0.weight"].detach().to(self.device, torch.float32)
+                             for i in range(n_experts)], 0).contiguous()
+        seq_b = torch.stack([sd[f"{prefix}model.{i}.model.SequenceModeling.0.bias"].detach().to(self.device, torch.float32)
+                             for i in range(n_experts)], 0).contiguous()
+        put(L.P_SEQ_W, seq_w, gemm_weight=True)
+        put(L.P_SEQ_B, seq_b)
+        for i in range(n_experts):
+            w = sd[f"{prefix}model.{i}.fc.weight"].detach().to(self.device, torch.float32).contiguous()
+            b = sd[f"{prefix}model.{i}.fc.bias"].detach().to(self.device, torch.float32).contiguous()
+            self.tensors += [w, b]
+            self.struct.fc_w[i] = w.data_ptr()
+            self.struct.fc_b[i] = b.data_ptr()
+            self.struct.n_class[i] = w.shape[0]
+            self.n_class.append(int(w.shape[0]))
+            if prec == L.PREC_BF16:
+                h = cast_bf16(w)
+                self.tensors.append(h)
+                self.struct.fc_w16[i] = h.data_ptr()
+        self._ws: Optional[torch.Tensor] = None
+
+    def bn_running_stats(self):
+        """(mean0, var0, mean1, var1), each [I, C]: updated in place by train-mode forwards."""
+        return tuple(self.slot_tensors[s] for s in (L.P_BN0_MEAN, L.P_BN0_VAR, L.P_BN1_MEAN, L.P_BN1_VAR))
+
+    def workspace(self, B, chunk):
+        need = int(L.load().mrnb_svtr_workspace_bytes(self.n_experts, B, chunk, self.prec))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+
+def svtr_experts_forward(pack: SvtrPack, image: torch.Tensor, bn_batch_stats: bool = False, update_running: bool = False,
+                         drop_scales: Optional[torch.Tensor] = None, chunk: int = 0, want_logits: bool = True,
+                         experts_with_logits: Optional[Sequence[int]] = None):
+    """Runs every expert on `image` [B,4,32,256].  Returns (features [B,I,64,256], [logits_i [B,64,C_i] views])."""
+    _chk_f32(image, drop_scales)
+    B = image.shape[0]
+    I = pack.n_experts
+    feats = torch.empty(B, I, T_FRAMES, D_FEAT, device=image.device, dtype=torch.float32)
+    ptrs = (C.c_void_p * I)()
+    lds = (C.c_long * I)()
+    logits = []
+    for i in range(I):
+        ld = round_up(pack.n_class[i], 4)
+        lds[i] = ld
+        if want_logits and (experts_with_logits is None or i in experts_with_logits):
+            buf = torch.empty(B, T_FRAMES, ld, device=image.device, dtype=torch.float32)
+            ptrs[i] = buf.data_ptr()
+            logits.append(buf[:, :, :pack.n_class[i]])
+        else:
+            ptrs[i] = None
+            logits.append(None)
+    ws = pack.workspace(B, chunk)
+    rc = L.load().mrnb_svtr_experts_forward(C.byref(pack.struct), _p(image), B, int(chunk), pack.prec, int(bn_batch_stats),
+                                            int(update_running), _p(drop_scales), _p(feats), ptrs, lds, _p(ws),
+                                            ws.numel(), _stream())
+    L.check(rc, "svtr_experts_forward")
+    return feats, logits
+
+
+# ------------------------------------------------------------------------------------------------ router
+ROUTER_PARAM_NAMES = ("route.weight", "route.bias", "channel_route.weight", "channel_route.bias",
+                      "dm_router.0.norm.weight", "dm_router.0.norm.bias",
+                      "dm_router.0.proj_1.weight", "dm_router.0.proj_1.bias",
+                      "dm_router.0.spatial_gating.norm.weight", "dm_router.0.spatial_gating.norm.bias",
+                      "dm_router.0.spatial_gating.proj.weight", "dm_router.0.spatial_gating.proj.bias",
+                      "dm_router.0.channel_gating.norm.weight", "dm_router.0.channel_gating.norm.bias",
+                      "dm_router.0.channel_gating.proj.weight", "dm_router.0.channel_gating.proj.bias",
+                      "dm_router.0.proj_2.weight", "dm_router.0.proj_2.bias",
+                      "dm_router.0.proj_3.weight", "dm_router.0.proj_3.bias")
+
+
+def router_param_offsets(n_experts: int, T: int = T_FRAMES, D: int = D_FEAT):
+    off = (C.c_long * (L.ROUTER_NPARAMS + 1))()
+    n = L.load().mrnb_router_param_offsets(n_experts, T, D, off)
+    return int(n), [int(v) for v in off]
+
+
+class RouterWorkspace:
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self, B, I, T, D, bwd, device):
+        need = int(L.load().mrnb_router_workspace_bytes(B, I, T, D, int(bwd)))
+        if self.buf is None or self.buf.numel() < need or self.buf.device != device:
+            self.buf = torch.empty(need, dtype=torch.uint8, device=device)
+        return self.buf
+
+
+def router_forward(params: torch.Tensor, x: torch.Tensor, ws: RouterWorkspace, with_backward=False, prec=L.PREC_FP32,
+                   want_out=True):
+    """params: flat fp32 arena; x [B,I,T,D].  Returns (out or None, scores [B,I], gate [B,I], index [B] int32)."""
+    _chk_f32(params, x)
+    B, I, T, D = x.shape
+    out = torch.empty_like(x) if want_out else None
+    scores = torch.empty(B, I, device=x.device, dtype=torch.float32)
+    gate = torch.empty(B, I, device=x.device, dtype=torch.float32)
+    index = torch.empty(B, device=x.device, dtype=torch.int32)
+    w = ws.get(B, I, T, D, with_backward, x.device)
+    L.check(L.load().mrnb_router_forward(_p(params), _p(x), B, I, T, D, prec, _p(out), _p(scores), _p(gate), _p(index),
+                                         _p(w), w.numel(), _stream()), "router_forward")
+    return out, scores, gate, index
+
+
+def router_backward(params, x, gate, dgate_ctc, domain, grads, ws: RouterWorkspace, prec=L.PREC_FP32):
+    _chk_f32(params, x, gate, dgate_ctc, grads)
+    assert domain.dtype == torch.int64
+    B, I, T, D = x.shape
+    taski = torch.empty(1, device=x.device, dtype=torch.float32)
+    w = ws.get(B, I, T, D, True, x.device)
+    L.check(L.load().mrnb_router_backward(_p(params), _p(x), _p(gate), _p(dgate_ctc), _p(domain), B, I, T, D, prec,
+                                          _p(grads), _p(taski), _p(w), w.numel(), _stream()), "router_backward")
+    return taski
+
+
+def dm_router_backward(params, x, d_out, grads, ws: RouterWorkspace, want_dx=True, prec=L.PREC_FP32):
+    _chk_f32(params, x, d_out, grads)
+    B, I, T, D = x.shape
+    dx = torch.empty_like(x) if want_dx else None
+    w = ws.get(B, I, T, D, True, x.device)
+    L.check(L.load().mrnb_dm_router_backward(_p(params), _p(x), _p(d_out), B, I, T, D, prec, _p(grads), _p(dx), _p(w),
+                                             w.numel(), _stream()), "dm_router_backward")
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------ combine / CTC / decode
+def _expert_tables(logits: Sequence[torch.Tensor]):
+    I = len(logits)
+    ptrs = (C.c_void_p * I)()
+    lds = (C.c_long * I)()
+    cs = (C.c_int * I)()
+    for i, z in enumerate(logits):
+        if z.dtype != torch.float32 or z.stride(-1) != 1 or z.stride(0) != z.shape[1] * z.stride(1):
+            raise RuntimeError("expert logits must be fp32 [B,T,C_i] with a dense row layout")
+        ptrs[i] = z.data_ptr()
+        lds[i] = z.stride(1)
+        cs[i] = z.shape[2]
+    return ptrs, lds, cs
+
+
+def gate_combine(logits: Sequence[torch.Tensor], gate: torch.Tensor, targets: Optional[torch.Tensor] = None,
+                 lengths: Optional[torch.Tensor] = None, want_logits=False, want_E=False, want_decode=False):
+    """Fused pad-with-ones + gated sum + row log-sum-exp (+ label gathers, + argmax).  Returns a dict."""
+    _chk_f32(gate)
+    B, T, _ = logits[0].shape
+    I = len(logits)
+    Cmax = logits[-1].shape[2]
+    dev = gate.device
+    ptrs, lds, cs = _expert_tables(logits)
+    r = dict(lse=torch.empty(B, T, device=dev, dtype=torch.float32))
+    ldo = round_up(Cmax, 4)
+    if want_logits:
+        buf = torch.empty(B, T, ldo, device=dev, dtype=torch.float32)
+        r["logits_buf"] = buf
+        r["logits"] = buf[:, :, :Cmax]
+    if want_E:
+        r["E"] = torch.empty(B, T, I, device=dev, dtype=torch.float32)
+    if want_decode:
+        r["amax"] = torch.empty(B, T, device=dev, dtype=torch.int32)
+        r["maxprob"] = torch.empty(B, T, device=dev, dtype=torch.float32)
+    Lmax = 0
+    if targets is not None:
+        assert targets.dtype == torch.int64 and lengths.dtype == torch.int32 and targets.is_contiguous()
+        Lmax = targets.shape[1]
+        r["lpe"] = torch.empty(B, T, Lmax + 1, device=dev, dtype=torch.float32)
+        r["zlab"] = torch.empty(B, T, Lmax + 1, I, device=dev, dtype=torch.float32)
+    L.check(L.load().mrnb_gate_combine(ptrs, lds, cs, I, _p(gate), B, T, _p(r.get("logits_buf")), ldo, _p(r["lse"]),
+                                       _p(r.get("E")), _p(r.get("amax")), _p(r.get("maxprob")), _p(targets), _p(lengths),
+                                       Lmax, _p(r.get("lpe")), _p(r.get("zlab")), _stream()), "gate_combine")
+    return r
+
+
+def ctc_lattice(lpe, targets, lengths, zlab=None, E=None, grad_scale=0.0, want_dgate=False, want_occ=False):
+    B, T, S1 = lpe.shape
+    I = zlab.shape[-1] if zlab is not None else 0
+    dev = lpe.device
+    nll = torch.empty(B, device=dev, dtype=torch.float32)
+    loss = torch.empty(1, device=dev, dtype=torch.float32)
+    dgate = torch.empty(B, I, device=dev, dtype=torch.float32) if want_dgate else None
+    occ = torch.empty(B, T, S1, device=dev, dtype=torch.float32) if want_occ else None
+    L.check(L.load().mrnb_ctc_lattice(_p(lpe), _p(zlab), _p(E), _p(targets), _p(lengths), S1 - 1, B, T, I, float(grad_scale),
+                                      _p(nll), _p(loss), _p(dgate), _p(occ), _stream()), "ctc_lattice")
+    return dict(nll=nll, loss=loss, dgate=dgate, occ=occ)
+
+
+def ctc_dense_grad(logits_view, lse, occ, nll, targets, lengths, grad_scale):
+    B, T, Cc = logits_view.shape
+    grad = torch.empty(B, T, Cc, device=lse.device, dtype=torch.float32)
+    L.check(L.load().mrnb_ctc_dense_grad(_p(logits_view), logits_view.stride(1), _p(lse), _p(occ), _p(nll), _p(targets),
+                                         _p(lengths), targets.shape[1], B, T, Cc, float(grad_scale), _p(grad), Cc, _stream()),
+            "ctc_dense_grad")
+    return grad
+
+
+def greedy_decode(amax, maxprob):
+    B, T = amax.shape
+    ids = torch.empty(B, T, device=amax.device, dtype=torch.int32)
+    lens = torch.empty(B, device=amax.device, dtype=torch.int32)
+    conf = torch.empty(B, device=amax.device, dtype=torch.float32)
+    L.check(L.load().mrnb_greedy_decode(_p(amax), _p(maxprob), B, T, _p(ids), _p(lens), _p(conf), _stream()), "greedy_decode")
+    return ids, lens, conf
+
+
+# ------------------------------------------------------------------------------------------------ optimiser
+def clip_adam(params, grads, exp_avg, exp_avg_sq, lr, step, max_norm=5.0, betas=(0.9, 0.999), eps=1e-8, scratch=None,
+              norm_out=None):
+    _chk_f32(params, grads, exp_avg, exp_avg_sq)
+    if scratch is None:
+        scratch = torch.empty(4096, dtype=torch.uint8, device=params.device)
+    if norm_out is None:
+        norm_out = torch.empty(1, dtype=torch.float32, device=params.device)
+    L.check(L.load().mrnb_clip_adam(_p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), params.numel(), float(lr),
+                                    float(betas[0]), float(betas[1]), float(eps), float(max_norm), int(step), _p(norm_out),
+                                    _p(scratch), _stream()), "clip_adam")
+    return norm_out

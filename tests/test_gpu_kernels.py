@@ -1,0 +1,271 @@
+"""GPU parity tests, building blocks first: every CUDA kernel against the CPU oracle / a torch fp64 statement of the
+same op on the same seeded inputs.  All calls go through the C ABI (mrn_b200.ops -> libmrn_b200.so)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mrn_oracle as O
+from oracle import synth
+from conftest import load_golden, gview, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from mrn_b200 import ops
+    return ops
+
+
+def dev(t):
+    return t.cuda().contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ GEMMs
+@pytest.mark.parametrize("M,N,K,gelu,res", [(256, 192, 64, False, False), (300, 70, 100, True, True),
+                                            (1000, 513, 257, False, True), (64, 6, 1536, False, False)])
+def test_sgemm_matches_fp64(M, N, K, gelu, res):
+    ops = _ops()
+    torch.manual_seed(M + N + K)
+    a, w, b = torch.randn(M, K), torch.randn(N, K) / math.sqrt(K), torch.randn(N)
+    r = torch.randn(M, N) if res else None
+    ref = a.double() @ w.double().T + b.double()
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    if res:
+        ref = ref + r.double()
+    out = ops.linear_f32(dev(a), dev(w), dev(b), dev(r) if res else None, gelu).cpu()
+    assert rel_err(out.numpy(), ref.numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("M,N,K,gelu,res,f32out", [
+    (256, 192, 64, False, False, True),      # qkv of stage 1: one k-block, BN=64 tiles
+    (384, 128, 256, False, True, True),      # proj + residual, BN=128
+    (300, 70, 128, True, False, False),      # M and N tails, bf16 output, GELU
+    (1024, 512, 1024, True, False, False),   # fc1-like, 16 k-blocks: exercises the 4-stage ring twice over
+    (640, 1899, 256, False, False, True),    # classifier head: N not a multiple of anything
+])
+def test_tcgen05_gemm_matches_fp64(M, N, K, gelu, res, f32out):
+    ops = _ops()
+    torch.manual_seed(M * 7 + N)
+    a = torch.randn(M, K).bfloat16()
+    w = (torch.randn(N, K) / math.sqrt(K)).bfloat16()
+    b = torch.randn(N)
+    r = torch.randn(M, N) if res else None
+    ref = a.double() @ w.double().T + b.double()
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    if res:
+        ref = ref + r.double()
+    out = ops.linear_bf16(dev(a), dev(w), dev(b), dev(r) if res else None, gelu, f32out).float().cpu()
+    tol = 2e-5 if f32out else 6e-3       # fp32 accumulate of exact bf16 products; bf16 output rounding = 2^-8
+    assert rel_err(out.numpy(), ref.numpy()) < tol
+
+
+# ------------------------------------------------------------------------------------------------ LN / attention
+@pytest.mark.parametrize("D", [64, 128, 256, 512])
+def test_layernorm(D):
+    ops = _ops()
+    torch.manual_seed(D)
+    x, g, b = torch.randn(37, D) * 3 + 1, torch.randn(D), torch.randn(D)
+    ref = O._ln(x.double(), g.double(), b.double(), 1e-6)
+    out = ops.layernorm(dev(x), dev(g), dev(b), 1e-6).cpu()
+    assert rel_err(out.numpy(), ref.numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("stage,local", [(0, True), (1, True), (1, False), (2, False)])
+def test_svtr_attention(stage, local):
+    ops = _ops()
+    d, heads = O.SVTR_DIMS[stage], O.SVTR_HEADS[stage]
+    H, W = O.SVTR_GRID[stage]
+    N = H * W
+    torch.manual_seed(stage)
+    qkv = torch.randn(3, N, 3 * d)
+    q, k, v = qkv.double().reshape(3, N, 3, heads, 32).permute(2, 0, 3, 1, 4)
+    att = (q * 32 ** -0.5) @ k.transpose(-1, -2)
+    if local:
+        att = att + O.local_mask(H, W, dtype=torch.float64)
+    ref = (torch.softmax(att, -1) @ v).permute(0, 2, 1, 3).reshape(3, N, d)
+    out = ops.svtr_attention(dev(qkv), heads, H, W, local).cpu()
+    assert rel_err(out.numpy(), ref.numpy()) < 3e-6
+
+
+# ------------------------------------------------------------------------------------------------ experts
+def _expert_case(cc, B, seed):
+    sd = synth.synth_state_dict(cc, seed)
+    img, tgt, lens, dom = synth.synth_batch(B, cc, seed)
+    return sd, img, tgt, lens, dom
+
+
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_svtr_experts_fp32_match_oracle(mode):
+    ops = _ops()
+    from mrn_b200 import _lib as L
+    cc, B, seed = (37, 61, 96), 3, 111
+    sd, img, tgt, lens, dom = _expert_case(cc, B, seed)
+    I = len(cc)
+    drop = synth.synth_drop_scales(I, B, O.svtr_drop_path_rates(), seed) if mode == "train" else None
+    with torch.no_grad():
+        o = O.mrn_forward(sd, I, img, True, True, bn_mode="batch" if mode == "train" else "eval", drop_scales=drop)
+    pack = ops.SvtrPack(sd, I, "cuda", L.PREC_FP32)
+    feats, logits = ops.svtr_experts_forward(pack, dev(img), bn_batch_stats=mode == "train", update_running=mode == "train",
+                                             drop_scales=dev(drop) if drop is not None else None, chunk=2)
+    assert rel_err(feats.cpu().numpy(), o["features"].numpy()) < 1e-4
+    for i in range(I):
+        assert rel_err(logits[i].cpu().numpy(), o["preds"][i].numpy()) < 1e-4
+    g = load_golden("svtr_mrn_i3_b3")          # and directly against the reference's own output
+    key = "train_features" if mode == "train" else "features"
+    assert rel_err(gview(feats.cpu(), g), g[key]) < 1e-4
+    if mode == "train":
+        rm = pack.bn_running_stats()[0][0].cpu().numpy()
+        assert np.abs(rm - g["train_bn1_running_mean_e0"]).max() < 1e-5
+
+
+def test_svtr_experts_bf16_within_budget():
+    ops = _ops()
+    from mrn_b200 import _lib as L
+    cc, B, seed = (37, 61, 96), 3, 111
+    sd, img, tgt, lens, dom = _expert_case(cc, B, seed)
+    with torch.no_grad():
+        o = O.mrn_forward(sd, 3, img, True, True)
+    pack = ops.SvtrPack(sd, 3, "cuda", L.PREC_BF16)
+    feats, logits = ops.svtr_experts_forward(pack, dev(img))
+    assert rel_err(feats.cpu().numpy(), o["features"].numpy()) < 2e-2
+    for i in range(3):
+        assert rel_err(logits[i].cpu().numpy(), o["preds"][i].numpy()) < 2e-2      # north-star bf16 tolerance
+
+
+# ------------------------------------------------------------------------------------------------ router
+def _router_arena(sd, I, device="cuda"):
+    ops = _ops()
+    n, off = ops.router_param_offsets(I)
+    arena = torch.zeros(n, dtype=torch.float32)
+    for k, name in enumerate(ops.ROUTER_PARAM_NAMES):
+        arena[off[k]:off[k + 1]] = sd[name].reshape(-1).float()
+    return arena.to(device), off
+
+
+@pytest.mark.parametrize("name", ["dm_router_i3_b2", "dm_router_i6_b1"])
+def test_dm_router_forward_backward(name):
+    ops = _ops()
+    g = load_golden(name)
+    I, B, seed = int(g["I"]), int(g["B"]), int(g["seed"])
+    sd = {k: synth.synth_tensor(seed, k, s) for k, s in synth.router_shapes(I).items()}
+    x = synth.randn(seed, "router_x", (B, I, 64, 256))
+    dy = synth.randn(seed, "router_dy", (B, I, 64, 256))
+    arena, off = _router_arena(sd, I)
+    ws = ops.RouterWorkspace()
+    out, scores, gate, index = ops.router_forward(arena, dev(x), ws, with_backward=True)
+    assert rel_err(gview(out.cpu(), g), g["out"]) < 1e-4
+    sdd = {k: v.double() for k, v in sd.items()}
+    r_ref = O.gate_scores(sdd, O.dm_router(sdd, x.double()))
+    assert rel_err(scores.cpu().numpy(), r_ref.numpy()) < 1e-4
+    assert np.abs(gate.cpu().numpy() - torch.softmax(r_ref, -1).numpy()).max() < 1e-4
+    grads = torch.empty_like(arena)
+    dx = ops.dm_router_backward(arena, dev(x), dev(dy), grads, ws, want_dx=True)
+    assert rel_err(gview(dx.cpu(), g), g["dx"]) < 2e-4
+    gc = grads.cpu()
+    for k, pname in enumerate(ops.ROUTER_PARAM_NAMES):
+        if not pname.startswith("dm_router.0."):
+            continue
+        got = gc[off[k]:off[k + 1]].reshape(sd[pname].shape)
+        assert rel_err(gview(got, g), g["grad." + pname[len("dm_router.0."):]]) < 5e-4, pname
+
+
+# ------------------------------------------------------------------------------------------------ combine / CTC / decode
+def _ragged_logits(cc, B, T, seed, scale=3.0):
+    return [synth.randn(seed, f"z{i}", (B, T, c), scale) for i, c in enumerate(cc)]
+
+
+def _dev_ragged(zs):
+    ops = _ops()
+    out = []
+    for z in zs:
+        ld = ops.round_up(z.shape[2], 4)
+        buf = torch.zeros(z.shape[0], z.shape[1], ld, device="cuda")
+        buf[:, :, :z.shape[2]] = z.cuda()
+        out.append(buf[:, :, :z.shape[2]])
+    return out
+
+
+@pytest.mark.parametrize("cc,B,T", [((37, 61, 96), 5, 64), ((1899, 2224, 3844, 4968, 5041, 5153), 4, 64), ((50,), 3, 63)])
+def test_combine_ctc_decode_match_oracle(cc, B, T):
+    ops = _ops()
+    seed = 5 + len(cc)
+    I = len(cc)
+    zs = _ragged_logits(cc, B, T, seed)
+    gate = torch.softmax(synth.randn(seed, "gate", (B, I), 2.0), -1)
+    _, tgt, lens, _ = synth.synth_batch(B, cc, seed)
+    tgt[0, :3] = torch.tensor([7, 7, 9]); lens[0] = 3           # repeated label
+    if B > 2:
+        lens[2] = 0                                             # empty target
+    logits_ref = O.combine_soft([z.double() for z in zs], gate.double())
+    nll_ref, grad_ref = O.ctc_nll_and_grad(logits_ref, tgt, lens)
+    zd = _dev_ragged(zs)
+    r = ops.gate_combine(zd, dev(gate), dev(tgt), dev(lens), want_logits=True, want_E=True, want_decode=True)
+    assert rel_err(r["logits"].cpu().numpy(), logits_ref.numpy()) < 1e-6
+    assert rel_err(r["lse"].cpu().numpy(), torch.logsumexp(logits_ref, -1).numpy()) < 1e-6
+    pi = 15.0
+    c = ops.ctc_lattice(r["lpe"], dev(tgt), dev(lens), r["zlab"], r["E"], grad_scale=pi / B, want_dgate=True, want_occ=True)
+    assert rel_err(c["nll"].cpu().numpy(), nll_ref.numpy()) < 1e-5
+    loss_ref = float((nll_ref / lens.clamp(min=1)).mean())
+    assert abs(float(c["loss"].cpu()) - loss_ref) / abs(loss_ref) < 1e-5
+    dg_ref = O.gate_grad_shortcut(logits_ref, [z.double() for z in zs], gate, tgt, lens, pi)
+    assert rel_err(c["dgate"].cpu().numpy(), dg_ref.numpy()) < 1e-4
+    # dense gradient (expert-training stage)
+    dense = ops.ctc_dense_grad(r["logits"], r["lse"], c["occ"], c["nll"], dev(tgt), dev(lens), 1.0 / B)
+    scale = (1.0 / (B * lens.clamp(min=1).double())).view(-1, 1, 1)
+    assert rel_err(dense.cpu().numpy(), (grad_ref * scale).numpy()) < 1e-4
+    # decode
+    raw_ref, seqs_ref, conf_ref = O.greedy_decode(logits_ref.float())
+    assert (r["amax"].cpu().long() == raw_ref).all()
+    ids, n, conf = ops.greedy_decode(r["amax"], r["maxprob"])
+    for b in range(B):
+        assert int(n[b]) == len(seqs_ref[b]) and ids[b, :len(seqs_ref[b])].cpu().tolist() == seqs_ref[b]
+    assert rel_err(conf.cpu().numpy(), conf_ref.numpy()) < 1e-4
+
+
+def test_hard_route_and_ones_plateau_tie_break():
+    """Eval route = one-hot gate; a row whose real logits are all < 1 must arg-max onto the FIRST padded column
+    (index C_i), as torch.max does on the reference's ones-padding (modules/model.py:361-364)."""
+    ops = _ops()
+    cc, B, T = (20, 33), 2, 64
+    zs = [-(synth.randn(3, "a", (B, T, 20)).abs()) - 0.1, synth.randn(3, "b", (B, T, 33), 3.0)]
+    index = torch.tensor([0, 1])
+    gate = torch.nn.functional.one_hot(index, 2).float()
+    ref = O.combine_hard(zs, index)
+    r = ops.gate_combine(_dev_ragged(zs), dev(gate), want_logits=True, want_decode=True)
+    assert torch.equal(r["logits"].cpu(), ref)                       # bit exact: no arithmetic on the selected expert
+    assert (r["amax"][0].cpu() == 20).all()                          # plateau hit -> first padded column
+    assert (r["amax"].cpu().long() == ref.max(2)[1]).all()
+
+
+def test_ctc_infeasible_target_is_zeroed():
+    ops = _ops()
+    B, T, Cc = 2, 4, 11
+    z = [synth.randn(1, "z", (B, T, Cc))]
+    tgt = torch.ones(B, 25, dtype=torch.long); tgt[0, :5] = torch.tensor([3, 3, 3, 3, 3]); tgt[1, :2] = torch.tensor([4, 5])
+    lens = torch.tensor([5, 2], dtype=torch.int32)                   # 5 repeated labels need 9 frames > T=4
+    gate = torch.ones(B, 1)
+    r = ops.gate_combine(_dev_ragged(z), dev(gate), dev(tgt), dev(lens), want_E=True)
+    c = ops.ctc_lattice(r["lpe"], dev(tgt), dev(lens), r["zlab"], r["E"], grad_scale=1.0, want_dgate=True)
+    nll_ref, _ = O.ctc_nll_and_grad(z[0].double(), tgt, lens)
+    assert float(c["nll"][0]) == 0.0 and float(c["dgate"][0].abs().max()) == 0.0
+    assert abs(float(c["nll"][1]) - float(nll_ref[1])) < 1e-5
+
+
+def test_clip_adam_matches_oracle():
+    ops = _ops()
+    torch.manual_seed(0)
+    n = 100003
+    p, g = torch.randn(n), torch.randn(n) * 0.3
+    ref_p = {"a": p.clone()}
+    state = dict(step=0, m={}, v={})
+    pd, m, v = dev(p), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for step in range(1, 4):
+        gg = g * step
+        norm_ref = O.clip_and_adam(ref_p, {"a": gg.clone()}, state, lr=5e-4)
+        norm = ops.clip_adam(pd, dev(gg), m, v, 5e-4, step)
+        assert abs(float(norm) - norm_ref) / norm_ref < 1e-5
+        assert (pd.cpu() - ref_p["a"]).abs().max() < 2e-6
