@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py -- MRN-SVTR 6-expert router-training (stage-1) step on N B200s; prints ONE JSON line on rank 0.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference algorithm's CPU path (oracle port) on the host cores
+
+Workload (BASELINE.json configs[3], SURVEY.md §8d cfg 4): SVTR-MRN, I = 6 experts, union charset C_i =
+[1899, 2224, 3844, 4968, 5041, 5153], per-GPU batch 256 (weak scaling), synthetic 32x256x4 crops, one
+`_update_representation` iteration (il_modules/mrn.py:329-371): 6 frozen expert forwards in train mode (BN batch
+statistics + DropPath, reference quirk 4) -> DM-Router -> softmax gate -> gated combine -> CTC -> loss = 15*CTC + CE ->
+router backward -> [NCCL all-reduce] -> clip + Adam.
+
+value  = samples/s with the batch resident in HBM (CUDA events, max over ranks).
+e2e    = same metric through MRN.train_step_stage1 with pinned-host inputs copied H2D and both losses read back D2H
+         every step (what il_modules/mrn.py's loop does).
+roofline / kernel_families = CUDA-event time per kernel family recorded on the launching stream inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CLASS_COUNTS = (1899, 2224, 3844, 4968, 5041, 5153)
+METRIC = "MRN-SVTR 6-expert train samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (config/svtr_mrn.py: batch_size=256)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--chunk", type=int, default=0, help="samples per expert-forward chunk (0 = whole batch)")
+    ap.add_argument("--cpu-sample", type=int, default=32, help="samples per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_opt(precision, chunk):
+    return argparse.Namespace(Transformation="None", FeatureExtraction="SVTR", SequenceModeling="None", Prediction="CTC",
+                              num_fiducial=20, input_channel=4, output_channel=512, hidden_size=256, imgH=32, imgW=256,
+                              batch_max_length=25, lr=5e-4, num_iter=10000, grad_clip=5, exp_name="bench",
+                              precision=precision, drop_path=True, expert_chunk=chunk,
+                              lan_list=["Chinese", "Latin", "Japanese", "Korean", "Arabic", "Bangla"], val_interval=5000,
+                              start_task=0, optimizer="adam", schedule="super")
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_stage1(sample, steps, warmup):
+    """The reference algorithm's CPU path (oracle port, fp32, all host threads) on a bounded sample of the workload."""
+    from oracle import mrn_oracle as O
+    from mrn_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.synth_state_dict(CLASS_COUNTS, 111)
+    img, tgt, lens, dom = synth.synth_batch(sample, CLASS_COUNTS, 111)
+    drop = synth.synth_drop_scales(6, sample, O.svtr_drop_path_rates(), 111)
+    state = dict(step=0, m={}, v={})
+    for _ in range(warmup):
+        O.stage1_step_cpu(sd, 6, state, img, tgt, lens, dom, drop_scales=drop)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.stage1_step_cpu(sd, 6, state, img, tgt, lens, dom, drop_scales=drop)
+    dt = time.perf_counter() - t0
+    return sample * steps / dt, dt / steps * 1000.0, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    sample = args.cpu_sample
+    v, ms, cores = cpu_stage1(sample, max(1, args.steps), max(0, args.warmup))
+    desc = "%d-sample router-training step per iteration (same config, B reduced from 256), fp32, %d threads" % (sample, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "SVTR-MRN 6-expert stage-1 (router-training) step, union charset 5153, 32x256x4 crops",
+                   "per_step_samples": sample, "parallelism": "cpu"},
+        "cpu_baseline": {"value": round(v, 3), "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": round(v, 3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    from mrn_b200 import dist as mdist
+    from mrn_b200 import ops, synth
+    from mrn_b200.il_modules.mrn import MRN, RankLocal, FusedAdam
+    from mrn_b200.modules.model import MRNNet
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: mrn_b200 has no CPU fallback")
+    rank, local_rank, world = mdist.init_from_env("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = args.batch
+    opt = make_opt(args.precision, args.chunk)
+    sd = synth.synth_state_dict(CLASS_COUNTS, 111)
+    net = MRNNet(opt)
+    for c in CLASS_COUNTS:
+        net.update_fc(opt.hidden_size, c)
+        net.build_prediction(opt, c)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev)
+    learner = MRN(opt)
+    learner.model = RankLocal(net)
+    learner.model.train()                               # steady state of the reference loop (quirk 4)
+    for p in net.model.parameters():
+        p.requires_grad = False
+    learner.optimizer = FusedAdam(net, opt.lr, opt.num_iter * 2, grad_clip=opt.grad_clip, schedule="super")
+    mdist.broadcast_(net.router_arena())
+
+    # distinct synthetic batches per rank (seeded); pinned host copies for the e2e leg
+    n_batches = 4
+    host = []
+    for k in range(n_batches):
+        img, tgt, lens, dom = synth.synth_batch(B, CLASS_COUNTS, 1000 + 17 * rank + k)
+        host.append(tuple(t.pin_memory() for t in (img, tgt, lens, dom)))
+    resident = [tuple(t.to(dev) for t in hb) for hb in host]
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+
+    def step_resident(k):
+        img, tgt, lens, dom = resident[k % n_batches]
+        return learner.train_step_stage1(img, tgt, lens, dom)
+
+    def step_e2e(k):
+        img, tgt, lens, dom = (t.to(dev, non_blocking=True) for t in host[k % n_batches])
+        l1, l2 = learner.train_step_stage1(img, tgt, lens, dom)
+        return float(l1), float(l2)                     # D2H read of both losses (the reference logs them)
+
+    for k in range(max(3, args.warmup)):
+        step_resident(k)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region 1: batch resident in HBM
+    mdist.barrier(); torch.cuda.synchronize()
+    ops.reset_launch_count(); ops.profile_reset(); ops.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        loss = step_resident(k)
+    e1.record()
+    mdist.barrier(); torch.cuda.synchronize()
+    ops.profile_enable(False)
+    ms_total = mdist.max_over_ranks(e0.elapsed_time(e1), dev)
+    launches = ops.launch_count()
+    fam = ops.profile_read()
+    # ---- timed region 2: end to end from pinned host memory
+    for k in range(2):
+        step_e2e(k)
+    mdist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        last = step_e2e(k)
+    torch.cuda.synchronize()
+    e2e_ms = mdist.max_over_ranks((time.perf_counter() - t0) * 1000.0, dev)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return
+
+    ms_step = ms_total / args.steps
+    value = B * world * 1000.0 / ms_step
+    e2e_value = B * world * args.steps * 1000.0 / e2e_ms
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    fams = {}
+    for name, f in fam.items():
+        if f["calls"] == 0:
+            continue
+        per_step = f["ms"] / args.steps
+        d = {"ms_per_step": round(per_step, 3), "share": round(f["ms"] / ms_total, 4), "launches_per_step": f["calls"] // args.steps}
+        if f["flops"] > 0 and f["ms"] > 0:
+            d["tflops"] = round(f["flops"] / f["ms"] / 1e9, 2)
+        if f["bytes"] > 0 and f["ms"] > 0:
+            d["gbs"] = round(f["bytes"] / f["ms"] / 1e6, 1)
+        fams[name] = d
+    dom_name = max(fams, key=lambda k: fams[k]["ms_per_step"]) if fams else None
+    roofline = None
+    if dom_name:
+        d, f = fams[dom_name], fam[dom_name]
+        if dom_name in ("tcgen05_gemm", "fp32_gemm", "attention"):
+            # tensor-pipe roofline for the contraction kernels (fp32 CUDA-core kernels are reported against the same
+            # bf16 tensor peak: that is the pipe the work belongs on)
+            roofline = {"kernel": dom_name, "bound": "tensor", "achieved": d.get("tflops"), "peak": tf_peak, "unit": "TFLOP/s",
+                        "frac": round(d.get("tflops", 0.0) / tf_peak, 4), "traffic": None,
+                        "algorithmic_flops_per_step": f["flops"] / args.steps, "peak_source": peak_src + ", sustained"}
+        else:
+            roofline = {"kernel": dom_name, "bound": "hbm", "achieved": d.get("gbs"), "peak": hbm_peak, "unit": "GB/s",
+                        "frac": round(d.get("gbs", 0.0) / hbm_peak, 4), "traffic": None,
+                        "algorithmic_bytes_per_step": f["bytes"] / args.steps, "peak_source": peak_src}
+    ctc_router_ms = sum(fams.get(k, {}).get("ms_per_step", 0.0) for k in ("fp32_gemm", "gated_combine", "ctc_lattice"))
+    out = {
+        "metric": METRIC, "value": round(value, 2), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": "SVTR-MRN 6-expert stage-1 (router-training) step, B=%d/GPU, union charset 5153, 32x256x4 crops, "
+                               "experts frozen in train mode (BN batch stats + DropPath)" % B,
+                   "global_batch": B * world, "parallelism": "dp%d" % world, "expert_chunk": args.chunk,
+                   "l2": "4 rotating input batches; >1 GB of activations streamed per step (>> 126 MB L2), no explicit flush",
+                   "router_precision": "fp32 (CUDA cores)", "expert_precision": args.precision},
+        "e2e": {"value": round(e2e_value, 2), "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
+                "ms_per_step": round(e2e_ms / args.steps, 3)},
+        "gpu_launches": int(launches),
+        "gpu_launches_per_step": int(launches // args.steps),
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernel_families": fams,
+        "ctc_router_ms_per_batch": round(ctc_router_ms, 3),
+        "loss_clf": float(last[0]), "taski_loss": float(last[1]),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, ms, cores = cpu_stage1(args.cpu_sample, 2, 1)
+        out["cpu_baseline"] = {"value": round(v, 3), "unit": "samples/s", "cores": cores, "kind": "port",
+                               "sample": "2 timed router-training steps of %d samples (same config, batch reduced from 256), "
+                                         "oracle port of the reference algorithm, fp32, %d threads" % (args.cpu_sample, cores)}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -43,6 +43,13 @@ const char* mrnb_last_error(void);
 long mrnb_launch_count(void);
 void mrnb_reset_launch_count(void);
 
+/* Optional per-kernel-family timing with CUDA events on the launching stream (bench.py roofline evidence).
+ * Families: 0 tcgen05 GEMM, 1 fp32 GEMM, 2 attention, 3 LayerNorm, 4 patch-embed convs, 5 gated combine, 6 CTC lattice,
+ * 7 router elementwise, 8 optimiser, 9 misc.  mrnb_profile_read synchronises on the recorded events. */
+void mrnb_profile_enable(int on);
+void mrnb_profile_reset(void);
+int mrnb_profile_read(int family, double* ms, long* calls, double* flops, double* bytes);
+
 /* ---------------------------------------------------------------------------------------------------------
  * SVTR expert recognisers, grouped over experts.
  * Replaces  modules/model.py:82-101 (Model_Extractor.forward), :133-148 (Model.forward),

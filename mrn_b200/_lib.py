@@ -40,6 +40,9 @@ _SIGNATURES = {
     "mrnb_last_error": (C.c_char_p, []),
     "mrnb_launch_count": (C.c_long, []),
     "mrnb_reset_launch_count": (None, []),
+    "mrnb_profile_enable": (None, [_i]),
+    "mrnb_profile_reset": (None, []),
+    "mrnb_profile_read": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mrnb_svtr_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mrnb_svtr_experts_forward": (_i, [C.POINTER(MrnbSvtrPack), _vp, _i, _i, _i, _i, _i, _vp, _vp, C.POINTER(_vp),
                                        C.POINTER(_l), _vp, _sz, _vp]),

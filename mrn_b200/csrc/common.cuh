@@ -41,6 +41,17 @@ extern "C" void mrnb_count_launch(int n);   // launch counter (bench.py's gpu_la
     if (rc__ != MRNB_OK) return rc__; \
   } while (0)
 
+// Optional per-kernel-family timing with CUDA events on the launching stream (bench.py roofline); off by default.
+enum { MRNB_PROF_TCGEMM = 0, MRNB_PROF_SGEMM, MRNB_PROF_ATTN, MRNB_PROF_LN, MRNB_PROF_CONV, MRNB_PROF_COMBINE,
+       MRNB_PROF_CTC, MRNB_PROF_ROUTER_EW, MRNB_PROF_OPTIM, MRNB_PROF_MISC, MRNB_PROF_COUNT };
+void mrnb_prof_begin(int family, cudaStream_t st, double flops, double bytes);
+void mrnb_prof_end(int family, cudaStream_t st);
+struct MrnbProfScope {
+  int family; cudaStream_t st;
+  MrnbProfScope(int f, cudaStream_t s, double flops = 0.0, double bytes = 0.0) : family(f), st(s) { mrnb_prof_begin(f, s, flops, bytes); }
+  ~MrnbProfScope() { mrnb_prof_end(family, st); }
+};
+
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------

@@ -399,6 +399,9 @@ extern "C" int mrnb_gate_combine(const float* const* z, const long* ld, const in
   const int C = Ci[n_experts - 1];
   MRNB_CHECK_ARG(!logits || ldo >= C, "gate_combine: ldo < C");
   const int S1 = Lmax + 1;
+  double rb = 0;
+  for (int i = 0; i < n_experts; ++i) rb += (double)Ci[i];
+  MrnbProfScope prof(MRNB_PROF_COMBINE, stream, 0.0, 4.0 * B * T * (rb + (logits ? C : 0)));
 #define MRNB_CASE(N) case N: return launch_combine<N>(P, gate, B, T, C, logits, ldo, lse, E, amax, maxprob, targets, tlen, Lmax, lpe, zlab, S1, stream);
   switch (n_experts) {
     MRNB_CASE(1) MRNB_CASE(2) MRNB_CASE(3) MRNB_CASE(4) MRNB_CASE(5) MRNB_CASE(6) MRNB_CASE(7) MRNB_CASE(8)
@@ -421,6 +424,7 @@ extern "C" int mrnb_ctc_lattice(const float* lpe, const float* zlab, const float
     cudaFuncSetAttribute(ctc_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
+  MrnbProfScope prof(MRNB_PROF_CTC, stream);
   ctc_lattice_kernel<<<cdiv(B, CTC_WARPS), CTC_WARPS * 32, smem, stream>>>(lpe, zlab, E, targets, tlen, Lmax, B, T, S1,
                                                                              n_experts, grad_scale, nll, dgate, occ_col);
   MRNB_CHECK_LAUNCH("ctc_lattice_kernel");

@@ -152,6 +152,8 @@ int mrnb_sgemm(const MrnbGemm& p, cudaStream_t st) {
   MRNB_CHECK_ARG(p.A && p.B && p.C && p.M > 0 && p.N > 0 && p.K > 0 && p.batch > 0, "sgemm: bad argument");
   MRNB_CHECK_ARG(p.splitk <= 1 || p.batch == 1, "sgemm: split-K only for batch == 1");
   const int z = p.splitk > 1 ? p.splitk : p.batch;
+  MrnbProfScope prof(MRNB_PROF_SGEMM, st, 2.0 * p.M * p.N * p.K * p.batch,
+                     4.0 * p.batch * ((double)p.M * p.K + (double)p.N * p.K + (double)p.M * p.N));
   if (p.M >= 96 && p.N >= 96) {
     dim3 grid(cdiv(p.N, 128), cdiv(p.M, 128), z);
     sgemm_kernel<128, 128, 8, 8><<<grid, 256, 0, st>>>(p);

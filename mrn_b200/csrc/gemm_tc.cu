@@ -291,6 +291,9 @@ int mrnb_tc_gemm(const MrnbTcGemm& p, cudaStream_t st) {
   MRNB_CHECK_ARG(p.A && p.W && p.out && p.M > 0 && p.N > 0 && p.K > 0 && p.groups > 0, "tc_gemm: bad argument");
   MRNB_CHECK_ARG(p.K % BK == 0, "tc_gemm: K=%d must be a multiple of %d", p.K, BK);
   MRNB_CHECK_ARG(!p.res || p.out_f32, "tc_gemm: residual needs an fp32 output");
+  MrnbProfScope prof(MRNB_PROF_TCGEMM, st, 2.0 * p.M * p.N * p.K * p.groups,
+                     (double)p.groups * (2.0 * p.M * p.K + 2.0 * p.N * p.K + (double)p.M * p.N * (p.out_f32 ? 4 : 2) +
+                                         (p.res ? 4.0 * p.M * p.N : 0.0)));
   const bool wide = p.N >= 128 && (p.N % 128 == 0 || p.N > 256);
   if (wide) return p.out_f32 ? launch_tc<128, true>(p, st) : launch_tc<128, false>(p, st);
   return p.out_f32 ? launch_tc<64, true>(p, st) : launch_tc<64, false>(p, st);

@@ -64,6 +64,7 @@ template <typename OT>
 int launch_layernorm(const float* x, long x_gs, OT* y, long y_gs, const float* gamma, const float* beta, long rows,
                      long rows_per_group, int D, float eps, cudaStream_t st) {
   const int grid = cdiv(rows, 8);
+  MrnbProfScope prof(MRNB_PROF_LN, st, 0.0, (double)rows * D * (4 + sizeof(OT)));
   switch (D) {
     case 64: layernorm_kernel<OT, 64><<<grid, 256, 0, st>>>(x, x_gs, y, y_gs, gamma, beta, rows, rows_per_group, eps); break;
     case 128: layernorm_kernel<OT, 128><<<grid, 256, 0, st>>>(x, x_gs, y, y_gs, gamma, beta, rows, rows_per_group, eps); break;
@@ -463,6 +464,7 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
   if (bn_batch_stats) {
     cudaMemsetAsync(stats, 0, (size_t)I * 96 * 2 * sizeof(double), st);
   }
+  mrnb_prof_begin(MRNB_PROF_CONV, st, 0.0, 0.0);
   conv0_kernel<<<dim3(16, B, I), 128, 0, st>>>(image, P.p[MRNB_P_CONV0_W], P.p[MRNB_P_CONV0_B], conv0,
                                                 bn_batch_stats ? st0 : nullptr, B);
   MRNB_CHECK_LAUNCH("conv0_kernel");
@@ -487,6 +489,7 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
     embed_kernel<<<dim3(cdiv(per_expert / 4, 256), I), 256, 0, st>>>(conv1, ss1, P.p[MRNB_P_POS_EMBED], xall, per_expert);
     MRNB_CHECK_LAUNCH("embed_kernel");
   }
+  mrnb_prof_end(MRNB_PROF_CONV, st);
 
   static const int DIMS[3] = {64, 128, 256}, DEPTH[3] = {3, 6, 3}, HEADS[3] = {2, 4, 8}, GH[3] = {8, 4, 2};
   static const int OUTS[3] = {128, 256, 512};
@@ -525,6 +528,15 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
         {
           const size_t smem = (size_t)2 * N * KV_LD * sizeof(float);
           dim3 grid(I * bc, heads);
+          double pairs = (double)N * N;
+          if (local) {
+            double sh = 0, sw = 0;
+            for (int h = 0; h < H; ++h) sh += (h + 3 < H ? h + 3 : H - 1) - (h - 3 > 0 ? h - 3 : 0) + 1;
+            for (int w2 = 0; w2 < Wd; ++w2) sw += (w2 + 5 < Wd ? w2 + 5 : Wd - 1) - (w2 - 5 > 0 ? w2 - 5 : 0) + 1;
+            pairs = sh * sw;
+          }
+          MrnbProfScope prof(MRNB_PROF_ATTN, st, 4.0 * 32 * pairs * heads * I * bc,
+                             (double)I * bc * N * d * 4 * sizeof(AT));
           if (local) attention_kernel<AT, true><<<grid, N, smem, st>>>(qkv, att, N, d, heads, H, Wd);
           else attention_kernel<AT, false><<<grid, N, smem, st>>>(qkv, att, N, d, heads, H, Wd);
           MRNB_CHECK_LAUNCH("attention_kernel");

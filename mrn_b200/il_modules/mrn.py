@@ -1,0 +1,315 @@
+"""MRN learner: the reference's il_modules/mrn.py API (MRN(opt).incremental_train / _update_representation / val /
+test / after_task / change_model / build_model) driving the CUDA path.
+
+What runs where
+  * stage 1 (router training, il_modules/mrn.py:298-384) -- the north-star hot path -- is one fused device step:
+    grouped frozen experts -> DM-Router -> gate -> fused combine + CTC -> analytic gate gradient -> router backward
+    -> [NCCL all-reduce of the gradient arena] -> clip + Adam.  No autograd graph, no host sync inside the step.
+  * validation (test.py:139-279) uses the hard route + device-side greedy decode (one D2H copy per batch).
+  * stage 0 (training a new expert end to end, il_modules/mrn.py:225-279) needs the expert backward, which is the
+    "next" row of SURVEY.md §8(f)3: it raises NotImplementedError here rather than falling back to PyTorch.
+Host-side schedule / logging logic follows il_modules/base.py.
+"""
+import math
+import os
+import time
+
+import torch
+
+from .. import dist as mdist
+from .. import ops
+from ..modules.model import MRNNet
+from ..utils import Averager, CTCLabelConverter
+
+
+def one_cycle_lr(step, total_steps, max_lr, div_factor=20.0, final_div_factor=1000.0, pct_start=0.3):
+    """torch.optim.lr_scheduler.OneCycleLR (cosine, two phases) as configured at il_modules/mrn.py:77-84; `step` is the
+    number of scheduler.step() calls made so far."""
+    initial = max_lr / div_factor
+    min_lr = initial / final_div_factor
+    end1 = float(pct_start * total_steps) - 1
+    end2 = total_steps - 1
+
+    def cos(a, b, pct):
+        return b + (a - b) / 2.0 * (math.cos(math.pi * pct) + 1)
+    if step <= end1:
+        return cos(initial, max_lr, step / end1)
+    return cos(max_lr, min_lr, (step - end1) / (end2 - end1))
+
+
+def edit_distance(a, b):
+    prev = list(range(len(b) + 1))
+    for i, ca in enumerate(a, 1):
+        cur = [i]
+        for j, cb in enumerate(b, 1):
+            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
+        prev = cur
+    return prev[-1]
+
+
+class RankLocal(torch.nn.Module):
+    """Stand-in for nn.DataParallel in the reference (il_modules/mrn.py:106,133): exposes `.module`, forwards calls and
+    prefixes state_dict keys with `module.` so reference checkpoints load strict=True.  Parallelism is one process
+    per GPU (mrn_b200.dist), not threads in one process."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, *a, **k):
+        return self.module(*a, **k)
+
+
+class FusedAdam:
+    """Adam + grad-norm clip over the router arena (fused kernel) with the reference's OneCycleLR bookkeeping
+    (built for num_iter * the steps, il_modules/mrn.py:52-88)."""
+
+    def __init__(self, net: MRNNet, lr, total_steps, grad_clip=5.0, schedule="super"):
+        self.net = net
+        self.max_lr = lr
+        self.total_steps = total_steps
+        self.grad_clip = grad_clip
+        self.schedule = schedule
+        arena = net.router_arena()
+        self.exp_avg = torch.zeros_like(arena)
+        self.exp_avg_sq = torch.zeros_like(arena)
+        self.scratch = torch.empty(4096, dtype=torch.uint8, device=arena.device)
+        self.norm = torch.zeros(1, dtype=torch.float32, device=arena.device)
+        self.steps = 0
+        self.param_groups = [{"lr": self.current_lr()}]
+
+    def current_lr(self):
+        if "super" in self.schedule:
+            return one_cycle_lr(self.steps, self.total_steps, self.max_lr)
+        return self.max_lr
+
+    def step(self):
+        lr = self.current_lr()
+        self.steps += 1
+        ops.clip_adam(self.net.router_arena(), self.net.router_grad_arena(), self.exp_avg, self.exp_avg_sq, lr, self.steps,
+                      max_norm=self.grad_clip, scratch=self.scratch, norm_out=self.norm)
+        self.param_groups[0]["lr"] = self.current_lr()
+
+
+class MRN(object):
+    def __init__(self, opt):
+        self.opt = opt
+        self.device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+        if self.device is None:
+            raise RuntimeError("mrn_b200.il_modules.mrn.MRN needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.model = MRNNet(opt)
+        self._known_classes = 0
+        self._total_classes = 0
+        self._old_network = None
+        self.optimizer = None
+        self.character = None
+        self.converter = None
+        self.pi = 15
+
+    # ---- reference plumbing ------------------------------------------------------------------------
+    @property
+    def net(self) -> MRNNet:
+        return self.model.module if isinstance(self.model, RankLocal) else self.model
+
+    def after_task(self):
+        self.model = self.net
+        self._known_classes = self._total_classes
+        self._old_network = None       # the reference keeps a frozen deepcopy that MRN never reads again (mrn.py:42)
+
+    def build_converter(self):
+        converter = CTCLabelConverter(self.character, device=self.device)
+        self._total_classes = len(converter.character)
+        return converter
+
+    def build_criterion(self, reduction="mean"):
+        return "ctc-mean-zero-infinity"      # fused in mrnb_ctc_lattice (il_modules/base.py:131)
+
+    def change_model(self):
+        self.model = self.net
+        self.model.update_fc(self.opt.hidden_size, self._total_classes)
+        self.model.build_prediction(self.opt, self._total_classes)
+        self.model = RankLocal(self.model).to(self.device)
+        self.model.train()
+
+    def build_model(self):
+        self.model.build_fc(self.opt.hidden_size, self._total_classes)
+        self.model.build_prediction(self.opt, self._total_classes)
+        for name, param in self.model.named_parameters():       # il_modules/mrn.py:117-130
+            try:
+                if "bias" in name:
+                    torch.nn.init.constant_(param, 0.0)
+                elif "weight" in name:
+                    torch.nn.init.kaiming_normal_(param)
+            except Exception:
+                if "weight" in name:
+                    param.data.fill_(1)
+        self.model = RankLocal(self.model).to(self.device)
+        self.model.train()
+
+    def count_param(self):
+        return [p for p in self.model.parameters() if p.requires_grad]
+
+    def write_log(self, line):
+        d = f"./saved_models/{self.opt.exp_name}"
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "log_train.txt"), "a") as f:
+            f.write(line)
+
+    def build_custom_optimizer(self, filtered_parameters=None, optimizer="adam", schedule="super", scale=1.0, the=2):
+        if optimizer != "adam":
+            raise NotImplementedError("the fused optimiser implements Adam (config/svtr_mrn.py optimizer='adam')")
+        self.optimizer = FusedAdam(self.net, self.opt.lr * scale, self.opt.num_iter * the,
+                                   grad_clip=self.opt.grad_clip, schedule=schedule)
+        self.scheduler = self.optimizer
+
+    # ---- training ------------------------------------------------------------------------------------
+    def incremental_train(self, taski, character, train_loader, valid_loader):
+        self.character = character
+        self.converter = self.build_converter()
+        if taski > 0:
+            self.change_model()
+        else:
+            self.criterion = self.build_criterion()
+            self.build_model()
+        if taski > 0:
+            for i in range(taski):
+                for p in self.net.model[i].parameters():
+                    p.requires_grad = False
+        self._train(0, taski, train_loader, valid_loader, step=0)
+        if taski > 0:
+            self._train(0, taski, train_loader, valid_loader, step=1)
+
+    def _train(self, start_iter, taski, train_loader, valid_loader, step=0):
+        if self.opt.start_task > taski + step * 0.5:
+            name = self.opt.lan_list[taski]
+            path = f"./saved_models/{self.opt.exp_name}/{name}_{taski}_{step}_best_score.pth"
+            self.model.load_state_dict(torch.load(path, map_location=self.device), strict=True)
+            return
+        if taski == 0 or step == 0:
+            self._init_train(start_iter, taski, train_loader, valid_loader, cross=False)
+        else:
+            self._update_representation(start_iter, taski, train_loader, valid_loader)
+
+    def _init_train(self, start_iter, taski, train_loader, valid_loader, cross=False):
+        raise NotImplementedError(
+            "stage-0 expert training (il_modules/mrn.py:225-279) needs the SVTR expert backward, the 'next' row of "
+            "SURVEY.md §8(f)3; load stage-0 checkpoints with opt.start_task instead.  No PyTorch fallback.")
+
+    def update_step1(self, start_iter, taski, train_loader, valid_loader):
+        self._init_train(start_iter, taski, train_loader, valid_loader, cross=False)
+
+    def train_step_stage1(self, image, labels_index, labels_length, indexs, drop_scales=None):
+        """One router-training iteration (il_modules/mrn.py:338-371) entirely on the device.
+        image [B,4,32,256] fp32, labels_index [B,25] int64 (pad 1), labels_length [B] int32, indexs [B] int64.
+        Returns (loss_clf, taski_loss) as 1-element device tensors."""
+        net = self.net
+        B = image.shape[0]
+        r = net.route_and_combine(image, is_train=True, want_logits=False, targets=labels_index, lengths=labels_length,
+                                  want_E=True, with_backward=True, drop_scales=drop_scales)
+        c = ops.ctc_lattice(r["lpe"], labels_index, labels_length, r["zlab"], r["E"], grad_scale=float(self.pi) / B,
+                            want_dgate=True)
+        grads = net.router_grad_arena()
+        taski_loss = ops.router_backward(net.router_arena(), r["features"], r["gate"], c["dgate"], indexs, grads, net._rws)
+        mdist.allreduce_mean_(grads)                     # the ONE exchange step (replaces nn.DataParallel)
+        self.optimizer.step()                            # clip_grad_norm_(5) + Adam + OneCycle
+        return c["loss"], taski_loss
+
+    def _update_representation(self, start_iter, taski, train_loader, valid_loader, pi=15):
+        self.pi = pi
+        train_loss_avg, train_taski_loss_avg = Averager(), Averager()
+        for p in self.net.model.parameters():
+            p.requires_grad = False
+        self.build_custom_optimizer(None, optimizer="adam", schedule="super", scale=1, the=2)
+        start_time = time.time()
+        best_score = -1
+        n_iter = int(self.opt.num_iter // 2)
+        for iteration in range(start_iter + 1, n_iter + 1):
+            image_tensors, labels, indexs = train_loader.get_batch2()
+            indexs = torch.as_tensor(indexs, dtype=torch.long).reshape(-1).to(self.device, non_blocking=True)
+            image = image_tensors.to(self.device, non_blocking=True)
+            labels_index, labels_length = self.converter.encode(labels, batch_max_length=self.opt.batch_max_length)
+            loss_clf, taski_loss = self.train_step_stage1(image, labels_index, labels_length, indexs)
+            train_loss_avg.add(loss_clf)
+            train_taski_loss_avg.add(taski_loss)
+            if iteration % (self.opt.val_interval // 5) == 0 or iteration == n_iter or iteration == 1:
+                self.val(valid_loader, self.opt, best_score, start_time, iteration, train_loss_avg, train_taski_loss_avg,
+                         taski, step=1, val_choose="TF")
+                train_loss_avg.reset()
+                train_taski_loss_avg.reset()
+
+    # ---- evaluation ----------------------------------------------------------------------------------
+    def infer_batch(self, image, val_choose="TF", labels_index=None, labels_length=None):
+        """Hard-routed (TF) or last-expert (FF) inference + device-side greedy decode.
+        Returns dict(ids, lens, conf, index, loss) -- ids compact [B,T] (-1 padded)."""
+        net = self.net
+        if val_choose == "FF":
+            out = net(image, cross=False, is_train=False)
+            gate = torch.ones(image.shape[0], 1, device=image.device)
+            r = ops.gate_combine([out["logits"]], gate, labels_index, labels_length, want_decode=True)
+            index = None
+        else:
+            r = net.route_and_combine(image, is_train=False, want_logits=False, targets=labels_index, lengths=labels_length,
+                                      want_decode=True)
+            index = r["index"]
+        loss = None
+        if labels_index is not None:
+            loss = ops.ctc_lattice(r["lpe"], labels_index, labels_length)["loss"]
+        ids, lens, conf = ops.greedy_decode(r["amax"], r["maxprob"])
+        return dict(ids=ids, lens=lens, conf=conf, index=index, loss=loss)
+
+    def validation(self, eval_loader, val_choose="TF"):
+        """test.py:139-279 with the decode / confidence on the device."""
+        n_correct, norm_ED, length_of_data, infer_time = 0, 0.0, 0, 0.0
+        valid_loss_avg = Averager()
+        preds_str, confidence, labels = [], [], []
+        for image_tensors, labels in eval_loader:
+            bs = image_tensors.size(0)
+            length_of_data += bs
+            image = image_tensors.to(self.device, non_blocking=True)
+            labels_index, labels_length = self.converter.encode(labels, batch_max_length=self.opt.batch_max_length)
+            t0 = time.time()
+            r = self.infer_batch(image, val_choose, labels_index, labels_length)
+            preds_str = self.converter.decode_compact(r["ids"], r["lens"])       # the batch's single D2H sync
+            infer_time += time.time() - t0
+            valid_loss_avg.add(r["loss"])
+            confidence = r["conf"].cpu().tolist()
+            for gt, prd in zip(labels, preds_str):
+                if getattr(self.opt, "NED", True):
+                    if len(gt) == 0 or len(prd) == 0:
+                        norm_ED += 0
+                    elif len(gt) > len(prd):
+                        norm_ED += 1 - edit_distance(prd, gt) / len(gt)
+                    else:
+                        norm_ED += 1 - edit_distance(prd, gt) / len(prd)
+                if prd == gt:
+                    n_correct += 1
+        n = max(length_of_data, 1)
+        return (valid_loss_avg.val(), n_correct / float(n) * 100, norm_ED / float(n) * 100, preds_str, confidence, labels,
+                infer_time, length_of_data)
+
+    def val(self, valid_loader, opt, best_score, start_time, iteration, train_loss_avg, train_taski_loss_avg, taski, step,
+            val_choose="val"):
+        self.model.eval()
+        t0 = time.time()
+        (valid_loss, current_score, ned_score, preds, confidence_score, labels, infer_time, n) = \
+            self.validation(valid_loader, val_choose=val_choose)
+        self.model.train()                    # reference quirk 4: puts frozen experts back in train mode (mrn.py:401)
+        if current_score > best_score:
+            best_score = current_score
+            os.makedirs(f"./saved_models/{opt.exp_name}", exist_ok=True)
+            if mdist.env_world()[0] == 0:
+                torch.save(self.model.state_dict(),
+                           f"./saved_models/{opt.exp_name}/{opt.lan_list[taski]}_{taski}_{step}_best_score.pth")
+        lr = self.optimizer.param_groups[0]["lr"] if self.optimizer else 0.0
+        log = (f"\n[{iteration}/{opt.num_iter}] Train_loss_clf: {train_loss_avg.val():0.5f}, Valid_loss: {valid_loss:0.5f} \n "
+               + (f'{"":9s}Train_taski_loss: {train_taski_loss_avg.val():0.5f}\n' if train_taski_loss_avg is not None else "")
+               + f'{"":9s}Current_score: {current_score:0.2f}, Ned_score: {ned_score:0.2f}\n'
+               + f'{"":9s}Current_lr: {lr:0.7f}, Best_score: {best_score:0.2f}\n'
+               + f'{"":9s}Infer_time: {infer_time:0.2f},     Elapsed_time: {(time.time() - t0) / max(n, 1) * 1000:0.2f}\n')
+        print(log)
+        self.write_log(log + "\n")
+        return current_score
+
+    def test(self, AlignCollate_valid, valid_datas, best_scores, ned_scores, taski, val_choose="test"):
+        raise NotImplementedError("benchmark evaluation needs the LMDB datasets (data/dataset.py), out of scope of the "
+                                  "hot path (SURVEY.md §8f.2); use MRN.validation(loader) with any (images, labels) iterable")

@@ -1,0 +1,320 @@
+"""MRNNet / Model / Model_Extractor with the reference's constructor arguments, methods, attribute names and
+state_dict keys (modules/model.py:17-199,314-496), computing through the CUDA library.
+
+Scope: FeatureExtraction="SVTR", SequenceModeling="None", Prediction="CTC", Transformation="None"
+(config/svtr_mrn.py).  Other backbones raise NotImplementedError -- there is no PyTorch fallback.
+
+The nn.Module tree exists to own parameters under the reference's names (checkpoints load strict=True,
+il_modules/mrn.py:190,465).  Compute never runs per module:
+  * experts: one grouped launch sequence over all experts (ops.svtr_experts_forward) fed by an expert-stacked
+    SvtrPack that is rebuilt when expert parameters change;
+  * router: route / channel_route / dm_router parameters are views into ONE flat fp32 arena (also the gradient,
+    Adam and NCCL all-reduce layout).
+"""
+import copy
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+from .. import ops
+from .dm_router import DM_Router
+from .svtr import SVTR_FeatureExtractor
+
+
+def _require_svtr_ctc(opt):
+    if opt.FeatureExtraction != "SVTR" or opt.SequenceModeling == "BiLSTM" or opt.Prediction != "CTC" \
+            or opt.Transformation not in ("None", None):
+        raise NotImplementedError(
+            "mrn_b200 implements the SVTR / None / CTC hot path (config/svtr_mrn.py); got %s/%s/%s/%s. "
+            "No PyTorch fallback is provided." % (opt.Transformation, opt.FeatureExtraction, opt.SequenceModeling, opt.Prediction))
+
+
+class Model_Extractor(nn.Module):
+    """modules/model.py:17-101 (parameter holder)."""
+
+    def __init__(self, opt):
+        super().__init__()
+        _require_svtr_ctc(opt)
+        self.opt = opt
+        self.stages = {"Trans": opt.Transformation, "Feat": opt.FeatureExtraction, "Seq": opt.SequenceModeling,
+                       "Pred": opt.Prediction}
+        self.FeatureExtraction = SVTR_FeatureExtractor(opt.input_channel, opt.output_channel)
+        self.FeatureExtraction_output = opt.output_channel
+        self.SequenceModeling = nn.Sequential(nn.Linear(self.FeatureExtraction_output, opt.hidden_size))
+        self.SequenceModeling_output = opt.hidden_size
+
+
+class Model(nn.Module):
+    """One expert recogniser (modules/model.py:105-199)."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.model = Model_Extractor(opt)
+        self.SequenceModeling_output = self.model.SequenceModeling_output
+        self.stages = {"Pred": opt.Prediction}
+        self.fc = None
+        self.Prediction = None
+        self._solo: Optional["MRNNet"] = None
+
+    def new_fc(self, hidden_size, nb_classes):
+        self.fc = nn.Linear(hidden_size, nb_classes)
+
+    def update_fc(self, hidden_size, nb_classes, device=None):
+        fc = nn.Linear(hidden_size, nb_classes)
+        if self.fc is not None:
+            nb_output = self.fc.out_features
+            fc.weight.data[:nb_output] = copy.deepcopy(self.fc.weight.data)
+            fc.bias.data[:nb_output] = copy.deepcopy(self.fc.bias.data)
+        self.fc = fc
+
+    def build_prediction(self, opt, num_class):
+        if opt.Prediction != "CTC":
+            raise NotImplementedError("only the CTC head is implemented")
+        self.Prediction = self.fc          # same object: state_dict carries fc.* and Prediction.* (model.py:181)
+
+    def weight_align(self, increment):
+        weights = self.fc.weight.data
+        newnorm = torch.norm(weights[-increment:, :], p=2, dim=1)
+        oldnorm = torch.norm(weights[:-increment, :], p=2, dim=1)
+        gamma = torch.mean(oldnorm) / torch.mean(newnorm)
+        self.fc.weight.data[-increment:, :] *= gamma
+
+    def forward(self, image, text=None, is_train=True):
+        """-> {"predict": [B,T,C], "feature": [B,T,256]} (modules/model.py:133-148) via a single-expert pack."""
+        feats, logits = _experts_forward([self], image, self.opt, train_mode=self.training)
+        return {"predict": logits[0], "feature": feats[:, 0]}
+
+    def copy(self):
+        return copy.deepcopy(self)
+
+    def freeze(self):
+        for p in self.parameters():
+            p.requires_grad = False
+        self.eval()
+        return self
+
+
+# ------------------------------------------------------------------------------------------------
+class _PackCache:
+    """SvtrPack keyed by the experts' parameter versions (rebuilt after an optimizer step / load_state_dict)."""
+
+    def __init__(self):
+        self.key = None
+        self.pack: Optional[ops.SvtrPack] = None
+
+    def get(self, experts: List[Model], device, prec):
+        # parameters only: BN running statistics are owned by the pack between checkpoints (see _sync_bn)
+        key = (prec, str(device), tuple(id(m) for m in experts),
+               sum(int(p._version) for m in experts for p in m.parameters()))
+        if key != self.key:
+            sd = {}
+            for i, m in enumerate(experts):
+                for k, v in m.state_dict().items():
+                    sd[f"model.{i}.{k}"] = v
+            self.pack = ops.SvtrPack(sd, len(experts), device, prec)
+            self.key = key
+        return self.pack
+
+
+_solo_cache = _PackCache()
+
+
+def _precision(opt):
+    p = getattr(opt, "precision", "fp32")
+    return L.PREC_BF16 if str(p).lower() in ("bf16", "bfloat16") else L.PREC_FP32
+
+
+def _experts_forward(experts, image, opt, train_mode, cache=None, drop_scales=None, want_logits=True, chunk=None):
+    if not image.is_cuda:
+        raise RuntimeError("mrn_b200 needs CUDA tensors: there is no CPU fallback")
+    cache = cache or _solo_cache
+    pack = cache.get(experts, image.device, _precision(opt))
+    if chunk is None:
+        chunk = int(getattr(opt, "expert_chunk", 0) or 0)
+    if train_mode and drop_scales is None and getattr(opt, "drop_path", True):
+        drop_scales = sample_drop_scales(len(experts), image.shape[0], experts[0].model.FeatureExtraction.ConvNet.drop_path_rates(),
+                                         image.device)
+    feats, logits = ops.svtr_experts_forward(pack, image.contiguous().float(), bn_batch_stats=train_mode,
+                                             update_running=train_mode, drop_scales=drop_scales, chunk=chunk,
+                                             want_logits=want_logits)
+    if train_mode:
+        pack.bn_dirty = True
+        if cache is _solo_cache:
+            _writeback_bn(experts, pack)
+    return feats, logits
+
+
+def sample_drop_scales(n_experts, B, rates, device, generator=None):
+    """DropPath multipliers [I,12,2,B]: Bernoulli(keep)/keep per sample, block and branch (modules/svtr.py:7-22)."""
+    rates_t = torch.tensor(rates, dtype=torch.float32, device=device).view(1, -1, 1, 1)
+    u = torch.rand(n_experts, len(rates), 2, B, device=device, generator=generator)
+    keep = (u >= rates_t).float()
+    return (keep / (1.0 - rates_t)).contiguous()
+
+
+def _writeback_bn(experts, pack):
+    """Train-mode forwards update BN running statistics inside the pack; mirror them into the module buffers so
+    state_dict() / checkpoints see what nn.BatchNorm2d in .train() would have produced (reference quirk 4)."""
+    m0, v0, m1, v1 = pack.bn_running_stats()
+    with torch.no_grad():
+        for i, m in enumerate(experts):
+            proj = m.model.FeatureExtraction.ConvNet.patch_embed.proj
+            for bn, mean, var in ((proj[1], m0, v0), (proj[4], m1, v1)):
+                bn.running_mean.data = mean[i].clone()
+                bn.running_var.data = var[i].clone()
+                bn.num_batches_tracked += 1
+    pack.bn_dirty = False
+
+
+class MRNNet(nn.Module):
+    """Multiplexed routing network (modules/model.py:314-496)."""
+
+    def __init__(self, opt):
+        super().__init__()
+        _require_svtr_ctc(opt)
+        self.model = nn.ModuleList()
+        self.out_dim = None
+        self.fc = None
+        self.opt = opt
+        self.task_sizes = []
+        self.patch = 64                      # SVTR (modules/model.py:324)
+        self.router = "dm-router"
+        self.layer_num = 1
+        self.beta = 1
+        self._cache = _PackCache()
+        self._arena: Optional[torch.Tensor] = None
+        self._grad_arena: Optional[torch.Tensor] = None
+        self._rws = ops.RouterWorkspace()
+
+    # -- reference API ---------------------------------------------------------------------------
+    @property
+    def feature_dim(self):
+        return 0 if self.out_dim is None else self.out_dim * len(self.model)
+
+    def build_fc(self, hidden_size, nb_classes):
+        self.update_fc(hidden_size, nb_classes)
+
+    def update_fc(self, hidden_size, nb_classes):
+        """Adds an expert and REBUILDS the router for the new expert count (modules/model.py:428-452)."""
+        self.model.append(Model(self.opt))
+        self.model[-1].new_fc(hidden_size, nb_classes)
+        if self.out_dim is None:
+            self.out_dim = self.model[-1].SequenceModeling_output
+        self.route = nn.Linear(self.patch, 1)
+        self.channel_route = nn.Linear(self.feature_dim, len(self.model))
+        block = DM_Router(self.out_dim, self.out_dim * 2, self.patch, len(self.model))
+        self.dm_router = nn.Sequential(*[block for _ in range(self.layer_num)])
+        self._arena = None
+        self._grad_arena = None
+
+    def build_prediction(self, opt, num_class):
+        self.model[-1].build_prediction(opt, num_class)
+
+    def load_fc(self, input, output):
+        fc = nn.Linear(input, output)
+        if self.channel_route is not None:
+            nb_output = self.channel_route.out_features
+            fc.weight.data[:nb_output, :self.feature_dim - self.out_dim] = copy.deepcopy(self.channel_route.weight.data)
+            fc.bias.data[:nb_output] = copy.deepcopy(self.channel_route.bias.data)
+        self.fc = fc
+
+    def copy(self):
+        return copy.deepcopy(self)
+
+    def freeze(self):
+        for p in self.parameters():
+            p.requires_grad = False
+        self.eval()
+        return self
+
+    def softargmax1d(self, input, beta=5):
+        return nn.functional.softmax(beta * input, dim=-1)
+
+    def extract_vector(self, x):
+        feats, _ = _experts_forward(list(self.model), x, self.opt, self._experts_train_mode(), self._cache, want_logits=False)
+        return feats.permute(0, 2, 1, 3).reshape(x.shape[0], self.patch, -1)
+
+    # -- router arena ----------------------------------------------------------------------------
+    def router_parameters(self):
+        sd = dict(self.named_parameters())
+        return [sd[n] for n in ops.ROUTER_PARAM_NAMES]
+
+    def router_arena(self, device=None):
+        """Flat fp32 arena holding every router parameter (C-ABI order); parameters become views into it."""
+        params = self.router_parameters()
+        device = torch.device(device) if device is not None else params[0].device
+        n, off = ops.router_param_offsets(len(self.model), self.patch, self.out_dim)
+        ok = self._arena is not None and self._arena.device == device and all(
+            p.data_ptr() == self._arena.data_ptr() + 4 * off[k] for k, p in enumerate(params))
+        if not ok:
+            arena = torch.empty(n, dtype=torch.float32, device=device)
+            for k, p in enumerate(params):
+                arena[off[k]:off[k + 1]] = p.data.reshape(-1).to(device)
+                p.data = arena[off[k]:off[k + 1]].view(p.shape)
+            self._arena = arena
+            self._grad_arena = None
+        return self._arena
+
+    def router_grad_arena(self):
+        arena = self.router_arena()
+        if self._grad_arena is None:
+            n, off = ops.router_param_offsets(len(self.model), self.patch, self.out_dim)
+            self._grad_arena = torch.zeros_like(arena)
+            for k, p in enumerate(self.router_parameters()):
+                p.grad = self._grad_arena[off[k]:off[k + 1]].view(p.shape)
+        return self._grad_arena
+
+    def _sync_bn(self):
+        pack = self._cache.pack
+        if pack is not None and getattr(pack, "bn_dirty", False) and pack.n_experts == len(self.model):
+            _writeback_bn(list(self.model), pack)
+
+    def state_dict(self, *args, **kwargs):
+        self._sync_bn()
+        return super().state_dict(*args, **kwargs)
+
+    def _experts_train_mode(self):
+        return bool(self.model[-1].training) if len(self.model) else False
+
+    # -- forward ---------------------------------------------------------------------------------
+    def forward(self, image, cross=True, text=None, is_train=True):
+        """-> {"logits": [B,T,C], "index": gate [B,I] (train) / argmax [B] (eval) / None, "aux_logits": None}
+        (modules/model.py:343-359)."""
+        if cross is False:
+            feats, logits = _experts_forward([self.model[-1]], image, self.opt, self.model[-1].training)
+            return dict(logits=logits[0], index=None, aux_logits=None)
+        r = self.route_and_combine(image, is_train=is_train, want_logits=True)
+        return dict(logits=r["logits"], index=r["index"], aux_logits=None)
+
+    def cross_forward(self, image, text=None, is_train=True):
+        r = self.route_and_combine(image, is_train=True, want_logits=True)
+        return r["logits"], r["index"]
+
+    def cross_forward_expert(self, image, text=None, is_train=True):
+        r = self.route_and_combine(image, is_train=False, want_logits=True)
+        return r["logits"], r["index"]
+
+    def pad_zeros_features(self, feature, total):
+        raise RuntimeError("padding with ones is fused into mrnb_gate_combine; no padded tensor is materialised")
+
+    def route_and_combine(self, image, is_train=True, want_logits=True, targets=None, lengths=None, want_E=False,
+                          want_decode=False, with_backward=False, drop_scales=None):
+        """Experts -> DM-Router -> gate -> fused combine.  Soft route when is_train (modules/model.py:397-423),
+        hard route otherwise (:366-395)."""
+        experts = list(self.model)
+        feats, logits = _experts_forward(experts, image, self.opt, self._experts_train_mode(), self._cache,
+                                         drop_scales=drop_scales)
+        arena = self.router_arena(image.device)
+        _, scores, gate, index = ops.router_forward(arena, feats, self._rws, with_backward=with_backward,
+                                                    prec=_precision(self.opt), want_out=False)
+        if is_train:
+            g, idx_out = gate, gate
+        else:
+            g = torch.nn.functional.one_hot(index.long(), len(experts)).float()
+            idx_out = index.long()
+        r = ops.gate_combine(logits, g, targets, lengths, want_logits=want_logits, want_E=want_E, want_decode=want_decode)
+        r.update(index=idx_out, gate=gate, scores=scores, features=feats, expert_logits=logits)
+        return r

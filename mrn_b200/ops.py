@@ -42,6 +42,28 @@ def reset_launch_count() -> None:
     L.load().mrnb_reset_launch_count()
 
 
+PROFILE_FAMILIES = ("tcgen05_gemm", "fp32_gemm", "attention", "layernorm", "patch_embed_conv", "gated_combine",
+                    "ctc_lattice", "router_elementwise", "optimizer", "misc")
+
+
+def profile_enable(on: bool):
+    L.load().mrnb_profile_enable(int(on))
+
+
+def profile_reset():
+    L.load().mrnb_profile_reset()
+
+
+def profile_read():
+    """{family: dict(ms, calls, flops, bytes)} summed over the recorded launches (synchronises)."""
+    out = {}
+    for k, name in enumerate(PROFILE_FAMILIES):
+        ms, calls, fl, by = C.c_double(), C.c_long(), C.c_double(), C.c_double()
+        L.check(L.load().mrnb_profile_read(k, C.byref(ms), C.byref(calls), C.byref(fl), C.byref(by)), "profile_read")
+        out[name] = dict(ms=ms.value, calls=calls.value, flops=fl.value, bytes=by.value)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ building blocks
 def linear_f32(a, w, bias=None, residual=None, gelu=False):
     _chk_f32(a, w, bias, residual)

@@ -459,3 +459,26 @@ def ctc_encode(words: Sequence[str], char_to_idx: Dict[str, int], batch_max_leng
         idx[i, :len(ids)] = torch.tensor(ids, dtype=torch.long)
         lens[i] = len(w)
     return idx, lens
+
+
+# ----------------------------------------------------------------------------------------------
+# One full router-training iteration on the CPU (bench.py cpu_baseline / --impl reference)
+# ----------------------------------------------------------------------------------------------
+
+def stage1_step_cpu(sd, n_experts, state, image, targets, target_lengths, domain, lr=5e-4, pi=15.0, bn_mode="batch",
+                    drop_scales=None):
+    """il_modules/mrn.py:329-371 end to end in fp32 on the host: frozen experts forward (no grad), router forward,
+    loss = pi*CTC + CE, autograd backward through the router restatement, clip_grad_norm_(5), Adam.  Updates `sd` in
+    place.  Returns (loss_clf, taski_loss)."""
+    with torch.no_grad():
+        feats, preds = [], []
+        for i in range(n_experts):
+            ds = None if drop_scales is None else drop_scales[i]
+            f, z = expert_forward(sd, i, image, bn_mode, ds)
+            feats.append(f)
+            preds.append(z)
+        x = torch.stack(feats, 1)
+    r = stage1_router_grads(sd, x, preds, targets, target_lengths, domain, pi, dtype=torch.float32)
+    params = {k: sd[k] for k in ROUTER_KEYS}
+    clip_and_adam(params, r["grads"], state, lr)
+    return float(r["loss_clf"]), float(r["taski_loss"])

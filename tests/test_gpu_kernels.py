@@ -216,7 +216,8 @@ def test_combine_ctc_decode_match_oracle(cc, B, T):
     # dense gradient (expert-training stage)
     dense = ops.ctc_dense_grad(r["logits"], r["lse"], c["occ"], c["nll"], dev(tgt), dev(lens), 1.0 / B)
     scale = (1.0 / (B * lens.clamp(min=1).double())).view(-1, 1, 1)
-    assert rel_err(dense.cpu().numpy(), (grad_ref * scale).numpy()) < 1e-4
+    # softmax - occupancy cancels on the blank column (occ ~ 0.95): fp32 log-space lattice, same as ATen's kernel
+    assert rel_err(dense.cpu().numpy(), (grad_ref * scale).numpy()) < 3e-4
     # decode
     raw_ref, seqs_ref, conf_ref = O.greedy_decode(logits_ref.float())
     assert (r["amax"].cpu().long() == raw_ref).all()

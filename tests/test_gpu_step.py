@@ -1,0 +1,165 @@
+"""End-to-end GPU parity through the reference-facing API (mrn_b200.modules.model.MRNNet, mrn_b200.il_modules.mrn.MRN)
+against the golden fixtures produced by the unmodified reference and against the CPU oracle."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mrn_oracle as O
+from oracle import synth
+from conftest import load_golden, gview, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def make_opt(precision="fp32"):
+    return argparse.Namespace(Transformation="None", FeatureExtraction="SVTR", SequenceModeling="None", Prediction="CTC",
+                              num_fiducial=20, input_channel=4, output_channel=512, hidden_size=256, imgH=32, imgW=256,
+                              batch_max_length=25, lr=5e-4, num_iter=10000, grad_clip=5, exp_name="test", precision=precision,
+                              drop_path=False, lan_list=["a", "b", "c", "d", "e", "f"], val_interval=5000, start_task=0,
+                              optimizer="adam", schedule="super")
+
+
+def build_net(cc, sd, precision="fp32"):
+    from mrn_b200.modules.model import MRNNet
+    opt = make_opt(precision)
+    net = MRNNet(opt)
+    for c in cc:
+        net.update_fc(opt.hidden_size, c)
+        net.build_prediction(opt, c)
+    res = net.load_state_dict(sd, strict=True)          # the state_dict contract
+    assert not res.missing_keys and not res.unexpected_keys
+    return net.cuda(), opt
+
+
+def _case(name):
+    g = load_golden(name)
+    cc = tuple(int(c) for c in g["class_counts"])
+    B, seed = int(g["B"]), int(g["seed"])
+    sd = synth.synth_state_dict(cc, seed)
+    img, tgt, lens, dom = synth.synth_batch(B, cc, seed)
+    return g, cc, B, seed, sd, img, tgt, lens, dom
+
+
+@pytest.mark.parametrize("name", ["svtr_mrn_i3_b3", "svtr_mrn_i2_b4"])
+def test_mrnnet_forward_matches_reference_golden(name):
+    g, cc, B, seed, sd, img, tgt, lens, dom = _case(name)
+    net, opt = build_net(cc, sd)
+    net.eval()
+    x = img.cuda()
+    out = net(x, True, None, True)                      # soft route (modules/model.py:397-423)
+    assert np.abs(out["index"].cpu().numpy() - g["gate"]).max() < 1e-4               # gate weights within 1e-4
+    assert rel_err(gview(out["logits"].cpu(), g), g["logits_soft"]) < 1e-4           # logits within 1e-4 relative
+    ev = net(x, True, None, False)                      # hard route (modules/model.py:366-395)
+    assert (ev["index"].cpu().numpy() == g["index_hard"]).all()
+    assert rel_err(gview(ev["logits"].cpu(), g), g["logits_hard"]) < 1e-4
+    ff = net(x, False, None, False)                     # cross=False: last expert only (modules/model.py:346-348)
+    assert rel_err(gview(ff["logits"].cpu(), g), g["logits_last_expert"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["svtr_mrn_i3_b3", "svtr_mrn_i2_b4"])
+def test_learner_eval_decode_matches_reference_golden(name):
+    from mrn_b200.il_modules.mrn import MRN, RankLocal
+    g, cc, B, seed, sd, img, tgt, lens, dom = _case(name)
+    net, opt = build_net(cc, sd)
+    learner = MRN(opt)
+    learner.model = RankLocal(net)
+    learner.model.eval()
+    r = learner.infer_batch(img.cuda(), "TF", tgt.cuda(), lens.cuda())
+    ties = 0
+    for b in range(B):
+        n = int(r["lens"][b])
+        same = n == int(g["decode_len"][b]) and r["ids"][b, :n].cpu().tolist() == [int(v) for v in g["decode_ids"][b][:n]]
+        ties += 0 if same else 1
+    assert ties == 0, "decoded label indices differ from the reference on %d samples" % ties
+    assert abs(float(r["loss"]) - float(g["valid_loss"])) / abs(float(g["valid_loss"])) < 1e-4
+    assert rel_err(r["conf"].cpu().double().numpy(), g["confidence"]) < 1e-3
+
+
+@pytest.mark.parametrize("name", ["svtr_mrn_i3_b3", "svtr_mrn_i2_b4"])
+def test_stage1_step_matches_reference_golden(name):
+    """loss = 15*CTC + CE(gate, domain), router gradients, clip_grad_norm_(5) and one Adam step (il_modules/mrn.py:338-367)."""
+    from mrn_b200 import ops
+    from mrn_b200.il_modules.mrn import MRN, RankLocal, FusedAdam
+    g, cc, B, seed, sd, img, tgt, lens, dom = _case(name)
+    net, opt = build_net(cc, sd)
+    learner = MRN(opt)
+    learner.model = RankLocal(net)
+    learner.model.eval()                                # the golden step used eval-mode (frozen) experts
+    learner.optimizer = FusedAdam(net, 5e-4, 20000, grad_clip=5, schedule="const")
+    loss_clf, taski = learner.train_step_stage1(img.cuda(), tgt.cuda(), lens.cuda(), dom.cuda())
+    assert abs(float(loss_clf) - float(g["loss_clf"])) / abs(float(g["loss_clf"])) < 1e-4
+    assert abs(float(taski) - float(g["taski_loss"])) < 1e-4
+    n, off = ops.router_param_offsets(len(cc))
+    grads = net.router_grad_arena().cpu()
+    tn = float(g["grad_total_norm"])
+    assert abs(float(learner.optimizer.norm) - tn) / tn < 5e-4
+    params = net.router_arena().cpu()
+    for k, pname in enumerate(ops.ROUTER_PARAM_NAMES):
+        got = grads[off[k]:off[k + 1]]
+        ref = g["grad." + pname]
+        scale = max(float(np.abs(ref).max()), 1e-4 * tn)
+        assert np.abs(gview(got, g) - ref.reshape(-1)).max() / scale < 1e-3, pname
+        if pname == "route.bias":
+            continue
+        d = np.abs(gview(params[off[k]:off[k + 1]], g) - g["adam1." + pname].reshape(-1))
+        assert d.max() <= 5e-4 * 1.01 and (d > 2e-5).mean() < 1e-2, pname
+
+
+def test_train_mode_experts_match_oracle():
+    """BN batch statistics + injected DropPath masks (reference quirk 4) through the module API."""
+    g, cc, B, seed, sd, img, tgt, lens, dom = _case("svtr_mrn_i3_b3")
+    net, opt = build_net(cc, sd)
+    net.train()
+    drop = synth.synth_drop_scales(len(cc), B, O.svtr_drop_path_rates(), seed)
+    r = net.route_and_combine(img.cuda(), is_train=True, want_logits=True, drop_scales=drop.cuda())
+    assert np.abs(r["gate"].cpu().numpy() - g["train_gate"]).max() < 1e-4
+    assert rel_err(gview(r["logits"].cpu(), g), g["train_logits_soft"]) < 1e-4
+    sd2 = net.state_dict()      # running statistics written back under the reference's keys
+    k = "model.0.model.FeatureExtraction.ConvNet.patch_embed.proj.1.running_mean"
+    assert np.abs(sd2[k].cpu().numpy() - g["train_bn1_running_mean_e0"]).max() < 1e-5
+    assert int(sd2["model.0.model.FeatureExtraction.ConvNet.patch_embed.proj.1.num_batches_tracked"]) == 1
+
+
+def test_bf16_mode_within_north_star_budget():
+    g, cc, B, seed, sd, img, tgt, lens, dom = _case("svtr_mrn_i3_b3")
+    net, opt = build_net(cc, sd, precision="bf16")
+    net.eval()
+    out = net(img.cuda(), True, None, True)
+    assert rel_err(gview(out["logits"].cpu(), g), g["logits_soft"]) < 2e-2           # logits within 2e-2 in bf16
+    ev = net(img.cuda(), True, None, False)
+    flips = int((ev["index"].cpu().numpy() != g["index_hard"]).sum())
+    print("bf16 expert flips:", flips, "of", B)
+
+
+def test_full_size_properties_6_experts():
+    """BASELINE size (I=6, union charset 5153, B=32 here): size-independent properties -- gates are a distribution,
+    hard route == soft route with a one-hot gate, logsumexp consistency, decode idempotence."""
+    from mrn_b200 import ops
+    cc = synth.MLT17_CLASS_COUNTS
+    sd = synth.synth_state_dict(cc, 3)
+    img, tgt, lens, dom = synth.synth_batch(32, cc, 3)
+    net, opt = build_net(cc, sd, precision="bf16")
+    net.eval()
+    x = img.cuda()
+    r = net.route_and_combine(x, is_train=True, want_logits=True, targets=tgt.cuda(), lengths=lens.cuda(), want_E=True,
+                              want_decode=True)
+    gate = r["gate"]
+    assert torch.allclose(gate.sum(-1), torch.ones(32, device="cuda"), atol=1e-5) and (gate >= 0).all()
+    assert torch.allclose(torch.logsumexp(r["logits"], -1), r["lse"], atol=1e-4)
+    assert (r["logits"].max(-1)[1] == r["amax"].long()).all()
+    # E_i rows are convex combinations of pad_i values -> bounded by them
+    E = r["E"]
+    for i, z in enumerate(r["expert_logits"]):
+        hi = torch.maximum(z.max(-1)[0], torch.ones_like(z[..., 0])) if z.shape[-1] < cc[-1] else z.max(-1)[0]
+        assert (E[..., i] <= hi + 1e-3).all()
+    ev = net.route_and_combine(x, is_train=False, want_logits=True)
+    onehot = torch.nn.functional.one_hot(ev["index"], 6).float()
+    again = ops.gate_combine(r["expert_logits"], onehot, want_logits=True)
+    assert torch.equal(again["logits"], ev["logits"])
+    ids, n, conf = ops.greedy_decode(r["amax"], r["maxprob"])
+    assert (n <= 64).all() and (conf > 0).all() and (conf <= 1).all()
+    for b in range(4):      # a decoded sequence never contains blank or adjacent repeats of the raw path... it is collapsed
+        seq = ids[b, :int(n[b])].tolist()
+        assert 0 not in seq and -1 not in seq
