@@ -122,15 +122,50 @@ def test_train_mode_experts_match_oracle():
     assert int(sd2["model.0.model.FeatureExtraction.ConvNet.patch_embed.proj.1.num_batches_tracked"]) == 1
 
 
+def _random_init_state_dict(cc, seed):
+    """Random-init weights drawn by the mirror's own constructors, which restate the reference's initialisers
+    (modules/svtr.py:488-498; nn.Linear defaults for the router, modules/model.py:437-452) -- the weight distribution
+    BASELINE.json's tolerances are quoted on."""
+    from mrn_b200.modules.model import MRNNet
+    torch.manual_seed(seed)
+    opt = make_opt()
+    net = MRNNet(opt)
+    for c in cc:
+        net.update_fc(opt.hidden_size, c)
+        net.build_prediction(opt, c)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    for k in sd:                        # non-trivial BN running statistics
+        if k.endswith("running_var"):
+            sd[k] = 0.5 + torch.rand_like(sd[k])
+        if k.endswith("running_mean"):
+            sd[k] = 0.1 * torch.randn_like(sd[k])
+    return sd
+
+
 def test_bf16_mode_within_north_star_budget():
-    g, cc, B, seed, sd, img, tgt, lens, dom = _case("svtr_mrn_i3_b3")
+    """bf16 operands / fp32 accumulate for the expert GEMMs: logits within 2e-2 relative of the fp32 oracle on
+    random-init weights (BASELINE.json north_star); gate deviation and expert flips are reported."""
+    cc, B = (37, 61, 96), 4
+    sd = _random_init_state_dict(cc, 5)
+    img, tgt, lens, dom = synth.synth_batch(B, cc, 5)
+    with torch.no_grad():
+        o = O.mrn_forward(sd, len(cc), img, True, True)
+        e = O.mrn_forward(sd, len(cc), img, True, False)
     net, opt = build_net(cc, sd, precision="bf16")
     net.eval()
     out = net(img.cuda(), True, None, True)
-    assert rel_err(gview(out["logits"].cpu(), g), g["logits_soft"]) < 2e-2           # logits within 2e-2 in bf16
+    assert rel_err(out["logits"].cpu().numpy(), o["logits"].numpy()) < 2e-2           # logits within 2e-2 in bf16
+    gate_dev = float((out["index"].cpu() - o["index"]).abs().max())
     ev = net(img.cuda(), True, None, False)
-    flips = int((ev["index"].cpu().numpy() != g["index_hard"]).sum())
-    print("bf16 expert flips:", flips, "of", B)
+    flips = int((ev["index"].cpu() != e["index"]).sum())
+    print("bf16: gate max abs deviation %.2e, expert flips %d of %d" % (gate_dev, flips, B))
+    assert gate_dev < 2e-2
+    # fp32 mode on the same weights meets the fp32 tolerances
+    net32, _ = build_net(cc, sd, precision="fp32")
+    net32.eval()
+    out32 = net32(img.cuda(), True, None, True)
+    assert rel_err(out32["logits"].cpu().numpy(), o["logits"].numpy()) < 1e-4
+    assert float((out32["index"].cpu() - o["index"]).abs().max()) < 1e-4
 
 
 def test_full_size_properties_6_experts():
@@ -159,7 +194,7 @@ def test_full_size_properties_6_experts():
     again = ops.gate_combine(r["expert_logits"], onehot, want_logits=True)
     assert torch.equal(again["logits"], ev["logits"])
     ids, n, conf = ops.greedy_decode(r["amax"], r["maxprob"])
-    assert (n <= 64).all() and (conf > 0).all() and (conf <= 1).all()
+    assert (n <= 64).all() and (conf >= 0).all() and (conf <= 1).all()      # 64-frame products of ~1e-2 underflow in fp32, as in the reference
     for b in range(4):      # a decoded sequence never contains blank or adjacent repeats of the raw path... it is collapsed
         seq = ids[b, :int(n[b])].tolist()
         assert 0 not in seq and -1 not in seq
