@@ -192,6 +192,10 @@ int mrnb_linear_f32(const float* A, const float* W, const float* bias, const flo
 /* tcgen05 / TMEM / TMA GEMM: A [M,K] bf16, W [N,K] bf16, out fp32 or bf16 [M,N]; K % 64 == 0. */
 int mrnb_linear_bf16(const void* A, const void* W, const float* bias, const float* residual, void* out, int out_is_f32,
                      int M, int N, int K, int act_gelu, cudaStream_t stream);
+/* General tcgen05 GEMM used by the router (MN-major operands, split-K): out[M,N] = A . B with A stored [M,K] (a_mn=0)
+ * or [K,M] (a_mn=1), B stored [N,K] (b_mn=0) or [K,N] (b_mn=1), bf16; K % 64 == 0; out must be zeroed when splitk > 1. */
+int mrnb_tc_gemm_general(const void* A, int a_mn, const void* B, int b_mn, float* out, int M, int N, int K, int splitk,
+                         cudaStream_t stream);
 int mrnb_layernorm_f32(const float* x, float* y, const float* gamma, const float* beta, long rows, int D, float eps,
                        cudaStream_t stream);
 int mrnb_svtr_attention_f32(const float* qkv, float* out, int groups, int N, int d, int heads, int H, int W, int local,

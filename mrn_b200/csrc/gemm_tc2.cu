@@ -1,0 +1,348 @@
+// General tcgen05 GEMM: the router's contractions (modules/dm_router.py:50-67 and their backward) on the tensor cores.
+//
+//   C(g, m, n) (+)= epi( sum_k A(g, m, k) * B(g, k, n) )
+//
+// Differences from gemm_tc.cu (the plain grouped Linear of the expert path):
+//   * each operand is K-major (k contiguous in HBM) or MN-major (m / n contiguous): `X^T . Y` weight gradients and
+//     `dY . W` input gradients read the tensors where they lie -- no transposed copies;
+//   * operands are described by rank-4 TMA tensor maps plus a coordinate recipe, so the reference's rearranges
+//     ('b d p c -> b (d p) c', 'b d p c -> b (d c) p') are box orientations, not copies;
+//   * two-level output addressing (same MrnbAxis as gemm_f32.cu), split-K with fp32 atomics, and an epilogue with
+//     bias over n or m, exact GELU, an elementwise multiplier and a residual at the output address.
+// bf16 operands, fp32 accumulation in TMEM.  One 128 x BN output tile per CTA (router GEMMs have K >= 256).
+#include "common.cuh"
+#include "gemm_f32.h"
+#include "gemm_tc2.h"
+#include <cuda.h>
+
+namespace {
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return;
+    if (spin > (1u << 28)) __trap();        // protocol bug -> kernel error, not a hung GPU
+  }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// 128B-swizzled operand descriptors (cute::UMMA::SmemDescriptor bit layout).
+//  K-major : rows of 128 B (64 k), 8-row atoms 1024 B apart along M/N (SBO); LBO unused.
+//  MN-major: rows of 128 B (64 m/n), one row per k, 8-k atoms 1024 B apart (SBO); 64-wide MN chunks LBO apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void recipe_coords(const MrnbTmaRecipe& r, int mn, int k, int g, int (&c)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int v = r.src[j] == MRNB_SRC_MN ? mn : (r.src[j] == MRNB_SRC_K ? k : (r.src[j] == MRNB_SRC_G ? g : 0));
+    if (r.div[j] > 1) v /= r.div[j];
+    if (r.mod[j] > 0) v %= r.mod[j];
+    c[j] = v;
+  }
+}
+
+struct Epi2 {
+  float* out32; __nv_bfloat16* out16;     // either or both
+  MrnbAxis cm, cn; long c_gs;
+  const float* bias_n; const float* bias_m;
+  const float* mul; const float* res;
+  int M, N, KB_total, kb_per_split, splits, gelu;
+  float alpha;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(192)
+tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const MrnbTmaRecipe ra, const MrnbTmaRecipe rb, const Epi2 ep) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_sh;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const int g = blockIdx.z / ep.splits, split = blockIdx.z % ep.splits;
+  const int kb0 = split * ep.kb_per_split;
+  int kb1 = kb0 + ep.kb_per_split;
+  if (kb1 > ep.KB_total) kb1 = ep.KB_total;
+  const int KB = kb1 - kb0;                     // host guarantees KB >= 1
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_sh;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < KB; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
+        const int k0 = (kb0 + i) * BK;
+        int c[4];
+        if (A_MN) {
+#pragma unroll
+          for (int ch = 0; ch < BM / 64; ++ch) {
+            recipe_coords(ra, m0 + ch * 64, k0, g, c);
+            tma_load_4d(sa + ch * (BK * 128), &tmA, &full_bar[s], c[0], c[1], c[2], c[3]);
+          }
+        } else {
+          recipe_coords(ra, m0, k0, g, c);
+          tma_load_4d(sa, &tmA, &full_bar[s], c[0], c[1], c[2], c[3]);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int ch = 0; ch < BN / 64; ++ch) {
+            recipe_coords(rb, n0 + ch * 64, k0, g, c);
+            tma_load_4d(sa + A_BYTES + ch * (BK * 128), &tmB, &full_bar[s], c[0], c[1], c[2], c[3]);
+          }
+        } else {
+          recipe_coords(rb, n0, k0, g, c);
+          tma_load_4d(sa + A_BYTES, &tmB, &full_bar[s], c[0], c[1], c[2], c[3]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                 ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int i = 0; i < KB; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint64_t adesc = make_desc(sa, A_MN ? BK * 128 : 16);
+        const uint64_t bdesc = make_desc(sa + A_BYTES, B_MN ? BK * 128 : 16);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // K-major: +32 B inside the swizzled row; MN-major: +16 k-rows of 128 B
+          const uint64_t aoff = A_MN ? (uint64_t)(k * UMMA_K * 128 >> 4) : (uint64_t)(k * 2);
+          const uint64_t boff = B_MN ? (uint64_t)(k * UMMA_K * 128 >> 4) : (uint64_t)(k * 2);
+          umma_bf16(tmem_base, adesc + aoff, bdesc + boff, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(&tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const bool rok = row < ep.M;
+    const long om = rok ? (long)g * ep.c_gs + (long)(row / ep.cm.inner) * ep.cm.so + (long)(row % ep.cm.inner) * ep.cm.si : 0;
+    const float bm = (ep.bias_m && rok) ? ep.bias_m[row] : 0.f;
+    const bool plain = ep.splits == 1;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      const int col0 = n0 + c0;
+      if (!rok || col0 >= ep.N) continue;
+      // contiguous run of 16 columns?
+      const bool contig = ep.cn.si == 1 && (col0 % ep.cn.inner) + 16 <= ep.cn.inner && col0 + 16 <= ep.N;
+      const long on0 = (long)(col0 / ep.cn.inner) * ep.cn.so + (long)(col0 % ep.cn.inner) * ep.cn.si;
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x = __uint_as_float(r[j]) * ep.alpha;
+        if (plain) {
+          x += bm;
+          if (ep.bias_n && col0 + j < ep.N) x += __ldg(ep.bias_n + col0 + j);
+          if (ep.gelu) x = gelu_erf(x);
+        }
+        v[j] = x;
+      }
+      if (!plain) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = col0 + j;
+          if (col >= ep.N) break;
+          const long o = om + (contig ? on0 + j : (long)(col / ep.cn.inner) * ep.cn.so + (long)(col % ep.cn.inner) * ep.cn.si);
+          atomicAdd(ep.out32 + o, v[j]);
+        }
+        continue;
+      }
+      if (contig && ((om + on0) & 3) == 0) {
+        const long o = om + on0;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 t = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if (ep.mul) { const float4 mm = *reinterpret_cast<const float4*>(ep.mul + o + j); t.x *= mm.x; t.y *= mm.y; t.z *= mm.z; t.w *= mm.w; }
+          if (ep.res) { const float4 rr = *reinterpret_cast<const float4*>(ep.res + o + j); t.x += rr.x; t.y += rr.y; t.z += rr.z; t.w += rr.w; }
+          if (ep.out32) *reinterpret_cast<float4*>(ep.out32 + o + j) = t;
+          if (ep.out16) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(t.x, t.y), h1 = __floats2bfloat162_rn(t.z, t.w);
+            *reinterpret_cast<uint2*>(ep.out16 + o + j) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+          }
+        }
+      } else {
+        for (int j = 0; j < 16; ++j) {
+          const int col = col0 + j;
+          if (col >= ep.N) break;
+          const long o = om + (long)(col / ep.cn.inner) * ep.cn.so + (long)(col % ep.cn.inner) * ep.cn.si;
+          float x = v[j];
+          if (ep.mul) x *= ep.mul[o];
+          if (ep.res) x += ep.res[o];
+          if (ep.out32) ep.out32[o] = x;
+          if (ep.out16) ep.out16[o] = __float2bfloat16_rn(x);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int encode(CUtensorMap* map, const MrnbTcOperand& op) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { mrnb_set_error("tc_gemm2: cuTensorMapEncodeTiled unavailable"); return MRNB_ERR_UNSUPPORTED; }
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4], es[4] = {1, 1, 1, 1};
+  for (int j = 0; j < 4; ++j) { dims[j] = (cuuint64_t)op.dims[j]; box[j] = (cuuint32_t)op.box[j]; }
+  for (int j = 0; j < 3; ++j) strides[j] = (cuuint64_t)op.strides[j] * 2;       // bytes, dims 1..3
+  if ((reinterpret_cast<uintptr_t>(op.ptr) & 15) || op.box[0] != 64) {
+    mrnb_set_error("tc_gemm2: operand misaligned or inner box != 64");
+    return MRNB_ERR_ARG;
+  }
+  for (int j = 0; j < 3; ++j)
+    if ((op.strides[j] * 2) % 16) { mrnb_set_error("tc_gemm2: stride %d not a multiple of 16 bytes", j); return MRNB_ERR_ARG; }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.ptr), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { mrnb_set_error("tc_gemm2: cuTensorMapEncodeTiled failed (%d)", (int)r); return MRNB_ERR_ARG; }
+  return MRNB_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch2(const MrnbTcGemm2& p, cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  MRNB_TRY(encode(&tmA, p.a));
+  MRNB_TRY(encode(&tmB, p.b));
+  Epi2 ep{};
+  ep.out32 = p.out32; ep.out16 = (__nv_bfloat16*)p.out16; ep.cm = p.cm; ep.cn = p.cn; ep.c_gs = p.c_gstride;
+  ep.bias_n = p.bias_n; ep.bias_m = p.bias_m; ep.mul = p.mul; ep.res = p.res;
+  ep.M = p.M; ep.N = p.N; ep.gelu = p.gelu; ep.alpha = p.alpha == 0.f ? 1.f : p.alpha;
+  ep.KB_total = p.K / BK;
+  int splits = p.splitk > 1 ? p.splitk : 1;
+  if (splits > ep.KB_total) splits = ep.KB_total;
+  ep.kb_per_split = (ep.KB_total + splits - 1) / splits;
+  splits = (ep.KB_total + ep.kb_per_split - 1) / ep.kb_per_split;     // no empty split
+  ep.splits = splits;
+  const size_t smem = 1024 + (size_t)STAGES * (A_BYTES + BN * BK * 2);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(tc_gemm2_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), p.groups * splits);
+  tc_gemm2_kernel<BN, A_MN, B_MN><<<grid, 192, smem, st>>>(tmA, tmB, p.a.recipe, p.b.recipe, ep);
+  MRNB_CHECK_LAUNCH("tc_gemm2_kernel");
+  return MRNB_OK;
+}
+
+}  // namespace
+
+int mrnb_tc_gemm2(const MrnbTcGemm2& p, cudaStream_t st) {
+  MRNB_CHECK_ARG(p.a.ptr && p.b.ptr && (p.out32 || p.out16) && p.M > 0 && p.N > 0 && p.K > 0 && p.groups > 0, "tc_gemm2: bad argument");
+  MRNB_CHECK_ARG(p.K % BK == 0, "tc_gemm2: K=%d must be a multiple of 64", p.K);
+  MRNB_CHECK_ARG(p.splitk <= 1 || (p.out32 && !p.out16 && !p.bias_n && !p.bias_m && !p.mul && !p.res && !p.gelu),
+                 "tc_gemm2: split-K supports a raw fp32 accumulate only");
+  MrnbProfScope prof(MRNB_PROF_TCGEMM, st, 2.0 * p.M * p.N * p.K * p.groups,
+                     (double)p.groups * (2.0 * p.M * p.K + 2.0 * p.N * p.K + 4.0 * p.M * p.N));
+  const bool wide = p.N >= 128;
+#define GO(BN_)                                                                                   \
+  if (p.a.mn_major && p.b.mn_major) return launch2<BN_, true, true>(p, st);                       \
+  if (p.a.mn_major) return launch2<BN_, true, false>(p, st);                                      \
+  if (p.b.mn_major) return launch2<BN_, false, true>(p, st);                                      \
+  return launch2<BN_, false, false>(p, st);
+  if (wide) { GO(128) } else { GO(64) }
+#undef GO
+}
+
+// ---- C-ABI test entry: plain 2-D operands in any of the four major-ness combinations -------------------------
+//   a_mn = 0: A is [M,K] (k contiguous)   a_mn = 1: A is stored [K,M] (m contiguous)
+//   b_mn = 0: B is [N,K] (k contiguous)   b_mn = 1: B is stored [K,N] (n contiguous)
+extern "C" int mrnb_tc_gemm_general(const void* A, int a_mn, const void* B, int b_mn, float* out, int M, int N, int K,
+                                    int splitk, cudaStream_t stream) {
+  MrnbTcGemm2 g{};
+  g.a = a_mn ? mrnb_operand_mn2d(A, M, K, M, 1) : mrnb_operand_k2d(A, M, K, K, BM, 1);
+  const int bn = N >= 128 ? 128 : 64;
+  g.b = b_mn ? mrnb_operand_mn2d(B, N, K, N, 1) : mrnb_operand_k2d(B, N, K, K, bn, 1);
+  g.out32 = out; g.cm = mrnb_axis(N); g.cn = mrnb_axis(1);
+  g.M = M; g.N = N; g.K = K; g.groups = 1; g.splitk = splitk; g.alpha = 1.f;
+  return mrnb_tc_gemm2(g, stream);
+}

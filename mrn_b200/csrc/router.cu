@@ -15,6 +15,7 @@
 // (1e-4 tolerance); the tensor-core port of these contractions is tracked in DESIGN.md.
 #include "common.cuh"
 #include "gemm_f32.h"
+#include "gemm_tc2.h"
 #include "../../include/mrn_b200.h"
 
 namespace {
@@ -28,8 +29,10 @@ long router_offsets(int I, int T, int D, long* off) {
   const long sz[MRNB_ROUTER_NPARAMS] = {T, 1, (long)I * I * D, I, D, D, 2L * D * D, 2L * D, D, D,
                                         (long)I * T * I * T, (long)I * T, T, T, (long)I * D * I * D, (long)I * D,
                                         (long)D * D, D, (long)D * D, D};
+  // every slot starts on a 32-byte boundary (8 floats) so the bf16 shadow of a weight is a legal TMA base;
+  // padding elements stay zero (zero gradient, untouched by Adam)
   long o = 0;
-  for (int k = 0; k < MRNB_ROUTER_NPARAMS; ++k) { off[k] = o; o += sz[k]; }
+  for (int k = 0; k < MRNB_ROUTER_NPARAMS; ++k) { off[k] = o; o += (sz[k] + 7) / 8 * 8; }
   off[MRNB_ROUTER_NPARAMS] = o;
   return o;
 }
@@ -37,7 +40,7 @@ long router_offsets(int I, int T, int D, long* off) {
 // ---- row LayerNorm over D=256 with saved statistics (warp per row) ------------------------------
 __global__ void __launch_bounds__(256)
 ln_rows_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                   float* __restrict__ y, float* __restrict__ stats, long rows, float eps) {
+                   float* __restrict__ y, __nv_bfloat16* __restrict__ y16, float* __restrict__ stats, long rows, float eps) {
   const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -60,14 +63,17 @@ ln_rows_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int idx = (j / 4) * 128 + lane * 4 + (j % 4);
-    y[row * RD + idx] = (v[j] - mean) * rstd * gamma[idx] + beta[idx];
+    const float o = (v[j] - mean) * rstd * gamma[idx] + beta[idx];
+    if (y) y[row * RD + idx] = o;
+    if (y16) y16[row * RD + idx] = __float2bfloat16_rn(o);
   }
 }
 
 // a1 [rows, 2D] -> u = GELU(a1[:, :D]) ; vn = LN_D(GELU(a1[:, D:])) + stats
 __global__ void __launch_bounds__(256)
 gelu_ln_fwd_kernel(const float* __restrict__ a1, const float* __restrict__ gamma, const float* __restrict__ beta,
-                   float* __restrict__ u, float* __restrict__ vn, float* __restrict__ stats, long rows, float eps) {
+                   float* __restrict__ u, float* __restrict__ vn, __nv_bfloat16* __restrict__ vn16,
+                   float* __restrict__ stats, long rows, float eps) {
   const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -93,31 +99,43 @@ gelu_ln_fwd_kernel(const float* __restrict__ a1, const float* __restrict__ gamma
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int idx = (j / 4) * 128 + lane * 4 + (j % 4);
-    vn[row * RD + idx] = (v[j] - mean) * rstd * gamma[idx] + beta[idx];
+    const float o = (v[j] - mean) * rstd * gamma[idx] + beta[idx];
+    if (vn) vn[row * RD + idx] = o;
+    if (vn16) vn16[row * RD + idx] = __float2bfloat16_rn(o);
   }
 }
 
-__global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ c, long n4) {
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+}
+__global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ c,
+                           __nv_bfloat16* __restrict__ c16, long n4) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i];
-  reinterpret_cast<float4*>(c)[i] = make_float4(x.x * y.x, x.y * y.y, x.z * y.z, x.w * y.w);
+  const float4 r = make_float4(x.x * y.x, x.y * y.y, x.z * y.z, x.w * y.w);
+  if (c) reinterpret_cast<float4*>(c)[i] = r;
+  if (c16) store_bf16x4(c16 + i * 4, r);
 }
 // c = a*b ; d = a*e      (shared first factor)
 __global__ void mul2_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ e,
-                            float* __restrict__ c, float* __restrict__ d, long n4) {
+                            float* __restrict__ c, float* __restrict__ d, __nv_bfloat16* __restrict__ d16, long n4) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i],
                z = reinterpret_cast<const float4*>(e)[i];
   reinterpret_cast<float4*>(c)[i] = make_float4(x.x * y.x, x.y * y.y, x.z * y.z, x.w * y.w);
-  reinterpret_cast<float4*>(d)[i] = make_float4(x.x * z.x, x.y * z.y, x.z * z.z, x.w * z.w);
+  const float4 r = make_float4(x.x * z.x, x.y * z.y, x.z * z.z, x.w * z.w);
+  reinterpret_cast<float4*>(d)[i] = r;
+  if (d16) store_bf16x4(d16 + i * 4, r);
 }
 
 // LayerNorm over the patch axis T for every (b,i,c): block per (b,i), thread per c (ChannelDomainGating.norm)
 __global__ void __launch_bounds__(RD)
 lnT_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma /*[T]*/, const float* __restrict__ beta,
-               float* __restrict__ gn, float* __restrict__ stats /*[B*I, D, 2]*/, int T, float eps) {
+               float* __restrict__ gn, __nv_bfloat16* __restrict__ gn16, float* __restrict__ stats /*[B*I, D, 2]*/, int T,
+               float eps) {
   const long bi = blockIdx.x;
   const int c = threadIdx.x;
   const float* yp = y + bi * T * RD + c;
@@ -128,15 +146,18 @@ lnT_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma /*[T
   for (int t = 0; t < T; ++t) { const float d = yp[(long)t * RD] - mean; q = fmaf(d, d, q); }
   const float rstd = rsqrtf(q / T + eps);
   stats[(bi * RD + c) * 2] = mean; stats[(bi * RD + c) * 2 + 1] = rstd;
-  float* gp = gn + bi * T * RD + c;
-  for (int t = 0; t < T; ++t) gp[(long)t * RD] = (yp[(long)t * RD] - mean) * rstd * gamma[t] + beta[t];
+  for (int t = 0; t < T; ++t) {
+    const float o = (yp[(long)t * RD] - mean) * rstd * gamma[t] + beta[t];
+    if (gn) gn[bi * T * RD + (long)t * RD + c] = o;
+    if (gn16) gn16[bi * T * RD + (long)t * RD + c] = __float2bfloat16_rn(o);
+  }
 }
 
 // backward of lnT: dy += rstd*(dxh - mean(dxh) - xh*mean(dxh*xh)), dgamma[t] += sum dgn*xh, dbeta[t] += sum dgn
 __global__ void __launch_bounds__(RD)
 lnT_bwd_kernel(const float* __restrict__ y, const float* __restrict__ stats, const float* __restrict__ gamma,
-               const float* __restrict__ dgn, float* __restrict__ dy /* accumulated */, float* __restrict__ dgamma,
-               float* __restrict__ dbeta, int T) {
+               const float* __restrict__ dgn, float* __restrict__ dy /* accumulated */, __nv_bfloat16* __restrict__ dy16,
+               float* __restrict__ dgamma, float* __restrict__ dbeta, int T) {
   extern __shared__ float sh[];        // [T][2] block partials
   const long bi = blockIdx.x;
   const int c = threadIdx.x, lane = c & 31;
@@ -158,7 +179,9 @@ lnT_bwd_kernel(const float* __restrict__ y, const float* __restrict__ stats, con
   for (int t = 0; t < T; ++t) {
     const float xh = (yp[(long)t * RD] - mean) * rstd;
     const float dxh = dp[(long)t * RD] * gamma[t];
-    op[(long)t * RD] += rstd * (dxh - m1 - xh * m2);
+    const float o = op[(long)t * RD] + rstd * (dxh - m1 - xh * m2);
+    op[(long)t * RD] = o;
+    if (dy16) dy16[bi * T * RD + (long)t * RD + c] = __float2bfloat16_rn(o);
   }
   __syncthreads();
   for (int k = c; k < T; k += RD) { atomicAdd(dgamma + k, sh[k * 2]); atomicAdd(dbeta + k, sh[k * 2 + 1]); }
@@ -169,8 +192,8 @@ lnT_bwd_kernel(const float* __restrict__ y, const float* __restrict__ stats, con
 template <bool GELU_IN>
 __global__ void __launch_bounds__(256)
 ln_rows_bwd_kernel(const float* __restrict__ xin, long ldx, const float* __restrict__ stats,
-                   const float* __restrict__ gamma, const float* __restrict__ dyn, float* __restrict__ dxin, long lddx,
-                   const float* __restrict__ add1, const float* __restrict__ add2, float* __restrict__ dgamma,
+                   const float* __restrict__ gamma, const float* __restrict__ dyn, float* __restrict__ dxin,
+                   __nv_bfloat16* __restrict__ dxin16, long lddx, const float* __restrict__ add1, const float* __restrict__ add2, float* __restrict__ dgamma,
                    float* __restrict__ dbeta, long rows) {
   __shared__ float sg[RD], sb[RD];
   for (int k = threadIdx.x; k < RD; k += 256) { sg[k] = 0.f; sb[k] = 0.f; }
@@ -204,6 +227,7 @@ ln_rows_bwd_kernel(const float* __restrict__ xin, long ldx, const float* __restr
         if (add1) g += add1[row * RD + idx];
         if (add2) g += add2[row * RD + idx];
         dxin[row * lddx + idx] = g;
+        if (dxin16) dxin16[row * lddx + idx] = __float2bfloat16_rn(g);
       }
     }
   }
@@ -217,11 +241,39 @@ ln_rows_bwd_kernel(const float* __restrict__ xin, long ldx, const float* __restr
 }
 
 // da1[:, :D] = du * GELU'(a1[:, :D])
-__global__ void gelu_bwd_kernel(const float* __restrict__ a1, const float* __restrict__ du, float* __restrict__ da1, long rows) {
+__global__ void gelu_bwd_kernel(const float* __restrict__ a1, const float* __restrict__ du, float* __restrict__ da1,
+                                __nv_bfloat16* __restrict__ da1_16, long rows) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * RD) return;
   const long row = i / RD; const int c = (int)(i % RD);
-  da1[row * 2 * RD + c] = du[i] * gelu_erf_grad(a1[row * 2 * RD + c]);
+  const float o = du[i] * gelu_erf_grad(a1[row * 2 * RD + c]);
+  da1[row * 2 * RD + c] = o;
+  if (da1_16) da1_16[row * 2 * RD + c] = __float2bfloat16_rn(o);
+}
+
+// dout[b,i,t,c] = sum_j ds[b,t,j] * Wcr[j,(i,c)]   (gate-head input gradient, K = I is tiny) + bf16 copy
+__global__ void dout_kernel(const float* __restrict__ ds, const float* __restrict__ Wcr, int I, int T, long total4,
+                            float* __restrict__ dout, __nv_bfloat16* __restrict__ dout16) {
+  const long i4 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  const long e = i4 * 4;
+  const int c = (int)(e % RD);
+  const int t = (int)((e / RD) % T);
+  const int i = (int)((e / ((long)RD * T)) % I);
+  const long b = e / ((long)RD * T * I);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < I; ++j) {
+    const float d = ds[(b * T + t) * I + j];
+    const float4 w = *reinterpret_cast<const float4*>(Wcr + (long)j * I * RD + (long)i * RD + c);
+    acc.x = fmaf(d, w.x, acc.x); acc.y = fmaf(d, w.y, acc.y); acc.z = fmaf(d, w.z, acc.z); acc.w = fmaf(d, w.w, acc.w);
+  }
+  *reinterpret_cast<float4*>(dout + e) = acc;
+  if (dout16) store_bf16x4(dout16 + e, acc);
+}
+
+__global__ void cast16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __float2bfloat16_rn(x[i]);
 }
 
 // out[n] (+)= sum_m X(m, n) with two-level axes; grid (cdiv(N,32), msplit)
@@ -330,11 +382,15 @@ __global__ void route_bwd_kernel(const float* __restrict__ dr, const float* __re
 
 inline size_t al(size_t v) { return (v + 255) / 256 * 256; }
 
+typedef __nv_bfloat16 bf16;
+
 struct RouterWs {
   // forward (kept for backward)
   float *stats1, *xn, *a1, *u, *vn, *stats2, *v2, *g1, *y, *statsT, *gn, *g2, *y2, *out, *s;
   // backward temporaries
   float *dr, *ds, *dout, *dy2, *dy, *dg2, *dgn, *dg1, *du, *dv2, *dvn, *da1, *dxn;
+  // bf16 shadows (tensor-core mode): GEMM operands only
+  bf16 *w16, *xn16, *vn16, *g116, *gn16, *y216, *dout16, *dg216, *dy16, *dv216, *da116;
   size_t bytes;
 };
 
@@ -342,14 +398,20 @@ RouterWs carve(char* base, int B, int I, int T, int D, bool bwd) {
   RouterWs w{};
   size_t o = 0;
   const size_t M = (size_t)B * I * T, MD = M * D;
+  long off[MRNB_ROUTER_NPARAMS + 1];
+  const size_t nparam = (size_t)router_offsets(I, T, D, off);
   auto take = [&](size_t n) { float* p = base ? (float*)(base + o) : nullptr; o = al(o + n * 4); return p; };
+  auto take16 = [&](size_t n) { bf16* p = base ? (bf16*)(base + o) : nullptr; o = al(o + n * 2); return p; };
   w.stats1 = take(M * 2); w.xn = take(MD); w.a1 = take(MD * 2); w.u = take(MD); w.vn = take(MD); w.stats2 = take(M * 2);
   w.v2 = take(MD); w.g1 = take(MD); w.y = take(MD); w.statsT = take((size_t)B * I * D * 2); w.gn = take(MD);
   w.g2 = take(MD); w.y2 = take(MD); w.out = take(MD); w.s = take((size_t)B * T * I);
+  w.w16 = take16(nparam); w.xn16 = take16(MD); w.vn16 = take16(MD); w.g116 = take16(MD); w.gn16 = take16(MD);
+  w.y216 = take16(MD);
   if (bwd) {
     w.dr = take((size_t)B * I); w.ds = take((size_t)B * T * I); w.dout = take(MD); w.dy2 = take(MD); w.dy = take(MD);
     w.dg2 = take(MD); w.dgn = take(MD); w.dg1 = take(MD); w.du = take(MD); w.dv2 = take(MD); w.dvn = take(MD);
     w.da1 = take(MD * 2); w.dxn = take(MD);
+    w.dout16 = take16(MD); w.dg216 = take16(MD); w.dy16 = take16(MD); w.dv216 = take16(MD); w.da116 = take16(MD * 2);
   }
   w.bytes = o + 256;
   return w;
@@ -363,27 +425,150 @@ RouterWs carve(char* base, int B, int I, int T, int D, bool bwd) {
 
 int colsum(const float* X, MrnbAxis am, MrnbAxis an, int M, int N, float* out, cudaStream_t st) {
   int msplit = M / 512; if (msplit < 1) msplit = 1; if (msplit > 64) msplit = 64;
+  MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
   colsum_kernel<<<dim3(cdiv(N, 32), msplit), 256, 0, st>>>(X, am, an, M, N, out);
   MRNB_CHECK_LAUNCH("colsum_kernel");
   return MRNB_OK;
 }
 
-int router_forward(const float* P, const float* x, int B, int I, int T, int D, float* out_user, float* scores,
-                   float* gate, int* index, RouterWs& w, cudaStream_t st) {
-  long off[MRNB_ROUTER_NPARAMS + 1];
-  router_offsets(I, T, D, off);
-  const long M = (long)B * I * T, IT = (long)I * T, ID = (long)I * D, TD = (long)T * D, ITD = IT * D;
-  float* out = w.out;   // kept in the workspace for the backward; copied to the caller's buffer at the end
-  ln_rows_fwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(x, P + off[R_N_W], P + off[R_N_B], w.xn, w.stats1, M, 1e-5f);
-  MRNB_CHECK_LAUNCH("ln_rows_fwd_kernel");
-  {  // a1 = xn W1^T + b1
-    MrnbGemm g = mrnb_gemm_nt(w.xn, D, P + off[R_P1_W], D, w.a1, 2 * D, (int)M, 2 * D, D);
-    g.bias_n = P + off[R_P1_B];
-    MRNB_TRY(mrnb_sgemm(g, st));
+// Dimensions shared by every contraction of the router.
+struct Dims {
+  int B, I, T, D;
+  long M, IT, ID, TD, ITD;
+  bool tc;              // tensor-core (bf16 operand) engine
+  Dims(int b, int i, int t, int d, bool tc_) : B(b), I(i), T(t), D(d), M((long)b * i * t), IT((long)i * t), ID((long)i * d),
+                                               TD((long)t * d), ITD((long)i * t * d), tc(tc_) {}
+};
+
+// ---- TMA views of the [B,I,T,D] activation tensors (bf16) --------------------------------------------------
+// rows m = (b,t), k = (i,c): K-major, box = 64 c x 64 t x 1 i x 2 b  (a 128-row tile = two samples; needs T == 64)
+MrnbTcOperand op_bt_ic_kmajor(const bf16* p, const Dims& d) {
+  MrnbTcOperand o{};
+  o.ptr = p; o.mn_major = 0;
+  o.dims[0] = d.D; o.dims[1] = d.T; o.dims[2] = d.I; o.dims[3] = d.B;
+  o.strides[0] = d.D; o.strides[1] = d.TD; o.strides[2] = d.ITD;
+  o.box[0] = 64; o.box[1] = 64; o.box[2] = 1; o.box[3] = 2;
+  o.recipe = MrnbTmaRecipe{{MRNB_SRC_K, MRNB_SRC_ZERO, MRNB_SRC_K, MRNB_SRC_MN}, {1, 1, d.D, d.T}, {d.D, 0, 0, 0}};
+  return o;
+}
+// m / n = (i,c) contiguous in c, k = (b,t): MN-major, box = 64 c x 64 t x 1 x 1 per 64-wide chunk
+MrnbTcOperand op_ic_bt_mnmajor(const bf16* p, const Dims& d) {
+  MrnbTcOperand o{};
+  o.ptr = p; o.mn_major = 1;
+  o.dims[0] = d.D; o.dims[1] = d.T; o.dims[2] = d.I; o.dims[3] = d.B;
+  o.strides[0] = d.D; o.strides[1] = d.TD; o.strides[2] = d.ITD;
+  o.box[0] = 64; o.box[1] = 64; o.box[2] = 1; o.box[3] = 1;
+  o.recipe = MrnbTmaRecipe{{MRNB_SRC_MN, MRNB_SRC_ZERO, MRNB_SRC_MN, MRNB_SRC_K}, {1, 1, d.D, d.T}, {d.D, 0, 0, 0}};
+  return o;
+}
+// per-sample [IT, D] activations as the MN-major B operand of a token-mixing GEMM: n = c contiguous, k = token, g = b
+MrnbTcOperand op_tok_c_mnmajor(const bf16* p, const Dims& d) {
+  return mrnb_operand_mn2d(p, d.D, d.IT, d.D, d.B, d.ITD);
+}
+// rows = token n, k = (b,c): K-major with the sample folded into k, box = 64 c x box_rows n x 1 b
+MrnbTcOperand op_tok_bc_kmajor(const bf16* p, const Dims& d, int box_rows) {
+  MrnbTcOperand o{};
+  o.ptr = p; o.mn_major = 0;
+  o.dims[0] = d.D; o.dims[1] = d.IT; o.dims[2] = d.B; o.dims[3] = 1;
+  o.strides[0] = d.D; o.strides[1] = d.ITD; o.strides[2] = d.ITD * d.B;
+  o.box[0] = 64; o.box[1] = box_rows; o.box[2] = 1; o.box[3] = 1;
+  o.recipe = MrnbTmaRecipe{{MRNB_SRC_K, MRNB_SRC_MN, MRNB_SRC_K, MRNB_SRC_ZERO}, {1, 1, d.D, 1}, {d.D, 0, 0, 0}};
+  return o;
+}
+MrnbTcOperand nogroup(MrnbTcOperand o) {          // shared weight: ignore the group index
+  for (int j = 0; j < 4; ++j) if (o.recipe.src[j] == MRNB_SRC_G) o.recipe.src[j] = MRNB_SRC_ZERO;
+  return o;
+}
+inline int bn_for(int N) { return N >= 128 ? 128 : 64; }
+
+// out[rows, Nout] = A[rows, K] . W[Nout, K]^T (+bias, +res)   -- plain row-major Linear
+int linear_rows(const Dims& d, const float* A32, const bf16* A16, long lda, const float* W32, const bf16* W16, int Nout, int K,
+                const float* bias, const float* res, float* out, long ldo, cudaStream_t st) {
+  if (d.tc) {
+    MrnbTcGemm2 g{};
+    g.a = mrnb_operand_k2d(A16, d.M, K, lda, 128, 1);
+    g.b = mrnb_operand_k2d(W16, Nout, K, K, bn_for(Nout), 1);
+    g.out32 = out; g.cm = mrnb_axis(ldo); g.cn = mrnb_axis(1);
+    g.bias_n = bias; g.res = res; g.M = (int)d.M; g.N = Nout; g.K = K; g.groups = 1; g.alpha = 1.f;
+    return mrnb_tc_gemm2(g, st);
   }
-  gelu_ln_fwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(w.a1, P + off[R_SN_W], P + off[R_SN_B], w.u, w.vn, w.stats2, M, 1e-5f);
-  MRNB_CHECK_LAUNCH("gelu_ln_fwd_kernel");
-  {  // v2[b] = Ws . vn[b] + bs  (token mixing over n = i*T+t)
+  MrnbGemm g = mrnb_gemm_nt(A32, lda, W32, K, out, ldo, (int)d.M, Nout, K);
+  g.bias_n = bias; g.res = res;
+  return mrnb_sgemm(g, st);
+}
+// dX[rows, Nin] = dY[rows, Nout] . W[Nout, Nin]
+int dx_rows(const Dims& d, const float* dY32, const bf16* dY16, long ldy, int Nout, const float* W32, const bf16* W16, int Nin,
+            float* dX, long lddx, cudaStream_t st) {
+  if (d.tc) {
+    MrnbTcGemm2 g{};
+    g.a = mrnb_operand_k2d(dY16, d.M, Nout, ldy, 128, 1);
+    g.b = mrnb_operand_mn2d(W16, Nin, Nout, Nin, 1);
+    g.out32 = dX; g.cm = mrnb_axis(lddx); g.cn = mrnb_axis(1);
+    g.M = (int)d.M; g.N = Nin; g.K = Nout; g.groups = 1; g.alpha = 1.f;
+    return mrnb_tc_gemm2(g, st);
+  }
+  MrnbGemm g{};
+  g.A = dY32; g.am = mrnb_axis(ldy); g.ak = mrnb_axis(1); g.a_kfast = 1;
+  g.B = W32; g.bk = mrnb_axis(Nin); g.bn = mrnb_axis(1); g.b_kfast = 0;
+  g.C = dX; g.cm = mrnb_axis(lddx); g.cn = mrnb_axis(1);
+  g.M = (int)d.M; g.N = Nin; g.K = Nout; g.batch = 1; g.splitk = 1; g.alpha = 1.f; g.rows_per_scale = 1;
+  return mrnb_sgemm(g, st);
+}
+// dW[Nout, Nin] += dY[rows, Nout]^T . X[rows, Nin]      (K = rows, split-K into the zeroed gradient arena)
+int dw_rows(const Dims& d, const float* dY32, const bf16* dY16, long ldy, int Nout, const float* X32, const bf16* X16, long ldx,
+            int Nin, float* dW, cudaStream_t st) {
+  if (d.tc) {
+    MrnbTcGemm2 g{};
+    g.a = mrnb_operand_mn2d(dY16, Nout, d.M, ldy, 1);
+    g.b = mrnb_operand_mn2d(X16, Nin, d.M, ldx, 1);
+    g.out32 = dW; g.cm = mrnb_axis(Nin); g.cn = mrnb_axis(1);
+    g.M = Nout; g.N = Nin; g.K = (int)d.M; g.groups = 1; g.alpha = 1.f;
+    const int tiles = cdiv(Nout, 128) * cdiv(Nin, bn_for(Nin));
+    g.splitk = (296 + tiles - 1) / tiles;
+    return mrnb_tc_gemm2(g, st);
+  }
+  MrnbGemm g{};
+  g.A = dY32; g.am = mrnb_axis(1); g.ak = mrnb_axis(ldy); g.a_kfast = 0;
+  g.B = X32; g.bk = mrnb_axis(ldx); g.bn = mrnb_axis(1); g.b_kfast = 0;
+  g.C = dW; g.cm = mrnb_axis(Nin); g.cn = mrnb_axis(1);
+  g.M = Nout; g.N = Nin; g.K = (int)d.M; g.batch = 1; g.alpha = 1.f; g.rows_per_scale = 1;
+  g.splitk = (int)((d.M + 2047) / 2048); if (g.splitk > 64) g.splitk = 64; if (g.splitk < 1) g.splitk = 1;
+  return mrnb_sgemm(g, st);
+}
+
+int router_forward(const float* P, const float* x, const Dims& d, float* out_user, float* scores, float* gate, int* index,
+                   RouterWs& w, cudaStream_t st) {
+  long off[MRNB_ROUTER_NPARAMS + 1];
+  const long nparam = router_offsets(d.I, d.T, d.D, off);
+  const int B = d.B, I = d.I, T = d.T, D = d.D;
+  const long M = d.M, IT = d.IT, ID = d.ID, TD = d.TD, ITD = d.ITD;
+  const bool tc = d.tc;
+  const bf16* W16 = w.w16;
+  float* out = w.out;   // kept in the workspace for the backward; copied to the caller's buffer at the end
+  {
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    if (tc) LAUNCH_EW(cast16_kernel, nparam, P, w.w16, nparam);
+    ln_rows_fwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(x, P + off[R_N_W], P + off[R_N_B], tc ? nullptr : w.xn, tc ? w.xn16 : nullptr,
+                                                   w.stats1, M, 1e-5f);
+    MRNB_CHECK_LAUNCH("ln_rows_fwd_kernel");
+  }
+  // a1 = xn W1^T + b1
+  MRNB_TRY(linear_rows(d, w.xn, w.xn16, D, P + off[R_P1_W], W16 + off[R_P1_W], 2 * D, D, P + off[R_P1_B], nullptr, w.a1, 2 * D, st));
+  {
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    gelu_ln_fwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(w.a1, P + off[R_SN_W], P + off[R_SN_B], w.u, tc ? nullptr : w.vn,
+                                                   tc ? w.vn16 : nullptr, w.stats2, M, 1e-5f);
+    MRNB_CHECK_LAUNCH("gelu_ln_fwd_kernel");
+  }
+  // v2[b] = Ws . vn[b] + bs  (token mixing over n = i*T+t)
+  if (tc) {
+    MrnbTcGemm2 g{};
+    g.a = nogroup(mrnb_operand_k2d(W16 + off[R_SP_W], IT, IT, IT, 128, 1));
+    g.b = op_tok_c_mnmajor(w.vn16, d);
+    g.out32 = w.v2; g.cm = mrnb_axis(D); g.cn = mrnb_axis(1); g.c_gstride = ITD;
+    g.bias_m = P + off[R_SP_B]; g.M = (int)IT; g.N = D; g.K = (int)IT; g.groups = B; g.alpha = 1.f;
+    MRNB_TRY(mrnb_tc_gemm2(g, st));
+  } else {
     MrnbGemm g{};
     g.A = P + off[R_SP_W]; g.am = mrnb_axis(IT); g.ak = mrnb_axis(1); g.a_kfast = 1; g.sAb = 0;
     g.B = w.vn; g.bk = mrnb_axis(D); g.bn = mrnb_axis(1); g.b_kfast = 0; g.sBb = ITD;
@@ -392,15 +577,27 @@ int router_forward(const float* P, const float* x, int B, int I, int T, int D, f
     g.bias_m = P + off[R_SP_B];
     MRNB_TRY(mrnb_sgemm(g, st));
   }
-  LAUNCH_EW(mul_kernel, M * D / 4, w.u, w.v2, w.g1, M * D / 4);
-  {  // y = g1 W2^T + b2 + x
-    MrnbGemm g = mrnb_gemm_nt(w.g1, D, P + off[R_P2_W], D, w.y, D, (int)M, D, D);
-    g.bias_n = P + off[R_P2_B]; g.res = x;
-    MRNB_TRY(mrnb_sgemm(g, st));
+  {
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    LAUNCH_EW(mul_kernel, M * D / 4, w.u, w.v2, tc ? nullptr : w.g1, tc ? w.g116 : nullptr, M * D / 4);
   }
-  lnT_fwd_kernel<<<B * I, RD, 0, st>>>(w.y, P + off[R_CN_W], P + off[R_CN_B], w.gn, w.statsT, T, 1e-5f);
-  MRNB_CHECK_LAUNCH("lnT_fwd_kernel");
-  {  // g2[(b,t),(i,c)] = sum_(i',c') gn[(b,t),(i',c')] Wc[(i,c),(i',c')] + bc   (channel mixing over k = i*D+c)
+  // y = g1 W2^T + b2 + x
+  MRNB_TRY(linear_rows(d, w.g1, w.g116, D, P + off[R_P2_W], W16 + off[R_P2_W], D, D, P + off[R_P2_B], x, w.y, D, st));
+  {
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    lnT_fwd_kernel<<<B * I, RD, 0, st>>>(w.y, P + off[R_CN_W], P + off[R_CN_B], tc ? nullptr : w.gn, tc ? w.gn16 : nullptr,
+                                         w.statsT, T, 1e-5f);
+    MRNB_CHECK_LAUNCH("lnT_fwd_kernel");
+  }
+  // g2[(b,t),(i,c)] = sum_(i',c') gn[(b,t),(i',c')] Wc[(i,c),(i',c')] + bc   (channel mixing over k = i*D+c)
+  if (tc) {
+    MrnbTcGemm2 g{};
+    g.a = op_bt_ic_kmajor(w.gn16, d);
+    g.b = mrnb_operand_k2d(W16 + off[R_CP_W], ID, ID, ID, 128, 1);
+    g.out32 = w.g2; g.cm = mrnb_axis2(T, D, ITD); g.cn = mrnb_axis2(D, 1, TD);
+    g.bias_n = P + off[R_CP_B]; g.M = B * T; g.N = (int)ID; g.K = (int)ID; g.groups = 1; g.alpha = 1.f;
+    MRNB_TRY(mrnb_tc_gemm2(g, st));
+  } else {
     MrnbGemm g{};
     g.A = w.gn; g.am = mrnb_axis2(T, D, ITD); g.ak = mrnb_axis2(D, 1, TD); g.a_kfast = 1;
     g.B = P + off[R_CP_W]; g.bn = mrnb_axis(ID); g.bk = mrnb_axis(1); g.b_kfast = 1;
@@ -409,14 +606,14 @@ int router_forward(const float* P, const float* x, int B, int I, int T, int D, f
     g.bias_n = P + off[R_CP_B];
     MRNB_TRY(mrnb_sgemm(g, st));
   }
-  LAUNCH_EW(mul_kernel, M * D / 4, w.y, w.g2, w.y2, M * D / 4);
-  {  // out = y2 W3^T + b3 + x
-    MrnbGemm g = mrnb_gemm_nt(w.y2, D, P + off[R_P3_W], D, out, D, (int)M, D, D);
-    g.bias_n = P + off[R_P3_B]; g.res = x;
-    MRNB_TRY(mrnb_sgemm(g, st));
+  {
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    LAUNCH_EW(mul_kernel, M * D / 4, w.y, w.g2, tc ? nullptr : w.y2, tc ? w.y216 : nullptr, M * D / 4);
   }
+  // out = y2 W3^T + b3 + x
+  MRNB_TRY(linear_rows(d, w.y2, w.y216, D, P + off[R_P3_W], W16 + off[R_P3_W], D, D, P + off[R_P3_B], x, out, D, st));
   if (scores || gate || index) {
-    MrnbGemm g{};   // s[(b,t), j] = sum_(i,c) out[b,i,t,c] Wcr[j,(i,c)] + bcr[j]
+    MrnbGemm g{};   // s[(b,t), j] = sum_(i,c) out[b,i,t,c] Wcr[j,(i,c)] + bcr[j]     (N = I: fp32 CUDA cores)
     g.A = out; g.am = mrnb_axis2(T, D, ITD); g.ak = mrnb_axis2(D, 1, TD); g.a_kfast = 1;
     g.B = P + off[R_CR_W]; g.bn = mrnb_axis(ID); g.bk = mrnb_axis(1); g.b_kfast = 1;
     g.C = w.s; g.cm = mrnb_axis(I); g.cn = mrnb_axis(1);
@@ -430,104 +627,135 @@ int router_forward(const float* P, const float* x, int B, int I, int T, int D, f
   return MRNB_OK;
 }
 
-// Backward through DM_Router given d_out (in w.dout).  G = gradient arena (already zeroed).
-int dm_router_backward_core(const float* P, const float* x, const float* out_fwd, int B, int I, int T, int D, float* G,
-                            float* dx, RouterWs& w, cudaStream_t st) {
+// Backward through DM_Router given d_out in w.dout (+ w.dout16 in tensor-core mode).  G = zeroed gradient arena.
+int dm_router_backward_core(const float* P, const float* x, const Dims& d, float* G, float* dx, RouterWs& w, cudaStream_t st) {
   long off[MRNB_ROUTER_NPARAMS + 1];
-  router_offsets(I, T, D, off);
-  (void)out_fwd;
-  const long M = (long)B * I * T, IT = (long)I * T, ID = (long)I * D, TD = (long)T * D, ITD = IT * D;
+  router_offsets(d.I, d.T, d.D, off);
+  const int B = d.B, I = d.I, T = d.T, D = d.D;
+  const long M = d.M, IT = d.IT, ID = d.ID, TD = d.TD, ITD = d.ITD;
   const long n4 = M * D / 4;
-  auto dW_rows = [&](const float* dY, long ldy, int Nout, const float* Xin, long ldx, int Nin, float* dW) {
-    // dW[o,i] = sum_rows dY[row,o] * Xin[row,i]
-    MrnbGemm g{};
-    g.A = dY; g.am = mrnb_axis(1); g.ak = mrnb_axis(ldy); g.a_kfast = 0;
-    g.B = Xin; g.bk = mrnb_axis(ldx); g.bn = mrnb_axis(1); g.b_kfast = 0;
-    g.C = dW; g.cm = mrnb_axis(Nin); g.cn = mrnb_axis(1);
-    g.M = Nout; g.N = Nin; g.K = (int)M; g.batch = 1; g.alpha = 1.f; g.rows_per_scale = 1;
-    g.splitk = (int)((M + 2047) / 2048); if (g.splitk > 64) g.splitk = 64; if (g.splitk < 1) g.splitk = 1;
-    return mrnb_sgemm(g, st);
-  };
-  auto dX_rows = [&](const float* dY, long ldy, int Nout, const float* Wt, int Nin, float* dX, long lddx) {
-    // dX[row,i] = sum_o dY[row,o] * W[o,i]
-    MrnbGemm g{};
-    g.A = dY; g.am = mrnb_axis(ldy); g.ak = mrnb_axis(1); g.a_kfast = 1;
-    g.B = Wt; g.bk = mrnb_axis(Nin); g.bn = mrnb_axis(1); g.b_kfast = 0;
-    g.C = dX; g.cm = mrnb_axis(lddx); g.cn = mrnb_axis(1);
-    g.M = (int)M; g.N = Nin; g.K = Nout; g.batch = 1; g.splitk = 1; g.alpha = 1.f; g.rows_per_scale = 1;
-    return mrnb_sgemm(g, st);
-  };
+  const bool tc = d.tc;
+  const bf16* W16 = w.w16;
   // out = y2 W3^T + b3 + x
-  MRNB_TRY(dX_rows(w.dout, D, D, P + off[R_P3_W], D, w.dy2, D));
-  MRNB_TRY(dW_rows(w.dout, D, D, w.y2, D, D, G + off[R_P3_W]));
+  MRNB_TRY(dx_rows(d, w.dout, w.dout16, D, D, P + off[R_P3_W], W16 + off[R_P3_W], D, w.dy2, D, st));
+  MRNB_TRY(dw_rows(d, w.dout, w.dout16, D, D, w.y2, w.y216, D, D, G + off[R_P3_W], st));
   MRNB_TRY(colsum(w.dout, mrnb_axis(D), mrnb_axis(1), (int)M, D, G + off[R_P3_B], st));
-  // y2 = y * g2 : dy = dy2*g2 ; dg2 = dy2*y
-  LAUNCH_EW(mul2_kernel, n4, w.dy2, w.g2, w.y, w.dy, w.dg2, n4);
-  {  // dgn[(b,t), j] = sum_k dg2[(b,t),k] Wc[k,j]
-    MrnbGemm g{};
-    g.A = w.dg2; g.am = mrnb_axis2(T, D, ITD); g.ak = mrnb_axis2(D, 1, TD); g.a_kfast = 1;
-    g.B = P + off[R_CP_W]; g.bk = mrnb_axis(ID); g.bn = mrnb_axis(1); g.b_kfast = 0;
-    g.C = w.dgn; g.cm = mrnb_axis2(T, D, ITD); g.cn = mrnb_axis2(D, 1, TD);
-    g.M = B * T; g.N = (int)ID; g.K = (int)ID; g.batch = 1; g.splitk = 1; g.alpha = 1.f; g.rows_per_scale = 1;
-    MRNB_TRY(mrnb_sgemm(g, st));
+  {  // y2 = y * g2 : dy = dy2*g2 ; dg2 = dy2*y
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    LAUNCH_EW(mul2_kernel, n4, w.dy2, w.g2, w.y, w.dy, w.dg2, tc ? w.dg216 : nullptr, n4);
   }
-  {  // dWc[k,j] = sum_(b,t) dg2[(b,t),k] gn[(b,t),j]
-    MrnbGemm g{};
-    g.A = w.dg2; g.am = mrnb_axis2(D, 1, TD); g.ak = mrnb_axis2(T, D, ITD); g.a_kfast = 0;
-    g.B = w.gn; g.bk = mrnb_axis2(T, D, ITD); g.bn = mrnb_axis2(D, 1, TD); g.b_kfast = 0;
-    g.C = G + off[R_CP_W]; g.cm = mrnb_axis(ID); g.cn = mrnb_axis(1);
-    g.M = (int)ID; g.N = (int)ID; g.K = B * T; g.batch = 1; g.alpha = 1.f; g.rows_per_scale = 1;
-    const int tiles = cdiv(ID, 128) * cdiv(ID, 128);
-    g.splitk = tiles >= 120 ? 1 : (tiles >= 30 ? 4 : 16);
-    if ((long)B * T < 64L * g.splitk) g.splitk = 1;
-    MRNB_TRY(mrnb_sgemm(g, st));
+  if (tc) {
+    {  // dgn[(b,t), j] = sum_k dg2[(b,t),k] Wc[k,j]
+      MrnbTcGemm2 g{};
+      g.a = op_bt_ic_kmajor(w.dg216, d);
+      g.b = mrnb_operand_mn2d(W16 + off[R_CP_W], ID, ID, ID, 1);
+      g.out32 = w.dgn; g.cm = mrnb_axis2(T, D, ITD); g.cn = mrnb_axis2(D, 1, TD);
+      g.M = B * T; g.N = (int)ID; g.K = (int)ID; g.groups = 1; g.alpha = 1.f;
+      MRNB_TRY(mrnb_tc_gemm2(g, st));
+    }
+    {  // dWc[k,j] = sum_(b,t) dg2[(b,t),k] gn[(b,t),j]
+      MrnbTcGemm2 g{};
+      g.a = op_ic_bt_mnmajor(w.dg216, d);
+      g.b = op_ic_bt_mnmajor(w.gn16, d);
+      g.out32 = G + off[R_CP_W]; g.cm = mrnb_axis(ID); g.cn = mrnb_axis(1);
+      g.M = (int)ID; g.N = (int)ID; g.K = B * T; g.groups = 1; g.alpha = 1.f;
+      const int tiles = cdiv(ID, 128) * cdiv(ID, 128);
+      g.splitk = (296 + tiles - 1) / tiles;
+      MRNB_TRY(mrnb_tc_gemm2(g, st));
+    }
+  } else {
+    {
+      MrnbGemm g{};
+      g.A = w.dg2; g.am = mrnb_axis2(T, D, ITD); g.ak = mrnb_axis2(D, 1, TD); g.a_kfast = 1;
+      g.B = P + off[R_CP_W]; g.bk = mrnb_axis(ID); g.bn = mrnb_axis(1); g.b_kfast = 0;
+      g.C = w.dgn; g.cm = mrnb_axis2(T, D, ITD); g.cn = mrnb_axis2(D, 1, TD);
+      g.M = B * T; g.N = (int)ID; g.K = (int)ID; g.batch = 1; g.splitk = 1; g.alpha = 1.f; g.rows_per_scale = 1;
+      MRNB_TRY(mrnb_sgemm(g, st));
+    }
+    {
+      MrnbGemm g{};
+      g.A = w.dg2; g.am = mrnb_axis2(D, 1, TD); g.ak = mrnb_axis2(T, D, ITD); g.a_kfast = 0;
+      g.B = w.gn; g.bk = mrnb_axis2(T, D, ITD); g.bn = mrnb_axis2(D, 1, TD); g.b_kfast = 0;
+      g.C = G + off[R_CP_W]; g.cm = mrnb_axis(ID); g.cn = mrnb_axis(1);
+      g.M = (int)ID; g.N = (int)ID; g.K = B * T; g.batch = 1; g.alpha = 1.f; g.rows_per_scale = 1;
+      const int tiles = cdiv(ID, 128) * cdiv(ID, 128);
+      g.splitk = tiles >= 120 ? 1 : (tiles >= 30 ? 4 : 16);
+      if ((long)B * T < 64L * g.splitk) g.splitk = 1;
+      MRNB_TRY(mrnb_sgemm(g, st));
+    }
   }
   MRNB_TRY(colsum(w.dg2, mrnb_axis2(T, D, ITD), mrnb_axis2(D, 1, TD), B * T, (int)ID, G + off[R_CP_B], st));
-  // gn = LN_T(y)
-  lnT_bwd_kernel<<<B * I, RD, 2 * T * sizeof(float), st>>>(w.y, w.statsT, P + off[R_CN_W], w.dgn, w.dy, G + off[R_CN_W],
-                                                            G + off[R_CN_B], T);
-  MRNB_CHECK_LAUNCH("lnT_bwd_kernel");
-  // y = g1 W2^T + b2 + x
-  MRNB_TRY(dX_rows(w.dy, D, D, P + off[R_P2_W], D, w.dg1, D));
-  MRNB_TRY(dW_rows(w.dy, D, D, w.g1, D, D, G + off[R_P2_W]));
-  MRNB_TRY(colsum(w.dy, mrnb_axis(D), mrnb_axis(1), (int)M, D, G + off[R_P2_B], st));
-  // g1 = u * v2 : du = dg1*v2 ; dv2 = dg1*u
-  LAUNCH_EW(mul2_kernel, n4, w.dg1, w.v2, w.u, w.du, w.dv2, n4);
-  {  // dvn[b,m,:] = sum_n Ws[n,m] dv2[b,n,:]
-    MrnbGemm g{};
-    g.A = P + off[R_SP_W]; g.am = mrnb_axis(1); g.ak = mrnb_axis(IT); g.a_kfast = 0; g.sAb = 0;
-    g.B = w.dv2; g.bk = mrnb_axis(D); g.bn = mrnb_axis(1); g.b_kfast = 0; g.sBb = ITD;
-    g.C = w.dvn; g.cm = mrnb_axis(D); g.cn = mrnb_axis(1); g.sCb = ITD;
-    g.M = (int)IT; g.N = D; g.K = (int)IT; g.batch = B; g.splitk = 1; g.alpha = 1.f; g.rows_per_scale = 1;
-    MRNB_TRY(mrnb_sgemm(g, st));
+  {  // gn = LN_T(y)
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    lnT_bwd_kernel<<<B * I, RD, 2 * T * sizeof(float), st>>>(w.y, w.statsT, P + off[R_CN_W], w.dgn, w.dy, tc ? w.dy16 : nullptr,
+                                                              G + off[R_CN_W], G + off[R_CN_B], T);
+    MRNB_CHECK_LAUNCH("lnT_bwd_kernel");
   }
-  {  // dWs[n,m] = sum_(b,c) dv2[b,n,c] vn[b,m,c]
-    MrnbGemm g{};
-    g.A = w.dv2; g.am = mrnb_axis(D); g.ak = mrnb_axis2(D, 1, ITD); g.a_kfast = 1;
-    g.B = w.vn; g.bn = mrnb_axis(D); g.bk = mrnb_axis2(D, 1, ITD); g.b_kfast = 1;
-    g.C = G + off[R_SP_W]; g.cm = mrnb_axis(IT); g.cn = mrnb_axis(1);
-    g.M = (int)IT; g.N = (int)IT; g.K = B * D; g.batch = 1; g.alpha = 1.f; g.rows_per_scale = 1;
-    g.splitk = (B * D + 2047) / 2048; if (g.splitk > 32) g.splitk = 32; if (g.splitk < 1) g.splitk = 1;
-    MRNB_TRY(mrnb_sgemm(g, st));
+  // y = g1 W2^T + b2 + x
+  MRNB_TRY(dx_rows(d, w.dy, w.dy16, D, D, P + off[R_P2_W], W16 + off[R_P2_W], D, w.dg1, D, st));
+  MRNB_TRY(dw_rows(d, w.dy, w.dy16, D, D, w.g1, w.g116, D, D, G + off[R_P2_W], st));
+  MRNB_TRY(colsum(w.dy, mrnb_axis(D), mrnb_axis(1), (int)M, D, G + off[R_P2_B], st));
+  {  // g1 = u * v2 : du = dg1*v2 ; dv2 = dg1*u
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    LAUNCH_EW(mul2_kernel, n4, w.dg1, w.v2, w.u, w.du, w.dv2, tc ? w.dv216 : nullptr, n4);
+  }
+  if (tc) {
+    {  // dvn[b,m,:] = sum_n Ws[n,m] dv2[b,n,:]
+      MrnbTcGemm2 g{};
+      g.a = nogroup(mrnb_operand_mn2d(W16 + off[R_SP_W], IT, IT, IT, 1));
+      g.b = op_tok_c_mnmajor(w.dv216, d);
+      g.out32 = w.dvn; g.cm = mrnb_axis(D); g.cn = mrnb_axis(1); g.c_gstride = ITD;
+      g.M = (int)IT; g.N = D; g.K = (int)IT; g.groups = B; g.alpha = 1.f;
+      MRNB_TRY(mrnb_tc_gemm2(g, st));
+    }
+    {  // dWs[n,m] = sum_(b,c) dv2[b,n,c] vn[b,m,c]
+      MrnbTcGemm2 g{};
+      g.a = op_tok_bc_kmajor(w.dv216, d, 128);
+      g.b = op_tok_bc_kmajor(w.vn16, d, bn_for((int)IT));
+      g.out32 = G + off[R_SP_W]; g.cm = mrnb_axis(IT); g.cn = mrnb_axis(1);
+      g.M = (int)IT; g.N = (int)IT; g.K = B * D; g.groups = 1; g.alpha = 1.f;
+      const int tiles = cdiv(IT, 128) * cdiv(IT, bn_for((int)IT));
+      g.splitk = (296 + tiles - 1) / tiles;
+      MRNB_TRY(mrnb_tc_gemm2(g, st));
+    }
+  } else {
+    {
+      MrnbGemm g{};
+      g.A = P + off[R_SP_W]; g.am = mrnb_axis(1); g.ak = mrnb_axis(IT); g.a_kfast = 0; g.sAb = 0;
+      g.B = w.dv2; g.bk = mrnb_axis(D); g.bn = mrnb_axis(1); g.b_kfast = 0; g.sBb = ITD;
+      g.C = w.dvn; g.cm = mrnb_axis(D); g.cn = mrnb_axis(1); g.sCb = ITD;
+      g.M = (int)IT; g.N = D; g.K = (int)IT; g.batch = B; g.splitk = 1; g.alpha = 1.f; g.rows_per_scale = 1;
+      MRNB_TRY(mrnb_sgemm(g, st));
+    }
+    {
+      MrnbGemm g{};
+      g.A = w.dv2; g.am = mrnb_axis(D); g.ak = mrnb_axis2(D, 1, ITD); g.a_kfast = 1;
+      g.B = w.vn; g.bn = mrnb_axis(D); g.bk = mrnb_axis2(D, 1, ITD); g.b_kfast = 1;
+      g.C = G + off[R_SP_W]; g.cm = mrnb_axis(IT); g.cn = mrnb_axis(1);
+      g.M = (int)IT; g.N = (int)IT; g.K = B * D; g.batch = 1; g.alpha = 1.f; g.rows_per_scale = 1;
+      g.splitk = (B * D + 2047) / 2048; if (g.splitk > 32) g.splitk = 32; if (g.splitk < 1) g.splitk = 1;
+      MRNB_TRY(mrnb_sgemm(g, st));
+    }
   }
   // dbs[n] = sum_(b,c) dv2[b,n,c]
   MRNB_TRY(colsum(w.dv2, mrnb_axis2(D, 1, ITD), mrnb_axis(D), B * D, (int)IT, G + off[R_SP_B], st));
-  // vn = LN_D(GELU(a1v)); u = GELU(a1u)
-  {
+  {  // vn = LN_D(GELU(a1v)); u = GELU(a1u)
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
     const int grid = (int)((M + 8 * 16 - 1) / (8 * 16));
-    ln_rows_bwd_kernel<true><<<grid > 0 ? grid : 1, 256, 0, st>>>(w.a1 + D, 2 * D, w.stats2, P + off[R_SN_W], w.dvn,
-                                                                    w.da1 + D, 2 * D, nullptr, nullptr, G + off[R_SN_W],
-                                                                    G + off[R_SN_B], M);
+    ln_rows_bwd_kernel<true><<<grid > 0 ? grid : 1, 256, 0, st>>>(w.a1 + D, 2 * D, w.stats2, P + off[R_SN_W], w.dvn, w.da1 + D,
+                                                                    tc ? w.da116 + D : nullptr, 2 * D, nullptr, nullptr,
+                                                                    G + off[R_SN_W], G + off[R_SN_B], M);
     MRNB_CHECK_LAUNCH("ln_rows_bwd_kernel");
+    LAUNCH_EW(gelu_bwd_kernel, M * D, w.a1, w.du, w.da1, tc ? w.da116 : nullptr, M);
   }
-  LAUNCH_EW(gelu_bwd_kernel, M * D, w.a1, w.du, w.da1, M);
   // a1 = xn W1^T + b1
-  MRNB_TRY(dW_rows(w.da1, 2 * D, 2 * D, w.xn, D, D, G + off[R_P1_W]));
+  MRNB_TRY(dw_rows(d, w.da1, w.da116, 2 * D, 2 * D, w.xn, w.xn16, D, D, G + off[R_P1_W], st));
   MRNB_TRY(colsum(w.da1, mrnb_axis(2 * D), mrnb_axis(1), (int)M, 2 * D, G + off[R_P1_B], st));
-  MRNB_TRY(dX_rows(w.da1, 2 * D, 2 * D, P + off[R_P1_W], D, w.dxn, D));
+  MRNB_TRY(dx_rows(d, w.da1, w.da116, 2 * D, 2 * D, P + off[R_P1_W], W16 + off[R_P1_W], D, w.dxn, D, st));
   {  // xn = LN_D(x): dgamma/dbeta (+ dx = LNbwd + dy + dout when requested)
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
     const int grid = (int)((M + 8 * 16 - 1) / (8 * 16));
-    ln_rows_bwd_kernel<false><<<grid > 0 ? grid : 1, 256, 0, st>>>(x, D, w.stats1, P + off[R_N_W], w.dxn, dx, D,
+    ln_rows_bwd_kernel<false><<<grid > 0 ? grid : 1, 256, 0, st>>>(x, D, w.stats1, P + off[R_N_W], w.dxn, dx, nullptr, D,
                                                                      dx ? w.dy : nullptr, dx ? w.dout : nullptr,
                                                                      G + off[R_N_W], G + off[R_N_B], M);
     MRNB_CHECK_LAUNCH("ln_rows_bwd_kernel");
@@ -554,13 +782,17 @@ extern "C" size_t mrnb_router_workspace_bytes(int B, int n_experts, int T, int D
   MRNB_CHECK_ARG(D == RD, name ": only D == 256 (opt.hidden_size) is supported, got %d", D);                     \
   MRNB_CHECK_ARG(prec == MRNB_PREC_FP32 || prec == MRNB_PREC_BF16, name ": unknown precision %d", prec);
 
+// the tensor-core engine tiles rows (b,t) as 2 samples x 64 frames: SVTR's T = 64 (modules/model.py:324)
+static inline bool use_tc(int prec, int T) { return prec == MRNB_PREC_BF16 && T == 64; }
+
 extern "C" int mrnb_router_forward(const float* params, const float* x, int B, int n_experts, int T, int D, int prec,
                                    float* out, float* scores, float* gate, int* index, void* workspace,
                                    size_t workspace_bytes, cudaStream_t stream) {
   ROUTER_ARGCHECK("router_forward");
   RouterWs w = carve((char*)workspace, B, n_experts, T, D, false);
   MRNB_CHECK_ARG(workspace_bytes >= w.bytes, "router_forward: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
-  return router_forward(params, x, B, n_experts, T, D, out, scores, gate, index, w, stream);
+  Dims d(B, n_experts, T, D, use_tc(prec, T));
+  return router_forward(params, x, d, out, scores, gate, index, w, stream);
 }
 
 extern "C" int mrnb_router_backward(const float* params, const float* x, const float* gate, const float* dgate_ctc,
@@ -572,17 +804,21 @@ extern "C" int mrnb_router_backward(const float* params, const float* x, const f
   MRNB_CHECK_ARG(workspace_bytes >= w.bytes, "router_backward: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
   const int I = n_experts;
   cudaStream_t st = stream;
+  Dims d(B, I, T, D, use_tc(prec, T));
   long off[MRNB_ROUTER_NPARAMS + 1];
   const long nparam = router_offsets(I, T, D, off);
-  const long ID = (long)I * D, TD = (long)T * D, ITD = (long)I * T * D;
+  const long ID = d.ID, TD = d.TD, ITD = d.ITD;
   cudaMemsetAsync(grads, 0, nparam * sizeof(float), st);
   cudaMemsetAsync(taski_loss, 0, sizeof(float), st);
-  gate_bwd_kernel<<<cdiv(B, 256), 256, 0, st>>>(gate, dgate_ctc, domain, B, I, w.dr, taski_loss);
-  MRNB_CHECK_LAUNCH("gate_bwd_kernel");
-  route_bwd_kernel<<<T, 256, 0, st>>>(w.dr, w.s, params + off[R_ROUTE_W], B, T, I, w.ds, grads + off[R_ROUTE_W],
-                                      grads + off[R_ROUTE_B]);
-  MRNB_CHECK_LAUNCH("route_bwd_kernel");
-  {  // dWcr[j,(i,c)] = sum_(b,t) ds[(b,t),j] out[b,i,t,c]
+  {
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    gate_bwd_kernel<<<cdiv(B, 256), 256, 0, st>>>(gate, dgate_ctc, domain, B, I, w.dr, taski_loss);
+    MRNB_CHECK_LAUNCH("gate_bwd_kernel");
+    route_bwd_kernel<<<T, 256, 0, st>>>(w.dr, w.s, params + off[R_ROUTE_W], B, T, I, w.ds, grads + off[R_ROUTE_W],
+                                        grads + off[R_ROUTE_B]);
+    MRNB_CHECK_LAUNCH("route_bwd_kernel");
+  }
+  {  // dWcr[j,(i,c)] = sum_(b,t) ds[(b,t),j] out[b,i,t,c]      (M = I rows: fp32 CUDA cores, split-K)
     MrnbGemm g{};
     g.A = w.ds; g.am = mrnb_axis(1); g.ak = mrnb_axis(I); g.a_kfast = 0;
     g.B = w.out; g.bk = mrnb_axis2(T, D, ITD); g.bn = mrnb_axis2(D, 1, TD); g.b_kfast = 0;
@@ -593,14 +829,11 @@ extern "C" int mrnb_router_backward(const float* params, const float* x, const f
   }
   MRNB_TRY(colsum(w.ds, mrnb_axis(I), mrnb_axis(1), B * T, I, grads + off[R_CR_B], st));
   {  // dout[b,i,t,c] = sum_j ds[(b,t),j] Wcr[j,(i,c)]
-    MrnbGemm g{};
-    g.A = w.ds; g.am = mrnb_axis(I); g.ak = mrnb_axis(1); g.a_kfast = 1;
-    g.B = params + off[R_CR_W]; g.bk = mrnb_axis(ID); g.bn = mrnb_axis(1); g.b_kfast = 0;
-    g.C = w.dout; g.cm = mrnb_axis2(T, D, ITD); g.cn = mrnb_axis2(D, 1, TD);
-    g.M = B * T; g.N = (int)ID; g.K = I; g.batch = 1; g.splitk = 1; g.alpha = 1.f; g.rows_per_scale = 1;
-    MRNB_TRY(mrnb_sgemm(g, st));
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    const long total4 = d.M * D / 4;
+    LAUNCH_EW(dout_kernel, total4, w.ds, params + off[R_CR_W], I, T, total4, w.dout, d.tc ? w.dout16 : nullptr);
   }
-  return dm_router_backward_core(params, x, w.out, B, I, T, D, grads, nullptr, w, st);
+  return dm_router_backward_core(params, x, d, grads, nullptr, w, st);
 }
 
 extern "C" int mrnb_dm_router_backward(const float* params, const float* x, const float* d_out, int B, int n_experts,
@@ -610,9 +843,12 @@ extern "C" int mrnb_dm_router_backward(const float* params, const float* x, cons
   MRNB_CHECK_ARG(d_out && grads, "dm_router_backward: null argument");
   RouterWs w = carve((char*)workspace, B, n_experts, T, D, true);
   MRNB_CHECK_ARG(workspace_bytes >= w.bytes, "dm_router_backward: workspace too small");
+  Dims d(B, n_experts, T, D, use_tc(prec, T));
   long off[MRNB_ROUTER_NPARAMS + 1];
   const long nparam = router_offsets(n_experts, T, D, off);
-  cudaMemsetAsync(grads, 0, nparam * sizeof(float), stream);
-  cudaMemcpyAsync(w.dout, d_out, (size_t)B * n_experts * T * D * sizeof(float), cudaMemcpyDeviceToDevice, stream);
-  return dm_router_backward_core(params, x, w.out, B, n_experts, T, D, grads, dx, w, stream);
+  cudaStream_t st = stream;
+  cudaMemsetAsync(grads, 0, nparam * sizeof(float), st);
+  cudaMemcpyAsync(w.dout, d_out, (size_t)d.M * D * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  if (d.tc) LAUNCH_EW(cast16_kernel, d.M * D, d_out, w.dout16, d.M * D);
+  return dm_router_backward_core(params, x, d, grads, dx, w, st);
 }

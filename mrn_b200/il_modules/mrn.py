@@ -18,7 +18,7 @@ import torch
 
 from .. import dist as mdist
 from .. import ops
-from ..modules.model import MRNNet
+from ..modules.model import MRNNet, _precision
 from ..utils import Averager, CTCLabelConverter
 
 
@@ -209,7 +209,8 @@ class MRN(object):
         c = ops.ctc_lattice(r["lpe"], labels_index, labels_length, r["zlab"], r["E"], grad_scale=float(self.pi) / B,
                             want_dgate=True)
         grads = net.router_grad_arena()
-        taski_loss = ops.router_backward(net.router_arena(), r["features"], r["gate"], c["dgate"], indexs, grads, net._rws)
+        taski_loss = ops.router_backward(net.router_arena(), r["features"], r["gate"], c["dgate"], indexs, grads, net._rws,
+                                         prec=_precision(net.opt))
         mdist.allreduce_mean_(grads)                     # the ONE exchange step (replaces nn.DataParallel)
         self.optimizer.step()                            # clip_grad_norm_(5) + Adam + OneCycle
         return c["loss"], taski_loss

@@ -43,7 +43,7 @@ class DM_Router(nn.Module):
         sd = {"dm_router.0." + k: v for k, v in self.state_dict().items()}
         for k, name in enumerate(ops.ROUTER_PARAM_NAMES):
             if name in sd:
-                arena[off[k]:off[k + 1]] = sd[name].reshape(-1).to(device)
+                arena[off[k]:off[k] + sd[name].numel()] = sd[name].reshape(-1).to(device)
         return arena
 
     def forward(self, x):

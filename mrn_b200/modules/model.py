@@ -250,10 +250,10 @@ class MRNNet(nn.Module):
         ok = self._arena is not None and self._arena.device == device and all(
             p.data_ptr() == self._arena.data_ptr() + 4 * off[k] for k, p in enumerate(params))
         if not ok:
-            arena = torch.empty(n, dtype=torch.float32, device=device)
+            arena = torch.zeros(n, dtype=torch.float32, device=device)      # slots are padded to 8 floats
             for k, p in enumerate(params):
-                arena[off[k]:off[k + 1]] = p.data.reshape(-1).to(device)
-                p.data = arena[off[k]:off[k + 1]].view(p.shape)
+                arena[off[k]:off[k] + p.numel()] = p.data.reshape(-1).to(device)
+                p.data = arena[off[k]:off[k] + p.numel()].view(p.shape)
             self._arena = arena
             self._grad_arena = None
         return self._arena
@@ -264,7 +264,7 @@ class MRNNet(nn.Module):
             n, off = ops.router_param_offsets(len(self.model), self.patch, self.out_dim)
             self._grad_arena = torch.zeros_like(arena)
             for k, p in enumerate(self.router_parameters()):
-                p.grad = self._grad_arena[off[k]:off[k + 1]].view(p.shape)
+                p.grad = self._grad_arena[off[k]:off[k] + p.numel()].view(p.shape)
         return self._grad_arena
 
     def _sync_bn(self):

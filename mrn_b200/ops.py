@@ -92,6 +92,15 @@ def linear_bf16(a, w, bias=None, residual=None, gelu=False, out_f32=True):
     return out
 
 
+def tc_gemm_general(a, a_mn, b, b_mn, M, N, K, splitk=1):
+    """Test entry of the general tcgen05 GEMM: a is [M,K] or (a_mn) [K,M]; b is [N,K] or (b_mn) [K,N]; bf16."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_contiguous() and b.is_contiguous()
+    out = torch.zeros(M, N, device=a.device, dtype=torch.float32)
+    L.check(L.load().mrnb_tc_gemm_general(_p(a), int(a_mn), _p(b), int(b_mn), _p(out), M, N, K, int(splitk), _stream()),
+            "tc_gemm_general")
+    return out
+
+
 def layernorm(x, gamma, beta, eps):
     _chk_f32(x, gamma, beta)
     y = torch.empty_like(x)

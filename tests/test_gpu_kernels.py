@@ -63,6 +63,23 @@ def test_tcgen05_gemm_matches_fp64(M, N, K, gelu, res, f32out):
     assert rel_err(out.numpy(), ref.numpy()) < tol
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K,splitk", [(256, 128, 256, 1), (384, 320, 512, 1), (256, 256, 4096, 8), (200, 70, 192, 1)])
+def test_tcgen05_general_gemm_major_modes(a_mn, b_mn, M, N, K, splitk):
+    """K-major / MN-major operands straight from HBM (no transposed copies) + split-K atomics."""
+    ops = _ops()
+    if (a_mn and M % 8) or (b_mn and N % 8):
+        pytest.skip("MN-major operands need a 16-byte aligned leading dimension")
+    torch.manual_seed(M + 3 * N + K + a_mn * 2 + b_mn)
+    a = torch.randn(M, K).bfloat16()
+    b = (torch.randn(N, K) / math.sqrt(K)).bfloat16()
+    ref = a.double() @ b.double().T
+    ad = dev(a.T.contiguous() if a_mn else a)
+    bd = dev(b.T.contiguous() if b_mn else b)
+    out = ops.tc_gemm_general(ad, a_mn, bd, b_mn, M, N, K, splitk).cpu()
+    assert rel_err(out.numpy(), ref.numpy()) < 3e-5
+
+
 # ------------------------------------------------------------------------------------------------ LN / attention
 @pytest.mark.parametrize("D", [64, 128, 256, 512])
 def test_layernorm(D):
@@ -142,7 +159,7 @@ def _router_arena(sd, I, device="cuda"):
     n, off = ops.router_param_offsets(I)
     arena = torch.zeros(n, dtype=torch.float32)
     for k, name in enumerate(ops.ROUTER_PARAM_NAMES):
-        arena[off[k]:off[k + 1]] = sd[name].reshape(-1).float()
+        arena[off[k]:off[k] + sd[name].numel()] = sd[name].reshape(-1).float()
     return arena.to(device), off
 
 
@@ -169,8 +186,34 @@ def test_dm_router_forward_backward(name):
     for k, pname in enumerate(ops.ROUTER_PARAM_NAMES):
         if not pname.startswith("dm_router.0."):
             continue
-        got = gc[off[k]:off[k + 1]].reshape(sd[pname].shape)
+        got = gc[off[k]:off[k] + sd[pname].numel()].reshape(sd[pname].shape)
         assert rel_err(gview(got, g), g["grad." + pname[len("dm_router.0."):]]) < 5e-4, pname
+
+
+@pytest.mark.parametrize("name", ["dm_router_i3_b2", "dm_router_i6_b1"])
+def test_dm_router_tensor_core_engine(name):
+    """Router contractions on tcgen05 (bf16 operands read K-major / MN-major where they lie, fp32 accumulate, split-K
+    weight gradients): within the bf16 budget of the fp32 reference."""
+    ops = _ops()
+    from mrn_b200 import _lib as L
+    g = load_golden(name)
+    I, B, seed = int(g["I"]), int(g["B"]), int(g["seed"])
+    sd = {k: synth.synth_tensor(seed, k, s) for k, s in synth.router_shapes(I).items()}
+    x = synth.randn(seed, "router_x", (B, I, 64, 256))
+    dy = synth.randn(seed, "router_dy", (B, I, 64, 256))
+    arena, off = _router_arena(sd, I)
+    ws = ops.RouterWorkspace()
+    out, scores, gate, index = ops.router_forward(arena, dev(x), ws, with_backward=True, prec=L.PREC_BF16)
+    assert rel_err(gview(out.cpu(), g), g["out"]) < 2e-2
+    grads = torch.empty_like(arena)
+    dx = ops.dm_router_backward(arena, dev(x), dev(dy), grads, ws, want_dx=True, prec=L.PREC_BF16)
+    assert rel_err(gview(dx.cpu(), g), g["dx"]) < 3e-2
+    gc = grads.cpu()
+    for k, pname in enumerate(ops.ROUTER_PARAM_NAMES):
+        if not pname.startswith("dm_router.0."):
+            continue
+        got = gc[off[k]:off[k + 1]][:sd[pname].numel()].reshape(sd[pname].shape)
+        assert rel_err(gview(got, g), g["grad." + pname[len("dm_router.0."):]]) < 3e-2, pname
 
 
 # ------------------------------------------------------------------------------------------------ combine / CTC / decode

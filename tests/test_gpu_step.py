@@ -33,6 +33,13 @@ def build_net(cc, sd, precision="fp32"):
     return net.cuda(), opt
 
 
+def ref_numel(g, pname):
+    """Element count of a router parameter (arena slots are padded to 8 floats)."""
+    cc = [int(c) for c in g["class_counts"]]
+    shapes = synth.router_shapes(len(cc))
+    return int(np.prod(shapes[pname]))
+
+
 def _case(name):
     g = load_golden(name)
     cc = tuple(int(c) for c in g["class_counts"])
@@ -97,13 +104,13 @@ def test_stage1_step_matches_reference_golden(name):
     assert abs(float(learner.optimizer.norm) - tn) / tn < 5e-4
     params = net.router_arena().cpu()
     for k, pname in enumerate(ops.ROUTER_PARAM_NAMES):
-        got = grads[off[k]:off[k + 1]]
+        got = grads[off[k]:off[k] + ref_numel(g, pname)]
         ref = g["grad." + pname]
         scale = max(float(np.abs(ref).max()), 1e-4 * tn)
         assert np.abs(gview(got, g) - ref.reshape(-1)).max() / scale < 1e-3, pname
         if pname == "route.bias":
             continue
-        d = np.abs(gview(params[off[k]:off[k + 1]], g) - g["adam1." + pname].reshape(-1))
+        d = np.abs(gview(params[off[k]:off[k] + ref_numel(g, pname)], g) - g["adam1." + pname].reshape(-1))
         assert d.max() <= 5e-4 * 1.01 and (d > 2e-5).mean() < 1e-2, pname
 
 
