@@ -200,6 +200,9 @@ int mrnb_layernorm_f32(const float* x, float* y, const float* gamma, const float
                        cudaStream_t stream);
 int mrnb_svtr_attention_f32(const float* qkv, float* out, int groups, int N, int d, int heads, int H, int W, int local,
                             cudaStream_t stream);
+/* tcgen05 attention (bf16 mode): qkv [groups*N, 3d] bf16 -> out [groups*N, d] bf16; N % 128 == 0, head_dim 32. */
+int mrnb_svtr_attention_bf16(const void* qkv, void* out, int groups, int N, int d, int heads, int H, int W, int local,
+                             cudaStream_t stream);
 int mrnb_cast_f32_to_bf16(const float* x, void* y, long n, cudaStream_t stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,303 @@
+// SVTR mixer attention on the tensor cores (bf16 mode).   Reference: modules/svtr.py:133-152 (Attention.forward),
+// Local mixer mask :116-128.
+//
+// One CTA per (expert*sample, head, 128-query tile).  Key blocks of 128:
+//   S_j = Q K_j^T      tcgen05.mma M128 N128 K32  (Q, K_j: TMA -> 64B-swizzled K-major smem tiles)      -> TMEM cols [0,128)
+//   softmax warps: tcgen05.ld S_j, scale (+ Local window predicate on the index), running max / sum per query row
+//                  (one row per thread), P_j = exp(S_j - m) as bf16 into a 128B-swizzled K-major smem tile
+//   O_j = P_j V_j      tcgen05.mma M128 N32 K128  (V_j read where it lies: MN-major, 64B swizzle)       -> TMEM cols [128,160)
+//   acc = acc * exp(m_old - m_new) + O_j in registers; out = acc / l.
+// Warp roles: warp 0 TMA producer, warp 1 TMEM alloc + MMA issuer, warps 2..5 softmax / epilogue.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int QT = 128, KT = 128, HD = 32;
+constexpr int TILE_BYTES = 128 * HD * 2;        // 8 KiB: one Q / K / V tile
+constexpr int P_BYTES = 128 * KT * 2;           // 32 KiB
+constexpr int TMEM_COLS = 256;
+constexpr uint32_t O_COL = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return;
+    if (spin > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// layout_type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B ; sbo = byte distance between 8-row (K-major) / 8-k (MN-major) atoms
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <bool LOCAL>
+__global__ void __launch_bounds__(192)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int N, int d) {
+  constexpr int W = 64;            // SVTR token grid width for 32x256 crops (modules/svtr.py:348): shifts, not divisions
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                          // 8 KiB
+  uint8_t* sKV = smem + TILE_BYTES;            // 2 slots x (K 8 KiB + V 8 KiB)
+  uint8_t* sP = smem + TILE_BYTES + 4 * TILE_BYTES;   // 32 KiB, 1024-aligned (offset 40 KiB)
+  __shared__ __align__(8) uint64_t q_full, kv_full[2], kv_empty[2], s_full, s_empty, p_full, o_full;
+  __shared__ uint32_t tmem_base_sh;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, g = blockIdx.z;
+  const int nb = N / KT;
+  const long row0 = (long)g * N;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(&s_full, 1); mbar_init(&s_empty, 128); mbar_init(&p_full, 128); mbar_init(&o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_sh;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&q_full, TILE_BYTES);
+      tma_load_2d(sQ, &tm, &q_full, h * HD, (int)(row0 + qt * QT));
+      for (int j = 0; j < nb; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_empty[s], ((uint32_t)(j >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+        tma_load_2d(sKV + s * 2 * TILE_BYTES, &tm, &kv_full[s], d + h * HD, (int)(row0 + j * KT));
+        tma_load_2d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &tm, &kv_full[s], 2 * d + h * HD, (int)(row0 + j * KT));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // S = Q K^T : M128 N128, A and B K-major ; O = P V : M128 N32, A K-major, B MN-major
+      constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KT >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
+      constexpr uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
+      const uint64_t qdesc = make_desc(smem_u32(sQ), 512, 4);
+      const uint64_t pdesc = make_desc(smem_u32(sP), 1024, 2);
+      auto issue_s = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(&kv_full[s], (uint32_t)(j >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t kdesc = make_desc(smem_u32(sKV + s * 2 * TILE_BYTES), 512, 4);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k);
+        umma_commit(&s_full);
+      };
+      mbar_wait(&q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < nb; ++j) {
+        if (j + 1 < nb) {
+          mbar_wait(&s_empty, (uint32_t)j & 1u);          // softmax warps have pulled S_j out of TMEM
+          issue_s(j + 1);
+        }
+        mbar_wait(&p_full, (uint32_t)j & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int s = j & 1;
+        const uint64_t vdesc = make_desc(smem_u32(sKV + s * 2 * TILE_BYTES + TILE_BYTES), 512, 4);
+#pragma unroll
+        for (int k = 0; k < KT / 16; ++k) {
+          // P: two 64-key halves of 16 KiB, +32 B per 16 keys inside the 128 B row; V: +16 key rows of 64 B
+          const uint64_t pa = pdesc + (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4);
+          const uint64_t vb = vdesc + (uint64_t)((k * 16 * 64) >> 4);
+          umma_bf16(tmem_base + O_COL, pa, vb, idesc_o, k);
+        }
+        umma_commit(&kv_empty[s]);
+        umma_commit(&o_full);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                  // query row inside the tile == TMEM lane
+    const int n = qt * QT + r;                    // token index of this query
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int qh = n / W, qw = n % W;
+    const float sl2 = 0.17677669529663688110f * 1.4426950408889634f;     // 32^-0.5 * log2(e)
+    float m = -INFINITY, l = 0.f;
+    float acc[HD];
+#pragma unroll
+    for (int j = 0; j < HD; ++j) acc[j] = 0.f;
+    for (int j = 0; j < nb; ++j) {
+      mbar_wait(&s_full, (uint32_t)j & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // pass 1: block maximum of the (masked) scores
+      float bmax = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < KT / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + (uint32_t)(c * 32), v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(v[i]);
+          if (LOCAL) {
+            const int key = j * KT + c * 32 + i;
+            const int dh = key / W - qh, dw = key % W - qw;
+            if (dh < -3 || dh > 3 || dw < -5 || dw > 5) s = -INFINITY;
+          }
+          bmax = fmaxf(bmax, s);
+        }
+      }
+      const float mnew = fmaxf(m, bmax * sl2);
+      const float mref = (mnew == -INFINITY) ? 0.f : mnew;       // whole block masked so far
+      const float corr = exp2f(m - mref);                        // m = -inf -> 0
+      float bsum = 0.f;
+      // pass 2: P = exp2(s*scale*log2e - m) -> bf16 -> swizzled smem
+#pragma unroll 1
+      for (int c = 0; c < KT / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + (uint32_t)(c * 32), v);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+          if (LOCAL) {
+            const int key = j * KT + c * 32 + i;
+            const int dh = key / W - qh, dw0 = key % W - qw, dw1 = dw0 + 1;      // W is even: key, key+1 share a row
+            const bool okh = dh >= -3 && dh <= 3;
+            if (!okh || dw0 < -5 || dw0 > 5) s0 = -INFINITY;
+            if (!okh || dw1 < -5 || dw1 > 5) s1 = -INFINITY;
+          }
+          const float p0 = exp2f(fmaf(s0, sl2, -mref)), p1 = exp2f(fmaf(s1, sl2, -mref));
+          __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+          // the PV product uses the bf16-rounded probabilities: sum the same values for a consistent normaliser
+          bsum += __bfloat162float(hb.x) + __bfloat162float(hb.y);
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+        }
+        uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+        for (int p4 = 0; p4 < 4; ++p4) {
+          const int piece = ((c & 1) * 4 + p4) ^ (r & 7);
+          *reinterpret_cast<uint4*>(prow + piece * 16) = make_uint4(pk[p4 * 4], pk[p4 * 4 + 1], pk[p4 * 4 + 2], pk[p4 * 4 + 3]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&s_empty);                                      // S_j fully consumed
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy smem writes -> visible to UMMA
+      mbar_arrive(&p_full);
+      l = l * corr + bsum;
+      m = mnew;
+      mbar_wait(&o_full, (uint32_t)j & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t o[32];
+      tmem_ld32(lane_addr + O_COL, o);
+#pragma unroll
+      for (int i = 0; i < HD; ++i) acc[i] = fmaf(acc[i], corr, __uint_as_float(o[i]));
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    const float inv = 1.0f / l;
+    __nv_bfloat16* op = out + (row0 + n) * d + h * HD;
+#pragma unroll
+    for (int i = 0; i < HD; i += 8) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        __nv_bfloat162 hb = __floats2bfloat162_rn(acc[i + 2 * u] * inv, acc[i + 2 * u + 1] * inv);
+        pk[u] = *reinterpret_cast<uint32_t*>(&hb);
+      }
+      *reinterpret_cast<uint4*>(op + i) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+// qkv [groups*N, 3d] bf16 -> out [groups*N, d] bf16 ; N % 128 == 0, head_dim 32
+int mrnb_attention_tc(const void* qkv, void* out, int groups, int N, int d, int heads, int H, int W, int local, cudaStream_t st) {
+  MRNB_CHECK_ARG(qkv && out && groups > 0 && N % 128 == 0 && d == heads * HD && H * W == N && W == 64, "attention_tc: bad argument (token grid width must be 64)");
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { mrnb_set_error("attention_tc: cuTensorMapEncodeTiled unavailable"); return MRNB_ERR_UNSUPPORTED; }
+  CUtensorMap tm;
+  cuuint64_t dims[2] = {(cuuint64_t)(3 * d), (cuuint64_t)((long)groups * N)};
+  cuuint64_t strides[1] = {(cuuint64_t)(3 * d) * 2};
+  cuuint32_t box[2] = {HD, 128}, es[2] = {1, 1};
+  CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qkv), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { mrnb_set_error("attention_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return MRNB_ERR_ARG; }
+  const size_t smem = 1024 + TILE_BYTES + 4 * TILE_BYTES + P_BYTES;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  dim3 grid(N / QT, heads, groups);
+  if (local) attn_tc_kernel<true><<<grid, 192, smem, st>>>(tm, (__nv_bfloat16*)out, N, d);
+  else attn_tc_kernel<false><<<grid, 192, smem, st>>>(tm, (__nv_bfloat16*)out, N, d);
+  MRNB_CHECK_LAUNCH("attn_tc_kernel");
+  return MRNB_OK;
+}
+
+extern "C" int mrnb_svtr_attention_bf16(const void* qkv, void* out, int groups, int N, int d, int heads, int H, int W,
+                                        int local, cudaStream_t stream) {
+  return mrnb_attention_tc(qkv, out, groups, N, d, heads, H, W, local, stream);
+}

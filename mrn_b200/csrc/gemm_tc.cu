@@ -271,7 +271,8 @@ int launch_tc(const MrnbTcGemm& p, cudaStream_t st) {
   ep.res = p.res; ep.rowscale = p.rowscale; ep.rows_per_scale = p.rows_per_scale > 0 ? p.rows_per_scale : 1;
   ep.rowscale_gs = p.rowscale_gstride;
   ep.M = p.M; ep.N = p.N; ep.KB = p.K / BK; ep.gelu = p.gelu;
-  ep.stages = ep.KB < MAX_STAGES ? ep.KB : MAX_STAGES;
+  // two stages keep the tile at <= 64 KiB of smem: 3 CTAs per SM interleave their (short) K loops and epilogues
+  ep.stages = ep.KB < 2 ? ep.KB : 2;
   const size_t smem = 1024 + (size_t)ep.stages * (A_STAGE_BYTES + BN * BK * 2);
   static bool attr_set = false;
   if (!attr_set) {

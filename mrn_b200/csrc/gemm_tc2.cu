@@ -17,7 +17,7 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 64, UMMA_K = 16, STAGES = 4;
+constexpr int BM = 128, BK = 64, UMMA_K = 16, STAGES = 3;
 constexpr int A_BYTES = BM * BK * 2;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -15,6 +15,8 @@
 #include "gemm_tc.h"
 #include "svtr.h"
 
+int mrnb_attention_tc(const void* qkv, void* out, int groups, int N, int d, int heads, int H, int W, int local, cudaStream_t st);
+
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -537,9 +539,13 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
           }
           MrnbProfScope prof(MRNB_PROF_ATTN, st, 4.0 * 32 * pairs * heads * I * bc,
                              (double)I * bc * N * d * 4 * sizeof(AT));
-          if (local) attention_kernel<AT, true><<<grid, N, smem, st>>>(qkv, att, N, d, heads, H, Wd);
-          else attention_kernel<AT, false><<<grid, N, smem, st>>>(qkv, att, N, d, heads, H, Wd);
-          MRNB_CHECK_LAUNCH("attention_kernel");
+          if constexpr (sizeof(AT) == 2) {
+            MRNB_TRY(mrnb_attention_tc(qkv, att, I * bc, N, d, heads, H, Wd, local ? 1 : 0, st));     // tcgen05 path
+          } else {
+            if (local) attention_kernel<AT, true><<<grid, N, smem, st>>>(qkv, att, N, d, heads, H, Wd);
+            else attention_kernel<AT, false><<<grid, N, smem, st>>>(qkv, att, N, d, heads, H, Wd);
+            MRNB_CHECK_LAUNCH("attention_kernel");
+          }
         }
         // proj + DropPath scale + residual (in place on x)
         LinearArgs pr{};

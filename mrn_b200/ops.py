@@ -117,6 +117,15 @@ def svtr_attention(qkv, heads, H, W, local):
     return out
 
 
+def svtr_attention_bf16(qkv, heads, H, W, local):
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous()
+    G, N, d3 = qkv.shape
+    out = torch.empty(G, N, d3 // 3, device=qkv.device, dtype=torch.bfloat16)
+    L.check(L.load().mrnb_svtr_attention_bf16(_p(qkv), _p(out), G, N, d3 // 3, heads, H, W, int(local), _stream()),
+            "attention_bf16")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ SVTR experts
 _BLOCK_KEYS = ("norm1.weight", "norm1.bias", "mixer.qkv.weight", "mixer.qkv.bias", "mixer.proj.weight",
                "mixer.proj.bias", "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight",

@@ -108,6 +108,24 @@ def test_svtr_attention(stage, local):
     assert rel_err(out.numpy(), ref.numpy()) < 3e-6
 
 
+@pytest.mark.parametrize("stage,local", [(0, True), (1, True), (1, False), (2, False)])
+def test_svtr_attention_tcgen05(stage, local):
+    """Tensor-core attention (QK^T and PV on tcgen05, softmax in registers) vs fp64 on the same bf16 inputs."""
+    ops = _ops()
+    d, heads = O.SVTR_DIMS[stage], O.SVTR_HEADS[stage]
+    H, W = O.SVTR_GRID[stage]
+    N = H * W
+    torch.manual_seed(10 + stage)
+    qkv = (torch.randn(5, N, 3 * d) * 1.5).bfloat16()
+    q, k, v = qkv.double().reshape(5, N, 3, heads, 32).permute(2, 0, 3, 1, 4)
+    att = (q * 32 ** -0.5) @ k.transpose(-1, -2)
+    if local:
+        att = att + O.local_mask(H, W, dtype=torch.float64)
+    ref = (torch.softmax(att, -1) @ v).permute(0, 2, 1, 3).reshape(5, N, d)
+    out = ops.svtr_attention_bf16(dev(qkv), heads, H, W, local).float().cpu()
+    assert rel_err(out.numpy(), ref.numpy()) < 1e-2       # bf16 probabilities and bf16 output
+
+
 # ------------------------------------------------------------------------------------------------ experts
 def _expert_case(cc, B, seed):
     sd = synth.synth_state_dict(cc, seed)
