@@ -59,6 +59,21 @@ __device__ __forceinline__ float gelu_erf(float x) {
   // nn.GELU() exact form: 0.5 x (1 + erf(x / sqrt(2)))
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
+// GELU(erf form) with erf from Abramowitz-Stegun 7.1.26 (|erf error| < 1.5e-7): ~16 instructions instead of erff's
+// ~35.  Used where the result is rounded to bf16 anyway (tensor-core mode); the fp32 mode keeps erff.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = exp2f(-1.4426950408889634f * z * z);
+  const float erf_abs = fmaf(-p, e, 1.0f);
+  const float h = 0.5f * x;
+  return fmaf(h, copysignf(erf_abs, x), h);
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
   const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);

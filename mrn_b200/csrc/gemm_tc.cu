@@ -89,6 +89,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 struct TcEpi {
   const float* bias; long bias_gs;
   void* out; long ldo; long o_gs;
@@ -97,7 +109,7 @@ struct TcEpi {
   int M, N, KB, stages, gelu;
 };
 
-template <int BN, bool OUT_F32>
+template <int BN, bool OUT_F32, bool GELU>
 __global__ void __launch_bounds__(192)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcEpi ep) {
   extern __shared__ uint8_t smem_raw[];
@@ -163,58 +175,82 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(&tmem_full_bar);           // accumulator complete
     }
   } else {
-    // ---- epilogue: warps 2..5, TMEM lane quarter q = warp % 4, one output row per thread
+    // ---- epilogue: warps 2..5, TMEM lane quarter q = warp % 4.
+    // Phase A: each thread owns one accumulator row (tcgen05.ld) and parks 64 columns of it in a per-warp staging
+    // tile in shared memory (the pipeline stages are free once the accumulator is complete).
+    // Phase B: lanes own columns: half a warp covers one 64-column row segment with float4s, so bias lives in
+    // registers and the residual load / output store are fully coalesced 256-byte segments.
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
     mbar_wait(&tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    constexpr int SLD = 68;                                   // staging row stride in floats (conflict-free 16B slots)
+    float* stg = reinterpret_cast<float*>(smem) + (size_t)q * 32 * SLD;
+    const int c4 = (lane & 15) * 4, rsel = lane >> 4;
     const float* bias = ep.bias ? ep.bias + (long)g * ep.bias_gs : nullptr;
-    float rs = 1.f;
-    if (ep.rowscale && row < ep.M) rs = ep.rowscale[(long)g * ep.rowscale_gs + row / ep.rows_per_scale];
-    const long obase = (long)g * ep.o_gs + (long)row * ep.ldo;
+    const long gbase = (long)g * ep.o_gs;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);   // warp-collective: no early exit above
-      const int col0 = n0 + c0;
-      if (row >= ep.M || col0 >= ep.N) continue;
-      float v[16];
+    for (int cg = 0; cg < BN / 64; ++cg) {
+      const int colb = n0 + cg * 64;
+      if (colb >= ep.N) break;                                // warp-uniform
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float x = __uint_as_float(r[j]);
-        if (bias && col0 + j < ep.N) x += __ldg(bias + col0 + j);
-        if (ep.gelu) x = gelu_erf(x);
-        v[j] = x * rs;
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 64 + hh * 32), r);
+        float4* dst = reinterpret_cast<float4*>(stg + lane * SLD + hh * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                               __uint_as_float(r[4 * j + 3]));
       }
-      const bool full = (col0 + 16 <= ep.N);
-      if (OUT_F32) {
-        float* o = reinterpret_cast<float*>(ep.out) + obase + col0;
-        const float* rp = ep.res ? ep.res + obase + col0 : nullptr;
-        if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 t = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (rp) { const float4 rr = *reinterpret_cast<const float4*>(rp + j); t.x += rr.x; t.y += rr.y; t.z += rr.z; t.w += rr.w; }
-            *reinterpret_cast<float4*>(o + j) = t;
-          }
-        } else {
-          for (int j = 0; j < 16 && col0 + j < ep.N; ++j) o[j] = v[j] + (rp ? rp[j] : 0.f);
-        }
-      } else {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + obase + col0;
-        if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-          uint32_t pk[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            pk[j] = *reinterpret_cast<uint32_t*>(&h);
-          }
-          *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        } else {
-          for (int j = 0; j < 16 && col0 + j < ep.N; ++j) o[j] = __float2bfloat16_rn(v[j]);
+      __syncwarp();
+      const int col = colb + c4;
+      const bool cfull = col + 4 <= ep.N;
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias) {
+        if (cfull) b4 = *reinterpret_cast<const float4*>(bias + col);
+        else {
+          if (col < ep.N) b4.x = bias[col];
+          if (col + 1 < ep.N) b4.y = bias[col + 1];
+          if (col + 2 < ep.N) b4.z = bias[col + 2];
         }
       }
+#pragma unroll 4
+      for (int rr = 0; rr < 32; rr += 2) {
+        const int rl = rr + rsel;
+        const int row = m0 + q * 32 + rl;
+        if (row >= ep.M || col >= ep.N) continue;
+        float4 x = *reinterpret_cast<const float4*>(stg + rl * SLD + c4);
+        x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+        if (GELU) {
+          if (OUT_F32) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+          else { x.x = gelu_fast(x.x); x.y = gelu_fast(x.y); x.z = gelu_fast(x.z); x.w = gelu_fast(x.w); }
+        }
+        if (ep.rowscale) {
+          const float rs = ep.rowscale[(long)g * ep.rowscale_gs + row / ep.rows_per_scale];
+          x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
+        }
+        const long o = gbase + (long)row * ep.ldo + col;
+        if (OUT_F32) {
+          float* op = reinterpret_cast<float*>(ep.out) + o;
+          if (cfull && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+            if (ep.res) { const float4 rv = *reinterpret_cast<const float4*>(ep.res + o); x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w; }
+            *reinterpret_cast<float4*>(op) = x;
+          } else {
+            const float xv[4] = {x.x, x.y, x.z, x.w};
+            for (int j = 0; j < 4 && col + j < ep.N; ++j) op[j] = xv[j] + (ep.res ? ep.res[o + j] : 0.f);
+          }
+        } else {
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ep.out) + o;
+          if (cfull && ((reinterpret_cast<uintptr_t>(op) & 7) == 0)) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
+            *reinterpret_cast<uint2*>(op) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+          } else {
+            const float xv[4] = {x.x, x.y, x.z, x.w};
+            for (int j = 0; j < 4 && col + j < ep.N; ++j) op[j] = __float2bfloat16_rn(xv[j]);
+          }
+        }
+      }
+      __syncwarp();
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -260,7 +296,7 @@ int make_map(CUtensorMap* map, const void* ptr, long K, long rows, long groups, 
   return MRNB_OK;
 }
 
-template <int BN, bool OUT_F32>
+template <int BN, bool OUT_F32, bool GELU>
 int launch_tc(const MrnbTcGemm& p, cudaStream_t st) {
   CUtensorMap tmA, tmW;
   MRNB_TRY(make_map(&tmA, p.A, p.K, p.M, p.groups, p.lda, p.a_gstride, BM));
@@ -273,15 +309,18 @@ int launch_tc(const MrnbTcGemm& p, cudaStream_t st) {
   ep.M = p.M; ep.N = p.N; ep.KB = p.K / BK; ep.gelu = p.gelu;
   // two stages keep the tile at <= 64 KiB of smem: 3 CTAs per SM interleave their (short) K loops and epilogues
   ep.stages = ep.KB < 2 ? ep.KB : 2;
-  const size_t smem = 1024 + (size_t)ep.stages * (A_STAGE_BYTES + BN * BK * 2);
+  constexpr size_t STAGING = 4 * 32 * 68 * sizeof(float);     // epilogue staging tile (reuses the pipeline stages)
+  size_t smem = (size_t)ep.stages * (A_STAGE_BYTES + BN * BK * 2);
+  if (smem < STAGING) smem = STAGING;
+  smem += 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(tc_gemm_kernel<BN, OUT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(tc_gemm_kernel<BN, OUT_F32, GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          1024 + MAX_STAGES * (A_STAGE_BYTES + BN * BK * 2));
     attr_set = true;
   }
   dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), p.groups);
-  tc_gemm_kernel<BN, OUT_F32><<<grid, 192, smem, st>>>(tmA, tmW, ep);
+  tc_gemm_kernel<BN, OUT_F32, GELU><<<grid, 192, smem, st>>>(tmA, tmW, ep);
   MRNB_CHECK_LAUNCH("tc_gemm_kernel");
   return MRNB_OK;
 }
@@ -296,8 +335,12 @@ int mrnb_tc_gemm(const MrnbTcGemm& p, cudaStream_t st) {
                      (double)p.groups * (2.0 * p.M * p.K + 2.0 * p.N * p.K + (double)p.M * p.N * (p.out_f32 ? 4 : 2) +
                                          (p.res ? 4.0 * p.M * p.N : 0.0)));
   const bool wide = p.N >= 128 && (p.N % 128 == 0 || p.N > 256);
-  if (wide) return p.out_f32 ? launch_tc<128, true>(p, st) : launch_tc<128, false>(p, st);
-  return p.out_f32 ? launch_tc<64, true>(p, st) : launch_tc<64, false>(p, st);
+#define MRNB_GO(BN_)                                                                                      \
+  if (p.out_f32) return p.gelu ? launch_tc<BN_, true, true>(p, st) : launch_tc<BN_, true, false>(p, st);   \
+  return p.gelu ? launch_tc<BN_, false, true>(p, st) : launch_tc<BN_, false, false>(p, st);
+  if (wide) { MRNB_GO(128) }
+  MRNB_GO(64)
+#undef MRNB_GO
 }
 
 extern "C" int mrnb_linear_bf16(const void* A, const void* W, const float* bias, const float* residual, void* out,
