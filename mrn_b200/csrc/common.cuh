@@ -63,13 +63,15 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // ~35.  Used where the result is rounded to bf16 anyway (tensor-core mode); the fp32 mode keeps erff.
 __device__ __forceinline__ float gelu_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
   p *= t;
-  const float e = exp2f(-1.4426950408889634f * z * z);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
   const float erf_abs = fmaf(-p, e, 1.0f);
   const float h = 0.5f * x;
   return fmaf(h, copysignf(erf_abs, x), h);

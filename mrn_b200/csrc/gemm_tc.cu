@@ -28,21 +28,24 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)      // suspend-time hint: sleep in hardware, do not spin
       : "memory");
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-    if (spin > (1u << 28)) __trap();
+    if (spin > (1u << 22)) __trap();
   }
 }
 
@@ -107,28 +110,40 @@ struct TcEpi {
   const float* res;
   const float* rowscale; int rows_per_scale; long rowscale_gs;
   int M, N, KB, stages, gelu;
+  int n_tiles, m_tiles, total_tiles;
 };
 
+constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each owning half of the tile columns
+constexpr int NTHREADS = 64 + EPI_WARPS * 32;      // warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 epilogue
+constexpr int SLD = 68;                            // staging row stride in floats (16B slots conflict-free)
+constexpr int STAGING_BYTES = EPI_WARPS * 32 * SLD * 4;
+
+// Persistent kernel: CTA c walks tiles c, c + gridDim.x, ... (n fastest so neighbouring CTAs share the A tile in L2).
+// The smem ring runs across tile boundaries, and the accumulator is double buffered in TMEM so the MMAs of tile i+1
+// overlap the epilogue of tile i.
 template <int BN, bool OUT_F32, bool GELU>
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcEpi ep) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr int TMEM_COLS = 2 * BN;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_sh;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, g = blockIdx.z;
   const int stages = ep.stages, KB = ep.KB;
+  const int n_tiles = ep.n_tiles, m_tiles = ep.m_tiles;
+  const int total = ep.total_tiles;
+  float* staging = reinterpret_cast<float*>(smem + (size_t)stages * STAGE_BYTES);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
@@ -145,112 +160,163 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (uint32_t)(kb / stages) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
-        tma_load_3d(sa, &tmA, &full_bar[s], kb * BK, m0, g);
-        tma_load_3d(sa + A_STAGE_BYTES, &tmW, &full_bar[s], kb * BK, n0, g);
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int n0 = (t % n_tiles) * BN, m0 = ((t / n_tiles) % m_tiles) * BM, g = t / (n_tiles * m_tiles);
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
+          tma_load_3d(sa, &tmA, &full_bar[s], kb * BK, m0, g);
+          tma_load_3d(sa + A_STAGE_BYTES, &tmW, &full_bar[s], kb * BK, n0, g);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN);
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (uint32_t)(kb / stages) & 1u;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0;
+      int i = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
+        const int buf = i & 1;
+        mbar_wait(&tmem_empty_bar[buf], (((uint32_t)i >> 1) & 1u) ^ 1u);      // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-        const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_STAGE_BYTES);
+        const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_STAGE_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
+            umma_bf16(acc, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs have read it
+        umma_commit(&tmem_full_bar[buf]);      // accumulator complete
       }
-      umma_commit(&tmem_full_bar);           // accumulator complete
     }
   } else {
-    // ---- epilogue: warps 2..5, TMEM lane quarter q = warp % 4.
-    // Phase A: each thread owns one accumulator row (tcgen05.ld) and parks 64 columns of it in a per-warp staging
-    // tile in shared memory (the pipeline stages are free once the accumulator is complete).
-    // Phase B: lanes own columns: half a warp covers one 64-column row segment with float4s, so bias lives in
-    // registers and the residual load / output store are fully coalesced 256-byte segments.
-    const int q = warp & 3;
-    mbar_wait(&tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    constexpr int SLD = 68;                                   // staging row stride in floats (conflict-free 16B slots)
-    float* stg = reinterpret_cast<float*>(smem) + (size_t)q * 32 * SLD;
-    const int c4 = (lane & 15) * 4, rsel = lane >> 4;
-    const float* bias = ep.bias ? ep.bias + (long)g * ep.bias_gs : nullptr;
-    const long gbase = (long)g * ep.o_gs;
-#pragma unroll 1
-    for (int cg = 0; cg < BN / 64; ++cg) {
-      const int colb = n0 + cg * 64;
-      if (colb >= ep.N) break;                                // warp-uniform
+    // ---- epilogue warps: quarter q = warp % 4 (TMEM lanes 32q..32q+31), column half ch = (warp - 2) / 4.
+    // Phase A: one accumulator row per thread (tcgen05.ld) parked in a per-warp staging tile; the TMEM buffer is
+    // released as soon as it is drained.  Phase B: lanes own columns (float4 each, half a warp per row segment), so
+    // bias sits in registers and residual loads / output stores are coalesced.
+    const int ew = warp - 2;
+    const int q = warp & 3, ch = ew >> 2;
+    constexpr int CW = BN / 2;                                 // columns per epilogue warp: 64 (BN=128) or 32 (BN=64)
+    constexpr int LPR = CW / 4;                                // lanes per row segment: 16 or 8
+    constexpr int RPI = 32 / LPR;                              // rows per phase-B iteration: 2 or 4
+    float* stg = staging + (size_t)ew * 32 * SLD;
+    const int c4 = (lane % LPR) * 4, rsel = lane / LPR;
+    int i = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
+      const int n0 = (t % n_tiles) * BN, m0 = ((t / n_tiles) % m_tiles) * BM, g = t / (n_tiles * m_tiles);
+      const int buf = i & 1;
+      mbar_wait(&tmem_full_bar[buf], ((uint32_t)i >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + ch * CW);
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
+      for (int hh = 0; hh < CW / 32; ++hh) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 64 + hh * 32), r);
+        tmem_ld32(tcol + (uint32_t)(hh * 32), r);
         float4* dst = reinterpret_cast<float4*>(stg + lane * SLD + hh * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
                                __uint_as_float(r[4 * j + 3]));
       }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      const int col = colb + c4;
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);        // this warp's share of the accumulator is in smem
+      const int col = n0 + ch * CW + c4;
       const bool cfull = col + 4 <= ep.N;
+      const float* bias = ep.bias ? ep.bias + (long)g * ep.bias_gs : nullptr;
       float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (bias) {
+      if (bias && col < ep.N) {
         if (cfull) b4 = *reinterpret_cast<const float4*>(bias + col);
         else {
-          if (col < ep.N) b4.x = bias[col];
+          b4.x = bias[col];
           if (col + 1 < ep.N) b4.y = bias[col + 1];
           if (col + 2 < ep.N) b4.z = bias[col + 2];
         }
       }
-#pragma unroll 4
-      for (int rr = 0; rr < 32; rr += 2) {
-        const int rl = rr + rsel;
-        const int row = m0 + q * 32 + rl;
-        if (row >= ep.M || col >= ep.N) continue;
-        float4 x = *reinterpret_cast<const float4*>(stg + rl * SLD + c4);
-        x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
-        if (GELU) {
-          if (OUT_F32) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
-          else { x.x = gelu_fast(x.x); x.y = gelu_fast(x.y); x.z = gelu_fast(x.z); x.w = gelu_fast(x.w); }
-        }
-        if (ep.rowscale) {
-          const float rs = ep.rowscale[(long)g * ep.rowscale_gs + row / ep.rows_per_scale];
-          x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
-        }
-        const long o = gbase + (long)row * ep.ldo + col;
+      const long gbase = (long)g * ep.o_gs;
+      // interior tile with aligned rows: branch-free path (pointer increments, tile-uniform DropPath scale)
+      const bool interior = (m0 + BM <= ep.M) && (n0 + BN <= ep.N) && ((ep.ldo & 3) == 0) && ((gbase & 3) == 0) &&
+                            (!ep.rowscale || (ep.rows_per_scale % BM) == 0);
+      if (interior) {
+        const float rs = ep.rowscale ? ep.rowscale[(long)g * ep.rowscale_gs + m0 / ep.rows_per_scale] : 1.0f;
+        const float* sp = stg + rsel * SLD + c4;
+        const long o0 = gbase + (long)(m0 + q * 32 + rsel) * ep.ldo + col;
+        const long ostep = (long)RPI * ep.ldo;
         if (OUT_F32) {
-          float* op = reinterpret_cast<float*>(ep.out) + o;
-          if (cfull && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
-            if (ep.res) { const float4 rv = *reinterpret_cast<const float4*>(ep.res + o); x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w; }
-            *reinterpret_cast<float4*>(op) = x;
-          } else {
-            const float xv[4] = {x.x, x.y, x.z, x.w};
-            for (int j = 0; j < 4 && col + j < ep.N; ++j) op[j] = xv[j] + (ep.res ? ep.res[o + j] : 0.f);
+          float* op = reinterpret_cast<float*>(ep.out) + o0;
+          const float* rp = ep.res ? ep.res + o0 : nullptr;
+#pragma unroll
+          for (int itr = 0; itr < 32 / RPI; ++itr) {
+            float4 x = *reinterpret_cast<const float4*>(sp + itr * RPI * SLD);
+            x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+            if (GELU) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+            x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
+            if (rp) { const float4 rv = *reinterpret_cast<const float4*>(rp + itr * ostep); x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w; }
+            *reinterpret_cast<float4*>(op + itr * ostep) = x;
           }
         } else {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ep.out) + o;
-          if (cfull && ((reinterpret_cast<uintptr_t>(op) & 7) == 0)) {
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ep.out) + o0;
+#pragma unroll
+          for (int itr = 0; itr < 32 / RPI; ++itr) {
+            float4 x = *reinterpret_cast<const float4*>(sp + itr * RPI * SLD);
+            x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+            if (GELU) { x.x = gelu_fast(x.x); x.y = gelu_fast(x.y); x.z = gelu_fast(x.z); x.w = gelu_fast(x.w); }
+            x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
             __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
-            *reinterpret_cast<uint2*>(op) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+            *reinterpret_cast<uint2*>(op + itr * ostep) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+          }
+        }
+      } else {
+  #pragma unroll 4
+        for (int rr = 0; rr < 32; rr += RPI) {
+          const int rl = rr + rsel;
+          const int row = m0 + q * 32 + rl;
+          if (row >= ep.M || col >= ep.N) continue;
+          float4 x = *reinterpret_cast<const float4*>(stg + rl * SLD + c4);
+          x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+          if (GELU) {
+            if (OUT_F32) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+            else { x.x = gelu_fast(x.x); x.y = gelu_fast(x.y); x.z = gelu_fast(x.z); x.w = gelu_fast(x.w); }
+          }
+          if (ep.rowscale) {
+            const float rs = ep.rowscale[(long)g * ep.rowscale_gs + row / ep.rows_per_scale];
+            x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
+          }
+          const long o = gbase + (long)row * ep.ldo + col;
+          if (OUT_F32) {
+            float* op = reinterpret_cast<float*>(ep.out) + o;
+            if (cfull && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+              if (ep.res) { const float4 rv = *reinterpret_cast<const float4*>(ep.res + o); x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w; }
+              *reinterpret_cast<float4*>(op) = x;
+            } else {
+              const float xv[4] = {x.x, x.y, x.z, x.w};
+              for (int j = 0; j < 4 && col + j < ep.N; ++j) op[j] = xv[j] + (ep.res ? ep.res[o + j] : 0.f);
+            }
           } else {
-            const float xv[4] = {x.x, x.y, x.z, x.w};
-            for (int j = 0; j < 4 && col + j < ep.N; ++j) op[j] = __float2bfloat16_rn(xv[j]);
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ep.out) + o;
+            if (cfull && ((reinterpret_cast<uintptr_t>(op) & 7) == 0)) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
+              *reinterpret_cast<uint2*>(op) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+            } else {
+              const float xv[4] = {x.x, x.y, x.z, x.w};
+              for (int j = 0; j < 4 && col + j < ep.N; ++j) op[j] = __float2bfloat16_rn(xv[j]);
+            }
           }
         }
       }
-      __syncwarp();
+      __syncwarp();                                            // staging tile is reused by the next tile
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -307,20 +373,22 @@ int launch_tc(const MrnbTcGemm& p, cudaStream_t st) {
   ep.res = p.res; ep.rowscale = p.rowscale; ep.rows_per_scale = p.rows_per_scale > 0 ? p.rows_per_scale : 1;
   ep.rowscale_gs = p.rowscale_gstride;
   ep.M = p.M; ep.N = p.N; ep.KB = p.K / BK; ep.gelu = p.gelu;
-  // two stages keep the tile at <= 64 KiB of smem: 3 CTAs per SM interleave their (short) K loops and epilogues
-  ep.stages = ep.KB < 2 ? ep.KB : 2;
-  constexpr size_t STAGING = 4 * 32 * 68 * sizeof(float);     // epilogue staging tile (reuses the pipeline stages)
-  size_t smem = (size_t)ep.stages * (A_STAGE_BYTES + BN * BK * 2);
-  if (smem < STAGING) smem = STAGING;
-  smem += 1024;
+  ep.stages = ep.KB < MAX_STAGES ? ep.KB : MAX_STAGES;
+  ep.n_tiles = cdiv(p.N, BN); ep.m_tiles = cdiv(p.M, BM);
+  ep.total_tiles = ep.n_tiles * ep.m_tiles * p.groups;
+  const size_t smem = 1024 + (size_t)ep.stages * (A_STAGE_BYTES + BN * BK * 2) + STAGING_BYTES;
   static bool attr_set = false;
+  static int num_sms = 148;
   if (!attr_set) {
     cudaFuncSetAttribute(tc_gemm_kernel<BN, OUT_F32, GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         1024 + MAX_STAGES * (A_STAGE_BYTES + BN * BK * 2));
+                         1024 + MAX_STAGES * (A_STAGE_BYTES + BN * BK * 2) + STAGING_BYTES);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     attr_set = true;
   }
-  dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), p.groups);
-  tc_gemm_kernel<BN, OUT_F32, GELU><<<grid, 192, smem, st>>>(tmA, tmW, ep);
+  const int grid = ep.total_tiles < num_sms ? ep.total_tiles : num_sms;       // one persistent CTA per SM
+  tc_gemm_kernel<BN, OUT_F32, GELU><<<grid, NTHREADS, smem, st>>>(tmA, tmW, ep);
   MRNB_CHECK_LAUNCH("tc_gemm_kernel");
   return MRNB_OK;
 }
