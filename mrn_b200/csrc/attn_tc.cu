@@ -73,6 +73,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <bool LOCAL>
 __global__ void __launch_bounds__(192)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int N, int d) {
@@ -87,7 +93,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, g = blockIdx.z;
-  const int nb = N / KT;
+  const int nb_all = N / KT;
+  // Local mixer: a 128-token block is two rows of the 64-wide token grid; rows further than 3 apart never interact,
+  // so q-tile t only needs key blocks |t - j| <= 2 (CTA-uniform skip of MMAs, loads and softmax).
+  const int jb0 = LOCAL ? (qt - 2 > 0 ? qt - 2 : 0) : 0;
+  const int jb1 = LOCAL ? (qt + 3 < nb_all ? qt + 3 : nb_all) : nb_all;
+  const int nb = jb1 - jb0;
   const long row0 = (long)g * N;
 
   if (threadIdx.x == 0) {
@@ -114,8 +125,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict
         const int s = j & 1;
         mbar_wait(&kv_empty[s], ((uint32_t)(j >> 1) & 1u) ^ 1u);
         mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
-        tma_load_2d(sKV + s * 2 * TILE_BYTES, &tm, &kv_full[s], d + h * HD, (int)(row0 + j * KT));
-        tma_load_2d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &tm, &kv_full[s], 2 * d + h * HD, (int)(row0 + j * KT));
+        tma_load_2d(sKV + s * 2 * TILE_BYTES, &tm, &kv_full[s], d + h * HD, (int)(row0 + (jb0 + j) * KT));
+        tma_load_2d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &tm, &kv_full[s], 2 * d + h * HD, (int)(row0 + (jb0 + j) * KT));
       }
     }
   } else if (warp == 1) {
@@ -161,7 +172,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict
     const int r = q * 32 + lane;                  // query row inside the tile == TMEM lane
     const int n = qt * QT + r;                    // token index of this query
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int qh = n / W, qw = n % W;
+    const int qh = n >> 6, qw = n & 63;
     const float sl2 = 0.17677669529663688110f * 1.4426950408889634f;     // 32^-0.5 * log2(e)
     float m = -INFINITY, l = 0.f;
     float acc[HD];
@@ -170,21 +181,35 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict
     for (int j = 0; j < nb; ++j) {
       mbar_wait(&s_full, (uint32_t)j & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // Local window as a 32-bit validity mask per 32-key chunk (a chunk lies inside one row of the token grid):
+      // bit i set <=> |kh - qh| <= 3 and |kw0 + i - qw| <= 5.
+      uint32_t vmask[KT / 32];
+#pragma unroll
+      for (int c = 0; c < KT / 32; ++c) {
+        vmask[c] = 0xffffffffu;
+        if (LOCAL) {
+          const int key0 = (jb0 + j) * KT + c * 32;
+          const int dh = (key0 >> 6) - qh;
+          const int lo = qw - 5 - (key0 & 63), hi = qw + 5 - (key0 & 63);       // valid i in [lo, hi]
+          uint32_t mk = 0u;
+          if (dh >= -3 && dh <= 3 && hi >= 0 && lo <= 31) {
+            const int l2 = lo < 0 ? 0 : lo, h2 = hi > 31 ? 31 : hi;
+            mk = (0xffffffffu >> (31 - h2)) & (0xffffffffu << l2);
+          }
+          vmask[c] = mk;
+        }
+      }
       // pass 1: block maximum of the (masked) scores
       float bmax = -INFINITY;
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < KT / 32; ++c) {
+        if (LOCAL && __all_sync(0xffffffffu, vmask[c] == 0u)) continue;        // warp-uniform: nothing visible here
         uint32_t v[32];
         tmem_ld32(lane_addr + (uint32_t)(c * 32), v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(v[i]);
-          if (LOCAL) {
-            const int key = j * KT + c * 32 + i;
-            const int dh = key / W - qh, dw = key % W - qw;
-            if (dh < -3 || dh > 3 || dw < -5 || dw > 5) s = -INFINITY;
-          }
-          bmax = fmaxf(bmax, s);
+          const float s = __uint_as_float(v[i]);
+          if (!LOCAL || ((vmask[c] >> i) & 1u)) bmax = fmaxf(bmax, s);
         }
       }
       const float mnew = fmaxf(m, bmax * sl2);
@@ -192,26 +217,28 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict
       const float corr = exp2f(m - mref);                        // m = -inf -> 0
       float bsum = 0.f;
       // pass 2: P = exp2(s*scale*log2e - m) -> bf16 -> swizzled smem
-#pragma unroll 1
-      for (int c = 0; c < KT / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(lane_addr + (uint32_t)(c * 32), v);
-        uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-          if (LOCAL) {
-            const int key = j * KT + c * 32 + i;
-            const int dh = key / W - qh, dw0 = key % W - qw, dw1 = dw0 + 1;      // W is even: key, key+1 share a row
-            const bool okh = dh >= -3 && dh <= 3;
-            if (!okh || dw0 < -5 || dw0 > 5) s0 = -INFINITY;
-            if (!okh || dw1 < -5 || dw1 > 5) s1 = -INFINITY;
+      for (int c = 0; c < KT / 32; ++c) {
+        uint32_t pk[16];
+        if (LOCAL && __all_sync(0xffffffffu, vmask[c] == 0u)) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+        } else {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + (uint32_t)(c * 32), v);
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -mref));
+            float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, -mref));
+            if (LOCAL) {
+              if (!((vmask[c] >> i) & 1u)) p0 = 0.f;
+              if (!((vmask[c] >> (i + 1)) & 1u)) p1 = 0.f;
+            }
+            __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+            // the PV product uses the bf16-rounded probabilities: sum the same values for a consistent normaliser
+            bsum += __bfloat162float(hb.x) + __bfloat162float(hb.y);
+            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
           }
-          const float p0 = exp2f(fmaf(s0, sl2, -mref)), p1 = exp2f(fmaf(s1, sl2, -mref));
-          __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-          // the PV product uses the bf16-rounded probabilities: sum the same values for a consistent normaliser
-          bsum += __bfloat162float(hb.x) + __bfloat162float(hb.y);
-          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
         }
         uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
 #pragma unroll
