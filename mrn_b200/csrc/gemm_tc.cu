@@ -44,8 +44,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint64_t t0 = 0;
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-    if (spin > (1u << 22)) __trap();
+    if ((spin & 63u) == 63u && mrnb_wait_expired(t0)) __trap();   // > 2 s: protocol bug -> fail loudly, never hang
   }
 }
 
@@ -53,6 +54,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 
@@ -111,6 +119,8 @@ struct TcEpi {
   const float* rowscale; int rows_per_scale; long rowscale_gs;
   int M, N, KB, stages, gelu;
   int n_tiles, m_tiles, total_tiles;
+  // implicit-GEMM convolution (see MrnbTcConv)
+  int conv, rows_per_img, per_kh, cch, w_off, sh, imgs_per_group;
 };
 
 constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each owning half of the tile columns
@@ -169,7 +179,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty_bar[s], ph ^ 1u);
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
-          tma_load_3d(sa, &tmA, &full_bar[s], kb * BK, m0, g);
+          if (ep.conv) {
+            const int img = g * ep.imgs_per_group + m0 / ep.rows_per_img;
+            const int oh0 = (m0 % ep.rows_per_img) >> 6;               // 64 output columns per output row
+            const int kh = kb / ep.per_kh, j = kb % ep.per_kh;
+            tma_load_4d(sa, &tmA, &full_bar[s], (j % ep.cch) * 64, j / ep.cch + ep.w_off, oh0 * ep.sh - 1 + kh, img);
+          } else {
+            tma_load_3d(sa, &tmA, &full_bar[s], kb * BK, m0, g);
+          }
           tma_load_3d(sa + A_STAGE_BYTES, &tmW, &full_bar[s], kb * BK, n0, g);
         }
       }
@@ -362,10 +379,31 @@ int make_map(CUtensorMap* map, const void* ptr, long K, long rows, long groups, 
   return MRNB_OK;
 }
 
+int make_conv_map(CUtensorMap* map, const void* ptr, const MrnbTcConv& c) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { mrnb_set_error("tc_gemm: cuTensorMapEncodeTiled is not available from the driver"); return MRNB_ERR_UNSUPPORTED; }
+  cuuint64_t dims[4], strides[3];
+  for (int j = 0; j < 4; ++j) dims[j] = (cuuint64_t)c.dims[j];
+  for (int j = 0; j < 3; ++j) strides[j] = (cuuint64_t)c.strides[j] * 2;
+  // with a traversal stride s the box spans (n - 1) * s + 1 elements to pick up n of them
+  cuuint32_t box[4] = {64, 64, (cuuint32_t)((c.box_h - 1) * c.sh + 1), (cuuint32_t)c.box_img};
+  cuuint32_t estr[4] = {1, 1, (cuuint32_t)(c.box_h > 1 ? c.sh : 1), 1};
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || c.box_h * c.box_img * 64 != BM) {
+    mrnb_set_error("tc_gemm: bad convolution view");
+    return MRNB_ERR_ARG;
+  }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { mrnb_set_error("tc_gemm: cuTensorMapEncodeTiled (conv) failed (%d)", (int)r); return MRNB_ERR_ARG; }
+  return MRNB_OK;
+}
+
 template <int BN, bool OUT_F32, bool GELU>
 int launch_tc(const MrnbTcGemm& p, cudaStream_t st) {
   CUtensorMap tmA, tmW;
-  MRNB_TRY(make_map(&tmA, p.A, p.K, p.M, p.groups, p.lda, p.a_gstride, BM));
+  if (p.conv.enabled) MRNB_TRY(make_conv_map(&tmA, p.A, p.conv));
+  else MRNB_TRY(make_map(&tmA, p.A, p.K, p.M, p.groups, p.lda, p.a_gstride, BM));
   MRNB_TRY(make_map(&tmW, p.W, p.K, p.N, p.groups, p.ldw, p.w_gstride, BN));
   TcEpi ep;
   ep.bias = p.bias; ep.bias_gs = p.bias_gstride;
@@ -374,6 +412,8 @@ int launch_tc(const MrnbTcGemm& p, cudaStream_t st) {
   ep.rowscale_gs = p.rowscale_gstride;
   ep.M = p.M; ep.N = p.N; ep.KB = p.K / BK; ep.gelu = p.gelu;
   ep.stages = ep.KB < MAX_STAGES ? ep.KB : MAX_STAGES;
+  ep.conv = p.conv.enabled; ep.rows_per_img = p.conv.rows_per_img; ep.per_kh = p.conv.per_kh; ep.cch = p.conv.cch;
+  ep.w_off = p.conv.w_off; ep.sh = p.conv.sh; ep.imgs_per_group = p.conv.imgs_per_group;
   ep.n_tiles = cdiv(p.N, BN); ep.m_tiles = cdiv(p.M, BM);
   ep.total_tiles = ep.n_tiles * ep.m_tiles * p.groups;
   const size_t smem = 1024 + (size_t)ep.stages * (A_STAGE_BYTES + BN * BK * 2) + STAGING_BYTES;

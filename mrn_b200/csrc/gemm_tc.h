@@ -2,6 +2,21 @@
 #pragma once
 #include <cuda_runtime.h>
 
+// Implicit-GEMM convolution: the A operand is gathered by TMA straight from an NHWC bf16 activation
+// [img][h][w-slot][64-element slot] (rank-4 map, zero fill outside the image = padding).  Output rows are
+// (img, oh, ow) with ow fastest; a 128-row tile is box_h output rows x 64 columns of box_img images.
+//   k-block kb -> kh = kb / per_kh, j = kb % per_kh ; TMA coords (c, w, h, img) =
+//   ((j % cch) * 64, j / cch + w_off, oh0 * sh - 1 + kh, img0)
+struct MrnbTcConv {
+  int enabled;
+  long dims[4];        // elements: {inner (>= 64), w slots, H, images}
+  long strides[3];     // elements: {w slot, h, image}
+  int box_h, box_img;  // 128 rows = 64 w-slots x box_h x box_img
+  int sh;              // stride along h (TMA element stride)
+  int rows_per_img, per_kh, cch, w_off;
+  int imgs_per_group;
+};
+
 struct MrnbTcGemm {
   // out[g, m, n] = epi( sum_k A[g, m, k] * W[g, n, k] + bias[g, n] )     A, W: bf16, k-contiguous
   const void* A; long lda; long a_gstride;     // elements
@@ -11,6 +26,7 @@ struct MrnbTcGemm {
   const float* res;                                    // fp32 residual at the output address (out_f32 only)
   const float* rowscale; int rows_per_scale; long rowscale_gstride;   // DropPath: * rowscale[g*gs + m / rows_per_scale]
   int M, N, K, groups, gelu;
+  MrnbTcConv conv;     // optional: A is an implicit im2col view (A / lda / a_gstride ignored except A as base pointer)
 };
 
 int mrnb_tc_gemm(const MrnbTcGemm& g, cudaStream_t st);

@@ -82,9 +82,10 @@ int launch_layernorm(const float* x, long x_gs, OT* y, long y_gs, const float* g
 // Patch embedding.  conv0: 4->32, 3x3 s2 p1 on the NCHW image (shared by all experts) -> raw NHWC [I,B,16,128,32]
 // plus per-channel sum / sum-of-squares for train-mode BatchNorm.
 // ------------------------------------------------------------------------------------------------
+template <typename OT>
 __global__ void __launch_bounds__(128)
 conv0_kernel(const float* __restrict__ img, const float* __restrict__ w /*[I,32,4,3,3]*/,
-             const float* __restrict__ bias /*[I,32]*/, float* __restrict__ out, double* __restrict__ stats /*[I,32,2]*/,
+             const float* __restrict__ bias /*[I,32]*/, OT* __restrict__ out, double* __restrict__ stats /*[I,32,2]*/,
              int B) {
   // grid: (16 output rows, B, I); block: 128 threads = 128 output columns
   const int oh = blockIdx.x, b = blockIdx.y, e = blockIdx.z, ow = threadIdx.x;
@@ -105,7 +106,7 @@ conv0_kernel(const float* __restrict__ img, const float* __restrict__ w /*[I,32,
         in[c * 9 + kh * 3 + kw] = (ih >= 0 && ih < 32 && iw >= 0 && iw < 256)
                                       ? __ldg(img + (((long)b * 4 + c) * 32 + ih) * 256 + iw) : 0.f;
       }
-  float* o = out + ((((long)e * B + b) * 16 + oh) * 128 + ow) * 32;
+  OT* o = out + ((((long)e * B + b) * 16 + oh) * 128 + ow) * 32;
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   for (int oc0 = 0; oc0 < 32; oc0 += 4) {
     float r[4];
@@ -116,7 +117,12 @@ conv0_kernel(const float* __restrict__ img, const float* __restrict__ w /*[I,32,
       for (int k = 0; k < 36; ++k) a = fmaf(in[k], sw[(oc0 + u) * 36 + k], a);
       r[u] = a;
     }
-    *reinterpret_cast<float4*>(o + oc0) = make_float4(r[0], r[1], r[2], r[3]);
+    if constexpr (sizeof(OT) == 4) {
+      *reinterpret_cast<float4*>(o + oc0) = make_float4(r[0], r[1], r[2], r[3]);
+    } else {
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(r[0], r[1]), h1 = __floats2bfloat162_rn(r[2], r[3]);
+      *reinterpret_cast<uint2*>(o + oc0) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+    }
     if (stats) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -223,6 +229,52 @@ conv1_kernel(const float* __restrict__ in /*[I,B,16,128,32]*/, const float* __re
       const int c = tid >> 1, k = tid & 1, g = c >> 4, u = c & 15;
       atomicAdd(stats + ((long)e * 64 + c) * 2 + k, (double)red[2 * g][u][k] + (double)red[2 * g + 1][u][k]);
     }
+  }
+}
+
+// bf16 mode: GELU(BN(conv0 raw)) -> bf16 NHWC activation with one zero pixel on each side of every row
+// [img][16][130][32], the layout the implicit-GEMM conv1 gathers with TMA (two pixels = one 128-byte k-slot).
+__global__ void bn_gelu_pad_kernel(const __nv_bfloat16* __restrict__ raw /*[I*B,16,128,32]*/, const float* __restrict__ ss0,
+                                   __nv_bfloat16* __restrict__ act /*[I*B,16,130,32]*/, int B, long total8) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int c = (int)(i & 3) * 8;
+  const int col = (int)((i >> 2) % 130);
+  const long rowi = (i >> 2) / 130;            // img * 16 + h
+  const int e = (int)(rowi / (16L * B));
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (col >= 1 && col <= 128) {
+    const uint4 v = *reinterpret_cast<const uint4*>(raw + (rowi * 128 + (col - 1)) * 32 + c);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+    const float* ss = ss0 + (e * 32 + c) * 2;
+    uint32_t pk[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float a = gelu_erf(fmaf(__bfloat162float(h[u].x), ss[4 * u], ss[4 * u + 1]));
+      const float b2 = gelu_erf(fmaf(__bfloat162float(h[u].y), ss[4 * u + 2], ss[4 * u + 3]));
+      __nv_bfloat162 r = __floats2bfloat162_rn(a, b2);
+      pk[u] = *reinterpret_cast<uint32_t*>(&r);
+    }
+    o = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+  *reinterpret_cast<uint4*>(act + i * 8) = o;
+}
+
+// per-channel sum / sum of squares of a [I][rows][64] fp32 tensor (BatchNorm statistics of conv1), fp64 accumulation
+__global__ void __launch_bounds__(256)
+bn_stats_rows_kernel(const float* __restrict__ x, long rows, double* __restrict__ stats /*[I,64,2]*/) {
+  __shared__ double sh[4][64][2];
+  const int e = blockIdx.y, c = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const long per = (rows + gridDim.x - 1) / gridDim.x;
+  const long r0 = (long)blockIdx.x * per, r1 = r0 + per < rows ? r0 + per : rows;
+  double s1 = 0.0, s2 = 0.0;
+  const float* xp = x + (long)e * rows * 64 + c;
+  for (long r = r0 + rg; r < r1; r += 4) { const float v = xp[r * 64]; s1 += v; s2 += (double)v * v; }
+  sh[rg][c][0] = s1; sh[rg][c][1] = s2;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int cc = threadIdx.x >> 1, k = threadIdx.x & 1;
+    atomicAdd(stats + ((long)e * 64 + cc) * 2 + k, sh[0][cc][k] + sh[1][cc][k] + sh[2][cc][k] + sh[3][cc][k]);
   }
 }
 
@@ -421,7 +473,8 @@ struct Workspace {
 template <typename AT>
 size_t svtr_workspace_bytes_t(int I, int B, int Bc) {
   size_t s = 0;
-  s += align_up((size_t)I * B * 16 * 128 * 32 * 4);        // conv0 raw
+  s += align_up((size_t)I * B * 16 * 128 * 32 * 4);        // conv0 raw (fp32; bf16 mode: bf16 raw + padded bf16 activation)
+  if (sizeof(AT) == 2) s += align_up((size_t)I * B * 16 * 130 * 32 * 2);
   s += align_up((size_t)I * B * 8 * 64 * 64 * 4);          // conv1 raw
   s += align_up((size_t)I * 96 * 2 * 8);                    // stats
   s += align_up((size_t)I * 96 * 2 * 4);                    // scale/shift
@@ -446,6 +499,8 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
                  ws_bytes, svtr_workspace_bytes_t<AT>(I, B, Bc));
   Workspace W{(char*)ws, 0, ws_bytes};
   float* conv0 = W.take<float>((size_t)I * B * 16 * 128 * 32);
+  __nv_bfloat16* act0p = nullptr;
+  if (sizeof(AT) == 2) act0p = W.take<__nv_bfloat16>((size_t)I * B * 16 * 130 * 32);
   float* conv1 = W.take<float>((size_t)I * B * 8 * 64 * 64);
   double* stats = W.take<double>((size_t)I * 96 * 2);
   float* ss = W.take<float>((size_t)I * 96 * 2);
@@ -467,14 +522,44 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
     cudaMemsetAsync(stats, 0, (size_t)I * 96 * 2 * sizeof(double), st);
   }
   mrnb_prof_begin(MRNB_PROF_CONV, st, 0.0, 0.0);
-  conv0_kernel<<<dim3(16, B, I), 128, 0, st>>>(image, P.p[MRNB_P_CONV0_W], P.p[MRNB_P_CONV0_B], conv0,
-                                                bn_batch_stats ? st0 : nullptr, B);
-  MRNB_CHECK_LAUNCH("conv0_kernel");
-  bn_finalize_kernel<<<cdiv(I * 32, 128), 128, 0, st>>>(st0, P.p[MRNB_P_BN0_W], P.p[MRNB_P_BN0_B],
-                                                        (float*)P.p[MRNB_P_BN0_MEAN], (float*)P.p[MRNB_P_BN0_VAR], ss0, I,
-                                                        32, (double)B * 16 * 128, bn_batch_stats, update_running, 1e-5f);
-  MRNB_CHECK_LAUNCH("bn_finalize_kernel");
-  {
+  if constexpr (sizeof(AT) == 2) {
+    // ---- tensor-core mode: conv0 direct (K = 36) -> bf16 raw; conv1 as an implicit GEMM fed by TMA from the padded
+    // NHWC activation (K = 3 kh x 128: {kw0,kw1} and {kw2, zero} 64-element slots), BN statistics from its fp32 output.
+    __nv_bfloat16* raw0 = reinterpret_cast<__nv_bfloat16*>(conv0);
+    conv0_kernel<__nv_bfloat16><<<dim3(16, B, I), 128, 0, st>>>(image, P.p[MRNB_P_CONV0_W], P.p[MRNB_P_CONV0_B], raw0,
+                                                                  bn_batch_stats ? st0 : nullptr, B);
+    MRNB_CHECK_LAUNCH("conv0_kernel");
+    bn_finalize_kernel<<<cdiv(I * 32, 128), 128, 0, st>>>(st0, P.p[MRNB_P_BN0_W], P.p[MRNB_P_BN0_B],
+                                                          (float*)P.p[MRNB_P_BN0_MEAN], (float*)P.p[MRNB_P_BN0_VAR], ss0, I,
+                                                          32, (double)B * 16 * 128, bn_batch_stats, update_running, 1e-5f);
+    MRNB_CHECK_LAUNCH("bn_finalize_kernel");
+    const long total8 = (long)I * B * 16 * 130 * 4;
+    bn_gelu_pad_kernel<<<cdiv(total8, 256), 256, 0, st>>>(raw0, ss0, act0p, B, total8);
+    MRNB_CHECK_LAUNCH("bn_gelu_pad_kernel");
+    MRNB_CHECK_ARG(P.h[MRNB_P_CONV1_W], "svtr_forward: bf16 mode needs the GEMM-packed conv1 weight in h[MRNB_P_CONV1_W]");
+    MrnbTcGemm g{};
+    g.A = act0p; g.W = P.h[MRNB_P_CONV1_W]; g.ldw = 384; g.w_gstride = 64 * 384;
+    g.bias = P.p[MRNB_P_CONV1_B]; g.bias_gstride = 64;
+    g.out = conv1; g.ldo = 64; g.o_gstride = (long)B * 512 * 64; g.out_f32 = 1;
+    g.M = B * 512; g.N = 64; g.K = 384; g.groups = I; g.rows_per_scale = 1;
+    g.conv.enabled = 1;
+    g.conv.dims[0] = 64; g.conv.dims[1] = 65; g.conv.dims[2] = 16; g.conv.dims[3] = (long)I * B;
+    g.conv.strides[0] = 64; g.conv.strides[1] = 130 * 32; g.conv.strides[2] = 16L * 130 * 32;
+    g.conv.box_h = 2; g.conv.box_img = 1; g.conv.sh = 2; g.conv.rows_per_img = 512; g.conv.per_kh = 2; g.conv.cch = 1;
+    g.conv.w_off = 0; g.conv.imgs_per_group = B;
+    MRNB_TRY(mrnb_tc_gemm(g, st));
+    if (bn_batch_stats) {
+      bn_stats_rows_kernel<<<dim3(148, I), 256, 0, st>>>(conv1, (long)B * 512, st1);
+      MRNB_CHECK_LAUNCH("bn_stats_rows_kernel");
+    }
+  } else {
+    conv0_kernel<float><<<dim3(16, B, I), 128, 0, st>>>(image, P.p[MRNB_P_CONV0_W], P.p[MRNB_P_CONV0_B], conv0,
+                                                         bn_batch_stats ? st0 : nullptr, B);
+    MRNB_CHECK_LAUNCH("conv0_kernel");
+    bn_finalize_kernel<<<cdiv(I * 32, 128), 128, 0, st>>>(st0, P.p[MRNB_P_BN0_W], P.p[MRNB_P_BN0_B],
+                                                          (float*)P.p[MRNB_P_BN0_MEAN], (float*)P.p[MRNB_P_BN0_VAR], ss0, I,
+                                                          32, (double)B * 16 * 128, bn_batch_stats, update_running, 1e-5f);
+    MRNB_CHECK_LAUNCH("bn_finalize_kernel");
     const size_t smem = (12872 + 288 * 64) * sizeof(float);
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set = true; }
@@ -583,16 +668,37 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
       // SubSample: im2col -> conv GEMM (+bias) -> LN(eps 1e-5)
       const int Co = OUTS[sidx];
       const long orows_g = (long)bc * (H / 2) * Wd;
-      {
-        const long total4 = (long)I * orows_g * 9 * d / 4;
-        im2col_kernel<AT><<<cdiv(total4, 256), 256, 0, st>>>(x, x_gs, bc, big, H, Wd, d, total4);
-        MRNB_CHECK_LAUNCH("im2col_kernel");
-      }
       const int ps = MRNB_P_SUB0 + sidx * MRNB_PS_COUNT;
       float* cv = (x == xb) ? xall : xb;          // conv output buffer distinct from x
       // (xall chunk region is free to reuse once x has moved to xb and vice versa)
       float* cvx = (cv == xall) ? xall + (size_t)b0 * 32768 : xb;
       const long cv_gs = (cv == xall) ? (long)B * 32768 : (long)bc * 32768;
+      if constexpr (sizeof(AT) == 2) {
+        // implicit GEMM: bf16 copy of the NHWC residual stream, A tiles gathered by TMA (zero fill = padding)
+        const long tot = (long)bc * 32768;
+        for (int e = 0; e < I; ++e) {
+          cast_kernel<AT><<<cdiv(tot, 256), 256, 0, st>>>(x + e * x_gs, att + (size_t)e * tot, tot);
+          MRNB_CHECK_LAUNCH("cast_kernel");
+        }
+        MrnbTcGemm g{};
+        g.A = att; g.W = P.h[ps + MRNB_PS_CONV_W]; g.ldw = 9 * d; g.w_gstride = (long)Co * 9 * d;
+        g.bias = P.p[ps + MRNB_PS_CONV_B]; g.bias_gstride = Co;
+        g.out = cvx; g.ldo = Co; g.o_gstride = cv_gs; g.out_f32 = 1;
+        g.M = (int)orows_g; g.N = Co; g.K = 9 * d; g.groups = I; g.rows_per_scale = 1;
+        g.conv.enabled = 1;
+        g.conv.dims[0] = d; g.conv.dims[1] = Wd; g.conv.dims[2] = H; g.conv.dims[3] = (long)I * bc;
+        g.conv.strides[0] = d; g.conv.strides[1] = (long)Wd * d; g.conv.strides[2] = (long)H * Wd * d;
+        const int Ho = H / 2;
+        g.conv.box_h = Ho >= 2 ? 2 : 1; g.conv.box_img = Ho >= 2 ? 1 : 2; g.conv.sh = 2;
+        g.conv.rows_per_img = Ho * Wd; g.conv.per_kh = 3 * (d / 64); g.conv.cch = d / 64; g.conv.w_off = -1;
+        g.conv.imgs_per_group = bc;
+        MRNB_TRY(mrnb_tc_gemm(g, st));
+      } else {
+      {
+        const long total4 = (long)I * orows_g * 9 * d / 4;
+        im2col_kernel<AT><<<cdiv(total4, 256), 256, 0, st>>>(x, x_gs, bc, big, H, Wd, d, total4);
+        MRNB_CHECK_LAUNCH("im2col_kernel");
+      }
       LinearArgs cvl{};
       cvl.A = big; cvl.lda = 9 * d; cvl.a_gstride = orows_g * 9 * d;
       cvl.W32 = P.p[ps + MRNB_PS_CONV_W]; cvl.W16 = P.h[ps + MRNB_PS_CONV_W]; cvl.w_gstride = (long)Co * 9 * d;
@@ -600,6 +706,7 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
       cvl.out = cvx; cvl.ldo = Co; cvl.o_gstride = cv_gs; cvl.out_is_f32 = 1;
       cvl.M = (int)orows_g; cvl.N = Co; cvl.K = 9 * d; cvl.groups = I;
       MRNB_TRY(linear<AT>(cvl, st));
+      }
       if (sidx < 2) {
         // LN in place (fp32 -> fp32) : next stage's residual stream
         MRNB_TRY(launch_layernorm<float>(cvx, cv_gs, cvx, cv_gs, P.p[ps + MRNB_PS_NORM_W], P.p[ps + MRNB_PS_NORM_B],

@@ -182,6 +182,14 @@ class SvtrPack:
             for k, nm in enumerate(("weight", "bias", "running_mean", "running_var")):
                 put(base + k, stack(f"patch_embed.proj.{idx}.{nm}"))
         put(L.P_CONV1_W, stack("patch_embed.proj.3.weight", permute=(0, 2, 3, 1)))
+        if prec == L.PREC_BF16:
+            # implicit-GEMM layout of conv1: k = kh*128 + kw*32 + c with a zero fourth tap ({kw0,kw1}, {kw2,0} slots)
+            w = self.slot_tensors[L.P_CONV1_W]                                   # [I,64,3,3,32]
+            wg = torch.zeros(n_experts, 64, 3, 4, 32, device=self.device, dtype=torch.float32)
+            wg[:, :, :, :3, :] = w
+            h = cast_bf16(wg.reshape(n_experts, 64, 384).contiguous())
+            self.tensors.append(h)
+            self.struct.h[L.P_CONV1_W] = h.data_ptr()
         put(L.P_CONV1_B, stack("patch_embed.proj.3.bias"))
         for b, name in enumerate(_BLOCK_NAMES):
             for k, key in enumerate(_BLOCK_KEYS):
