@@ -234,6 +234,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
       const int n0 = (t % n_tiles) * BN, m0 = ((t / n_tiles) % m_tiles) * BM, g = t / (n_tiles * m_tiles);
       const int buf = i & 1;
+      const int col = n0 + ch * CW + c4;
+      const long gbase = (long)g * ep.o_gs;
+      // interior tile with aligned rows: branch-free path (pointer increments, tile-uniform DropPath scale)
+      const bool interior = (m0 + BM <= ep.M) && (n0 + BN <= ep.N) && ((ep.ldo & 3) == 0) && ((gbase & 3) == 0) &&
+                            (!ep.rowscale || (ep.rows_per_scale % BM) == 0);
+      const long o0 = gbase + (long)(m0 + q * 32 + rsel) * ep.ldo + col;
+      const long ostep = (long)RPI * ep.ldo;
+      // residual rows of this tile are known before the accumulator is: issue all loads now so their HBM latency
+      // overlaps the MMA wait and the TMEM drain
+      float4 rv[32 / RPI];
+      const bool pre_res = OUT_F32 && interior && ep.res != nullptr;
+      if (pre_res) {
+        const float* rp = ep.res + o0;
+#pragma unroll
+        for (int itr = 0; itr < 32 / RPI; ++itr) rv[itr] = *reinterpret_cast<const float4*>(rp + itr * ostep);
+      }
       mbar_wait(&tmem_full_bar[buf], ((uint32_t)i >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + ch * CW);
@@ -250,7 +266,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);        // this warp's share of the accumulator is in smem
-      const int col = n0 + ch * CW + c4;
       const bool cfull = col + 4 <= ep.N;
       const float* bias = ep.bias ? ep.bias + (long)g * ep.bias_gs : nullptr;
       float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -262,25 +277,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (col + 2 < ep.N) b4.z = bias[col + 2];
         }
       }
-      const long gbase = (long)g * ep.o_gs;
-      // interior tile with aligned rows: branch-free path (pointer increments, tile-uniform DropPath scale)
-      const bool interior = (m0 + BM <= ep.M) && (n0 + BN <= ep.N) && ((ep.ldo & 3) == 0) && ((gbase & 3) == 0) &&
-                            (!ep.rowscale || (ep.rows_per_scale % BM) == 0);
       if (interior) {
         const float rs = ep.rowscale ? ep.rowscale[(long)g * ep.rowscale_gs + m0 / ep.rows_per_scale] : 1.0f;
         const float* sp = stg + rsel * SLD + c4;
-        const long o0 = gbase + (long)(m0 + q * 32 + rsel) * ep.ldo + col;
-        const long ostep = (long)RPI * ep.ldo;
         if (OUT_F32) {
           float* op = reinterpret_cast<float*>(ep.out) + o0;
-          const float* rp = ep.res ? ep.res + o0 : nullptr;
 #pragma unroll
           for (int itr = 0; itr < 32 / RPI; ++itr) {
             float4 x = *reinterpret_cast<const float4*>(sp + itr * RPI * SLD);
             x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
             if (GELU) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
             x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
-            if (rp) { const float4 rv = *reinterpret_cast<const float4*>(rp + itr * ostep); x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w; }
+            if (pre_res) { x.x += rv[itr].x; x.y += rv[itr].y; x.z += rv[itr].z; x.w += rv[itr].w; }
             *reinterpret_cast<float4*>(op + itr * ostep) = x;
           }
         } else {
