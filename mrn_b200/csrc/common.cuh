@@ -59,22 +59,19 @@ __device__ __forceinline__ float gelu_erf(float x) {
   // nn.GELU() exact form: 0.5 x (1 + erf(x / sqrt(2)))
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
-// GELU(erf form) with erf from Abramowitz-Stegun 7.1.26 (|erf error| < 1.5e-7): ~16 instructions instead of erff's
-// ~35.  Used where the result is rounded to bf16 anyway (tensor-core mode); the fp32 mode keeps erff.
+// erf-form GELU for values that are rounded to bf16 afterwards (tensor-core mode): x * Phi(x) with
+// Phi(x) = 0.5 (1 + tanh(q(x))), q an odd minimax polynomial fitted to atanh(erf(x / sqrt 2)) on [0, 7]
+// (max |error| of x*Phi(x) 2.5e-5, i.e. 20x tighter than the usual tanh-GELU and far below bf16 rounding),
+// evaluated with the hardware tanh (MUFU.TANH): 9 instructions instead of erff's ~35.  fp32 mode keeps erff.
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float xc = fminf(fmaxf(x, -7.0f), 7.0f);
+  const float x2 = xc * xc;
+  float p = fmaf(x2, -3.51516867e-4f, 3.70056465e-2f);
+  p = fmaf(x2, p, 0.797507884f);
   float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
-  const float erf_abs = fmaf(-p, e, 1.0f);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(xc * p));
   const float h = 0.5f * x;
-  return fmaf(h, copysignf(erf_abs, x), h);
+  return fmaf(h, t, h);
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));

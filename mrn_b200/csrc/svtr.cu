@@ -27,45 +27,77 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x, long x_gs, OT* y, long y_gs, const float* __restrict__ gamma,
                  const float* __restrict__ beta, long rows, long rows_per_group, float eps) {
   constexpr int VPT = D / 32;
-  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  constexpr int RPW = 4;                       // rows per warp: all loads are issued before the first reduction
+  const long row0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const long grp = row / rows_per_group;
-  const long rin = row % rows_per_group;
-  const float* xr = x + grp * x_gs + rin * D;
-  float v[VPT];
-  if constexpr (VPT >= 4) {
+  float v[RPW][VPT];
 #pragma unroll
-    for (int c = 0; c < VPT / 4; ++c) {
-      const float4 t = *reinterpret_cast<const float4*>(xr + c * 128 + lane * 4);
-      v[c * 4] = t.x; v[c * 4 + 1] = t.y; v[c * 4 + 2] = t.z; v[c * 4 + 3] = t.w;
+  for (int r = 0; r < RPW; ++r) {
+    const long row = row0 + r;
+    if (row < rows) {
+      const float* xr = x + (row / rows_per_group) * x_gs + (row % rows_per_group) * D;
+      if constexpr (VPT >= 4) {
+#pragma unroll
+        for (int c = 0; c < VPT / 4; ++c) {
+          const float4 t = *reinterpret_cast<const float4*>(xr + c * 128 + lane * 4);
+          v[r][c * 4] = t.x; v[r][c * 4 + 1] = t.y; v[r][c * 4 + 2] = t.z; v[r][c * 4 + 3] = t.w;
+        }
+      } else {
+        const float2 t = *reinterpret_cast<const float2*>(xr + lane * 2);
+        v[r][0] = t.x; v[r][1] = t.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) v[r][j] = 0.f;
     }
-  } else {
-    const float2 t = *reinterpret_cast<const float2*>(xr + lane * 2);
-    v[0] = t.x; v[1] = t.y;
   }
-  float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < VPT; ++j) s += v[j];
-  const float mean = warp_sum(s) * (1.0f / D);
-  float q = 0.f;
+  for (int r = 0; r < RPW; ++r) {
+    const long row = row0 + r;
+    float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < VPT; ++j) { const float d = v[j] - mean; q = fmaf(d, d, q); }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
-  const float* g = gamma + grp * D;
-  const float* bt = beta + grp * D;
-  OT* yr = y + grp * y_gs + rin * D;
+    for (int j = 0; j < VPT; ++j) s += v[r][j];
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
 #pragma unroll
-  for (int j = 0; j < VPT; ++j) {
-    const int idx = (VPT >= 4) ? ((j / 4) * 128 + lane * 4 + (j % 4)) : (lane * 2 + j);
-    yr[idx] = from_f32<OT>((v[j] - mean) * rstd * g[idx] + bt[idx]);
+    for (int j = 0; j < VPT; ++j) { const float d = v[r][j] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+    if (row >= rows) continue;
+    const long grp = row / rows_per_group;
+    const float* g = gamma + grp * D;
+    const float* bt = beta + grp * D;
+    OT* yr = y + grp * y_gs + (row % rows_per_group) * D;
+    if constexpr (VPT >= 4) {
+#pragma unroll
+      for (int c = 0; c < VPT / 4; ++c) {
+        const int idx = c * 128 + lane * 4;
+        const float4 g4 = *reinterpret_cast<const float4*>(g + idx), b4 = *reinterpret_cast<const float4*>(bt + idx);
+        const float o0 = (v[r][c * 4] - mean) * rstd * g4.x + b4.x, o1 = (v[r][c * 4 + 1] - mean) * rstd * g4.y + b4.y;
+        const float o2 = (v[r][c * 4 + 2] - mean) * rstd * g4.z + b4.z, o3 = (v[r][c * 4 + 3] - mean) * rstd * g4.w + b4.w;
+        if constexpr (sizeof(OT) == 4) {
+          *reinterpret_cast<float4*>(yr + idx) = make_float4(o0, o1, o2, o3);
+        } else {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
+          *reinterpret_cast<uint2*>(yr + idx) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        }
+      }
+    } else {
+      const int idx = lane * 2;
+      const float o0 = (v[r][0] - mean) * rstd * g[idx] + bt[idx], o1 = (v[r][1] - mean) * rstd * g[idx + 1] + bt[idx + 1];
+      if constexpr (sizeof(OT) == 4) {
+        *reinterpret_cast<float2*>(yr + idx) = make_float2(o0, o1);
+      } else {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1);
+        *reinterpret_cast<uint32_t*>(yr + idx) = *reinterpret_cast<uint32_t*>(&h0);
+      }
+    }
   }
 }
 
 template <typename OT>
 int launch_layernorm(const float* x, long x_gs, OT* y, long y_gs, const float* gamma, const float* beta, long rows,
                      long rows_per_group, int D, float eps, cudaStream_t st) {
-  const int grid = cdiv(rows, 8);
+  const int grid = cdiv(rows, 8 * 4);
   MrnbProfScope prof(MRNB_PROF_LN, st, 0.0, (double)rows * D * (4 + sizeof(OT)));
   switch (D) {
     case 64: layernorm_kernel<OT, 64><<<grid, 256, 0, st>>>(x, x_gs, y, y_gs, gamma, beta, rows, rows_per_group, eps); break;
@@ -402,6 +434,17 @@ __global__ void im2col_kernel(const float* __restrict__ x, long x_gs, int bc, AT
   o[0] = from_f32<AT>(v.x); o[1] = from_f32<AT>(v.y); o[2] = from_f32<AT>(v.z); o[3] = from_f32<AT>(v.w);
 }
 
+// bf16 copy of a grouped fp32 tensor: y[g][i] = x[g * x_gs + i], 4 elements per thread
+__global__ void cast_groups_kernel(const float* __restrict__ x, long x_gs, __nv_bfloat16* __restrict__ y, long per_group4,
+                                   long total4) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const long g = i / per_group4, r = i % per_group4;
+  const float4 v = *reinterpret_cast<const float4*>(x + g * x_gs + r * 4);
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(y + i * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+}
+
 template <typename AT>
 __global__ void cast_kernel(const float* __restrict__ x, AT* __restrict__ y, long n) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -676,10 +719,9 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
       if constexpr (sizeof(AT) == 2) {
         // implicit GEMM: bf16 copy of the NHWC residual stream, A tiles gathered by TMA (zero fill = padding)
         const long tot = (long)bc * 32768;
-        for (int e = 0; e < I; ++e) {
-          cast_kernel<AT><<<cdiv(tot, 256), 256, 0, st>>>(x + e * x_gs, att + (size_t)e * tot, tot);
-          MRNB_CHECK_LAUNCH("cast_kernel");
-        }
+        cast_groups_kernel<<<cdiv(tot / 4 * I, 256), 256, 0, st>>>(x, x_gs, reinterpret_cast<__nv_bfloat16*>(att), tot / 4,
+                                                                    tot / 4 * I);
+        MRNB_CHECK_LAUNCH("cast_groups_kernel");
         MrnbTcGemm g{};
         g.A = att; g.W = P.h[ps + MRNB_PS_CONV_W]; g.ldw = 9 * d; g.w_gstride = (long)Co * 9 * d;
         g.bias = P.p[ps + MRNB_PS_CONV_B]; g.bias_gstride = Co;
