@@ -119,6 +119,8 @@ struct TcEpi {
   const float* rowscale; int rows_per_scale; long rowscale_gs;
   int M, N, KB, stages, gelu;
   int n_tiles, m_tiles, total_tiles;
+  // fused LayerNorm of the output rows (LNF kernels): bf16 ln_out[g][row][N], gamma/beta [groups][N]
+  __nv_bfloat16* ln_out; long ln_gs; const float* ln_gamma; const float* ln_beta; float ln_eps;
   // implicit-GEMM convolution (see MrnbTcConv)
   int conv, rows_per_img, per_kh, cch, w_off, sh, imgs_per_group;
 };
@@ -131,7 +133,7 @@ constexpr int STAGING_BYTES = EPI_WARPS * 32 * SLD * 4;
 // Persistent kernel: CTA c walks tiles c, c + gridDim.x, ... (n fastest so neighbouring CTAs share the A tile in L2).
 // The smem ring runs across tile boundaries, and the accumulator is double buffered in TMEM so the MMAs of tile i+1
 // overlap the epilogue of tile i.
-template <int BN, bool OUT_F32, bool GELU>
+template <int BN, bool OUT_F32, bool GELU, bool LNF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcEpi ep) {
   extern __shared__ uint8_t smem_raw[];
@@ -144,6 +146,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_sh;
+  __shared__ float ln_part[2][4][2][32];        // [pass][row quarter][column half][row]: LayerNorm partial sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stages = ep.stages, KB = ep.KB;
@@ -290,6 +293,48 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
             if (pre_res) { x.x += rv[itr].x; x.y += rv[itr].y; x.z += rv[itr].z; x.w += rv[itr].w; }
             *reinterpret_cast<float4*>(op + itr * ostep) = x;
+            if (LNF) *reinterpret_cast<float4*>(stg + (rsel + itr * RPI) * SLD + c4) = x;      // keep x_new for the LN passes
+          }
+          if (LNF) {
+            // Fused LayerNorm of the freshly written rows (the tile spans the whole row: N == BN).  Two-pass statistics;
+            // the two warps that share a row (column halves) exchange partial sums through shared memory.
+            constexpr int NIT = 32 / RPI;
+            const float invn = 1.0f / (float)BN;
+            float mean[NIT], rstd[NIT];
+#pragma unroll
+            for (int itr = 0; itr < NIT; ++itr) {
+              const float4 x = *reinterpret_cast<const float4*>(sp + itr * RPI * SLD);
+              float sres = (x.x + x.y) + (x.z + x.w);
+#pragma unroll
+              for (int o = LPR / 2; o > 0; o >>= 1) sres += __shfl_xor_sync(0xffffffffu, sres, o);
+              if ((lane % LPR) == 0) ln_part[0][q][ch][rsel + itr * RPI] = sres;
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+#pragma unroll
+            for (int itr = 0; itr < NIT; ++itr) {
+              const int rl = rsel + itr * RPI;
+              mean[itr] = (ln_part[0][q][0][rl] + ln_part[0][q][1][rl]) * invn;
+              const float4 x = *reinterpret_cast<const float4*>(sp + itr * RPI * SLD);
+              const float d0 = x.x - mean[itr], d1 = x.y - mean[itr], d2 = x.z - mean[itr], d3 = x.w - mean[itr];
+              float sq = fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3);
+#pragma unroll
+              for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+              if ((lane % LPR) == 0) ln_part[1][q][ch][rl] = sq;
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+            const float4 g4 = *reinterpret_cast<const float4*>(ep.ln_gamma + (long)g * BN + ch * CW + c4);
+            const float4 t4 = *reinterpret_cast<const float4*>(ep.ln_beta + (long)g * BN + ch * CW + c4);
+            __nv_bfloat16* lp = ep.ln_out + (long)g * ep.ln_gs + (long)(m0 + q * 32 + rsel) * BN + ch * CW + c4;
+#pragma unroll
+            for (int itr = 0; itr < NIT; ++itr) {
+              const int rl = rsel + itr * RPI;
+              rstd[itr] = rsqrtf((ln_part[1][q][0][rl] + ln_part[1][q][1][rl]) * invn + ep.ln_eps);
+              const float4 x = *reinterpret_cast<const float4*>(sp + itr * RPI * SLD);
+              const float y0 = (x.x - mean[itr]) * rstd[itr] * g4.x + t4.x, y1 = (x.y - mean[itr]) * rstd[itr] * g4.y + t4.y;
+              const float y2 = (x.z - mean[itr]) * rstd[itr] * g4.z + t4.z, y3 = (x.w - mean[itr]) * rstd[itr] * g4.w + t4.w;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
+              *reinterpret_cast<uint2*>(lp + (long)itr * RPI * BN) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+            }
           }
         } else {
           __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ep.out) + o0;
@@ -407,7 +452,7 @@ int make_conv_map(CUtensorMap* map, const void* ptr, const MrnbTcConv& c) {
   return MRNB_OK;
 }
 
-template <int BN, bool OUT_F32, bool GELU>
+template <int BN, bool OUT_F32, bool GELU, bool LNF>
 int launch_tc(const MrnbTcGemm& p, cudaStream_t st) {
   CUtensorMap tmA, tmW;
   if (p.conv.enabled) MRNB_TRY(make_conv_map(&tmA, p.A, p.conv));
@@ -420,6 +465,7 @@ int launch_tc(const MrnbTcGemm& p, cudaStream_t st) {
   ep.rowscale_gs = p.rowscale_gstride;
   ep.M = p.M; ep.N = p.N; ep.KB = p.K / BK; ep.gelu = p.gelu;
   ep.stages = ep.KB < MAX_STAGES ? ep.KB : MAX_STAGES;
+  ep.ln_out = (__nv_bfloat16*)p.ln_out; ep.ln_gs = p.ln_gstride; ep.ln_gamma = p.ln_gamma; ep.ln_beta = p.ln_beta; ep.ln_eps = p.ln_eps;
   ep.conv = p.conv.enabled; ep.rows_per_img = p.conv.rows_per_img; ep.per_kh = p.conv.per_kh; ep.cch = p.conv.cch;
   ep.w_off = p.conv.w_off; ep.sh = p.conv.sh; ep.imgs_per_group = p.conv.imgs_per_group;
   ep.n_tiles = cdiv(p.N, BN); ep.m_tiles = cdiv(p.M, BM);
@@ -428,7 +474,7 @@ int launch_tc(const MrnbTcGemm& p, cudaStream_t st) {
   static bool attr_set = false;
   static int num_sms = 148;
   if (!attr_set) {
-    cudaFuncSetAttribute(tc_gemm_kernel<BN, OUT_F32, GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(tc_gemm_kernel<BN, OUT_F32, GELU, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          1024 + MAX_STAGES * (A_STAGE_BYTES + BN * BK * 2) + STAGING_BYTES);
     int dev = 0;
     cudaGetDevice(&dev);
@@ -436,7 +482,7 @@ int launch_tc(const MrnbTcGemm& p, cudaStream_t st) {
     attr_set = true;
   }
   const int grid = ep.total_tiles < num_sms ? ep.total_tiles : num_sms;       // one persistent CTA per SM
-  tc_gemm_kernel<BN, OUT_F32, GELU><<<grid, NTHREADS, smem, st>>>(tmA, tmW, ep);
+  tc_gemm_kernel<BN, OUT_F32, GELU, LNF><<<grid, NTHREADS, smem, st>>>(tmA, tmW, ep);
   MRNB_CHECK_LAUNCH("tc_gemm_kernel");
   return MRNB_OK;
 }
@@ -451,9 +497,16 @@ int mrnb_tc_gemm(const MrnbTcGemm& p, cudaStream_t st) {
                      (double)p.groups * (2.0 * p.M * p.K + 2.0 * p.N * p.K + (double)p.M * p.N * (p.out_f32 ? 4 : 2) +
                                          (p.res ? 4.0 * p.M * p.N : 0.0)));
   const bool wide = p.N >= 128 && (p.N % 128 == 0 || p.N > 256);
-#define MRNB_GO(BN_)                                                                                      \
-  if (p.out_f32) return p.gelu ? launch_tc<BN_, true, true>(p, st) : launch_tc<BN_, true, false>(p, st);   \
-  return p.gelu ? launch_tc<BN_, false, true>(p, st) : launch_tc<BN_, false, false>(p, st);
+  if (p.ln_out) {
+    // fused LayerNorm: the tile must span whole rows and every tile must take the interior path
+    MRNB_CHECK_ARG(p.out_f32 && !p.gelu && (p.N == 64 || p.N == 128) && p.M % BM == 0 && p.ldo % 4 == 0 && p.o_gstride % 4 == 0 &&
+                   p.ln_gamma && p.ln_beta && (!p.rowscale || p.rows_per_scale % BM == 0),
+                   "tc_gemm: fused LayerNorm needs N in {64,128}, M %% 128 == 0, aligned fp32 output");
+    return p.N == 128 ? launch_tc<128, true, false, true>(p, st) : launch_tc<64, true, false, true>(p, st);
+  }
+#define MRNB_GO(BN_)                                                                                              \
+  if (p.out_f32) return p.gelu ? launch_tc<BN_, true, true, false>(p, st) : launch_tc<BN_, true, false, false>(p, st);   \
+  return p.gelu ? launch_tc<BN_, false, true, false>(p, st) : launch_tc<BN_, false, false, false>(p, st);
   if (wide) { MRNB_GO(128) }
   MRNB_GO(64)
 #undef MRNB_GO

@@ -26,6 +26,8 @@ struct MrnbTcGemm {
   const float* res;                                    // fp32 residual at the output address (out_f32 only)
   const float* rowscale; int rows_per_scale; long rowscale_gstride;   // DropPath: * rowscale[g*gs + m / rows_per_scale]
   int M, N, K, groups, gelu;
+  // optional fused LayerNorm of the fp32 output rows (N == 64 or 128): bf16 ln_out[g][m][N] = LN(out row) * gamma[g] + beta[g]
+  void* ln_out; long ln_gstride; const float* ln_gamma; const float* ln_beta; float ln_eps;
   MrnbTcConv conv;     // optional: A is an implicit im2col view (A / lda / a_gstride ignored except A as base pointer)
 };
 

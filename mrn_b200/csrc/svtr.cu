@@ -473,6 +473,8 @@ struct LinearArgs {
   void* out; long ldo; long o_gstride; int out_is_f32;   // out dtype: fp32 or AT
   const float* res; const float* rowscale; int rows_per_scale; long rowscale_gstride;
   int M, N, K, groups, gelu;
+  // tensor-core mode only: fused LayerNorm of the output rows -> ln_out (AT) [groups][M][N]
+  void* ln_out; const float* ln_gamma; const float* ln_beta; float ln_eps;
 };
 
 template <typename AT>
@@ -499,6 +501,7 @@ int linear<__nv_bfloat16>(const LinearArgs& a, cudaStream_t st) {
   g.res = a.res; g.rowscale = a.rowscale; g.rows_per_scale = a.rows_per_scale > 0 ? a.rows_per_scale : 1;
   g.rowscale_gstride = a.rowscale_gstride;
   g.M = a.M; g.N = a.N; g.K = a.K; g.groups = a.groups; g.gelu = a.gelu;
+  g.ln_out = a.ln_out; g.ln_gstride = (long)a.M * a.N; g.ln_gamma = a.ln_gamma; g.ln_beta = a.ln_beta; g.ln_eps = a.ln_eps;
   return mrnb_tc_gemm(g, st);
 }
 
@@ -645,9 +648,12 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
       for (int j = 0; j < DEPTH[sidx]; ++j, ++blk) {
         const int pb = MRNB_P_BLOCK0 + blk * MRNB_PB_COUNT;
         const bool local = blk < 6;
-        // LN1 (per expert: x groups are strided, outputs packed [I, rows_g, d])
-        MRNB_TRY(launch_layernorm<AT>(x, x_gs, lnout, rows_g * d, P.p[pb + MRNB_PB_NORM1_W], P.p[pb + MRNB_PB_NORM1_B],
-                                      rows_g * I, rows_g, d, 1e-6f, st));
+        // tensor-core mode, d <= 128: the residual GEMMs (proj, fc2) own whole rows and emit the following LayerNorm
+        const bool fuse_ln = sizeof(AT) == 2 && d <= 128 && (rows_g % 128) == 0;
+        // LN1 (per expert: x groups are strided, outputs packed [I, rows_g, d]); fused into the previous block's fc2
+        if (!(fuse_ln && j > 0))
+          MRNB_TRY(launch_layernorm<AT>(x, x_gs, lnout, rows_g * d, P.p[pb + MRNB_PB_NORM1_W], P.p[pb + MRNB_PB_NORM1_B],
+                                        rows_g * I, rows_g, d, 1e-6f, st));
         LinearArgs a{};
         a.A = lnout; a.lda = d; a.a_gstride = rows_g * d;
         a.W32 = P.p[pb + MRNB_PB_QKV_W]; a.W16 = P.h[pb + MRNB_PB_QKV_W]; a.w_gstride = (long)3 * d * d;
@@ -686,9 +692,11 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
           pr.rowscale_gstride = (long)12 * 2 * B;
         }
         pr.M = (int)rows_g; pr.N = d; pr.K = d; pr.groups = I;
+        if (fuse_ln) { pr.ln_out = lnout; pr.ln_gamma = P.p[pb + MRNB_PB_NORM2_W]; pr.ln_beta = P.p[pb + MRNB_PB_NORM2_B]; pr.ln_eps = 1e-6f; }
         MRNB_TRY(linear<AT>(pr, st));
-        MRNB_TRY(launch_layernorm<AT>(x, x_gs, lnout, rows_g * d, P.p[pb + MRNB_PB_NORM2_W], P.p[pb + MRNB_PB_NORM2_B],
-                                      rows_g * I, rows_g, d, 1e-6f, st));
+        if (!fuse_ln)
+          MRNB_TRY(launch_layernorm<AT>(x, x_gs, lnout, rows_g * d, P.p[pb + MRNB_PB_NORM2_W], P.p[pb + MRNB_PB_NORM2_B],
+                                        rows_g * I, rows_g, d, 1e-6f, st));
         LinearArgs f1{};
         f1.A = lnout; f1.lda = d; f1.a_gstride = rows_g * d;
         f1.W32 = P.p[pb + MRNB_PB_FC1_W]; f1.W16 = P.h[pb + MRNB_PB_FC1_W]; f1.w_gstride = (long)4 * d * d;
@@ -706,6 +714,10 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
           f2.rowscale_gstride = (long)12 * 2 * B;
         }
         f2.M = (int)rows_g; f2.N = d; f2.K = 4 * d; f2.groups = I;
+        if (fuse_ln && j + 1 < DEPTH[sidx]) {      // next block's norm1
+          const int pn = pb + MRNB_PB_COUNT;
+          f2.ln_out = lnout; f2.ln_gamma = P.p[pn + MRNB_PB_NORM1_W]; f2.ln_beta = P.p[pn + MRNB_PB_NORM1_B]; f2.ln_eps = 1e-6f;
+        }
         MRNB_TRY(linear<AT>(f2, st));
       }
       // SubSample: im2col -> conv GEMM (+bias) -> LN(eps 1e-5)
