@@ -196,6 +196,11 @@ int mrnb_linear_bf16(const void* A, const void* W, const float* bias, const floa
  * or [K,M] (a_mn=1), B stored [N,K] (b_mn=0) or [K,N] (b_mn=1), bf16; K % 64 == 0; out must be zeroed when splitk > 1. */
 int mrnb_tc_gemm_general(const void* A, int a_mn, const void* B, int b_mn, float* out, int M, int N, int K, int splitk,
                          cudaStream_t stream);
+/* Fused MLP branch (bf16 mode): x <- x + rs * (GELU(A W1^T + b1) W2^T + b2), A = LN2(x) as bf16 [M,D]; optional
+ * LayerNorm of the new x into ln_out (bf16 [M,D], D <= 128, may alias A).  Replaces modules/svtr.py:61-67,203. */
+int mrnb_mlp_bf16(const void* A, const void* W1, const float* b1, const void* W2, const float* b2, float* x,
+                  const float* rowscale, int rows_per_scale, void* ln_out, const float* ln_gamma, const float* ln_beta,
+                  float ln_eps, int M, int D, cudaStream_t stream);
 int mrnb_layernorm_f32(const float* x, float* y, const float* gamma, const float* beta, long rows, int D, float eps,
                        cudaStream_t stream);
 int mrnb_svtr_attention_f32(const float* qkv, float* out, int groups, int N, int d, int heads, int H, int W, int local,

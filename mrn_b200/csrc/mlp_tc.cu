@@ -1,0 +1,452 @@
+// Fused transformer MLP branch of an SVTR block on the tensor cores (bf16 mode):
+//
+//     x <- x + rs * ( GELU( LN2(x) W1^T + b1 ) W2^T + b2 )            [ + LN1_next(x) for the following block ]
+//
+// Reference: modules/svtr.py:61-67 (Mlp), :200-204 (Block.forward second branch), DropPath :7-22.
+// The 4d-wide hidden activation never leaves the SM: for every 128-row tile the kernel walks the hidden axis in
+// chunks of 128:   S_c = A W1_c^T  (tcgen05, TMEM, double buffered)  ->  epilogue warps: +b1, GELU, bf16 -> smem P
+//                  O  += P W2_c^T  (tcgen05, TMEM accumulator of width d)
+// and the final epilogue adds b2, the DropPath scale and the fp32 residual, stores x in place and (d <= 128)
+// emits the next LayerNorm.  Per tile HBM traffic: A (bf16) + x in + x out (+ LN out) instead of two GEMM round trips
+// through a [M,4d] tensor.  Warp roles: 0 = TMA producer, 1 = TMEM + MMA issuer, 2..9 = epilogue.
+#include "common.cuh"
+#include "mlp_tc.h"
+#include <cuda.h>
+
+namespace {
+
+constexpr int BM = 128, BK = 64, HC = 128;       // rows per tile, k-block, hidden chunk
+constexpr int EPI_WARPS = 8, NTHREADS = 64 + EPI_WARPS * 32;
+constexpr int TILE16K = 128 * 64 * 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint64_t t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+    if (ok) return;
+    if ((spin & 63u) == 63u && mrnb_wait_expired(t0)) __trap();   // > 2 s: protocol bug -> fail loudly, never hang
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// K-major SWIZZLE_128B tile: rows of 128 B, 8-row atoms 1024 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct MlpParams {
+  const float* b1; const float* b2; long b_gs1, b_gs2;        // [groups][4D], [groups][D]
+  float* x; long x_gs;                                        // fp32 residual stream, in place: [g][rows][D]
+  const float* rowscale; int rows_per_scale; long rowscale_gs;
+  __nv_bfloat16* ln_out; long ln_gs; const float* ln_gamma; const float* ln_beta; float ln_eps;   // optional (D <= 128)
+  int m_tiles, total_tiles;
+};
+
+template <int D>
+struct Cfg {
+  static constexpr int KB = D / BK;                    // k-blocks of the first GEMM
+  static constexpr int C = 4 * D / HC;                 // hidden chunks: 2, 4, 8
+  static constexpr int SLOT = D > 128 ? 32768 : 16384; // ring slot: W1 k-block [128 x 64] or W2 k-block [D x 64]
+  static constexpr int RS = D > 128 ? 3 : 4;           // ring slots
+  static constexpr int A_BYTES = KB * TILE16K;
+  static constexpr int P_BYTES = 2 * TILE16K;          // [128 x 128] bf16 as two 64-wide K halves
+  static constexpr int BIAS_BYTES = 5 * D * 4;
+  static constexpr int SMEM = 1024 + A_BYTES + P_BYTES + RS * SLOT + BIAS_BYTES;
+  static constexpr uint32_t O_COL = 256;               // TMEM: S buffers at 0 / 128, O at 256
+};
+
+template <int D, bool LNF>
+__global__ void __launch_bounds__(NTHREADS, 1)
+mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
+              const __grid_constant__ CUtensorMap tmW2, const MlpParams ep) {
+  using K = Cfg<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sP = smem + K::A_BYTES;
+  uint8_t* ring = sP + K::P_BYTES;
+  float* sb1 = reinterpret_cast<float*>(ring + K::RS * K::SLOT);
+  float* sb2 = sb1 + 4 * D;
+  __shared__ __align__(8) uint64_t a_full, a_empty, w_full[4], w_empty[4], s_full[2], s_empty[2], p_full, p_empty, o_full, o_empty;
+  __shared__ uint32_t tmem_base_sh;
+  __shared__ float ln_part[2][4][2][32];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = ep.total_tiles, m_tiles = ep.m_tiles;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&a_full, 1); mbar_init(&a_empty, 1);
+    for (int s = 0; s < K::RS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], EPI_WARPS); }
+    mbar_init(&p_full, EPI_WARPS); mbar_init(&p_empty, 1);
+    mbar_init(&o_full, 1); mbar_init(&o_empty, EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW1)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW2)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_sh;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      uint32_t it = 0;
+      auto load_w = [&](const CUtensorMap* map, int c0, int c1, int g, uint32_t bytes) {
+        const int s = it % K::RS;
+        mbar_wait(&w_empty[s], ((it / K::RS) & 1u) ^ 1u);
+        mbar_expect_tx(&w_full[s], bytes);
+        tma_load_3d(ring + (size_t)s * K::SLOT, map, &w_full[s], c0, c1, g);
+        ++it;
+      };
+      int i = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
+        const int g = t / m_tiles, m0 = (t % m_tiles) * BM;
+        mbar_wait(&a_empty, ((uint32_t)i & 1u) ^ 1u);
+        mbar_expect_tx(&a_full, K::A_BYTES);
+        for (int kb = 0; kb < K::KB; ++kb) tma_load_3d(sA + kb * TILE16K, &tmA, &a_full, kb * BK, m0, g);
+        // weights in consumption order: W1_0 ; then per chunk { W1_{c+1} ; W2_c }
+        for (int kb = 0; kb < K::KB; ++kb) load_w(&tmW1, kb * BK, 0, g, TILE16K);
+        for (int c = 0; c < K::C; ++c) {
+          if (c + 1 < K::C)
+            for (int kb = 0; kb < K::KB; ++kb) load_w(&tmW1, kb * BK, (c + 1) * HC, g, TILE16K);
+          for (int kk = 0; kk < 2; ++kk) load_w(&tmW2, c * HC + kk * BK, 0, g, D * BK * 2);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(HC), idesc_o = make_idesc(D);
+      uint32_t it = 0;
+      int i = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
+        auto issue_s = [&](int c) {
+          const int b = c & 1;
+          const uint32_t u = (uint32_t)(i * (K::C / 2) + (c >> 1));
+          mbar_wait(&s_empty[b], (u & 1u) ^ 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int kb = 0; kb < K::KB; ++kb, ++it) {
+            const int s = it % K::RS;
+            mbar_wait(&w_full[s], (it / K::RS) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t ad = make_desc(smem_u32(sA + kb * TILE16K)), bd = make_desc(smem_u32(ring + (size_t)s * K::SLOT));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + (uint32_t)(b * HC), ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc_s, (kb | k) != 0);
+            umma_commit(&w_empty[s]);
+          }
+          umma_commit(&s_full[b]);
+        };
+        mbar_wait(&a_full, (uint32_t)i & 1u);
+        issue_s(0);
+        for (int c = 0; c < K::C; ++c) {
+          if (c + 1 < K::C) issue_s(c + 1);
+          if (c + 1 == K::C - 1 || K::C == 1) umma_commit(&a_empty);      // last S issued: A tile is free once it retires
+          const uint32_t up = (uint32_t)(i * K::C + c);
+          mbar_wait(&p_full, up & 1u);
+          if (c == 0) mbar_wait(&o_empty, ((uint32_t)i & 1u) ^ 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int kk = 0; kk < 2; ++kk, ++it) {
+            const int s = it % K::RS;
+            mbar_wait(&w_full[s], (it / K::RS) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t ad = make_desc(smem_u32(sP + kk * TILE16K)), bd = make_desc(smem_u32(ring + (size_t)s * K::SLOT));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + K::O_COL, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc_o, (c | kk | k) != 0);
+            umma_commit(&w_empty[s]);
+          }
+          umma_commit(&p_empty);
+          if (c == K::C - 1) umma_commit(&o_full);
+        }
+      }
+    }
+  } else {
+    // ============================== epilogue warps ==============================
+    const int ew = warp - 2, q = warp & 3, ch = ew >> 2;
+    const int r = q * 32 + lane;                               // row inside the tile == TMEM lane
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    constexpr int OW = D / 2;                                  // output columns per warp
+    constexpr int NPASS = OW / 32;                             // 32-column passes of the final epilogue: 1, 2, 4
+    const int p8 = lane & 7, rsel = lane >> 3;                 // final epilogue: 8 lanes per 32-column row segment
+    float* stg = reinterpret_cast<float*>(sP) + (size_t)ew * 1024;   // 32 rows x 32 floats, 16B pieces XOR-swizzled by row
+    int i = 0;
+    int cur_g = -1;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
+      const int g = t / m_tiles, m0 = (t % m_tiles) * BM;
+      if (g != cur_g) {                                        // (re)load the biases of this expert
+        asm volatile("bar.sync 5, 256;" ::: "memory");         // everyone done with the previous expert's biases
+        for (int k = threadIdx.x - 64; k < 4 * D; k += EPI_WARPS * 32) sb1[k] = ep.b1[(long)g * ep.b_gs1 + k];
+        for (int k = threadIdx.x - 64; k < D; k += EPI_WARPS * 32) sb2[k] = ep.b2[(long)g * ep.b_gs2 + k];
+        asm volatile("bar.sync 5, 256;" ::: "memory");
+        cur_g = g;
+      }
+      // residual rows of pass 0 can be fetched long before they are needed
+      float* xrow = ep.x + (long)g * ep.x_gs + (long)(m0 + q * 32 + rsel) * D + ch * OW + p8 * 4;
+      float4 rv[8];
+#pragma unroll
+      for (int itr = 0; itr < 8; ++itr) rv[itr] = *reinterpret_cast<const float4*>(xrow + (long)itr * 4 * D);
+
+      // ---- hidden chunks: S_c -> +b1 -> GELU -> bf16 P
+      for (int c = 0; c < K::C; ++c) {
+        const int b = c & 1;
+        const uint32_t u = (uint32_t)(i * (K::C / 2) + (c >> 1));
+        mbar_wait(&s_full[b], u & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t v0[32], v1[32];
+        tmem_ld32(lane_addr + (uint32_t)(b * HC + ch * 64), v0);
+        tmem_ld32(lane_addr + (uint32_t)(b * HC + ch * 64 + 32), v1);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[b]);
+        const uint32_t up = (uint32_t)(i * K::C + c);
+        mbar_wait(&p_empty, (up & 1u) ^ 1u);                   // previous P has been consumed by its MMAs
+        const float* bb = sb1 + c * HC + ch * 64;
+        uint8_t* prow = sP + ch * TILE16K + r * 128;
+#pragma unroll
+        for (int pc = 0; pc < 8; ++pc) {                        // 8 pieces of 8 columns (16 B of bf16)
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int col = pc * 8 + e * 2;
+            const float a0 = __uint_as_float(col < 32 ? v0[col] : v1[col - 32]) + bb[col];
+            const float a1 = __uint_as_float(col + 1 < 32 ? v0[col + 1] : v1[col + 1 - 32]) + bb[col + 1];
+            __nv_bfloat162 hb = __floats2bfloat162_rn(gelu_fast(a0), gelu_fast(a1));
+            pk[e] = *reinterpret_cast<uint32_t*>(&hb);
+          }
+          *reinterpret_cast<uint4*>(prow + ((pc ^ (r & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full);
+      }
+
+      // ---- final epilogue: O -> +b2, DropPath scale, + residual -> x (in place) [+ fused LayerNorm]
+      mbar_wait(&o_full, (uint32_t)i & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const float rs = ep.rowscale ? ep.rowscale[(long)g * ep.rowscale_gs + m0 / ep.rows_per_scale] : 1.0f;
+      float4 keep[LNF ? NPASS * 8 : 1];
+#pragma unroll
+      for (int ps = 0; ps < NPASS; ++ps) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + K::O_COL + (uint32_t)(ch * OW + ps * 32), v);
+        if (ps == NPASS - 1) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&o_empty);                // accumulator drained: next tile may overwrite it
+        }
+#pragma unroll
+        for (int pc = 0; pc < 8; ++pc)
+          *reinterpret_cast<float4*>(stg + lane * 32 + ((pc ^ (lane & 7)) * 4)) =
+              make_float4(__uint_as_float(v[4 * pc]), __uint_as_float(v[4 * pc + 1]), __uint_as_float(v[4 * pc + 2]), __uint_as_float(v[4 * pc + 3]));
+        __syncwarp();
+        const float4 b4 = *reinterpret_cast<const float4*>(sb2 + ch * OW + ps * 32 + p8 * 4);
+        float4 nx[8];
+        if (ps + 1 < NPASS) {                                  // prefetch the next pass' residual rows
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr) nx[itr] = *reinterpret_cast<const float4*>(xrow + (ps + 1) * 32 + (long)itr * 4 * D);
+        }
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          const int rl = itr * 4 + rsel;
+          float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((p8 ^ (rl & 7)) * 4));
+          x.x = fmaf(x.x + b4.x, rs, rv[itr].x); x.y = fmaf(x.y + b4.y, rs, rv[itr].y);
+          x.z = fmaf(x.z + b4.z, rs, rv[itr].z); x.w = fmaf(x.w + b4.w, rs, rv[itr].w);
+          *reinterpret_cast<float4*>(xrow + ps * 32 + (long)itr * 4 * D) = x;
+          if (LNF) keep[ps * 8 + itr] = x;
+        }
+        if (ps + 1 < NPASS) {
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr) rv[itr] = nx[itr];
+        }
+        __syncwarp();
+      }
+      if (LNF) {
+        // LayerNorm of the new rows for the next block (two-pass statistics; the two warps of a row exchange partials)
+        const float invn = 1.0f / (float)D;
+        float mean[8], rstd[8];
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          float sres = 0.f;
+#pragma unroll
+          for (int ps = 0; ps < NPASS; ++ps) { const float4 x = keep[ps * 8 + itr]; sres += (x.x + x.y) + (x.z + x.w); }
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) sres += __shfl_xor_sync(0xffffffffu, sres, o);
+          if (p8 == 0) ln_part[0][q][ch][itr * 4 + rsel] = sres;
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          const int rl = itr * 4 + rsel;
+          mean[itr] = (ln_part[0][q][0][rl] + ln_part[0][q][1][rl]) * invn;
+          float sq = 0.f;
+#pragma unroll
+          for (int ps = 0; ps < NPASS; ++ps) {
+            const float4 x = keep[ps * 8 + itr];
+            const float d0 = x.x - mean[itr], d1 = x.y - mean[itr], d2 = x.z - mean[itr], d3 = x.w - mean[itr];
+            sq += fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3);
+          }
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+          if (p8 == 0) ln_part[1][q][ch][rl] = sq;
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        __nv_bfloat16* lrow = ep.ln_out + (long)g * ep.ln_gs + (long)(m0 + q * 32 + rsel) * D + ch * OW + p8 * 4;
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          const int rl = itr * 4 + rsel;
+          rstd[itr] = rsqrtf((ln_part[1][q][0][rl] + ln_part[1][q][1][rl]) * invn + ep.ln_eps);
+#pragma unroll
+          for (int ps = 0; ps < NPASS; ++ps) {
+            const int col = ch * OW + ps * 32 + p8 * 4;
+            const float4 g4 = *reinterpret_cast<const float4*>(ep.ln_gamma + (long)g * D + col);
+            const float4 t4 = *reinterpret_cast<const float4*>(ep.ln_beta + (long)g * D + col);
+            const float4 x = keep[ps * 8 + itr];
+            __nv_bfloat162 h0 = __floats2bfloat162_rn((x.x - mean[itr]) * rstd[itr] * g4.x + t4.x, (x.y - mean[itr]) * rstd[itr] * g4.y + t4.y);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn((x.z - mean[itr]) * rstd[itr] * g4.z + t4.z, (x.w - mean[itr]) * rstd[itr] * g4.w + t4.w);
+            *reinterpret_cast<uint2*>(lrow + ps * 32 + (long)itr * 4 * D) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+int map3(CUtensorMap* map, const void* ptr, long K, long rows, long groups, long ld, long gstride, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { mrnb_set_error("mlp_tc: cuTensorMapEncodeTiled unavailable"); return MRNB_ERR_UNSUPPORTED; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8) || (gstride % 8)) { mrnb_set_error("mlp_tc: misaligned operand"); return MRNB_ERR_ARG; }
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)groups};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)gstride * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1}, es[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { mrnb_set_error("mlp_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return MRNB_ERR_ARG; }
+  return MRNB_OK;
+}
+
+template <int D, bool LNF>
+int launch_mlp(const MrnbMlp& p, cudaStream_t st) {
+  using K = Cfg<D>;
+  CUtensorMap tmA, tmW1, tmW2;
+  MRNB_TRY(map3(&tmA, p.A, D, p.M, p.groups, D, (long)p.M * D, BM));
+  MRNB_TRY(map3(&tmW1, p.W1, D, 4 * D, p.groups, D, (long)4 * D * D, HC));
+  MRNB_TRY(map3(&tmW2, p.W2, 4 * D, D, p.groups, 4 * D, (long)4 * D * D, D));
+  MlpParams ep{};
+  ep.b1 = p.b1; ep.b2 = p.b2; ep.b_gs1 = 4 * D; ep.b_gs2 = D;
+  ep.x = p.x; ep.x_gs = p.x_gstride;
+  ep.rowscale = p.rowscale; ep.rows_per_scale = p.rows_per_scale > 0 ? p.rows_per_scale : 1; ep.rowscale_gs = p.rowscale_gstride;
+  ep.ln_out = (__nv_bfloat16*)p.ln_out; ep.ln_gs = (long)p.M * D; ep.ln_gamma = p.ln_gamma; ep.ln_beta = p.ln_beta; ep.ln_eps = p.ln_eps;
+  ep.m_tiles = p.M / BM; ep.total_tiles = ep.m_tiles * p.groups;
+  static bool attr = false;
+  static int num_sms = 148;
+  if (!attr) {
+    cudaFuncSetAttribute(mlp_tc_kernel<D, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    attr = true;
+  }
+  const int grid = ep.total_tiles < num_sms ? ep.total_tiles : num_sms;
+  mlp_tc_kernel<D, LNF><<<grid, NTHREADS, K::SMEM, st>>>(tmA, tmW1, tmW2, ep);
+  MRNB_CHECK_LAUNCH("mlp_tc_kernel");
+  return MRNB_OK;
+}
+
+}  // namespace
+
+int mrnb_mlp_tc(const MrnbMlp& p, cudaStream_t st) {
+  MRNB_CHECK_ARG(p.A && p.W1 && p.W2 && p.b1 && p.b2 && p.x && p.M > 0 && p.groups > 0, "mlp_tc: null/empty argument");
+  MRNB_CHECK_ARG(p.M % BM == 0 && (p.D == 64 || p.D == 128 || p.D == 256), "mlp_tc: need M %% 128 == 0 and D in {64,128,256}");
+  MRNB_CHECK_ARG(!p.rowscale || p.rows_per_scale % BM == 0, "mlp_tc: DropPath scale must be uniform per 128-row tile");
+  MRNB_CHECK_ARG(!p.ln_out || (p.D <= 128 && p.ln_gamma && p.ln_beta), "mlp_tc: fused LayerNorm needs D <= 128");
+  MRNB_CHECK_ARG(p.x_gstride % 4 == 0, "mlp_tc: misaligned residual stream");
+  const double M = (double)p.M * p.groups;
+  MrnbProfScope prof(MRNB_PROF_TCGEMM, st, 16.0 * M * p.D * p.D, M * p.D * (2.0 + 8.0 + (p.ln_out ? 2.0 : 0.0)));
+  switch (p.D) {
+    case 64: return p.ln_out ? launch_mlp<64, true>(p, st) : launch_mlp<64, false>(p, st);
+    case 128: return p.ln_out ? launch_mlp<128, true>(p, st) : launch_mlp<128, false>(p, st);
+    default: return launch_mlp<256, false>(p, st);
+  }
+}
+
+// C-ABI test entry: one group.  x [M,D] fp32 is updated in place; ln_out (bf16 [M,D]) optional.
+extern "C" int mrnb_mlp_bf16(const void* A, const void* W1, const float* b1, const void* W2, const float* b2, float* x,
+                             const float* rowscale, int rows_per_scale, void* ln_out, const float* ln_gamma,
+                             const float* ln_beta, float ln_eps, int M, int D, cudaStream_t stream) {
+  MrnbMlp p{};
+  p.A = A; p.W1 = W1; p.W2 = W2; p.b1 = b1; p.b2 = b2; p.x = x; p.x_gstride = (long)M * D;
+  p.rowscale = rowscale; p.rows_per_scale = rows_per_scale;
+  p.ln_out = ln_out; p.ln_gamma = ln_gamma; p.ln_beta = ln_beta; p.ln_eps = ln_eps;
+  p.M = M; p.D = D; p.groups = 1;
+  return mrnb_mlp_tc(p, stream);
+}

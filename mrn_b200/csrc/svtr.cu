@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "gemm_f32.h"
 #include "gemm_tc.h"
+#include "mlp_tc.h"
 #include "svtr.h"
 
 int mrnb_attention_tc(const void* qkv, void* out, int groups, int N, int d, int heads, int H, int W, int local, cudaStream_t st);
@@ -697,28 +698,46 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
         if (!fuse_ln)
           MRNB_TRY(launch_layernorm<AT>(x, x_gs, lnout, rows_g * d, P.p[pb + MRNB_PB_NORM2_W], P.p[pb + MRNB_PB_NORM2_B],
                                         rows_g * I, rows_g, d, 1e-6f, st));
-        LinearArgs f1{};
-        f1.A = lnout; f1.lda = d; f1.a_gstride = rows_g * d;
-        f1.W32 = P.p[pb + MRNB_PB_FC1_W]; f1.W16 = P.h[pb + MRNB_PB_FC1_W]; f1.w_gstride = (long)4 * d * d;
-        f1.bias = P.p[pb + MRNB_PB_FC1_B]; f1.bias_gstride = 4 * d;
-        f1.out = big; f1.ldo = 4 * d; f1.o_gstride = rows_g * 4 * d; f1.out_is_f32 = F32; f1.gelu = 1;
-        f1.M = (int)rows_g; f1.N = 4 * d; f1.K = d; f1.groups = I;
-        MRNB_TRY(linear<AT>(f1, st));
-        LinearArgs f2{};
-        f2.A = big; f2.lda = 4 * d; f2.a_gstride = rows_g * 4 * d;
-        f2.W32 = P.p[pb + MRNB_PB_FC2_W]; f2.W16 = P.h[pb + MRNB_PB_FC2_W]; f2.w_gstride = (long)4 * d * d;
-        f2.bias = P.p[pb + MRNB_PB_FC2_B]; f2.bias_gstride = d;
-        f2.out = x; f2.ldo = d; f2.o_gstride = x_gs; f2.out_is_f32 = 1; f2.res = x;
-        if (drop_scales) {
-          f2.rowscale = drop_scales + ((size_t)blk * 2 + 1) * B + b0; f2.rows_per_scale = N;
-          f2.rowscale_gstride = (long)12 * 2 * B;
+        if constexpr (sizeof(AT) == 2) {
+          // fused MLP branch: fc1 -> GELU -> fc2 -> DropPath -> +residual (-> next LN1), hidden kept on chip
+          MrnbMlp mp{};
+          mp.A = lnout; mp.W1 = P.h[pb + MRNB_PB_FC1_W]; mp.W2 = P.h[pb + MRNB_PB_FC2_W];
+          mp.b1 = P.p[pb + MRNB_PB_FC1_B]; mp.b2 = P.p[pb + MRNB_PB_FC2_B];
+          mp.x = x; mp.x_gstride = x_gs;
+          if (drop_scales) {
+            mp.rowscale = drop_scales + ((size_t)blk * 2 + 1) * B + b0; mp.rows_per_scale = N;
+            mp.rowscale_gstride = (long)12 * 2 * B;
+          }
+          if (fuse_ln && j + 1 < DEPTH[sidx]) {
+            const int pn = pb + MRNB_PB_COUNT;
+            mp.ln_out = lnout; mp.ln_gamma = P.p[pn + MRNB_PB_NORM1_W]; mp.ln_beta = P.p[pn + MRNB_PB_NORM1_B]; mp.ln_eps = 1e-6f;
+          }
+          mp.M = (int)rows_g; mp.D = d; mp.groups = I;
+          MRNB_TRY(mrnb_mlp_tc(mp, st));
+        } else {
+          LinearArgs f1{};
+          f1.A = lnout; f1.lda = d; f1.a_gstride = rows_g * d;
+          f1.W32 = P.p[pb + MRNB_PB_FC1_W]; f1.W16 = P.h[pb + MRNB_PB_FC1_W]; f1.w_gstride = (long)4 * d * d;
+          f1.bias = P.p[pb + MRNB_PB_FC1_B]; f1.bias_gstride = 4 * d;
+          f1.out = big; f1.ldo = 4 * d; f1.o_gstride = rows_g * 4 * d; f1.out_is_f32 = F32; f1.gelu = 1;
+          f1.M = (int)rows_g; f1.N = 4 * d; f1.K = d; f1.groups = I;
+          MRNB_TRY(linear<AT>(f1, st));
+          LinearArgs f2{};
+          f2.A = big; f2.lda = 4 * d; f2.a_gstride = rows_g * 4 * d;
+          f2.W32 = P.p[pb + MRNB_PB_FC2_W]; f2.W16 = P.h[pb + MRNB_PB_FC2_W]; f2.w_gstride = (long)4 * d * d;
+          f2.bias = P.p[pb + MRNB_PB_FC2_B]; f2.bias_gstride = d;
+          f2.out = x; f2.ldo = d; f2.o_gstride = x_gs; f2.out_is_f32 = 1; f2.res = x;
+          if (drop_scales) {
+            f2.rowscale = drop_scales + ((size_t)blk * 2 + 1) * B + b0; f2.rows_per_scale = N;
+            f2.rowscale_gstride = (long)12 * 2 * B;
+          }
+          f2.M = (int)rows_g; f2.N = d; f2.K = 4 * d; f2.groups = I;
+          if (fuse_ln && j + 1 < DEPTH[sidx]) {      // next block's norm1
+            const int pn = pb + MRNB_PB_COUNT;
+            f2.ln_out = lnout; f2.ln_gamma = P.p[pn + MRNB_PB_NORM1_W]; f2.ln_beta = P.p[pn + MRNB_PB_NORM1_B]; f2.ln_eps = 1e-6f;
+          }
+          MRNB_TRY(linear<AT>(f2, st));
         }
-        f2.M = (int)rows_g; f2.N = d; f2.K = 4 * d; f2.groups = I;
-        if (fuse_ln && j + 1 < DEPTH[sidx]) {      // next block's norm1
-          const int pn = pb + MRNB_PB_COUNT;
-          f2.ln_out = lnout; f2.ln_gamma = P.p[pn + MRNB_PB_NORM1_W]; f2.ln_beta = P.p[pn + MRNB_PB_NORM1_B]; f2.ln_eps = 1e-6f;
-        }
-        MRNB_TRY(linear<AT>(f2, st));
       }
       // SubSample: im2col -> conv GEMM (+bias) -> LN(eps 1e-5)
       const int Co = OUTS[sidx];

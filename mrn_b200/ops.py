@@ -101,6 +101,17 @@ def tc_gemm_general(a, a_mn, b, b_mn, M, N, K, splitk=1):
     return out
 
 
+def mlp_bf16(a16, w1_16, b1, w2_16, b2, x, rowscale=None, rows_per_scale=1, ln_gamma=None, ln_beta=None, ln_eps=1e-6):
+    """Fused MLP branch; x [M,D] fp32 is updated IN PLACE.  Returns the fused LayerNorm output (bf16) or None."""
+    assert a16.dtype == torch.bfloat16 and w1_16.dtype == torch.bfloat16 and w2_16.dtype == torch.bfloat16
+    _chk_f32(b1, b2, x, rowscale, ln_gamma, ln_beta)
+    M, D = x.shape
+    ln_out = torch.empty(M, D, device=x.device, dtype=torch.bfloat16) if ln_gamma is not None else None
+    L.check(L.load().mrnb_mlp_bf16(_p(a16), _p(w1_16), _p(b1), _p(w2_16), _p(b2), _p(x), _p(rowscale), int(rows_per_scale),
+                                   _p(ln_out), _p(ln_gamma), _p(ln_beta), float(ln_eps), M, D, _stream()), "mlp_bf16")
+    return ln_out
+
+
 def layernorm(x, gamma, beta, eps):
     _chk_f32(x, gamma, beta)
     y = torch.empty_like(x)

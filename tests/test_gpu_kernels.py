@@ -80,6 +80,31 @@ def test_tcgen05_general_gemm_major_modes(a_mn, b_mn, M, N, K, splitk):
     assert rel_err(out.numpy(), ref.numpy()) < 3e-5
 
 
+@pytest.mark.parametrize("D,M,ln,drop", [(64, 1024, True, True), (128, 512, True, False), (256, 384, False, True), (128, 2048, False, False)])
+def test_fused_mlp_tcgen05(D, M, ln, drop):
+    """x + rs * (GELU(A W1^T + b1) W2^T + b2) with the hidden activation kept on chip (+ fused next LayerNorm)."""
+    ops = _ops()
+    torch.manual_seed(D + M)
+    a = torch.randn(M, D).bfloat16()
+    w1 = (torch.randn(4 * D, D) / math.sqrt(D)).bfloat16()
+    w2 = (torch.randn(D, 4 * D) / math.sqrt(4 * D)).bfloat16()
+    b1, b2, x = torch.randn(4 * D) * 0.1, torch.randn(D) * 0.1, torch.randn(M, D)
+    rs = (torch.rand(M // 128) > 0.3).float() / 0.7 if drop else None
+    h = torch.nn.functional.gelu(a.double() @ w1.double().T + b1.double()).bfloat16().double()   # hidden is rounded to bf16
+    y = h @ w2.double().T + b2.double()
+    if drop:
+        y = y * rs.double().repeat_interleave(128).view(-1, 1)
+    ref = x.double() + y
+    g, bt = (1 + 0.1 * torch.randn(D)), 0.1 * torch.randn(D)
+    xd = dev(x)
+    out_ln = ops.mlp_bf16(dev(a), dev(w1), dev(b1), dev(w2), dev(b2), xd, dev(rs) if drop else None, 128,
+                          dev(g) if ln else None, dev(bt) if ln else None, 1e-6)
+    assert rel_err(xd.cpu().numpy(), ref.numpy()) < 3e-3
+    if ln:
+        ref_ln = O._ln(ref, g.double(), bt.double(), 1e-6)
+        assert rel_err(out_ln.float().cpu().numpy(), ref_ln.numpy()) < 8e-3
+
+
 # ------------------------------------------------------------------------------------------------ LN / attention
 @pytest.mark.parametrize("D", [64, 128, 256, 512])
 def test_layernorm(D):
