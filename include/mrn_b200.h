@@ -92,7 +92,8 @@ enum { /* per merge, Cin -> Cout = 64->128, 128->256, 256->512 */
 typedef struct MrnbSvtrPack {
   int n_experts;
   const float* p[MRNB_P_COUNT]; /* fp32 parameters (always required) */
-  const void* h[MRNB_P_COUNT];  /* bf16 copies of the GEMM weight slots (*_W of qkv/proj/fc1/fc2/conv/seq); MRNB_PREC_BF16 only */
+  const void* h[MRNB_P_COUNT];  /* 16-bit copies of the GEMM weight slots, MRNB_PREC_BF16 only: bf16 for qkv/proj/fc1/conv/seq
+                                   (conv1 in its implicit-GEMM layout [I,64,384]), f16 for mlp.fc2 (fused MLP second GEMM) */
   const float* fc_w[MRNB_MAX_EXPERTS];  /* [C_i,256] model.{i}.fc.weight (ragged over experts) */
   const void* fc_w16[MRNB_MAX_EXPERTS]; /* bf16 copy; MRNB_PREC_BF16 only */
   const float* fc_b[MRNB_MAX_EXPERTS];  /* [C_i] */
@@ -196,7 +197,8 @@ int mrnb_linear_bf16(const void* A, const void* W, const float* bias, const floa
  * or [K,M] (a_mn=1), B stored [N,K] (b_mn=0) or [K,N] (b_mn=1), bf16; K % 64 == 0; out must be zeroed when splitk > 1. */
 int mrnb_tc_gemm_general(const void* A, int a_mn, const void* B, int b_mn, float* out, int M, int N, int K, int splitk,
                          cudaStream_t stream);
-/* Fused MLP branch (bf16 mode): x <- x + rs * (GELU(A W1^T + b1) W2^T + b2), A = LN2(x) as bf16 [M,D]; optional
+/* Fused MLP branch (bf16 mode): x <- x + rs * (GELU(A W1^T + b1) W2^T + b2), A = LN2(x) and W1 bf16, W2 f16 (the GELU
+ * output is an f16 tensor-core operand); optional
  * LayerNorm of the new x into ln_out (bf16 [M,D], D <= 128, may alias A).  Replaces modules/svtr.py:61-67,203. */
 int mrnb_mlp_bf16(const void* A, const void* W1, const float* b1, const void* W2, const float* b2, float* x,
                   const float* rowscale, int rows_per_scale, void* ln_out, const float* ln_gamma, const float* ln_beta,
@@ -209,6 +211,7 @@ int mrnb_svtr_attention_f32(const float* qkv, float* out, int groups, int N, int
 int mrnb_svtr_attention_bf16(const void* qkv, void* out, int groups, int N, int d, int heads, int H, int W, int local,
                              cudaStream_t stream);
 int mrnb_cast_f32_to_bf16(const float* x, void* y, long n, cudaStream_t stream);
+int mrnb_cast_f32_to_f16(const float* x, void* y, long n, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,7 @@ _SIGNATURES = {
     "mrnb_svtr_attention_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mrnb_svtr_attention_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mrnb_cast_f32_to_bf16": (_i, [_vp, _vp, _l, _vp]),
+    "mrnb_cast_f32_to_f16": (_i, [_vp, _vp, _l, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -80,6 +80,20 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __r
 }
 }  // namespace
 
+namespace {
+__global__ void cast_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __float2half_rn(x[i]);
+}
+}  // namespace
+
+extern "C" int mrnb_cast_f32_to_f16(const float* x, void* y, long n, cudaStream_t stream) {
+  MRNB_CHECK_ARG(x && y && n > 0, "cast: bad argument");
+  cast_f16_kernel<<<cdiv(n, 256), 256, 0, stream>>>(x, (__half*)y, n);
+  MRNB_CHECK_LAUNCH("cast_f16_kernel");
+  return MRNB_OK;
+}
+
 extern "C" int mrnb_cast_f32_to_bf16(const float* x, void* y, long n, cudaStream_t stream) {
   MRNB_CHECK_ARG(x && y && n > 0, "cast: bad argument");
   cast_bf16_kernel<<<cdiv(n, 256), 256, 0, stream>>>(x, (__nv_bfloat16*)y, n);

@@ -34,8 +34,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t spin = 0;; ++spin) {
     uint32_t ok;
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     if (ok) return;
     if ((spin & 63u) == 63u && mrnb_wait_expired(t0)) __trap();   // > 2 s: protocol bug -> fail loudly, never hang
   }
@@ -167,7 +167,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc(HC), idesc_o = make_idesc(D);
+      constexpr uint32_t idesc_s = make_idesc(HC);
+      constexpr uint32_t idesc_o = make_idesc(D) & ~((7u << 7) | (7u << 10));   // second GEMM in f16 x f16: P (GELU output) and W2 are f16
       uint32_t it = 0;
       int i = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
@@ -249,23 +250,27 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[b]);
+        // +b1 (fp32), then GELU two values at a time in f16x2; P is handed to the tensor core as an f16 operand
+        const float4* bb4 = reinterpret_cast<const float4*>(sb1 + c * HC + ch * 64);
+        uint32_t pk[32];
+#pragma unroll
+        for (int e4 = 0; e4 < 16; ++e4) {                       // 4 columns per step
+          const float4 bq = bb4[e4];
+          const int col = e4 * 4;
+          const float a0 = __uint_as_float(col < 32 ? v0[col] : v1[col - 32]) + bq.x;
+          const float a1 = __uint_as_float(col < 32 ? v0[col + 1] : v1[col + 1 - 32]) + bq.y;
+          const float a2 = __uint_as_float(col < 32 ? v0[col + 2] : v1[col + 2 - 32]) + bq.z;
+          const float a3 = __uint_as_float(col < 32 ? v0[col + 3] : v1[col + 3 - 32]) + bq.w;
+          const __half2 g0 = gelu_fast_h2(__floats2half2_rn(a0, a1)), g1 = gelu_fast_h2(__floats2half2_rn(a2, a3));
+          pk[e4 * 2] = *reinterpret_cast<const uint32_t*>(&g0);
+          pk[e4 * 2 + 1] = *reinterpret_cast<const uint32_t*>(&g1);
+        }
         const uint32_t up = (uint32_t)(i * K::C + c);
-        mbar_wait(&p_empty, (up & 1u) ^ 1u);                   // previous P has been consumed by its MMAs
-        const float* bb = sb1 + c * HC + ch * 64;
+        mbar_wait(&p_empty, (up & 1u) ^ 1u);                   // previous P has been consumed by its MMAs (GELU already done)
         uint8_t* prow = sP + ch * TILE16K + r * 128;
 #pragma unroll
-        for (int pc = 0; pc < 8; ++pc) {                        // 8 pieces of 8 columns (16 B of bf16)
-          uint32_t pk[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int col = pc * 8 + e * 2;
-            const float a0 = __uint_as_float(col < 32 ? v0[col] : v1[col - 32]) + bb[col];
-            const float a1 = __uint_as_float(col + 1 < 32 ? v0[col + 1] : v1[col + 1 - 32]) + bb[col + 1];
-            __nv_bfloat162 hb = __floats2bfloat162_rn(gelu_fast(a0), gelu_fast(a1));
-            pk[e] = *reinterpret_cast<uint32_t*>(&hb);
-          }
-          *reinterpret_cast<uint4*>(prow + ((pc ^ (r & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        }
+        for (int pc = 0; pc < 8; ++pc)                          // 8 pieces of 8 columns (16 B of bf16), XOR-swizzled by row
+          *reinterpret_cast<uint4*>(prow + ((pc ^ (r & 7)) * 16)) = make_uint4(pk[pc * 4], pk[pc * 4 + 1], pk[pc * 4 + 2], pk[pc * 4 + 3]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full);

@@ -81,6 +81,13 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def cast_f16(x: torch.Tensor) -> torch.Tensor:
+    _chk_f32(x)
+    y = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    L.check(L.load().mrnb_cast_f32_to_f16(_p(x), _p(y), x.numel(), _stream()), "cast")
+    return y
+
+
 def linear_bf16(a, w, bias=None, residual=None, gelu=False, out_f32=True):
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.is_contiguous() and w.is_contiguous()
     _chk_f32(bias, residual)
@@ -103,7 +110,7 @@ def tc_gemm_general(a, a_mn, b, b_mn, M, N, K, splitk=1):
 
 def mlp_bf16(a16, w1_16, b1, w2_16, b2, x, rowscale=None, rows_per_scale=1, ln_gamma=None, ln_beta=None, ln_eps=1e-6):
     """Fused MLP branch; x [M,D] fp32 is updated IN PLACE.  Returns the fused LayerNorm output (bf16) or None."""
-    assert a16.dtype == torch.bfloat16 and w1_16.dtype == torch.bfloat16 and w2_16.dtype == torch.bfloat16
+    assert a16.dtype == torch.bfloat16 and w1_16.dtype == torch.bfloat16 and w2_16.dtype == torch.float16
     _chk_f32(b1, b2, x, rowscale, ln_gamma, ln_beta)
     M, D = x.shape
     ln_out = torch.empty(M, D, device=x.device, dtype=torch.bfloat16) if ln_gamma is not None else None
@@ -182,7 +189,9 @@ class SvtrPack:
             self.slot_tensors[slot] = t
             self.struct.p[slot] = t.data_ptr()
             if gemm_weight and prec == L.PREC_BF16:
-                h = cast_bf16(t)
+                # mlp.fc2 feeds the fused MLP's second GEMM, whose A operand (GELU output) is f16
+                is_fc2 = slot >= L.P_BLOCK0 and slot < L.P_SUB0 and (slot - L.P_BLOCK0) % L.PB_COUNT == L.PB_FC2_W
+                h = cast_f16(t) if is_fc2 else cast_bf16(t)
                 self.tensors.append(h)
                 self.struct.h[slot] = h.data_ptr()
 

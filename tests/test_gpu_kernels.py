@@ -87,10 +87,10 @@ def test_fused_mlp_tcgen05(D, M, ln, drop):
     torch.manual_seed(D + M)
     a = torch.randn(M, D).bfloat16()
     w1 = (torch.randn(4 * D, D) / math.sqrt(D)).bfloat16()
-    w2 = (torch.randn(D, 4 * D) / math.sqrt(4 * D)).bfloat16()
+    w2 = (torch.randn(D, 4 * D) / math.sqrt(4 * D)).half()          # second GEMM runs f16 x f16
     b1, b2, x = torch.randn(4 * D) * 0.1, torch.randn(D) * 0.1, torch.randn(M, D)
     rs = (torch.rand(M // 128) > 0.3).float() / 0.7 if drop else None
-    h = torch.nn.functional.gelu(a.double() @ w1.double().T + b1.double()).bfloat16().double()   # hidden is rounded to bf16
+    h = torch.nn.functional.gelu(a.double() @ w1.double().T + b1.double()).half().double()       # hidden is an f16 operand
     y = h @ w2.double().T + b2.double()
     if drop:
         y = y * rs.double().repeat_interleave(128).view(-1, 1)
