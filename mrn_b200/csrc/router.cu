@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "gemm_f32.h"
 #include "gemm_tc2.h"
+#include "gemm_tc.h"
 #include "../../include/mrn_b200.h"
 
 namespace {
@@ -485,12 +486,13 @@ inline int bn_for(int N) { return N >= 128 ? 128 : 64; }
 int linear_rows(const Dims& d, const float* A32, const bf16* A16, long lda, const float* W32, const bf16* W16, int Nout, int K,
                 const float* bias, const float* res, float* out, long ldo, cudaStream_t st) {
   if (d.tc) {
-    MrnbTcGemm2 g{};
-    g.a = mrnb_operand_k2d(A16, d.M, K, lda, 128, 1);
-    g.b = mrnb_operand_k2d(W16, Nout, K, K, bn_for(Nout), 1);
-    g.out32 = out; g.cm = mrnb_axis(ldo); g.cn = mrnb_axis(1);
-    g.bias_n = bias; g.res = res; g.M = (int)d.M; g.N = Nout; g.K = K; g.groups = 1; g.alpha = 1.f;
-    return mrnb_tc_gemm2(g, st);
+    // plain row-major Linear: the persistent TMEM-double-buffered kernel of the expert path (coalesced epilogue)
+    MrnbTcGemm g{};
+    g.A = A16; g.lda = lda; g.a_gstride = d.M * lda;
+    g.W = W16; g.ldw = K; g.w_gstride = (long)Nout * K;
+    g.bias = bias; g.out = out; g.ldo = ldo; g.o_gstride = d.M * ldo; g.out_f32 = 1; g.res = res;
+    g.M = (int)d.M; g.N = Nout; g.K = K; g.groups = 1; g.rows_per_scale = 1;
+    return mrnb_tc_gemm(g, st);
   }
   MrnbGemm g = mrnb_gemm_nt(A32, lda, W32, K, out, ldo, (int)d.M, Nout, K);
   g.bias_n = bias; g.res = res;
