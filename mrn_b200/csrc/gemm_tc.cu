@@ -17,7 +17,7 @@
 namespace {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 2;          // 2 x 32 KiB ring + 32 KiB staging: two persistent CTAs per SM
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -127,14 +127,13 @@ struct TcEpi {
 
 constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each owning half of the tile columns
 constexpr int NTHREADS = 64 + EPI_WARPS * 32;      // warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 epilogue
-constexpr int SLD = 68;                            // staging row stride in floats (16B slots conflict-free)
-constexpr int STAGING_BYTES = EPI_WARPS * 32 * SLD * 4;
+constexpr int STAGING_BYTES = EPI_WARPS * 32 * 32 * 4;    // 32x32 fp32 tile per epilogue warp, XOR-swizzled
 
 // Persistent kernel: CTA c walks tiles c, c + gridDim.x, ... (n fastest so neighbouring CTAs share the A tile in L2).
 // The smem ring runs across tile boundaries, and the accumulator is double buffered in TMEM so the MMAs of tile i+1
 // overlap the epilogue of tile i.
 template <int BN, bool OUT_F32, bool GELU, bool LNF>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, LNF ? 1 : 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcEpi ep) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int B_STAGE_BYTES = BN * BK * 2;
@@ -223,170 +222,177 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ---- epilogue warps: quarter q = warp % 4 (TMEM lanes 32q..32q+31), column half ch = (warp - 2) / 4.
-    // Phase A: one accumulator row per thread (tcgen05.ld) parked in a per-warp staging tile; the TMEM buffer is
-    // released as soon as it is drained.  Phase B: lanes own columns (float4 each, half a warp per row segment), so
-    // bias sits in registers and residual loads / output stores are coalesced.
+    // The warp's CW columns are processed in passes of 32:
+    //   phase A: one accumulator row per thread (tcgen05.ld) parked in a 32x32 fp32 staging tile (4 KiB per warp,
+    //            16-byte pieces XOR-swizzled by row: conflict-free without padding);
+    //   phase B: lanes own columns (8 lanes x float4 per row, 4 rows per step), so bias sits in registers and the
+    //            residual loads / output stores are coalesced 128-byte segments.
+    // Residual rows are prefetched before they are needed (pass 0: before the accumulator wait).
     const int ew = warp - 2;
     const int q = warp & 3, ch = ew >> 2;
     constexpr int CW = BN / 2;                                 // columns per epilogue warp: 64 (BN=128) or 32 (BN=64)
-    constexpr int LPR = CW / 4;                                // lanes per row segment: 16 or 8
-    constexpr int RPI = 32 / LPR;                              // rows per phase-B iteration: 2 or 4
-    float* stg = staging + (size_t)ew * 32 * SLD;
-    const int c4 = (lane % LPR) * 4, rsel = lane / LPR;
+    constexpr int NP = CW / 32;                                // passes
+    float* stg = staging + (size_t)ew * 1024;
+    const int p8 = lane & 7, rsel = lane >> 3;
     int i = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
       const int n0 = (t % n_tiles) * BN, m0 = ((t / n_tiles) % m_tiles) * BM, g = t / (n_tiles * m_tiles);
       const int buf = i & 1;
-      const int col = n0 + ch * CW + c4;
+      const int colw = n0 + ch * CW + p8 * 4;                  // this lane's first column in pass 0
       const long gbase = (long)g * ep.o_gs;
       // interior tile with aligned rows: branch-free path (pointer increments, tile-uniform DropPath scale)
       const bool interior = (m0 + BM <= ep.M) && (n0 + BN <= ep.N) && ((ep.ldo & 3) == 0) && ((gbase & 3) == 0) &&
                             (!ep.rowscale || (ep.rows_per_scale % BM) == 0);
-      const long o0 = gbase + (long)(m0 + q * 32 + rsel) * ep.ldo + col;
-      const long ostep = (long)RPI * ep.ldo;
-      // residual rows of this tile are known before the accumulator is: issue all loads now so their HBM latency
-      // overlaps the MMA wait and the TMEM drain
-      float4 rv[32 / RPI];
+      const long o0 = gbase + (long)(m0 + q * 32 + rsel) * ep.ldo + colw;
+      const long ostep = 4L * ep.ldo;
       const bool pre_res = OUT_F32 && interior && ep.res != nullptr;
+      float4 rv[8];
       if (pre_res) {
-        const float* rp = ep.res + o0;
 #pragma unroll
-        for (int itr = 0; itr < 32 / RPI; ++itr) rv[itr] = *reinterpret_cast<const float4*>(rp + itr * ostep);
+        for (int itr = 0; itr < 8; ++itr) rv[itr] = *reinterpret_cast<const float4*>(ep.res + o0 + itr * ostep);
       }
+      const float* bias = ep.bias ? ep.bias + (long)g * ep.bias_gs : nullptr;
+      const float rs = (interior && ep.rowscale) ? ep.rowscale[(long)g * ep.rowscale_gs + m0 / ep.rows_per_scale] : 1.0f;
       mbar_wait(&tmem_full_bar[buf], ((uint32_t)i >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + ch * CW);
+      float4 keep[LNF ? NP * 8 : 1];
 #pragma unroll
-      for (int hh = 0; hh < CW / 32; ++hh) {
-        uint32_t r[32];
-        tmem_ld32(tcol + (uint32_t)(hh * 32), r);
-        float4* dst = reinterpret_cast<float4*>(stg + lane * SLD + hh * 32);
+      for (int ps = 0; ps < NP; ++ps) {
+        {
+          uint32_t r[32];
+          tmem_ld32(tcol + (uint32_t)(ps * 32), r);
+          if (ps == NP - 1) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);  // this warp's share of the accumulator is out of TMEM
+          }
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                               __uint_as_float(r[4 * j + 3]));
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);        // this warp's share of the accumulator is in smem
-      const bool cfull = col + 4 <= ep.N;
-      const float* bias = ep.bias ? ep.bias + (long)g * ep.bias_gs : nullptr;
-      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (bias && col < ep.N) {
-        if (cfull) b4 = *reinterpret_cast<const float4*>(bias + col);
-        else {
-          b4.x = bias[col];
-          if (col + 1 < ep.N) b4.y = bias[col + 1];
-          if (col + 2 < ep.N) b4.z = bias[col + 2];
+          for (int pc = 0; pc < 8; ++pc)
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((pc ^ (lane & 7)) * 4)) =
+                make_float4(__uint_as_float(r[4 * pc]), __uint_as_float(r[4 * pc + 1]), __uint_as_float(r[4 * pc + 2]), __uint_as_float(r[4 * pc + 3]));
         }
-      }
-      if (interior) {
-        const float rs = ep.rowscale ? ep.rowscale[(long)g * ep.rowscale_gs + m0 / ep.rows_per_scale] : 1.0f;
-        const float* sp = stg + rsel * SLD + c4;
-        if (OUT_F32) {
-          float* op = reinterpret_cast<float*>(ep.out) + o0;
-#pragma unroll
-          for (int itr = 0; itr < 32 / RPI; ++itr) {
-            float4 x = *reinterpret_cast<const float4*>(sp + itr * RPI * SLD);
-            x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
-            if (GELU) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
-            x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
-            if (pre_res) { x.x += rv[itr].x; x.y += rv[itr].y; x.z += rv[itr].z; x.w += rv[itr].w; }
-            *reinterpret_cast<float4*>(op + itr * ostep) = x;
-            if (LNF) *reinterpret_cast<float4*>(stg + (rsel + itr * RPI) * SLD + c4) = x;      // keep x_new for the LN passes
-          }
-          if (LNF) {
-            // Fused LayerNorm of the freshly written rows (the tile spans the whole row: N == BN).  Two-pass statistics;
-            // the two warps that share a row (column halves) exchange partial sums through shared memory.
-            constexpr int NIT = 32 / RPI;
-            const float invn = 1.0f / (float)BN;
-            float mean[NIT], rstd[NIT];
-#pragma unroll
-            for (int itr = 0; itr < NIT; ++itr) {
-              const float4 x = *reinterpret_cast<const float4*>(sp + itr * RPI * SLD);
-              float sres = (x.x + x.y) + (x.z + x.w);
-#pragma unroll
-              for (int o = LPR / 2; o > 0; o >>= 1) sres += __shfl_xor_sync(0xffffffffu, sres, o);
-              if ((lane % LPR) == 0) ln_part[0][q][ch][rsel + itr * RPI] = sres;
-            }
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-#pragma unroll
-            for (int itr = 0; itr < NIT; ++itr) {
-              const int rl = rsel + itr * RPI;
-              mean[itr] = (ln_part[0][q][0][rl] + ln_part[0][q][1][rl]) * invn;
-              const float4 x = *reinterpret_cast<const float4*>(sp + itr * RPI * SLD);
-              const float d0 = x.x - mean[itr], d1 = x.y - mean[itr], d2 = x.z - mean[itr], d3 = x.w - mean[itr];
-              float sq = fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3);
-#pragma unroll
-              for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-              if ((lane % LPR) == 0) ln_part[1][q][ch][rl] = sq;
-            }
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-            const float4 g4 = *reinterpret_cast<const float4*>(ep.ln_gamma + (long)g * BN + ch * CW + c4);
-            const float4 t4 = *reinterpret_cast<const float4*>(ep.ln_beta + (long)g * BN + ch * CW + c4);
-            __nv_bfloat16* lp = ep.ln_out + (long)g * ep.ln_gs + (long)(m0 + q * 32 + rsel) * BN + ch * CW + c4;
-#pragma unroll
-            for (int itr = 0; itr < NIT; ++itr) {
-              const int rl = rsel + itr * RPI;
-              rstd[itr] = rsqrtf((ln_part[1][q][0][rl] + ln_part[1][q][1][rl]) * invn + ep.ln_eps);
-              const float4 x = *reinterpret_cast<const float4*>(sp + itr * RPI * SLD);
-              const float y0 = (x.x - mean[itr]) * rstd[itr] * g4.x + t4.x, y1 = (x.y - mean[itr]) * rstd[itr] * g4.y + t4.y;
-              const float y2 = (x.z - mean[itr]) * rstd[itr] * g4.z + t4.z, y3 = (x.w - mean[itr]) * rstd[itr] * g4.w + t4.w;
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
-              *reinterpret_cast<uint2*>(lp + (long)itr * RPI * BN) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-            }
-          }
-        } else {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ep.out) + o0;
-#pragma unroll
-          for (int itr = 0; itr < 32 / RPI; ++itr) {
-            float4 x = *reinterpret_cast<const float4*>(sp + itr * RPI * SLD);
-            x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
-            if (GELU) { x.x = gelu_fast(x.x); x.y = gelu_fast(x.y); x.z = gelu_fast(x.z); x.w = gelu_fast(x.w); }
-            x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
-            *reinterpret_cast<uint2*>(op + itr * ostep) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        __syncwarp();
+        const int col = colw + ps * 32;
+        const bool cfull = col + 4 <= ep.N;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias && col < ep.N) {
+          if (cfull) b4 = *reinterpret_cast<const float4*>(bias + col);
+          else {
+            b4.x = bias[col];
+            if (col + 1 < ep.N) b4.y = bias[col + 1];
+            if (col + 2 < ep.N) b4.z = bias[col + 2];
           }
         }
-      } else {
-  #pragma unroll 4
-        for (int rr = 0; rr < 32; rr += RPI) {
-          const int rl = rr + rsel;
-          const int row = m0 + q * 32 + rl;
-          if (row >= ep.M || col >= ep.N) continue;
-          float4 x = *reinterpret_cast<const float4*>(stg + rl * SLD + c4);
-          x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
-          if (GELU) {
-            if (OUT_F32) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
-            else { x.x = gelu_fast(x.x); x.y = gelu_fast(x.y); x.z = gelu_fast(x.z); x.w = gelu_fast(x.w); }
+        if (interior) {
+          float4 nx[8];
+          if (pre_res && ps + 1 < NP) {                        // next pass' residual rows
+#pragma unroll
+            for (int itr = 0; itr < 8; ++itr) nx[itr] = *reinterpret_cast<const float4*>(ep.res + o0 + (ps + 1) * 32 + itr * ostep);
           }
-          if (ep.rowscale) {
-            const float rs = ep.rowscale[(long)g * ep.rowscale_gs + row / ep.rows_per_scale];
-            x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
-          }
-          const long o = gbase + (long)row * ep.ldo + col;
           if (OUT_F32) {
-            float* op = reinterpret_cast<float*>(ep.out) + o;
-            if (cfull && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
-              if (ep.res) { const float4 rv = *reinterpret_cast<const float4*>(ep.res + o); x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w; }
-              *reinterpret_cast<float4*>(op) = x;
-            } else {
-              const float xv[4] = {x.x, x.y, x.z, x.w};
-              for (int j = 0; j < 4 && col + j < ep.N; ++j) op[j] = xv[j] + (ep.res ? ep.res[o + j] : 0.f);
+            float* op = reinterpret_cast<float*>(ep.out) + o0 + ps * 32;
+#pragma unroll
+            for (int itr = 0; itr < 8; ++itr) {
+              const int rl = itr * 4 + rsel;
+              float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((p8 ^ (rl & 7)) * 4));
+              x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+              if (GELU) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+              x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
+              if (pre_res) { x.x += rv[itr].x; x.y += rv[itr].y; x.z += rv[itr].z; x.w += rv[itr].w; }
+              *reinterpret_cast<float4*>(op + itr * ostep) = x;
+              if (LNF) keep[ps * 8 + itr] = x;
             }
           } else {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ep.out) + o;
-            if (cfull && ((reinterpret_cast<uintptr_t>(op) & 7) == 0)) {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ep.out) + o0 + ps * 32;
+#pragma unroll
+            for (int itr = 0; itr < 8; ++itr) {
+              const int rl = itr * 4 + rsel;
+              float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((p8 ^ (rl & 7)) * 4));
+              x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+              if (GELU) { x.x = gelu_fast(x.x); x.y = gelu_fast(x.y); x.z = gelu_fast(x.z); x.w = gelu_fast(x.w); }
+              x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
               __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
-              *reinterpret_cast<uint2*>(op) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-            } else {
-              const float xv[4] = {x.x, x.y, x.z, x.w};
-              for (int j = 0; j < 4 && col + j < ep.N; ++j) op[j] = __float2bfloat16_rn(xv[j]);
+              *reinterpret_cast<uint2*>(op + itr * ostep) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+            }
+          }
+          if (pre_res && ps + 1 < NP) {
+#pragma unroll
+            for (int itr = 0; itr < 8; ++itr) rv[itr] = nx[itr];
+          }
+        } else {
+          // edge tiles / unaligned outputs: guarded scalar path
+          for (int itr = 0; itr < 8; ++itr) {
+            const int rl = itr * 4 + rsel;
+            const int row = m0 + q * 32 + rl;
+            if (row >= ep.M || col >= ep.N) continue;
+            const float4 xs = *reinterpret_cast<const float4*>(stg + rl * 32 + ((p8 ^ (rl & 7)) * 4));
+            float xv[4] = {xs.x + b4.x, xs.y + b4.y, xs.z + b4.z, xs.w + b4.w};
+            const float rsr = ep.rowscale ? ep.rowscale[(long)g * ep.rowscale_gs + row / ep.rows_per_scale] : 1.0f;
+            const long o = gbase + (long)row * ep.ldo + col;
+            for (int j = 0; j < 4 && col + j < ep.N; ++j) {
+              float x = xv[j];
+              if (GELU) x = OUT_F32 ? gelu_erf(x) : gelu_fast(x);
+              x *= rsr;
+              if (OUT_F32) {
+                if (ep.res) x += ep.res[o + j];
+                reinterpret_cast<float*>(ep.out)[o + j] = x;
+              } else {
+                reinterpret_cast<__nv_bfloat16*>(ep.out)[o + j] = __float2bfloat16_rn(x);
+              }
             }
           }
         }
+        __syncwarp();                                          // staging tile is reused by the next pass / tile
       }
-      __syncwarp();                                            // staging tile is reused by the next tile
+      if (LNF) {
+        // Fused LayerNorm of the freshly written rows (the tile spans the whole row: N == BN).  Two-pass statistics;
+        // the two warps that share a row (column halves) exchange partial sums through shared memory.
+        const float invn = 1.0f / (float)BN;
+        float mean[8], rstd[8];
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          float sres = 0.f;
+#pragma unroll
+          for (int ps = 0; ps < NP; ++ps) { const float4 x = keep[ps * 8 + itr]; sres += (x.x + x.y) + (x.z + x.w); }
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) sres += __shfl_xor_sync(0xffffffffu, sres, o);
+          if (p8 == 0) ln_part[0][q][ch][itr * 4 + rsel] = sres;
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          const int rl = itr * 4 + rsel;
+          mean[itr] = (ln_part[0][q][0][rl] + ln_part[0][q][1][rl]) * invn;
+          float sq = 0.f;
+#pragma unroll
+          for (int ps = 0; ps < NP; ++ps) {
+            const float4 x = keep[ps * 8 + itr];
+            const float d0 = x.x - mean[itr], d1 = x.y - mean[itr], d2 = x.z - mean[itr], d3 = x.w - mean[itr];
+            sq += fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3);
+          }
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+          if (p8 == 0) ln_part[1][q][ch][rl] = sq;
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        __nv_bfloat16* lrow = ep.ln_out + (long)g * ep.ln_gs + (long)(m0 + q * 32 + rsel) * BN + ch * CW + p8 * 4;
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          const int rl = itr * 4 + rsel;
+          rstd[itr] = rsqrtf((ln_part[1][q][0][rl] + ln_part[1][q][1][rl]) * invn + ep.ln_eps);
+#pragma unroll
+          for (int ps = 0; ps < NP; ++ps) {
+            const int cc = ch * CW + ps * 32 + p8 * 4;
+            const float4 g4 = *reinterpret_cast<const float4*>(ep.ln_gamma + (long)g * BN + cc);
+            const float4 t4 = *reinterpret_cast<const float4*>(ep.ln_beta + (long)g * BN + cc);
+            const float4 x = keep[ps * 8 + itr];
+            __nv_bfloat162 h0 = __floats2bfloat162_rn((x.x - mean[itr]) * rstd[itr] * g4.x + t4.x, (x.y - mean[itr]) * rstd[itr] * g4.y + t4.y);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn((x.z - mean[itr]) * rstd[itr] * g4.z + t4.z, (x.w - mean[itr]) * rstd[itr] * g4.w + t4.w);
+            *reinterpret_cast<uint2*>(lrow + ps * 32 + (long)itr * 4 * BN) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+          }
+        }
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -481,7 +487,8 @@ int launch_tc(const MrnbTcGemm& p, cudaStream_t st) {
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     attr_set = true;
   }
-  const int grid = ep.total_tiles < num_sms ? ep.total_tiles : num_sms;       // one persistent CTA per SM
+  const int slots = (LNF ? 1 : 2) * num_sms;                                  // persistent CTAs: two per SM (one with fused LN)
+  const int grid = ep.total_tiles < slots ? ep.total_tiles : slots;
   tc_gemm_kernel<BN, OUT_F32, GELU, LNF><<<grid, NTHREADS, smem, st>>>(tmA, tmW, ep);
   MRNB_CHECK_LAUNCH("tc_gemm_kernel");
   return MRNB_OK;
