@@ -269,7 +269,8 @@ def run_ours(args):
                                "experts frozen in train mode (BN batch stats + DropPath)" % B,
                    "global_batch": B * world, "parallelism": "dp%d" % world, "expert_chunk": args.chunk,
                    "l2": "4 rotating input batches; >1 GB of activations streamed per step (>> 126 MB L2), no explicit flush",
-                   "router_precision": "fp32 (CUDA cores)", "expert_precision": args.precision},
+                   "router_precision": "bf16 operands / fp32 accumulate (tcgen05)" if args.precision == "bf16" else "fp32",
+                   "expert_precision": args.precision},
         "e2e": {"value": round(e2e_value, 2), "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
                 "ms_per_step": round(e2e_ms / args.steps, 3)},
         "gpu_launches": int(launches),
@@ -288,9 +289,18 @@ def run_ours(args):
     print(json.dumps(out))
 
 
+def _shutdown():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
     else:
-        run_ours(a)
+        try:
+            run_ours(a)
+        finally:
+            _shutdown()
