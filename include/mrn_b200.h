@@ -44,8 +44,8 @@ long mrnb_launch_count(void);
 void mrnb_reset_launch_count(void);
 
 /* Optional per-kernel-family timing with CUDA events on the launching stream (bench.py roofline evidence).
- * Families: 0 tcgen05 GEMM, 1 fp32 GEMM, 2 attention, 3 LayerNorm, 4 patch-embed convs, 5 gated combine, 6 CTC lattice,
- * 7 router elementwise, 8 optimiser, 9 misc.  mrnb_profile_read synchronises on the recorded events. */
+ * Families: 0 tc_gemm_kernel (persistent tcgen05 GEMM), 1 sgemm_kernel (fp32), 2 attention, 3 LayerNorm, 4 patch embed,
+ * 5 gated combine, 6 CTC lattice, 7 router elementwise, 8 optimiser, 9 misc, 10 mlp_tc_kernel, 11 tc_gemm2_kernel.  mrnb_profile_read synchronises on the recorded events. */
 void mrnb_profile_enable(int on);
 void mrnb_profile_reset(void);
 int mrnb_profile_read(int family, double* ms, long* calls, double* flops, double* bytes);

@@ -322,7 +322,7 @@ int mrnb_tc_gemm2(const MrnbTcGemm2& p, cudaStream_t st) {
   MRNB_CHECK_ARG(p.K % BK == 0, "tc_gemm2: K=%d must be a multiple of 64", p.K);
   MRNB_CHECK_ARG(p.splitk <= 1 || (p.out32 && !p.out16 && !p.bias_n && !p.bias_m && !p.mul && !p.res && !p.gelu),
                  "tc_gemm2: split-K supports a raw fp32 accumulate only");
-  MrnbProfScope prof(MRNB_PROF_TCGEMM, st, 2.0 * p.M * p.N * p.K * p.groups,
+  MrnbProfScope prof(MRNB_PROF_TCGEMM2, st, 2.0 * p.M * p.N * p.K * p.groups,
                      (double)p.groups * (2.0 * p.M * p.K + 2.0 * p.N * p.K + 4.0 * p.M * p.N));
   const bool wide = p.N >= 128;
 #define GO(BN_)                                                                                   \

@@ -436,7 +436,7 @@ int mrnb_mlp_tc(const MrnbMlp& p, cudaStream_t st) {
   MRNB_CHECK_ARG(!p.ln_out || (p.D <= 128 && p.ln_gamma && p.ln_beta), "mlp_tc: fused LayerNorm needs D <= 128");
   MRNB_CHECK_ARG(p.x_gstride % 4 == 0, "mlp_tc: misaligned residual stream");
   const double M = (double)p.M * p.groups;
-  MrnbProfScope prof(MRNB_PROF_TCGEMM, st, 16.0 * M * p.D * p.D, M * p.D * (2.0 + 8.0 + (p.ln_out ? 2.0 : 0.0)));
+  MrnbProfScope prof(MRNB_PROF_MLP, st, 16.0 * M * p.D * p.D, M * p.D * (2.0 + 8.0 + (p.ln_out ? 2.0 : 0.0)));
   switch (p.D) {
     case 64: return p.ln_out ? launch_mlp<64, true>(p, st) : launch_mlp<64, false>(p, st);
     case 128: return p.ln_out ? launch_mlp<128, true>(p, st) : launch_mlp<128, false>(p, st);

@@ -299,6 +299,81 @@ __global__ void colsum_kernel(const float* __restrict__ X, MrnbAxis am, MrnbAxis
   }
 }
 
+// gate head GEMV (N = I <= 8): s[(b,t), j] = sum_(i,c) out[b,i,t,c] * Wcr[j,(i,c)] + bcr[j].  One warp per (b,t) row;
+// `out` is streamed exactly once (modules/model.py:402-403: rearrange 'b h w c -> b w (h c)' + channel_route).
+template <int I>
+__global__ void __launch_bounds__(256)
+gate_head_fwd_kernel(const float* __restrict__ out, const float* __restrict__ Wcr, const float* __restrict__ bcr, int B,
+                     int T, float* __restrict__ s) {
+  const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);      // row = b*T + t
+  const int lane = threadIdx.x & 31;
+  if (row >= (long)B * T) return;
+  const long b = row / T, t = row % T;
+  float acc[I];
+#pragma unroll
+  for (int j = 0; j < I; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < I; ++i) {
+    const float* zp = out + ((b * I + i) * T + t) * RD + lane * 8;
+    const float4 z0 = *reinterpret_cast<const float4*>(zp), z1 = *reinterpret_cast<const float4*>(zp + 4);
+#pragma unroll
+    for (int j = 0; j < I; ++j) {
+      const float* wp = Wcr + (long)j * I * RD + i * RD + lane * 8;
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp)), w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+      acc[j] += z0.x * w0.x + z0.y * w0.y + z0.z * w0.z + z0.w * w0.w + z1.x * w1.x + z1.y * w1.y + z1.z * w1.z + z1.w * w1.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < I; ++j) {
+    const float v = warp_sum(acc[j]);
+    if (lane == 0) s[row * I + j] = v + bcr[j];
+  }
+}
+
+// dWcr[j,(i,c)] += sum_(b,t) ds[(b,t),j] * out[b,i,t,c].  grid (row chunks of 128, I); thread = channel c.
+template <int I>
+__global__ void __launch_bounds__(RD)
+gate_head_dw_kernel(const float* __restrict__ ds, const float* __restrict__ out, int B, int T, float* __restrict__ dW) {
+  __shared__ float sds[128 * I];
+  const int i = blockIdx.y, c = threadIdx.x;
+  const long row0 = (long)blockIdx.x * 128, nrows = (long)B * T;
+  for (int k = threadIdx.x; k < 128 * I; k += RD) sds[k] = (row0 + k / I < nrows) ? ds[row0 * I + k] : 0.f;
+  __syncthreads();
+  float acc[I];
+#pragma unroll
+  for (int j = 0; j < I; ++j) acc[j] = 0.f;
+  for (int r = 0; r < 128; ++r) {
+    const long row = row0 + r;
+    if (row >= nrows) break;
+    const long b = row / T, t = row % T;
+    const float z = out[((b * I + i) * T + t) * RD + c];
+#pragma unroll
+    for (int j = 0; j < I; ++j) acc[j] = fmaf(sds[r * I + j], z, acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < I; ++j) atomicAdd(dW + (long)j * I * RD + i * RD + c, acc[j]);
+}
+
+template <int I>
+int launch_gate_head(const float* out, const float* Wcr, const float* bcr, int B, int T, float* s, cudaStream_t st) {
+  gate_head_fwd_kernel<I><<<cdiv((long)B * T, 8), 256, 0, st>>>(out, Wcr, bcr, B, T, s);
+  MRNB_CHECK_LAUNCH("gate_head_fwd_kernel");
+  return MRNB_OK;
+}
+template <int I>
+int launch_gate_head_dw(const float* ds, const float* out, int B, int T, float* dW, cudaStream_t st) {
+  gate_head_dw_kernel<I><<<dim3(cdiv((long)B * T, 128), I), RD, 0, st>>>(ds, out, B, T, dW);
+  MRNB_CHECK_LAUNCH("gate_head_dw_kernel");
+  return MRNB_OK;
+}
+#define MRNB_DISPATCH_I(fn, I_, ...)                                                                   \
+  switch (I_) {                                                                                         \
+    case 1: MRNB_TRY(fn<1>(__VA_ARGS__)); break; case 2: MRNB_TRY(fn<2>(__VA_ARGS__)); break;           \
+    case 3: MRNB_TRY(fn<3>(__VA_ARGS__)); break; case 4: MRNB_TRY(fn<4>(__VA_ARGS__)); break;           \
+    case 5: MRNB_TRY(fn<5>(__VA_ARGS__)); break; case 6: MRNB_TRY(fn<6>(__VA_ARGS__)); break;           \
+    case 7: MRNB_TRY(fn<7>(__VA_ARGS__)); break; default: MRNB_TRY(fn<8>(__VA_ARGS__)); break;          \
+  }
+
 // gate head finish: r[b,j] = sum_t wr[t] s[b,t,j] + br ; gate = softmax(r) ; index = first argmax
 __global__ void gate_finish_kernel(const float* __restrict__ s, const float* __restrict__ wr, const float* __restrict__ br,
                                    int B, int T, int I, float* __restrict__ r, float* __restrict__ gate,
@@ -615,13 +690,10 @@ int router_forward(const float* P, const float* x, const Dims& d, float* out_use
   // out = y2 W3^T + b3 + x
   MRNB_TRY(linear_rows(d, w.y2, w.y216, D, P + off[R_P3_W], W16 + off[R_P3_W], D, D, P + off[R_P3_B], x, out, D, st));
   if (scores || gate || index) {
-    MrnbGemm g{};   // s[(b,t), j] = sum_(i,c) out[b,i,t,c] Wcr[j,(i,c)] + bcr[j]     (N = I: fp32 CUDA cores)
-    g.A = out; g.am = mrnb_axis2(T, D, ITD); g.ak = mrnb_axis2(D, 1, TD); g.a_kfast = 1;
-    g.B = P + off[R_CR_W]; g.bn = mrnb_axis(ID); g.bk = mrnb_axis(1); g.b_kfast = 1;
-    g.C = w.s; g.cm = mrnb_axis(I); g.cn = mrnb_axis(1);
-    g.M = B * T; g.N = I; g.K = (int)ID; g.batch = 1; g.splitk = 1; g.alpha = 1.f; g.rows_per_scale = 1;
-    g.bias_n = P + off[R_CR_B];
-    MRNB_TRY(mrnb_sgemm(g, st));
+    {   // s[(b,t), j] = sum_(i,c) out[b,i,t,c] Wcr[j,(i,c)] + bcr[j]     (N = I: fp32 GEMV, one pass over `out`)
+      MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+      MRNB_DISPATCH_I(launch_gate_head, I, out, P + off[R_CR_W], P + off[R_CR_B], B, T, w.s, st);
+    }
     gate_finish_kernel<<<cdiv(B, 128), 128, 0, st>>>(w.s, P + off[R_ROUTE_W], P + off[R_ROUTE_B], B, T, I, scores, gate, index);
     MRNB_CHECK_LAUNCH("gate_finish_kernel");
   }
@@ -820,14 +892,9 @@ extern "C" int mrnb_router_backward(const float* params, const float* x, const f
                                         grads + off[R_ROUTE_B]);
     MRNB_CHECK_LAUNCH("route_bwd_kernel");
   }
-  {  // dWcr[j,(i,c)] = sum_(b,t) ds[(b,t),j] out[b,i,t,c]      (M = I rows: fp32 CUDA cores, split-K)
-    MrnbGemm g{};
-    g.A = w.ds; g.am = mrnb_axis(1); g.ak = mrnb_axis(I); g.a_kfast = 0;
-    g.B = w.out; g.bk = mrnb_axis2(T, D, ITD); g.bn = mrnb_axis2(D, 1, TD); g.b_kfast = 0;
-    g.C = grads + off[R_CR_W]; g.cm = mrnb_axis(ID); g.cn = mrnb_axis(1);
-    g.M = I; g.N = (int)ID; g.K = B * T; g.batch = 1; g.alpha = 1.f; g.rows_per_scale = 1;
-    g.splitk = (B * T + 1023) / 1024; if (g.splitk > 32) g.splitk = 32; if (g.splitk < 1) g.splitk = 1;
-    MRNB_TRY(mrnb_sgemm(g, st));
+  {  // dWcr[j,(i,c)] = sum_(b,t) ds[(b,t),j] out[b,i,t,c]
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    MRNB_DISPATCH_I(launch_gate_head_dw, I, w.ds, w.out, B, T, grads + off[R_CR_W], st);
   }
   MRNB_TRY(colsum(w.ds, mrnb_axis(I), mrnb_axis(1), B * T, I, grads + off[R_CR_B], st));
   {  // dout[b,i,t,c] = sum_j ds[(b,t),j] Wcr[j,(i,c)]

@@ -42,8 +42,8 @@ def reset_launch_count() -> None:
     L.load().mrnb_reset_launch_count()
 
 
-PROFILE_FAMILIES = ("tcgen05_gemm", "fp32_gemm", "attention", "layernorm", "patch_embed_conv", "gated_combine",
-                    "ctc_lattice", "router_elementwise", "optimizer", "misc")
+PROFILE_FAMILIES = ("tc_gemm_kernel", "sgemm_kernel", "attn_tc_kernel", "layernorm_kernel", "patch_embed", "combine_row_kernel",
+                    "ctc_lattice_kernel", "router_elementwise", "optimizer", "misc", "mlp_tc_kernel", "tc_gemm2_kernel")
 
 
 def profile_enable(on: bool):
