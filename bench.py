@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--chunk", type=int, default=0, help="samples per expert-forward chunk (0 = whole batch)")
     ap.add_argument("--cpu-sample", type=int, default=32, help="samples per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"],
+                    help="train: router-training step (the BASELINE metric); infer: hard-routed forward + greedy decode (cfg 5)")
     return ap.parse_args()
 
 
@@ -192,12 +194,23 @@ def run_ours(args):
     resident = [tuple(t.to(dev) for t in hb) for hb in host]
     h2d = sum(t.numel() * t.element_size() for t in host[0])
 
+    infer = args.mode == "infer"
+    if infer:
+        learner.model.eval()                            # validation(): model.eval(), hard route, greedy decode (test.py:139-221)
+
     def step_resident(k):
         img, tgt, lens, dom = resident[k % n_batches]
+        if infer:
+            r = learner.infer_batch(img, "TF")
+            return r["conf"], r["lens"]
         return learner.train_step_stage1(img, tgt, lens, dom)
 
     def step_e2e(k):
         img, tgt, lens, dom = (t.to(dev, non_blocking=True) for t in host[k % n_batches])
+        if infer:
+            r = learner.infer_batch(img, "TF")
+            ids = r["ids"].cpu()                        # the single D2H copy of the decoded ids (+ lengths, confidences)
+            return float(r["conf"].sum()), float(r["lens"].sum()) + float(ids[0, 0])
         l1, l2 = learner.train_step_stage1(img, tgt, lens, dom)
         return float(l1), float(l2)                     # D2H read of both losses (the reference logs them)
 
@@ -277,7 +290,8 @@ def run_ours(args):
     ctc_router_ms = sum(fams.get(k, {}).get("ms_per_step", 0.0) for k in ("sgemm_kernel", "tc_gemm2_kernel", "router_elementwise",
                                                                           "combine_row_kernel", "ctc_lattice_kernel"))
     out = {
-        "metric": METRIC, "value": round(value, 2), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC if not infer else "MRN-SVTR 6-expert inference + greedy decode samples/s", "value": round(value, 2),
+        "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": "SVTR-MRN 6-expert stage-1 (router-training) step, B=%d/GPU, union charset 5153, 32x256x4 crops, "
@@ -286,7 +300,8 @@ def run_ours(args):
                    "l2": "4 rotating input batches; >1 GB of activations streamed per step (>> 126 MB L2), no explicit flush",
                    "router_precision": "bf16 operands / fp32 accumulate (tcgen05)" if args.precision == "bf16" else "fp32",
                    "expert_precision": args.precision},
-        "e2e": {"value": round(e2e_value, 2), "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
+        "e2e": {"value": round(e2e_value, 2), "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": 8 if not infer else B * 64 * 4 + B * 8,
                 "ms_per_step": round(e2e_ms / args.steps, 3)},
         "gpu_launches": int(launches),
         "gpu_launches_per_step": int(launches // args.steps),
@@ -296,7 +311,9 @@ def run_ours(args):
         "ctc_router_ms_per_batch": round(ctc_router_ms, 3),
         "loss_clf": float(last[0]), "taski_loss": float(last[1]),
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if infer:
+        out["config"]["workload"] = ("SVTR-MRN 6-expert hard-routed inference + device greedy decode, B=%d/GPU, union charset 5153" % B)
+    if world == 1 and not args.no_cpu_baseline and not infer:
         v, ms, cores = cpu_stage1(args.cpu_sample, 2, 1)
         out["cpu_baseline"] = {"value": round(v, 3), "unit": "samples/s", "cores": cores, "kind": "port",
                                "sample": "2 timed router-training steps of %d samples (same config, batch reduced from 256), "

@@ -215,7 +215,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict
       }
       const float mnew = fmaxf(m, bmax * sl2);
       const float mref = (mnew == -INFINITY) ? 0.f : mnew;       // whole block masked so far
-      const float corr = exp2f(m - mref);                        // m = -inf -> 0
+      const float corr = ex2_approx(m - mref);                   // m = -inf -> 0
       float bsum = 0.f;
       // pass 2: P = exp2(s*scale*log2e - m) -> bf16 -> swizzled smem
 #pragma unroll
@@ -236,8 +236,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict
               if (!((vmask[c] >> (i + 1)) & 1u)) p1 = 0.f;
             }
             __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-            // the PV product uses the bf16-rounded probabilities: sum the same values for a consistent normaliser
-            bsum += __bfloat162float(hb.x) + __bfloat162float(hb.y);
+            bsum += p0 + p1;          // fp32 normaliser (rounding of P to bf16 is unbiased: no systematic mismatch with PV)
             pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
           }
         }
