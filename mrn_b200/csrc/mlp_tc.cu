@@ -84,14 +84,27 @@ struct MlpParams {
   const float* rowscale; int rows_per_scale; long rowscale_gs;
   __nv_bfloat16* ln_out; long ln_gs; const float* ln_gamma; const float* ln_beta; float ln_eps;   // optional (D <= 128)
   int m_tiles, total_tiles;
+  unsigned long long* trace;      // optional debug timeline (CTA 0), see MRNB_TRACE
 };
+
+#define MRNB_TRACE(slot_, idx_)                                                                    \
+  do {                                                                                             \
+    if (ep.trace && blockIdx.x == 0 && (idx_) < 64) {                                              \
+      unsigned long long now__;                                                                    \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now__));                                    \
+      ep.trace[(slot_) * 64 + (idx_)] = now__;                                                     \
+    }                                                                                              \
+  } while (0)
 
 template <int D>
 struct Cfg {
   static constexpr int KB = D / BK;                    // k-blocks of the first GEMM
   static constexpr int C = 4 * D / HC;                 // hidden chunks: 2, 4, 8
   static constexpr int SLOT = D > 128 ? 32768 : 16384; // ring slot: W1 k-block [128 x 64] or W2 k-block [D x 64]
-  static constexpr int RS = D > 128 ? 3 : 4;           // ring slots
+  static constexpr int RS = D > 128 ? 3 : 4;           // ring slots.  D = 256 streams 1 MiB of weights per 128-row tile: that
+                                                       // launch is L2-bandwidth bound (1.5 GB / launch), see DESIGN.md
+  static constexpr int NH = 1;                         // N-splits of the second GEMM (UMMA N = D / NH)
+  static constexpr int W2ROWS = D / NH;
   static constexpr int A_BYTES = KB * TILE16K;
   static constexpr int P_BYTES = 2 * TILE16K;          // [128 x 128] bf16 as two 64-wide K halves
   static constexpr int BIAS_BYTES = 5 * D * 4;
@@ -111,7 +124,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint8_t* ring = sP + K::P_BYTES;
   float* sb1 = reinterpret_cast<float*>(ring + K::RS * K::SLOT);
   float* sb2 = sb1 + 4 * D;
-  __shared__ __align__(8) uint64_t a_full, a_empty, w_full[4], w_empty[4], s_full[2], s_empty[2], p_full, p_empty, o_full, o_empty;
+  __shared__ __align__(8) uint64_t a_full, a_empty, w_full[8], w_empty[8], s_full[2], s_empty[2], p_full, p_empty, o_full, o_empty;
   __shared__ uint32_t tmem_base_sh;
   __shared__ float ln_part[2][4][2][32];
 
@@ -160,7 +173,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         for (int c = 0; c < K::C; ++c) {
           if (c + 1 < K::C)
             for (int kb = 0; kb < K::KB; ++kb) load_w(&tmW1, kb * BK, (c + 1) * HC, g, TILE16K);
-          for (int kk = 0; kk < 2; ++kk) load_w(&tmW2, c * HC + kk * BK, 0, g, D * BK * 2);
+          for (int kk = 0; kk < 2; ++kk)
+            for (int nh = 0; nh < K::NH; ++nh) load_w(&tmW2, c * HC + kk * BK, nh * K::W2ROWS, g, K::W2ROWS * BK * 2);
         }
       }
     }
@@ -168,7 +182,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     // ============================== MMA issuer ==============================
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc(HC);
-      constexpr uint32_t idesc_o = make_idesc(D) & ~((7u << 7) | (7u << 10));   // second GEMM in f16 x f16: P (GELU output) and W2 are f16
+      constexpr uint32_t idesc_o = make_idesc(K::W2ROWS) & ~((7u << 7) | (7u << 10));   // second GEMM in f16 x f16: P (GELU output) and W2 are f16
       uint32_t it = 0;
       int i = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
@@ -194,20 +208,26 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           if (c + 1 < K::C) issue_s(c + 1);
           if (c + 1 == K::C - 1 || K::C == 1) umma_commit(&a_empty);      // last S issued: A tile is free once it retires
           const uint32_t up = (uint32_t)(i * K::C + c);
+          MRNB_TRACE(0, (int)up);                          // MMA: S_{c+1} issued, start waiting for P_c
           mbar_wait(&p_full, up & 1u);
+          MRNB_TRACE(1, (int)up);                          // MMA: P_c available
           if (c == 0) mbar_wait(&o_empty, ((uint32_t)i & 1u) ^ 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          for (int kk = 0; kk < 2; ++kk, ++it) {
-            const int s = it % K::RS;
-            mbar_wait(&w_full[s], (it / K::RS) & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t ad = make_desc(smem_u32(sP + kk * TILE16K)), bd = make_desc(smem_u32(ring + (size_t)s * K::SLOT));
+          for (int kk = 0; kk < 2; ++kk) {
+            for (int nh = 0; nh < K::NH; ++nh, ++it) {
+              const int s = it % K::RS;
+              mbar_wait(&w_full[s], (it / K::RS) & 1u);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint64_t ad = make_desc(smem_u32(sP + kk * TILE16K)), bd = make_desc(smem_u32(ring + (size_t)s * K::SLOT));
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + K::O_COL, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc_o, (c | kk | k) != 0);
-            umma_commit(&w_empty[s]);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_base + K::O_COL + (uint32_t)(nh * K::W2ROWS), ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc_o,
+                          (c | kk | k) != 0);
+              umma_commit(&w_empty[s]);
+            }
           }
           umma_commit(&p_empty);
+          MRNB_TRACE(2, (int)up);                          // MMA: PV_c issued
           if (c == K::C - 1) umma_commit(&o_full);
         }
       }
@@ -225,6 +245,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     int cur_g = -1;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
       const int g = t / m_tiles, m0 = (t % m_tiles) * BM;
+      if (warp == 2 && lane == 0) MRNB_TRACE(9, i);                // epi: tile start
       if (g != cur_g) {                                        // (re)load the biases of this expert
         asm volatile("bar.sync 5, 256;" ::: "memory");         // everyone done with the previous expert's biases
         for (int k = threadIdx.x - 64; k < 4 * D; k += EPI_WARPS * 32) sb1[k] = ep.b1[(long)g * ep.b_gs1 + k];
@@ -237,12 +258,21 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       float4 rv[8];
 #pragma unroll
       for (int itr = 0; itr < 8; ++itr) rv[itr] = *reinterpret_cast<const float4*>(xrow + (long)itr * 4 * D);
+      if (NPASS > 1 && p8 == 0) {                              // later passes: pull the rows into L2 now (one lane per 128 B)
+#pragma unroll
+        for (int ps = 1; ps < NPASS; ++ps)
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(xrow + ps * 32 + (long)itr * 4 * D));
+      }
 
       // ---- hidden chunks: S_c -> +b1 -> GELU -> bf16 P
       for (int c = 0; c < K::C; ++c) {
         const int b = c & 1;
         const uint32_t u = (uint32_t)(i * (K::C / 2) + (c >> 1));
+        if (warp == 2 && lane == 0) MRNB_TRACE(3, i * K::C + c);   // epi: start waiting for S_c
         mbar_wait(&s_full[b], u & 1u);
+        if (warp == 2 && lane == 0) MRNB_TRACE(4, i * K::C + c);   // epi: S_c ready
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t v0[32], v1[32];
         tmem_ld32(lane_addr + (uint32_t)(b * HC + ch * 64), v0);
@@ -266,7 +296,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           pk[e4 * 2 + 1] = *reinterpret_cast<const uint32_t*>(&g1);
         }
         const uint32_t up = (uint32_t)(i * K::C + c);
+        if (warp == 2 && lane == 0) MRNB_TRACE(5, (int)up);        // epi: GELU done
         mbar_wait(&p_empty, (up & 1u) ^ 1u);                   // previous P has been consumed by its MMAs (GELU already done)
+        if (warp == 2 && lane == 0) MRNB_TRACE(6, (int)up);        // epi: P buffer free
         uint8_t* prow = sP + ch * TILE16K + r * 128;
 #pragma unroll
         for (int pc = 0; pc < 8; ++pc)                          // 8 pieces of 8 columns (16 B of bf16), XOR-swizzled by row
@@ -274,10 +306,12 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full);
+        if (warp == 2 && lane == 0) MRNB_TRACE(7, (int)up);        // epi: P_c published
       }
 
       // ---- final epilogue: O -> +b2, DropPath scale, + residual -> x (in place) [+ fused LayerNorm]
       mbar_wait(&o_full, (uint32_t)i & 1u);
+      if (warp == 2 && lane == 0) MRNB_TRACE(8, i);                // epi: O ready
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const float rs = ep.rowscale ? ep.rowscale[(long)g * ep.rowscale_gs + m0 / ep.rows_per_scale] : 1.0f;
       float4 keep[LNF ? NPASS * 8 : 1];
@@ -405,13 +439,14 @@ int launch_mlp(const MrnbMlp& p, cudaStream_t st) {
   CUtensorMap tmA, tmW1, tmW2;
   MRNB_TRY(map3(&tmA, p.A, D, p.M, p.groups, D, (long)p.M * D, BM));
   MRNB_TRY(map3(&tmW1, p.W1, D, 4 * D, p.groups, D, (long)4 * D * D, HC));
-  MRNB_TRY(map3(&tmW2, p.W2, 4 * D, D, p.groups, 4 * D, (long)4 * D * D, D));
+  MRNB_TRY(map3(&tmW2, p.W2, 4 * D, D, p.groups, 4 * D, (long)4 * D * D, K::W2ROWS));
   MlpParams ep{};
   ep.b1 = p.b1; ep.b2 = p.b2; ep.b_gs1 = 4 * D; ep.b_gs2 = D;
   ep.x = p.x; ep.x_gs = p.x_gstride;
   ep.rowscale = p.rowscale; ep.rows_per_scale = p.rows_per_scale > 0 ? p.rows_per_scale : 1; ep.rowscale_gs = p.rowscale_gstride;
   ep.ln_out = (__nv_bfloat16*)p.ln_out; ep.ln_gs = (long)p.M * D; ep.ln_gamma = p.ln_gamma; ep.ln_beta = p.ln_beta; ep.ln_eps = p.ln_eps;
   ep.m_tiles = p.M / BM; ep.total_tiles = ep.m_tiles * p.groups;
+  ep.trace = (unsigned long long*)p.trace;
   static bool attr = false;
   static int num_sms = 148;
   if (!attr) {
@@ -445,10 +480,14 @@ int mrnb_mlp_tc(const MrnbMlp& p, cudaStream_t st) {
 }
 
 // C-ABI test entry: one group.  x [M,D] fp32 is updated in place; ln_out (bf16 [M,D]) optional.
+static void* g_mlp_trace = nullptr;
+extern "C" void mrnb_mlp_set_trace(void* device_buffer) { g_mlp_trace = device_buffer; }
+
 extern "C" int mrnb_mlp_bf16(const void* A, const void* W1, const float* b1, const void* W2, const float* b2, float* x,
                              const float* rowscale, int rows_per_scale, void* ln_out, const float* ln_gamma,
                              const float* ln_beta, float ln_eps, int M, int D, cudaStream_t stream) {
   MrnbMlp p{};
+  p.trace = g_mlp_trace;
   p.A = A; p.W1 = W1; p.W2 = W2; p.b1 = b1; p.b2 = b2; p.x = x; p.x_gstride = (long)M * D;
   p.rowscale = rowscale; p.rows_per_scale = rows_per_scale;
   p.ln_out = ln_out; p.ln_gamma = ln_gamma; p.ln_beta = ln_beta; p.ln_eps = ln_eps;

@@ -12,6 +12,7 @@ struct MrnbMlp {
   const float* rowscale; int rows_per_scale; long rowscale_gstride;    // DropPath multipliers (tile-uniform)
   void* ln_out; const float* ln_gamma; const float* ln_beta; float ln_eps;   // optional next LayerNorm (D <= 128), may alias A
   int M, D, groups;
+  void* trace;            // optional device buffer [10][64] u64: debug timeline of CTA 0 (tools/mlp_trace.py)
 };
 
 int mrnb_mlp_tc(const MrnbMlp& p, cudaStream_t st);
