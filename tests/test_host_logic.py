@@ -1,0 +1,114 @@
+"""CPU tests of the host-side mirror of the reference API (no GPU compute): label codec, schedules, module tree /
+state_dict contract, loud failure without CUDA."""
+import argparse
+
+import pytest
+import torch
+
+from mrn_b200 import synth
+from oracle import mrn_oracle as O
+from oracle.ref_import import reference_available
+
+
+def make_opt(**kw):
+    d = dict(Transformation="None", FeatureExtraction="SVTR", SequenceModeling="None", Prediction="CTC", num_fiducial=20,
+             input_channel=4, output_channel=512, hidden_size=256, imgH=32, imgW=256, batch_max_length=25, lr=5e-4,
+             num_iter=100, grad_clip=5, exp_name="t", precision="fp32", drop_path=False, lan_list=["a", "b"],
+             val_interval=50, start_task=0)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def test_ctc_label_converter_matches_reference_semantics():
+    from mrn_b200.utils import CTCLabelConverter
+    chars = list("abcdefg") + ["中", "文"]
+    conv = CTCLabelConverter(chars)
+    assert conv.character[:4] == ["[CTCblank]", "[PAD]", "[UNK]", " "] and conv.dict["a"] == 4       # tools/utils.py:15-31
+    idx, lens = conv.encode(["abc", "", "a中z", "g" * 25], batch_max_length=25)
+    assert idx.shape == (4, 25) and idx.dtype == torch.int64 and lens.tolist() == [3, 0, 3, 25]
+    assert idx[0, :4].tolist() == [4, 5, 6, 1] and idx[1].eq(1).all() and idx[2, :3].tolist() == [4, conv.dict["中"], 2]
+    ref_idx, ref_len = O.ctc_encode(["abc", "", "a中z", "g" * 25], conv.dict)
+    assert torch.equal(idx, ref_idx) and torch.equal(lens, ref_len)
+    raw = torch.tensor([[0, 4, 4, 0, 4, 5, 5, 0, 0, 6], [0] * 10])
+    assert conv.decode(raw, [10, 10]) == ["aabc", ""]                                                  # tools/utils.py:62-76
+    assert conv.decode_compact(torch.tensor([[4, 4, 5, 6, -1], [-1] * 5]), torch.tensor([4, 0])) == ["aabc", ""]
+    if reference_available():
+        from oracle.ref_import import reference_modules
+        import contextlib, io
+        with reference_modules() as ref, contextlib.redirect_stdout(io.StringIO()):
+            rc = ref.utils.CTCLabelConverter(chars)
+            assert rc.character == conv.character and rc.dict == conv.dict
+            ri, rl = rc.encode(["abc", "", "a中z"], batch_max_length=25)
+            assert torch.equal(ri.cpu(), idx[:3]) and rl.cpu().tolist() == [3, 0, 3]
+            assert rc.decode(raw, [10, 10]) == conv.decode(raw, [10, 10])
+
+
+def test_one_cycle_and_edit_distance():
+    from mrn_b200.il_modules.mrn import one_cycle_lr, edit_distance
+    for s in (0, 1, 59, 60, 150, 199):
+        assert abs(one_cycle_lr(s, 200, 5e-4) - O.one_cycle_lr(s, 200, 5e-4)) < 1e-15
+    assert edit_distance("kitten", "sitting") == 3 and edit_distance("", "abc") == 3 and edit_distance("abc", "abc") == 0
+
+
+def test_module_tree_keeps_the_reference_state_dict_contract():
+    from mrn_b200.il_modules.mrn import RankLocal
+    from mrn_b200.modules.model import MRNNet
+    cc = (37, 61, 96)
+    opt = make_opt()
+    net = MRNNet(opt)
+    for i, c in enumerate(cc):
+        net.update_fc(opt.hidden_size, c)
+        net.build_prediction(opt, c)
+        # the router is rebuilt for the new expert count at every task (modules/model.py:437-452)
+        assert net.channel_route.weight.shape == (i + 1, (i + 1) * 256)
+        assert net.dm_router[0].spatial_gating.proj.weight.shape == ((i + 1) * 64, (i + 1) * 64)
+    want = synth.svtr_mrn_shapes(cc)
+    got = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert got == {k: tuple(s) for k, s in want.items()}
+    sd = synth.synth_state_dict(cc, 3)
+    res = net.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert net.model[1].fc is net.model[1].Prediction                  # alias kept (modules/model.py:181)
+    wrapped = RankLocal(net).state_dict()
+    assert all(k.startswith("module.") for k in wrapped) and len(wrapped) == len(got)   # DataParallel key prefix (mrn.py:412-415)
+    # parameters() order of the router == the C-ABI arena order
+    from mrn_b200 import ops
+    names = [n for n, _ in net.named_parameters() if not n.startswith("model.")]
+    assert tuple(names) == ops.ROUTER_PARAM_NAMES
+    # SVTR constructor quirk: LayerNorm bias initialised to 1.0 (modules/svtr.py:494-496)
+    fresh = MRNNet(opt); fresh.update_fc(256, 10)
+    assert float(fresh.model[0].model.FeatureExtraction.ConvNet.blocks1[0].norm1.bias.detach().mean()) == 1.0
+
+
+def test_router_arena_views_share_storage():
+    from mrn_b200.modules.model import MRNNet
+    from mrn_b200 import ops
+    opt = make_opt()
+    net = MRNNet(opt)
+    for c in (20, 30):
+        net.update_fc(256, c); net.build_prediction(opt, c)
+    arena = net.router_arena("cpu")
+    n, off = ops.router_param_offsets(2)
+    assert arena.numel() == n
+    net.route.weight.data.fill_(7.0)
+    assert float(arena[off[0]]) == 7.0                                  # parameters are views into the arena
+    g = net.router_grad_arena()
+    g.fill_(2.0)
+    assert float(net.dm_router[0].proj_3.bias.grad[0]) == 2.0
+
+
+def test_no_cpu_fallback_and_unsupported_configs_fail_loudly():
+    from mrn_b200.modules.model import MRNNet, Model
+    opt = make_opt()
+    net = MRNNet(opt)
+    net.update_fc(256, 12); net.build_prediction(opt, 12)
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        net(torch.zeros(1, 4, 32, 256), True, None, True)
+    with pytest.raises(NotImplementedError):
+        MRNNet(make_opt(FeatureExtraction="VGG", SequenceModeling="BiLSTM"))
+    with pytest.raises(NotImplementedError):
+        Model(make_opt(Prediction="Attn"))
+    from mrn_b200.il_modules.mrn import MRN
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            MRN(opt)
