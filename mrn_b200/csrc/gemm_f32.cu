@@ -137,6 +137,7 @@ sgemm_kernel(const MrnbGemm p) {
       v += bm;
       if (p.bias_n) v += p.bias_n[(long)batch * p.bias_bstride + n];
       if (p.act == 1) v = gelu_erf(v);
+      else if (p.act == 2) v = fmaxf(v, 0.f);
       if (mul) v *= mul[o];
       v *= rs;
       if (res) v += res[o];

@@ -122,7 +122,8 @@ struct TcEpi {
   // fused LayerNorm of the output rows (LNF kernels): bf16 ln_out[g][row][N], gamma/beta [groups][N]
   __nv_bfloat16* ln_out; long ln_gs; const float* ln_gamma; const float* ln_beta; float ln_eps;
   // implicit-GEMM convolution (see MrnbTcConv)
-  int conv, rows_per_img, per_kh, cch, w_off, sh, imgs_per_group;
+  int conv, rows_per_img, per_kh, cch, w_off, sh, imgs_per_group, ow_shift, pad_h;
+  int relu;
 };
 
 constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each owning half of the tile columns
@@ -151,6 +152,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int stages = ep.stages, KB = ep.KB;
   const int n_tiles = ep.n_tiles, m_tiles = ep.m_tiles;
   const int total = ep.total_tiles;
+  const bool relu = ep.relu != 0;
   float* staging = reinterpret_cast<float*>(smem + (size_t)stages * STAGE_BYTES);
 
   if (threadIdx.x == 0) {
@@ -183,9 +185,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
           if (ep.conv) {
             const int img = g * ep.imgs_per_group + m0 / ep.rows_per_img;
-            const int oh0 = (m0 % ep.rows_per_img) >> 6;               // 64 output columns per output row
+            const int oh0 = (m0 % ep.rows_per_img) >> ep.ow_shift;     // 64 or 128 output columns per output row
             const int kh = kb / ep.per_kh, j = kb % ep.per_kh;
-            tma_load_4d(sa, &tmA, &full_bar[s], (j % ep.cch) * 64, j / ep.cch + ep.w_off, oh0 * ep.sh - 1 + kh, img);
+            tma_load_4d(sa, &tmA, &full_bar[s], (j % ep.cch) * 64, j / ep.cch + ep.w_off, oh0 * ep.sh - ep.pad_h + kh, img);
           } else {
             tma_load_3d(sa, &tmA, &full_bar[s], kb * BK, m0, g);
           }
@@ -298,6 +300,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((p8 ^ (rl & 7)) * 4));
               x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
               if (GELU) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+              if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
               x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
               if (pre_res) { x.x += rv[itr].x; x.y += rv[itr].y; x.z += rv[itr].z; x.w += rv[itr].w; }
               *reinterpret_cast<float4*>(op + itr * ostep) = x;
@@ -311,6 +314,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((p8 ^ (rl & 7)) * 4));
               x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
               if (GELU) { x.x = gelu_fast(x.x); x.y = gelu_fast(x.y); x.z = gelu_fast(x.z); x.w = gelu_fast(x.w); }
+              if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
               x.x *= rs; x.y *= rs; x.z *= rs; x.w *= rs;
               __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
               *reinterpret_cast<uint2*>(op + itr * ostep) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
@@ -333,6 +337,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 4 && col + j < ep.N; ++j) {
               float x = xv[j];
               if (GELU) x = OUT_F32 ? gelu_erf(x) : gelu_fast(x);
+              if (relu) x = fmaxf(x, 0.f);
               x *= rsr;
               if (OUT_F32) {
                 if (ep.res) x += ep.res[o + j];
@@ -445,9 +450,10 @@ int make_conv_map(CUtensorMap* map, const void* ptr, const MrnbTcConv& c) {
   for (int j = 0; j < 4; ++j) dims[j] = (cuuint64_t)c.dims[j];
   for (int j = 0; j < 3; ++j) strides[j] = (cuuint64_t)c.strides[j] * 2;
   // with a traversal stride s the box spans (n - 1) * s + 1 elements to pick up n of them
-  cuuint32_t box[4] = {64, 64, (cuuint32_t)((c.box_h - 1) * c.sh + 1), (cuuint32_t)c.box_img};
+  const int bw = c.box_w > 0 ? c.box_w : 64;
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)((c.box_h - 1) * c.sh + 1), (cuuint32_t)c.box_img};
   cuuint32_t estr[4] = {1, 1, (cuuint32_t)(c.box_h > 1 ? c.sh : 1), 1};
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || c.box_h * c.box_img * 64 != BM) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || c.box_h * c.box_img * bw != BM || (bw != 64 && bw != 128)) {
     mrnb_set_error("tc_gemm: bad convolution view");
     return MRNB_ERR_ARG;
   }
@@ -474,6 +480,7 @@ int launch_tc(const MrnbTcGemm& p, cudaStream_t st) {
   ep.ln_out = (__nv_bfloat16*)p.ln_out; ep.ln_gs = p.ln_gstride; ep.ln_gamma = p.ln_gamma; ep.ln_beta = p.ln_beta; ep.ln_eps = p.ln_eps;
   ep.conv = p.conv.enabled; ep.rows_per_img = p.conv.rows_per_img; ep.per_kh = p.conv.per_kh; ep.cch = p.conv.cch;
   ep.w_off = p.conv.w_off; ep.sh = p.conv.sh; ep.imgs_per_group = p.conv.imgs_per_group;
+  ep.ow_shift = p.conv.box_w == 128 ? 7 : 6; ep.pad_h = p.conv.pad_h; ep.relu = p.relu;
   ep.n_tiles = cdiv(p.N, BN); ep.m_tiles = cdiv(p.M, BM);
   ep.total_tiles = ep.n_tiles * ep.m_tiles * p.groups;
   const size_t smem = 1024 + (size_t)ep.stages * (A_STAGE_BYTES + BN * BK * 2) + STAGING_BYTES;

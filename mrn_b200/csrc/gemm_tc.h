@@ -6,7 +6,8 @@
 // [img][h][w-slot][64-element slot] (rank-4 map, zero fill outside the image = padding).  Output rows are
 // (img, oh, ow) with ow fastest; a 128-row tile is box_h output rows x 64 columns of box_img images.
 //   k-block kb -> kh = kb / per_kh, j = kb % per_kh ; TMA coords (c, w, h, img) =
-//   ((j % cch) * 64, j / cch + w_off, oh0 * sh - 1 + kh, img0)
+//   ((j % cch) * 64, j / cch + w_off, oh0 * sh - pad_h + kh, img0)
+// box_w (0 = 64) output columns per output row: 64 or 128 (a power of two); 128 rows = box_w x box_h x box_img.
 struct MrnbTcConv {
   int enabled;
   long dims[4];        // elements: {inner (>= 64), w slots, H, images}
@@ -15,6 +16,7 @@ struct MrnbTcConv {
   int sh;              // stride along h (TMA element stride)
   int rows_per_img, per_kh, cch, w_off;
   int imgs_per_group;
+  int box_w, pad_h;
 };
 
 struct MrnbTcGemm {
@@ -26,6 +28,7 @@ struct MrnbTcGemm {
   const float* res;                                    // fp32 residual at the output address (out_f32 only)
   const float* rowscale; int rows_per_scale; long rowscale_gstride;   // DropPath: * rowscale[g*gs + m / rows_per_scale]
   int M, N, K, groups, gelu;
+  int relu;                                            // ReLU on the biased accumulator (VGG convolutions)
   // optional fused LayerNorm of the fp32 output rows (N == 64 or 128): bf16 ln_out[g][m][N] = LN(out row) * gamma[g] + beta[g]
   void* ln_out; long ln_gstride; const float* ln_gamma; const float* ln_beta; float ln_eps;
   MrnbTcConv conv;     // optional: A is an implicit im2col view (A / lda / a_gstride ignored except A as base pointer)

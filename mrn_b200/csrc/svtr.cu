@@ -15,6 +15,7 @@
 #include "gemm_tc.h"
 #include "mlp_tc.h"
 #include "svtr.h"
+#include "expert_util.cuh"
 
 int mrnb_attention_tc(const void* qkv, void* out, int groups, int N, int d, int heads, int H, int W, int local, cudaStream_t st);
 
@@ -172,32 +173,6 @@ conv0_kernel(const float* __restrict__ img, const float* __restrict__ w /*[I,32,
       atomicAdd(stats + ((long)e * 32 + c) * 2 + k, t);
     }
   }
-}
-
-// BN finalize: scale/shift per (expert, channel) from batch statistics (train) or running statistics (eval);
-// in train mode also the running-stat update with momentum 0.1 and the unbiased variance (nn.BatchNorm2d).
-__global__ void bn_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ run_mean,
-                                   float* __restrict__ run_var, float* __restrict__ scale_shift /*[I,C,2]*/, int I, int C,
-                                   double count, int use_batch_stats, int update_running, float eps) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= I * C) return;
-  float mean, var;
-  if (use_batch_stats) {
-    const double m = stats[idx * 2] / count;
-    double v = stats[idx * 2 + 1] / count - m * m;
-    if (v < 0) v = 0;
-    mean = (float)m; var = (float)v;
-    if (update_running) {
-      run_mean[idx] = 0.9f * run_mean[idx] + 0.1f * mean;
-      run_var[idx] = 0.9f * run_var[idx] + 0.1f * (float)(v * count / (count - 1.0));
-    }
-  } else {
-    mean = run_mean[idx]; var = run_var[idx];
-  }
-  const float sc = gamma[idx] * rsqrtf(var + eps);
-  scale_shift[idx * 2] = sc;
-  scale_shift[idx * 2 + 1] = beta[idx] - mean * sc;
 }
 
 // conv1: 32->64, 3x3 s2 p1 over GELU(BN(conv0)) (applied on load) -> raw NHWC [I,B,8,64,64] + BN statistics.
@@ -446,12 +421,6 @@ __global__ void cast_groups_kernel(const float* __restrict__ x, long x_gs, __nv_
   *reinterpret_cast<uint2*>(y + i * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
 }
 
-template <typename AT>
-__global__ void cast_kernel(const float* __restrict__ x, AT* __restrict__ y, long n) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = from_f32<AT>(x[i]);
-}
-
 // features [I, Bc, T, D] (expert-major, AT) -> router layout [Bc, I, T, D] fp32   (torch.stack(...,1), model.py:400)
 __global__ void feature_scatter_kernel(const float* __restrict__ src, float* __restrict__ dst, int I, int Bc, long TD) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -463,59 +432,6 @@ __global__ void feature_scatter_kernel(const float* __restrict__ src, float* __r
   const long e = e4 / (TD * Bc);
   *reinterpret_cast<float4*>(dst + (b * I + e) * TD + td) = *reinterpret_cast<const float4*>(src + e4);
 }
-
-// ------------------------------------------------------------------------------------------------
-// linear<AT>: grouped Linear over experts: out[g, m, :] = epi(A[g, m, :] . W[g]^T + b[g])
-// ------------------------------------------------------------------------------------------------
-struct LinearArgs {
-  const void* A; long lda; long a_gstride;       // AT
-  const float* W32; const void* W16; long w_gstride;   // [groups, N, K]
-  const float* bias; long bias_gstride;
-  void* out; long ldo; long o_gstride; int out_is_f32;   // out dtype: fp32 or AT
-  const float* res; const float* rowscale; int rows_per_scale; long rowscale_gstride;
-  int M, N, K, groups, gelu;
-  // tensor-core mode only: fused LayerNorm of the output rows -> ln_out (AT) [groups][M][N]
-  void* ln_out; const float* ln_gamma; const float* ln_beta; float ln_eps;
-};
-
-template <typename AT>
-int linear(const LinearArgs& a, cudaStream_t st);
-
-template <>
-int linear<float>(const LinearArgs& a, cudaStream_t st) {
-  MrnbGemm g = mrnb_gemm_nt((const float*)a.A, a.lda, a.W32, a.K, (float*)a.out, a.ldo, a.M, a.N, a.K);
-  g.batch = a.groups; g.sAb = a.a_gstride; g.sBb = a.w_gstride; g.sCb = a.o_gstride;
-  g.bias_n = a.bias; g.bias_bstride = a.bias_gstride;
-  g.res = a.res; g.rowscale = a.rowscale; g.rows_per_scale = a.rows_per_scale > 0 ? a.rows_per_scale : 1;
-  g.rowscale_bstride = a.rowscale_gstride;
-  g.act = a.gelu;
-  return mrnb_sgemm(g, st);
-}
-
-template <>
-int linear<__nv_bfloat16>(const LinearArgs& a, cudaStream_t st) {
-  MrnbTcGemm g{};
-  g.A = a.A; g.lda = a.lda; g.a_gstride = a.a_gstride;
-  g.W = a.W16; g.ldw = a.K; g.w_gstride = a.w_gstride;
-  g.bias = a.bias; g.bias_gstride = a.bias_gstride;
-  g.out = a.out; g.ldo = a.ldo; g.o_gstride = a.o_gstride; g.out_f32 = a.out_is_f32;
-  g.res = a.res; g.rowscale = a.rowscale; g.rows_per_scale = a.rows_per_scale > 0 ? a.rows_per_scale : 1;
-  g.rowscale_gstride = a.rowscale_gstride;
-  g.M = a.M; g.N = a.N; g.K = a.K; g.groups = a.groups; g.gelu = a.gelu;
-  g.ln_out = a.ln_out; g.ln_gstride = (long)a.M * a.N; g.ln_gamma = a.ln_gamma; g.ln_beta = a.ln_beta; g.ln_eps = a.ln_eps;
-  return mrnb_tc_gemm(g, st);
-}
-
-inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
-
-struct Workspace {
-  char* base; size_t off, cap;
-  template <typename T> T* take(size_t n) {
-    T* p = reinterpret_cast<T*>(base + off);
-    off = align_up(off + n * sizeof(T));
-    return p;
-  }
-};
 
 template <typename AT>
 size_t svtr_workspace_bytes_t(int I, int B, int Bc) {
@@ -593,6 +509,7 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
     g.conv.dims[0] = 64; g.conv.dims[1] = 65; g.conv.dims[2] = 16; g.conv.dims[3] = (long)I * B;
     g.conv.strides[0] = 64; g.conv.strides[1] = 130 * 32; g.conv.strides[2] = 16L * 130 * 32;
     g.conv.box_h = 2; g.conv.box_img = 1; g.conv.sh = 2; g.conv.rows_per_img = 512; g.conv.per_kh = 2; g.conv.cch = 1;
+    g.conv.pad_h = 1;
     g.conv.w_off = 0; g.conv.imgs_per_group = B;
     MRNB_TRY(mrnb_tc_gemm(g, st));
     if (bn_batch_stats) {
@@ -762,7 +679,7 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
         g.conv.dims[0] = d; g.conv.dims[1] = Wd; g.conv.dims[2] = H; g.conv.dims[3] = (long)I * bc;
         g.conv.strides[0] = d; g.conv.strides[1] = (long)Wd * d; g.conv.strides[2] = (long)H * Wd * d;
         const int Ho = H / 2;
-        g.conv.box_h = Ho >= 2 ? 2 : 1; g.conv.box_img = Ho >= 2 ? 1 : 2; g.conv.sh = 2;
+        g.conv.box_h = Ho >= 2 ? 2 : 1; g.conv.box_img = Ho >= 2 ? 1 : 2; g.conv.sh = 2; g.conv.pad_h = 1;
         g.conv.rows_per_img = Ho * Wd; g.conv.per_kh = 3 * (d / 64); g.conv.cch = d / 64; g.conv.w_off = -1;
         g.conv.imgs_per_group = bc;
         MRNB_TRY(mrnb_tc_gemm(g, st));

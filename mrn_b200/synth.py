@@ -63,6 +63,45 @@ def svtr_expert_shapes(prefix: str, n_class: int) -> "OrderedDict[str, Tuple[int
     return s
 
 
+VGG_CONVS = ((0, 4, 64, 3, True), (3, 64, 128, 3, True), (6, 128, 256, 3, True), (8, 256, 256, 3, True),
+             (11, 256, 512, 3, False), (14, 512, 512, 3, False), (18, 512, 512, 2, True))   # (index, Cin, Cout, k, bias)
+VGG_BNS = (12, 15)
+
+
+def crnn_expert_shapes(prefix: str, n_class: int) -> "OrderedDict[str, Tuple[int, ...]]":
+    """state_dict keys of one Model(opt) with VGG / BiLSTM / CTC (modules/feature_extraction.py:19-47,
+    modules/sequence_modeling.py:4-22, modules/model.py:46-78,176-181)."""
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    c = prefix + "model.FeatureExtraction.ConvNet."
+    for idx, ci, co, k, bias in VGG_CONVS:
+        s[c + f"{idx}.weight"] = (co, ci, k, k)
+        if bias:
+            s[c + f"{idx}.bias"] = (co,)
+        if idx + 1 in VGG_BNS:
+            for nm in ("weight", "bias", "running_mean", "running_var"):
+                s[c + f"{idx + 1}.{nm}"] = (co,)
+            s[c + f"{idx + 1}.num_batches_tracked"] = ()
+    for layer, kin in ((0, 512), (1, 256)):
+        q = prefix + f"model.SequenceModeling.{layer}."
+        for suf in ("", "_reverse"):
+            s[q + "rnn.weight_ih_l0" + suf] = (1024, kin)
+            s[q + "rnn.weight_hh_l0" + suf] = (1024, 256)
+            s[q + "rnn.bias_ih_l0" + suf] = (1024,)
+            s[q + "rnn.bias_hh_l0" + suf] = (1024,)
+        s[q + "linear.weight"] = (256, 512); s[q + "linear.bias"] = (256,)
+    s[prefix + "fc.weight"] = (n_class, 256); s[prefix + "fc.bias"] = (n_class,)
+    s[prefix + "Prediction.weight"] = (n_class, 256); s[prefix + "Prediction.bias"] = (n_class,)
+    return s
+
+
+def crnn_mrn_shapes(class_counts: Sequence[int]) -> "OrderedDict[str, Tuple[int, ...]]":
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    for i, c in enumerate(class_counts):
+        s.update(crnn_expert_shapes(f"model.{i}.", c))
+    s.update(router_shapes(len(class_counts), T=63))          # modules/model.py:322-323: patch = 63 for VGG
+    return s
+
+
 def router_shapes(n_experts: int, T: int = 64, D: int = 256) -> "OrderedDict[str, Tuple[int, ...]]":
     """route / channel_route / dm_router.0.* (modules/model.py:437-452, modules/dm_router.py:35-47)."""
     I = n_experts
@@ -101,13 +140,18 @@ def synth_tensor(seed: int, key: str, shape) -> torch.Tensor:
         return randn(seed, key, shape, 0.1)
     if key.endswith("pos_embed"):
         return randn(seed, key, shape, 0.2)
-    is_norm = (".norm" in key) or ("patch_embed.proj.1." in key) or ("patch_embed.proj.4." in key)
+    is_norm = (".norm" in key) or ("patch_embed.proj.1." in key) or ("patch_embed.proj.4." in key) \
+        or ("ConvNet.12." in key) or ("ConvNet.15." in key)
     if is_norm and len(shape) == 1:
         return (1.0 + randn(seed, key, shape, 0.1)) if leaf == "weight" else randn(seed, key, shape, 0.1)
     if leaf == "bias":
         return randn(seed, key, shape, 0.05)
     fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else int(shape[0])
     gain = 1.0
+    if "ConvNet." in key and key.split("ConvNet.")[1].split(".")[0].isdigit():
+        gain = 1.4         # VGG: ReLU halves the second moment, keep activations O(1) through 7 convolutions
+    if "rnn.weight_hh" in key:
+        fan_in = 256
     if key.startswith("route.") or key.startswith("channel_route."):
         gain = 1.5         # spread the gate away from uniform
     if ".fc." in key or ".Prediction." in key:
@@ -115,9 +159,10 @@ def synth_tensor(seed: int, key: str, shape) -> torch.Tensor:
     return randn(seed, key, shape, gain / np.sqrt(fan_in))
 
 
-def synth_state_dict(class_counts: Sequence[int], seed: int = 111) -> "OrderedDict[str, torch.Tensor]":
+def synth_state_dict(class_counts: Sequence[int], seed: int = 111, arch: str = "svtr") -> "OrderedDict[str, torch.Tensor]":
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
-    for k, shp in svtr_mrn_shapes(class_counts).items():
+    shapes = svtr_mrn_shapes(class_counts) if arch == "svtr" else crnn_mrn_shapes(class_counts)
+    for k, shp in shapes.items():
         kk = k.replace(".Prediction.", ".fc.")      # Prediction is the same nn.Linear object as fc (model.py:181)
         sd[k] = synth_tensor(seed, kk, shp)
     return sd

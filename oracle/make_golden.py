@@ -32,8 +32,9 @@ def keep(t: torch.Tensor) -> np.ndarray:
     return a.copy()
 
 
-def build_ref_net(ref, class_counts, sd):
-    opt = argparse.Namespace(Transformation="None", FeatureExtraction="SVTR", SequenceModeling="None",
+def build_ref_net(ref, class_counts, sd, arch="svtr"):
+    opt = argparse.Namespace(Transformation="None", FeatureExtraction="SVTR" if arch == "svtr" else "VGG",
+                             SequenceModeling="None" if arch == "svtr" else "BiLSTM",
                              Prediction="CTC", num_fiducial=20, input_channel=4, output_channel=512,
                              hidden_size=256, imgH=32, imgW=256, batch_max_length=25)
     with contextlib.redirect_stdout(io.StringIO()):
@@ -46,15 +47,15 @@ def build_ref_net(ref, class_counts, sd):
     return net
 
 
-def run_case(name, class_counts, B, seed):
+def run_case(name, class_counts, B, seed, arch="svtr"):
     I = len(class_counts)
-    sd = synth.synth_state_dict(class_counts, seed)
+    sd = synth.synth_state_dict(class_counts, seed, arch=arch)
     img, tgt, lens, dom = synth.synth_batch(B, class_counts, seed)
     rates = [0.1 * i / 11 for i in range(12)]
     drop = synth.synth_drop_scales(I, B, rates, seed)
     g = {}
     with reference_modules() as ref:
-        net = build_ref_net(ref, class_counts, sd)
+        net = build_ref_net(ref, class_counts, sd, arch)
         crit = torch.nn.CTCLoss(reduction="mean", zero_infinity=True)       # il_modules/base.py:131
         ce = torch.nn.CrossEntropyLoss(reduction="mean")                     # il_modules/mrn.py:150
         conv = ref.utils.CTCLabelConverter([chr(0x4E00 + i) for i in range(class_counts[-1] - 4)])
@@ -110,8 +111,15 @@ def run_case(name, class_counts, B, seed):
             _, pidx = lg.max(2)                                              # test.py:211
             g["decode_raw"] = pidx.numpy()
             strs = conv.decode(pidx, torch.IntTensor([lg.size(1)] * B))      # test.py:212-213
-            g["decode_ids"] = np.array([[conv.dict[ch] for ch in s] + [-1] * (64 - len(s)) for s in strs], dtype=np.int64)
-            g["decode_len"] = np.array([len(s) for s in strs], dtype=np.int64)
+            # ids behind the reference's strings ([PAD]/[UNK] are multi-character entries, so re-derive the ids with
+            # the collapse rule of tools/utils.py:66-74 and check they spell exactly the reference's output)
+            ids = []
+            for b_, row in enumerate(pidx.tolist()):
+                r = [c for k_, c in enumerate(row) if c != 0 and not (k_ > 0 and row[k_ - 1] == c)]
+                assert "".join(conv.character[c] for c in r) == strs[b_]
+                ids.append(r)
+            g["decode_ids"] = np.array([r + [-1] * (lg.size(1) - len(r)) for r in ids], dtype=np.int64)
+            g["decode_len"] = np.array([len(r) for r in ids], dtype=np.int64)
             pmax, _ = torch.softmax(lg, dim=2).max(dim=2)                    # test.py:219-220
             g["confidence"] = np.array([float(pm.cumprod(dim=0)[-1]) for pm in pmax], dtype=np.float64)   # test.py:257
             ff = net(img, False, None, False)                                # cross=False path, model.py:346-348
@@ -127,7 +135,7 @@ def run_case(name, class_counts, B, seed):
             return x * s.view(-1, 1, 1)
         ref.svtr.drop_path = injected
         try:
-            for i in range(I):
+            for i in range(I if arch == "svtr" else 0):
                 for j in range(12):
                     if rates[j] > 0:                 # Block uses Identity when drop_path == 0 (svtr.py:187)
                         queue.append(drop[i, j, 0]); queue.append(drop[i, j, 1])
@@ -140,12 +148,14 @@ def run_case(name, class_counts, B, seed):
         g["train_features"] = keep(torch.stack(feats[:I], 1))
         g["train_gate"] = tr["index"].numpy()
         g["train_logits_soft"] = keep(tr["logits"])
-        bn = net.model[0].model.FeatureExtraction.ConvNet.patch_embed.proj[1]
+        cn = net.model[0].model.FeatureExtraction.ConvNet
+        bn = cn.patch_embed.proj[1] if arch == "svtr" else cn[12]
         g["train_bn1_running_mean_e0"] = bn.running_mean.numpy().copy()      # momentum 0.1 update
         g["train_bn1_running_var_e0"] = bn.running_var.numpy().copy()
         for h in hooks:
             h.remove()
     g["class_counts"] = np.array(class_counts); g["B"] = np.int64(B); g["seed"] = np.int64(seed)
+    g["arch"] = np.array(arch)
     g["sub"] = np.int64(SUB); g["max_full"] = np.int64(MAX_FULL)
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, name + ".npz")
@@ -176,9 +186,18 @@ def run_router_case(name, I, B, seed):
 
 
 if __name__ == "__main__":
+    import sys
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    run_case("svtr_mrn_i3_b3", (37, 61, 96), 3, 111)
-    run_case("svtr_mrn_i2_b4", (53, 80), 4, 7)
+    only = sys.argv[1:]
+    if not only or "svtr" in only:
+        run_case("svtr_mrn_i3_b3", (37, 61, 96), 3, 111)
+        run_case("svtr_mrn_i2_b4", (53, 80), 4, 7)
+    if not only or "crnn" in only:
+        # BASELINE.json configs[0] in miniature: CRNN-MRN (VGG + BiLSTM + CTC), 2 tasks; and a 3-task case
+        run_case("crnn_mrn_i2_b4", (53, 80), 4, 21, arch="crnn")
+        run_case("crnn_mrn_i3_b2", (37, 61, 96), 2, 33, arch="crnn")
+    if only and "router" not in only:
+        sys.exit(0)
     run_router_case("dm_router_i3_b2", 3, 2, 5)
     run_router_case("dm_router_i6_b1", 6, 1, 9)

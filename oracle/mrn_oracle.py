@@ -149,12 +149,67 @@ def svtr_backbone(sd: Dict[str, torch.Tensor], p: str, image: torch.Tensor, bn_m
     return x        # [B, 64, 512]  (svtr.py:527 + model.py:88-95 are pure relabelings of this tensor)
 
 
+# ----------------------------------------------------------------------------------------------
+# CRNN expert: VGG feature extractor + 2 x BidirectionalLSTM
+# (modules/feature_extraction.py:19-47, modules/sequence_modeling.py:4-22, modules/model.py:46-57,82-101)
+# ----------------------------------------------------------------------------------------------
+
+def vgg_backbone(sd: Dict[str, torch.Tensor], p: str, image: torch.Tensor, bn_mode: str = "eval") -> torch.Tensor:
+    """VGG_FeatureExtractor.forward (feature_extraction.py:19-47: Sequential indices 0..19) followed by
+    Model_Extractor's permute / AdaptiveAvgPool2d((None,1)) / squeeze (model.py:88-95) -> [B, 63, 512]."""
+    x = F.max_pool2d(F.relu(F.conv2d(image, sd[p + "0.weight"], sd[p + "0.bias"], padding=1)), 2, 2)      # 0-2
+    x = F.max_pool2d(F.relu(F.conv2d(x, sd[p + "3.weight"], sd[p + "3.bias"], padding=1)), 2, 2)          # 3-5
+    x = F.relu(F.conv2d(x, sd[p + "6.weight"], sd[p + "6.bias"], padding=1))                              # 6-7
+    x = F.max_pool2d(F.relu(F.conv2d(x, sd[p + "8.weight"], sd[p + "8.bias"], padding=1)), (2, 1), (2, 1))   # 8-10
+    x = F.relu(_bn(F.conv2d(x, sd[p + "11.weight"], None, padding=1), sd, p + "12.", bn_mode))            # 11-13
+    x = F.relu(_bn(F.conv2d(x, sd[p + "14.weight"], None, padding=1), sd, p + "15.", bn_mode))            # 14-16
+    x = F.max_pool2d(x, (2, 1), (2, 1))                                                                   # 17
+    x = F.relu(F.conv2d(x, sd[p + "18.weight"], sd[p + "18.bias"]))                                       # 18-19  [B,512,1,63]
+    return x.permute(0, 3, 1, 2).mean(dim=3)                                                              # model.py:88-95
+
+
+def lstm_direction(x: torch.Tensor, w_ih, w_hh, b_ih, b_hh, reverse: bool) -> torch.Tensor:
+    """One direction of nn.LSTM(batch_first=True), zero initial state, gate order i, f, g, o:
+    c_t = sigmoid(f) * c_{t-1} + sigmoid(i) * tanh(g);  h_t = sigmoid(o) * tanh(c_t).   x [B,T,K] -> [B,T,H]."""
+    B, T, _ = x.shape
+    H = w_hh.shape[1]
+    pre = F.linear(x, w_ih, b_ih + b_hh)
+    h = torch.zeros(B, H, dtype=x.dtype)
+    c = torch.zeros(B, H, dtype=x.dtype)
+    out = torch.empty(B, T, H, dtype=x.dtype)
+    for t in (range(T - 1, -1, -1) if reverse else range(T)):
+        a = pre[:, t] + h @ w_hh.t()
+        i_, f_, g_, o_ = a[:, :H], a[:, H:2 * H], a[:, 2 * H:3 * H], a[:, 3 * H:]
+        c = torch.sigmoid(f_) * c + torch.sigmoid(i_) * torch.tanh(g_)
+        h = torch.sigmoid(o_) * torch.tanh(c)
+        out[:, t] = h
+    return out
+
+
+def bilstm(sd, p: str, x: torch.Tensor) -> torch.Tensor:
+    """BidirectionalLSTM.forward (sequence_modeling.py:12-22): [fwd | bwd] hidden states -> Linear(2H -> out)."""
+    f = lstm_direction(x, sd[p + "rnn.weight_ih_l0"], sd[p + "rnn.weight_hh_l0"], sd[p + "rnn.bias_ih_l0"],
+                       sd[p + "rnn.bias_hh_l0"], False)
+    b = lstm_direction(x, sd[p + "rnn.weight_ih_l0_reverse"], sd[p + "rnn.weight_hh_l0_reverse"],
+                       sd[p + "rnn.bias_ih_l0_reverse"], sd[p + "rnn.bias_hh_l0_reverse"], True)
+    return F.linear(torch.cat([f, b], dim=-1), sd[p + "linear.weight"], sd[p + "linear.bias"])
+
+
+def expert_arch(sd, i: int = 0) -> str:
+    return "crnn" if f"model.{i}.model.SequenceModeling.0.rnn.weight_ih_l0" in sd else "svtr"
+
+
 def expert_forward(sd, i: int, image, bn_mode="eval", drop_scales=None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Model.forward for the SVTR + 'None' sequence model + CTC head (modules/model.py:133-148,75-80,176-181).
+    """Model.forward with the CTC head (modules/model.py:133-148,75-80,176-181): SVTR + Linear 'None' sequence
+    model, or VGG + two BidirectionalLSTMs (picked from the state_dict keys).
 
     Returns (feature [B,T,256], predict [B,T,C_i])."""
-    vis = svtr_backbone(sd, f"model.{i}.model.FeatureExtraction.ConvNet.", image, bn_mode, drop_scales)
-    feat = F.linear(vis, sd[f"model.{i}.model.SequenceModeling.0.weight"], sd[f"model.{i}.model.SequenceModeling.0.bias"])
+    if expert_arch(sd, i) == "crnn":
+        vis = vgg_backbone(sd, f"model.{i}.model.FeatureExtraction.ConvNet.", image, bn_mode)
+        feat = bilstm(sd, f"model.{i}.model.SequenceModeling.1.", bilstm(sd, f"model.{i}.model.SequenceModeling.0.", vis))
+    else:
+        vis = svtr_backbone(sd, f"model.{i}.model.FeatureExtraction.ConvNet.", image, bn_mode, drop_scales)
+        feat = F.linear(vis, sd[f"model.{i}.model.SequenceModeling.0.weight"], sd[f"model.{i}.model.SequenceModeling.0.bias"])
     pred = F.linear(feat, sd[f"model.{i}.fc.weight"], sd[f"model.{i}.fc.bias"])
     return feat, pred
 
