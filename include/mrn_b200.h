@@ -114,6 +114,61 @@ int mrnb_svtr_experts_forward(const MrnbSvtrPack* pack, const float* image, int 
                               cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * CRNN expert recognisers (VGG + 2 x BidirectionalLSTM + CTC head), T = 63 frames.
+ * Replaces modules/feature_extraction.py:19-47 (VGG_FeatureExtractor.forward), modules/sequence_modeling.py:12-22
+ * (BidirectionalLSTM.forward, x2), modules/model.py:82-101 (Model_Extractor.forward) and :133-148 (Model.forward),
+ * called once per expert by MRNNet.forward (modules/model.py:366-368,397-399).
+ *
+ * Parameter slots are stacked over experts (leading dimension I).  Convolution weights are re-laid once at load
+ * time as [Cout, kh, kw, Cin] (kh, kw before Cin), except conv0 which keeps nn.Conv2d's layout.  LSTM slots:
+ * W_ih of both directions concatenated along the gate axis, b_ih + b_hh pre-summed.
+ */
+enum {
+  MRNB_C_CONV0_W = 0,   /* [I,64,4,3,3]     ConvNet.0.weight */
+  MRNB_C_CONV0_B,       /* [I,64] */
+  MRNB_C_CONV1_W,       /* [I,128,3,3,64]   (*) ConvNet.3.weight permuted (0,2,3,1) */
+  MRNB_C_CONV1_B,       /* [I,128] */
+  MRNB_C_CONV2_W,       /* [I,256,3,3,128]  (*) ConvNet.6 */
+  MRNB_C_CONV2_B,
+  MRNB_C_CONV3_W,       /* [I,256,3,3,256]  (*) ConvNet.8 */
+  MRNB_C_CONV3_B,
+  MRNB_C_CONV4_W,       /* [I,512,3,3,256]  (*) ConvNet.11 (bias=False) */
+  MRNB_C_BN4_W, MRNB_C_BN4_B, MRNB_C_BN4_MEAN, MRNB_C_BN4_VAR, /* [I,512] ConvNet.12.* (mean/var updated in train mode) */
+  MRNB_C_CONV5_W,       /* [I,512,3,3,512]  (*) ConvNet.14 (bias=False) */
+  MRNB_C_BN5_W, MRNB_C_BN5_B, MRNB_C_BN5_MEAN, MRNB_C_BN5_VAR, /* [I,512] ConvNet.15.* */
+  MRNB_C_CONV6_W,       /* [I,512,2,2,512]  (*) ConvNet.18 */
+  MRNB_C_CONV6_B,       /* [I,512] */
+  MRNB_C_LSTM0 = 20,    /* 2 layers x MRNB_CL_COUNT slots: SequenceModeling.0, SequenceModeling.1 */
+  MRNB_C_COUNT = 20 + 2 * 5
+};
+enum { /* per BidirectionalLSTM, Kin = 512 (layer 0) / 256 (layer 1), gate order i,f,g,o */
+  MRNB_CL_WIH = 0, /* [I,2048,Kin]   rows 0..1023 rnn.weight_ih_l0, 1024..2047 rnn.weight_ih_l0_reverse */
+  MRNB_CL_WHH,     /* [I,2,1024,256] rnn.weight_hh_l0, rnn.weight_hh_l0_reverse */
+  MRNB_CL_BIAS,    /* [I,2048]       bias_ih + bias_hh, forward then reverse */
+  MRNB_CL_LIN_W,   /* [I,256,512]    linear.weight */
+  MRNB_CL_LIN_B,   /* [I,256] */
+  MRNB_CL_COUNT
+};
+
+typedef struct MrnbCrnnPack {
+  int n_experts;
+  const float* p[MRNB_C_COUNT]; /* fp32 parameters (always required) */
+  const void* h[MRNB_C_COUNT];  /* bf16 copies of the GEMM weight slots (conv1..6, W_ih, W_hh, linear); MRNB_PREC_BF16 only */
+  const float* fc_w[MRNB_MAX_EXPERTS];  /* [C_i,256] model.{i}.fc.weight */
+  const void* fc_w16[MRNB_MAX_EXPERTS]; /* bf16 copy; MRNB_PREC_BF16 only */
+  const float* fc_b[MRNB_MAX_EXPERTS];  /* [C_i] */
+  int n_class[MRNB_MAX_EXPERTS];
+} MrnbCrnnPack;
+
+size_t mrnb_crnn_workspace_bytes(int n_experts, int B, int prec);
+
+/* image [B,4,32,256] fp32 NCHW.  bn_batch_stats / update_running as in mrnb_svtr_experts_forward.
+ * features: NULL or [B,I,63,256] fp32 (router input).  logits[i]: NULL or [B,63,ld_logits[i]] fp32 (model.{i} "predict"). */
+int mrnb_crnn_experts_forward(const MrnbCrnnPack* pack, const float* image, int B, int prec, int bn_batch_stats,
+                              int update_running, float* features, float* const* logits, const long* ld_logits,
+                              void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * DM-Router + gate head.   Replaces modules/dm_router.py:50-67 (DM_Router.forward, both gating blocks) and
  * modules/model.py:402-406 (train) / :371-377 (eval): rearrange -> channel_route -> route -> softmax / argmax.
  *

@@ -21,12 +21,29 @@ P_SEQ_W = P_SUB0 + 3 * 4
 P_SEQ_B = P_SEQ_W + 1
 P_COUNT = P_SEQ_B + 1
 ROUTER_NPARAMS = 20
+# CRNN pack slots (include/mrn_b200.h MRNB_C_*)
+(C_CONV0_W, C_CONV0_B, C_CONV1_W, C_CONV1_B, C_CONV2_W, C_CONV2_B, C_CONV3_W, C_CONV3_B, C_CONV4_W, C_BN4_W, C_BN4_B,
+ C_BN4_MEAN, C_BN4_VAR, C_CONV5_W, C_BN5_W, C_BN5_B, C_BN5_MEAN, C_BN5_VAR, C_CONV6_W, C_CONV6_B) = range(20)
+C_LSTM0 = 20
+CL_COUNT = 5
+CL_WIH, CL_WHH, CL_BIAS, CL_LIN_W, CL_LIN_B = range(5)
+C_COUNT = C_LSTM0 + 2 * CL_COUNT
 
 
 class MrnbSvtrPack(C.Structure):
     _fields_ = [("n_experts", C.c_int),
                 ("p", C.c_void_p * P_COUNT),
                 ("h", C.c_void_p * P_COUNT),
+                ("fc_w", C.c_void_p * MAX_EXPERTS),
+                ("fc_w16", C.c_void_p * MAX_EXPERTS),
+                ("fc_b", C.c_void_p * MAX_EXPERTS),
+                ("n_class", C.c_int * MAX_EXPERTS)]
+
+
+class MrnbCrnnPack(C.Structure):
+    _fields_ = [("n_experts", C.c_int),
+                ("p", C.c_void_p * C_COUNT),
+                ("h", C.c_void_p * C_COUNT),
                 ("fc_w", C.c_void_p * MAX_EXPERTS),
                 ("fc_w16", C.c_void_p * MAX_EXPERTS),
                 ("fc_b", C.c_void_p * MAX_EXPERTS),
@@ -46,6 +63,9 @@ _SIGNATURES = {
     "mrnb_svtr_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mrnb_svtr_experts_forward": (_i, [C.POINTER(MrnbSvtrPack), _vp, _i, _i, _i, _i, _i, _vp, _vp, C.POINTER(_vp),
                                        C.POINTER(_l), _vp, _sz, _vp]),
+    "mrnb_crnn_workspace_bytes": (_sz, [_i, _i, _i]),
+    "mrnb_crnn_experts_forward": (_i, [C.POINTER(MrnbCrnnPack), _vp, _i, _i, _i, _i, _vp, C.POINTER(_vp), C.POINTER(_l),
+                                       _vp, _sz, _vp]),
     "mrnb_router_param_offsets": (_l, [_i, _i, _i, C.POINTER(_l)]),
     "mrnb_router_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "mrnb_router_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

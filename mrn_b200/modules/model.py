@@ -1,8 +1,9 @@
 """MRNNet / Model / Model_Extractor with the reference's constructor arguments, methods, attribute names and
 state_dict keys (modules/model.py:17-199,314-496), computing through the CUDA library.
 
-Scope: FeatureExtraction="SVTR", SequenceModeling="None", Prediction="CTC", Transformation="None"
-(config/svtr_mrn.py).  Other backbones raise NotImplementedError -- there is no PyTorch fallback.
+Scope: Prediction="CTC", Transformation="None" with either FeatureExtraction="SVTR" /
+SequenceModeling="None" (config/svtr_mrn.py, T = 64) or FeatureExtraction="VGG" / SequenceModeling="BiLSTM"
+(config/crnn_mrn.py, T = 63).  Other stages raise NotImplementedError -- there is no PyTorch fallback.
 
 The nn.Module tree exists to own parameters under the reference's names (checkpoints load strict=True,
 il_modules/mrn.py:190,465).  Compute never runs per module:
@@ -20,15 +21,25 @@ import torch.nn as nn
 from .. import _lib as L
 from .. import ops
 from .dm_router import DM_Router
+from .crnn import BidirectionalLSTM, VGG_FeatureExtractor
 from .svtr import SVTR_FeatureExtractor
 
 
+def _arch(opt):
+    """'svtr' (SVTR / None / CTC) or 'crnn' (VGG / BiLSTM / CTC); anything else is outside the implemented path."""
+    ok_common = opt.Prediction == "CTC" and opt.Transformation in ("None", None)
+    if ok_common and opt.FeatureExtraction == "SVTR" and opt.SequenceModeling != "BiLSTM":
+        return "svtr"
+    if ok_common and opt.FeatureExtraction == "VGG" and opt.SequenceModeling == "BiLSTM":
+        return "crnn"
+    raise NotImplementedError(
+        "mrn_b200 implements the SVTR / None / CTC (config/svtr_mrn.py) and VGG / BiLSTM / CTC (config/crnn_mrn.py) "
+        "hot paths; got %s/%s/%s/%s. No PyTorch fallback is provided."
+        % (opt.Transformation, opt.FeatureExtraction, opt.SequenceModeling, opt.Prediction))
+
+
 def _require_svtr_ctc(opt):
-    if opt.FeatureExtraction != "SVTR" or opt.SequenceModeling == "BiLSTM" or opt.Prediction != "CTC" \
-            or opt.Transformation not in ("None", None):
-        raise NotImplementedError(
-            "mrn_b200 implements the SVTR / None / CTC hot path (config/svtr_mrn.py); got %s/%s/%s/%s. "
-            "No PyTorch fallback is provided." % (opt.Transformation, opt.FeatureExtraction, opt.SequenceModeling, opt.Prediction))
+    _arch(opt)
 
 
 class Model_Extractor(nn.Module):
@@ -40,9 +51,15 @@ class Model_Extractor(nn.Module):
         self.opt = opt
         self.stages = {"Trans": opt.Transformation, "Feat": opt.FeatureExtraction, "Seq": opt.SequenceModeling,
                        "Pred": opt.Prediction}
-        self.FeatureExtraction = SVTR_FeatureExtractor(opt.input_channel, opt.output_channel)
         self.FeatureExtraction_output = opt.output_channel
-        self.SequenceModeling = nn.Sequential(nn.Linear(self.FeatureExtraction_output, opt.hidden_size))
+        if _arch(opt) == "svtr":
+            self.FeatureExtraction = SVTR_FeatureExtractor(opt.input_channel, opt.output_channel)
+            self.SequenceModeling = nn.Sequential(nn.Linear(self.FeatureExtraction_output, opt.hidden_size))
+        else:
+            self.FeatureExtraction = VGG_FeatureExtractor(opt.input_channel, opt.output_channel)
+            self.SequenceModeling = nn.Sequential(
+                BidirectionalLSTM(self.FeatureExtraction_output, opt.hidden_size, opt.hidden_size),
+                BidirectionalLSTM(opt.hidden_size, opt.hidden_size, opt.hidden_size))
         self.SequenceModeling_output = opt.hidden_size
 
 
@@ -107,14 +124,15 @@ class _PackCache:
 
     def get(self, experts: List[Model], device, prec):
         # parameters only: BN running statistics are owned by the pack between checkpoints (see _sync_bn)
-        key = (prec, str(device), tuple(id(m) for m in experts),
+        arch = _arch(experts[0].opt)
+        key = (arch, prec, str(device), tuple(id(m) for m in experts),
                sum(int(p._version) for m in experts for p in m.parameters()))
         if key != self.key:
             sd = {}
             for i, m in enumerate(experts):
                 for k, v in m.state_dict().items():
                     sd[f"model.{i}.{k}"] = v
-            self.pack = ops.SvtrPack(sd, len(experts), device, prec)
+            self.pack = (ops.SvtrPack if arch == "svtr" else ops.CrnnPack)(sd, len(experts), device, prec)
             self.key = key
         return self.pack
 
@@ -132,6 +150,14 @@ def _experts_forward(experts, image, opt, train_mode, cache=None, drop_scales=No
         raise RuntimeError("mrn_b200 needs CUDA tensors: there is no CPU fallback")
     cache = cache or _solo_cache
     pack = cache.get(experts, image.device, _precision(opt))
+    if pack.arch == "crnn":
+        feats, logits = ops.crnn_experts_forward(pack, image.contiguous().float(), bn_batch_stats=train_mode,
+                                                 update_running=train_mode, want_logits=want_logits)
+        if train_mode:
+            pack.bn_dirty = True
+            if cache is _solo_cache:
+                _writeback_bn(experts, pack)
+        return feats, logits
     if chunk is None:
         chunk = int(getattr(opt, "expert_chunk", 0) or 0)
     if train_mode and drop_scales is None and getattr(opt, "drop_path", True):
@@ -161,8 +187,9 @@ def _writeback_bn(experts, pack):
     m0, v0, m1, v1 = pack.bn_running_stats()
     with torch.no_grad():
         for i, m in enumerate(experts):
-            proj = m.model.FeatureExtraction.ConvNet.patch_embed.proj
-            for bn, mean, var in ((proj[1], m0, v0), (proj[4], m1, v1)):
+            cn = m.model.FeatureExtraction.ConvNet
+            bns = (cn[12], cn[15]) if pack.arch == "crnn" else (cn.patch_embed.proj[1], cn.patch_embed.proj[4])
+            for bn, mean, var in ((bns[0], m0, v0), (bns[1], m1, v1)):
                 bn.running_mean.data = mean[i].clone()
                 bn.running_var.data = var[i].clone()
                 bn.num_batches_tracked += 1
@@ -180,7 +207,7 @@ class MRNNet(nn.Module):
         self.fc = None
         self.opt = opt
         self.task_sizes = []
-        self.patch = 64                      # SVTR (modules/model.py:324)
+        self.patch = 64 if _arch(opt) == "svtr" else 63      # modules/model.py:322-325
         self.router = "dm-router"
         self.layer_num = 1
         self.beta = 1

@@ -161,6 +161,9 @@ class SvtrPack:
     (include/mrn_b200.h: MRNB_P_* slots).  Built from a reference-format state_dict; rebuilt when experts change
     (experts are frozen during router training, il_modules/mrn.py:154-157)."""
 
+    arch = "svtr"
+    n_frames = 64
+
     def __init__(self, state_dict: Dict[str, torch.Tensor], n_experts: int, device, prec: int, prefix: str = ""):
         self.n_experts = n_experts
         self.prec = prec
@@ -277,6 +280,122 @@ def svtr_experts_forward(pack: SvtrPack, image: torch.Tensor, bn_batch_stats: bo
                                             int(update_running), _p(drop_scales), _p(feats), ptrs, lds, _p(ws),
                                             ws.numel(), _stream())
     L.check(rc, "svtr_experts_forward")
+    return feats, logits
+
+
+# ------------------------------------------------------------------------------------------------ CRNN experts
+T_FRAMES_CRNN = 63          # modules/model.py:322-323
+
+_VGG_GEMM_CONVS = ((L.C_CONV1_W, L.C_CONV1_B, 3), (L.C_CONV2_W, L.C_CONV2_B, 6), (L.C_CONV3_W, L.C_CONV3_B, 8),
+                   (L.C_CONV4_W, None, 11), (L.C_CONV5_W, None, 14), (L.C_CONV6_W, L.C_CONV6_B, 18))
+
+
+class CrnnPack:
+    """Device-resident, expert-stacked copy of the CRNN expert parameters (include/mrn_b200.h: MRNB_C_* slots):
+    VGG convolutions re-laid as [Cout, kh, kw, Cin], LSTM input weights of both directions concatenated, the two
+    LSTM biases pre-summed.  Built from a reference-format state_dict."""
+
+    arch = "crnn"
+    n_frames = T_FRAMES_CRNN
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], n_experts: int, device, prec: int, prefix: str = ""):
+        self.n_experts = n_experts
+        self.prec = prec
+        self.device = torch.device(device)
+        self.tensors: List[torch.Tensor] = []
+        self.struct = L.MrnbCrnnPack()
+        self.struct.n_experts = n_experts
+        self.n_class: List[int] = []
+        self.slot_tensors: Dict[int, torch.Tensor] = {}
+        sd = state_dict
+
+        def get(i, key):
+            return sd[f"{prefix}model.{i}.{key}"].detach().to(self.device, torch.float32)
+
+        def stack(fn):
+            return torch.stack([fn(i).contiguous() for i in range(n_experts)], 0).contiguous()
+
+        def put(slot, t, gemm_weight=False):
+            self.tensors.append(t)
+            self.slot_tensors[slot] = t
+            self.struct.p[slot] = t.data_ptr()
+            if gemm_weight and prec == L.PREC_BF16:
+                h = cast_bf16(t)
+                self.tensors.append(h)
+                self.struct.h[slot] = h.data_ptr()
+
+        cn = "model.FeatureExtraction.ConvNet."
+        put(L.C_CONV0_W, stack(lambda i: get(i, cn + "0.weight")))
+        put(L.C_CONV0_B, stack(lambda i: get(i, cn + "0.bias")))
+        for wslot, bslot, idx in _VGG_GEMM_CONVS:
+            put(wslot, stack(lambda i: get(i, cn + f"{idx}.weight").permute(0, 2, 3, 1)), gemm_weight=True)
+            if bslot is not None:
+                put(bslot, stack(lambda i: get(i, cn + f"{idx}.bias")))
+        for base, idx in ((L.C_BN4_W, 12), (L.C_BN5_W, 15)):
+            for k, nm in enumerate(("weight", "bias", "running_mean", "running_var")):
+                put(base + k, stack(lambda i: get(i, cn + f"{idx}.{nm}")))
+        for layer in range(2):
+            q = f"model.SequenceModeling.{layer}."
+            base = L.C_LSTM0 + layer * L.CL_COUNT
+            put(base + L.CL_WIH, stack(lambda i: torch.cat([get(i, q + "rnn.weight_ih_l0"),
+                                                            get(i, q + "rnn.weight_ih_l0_reverse")], 0)), gemm_weight=True)
+            put(base + L.CL_WHH, stack(lambda i: torch.stack([get(i, q + "rnn.weight_hh_l0"),
+                                                              get(i, q + "rnn.weight_hh_l0_reverse")], 0)), gemm_weight=True)
+            put(base + L.CL_BIAS, stack(lambda i: torch.cat([
+                get(i, q + "rnn.bias_ih_l0") + get(i, q + "rnn.bias_hh_l0"),
+                get(i, q + "rnn.bias_ih_l0_reverse") + get(i, q + "rnn.bias_hh_l0_reverse")], 0)))
+            put(base + L.CL_LIN_W, stack(lambda i: get(i, q + "linear.weight")), gemm_weight=True)
+            put(base + L.CL_LIN_B, stack(lambda i: get(i, q + "linear.bias")))
+        for i in range(n_experts):
+            w = get(i, "fc.weight").contiguous()
+            b = get(i, "fc.bias").contiguous()
+            self.tensors += [w, b]
+            self.struct.fc_w[i] = w.data_ptr()
+            self.struct.fc_b[i] = b.data_ptr()
+            self.struct.n_class[i] = w.shape[0]
+            self.n_class.append(int(w.shape[0]))
+            if prec == L.PREC_BF16:
+                h = cast_bf16(w)
+                self.tensors.append(h)
+                self.struct.fc_w16[i] = h.data_ptr()
+        self._ws: Optional[torch.Tensor] = None
+
+    def bn_running_stats(self):
+        """(mean4, var4, mean5, var5), each [I, 512]: updated in place by train-mode forwards."""
+        return tuple(self.slot_tensors[s] for s in (L.C_BN4_MEAN, L.C_BN4_VAR, L.C_BN5_MEAN, L.C_BN5_VAR))
+
+    def workspace(self, B, chunk=0):
+        need = int(L.load().mrnb_crnn_workspace_bytes(self.n_experts, B, self.prec))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+
+def crnn_experts_forward(pack: CrnnPack, image: torch.Tensor, bn_batch_stats: bool = False, update_running: bool = False,
+                         want_logits: bool = True):
+    """Runs every CRNN expert on `image` [B,4,32,256].  Returns (features [B,I,63,256], [logits_i [B,63,C_i] views])."""
+    _chk_f32(image)
+    B = image.shape[0]
+    I = pack.n_experts
+    T = T_FRAMES_CRNN
+    feats = torch.empty(B, I, T, D_FEAT, device=image.device, dtype=torch.float32)
+    ptrs = (C.c_void_p * I)()
+    lds = (C.c_long * I)()
+    logits = []
+    for i in range(I):
+        ld = round_up(pack.n_class[i], 4)
+        lds[i] = ld
+        if want_logits:
+            buf = torch.empty(B, T, ld, device=image.device, dtype=torch.float32)
+            ptrs[i] = buf.data_ptr()
+            logits.append(buf[:, :, :pack.n_class[i]])
+        else:
+            ptrs[i] = None
+            logits.append(None)
+    ws = pack.workspace(B)
+    rc = L.load().mrnb_crnn_experts_forward(C.byref(pack.struct), _p(image), B, pack.prec, int(bn_batch_stats),
+                                            int(update_running), _p(feats), ptrs, lds, _p(ws), ws.numel(), _stream())
+    L.check(rc, "crnn_experts_forward")
     return feats, logits
 
 

@@ -80,6 +80,22 @@ def test_module_tree_keeps_the_reference_state_dict_contract():
     assert float(fresh.model[0].model.FeatureExtraction.ConvNet.blocks1[0].norm1.bias.detach().mean()) == 1.0
 
 
+def test_crnn_module_tree_keeps_the_reference_state_dict_contract():
+    from mrn_b200.modules.model import MRNNet
+    cc = (37, 61)
+    opt = make_opt(FeatureExtraction="VGG", SequenceModeling="BiLSTM")
+    net = MRNNet(opt)
+    for c in cc:
+        net.update_fc(opt.hidden_size, c)
+        net.build_prediction(opt, c)
+    assert net.patch == 63 and net.route.weight.shape == (1, 63)       # modules/model.py:322-323
+    want = synth.crnn_mrn_shapes(cc)
+    got = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert list(got) == list(want) and got == {k: tuple(s) for k, s in want.items()}
+    res = net.load_state_dict(synth.synth_state_dict(cc, 3, arch="crnn"), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+
+
 def test_router_arena_views_share_storage():
     from mrn_b200.modules.model import MRNNet
     from mrn_b200 import ops
@@ -105,7 +121,9 @@ def test_no_cpu_fallback_and_unsupported_configs_fail_loudly():
     with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
         net(torch.zeros(1, 4, 32, 256), True, None, True)
     with pytest.raises(NotImplementedError):
-        MRNNet(make_opt(FeatureExtraction="VGG", SequenceModeling="BiLSTM"))
+        MRNNet(make_opt(FeatureExtraction="ResNet", SequenceModeling="BiLSTM"))
+    with pytest.raises(NotImplementedError):
+        MRNNet(make_opt(Transformation="TPS"))
     with pytest.raises(NotImplementedError):
         Model(make_opt(Prediction="Attn"))
     from mrn_b200.il_modules.mrn import MRN
