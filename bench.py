@@ -45,13 +45,16 @@ def parse():
     ap.add_argument("--chunk", type=int, default=0, help="samples per expert-forward chunk (0 = whole batch)")
     ap.add_argument("--cpu-sample", type=int, default=32, help="samples per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--arch", default="svtr", choices=["svtr", "crnn"],
+                    help="expert recogniser: svtr = headline (BASELINE.json configs[3-4]); crnn = VGG+BiLSTM (configs[1])")
     ap.add_argument("--mode", default="train", choices=["train", "infer"],
                     help="train: router-training step (the BASELINE metric); infer: hard-routed forward + greedy decode (cfg 5)")
     return ap.parse_args()
 
 
-def make_opt(precision, chunk):
-    return argparse.Namespace(Transformation="None", FeatureExtraction="SVTR", SequenceModeling="None", Prediction="CTC",
+def make_opt(precision, chunk, arch="svtr"):
+    return argparse.Namespace(Transformation="None", FeatureExtraction="SVTR" if arch == "svtr" else "VGG",
+                              SequenceModeling="None" if arch == "svtr" else "BiLSTM", Prediction="CTC",
                               num_fiducial=20, input_channel=4, output_channel=512, hidden_size=256, imgH=32, imgW=256,
                               batch_max_length=25, lr=5e-4, num_iter=10000, grad_clip=5, exp_name="bench",
                               precision=precision, drop_path=True, expert_chunk=chunk,
@@ -110,15 +113,15 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_stage1(sample, steps, warmup):
+def cpu_stage1(sample, steps, warmup, arch="svtr"):
     """The reference algorithm's CPU path (oracle port, fp32, all host threads) on a bounded sample of the workload."""
     from oracle import mrn_oracle as O
     from mrn_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = synth.synth_state_dict(CLASS_COUNTS, 111)
+    sd = synth.synth_state_dict(CLASS_COUNTS, 111, arch=arch)
     img, tgt, lens, dom = synth.synth_batch(sample, CLASS_COUNTS, 111)
-    drop = synth.synth_drop_scales(6, sample, O.svtr_drop_path_rates(), 111)
+    drop = synth.synth_drop_scales(6, sample, O.svtr_drop_path_rates(), 111) if arch == "svtr" else None
     state = dict(step=0, m={}, v={})
     for _ in range(warmup):
         O.stage1_step_cpu(sd, 6, state, img, tgt, lens, dom, drop_scales=drop)
@@ -134,13 +137,13 @@ def run_reference(args):
     if rank != 0:
         return
     sample = args.cpu_sample
-    v, ms, cores = cpu_stage1(sample, max(1, args.steps), max(0, args.warmup))
+    v, ms, cores = cpu_stage1(sample, max(1, args.steps), max(0, args.warmup), args.arch)
     desc = "%d-sample router-training step per iteration (same config, B reduced from 256), fp32, %d threads" % (sample, cores)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": "samples/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC.replace("SVTR", args.arch.upper()), "value": round(v, 3), "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 2), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SVTR-MRN 6-expert stage-1 (router-training) step, union charset 5153, 32x256x4 crops",
+        "config": {"workload": "%s-MRN 6-expert stage-1 (router-training) step, union charset 5153, 32x256x4 crops" % args.arch.upper(),
                    "per_step_samples": sample, "parallelism": "cpu"},
         "cpu_baseline": {"value": round(v, 3), "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": round(v, 3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -169,8 +172,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     B = args.batch
-    opt = make_opt(args.precision, args.chunk)
-    sd = synth.synth_state_dict(CLASS_COUNTS, 111)
+    opt = make_opt(args.precision, args.chunk, args.arch)
+    sd = synth.synth_state_dict(CLASS_COUNTS, 111, arch=args.arch)
+    T = 64 if args.arch == "svtr" else 63
     net = MRNNet(opt)
     for c in CLASS_COUNTS:
         net.update_fc(opt.hidden_size, c)
@@ -290,18 +294,19 @@ def run_ours(args):
     ctc_router_ms = sum(fams.get(k, {}).get("ms_per_step", 0.0) for k in ("sgemm_kernel", "tc_gemm2_kernel", "router_elementwise",
                                                                           "combine_row_kernel", "ctc_lattice_kernel"))
     out = {
-        "metric": METRIC if not infer else "MRN-SVTR 6-expert inference + greedy decode samples/s", "value": round(value, 2),
+        "metric": (METRIC if not infer else "MRN-SVTR 6-expert inference + greedy decode samples/s").replace("SVTR", args.arch.upper()),
+        "value": round(value, 2),
         "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": "SVTR-MRN 6-expert stage-1 (router-training) step, B=%d/GPU, union charset 5153, 32x256x4 crops, "
-                               "experts frozen in train mode (BN batch stats + DropPath)" % B,
+        "config": {"workload": "%s-MRN 6-expert stage-1 (router-training) step, B=%d/GPU, union charset 5153, 32x256x4 crops, "
+                               "experts frozen in train mode (BN batch stats%s)" % (args.arch.upper(), B, " + DropPath" if args.arch == "svtr" else ""),
                    "global_batch": B * world, "parallelism": "dp%d" % world, "expert_chunk": args.chunk,
                    "l2": "4 rotating input batches; >1 GB of activations streamed per step (>> 126 MB L2), no explicit flush",
                    "router_precision": "bf16 operands / fp32 accumulate (tcgen05)" if args.precision == "bf16" else "fp32",
                    "expert_precision": args.precision},
         "e2e": {"value": round(e2e_value, 2), "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": 8 if not infer else B * 64 * 4 + B * 8,
+                "d2h_bytes_per_step": 8 if not infer else B * T * 4 + B * 8,
                 "ms_per_step": round(e2e_ms / args.steps, 3)},
         "gpu_launches": int(launches),
         "gpu_launches_per_step": int(launches // args.steps),
@@ -312,9 +317,10 @@ def run_ours(args):
         "loss_clf": float(last[0]), "taski_loss": float(last[1]),
     }
     if infer:
-        out["config"]["workload"] = ("SVTR-MRN 6-expert hard-routed inference + device greedy decode, B=%d/GPU, union charset 5153" % B)
+        out["config"]["workload"] = ("%s-MRN 6-expert hard-routed inference + device greedy decode, B=%d/GPU, union charset 5153"
+                                     % (args.arch.upper(), B))
     if world == 1 and not args.no_cpu_baseline and not infer:
-        v, ms, cores = cpu_stage1(args.cpu_sample, 2, 1)
+        v, ms, cores = cpu_stage1(args.cpu_sample, 2, 1, args.arch)
         out["cpu_baseline"] = {"value": round(v, 3), "unit": "samples/s", "cores": cores, "kind": "port",
                                "sample": "2 timed router-training steps of %d samples (same config, batch reduced from 256), "
                                          "oracle port of the reference algorithm, fp32, %d threads" % (args.cpu_sample, cores)}

@@ -136,19 +136,21 @@ __global__ void mul2_kernel(const float* __restrict__ a, const float* __restrict
 __global__ void __launch_bounds__(RD)
 lnT_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma /*[T]*/, const float* __restrict__ beta,
                float* __restrict__ gn, __nv_bfloat16* __restrict__ gn16, float* __restrict__ stats /*[B*I, D, 2]*/, int T,
-               float eps) {
+               int Tv, float eps) {
+  // T = stored frames per (b,i); Tv <= T = valid frames (the tensor-core engine pads T = 63 to 64): padded frames
+  // are excluded from the statistics and normalise to 0
   const long bi = blockIdx.x;
   const int c = threadIdx.x;
   const float* yp = y + bi * T * RD + c;
   float s = 0.f;
-  for (int t = 0; t < T; ++t) s += yp[(long)t * RD];
-  const float mean = s / T;
+  for (int t = 0; t < Tv; ++t) s += yp[(long)t * RD];
+  const float mean = s / Tv;
   float q = 0.f;
-  for (int t = 0; t < T; ++t) { const float d = yp[(long)t * RD] - mean; q = fmaf(d, d, q); }
-  const float rstd = rsqrtf(q / T + eps);
+  for (int t = 0; t < Tv; ++t) { const float d = yp[(long)t * RD] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(q / Tv + eps);
   stats[(bi * RD + c) * 2] = mean; stats[(bi * RD + c) * 2 + 1] = rstd;
   for (int t = 0; t < T; ++t) {
-    const float o = (yp[(long)t * RD] - mean) * rstd * gamma[t] + beta[t];
+    const float o = t < Tv ? (yp[(long)t * RD] - mean) * rstd * gamma[t] + beta[t] : 0.f;
     if (gn) gn[bi * T * RD + (long)t * RD + c] = o;
     if (gn16) gn16[bi * T * RD + (long)t * RD + c] = __float2bfloat16_rn(o);
   }
@@ -158,7 +160,7 @@ lnT_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma /*[T
 __global__ void __launch_bounds__(RD)
 lnT_bwd_kernel(const float* __restrict__ y, const float* __restrict__ stats, const float* __restrict__ gamma,
                const float* __restrict__ dgn, float* __restrict__ dy /* accumulated */, __nv_bfloat16* __restrict__ dy16,
-               float* __restrict__ dgamma, float* __restrict__ dbeta, int T) {
+               float* __restrict__ dgamma, float* __restrict__ dbeta, int T, int Tv) {
   extern __shared__ float sh[];        // [T][2] block partials
   const long bi = blockIdx.x;
   const int c = threadIdx.x, lane = c & 31;
@@ -168,19 +170,19 @@ lnT_bwd_kernel(const float* __restrict__ y, const float* __restrict__ stats, con
   const float* yp = y + bi * T * RD + c;
   const float* dp = dgn + bi * T * RD + c;
   float m1 = 0.f, m2 = 0.f;
-  for (int t = 0; t < T; ++t) {
+  for (int t = 0; t < Tv; ++t) {
     const float xh = (yp[(long)t * RD] - mean) * rstd, d = dp[(long)t * RD];
     const float dxh = d * gamma[t];
     m1 += dxh; m2 = fmaf(dxh, xh, m2);
     const float a = warp_sum(d * xh), b2 = warp_sum(d);
     if (lane == 0) { atomicAdd(&sh[t * 2], a); atomicAdd(&sh[t * 2 + 1], b2); }
   }
-  m1 /= T; m2 /= T;
+  m1 /= Tv; m2 /= Tv;
   float* op = dy + bi * T * RD + c;
   for (int t = 0; t < T; ++t) {
     const float xh = (yp[(long)t * RD] - mean) * rstd;
     const float dxh = dp[(long)t * RD] * gamma[t];
-    const float o = op[(long)t * RD] + rstd * (dxh - m1 - xh * m2);
+    const float o = op[(long)t * RD] + (t < Tv ? rstd * (dxh - m1 - xh * m2) : 0.f);
     op[(long)t * RD] = o;
     if (dy16) dy16[bi * T * RD + (long)t * RD + c] = __float2bfloat16_rn(o);
   }
@@ -512,8 +514,10 @@ struct Dims {
   int B, I, T, D;
   long M, IT, ID, TD, ITD;
   bool tc;              // tensor-core (bf16 operand) engine
-  Dims(int b, int i, int t, int d, bool tc_) : B(b), I(i), T(t), D(d), M((long)b * i * t), IT((long)i * t), ID((long)i * d),
-                                               TD((long)t * d), ITD((long)i * t * d), tc(tc_) {}
+  int Tv;               // valid frames (<= T): T = 63 is carried padded to 64 by the tensor-core engine
+  Dims(int b, int i, int t, int d, bool tc_, int tv = 0) : B(b), I(i), T(t), D(d), M((long)b * i * t), IT((long)i * t),
+                                                           ID((long)i * d), TD((long)t * d), ITD((long)i * t * d), tc(tc_),
+                                                           Tv(tv > 0 ? tv : t) {}
 };
 
 // ---- TMA views of the [B,I,T,D] activation tensors (bf16) --------------------------------------------------
@@ -663,7 +667,7 @@ int router_forward(const float* P, const float* x, const Dims& d, float* out_use
   {
     MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
     lnT_fwd_kernel<<<B * I, RD, 0, st>>>(w.y, P + off[R_CN_W], P + off[R_CN_B], tc ? nullptr : w.gn, tc ? w.gn16 : nullptr,
-                                         w.statsT, T, 1e-5f);
+                                         w.statsT, T, d.Tv, 1e-5f);
     MRNB_CHECK_LAUNCH("lnT_fwd_kernel");
   }
   // g2[(b,t),(i,c)] = sum_(i',c') gn[(b,t),(i',c')] Wc[(i,c),(i',c')] + bc   (channel mixing over k = i*D+c)
@@ -762,7 +766,7 @@ int dm_router_backward_core(const float* P, const float* x, const Dims& d, float
   {  // gn = LN_T(y)
     MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
     lnT_bwd_kernel<<<B * I, RD, 2 * T * sizeof(float), st>>>(w.y, w.statsT, P + off[R_CN_W], w.dgn, w.dy, tc ? w.dy16 : nullptr,
-                                                              G + off[R_CN_W], G + off[R_CN_B], T);
+                                                              G + off[R_CN_W], G + off[R_CN_B], T, d.Tv);
     MRNB_CHECK_LAUNCH("lnT_bwd_kernel");
   }
   // y = g1 W2^T + b2 + x
@@ -846,27 +850,133 @@ extern "C" long mrnb_router_param_offsets(int n_experts, int T, int D, long* off
   return n;
 }
 
-extern "C" size_t mrnb_router_workspace_bytes(int B, int n_experts, int T, int D, int with_backward) {
-  return carve(nullptr, B, n_experts, T, D, with_backward != 0).bytes;
-}
-
 #define ROUTER_ARGCHECK(name)                                                                                   \
   MRNB_CHECK_ARG(params && x && workspace && B > 0 && T > 0, name ": null/empty argument");                      \
   MRNB_CHECK_ARG(n_experts >= 1 && n_experts <= MRNB_MAX_EXPERTS, name ": n_experts %d out of range", n_experts); \
   MRNB_CHECK_ARG(D == RD, name ": only D == 256 (opt.hidden_size) is supported, got %d", D);                     \
   MRNB_CHECK_ARG(prec == MRNB_PREC_FP32 || prec == MRNB_PREC_BF16, name ": unknown precision %d", prec);
 
-// the tensor-core engine tiles rows (b,t) as 2 samples x 64 frames: SVTR's T = 64 (modules/model.py:324)
-static inline bool use_tc(int prec, int T) { return prec == MRNB_PREC_BF16 && T == 64; }
+// The tensor-core engine tiles rows (b,t) as 2 samples x 64 frames: SVTR's T = 64 (modules/model.py:324) runs as is;
+// CRNN's T = 63 (:322-323) runs PADDED to 64 frames: the activations get a zero frame, the T-dependent parameters
+// (route.weight, spatial_gating.proj.{weight,bias}, channel_gating.norm.{weight,bias}) get zero rows / columns, the
+// LayerNorm over frames masks the pad (Dims::Tv), and the gradient arena is un-padded at the end.  With those zeros the
+// pad frame contributes exactly nothing to any valid output or gradient.
+static inline bool use_tc(int prec, int T) { return prec == MRNB_PREC_BF16 && T <= 64 && T >= 32; }
+static inline int padded_T(int prec, int T) { return use_tc(prec, T) ? 64 : T; }
+
+namespace {
+
+struct RepackTable { long off[MRNB_ROUTER_NPARAMS + 1]; long offp[MRNB_ROUTER_NPARAMS + 1]; long sz[MRNB_ROUTER_NPARAMS]; };
+
+// unpadded arena index i  <->  padded arena index; to_padded: dst[pad(i)] = src[i] (dst pre-zeroed), else dst[i] = src[pad(i)]
+__global__ void repack_arena_kernel(const float* __restrict__ src, float* __restrict__ dst, RepackTable tb, int I, int T,
+                                    int Tp, long n, int to_padded) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int k = 0;
+  while (k + 1 < MRNB_ROUTER_NPARAMS && i >= tb.off[k + 1]) ++k;
+  const long j = i - tb.off[k];
+  if (j >= tb.sz[k]) { if (!to_padded) dst[i] = 0.f; return; }
+  long jp = j;
+  if (k == R_SP_W) {
+    const long IT = (long)I * T, ITp = (long)I * Tp;
+    const long r = j / IT, c = j % IT;
+    jp = ((r / T) * Tp + r % T) * ITp + (c / T) * Tp + c % T;
+  } else if (k == R_SP_B) {
+    jp = (j / T) * Tp + j % T;
+  }
+  if (to_padded) dst[tb.offp[k] + jp] = src[i];
+  else dst[i] = src[tb.offp[k] + jp];
+}
+
+// [B*I, T, D] <-> [B*I, Tp, D] (zero pad frame), one float4 per thread over the padded index space
+__global__ void pad_frames_kernel(const float* __restrict__ src, float* __restrict__ dst, int T, int Tp, long total4, int to_padded) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int c4 = (int)(i % (RD / 4));
+  const long r = i / (RD / 4);
+  const int t = (int)(r % Tp);
+  const long bi = r / Tp;
+  if (to_padded) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < T) v = reinterpret_cast<const float4*>(src)[(bi * T + t) * (RD / 4) + c4];
+    reinterpret_cast<float4*>(dst)[i] = v;
+  } else if (t < T) {
+    reinterpret_cast<float4*>(dst)[(bi * T + t) * (RD / 4) + c4] = reinterpret_cast<const float4*>(src)[i];
+  }
+}
+
+RepackTable make_table(int I, int T, int Tp, int D) {
+  RepackTable tb{};
+  router_offsets(I, T, D, tb.off);
+  router_offsets(I, Tp, D, tb.offp);
+  const long sz[MRNB_ROUTER_NPARAMS] = {T, 1, (long)I * I * D, I, D, D, 2L * D * D, 2L * D, D, D,
+                                        (long)I * T * I * T, (long)I * T, T, T, (long)I * D * I * D, (long)I * D,
+                                        (long)D * D, D, (long)D * D, D};
+  for (int k = 0; k < MRNB_ROUTER_NPARAMS; ++k) tb.sz[k] = sz[k];
+  return tb;
+}
+
+// workspace tail of the padded mode: padded input, padded parameters, padded gradients
+struct PadWs { float *xp, *Pp, *Gp; size_t bytes; };
+PadWs carve_pad(char* base, size_t start, int B, int I, int Tp, int D) {
+  PadWs p{};
+  size_t o = al(start);
+  long offp[MRNB_ROUTER_NPARAMS + 1];
+  const size_t np = (size_t)router_offsets(I, Tp, D, offp);
+  auto take = [&](size_t n) { float* q = base ? (float*)(base + o) : nullptr; o = al(o + n * 4); return q; };
+  p.xp = take((size_t)B * I * Tp * D); p.Pp = take(np); p.Gp = take(np);
+  p.bytes = o + 256;
+  return p;
+}
+
+int pad_inputs(const float* params, const float* x, int B, int I, int T, int Tp, int D, const PadWs& pw, cudaStream_t st) {
+  MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+  const RepackTable tb = make_table(I, T, Tp, D);
+  cudaMemsetAsync(pw.Pp, 0, (size_t)tb.offp[MRNB_ROUTER_NPARAMS] * sizeof(float), st);
+  const long n = tb.off[MRNB_ROUTER_NPARAMS];
+  LAUNCH_EW(repack_arena_kernel, n, params, pw.Pp, tb, I, T, Tp, n, 1);
+  const long total4 = (long)B * I * Tp * D / 4;
+  LAUNCH_EW(pad_frames_kernel, total4, x, pw.xp, T, Tp, total4, 1);
+  return MRNB_OK;
+}
+
+}  // namespace
+
+extern "C" size_t mrnb_router_workspace_bytes(int B, int n_experts, int T, int D, int with_backward) {
+  const size_t plain = carve(nullptr, B, n_experts, T, D, with_backward != 0).bytes;
+  if (T == padded_T(MRNB_PREC_BF16, T)) return plain;
+  const int Tp = padded_T(MRNB_PREC_BF16, T);
+  const size_t inner = carve(nullptr, B, n_experts, Tp, D, true).bytes;   // the padded tail always sits behind the full carve
+  const size_t padded = carve_pad(nullptr, inner, B, n_experts, Tp, D).bytes;
+  return plain > padded ? plain : padded;
+}
 
 extern "C" int mrnb_router_forward(const float* params, const float* x, int B, int n_experts, int T, int D, int prec,
                                    float* out, float* scores, float* gate, int* index, void* workspace,
                                    size_t workspace_bytes, cudaStream_t stream) {
   ROUTER_ARGCHECK("router_forward");
-  RouterWs w = carve((char*)workspace, B, n_experts, T, D, false);
-  MRNB_CHECK_ARG(workspace_bytes >= w.bytes, "router_forward: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
-  Dims d(B, n_experts, T, D, use_tc(prec, T));
-  return router_forward(params, x, d, out, scores, gate, index, w, stream);
+  const int Tp = padded_T(prec, T);
+  RouterWs w = carve((char*)workspace, B, n_experts, Tp, D, false);
+  if (Tp == T) {
+    MRNB_CHECK_ARG(workspace_bytes >= w.bytes, "router_forward: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+    Dims d(B, n_experts, T, D, use_tc(prec, T));
+    return router_forward(params, x, d, out, scores, gate, index, w, stream);
+  }
+  // padded tensor-core mode (the padded tail sits behind the backward-sized carve so forward and backward agree)
+  const size_t inner = carve(nullptr, B, n_experts, Tp, D, true).bytes;
+  PadWs pw = carve_pad((char*)workspace, inner, B, n_experts, Tp, D);
+  MRNB_CHECK_ARG(workspace_bytes >= pw.bytes, "router_forward: workspace too small (%zu < %zu)", workspace_bytes, pw.bytes);
+  MRNB_TRY(pad_inputs(params, x, B, n_experts, T, Tp, D, pw, stream));
+  Dims d(B, n_experts, Tp, D, true, T);
+  MRNB_TRY(router_forward(pw.Pp, pw.xp, d, nullptr, scores, gate, index, w, stream));
+  if (out) {
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, stream);
+    cudaStream_t st = stream;
+    const long total4 = (long)B * n_experts * Tp * D / 4;
+    LAUNCH_EW(pad_frames_kernel, total4, w.out, out, T, Tp, total4, 0);
+  }
+  return MRNB_OK;
 }
 
 extern "C" int mrnb_router_backward(const float* params, const float* x, const float* gate, const float* dgate_ctc,
@@ -874,11 +984,24 @@ extern "C" int mrnb_router_backward(const float* params, const float* x, const f
                                     float* taski_loss, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   ROUTER_ARGCHECK("router_backward");
   MRNB_CHECK_ARG(gate && domain && grads && taski_loss, "router_backward: null argument");
-  RouterWs w = carve((char*)workspace, B, n_experts, T, D, true);
-  MRNB_CHECK_ARG(workspace_bytes >= w.bytes, "router_backward: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+  const int Tu = T;                                  // caller's frame count
+  const int Tp = padded_T(prec, T);
+  const bool padded = Tp != T;
+  RouterWs w = carve((char*)workspace, B, n_experts, Tp, D, true);
+  PadWs pw{};
+  if (padded) {
+    pw = carve_pad((char*)workspace, w.bytes, B, n_experts, Tp, D);
+    MRNB_CHECK_ARG(workspace_bytes >= pw.bytes, "router_backward: workspace too small (%zu < %zu)", workspace_bytes, pw.bytes);
+    params = pw.Pp; x = pw.xp;                       // written by mrnb_router_forward on the same workspace
+  } else {
+    MRNB_CHECK_ARG(workspace_bytes >= w.bytes, "router_backward: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+  }
+  float* user_grads = grads;
+  if (padded) grads = pw.Gp;
+  T = Tp;
   const int I = n_experts;
   cudaStream_t st = stream;
-  Dims d(B, I, T, D, use_tc(prec, T));
+  Dims d(B, I, T, D, use_tc(prec, Tu), Tu);
   long off[MRNB_ROUTER_NPARAMS + 1];
   const long nparam = router_offsets(I, T, D, off);
   const long ID = d.ID, TD = d.TD, ITD = d.ITD;
@@ -902,7 +1025,14 @@ extern "C" int mrnb_router_backward(const float* params, const float* x, const f
     const long total4 = d.M * D / 4;
     LAUNCH_EW(dout_kernel, total4, w.ds, params + off[R_CR_W], I, T, total4, w.dout, d.tc ? w.dout16 : nullptr);
   }
-  return dm_router_backward_core(params, x, d, grads, nullptr, w, st);
+  MRNB_TRY(dm_router_backward_core(params, x, d, grads, nullptr, w, st));
+  if (padded) {
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    const RepackTable tb = make_table(I, Tu, Tp, D);
+    const long n = tb.off[MRNB_ROUTER_NPARAMS];
+    LAUNCH_EW(repack_arena_kernel, n, pw.Gp, user_grads, tb, I, Tu, Tp, n, 0);
+  }
+  return MRNB_OK;
 }
 
 extern "C" int mrnb_dm_router_backward(const float* params, const float* x, const float* d_out, int B, int n_experts,
@@ -910,14 +1040,40 @@ extern "C" int mrnb_dm_router_backward(const float* params, const float* x, cons
                                        size_t workspace_bytes, cudaStream_t stream) {
   ROUTER_ARGCHECK("dm_router_backward");
   MRNB_CHECK_ARG(d_out && grads, "dm_router_backward: null argument");
-  RouterWs w = carve((char*)workspace, B, n_experts, T, D, true);
-  MRNB_CHECK_ARG(workspace_bytes >= w.bytes, "dm_router_backward: workspace too small");
-  Dims d(B, n_experts, T, D, use_tc(prec, T));
-  long off[MRNB_ROUTER_NPARAMS + 1];
-  const long nparam = router_offsets(n_experts, T, D, off);
+  const int Tp = padded_T(prec, T);
+  const bool padded = Tp != T;
+  RouterWs w = carve((char*)workspace, B, n_experts, Tp, D, true);
   cudaStream_t st = stream;
-  cudaMemsetAsync(grads, 0, nparam * sizeof(float), st);
-  cudaMemcpyAsync(w.dout, d_out, (size_t)d.M * D * sizeof(float), cudaMemcpyDeviceToDevice, st);
-  if (d.tc) LAUNCH_EW(cast16_kernel, d.M * D, d_out, w.dout16, d.M * D);
-  return dm_router_backward_core(params, x, d, grads, dx, w, st);
+  if (!padded) {
+    MRNB_CHECK_ARG(workspace_bytes >= w.bytes, "dm_router_backward: workspace too small");
+    Dims d(B, n_experts, T, D, use_tc(prec, T));
+    long off[MRNB_ROUTER_NPARAMS + 1];
+    const long nparam = router_offsets(n_experts, T, D, off);
+    cudaMemsetAsync(grads, 0, nparam * sizeof(float), st);
+    cudaMemcpyAsync(w.dout, d_out, (size_t)d.M * D * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (d.tc) LAUNCH_EW(cast16_kernel, d.M * D, d_out, w.dout16, d.M * D);
+    return dm_router_backward_core(params, x, d, grads, dx, w, st);
+  }
+  PadWs pw = carve_pad((char*)workspace, w.bytes, B, n_experts, Tp, D);
+  MRNB_CHECK_ARG(workspace_bytes >= pw.bytes, "dm_router_backward: workspace too small");
+  Dims d(B, n_experts, Tp, D, true, T);
+  long offp[MRNB_ROUTER_NPARAMS + 1];
+  const long np = router_offsets(n_experts, Tp, D, offp);
+  cudaMemsetAsync(pw.Gp, 0, np * sizeof(float), st);
+  const long total4 = d.M * D / 4;
+  {
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    LAUNCH_EW(pad_frames_kernel, total4, d_out, w.dout, T, Tp, total4, 1);
+    LAUNCH_EW(cast16_kernel, d.M * D, w.dout, w.dout16, d.M * D);
+  }
+  float* dxp = dx ? w.dg2 : nullptr;        // padded dx: dg2 is dead by the time the core's last kernel writes dx
+  MRNB_TRY(dm_router_backward_core(pw.Pp, pw.xp, d, pw.Gp, dxp, w, st));
+  {
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    const RepackTable tb = make_table(n_experts, T, Tp, D);
+    const long n = tb.off[MRNB_ROUTER_NPARAMS];
+    LAUNCH_EW(repack_arena_kernel, n, pw.Gp, grads, tb, n_experts, T, Tp, n, 0);
+    if (dx) LAUNCH_EW(pad_frames_kernel, total4, dxp, dx, T, Tp, total4, 0);
+  }
+  return MRNB_OK;
 }

@@ -199,3 +199,30 @@ def test_crnn_baseline_config0_two_tasks_batch64():
             ties += 1
     print("configs[0]: decoded sequences differing from the oracle: %d of %d" % (ties, B))
     assert ties == 0
+
+
+def test_crnn_stage1_step_bf16_tensor_core_router():
+    """bf16 mode runs the T = 63 router on tcgen05 through the 64-frame padded problem; the step must stay within the
+    bf16 budget of the reference's loss and router gradients (compared on the caller's un-padded arena)."""
+    from mrn_b200 import ops
+    from mrn_b200.il_modules.mrn import MRN, RankLocal, FusedAdam
+    g, cc, B, seed, sd, img, tgt, lens, dom = _case("crnn_mrn_i3_b2")
+    net, opt = build_net(cc, sd, precision="bf16")
+    learner = MRN(opt)
+    learner.model = RankLocal(net)
+    learner.model.eval()
+    learner.optimizer = FusedAdam(net, 5e-4, 20000, grad_clip=5, schedule="const")
+    loss_clf, taski = learner.train_step_stage1(img.cuda(), tgt.cuda(), lens.cuda(), dom.cuda())
+    assert abs(float(loss_clf) - float(g["loss_clf"])) / abs(float(g["loss_clf"])) < 2e-2
+    assert abs(float(taski) - float(g["taski_loss"])) < 2e-2
+    n, off = ops.router_param_offsets(len(cc), 63)
+    grads = net.router_grad_arena().cpu()
+    tn = float(g["grad_total_norm"])
+    assert abs(float(learner.optimizer.norm) - tn) / tn < 5e-2
+    shapes = synth.router_shapes(len(cc), T=63)
+    for k, pname in enumerate(ops.ROUTER_PARAM_NAMES):
+        numel = int(np.prod(shapes[pname]))
+        got = grads[off[k]:off[k] + numel]
+        ref = g["grad." + pname]
+        scale = max(float(np.abs(ref).max()), 1e-3 * tn)
+        assert np.abs(gview(got, g) - ref.reshape(-1)).max() / scale < 8e-2, pname

@@ -259,6 +259,50 @@ def test_dm_router_tensor_core_engine(name):
         assert rel_err(gview(got, g), g["grad." + pname[len("dm_router.0."):]]) < 3e-2, pname
 
 
+@pytest.mark.parametrize("prec_name", ["fp32", "bf16"])
+@pytest.mark.parametrize("I,B", [(2, 3), (6, 2)])
+def test_dm_router_63_frames(prec_name, I, B):
+    """CRNN's T = 63 (modules/model.py:322-323).  fp32: the CUDA-core engine on the unpadded problem; bf16: the tcgen05
+    engine on the problem padded to 64 frames (zero frame, zero weight rows / columns, masked LayerNorm over frames)
+    -- both against the fp64 autograd of the oracle, incl. the un-padded gradient arena and the input gradient."""
+    ops = _ops()
+    from mrn_b200 import _lib as L
+    T, seed = 63, 40 + I
+    prec = L.PREC_BF16 if prec_name == "bf16" else L.PREC_FP32
+    tol_o, tol_g = (2e-2, 3e-2) if prec_name == "bf16" else (1e-4, 5e-4)
+    shapes = synth.router_shapes(I, T=T)
+    sd = {k: synth.synth_tensor(seed, k, s) for k, s in shapes.items()}
+    x = synth.randn(seed, "router_x", (B, I, T, 256))
+    dy = synth.randn(seed, "router_dy", (B, I, T, 256))
+    sdd = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    xd = x.double().requires_grad_(True)
+    y = O.dm_router(sdd, xd)
+    (y * dy.double()).sum().backward()
+    r_ref = O.gate_scores({k: v.detach() for k, v in sdd.items()}, y.detach())
+    n, off = ops.router_param_offsets(I, T)
+    arena = torch.zeros(n, dtype=torch.float32)
+    for k, name in enumerate(ops.ROUTER_PARAM_NAMES):
+        arena[off[k]:off[k] + sd[name].numel()] = sd[name].reshape(-1)
+    arena = arena.cuda()
+    ws = ops.RouterWorkspace()
+    out, scores, gate, index = ops.router_forward(arena, dev(x), ws, with_backward=True, prec=prec)
+    assert out.shape == (B, I, T, 256)
+    assert rel_err(out.cpu().numpy(), y.detach().numpy()) < tol_o
+    assert rel_err(scores.cpu().numpy(), r_ref.numpy()) < tol_o
+    assert np.abs(gate.cpu().numpy() - torch.softmax(r_ref, -1).numpy()).max() < tol_o
+    grads = torch.full_like(arena, float("nan"))
+    dx = ops.dm_router_backward(arena, dev(x), dev(dy), grads, ws, want_dx=True, prec=prec)
+    assert dx.shape == (B, I, T, 256)
+    assert rel_err(dx.cpu().numpy(), xd.grad.numpy()) < tol_g
+    gc = grads.cpu()
+    for k, pname in enumerate(ops.ROUTER_PARAM_NAMES):
+        got = gc[off[k]:off[k] + sd[pname].numel()].reshape(sd[pname].shape)
+        if not pname.startswith("dm_router.0."):
+            assert float(got.abs().max()) == 0.0           # gate-head slots are untouched by dm_router_backward
+            continue
+        assert rel_err(got.numpy(), sdd[pname].grad.numpy()) < tol_g, pname
+
+
 # ------------------------------------------------------------------------------------------------ combine / CTC / decode
 def _ragged_logits(cc, B, T, seed, scale=3.0):
     return [synth.randn(seed, f"z{i}", (B, T, c), scale) for i, c in enumerate(cc)]
