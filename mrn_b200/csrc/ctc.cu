@@ -45,11 +45,114 @@ __device__ __forceinline__ void acc_merge(float& m, float& s, float (&A)[I], flo
   if (best2 > best || (best2 == best && besti2 < besti)) { best = best2; besti = besti2; }
 }
 
-// One CTA per (b,t) row.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float LOG2E = 1.4426950408889634f;
+
+// Vector pass over one charset segment [lo, hi) in which experts i < K are past their charset (pad value 1.0) and
+// experts i >= K are valid: 4 columns per thread from 16-byte loads, no per-element predicates, one online-softmax
+// rescale per 4 columns.  The <= 3 ragged columns at either end of the segment go through the scalar update.
+template <int I>
+__device__ __forceinline__ void row_update(float l, const float (&v)[I], int c, float& m, float& s, float (&A)[I],
+                                           float& best, int& besti) {
+  if (l > best || (l == best && c < besti)) { best = l; besti = c; }
+  if (l > m) {
+    const float f = ex2_approx((m - l) * LOG2E);
+    s *= f;
+#pragma unroll
+    for (int i = 0; i < I; ++i) A[i] *= f;
+    m = l;
+  }
+  const float e = ex2_approx((l - m) * LOG2E);
+  s += e;
+#pragma unroll
+  for (int i = 0; i < I; ++i) A[i] = fmaf(e, v[i], A[i]);
+}
+
+template <int I, int K>
+__device__ __forceinline__ void row_segment(const float* const (&zr)[I], const float (&g)[I], int lo, int hi, int tid,
+                                            float* __restrict__ lrow, float& m, float& s, float (&A)[I], float& best,
+                                            int& besti) {
+  if (lo >= hi) return;
+  float gk = 0.f;
+#pragma unroll
+  for (int i = 0; i < K; ++i) gk += g[i];
+  const int lo4 = min((lo + 3) & ~3, hi), hi4 = max(hi & ~3, lo4);
+  for (int c0 = lo4 + tid * 4; c0 < hi4; c0 += ROW_THREADS * 4) {
+    float4 v[I];
+#pragma unroll
+    for (int i = K; i < I; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(zr[i] + c0));
+    float l0 = gk, l1 = gk, l2 = gk, l3 = gk;
+#pragma unroll
+    for (int i = K; i < I; ++i) {
+      l0 = fmaf(g[i], v[i].x, l0); l1 = fmaf(g[i], v[i].y, l1); l2 = fmaf(g[i], v[i].z, l2); l3 = fmaf(g[i], v[i].w, l3);
+    }
+    if (lrow) *reinterpret_cast<float4*>(lrow + c0) = make_float4(l0, l1, l2, l3);
+    // this thread visits columns in ascending order: strict > keeps the first maximum
+    if (l0 > best) { best = l0; besti = c0; }
+    if (l1 > best) { best = l1; besti = c0 + 1; }
+    if (l2 > best) { best = l2; besti = c0 + 2; }
+    if (l3 > best) { best = l3; besti = c0 + 3; }
+    const float cm = fmaxf(fmaxf(l0, l1), fmaxf(l2, l3));
+    if (cm > m) {
+      const float f = ex2_approx((m - cm) * LOG2E);        // m = -inf -> 0
+      s *= f;
+#pragma unroll
+      for (int i = 0; i < I; ++i) A[i] *= f;
+      m = cm;
+    }
+    const float mb = -m * LOG2E;
+    const float e0 = ex2_approx(fmaf(l0, LOG2E, mb)), e1 = ex2_approx(fmaf(l1, LOG2E, mb));
+    const float e2 = ex2_approx(fmaf(l2, LOG2E, mb)), e3 = ex2_approx(fmaf(l3, LOG2E, mb));
+    const float es = (e0 + e1) + (e2 + e3);
+    s += es;
+#pragma unroll
+    for (int i = 0; i < K; ++i) A[i] += es;                // pad value 1.0
+#pragma unroll
+    for (int i = K; i < I; ++i) A[i] = fmaf(e0, v[i].x, fmaf(e1, v[i].y, fmaf(e2, v[i].z, fmaf(e3, v[i].w, A[i]))));
+  }
+  // ragged ends (and segments shorter than one vector)
+  for (int part = 0; part < 2; ++part) {
+    const int a = part == 0 ? lo : hi4, b = part == 0 ? lo4 : hi;
+    const int c = a + tid;
+    if (c < b) {
+      float v[I];
+      float l = gk;
+#pragma unroll
+      for (int i = 0; i < I; ++i) {
+        v[i] = i < K ? 1.0f : __ldg(zr[i] + c);
+        if (i >= K) l = fmaf(g[i], v[i], l);
+      }
+      if (lrow) lrow[c] = l;
+      row_update<I>(l, v, c, m, s, A, best, besti);
+    }
+  }
+}
+
+template <int I, int K>
+struct SegLoop {
+  __device__ static __forceinline__ void run(const float* const (&zr)[I], const float (&g)[I], const RowPtrs& P, int tid,
+                                             float* lrow, float& m, float& s, float (&A)[I], float& best, int& besti) {
+    row_segment<I, K>(zr, g, K == 0 ? 0 : P.C[K - 1], P.C[K], tid, lrow, m, s, A, best, besti);
+    SegLoop<I, K + 1>::run(zr, g, P, tid, lrow, m, s, A, best, besti);
+  }
+};
+template <int I>
+struct SegLoop<I, I> {
+  __device__ static __forceinline__ void run(const float* const (&)[I], const float (&)[I], const RowPtrs&, int, float*, float&,
+                                             float&, float (&)[I], float&, int&) {}
+};
+
+// One CTA per (b,t) row.  fast = 1 (host-checked: charsets ascending, 16-byte aligned rows) enables the segment /
+// vector pass whenever every gate weight is non-zero (soft route); the hard route (one-hot gate) keeps the generic
+// loop, which skips the loads of the unselected experts.
 template <int I>
 __global__ void __launch_bounds__(ROW_THREADS)
 combine_row_kernel(RowPtrs P, const float* __restrict__ gate,   // [B,I]
-                   int T, int C,
+                   int T, int C, int fast,
                    float* __restrict__ logits, long ldo,          // optional [B*T, ldo]
                    float* __restrict__ lse,                       // [B*T]
                    float* __restrict__ E,                         // optional [B*T, I]
@@ -74,6 +177,12 @@ combine_row_kernel(RowPtrs P, const float* __restrict__ gate,   // [B,I]
 #pragma unroll
   for (int i = 0; i < I; ++i) A[i] = 0.f;
 
+  bool soft = fast != 0;
+#pragma unroll
+  for (int i = 0; i < I; ++i) soft = soft && (g[i] != 0.f);
+  if (soft) {
+    SegLoop<I, 0>::run(zr, g, P, tid, logits ? logits + (long)row * ldo : nullptr, m, s, A, best, besti);
+  } else
   for (int c0 = tid; c0 < C; c0 += ROW_THREADS * 4) {
     float v[4][I];
 #pragma unroll
@@ -174,6 +283,305 @@ combine_row_kernel(RowPtrs P, const float* __restrict__ gate,   // [B,I]
         }
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA-staged persistent variant of the row pass (the one the training step runs).
+//
+// One CTA per SM walks rows r = blockIdx.x, blockIdx.x + gridDim.x, ...  A producer thread streams each row's ragged
+// expert slices into shared memory with 1-D bulk copies (cp.async.bulk, mbarrier complete_tx): the row is cut into
+// chunks of 3072 columns, chunk j always lands in stage j ([I][3072] floats), so the columns past an expert's charset
+// are pre-filled with the pad value 1.0 ONCE and never overwritten.  Stage j is released as soon as the consumers have
+// pulled it into registers, so the next row's chunk j is already in flight while this row is still being reduced: up to
+// a whole row (I*C*4 bytes, 120 KB for MLT17) of loads is outstanding per SM, independent of the arithmetic.
+// Experts with a zero gate (hard route) are not loaded at all.  24 consumer warps do the online-softmax pass from
+// conflict-free LDS.128 reads (the per-chunk dependency chain is long: fewer warps leave the SM latency-bound); two
+// epilogue warps finish alternate rows from the per-thread partials, off the streaming path.
+// ---------------------------------------------------------------------------------------------
+constexpr int TMA_CONSUMERS = 704;             // 22 consumer warps: the per-chunk dependency chain needs the parallelism
+constexpr int TMA_CHUNK = 4 * TMA_CONSUMERS;   // columns per stage = 4 per consumer thread
+constexpr int TMA_MAX_CHUNKS = 8;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init_(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint64_t* bar, uint32_t parity) {
+  uint64_t t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity), "r"(0x989680u) : "memory");
+    if (ok) return;
+    if ((spin & 63u) == 63u && mrnb_wait_expired(t0)) __trap();      // protocol bug: fail loudly, never hang
+  }
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+constexpr int TMA_EPI_WARPS = 4;                          // epilogue warp e finishes rows it = e (mod 4)
+constexpr int TMA_THREADS = TMA_CONSUMERS + 32 + 32 * TMA_EPI_WARPS;      // + producer warp + epilogue warps
+
+template <int I>
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+combine_row_tma_kernel(RowPtrs P, const float* __restrict__ gate, int T, int C, int rows, int nchunks,
+                       float* __restrict__ logits, long ldo, float* __restrict__ lse, float* __restrict__ E,
+                       int* __restrict__ amax, float* __restrict__ maxprob, const long long* __restrict__ targets,
+                       const int* __restrict__ tlen, int Lmax, float* __restrict__ lpe, float* __restrict__ zlab, int S1) {
+  extern __shared__ __align__(128) float stage[];           // [nchunks][I][TMA_CHUNK], then partials [2][4 + I][256]
+  __shared__ __align__(8) uint64_t full_bar[TMA_MAX_CHUNKS], empty_bar[TMA_MAX_CHUNKS];
+  __shared__ __align__(8) uint64_t rowdone_bar[TMA_EPI_WARPS], partfree_bar[2];   // row-done: one per epilogue warp
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* part = stage + (size_t)nchunks * I * TMA_CHUNK;    // per-thread row partials, SoA: part[buf][k][tid]
+  constexpr int PK = 4 + I;
+
+  for (int k = tid; k < nchunks * I * TMA_CHUNK; k += blockDim.x) stage[k] = 1.0f;      // pad value, written once
+  if (tid == 0) {
+    for (int j = 0; j < nchunks; ++j) { mbar_init_(&full_bar[j], 1); mbar_init_(&empty_bar[j], TMA_CONSUMERS / 32); }
+    for (int k = 0; k < TMA_EPI_WARPS; ++k) mbar_init_(&rowdone_bar[k], TMA_CONSUMERS / 32);
+    for (int k = 0; k < 2; ++k) mbar_init_(&partfree_bar[k], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy fill before async-proxy (TMA) writes
+  __syncthreads();
+
+  if (warp == TMA_CONSUMERS / 32) {
+    // ---------------- producer warp: lane i streams expert i's slice of every chunk (lane 0 posts the byte count)
+    {
+      uint32_t it = 0;
+      float gn[I];                                               // next row's gate, fetched one row ahead
+#pragma unroll
+      for (int i = 0; i < I; ++i) gn[i] = blockIdx.x < rows ? __ldg(gate + (blockIdx.x / T) * I + i) : 0.f;
+      const int me = lane < I ? lane : 0;
+      const int myC = P.C[me];
+      const long myld = P.ld[me];
+      const float* myz = P.z[me];
+      for (int row = blockIdx.x; row < rows; row += gridDim.x, ++it) {
+        float g[I];
+#pragma unroll
+        for (int i = 0; i < I; ++i) g[i] = gn[i];
+        if (row + (int)gridDim.x < rows) {
+          const int bn = (row + gridDim.x) / T;
+#pragma unroll
+          for (int i = 0; i < I; ++i) gn[i] = __ldg(gate + bn * I + i);
+        }
+        float myg = 0.f;
+#pragma unroll
+        for (int i = 0; i < I; ++i) if (i == lane) myg = g[i];
+        const float* src = myz + (long)row * myld;
+        for (int j = 0; j < nchunks; ++j) {
+          uint32_t total = 0;
+#pragma unroll
+          for (int i = 0; i < I; ++i) {
+            int n = P.C[i] - j * TMA_CHUNK;
+            n = n < 0 ? 0 : (n > TMA_CHUNK ? TMA_CHUNK : n);
+            total += (g[i] != 0.f) ? (uint32_t)((n + 3) & ~3) * 4u : 0u;      // whole 16-byte pieces (ld is padded to 4)
+          }
+          int n = myC - j * TMA_CHUNK;
+          n = n < 0 ? 0 : (n > TMA_CHUNK ? TMA_CHUNK : n);
+          const uint32_t nb = (lane < I && myg != 0.f) ? (uint32_t)((n + 3) & ~3) * 4u : 0u;
+          mbar_wait_(&empty_bar[j], (it & 1u) ^ 1u);
+          if (lane == 0) {
+            if (total == 0) mbar_arrive_(&full_bar[j]);
+            else mbar_expect_tx_(&full_bar[j], total);
+          }
+          __syncwarp();
+          if (nb) bulk_load(stage + ((size_t)j * I + lane) * TMA_CHUNK, src + j * TMA_CHUNK, nb, &full_bar[j]);
+        }
+      }
+    }
+    return;
+  }
+
+  if (warp > TMA_CONSUMERS / 32) {
+    // ---------------- epilogue warps: warp ew finishes rows it = ew, ew + 4, ... from the partials in buffer it & 1
+    const int ew = warp - TMA_CONSUMERS / 32 - 1;
+    const int e = ew & 1;
+    const float* pb = part + (size_t)e * PK * TMA_CONSUMERS;
+    for (uint32_t it = ew; ; it += TMA_EPI_WARPS) {
+      const long row = (long)blockIdx.x + (long)it * gridDim.x;
+      if (row >= rows) break;
+      const int b = (int)(row / T);
+      // label-column gather first: it does not depend on the row reduction, so its DRAM latency hides behind the
+      // consumers still streaming this row (S1 <= 32: one lattice column per lane)
+      float lq = 0.f;
+      bool lvalid = false;
+      if (lpe && lane < S1) {
+        const int L = min(tlen[b], Lmax);
+        const long base = (row * S1 + lane) * I;
+        const bool valid = (lane == 0) || (lane - 1 < L);
+        int col = 0;
+        if (lane > 0 && valid) col = (int)targets[(long)b * Lmax + lane - 1];
+        lvalid = valid && col >= 0 && col < C;
+        if (lvalid) {
+#pragma unroll
+          for (int i = 0; i < I; ++i) {
+            const float gi = __ldg(gate + b * I + i);
+            const float v = (col < P.C[i]) ? ((gi != 0.f) ? __ldg(P.z[i] + row * P.ld[i] + col) : 0.f) : 1.0f;
+            lq = fmaf(gi, v, lq);
+            if (zlab) zlab[base + i] = v;
+          }
+        } else if (zlab) {
+#pragma unroll
+          for (int i = 0; i < I; ++i) zlab[base + i] = 0.f;
+        }
+      }
+      mbar_wait_(&rowdone_bar[ew], (it / TMA_EPI_WARPS) & 1u);
+      float m = -INFINITY, s = 0.f, best = -INFINITY;
+      int besti = 0x7fffffff;
+      float A[I];
+#pragma unroll
+      for (int i = 0; i < I; ++i) A[i] = 0.f;
+      for (int k = lane; k < TMA_CONSUMERS; k += 32) {
+        float A2[I];
+#pragma unroll
+        for (int i = 0; i < I; ++i) A2[i] = pb[(4 + i) * TMA_CONSUMERS + k];
+        acc_merge<I>(m, s, A, best, besti, pb[k], pb[TMA_CONSUMERS + k], A2, pb[2 * TMA_CONSUMERS + k],
+                     __float_as_int(pb[3 * TMA_CONSUMERS + k]));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_(&partfree_bar[e]);             // partial buffer e may be rewritten (row it + 2)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+        const float s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        const float b2 = __shfl_xor_sync(0xffffffffu, best, o);
+        const int bi2 = __shfl_xor_sync(0xffffffffu, besti, o);
+        float A2[I];
+#pragma unroll
+        for (int i = 0; i < I; ++i) A2[i] = __shfl_xor_sync(0xffffffffu, A[i], o);
+        acc_merge<I>(m, s, A, best, besti, m2, s2, A2, b2, bi2);
+      }
+      const float lrow_lse = m + logf(s);                        // every lane holds the full reduction
+      if (lane == 0) {
+        lse[row] = lrow_lse;
+        if (E) {
+          const float inv = 1.0f / s;
+#pragma unroll
+          for (int i = 0; i < I; ++i) E[row * I + i] = A[i] * inv;
+        }
+        if (amax) amax[row] = besti;
+        if (maxprob) maxprob[row] = __expf(best - lrow_lse);
+      }
+      if (lpe && lane < S1) lpe[row * S1 + lane] = lvalid ? lq - lrow_lse : -INFINITY;
+    }
+    return;
+  }
+
+  // ---------------- consumers (4 columns each per chunk)
+  // the one 4-column group per expert that straddles its charset boundary: lanes >= C_i % 4 take the pad value again
+  uint32_t smask = 0;                                            // chunks in which this thread owns a straddling group
+#pragma unroll
+  for (int i = 0; i < I; ++i) {
+    const int Ci = P.C[i];
+    if ((Ci & 3) != 0 && ((Ci % TMA_CHUNK) >> 2) == tid) smask |= 1u << (Ci / TMA_CHUNK);
+  }
+  uint32_t it = 0;
+  float gn[I];                                                   // next row's gate, fetched one row ahead
+#pragma unroll
+  for (int i = 0; i < I; ++i) gn[i] = blockIdx.x < rows ? __ldg(gate + (blockIdx.x / T) * I + i) : 0.f;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x, ++it) {
+    float g[I];
+    bool hard = false;
+#pragma unroll
+    for (int i = 0; i < I; ++i) { g[i] = gn[i]; hard = hard || (g[i] == 0.f); }
+    if (row + (int)gridDim.x < rows) {
+      const int bn = (row + gridDim.x) / T;
+#pragma unroll
+      for (int i = 0; i < I; ++i) gn[i] = __ldg(gate + bn * I + i);
+    }
+    float m = -INFINITY, s = 0.f, best = -INFINITY;
+    int besti = 0x7fffffff;
+    float A[I];
+#pragma unroll
+    for (int i = 0; i < I; ++i) A[i] = 0.f;
+    float* lrow = logits ? logits + (long)row * ldo : nullptr;
+
+    for (int j = 0; j < nchunks; ++j) {
+      mbar_wait_(&full_bar[j], it & 1u);
+      const int c0 = j * TMA_CHUNK + tid * 4;
+      float4 v[I];
+#pragma unroll
+      for (int i = 0; i < I; ++i) v[i] = *reinterpret_cast<const float4*>(stage + ((size_t)j * I + i) * TMA_CHUNK + tid * 4);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_(&empty_bar[j]);              // stage j may be refilled with the next row
+      if ((smask >> j) & 1u) {                                 // rare: re-impose the pad on the copied ld padding
+#pragma unroll
+        for (int i = 0; i < I; ++i) {
+          const int Ci = P.C[i], sn = Ci & 3;
+          if (sn != 0 && ((Ci % TMA_CHUNK) >> 2) == tid && Ci / TMA_CHUNK == j) {
+            if (sn <= 1) v[i].y = 1.0f;
+            if (sn <= 2) v[i].z = 1.0f;
+            v[i].w = 1.0f;
+          }
+        }
+      }
+      if (c0 >= C) continue;
+      if (hard) {                                              // one-hot gate: unselected stages hold stale (finite) data
+#pragma unroll
+        for (int i = 0; i < I; ++i) if (g[i] == 0.f) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < I; ++i) {
+        l0 = fmaf(g[i], v[i].x, l0); l1 = fmaf(g[i], v[i].y, l1); l2 = fmaf(g[i], v[i].z, l2); l3 = fmaf(g[i], v[i].w, l3);
+      }
+      if (c0 + 4 <= C) {
+        if (lrow) *reinterpret_cast<float4*>(lrow + c0) = make_float4(l0, l1, l2, l3);
+        if (l0 > best) { best = l0; besti = c0; }
+        if (l1 > best) { best = l1; besti = c0 + 1; }
+        if (l2 > best) { best = l2; besti = c0 + 2; }
+        if (l3 > best) { best = l3; besti = c0 + 3; }
+        const float cm = fmaxf(fmaxf(l0, l1), fmaxf(l2, l3));
+        if (cm > m) {
+          const float f = ex2_approx((m - cm) * LOG2E);
+          s *= f;
+#pragma unroll
+          for (int i = 0; i < I; ++i) A[i] *= f;
+          m = cm;
+        }
+        const float mb = -m * LOG2E;
+        const float e0 = ex2_approx(fmaf(l0, LOG2E, mb)), e1 = ex2_approx(fmaf(l1, LOG2E, mb));
+        const float e2 = ex2_approx(fmaf(l2, LOG2E, mb)), e3 = ex2_approx(fmaf(l3, LOG2E, mb));
+        s += (e0 + e1) + (e2 + e3);
+#pragma unroll
+        for (int i = 0; i < I; ++i) A[i] = fmaf(e0, v[i].x, fmaf(e1, v[i].y, fmaf(e2, v[i].z, fmaf(e3, v[i].w, A[i]))));
+      } else {
+        // the last, partial group of the row (C % 4 != 0)
+        const float lv[4] = {l0, l1, l2, l3};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (c0 + u < C) {
+            float vv[I];
+#pragma unroll
+            for (int i = 0; i < I; ++i) vv[i] = u == 0 ? v[i].x : (u == 1 ? v[i].y : (u == 2 ? v[i].z : v[i].w));
+            if (lrow) lrow[c0 + u] = lv[u];
+            row_update<I>(lv[u], vv, c0 + u, m, s, A, best, besti);
+          }
+        }
+      }
+    }
+    // ---- hand the per-thread partials to this row's epilogue warp and move on to the next row
+    const int buf = it & 1u;
+    mbar_wait_(&partfree_bar[buf], ((it >> 1) & 1u) ^ 1u);
+    float* pw = part + (size_t)buf * PK * TMA_CONSUMERS + tid;
+    pw[0] = m; pw[TMA_CONSUMERS] = s; pw[2 * TMA_CONSUMERS] = best; pw[3 * TMA_CONSUMERS] = __int_as_float(besti);
+#pragma unroll
+    for (int i = 0; i < I; ++i) pw[(4 + i) * TMA_CONSUMERS] = A[i];
+    __syncwarp();
+    if (lane == 0) mbar_arrive_(&rowdone_bar[it % TMA_EPI_WARPS]);
   }
 }
 
@@ -372,7 +780,33 @@ template <int I>
 int launch_combine(const RowPtrs& P, const float* gate, int B, int T, int C, float* logits, long ldo, float* lse,
                    float* E, int* amax, float* maxprob, const long long* targets, const int* tlen, int Lmax,
                    float* lpe, float* zlab, int S1, cudaStream_t st) {
-  combine_row_kernel<I><<<B * T, ROW_THREADS, 0, st>>>(P, gate, T, C, logits, ldo, lse, E, amax, maxprob, targets,
+  int fast = 1;
+  for (int i = 0; i < I; ++i) {
+    fast = fast && (P.ld[i] % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.z[i]) & 15) == 0) && (i == 0 || P.C[i] >= P.C[i - 1]);
+  }
+  fast = fast && P.C[I - 1] == C && (!logits || (ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0));
+  const int nchunks = (C + TMA_CHUNK - 1) / TMA_CHUNK;
+  const size_t smem = ((size_t)nchunks * I * TMA_CHUNK + 2 * (4 + I) * TMA_CONSUMERS) * sizeof(float);
+  static int use_tma = -1;
+  if (use_tma < 0) { const char* e = getenv("MRNB_COMBINE_TMA"); use_tma = (e && e[0] == '0') ? 0 : 1; }
+  if (fast && use_tma && nchunks <= TMA_MAX_CHUNKS && smem <= 220 * 1024) {
+    static bool attr_set = false;
+    static int num_sms = 148;
+    if (!attr_set) {
+      cudaFuncSetAttribute(combine_row_tma_kernel<I>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+      attr_set = true;
+    }
+    const int rows = B * T;
+    const int grid = rows < num_sms ? rows : num_sms;
+    combine_row_tma_kernel<I><<<grid, TMA_THREADS, smem, st>>>(P, gate, T, C, rows, nchunks, logits, ldo, lse, E, amax,
+                                                                       maxprob, targets, tlen, Lmax, lpe, zlab, S1);
+    MRNB_CHECK_LAUNCH("combine_row_tma_kernel");
+    return MRNB_OK;
+  }
+  combine_row_kernel<I><<<B * T, ROW_THREADS, 0, st>>>(P, gate, T, C, fast, logits, ldo, lse, E, amax, maxprob, targets,
                                                          tlen, Lmax, lpe, zlab, S1);
   MRNB_CHECK_LAUNCH("combine_row_kernel");
   return MRNB_OK;
