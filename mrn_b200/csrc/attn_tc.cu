@@ -7,7 +7,9 @@
 //                  (one row per thread), P_j = exp(S_j - m) as bf16 into a 128B-swizzled K-major smem tile
 //   O_j = P_j V_j      tcgen05.mma M128 N32 K128  (V_j read where it lies: MN-major, 64B swizzle)       -> TMEM cols [128,160)
 //   acc = acc * exp(m_old - m_new) + O_j in registers; out = acc / l.
-// Warp roles: warp 0 TMA producer, warp 1 TMEM alloc + MMA issuer, warps 2..5 softmax / epilogue.
+// Warp roles: warp 0 TMA producer, warp 1 TMEM alloc + MMA issuer, warps 2..9 softmax / epilogue: two warps per TMEM
+// lane quarter, each owning one 64-key half of the block (and one 16-dim half of O); the partners exchange their
+// half-row maxima through shared memory.  The softmax chain is latency-bound, so the extra warps are what buys speed.
 #include "common.cuh"
 #include <cuda.h>
 
@@ -74,14 +76,40 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));      // FMNMX3
+  return r;
+}
+
+// named barrier 1 + q for the two partner warps (64 threads) of TMEM lane quarter q; immediate ids keep the CTA at 5 barriers
+__device__ __forceinline__ void pair_sync(int q) {
+  switch (q) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
+constexpr int ATT_THREADS = 64 + 256;
+
 template <bool LOCAL>
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(ATT_THREADS)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int N, int d) {
   constexpr int W = 64;            // SVTR token grid width for 32x256 crops (modules/svtr.py:348): shifts, not divisions
   extern __shared__ uint8_t smem_raw[];
@@ -91,6 +119,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict
   uint8_t* sP = smem + TILE_BYTES + 4 * TILE_BYTES;   // 32 KiB, 1024-aligned (offset 40 KiB)
   __shared__ __align__(8) uint64_t q_full, kv_full[2], kv_empty[2], s_full, s_empty, p_full, o_full;
   __shared__ uint32_t tmem_base_sh;
+  __shared__ float xch[2][2][QT];              // [parity][column half][row]: partner exchange of half-row maxima / sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, g = blockIdx.z;
@@ -105,7 +134,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict
   if (threadIdx.x == 0) {
     mbar_init(&q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(&s_full, 1); mbar_init(&s_empty, 128); mbar_init(&p_full, 128); mbar_init(&o_full, 1);
+    mbar_init(&s_full, 1); mbar_init(&s_empty, 256); mbar_init(&p_full, 256); mbar_init(&o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm)) : "memory");
   }
@@ -170,26 +199,27 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict
     }
   } else {
     const int q = warp & 3;
+    const int ch = (warp - 2) >> 2;               // 64-key half of every block / 16-dim half of O owned by this warp
     const int r = q * 32 + lane;                  // query row inside the tile == TMEM lane
     const int n = qt * QT + r;                    // token index of this query
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int qh = n >> 6, qw = n & 63;
     const float sl2 = 0.17677669529663688110f * 1.4426950408889634f;     // 32^-0.5 * log2(e)
-    float m = -INFINITY, l = 0.f;
-    float acc[HD];
+    float m = -INFINITY, l = 0.f, corr_prev = 0.f;
+    float acc[HD / 2];
 #pragma unroll
-    for (int j = 0; j < HD; ++j) acc[j] = 0.f;
+    for (int j = 0; j < HD / 2; ++j) acc[j] = 0.f;
     for (int j = 0; j < nb; ++j) {
       mbar_wait(&s_full, (uint32_t)j & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // Local window as a 32-bit validity mask per 32-key chunk (a chunk lies inside one row of the token grid):
       // bit i set <=> |kh - qh| <= 3 and |kw0 + i - qw| <= 5.
-      uint32_t vmask[KT / 32];
+      uint32_t vmask[2];
 #pragma unroll
-      for (int c = 0; c < KT / 32; ++c) {
-        vmask[c] = 0xffffffffu;
+      for (int cc = 0; cc < 2; ++cc) {
+        vmask[cc] = 0xffffffffu;
         if (LOCAL) {
-          const int key0 = (jb0 + j) * KT + c * 32;
+          const int key0 = (jb0 + j) * KT + (ch * 2 + cc) * 32;
           const int dh = (key0 >> 6) - qh;
           const int lo = qw - 5 - (key0 & 63), hi = qw + 5 - (key0 & 63);       // valid i in [lo, hi]
           uint32_t mk = 0u;
@@ -197,74 +227,92 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict
             const int l2 = lo < 0 ? 0 : lo, h2 = hi > 31 ? 31 : hi;
             mk = (0xffffffffu >> (31 - h2)) & (0xffffffffu << l2);
           }
-          vmask[c] = mk;
+          vmask[cc] = mk;
         }
       }
-      // pass 1: block maximum of the (masked) scores
+      // pass 1: maximum over the chunks this warp visits.  The Local window mask is NOT applied here: any reference
+      // >= the true row maximum keeps exp2() <= 1, and the keys of a visited chunk sit next to the window, so the
+      // reference stays within a few units of the masked maximum (the bf16 / fp32 exponent range is ample).
       float bmax = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < KT / 32; ++c) {
-        if (LOCAL && __all_sync(0xffffffffu, vmask[c] == 0u)) continue;        // warp-uniform: nothing visible here
+      for (int cc = 0; cc < 2; ++cc) {
+        if (LOCAL && __all_sync(0xffffffffu, vmask[cc] == 0u)) continue;       // warp-uniform: nothing visible here
         uint32_t v[32];
-        tmem_ld32(lane_addr + (uint32_t)(c * 32), v);
+        tmem_ld32(lane_addr + (uint32_t)((ch * 2 + cc) * 32), v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = __uint_as_float(v[i]);
-          if (!LOCAL || ((vmask[c] >> i) & 1u)) bmax = fmaxf(bmax, s);
-        }
+        for (int i = 0; i < 32; i += 2) bmax = max3(bmax, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
       }
+      xch[j & 1][ch][r] = bmax;
+      pair_sync(q);                                              // the two warps of this lane quarter
+      bmax = fmaxf(bmax, xch[j & 1][ch ^ 1][r]);
       const float mnew = fmaxf(m, bmax * sl2);
-      const float mref = (mnew == -INFINITY) ? 0.f : mnew;       // whole block masked so far
+      const float mref = (mnew == -INFINITY) ? 0.f : mnew;       // nothing visible so far
       const float corr = ex2_approx(m - mref);                   // m = -inf -> 0
       float bsum = 0.f;
-      // pass 2: P = exp2(s*scale*log2e - m) -> bf16 -> swizzled smem
+      if (j > 0) {
+        // deferred accumulation of the previous block: O_{j-1} = P_{j-1} V_{j-1} had all of pass 1 to complete, and
+        // its completion also frees the P tile that pass 2 below overwrites
+        mbar_wait(&o_full, (uint32_t)(j - 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t o[16];
+        tmem_ld16(lane_addr + O_COL + (uint32_t)(ch * 16), o);
 #pragma unroll
-      for (int c = 0; c < KT / 32; ++c) {
+        for (int i = 0; i < HD / 2; ++i) acc[i] = fmaf(acc[i], corr_prev, __uint_as_float(o[i]));
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      }
+      // pass 2: P = exp2(s*scale*log2e - m) -> bf16 -> swizzled smem (this warp's 64-key half = one 16 KiB P tile half)
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
         uint32_t pk[16];
-        if (LOCAL && __all_sync(0xffffffffu, vmask[c] == 0u)) {
+        if (LOCAL && __all_sync(0xffffffffu, vmask[cc] == 0u)) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) pk[i] = 0u;
         } else {
           uint32_t v[32];
-          tmem_ld32(lane_addr + (uint32_t)(c * 32), v);
+          tmem_ld32(lane_addr + (uint32_t)((ch * 2 + cc) * 32), v);
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sl2, -mref));
             float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sl2, -mref));
             if (LOCAL) {
-              if (!((vmask[c] >> i) & 1u)) p0 = 0.f;
-              if (!((vmask[c] >> (i + 1)) & 1u)) p1 = 0.f;
+              if (!((vmask[cc] >> i) & 1u)) p0 = 0.f;
+              if (!((vmask[cc] >> (i + 1)) & 1u)) p1 = 0.f;
             }
             __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
             bsum += p0 + p1;          // fp32 normaliser (rounding of P to bf16 is unbiased: no systematic mismatch with PV)
             pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
           }
         }
-        uint8_t* prow = sP + (c >> 1) * 16384 + r * 128;
+        uint8_t* prow = sP + ch * 16384 + r * 128;
 #pragma unroll
         for (int p4 = 0; p4 < 4; ++p4) {
-          const int piece = ((c & 1) * 4 + p4) ^ (r & 7);
+          const int piece = (cc * 4 + p4) ^ (r & 7);
           *reinterpret_cast<uint4*>(prow + piece * 16) = make_uint4(pk[p4 * 4], pk[p4 * 4 + 1], pk[p4 * 4 + 2], pk[p4 * 4 + 3]);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&s_empty);                                      // S_j fully consumed
+      mbar_arrive(&s_empty);                                      // this warp's half of S_j is consumed
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy smem writes -> visible to UMMA
       mbar_arrive(&p_full);
-      l = l * corr + bsum;
+      l = l * corr + bsum;                                        // partial normaliser of this half (same reference m)
       m = mnew;
-      mbar_wait(&o_full, (uint32_t)j & 1u);
+      corr_prev = corr;
+    }
+    {
+      mbar_wait(&o_full, (uint32_t)(nb - 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t o[32];
-      tmem_ld32(lane_addr + O_COL, o);
+      uint32_t o[16];
+      tmem_ld16(lane_addr + O_COL + (uint32_t)(ch * 16), o);
 #pragma unroll
-      for (int i = 0; i < HD; ++i) acc[i] = fmaf(acc[i], corr, __uint_as_float(o[i]));
+      for (int i = 0; i < HD / 2; ++i) acc[i] = fmaf(acc[i], corr_prev, __uint_as_float(o[i]));
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
-    const float inv = 1.0f / l;
-    __nv_bfloat16* op = out + (row0 + n) * d + h * HD;
+    xch[nb & 1][ch][r] = l;
+    pair_sync(q);
+    const float inv = 1.0f / (l + xch[nb & 1][ch ^ 1][r]);
+    __nv_bfloat16* op = out + (row0 + n) * d + h * HD + ch * (HD / 2);
 #pragma unroll
-    for (int i = 0; i < HD; i += 8) {
+    for (int i = 0; i < HD / 2; i += 8) {
       uint32_t pk[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -318,8 +366,8 @@ int mrnb_attention_tc(const void* qkv, void* out, int groups, int N, int d, int 
     attr = true;
   }
   dim3 grid(N / QT, heads, groups);
-  if (local) attn_tc_kernel<true><<<grid, 192, smem, st>>>(tm, (__nv_bfloat16*)out, N, d);
-  else attn_tc_kernel<false><<<grid, 192, smem, st>>>(tm, (__nv_bfloat16*)out, N, d);
+  if (local) attn_tc_kernel<true><<<grid, ATT_THREADS, smem, st>>>(tm, (__nv_bfloat16*)out, N, d);
+  else attn_tc_kernel<false><<<grid, ATT_THREADS, smem, st>>>(tm, (__nv_bfloat16*)out, N, d);
   MRNB_CHECK_LAUNCH("attn_tc_kernel");
   return MRNB_OK;
 }
