@@ -156,7 +156,34 @@ lnT_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma /*[T
   }
 }
 
+// Sum 16 per-lane values across the warp with recursive halving: 16 shuffles instead of 16 x 5.  Returns, in every
+// lane, the warp total of value index (lane >> 1) & 15.
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+  float w8[8], w4[4], w2[2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = b4 ? v[i] : v[i + 8], keep = b4 ? v[i + 8] : v[i];
+    w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = b3 ? w8[i] : w8[i + 4], keep = b3 ? w8[i + 4] : w8[i];
+    w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b2 ? w4[i] : w4[i + 2], keep = b2 ? w4[i + 2] : w4[i];
+    w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float send = b1 ? w2[0] : w2[1], keep = b1 ? w2[1] : w2[0];
+  float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
 // backward of lnT: dy += rstd*(dxh - mean(dxh) - xh*mean(dxh*xh)), dgamma[t] += sum dgn*xh, dbeta[t] += sum dgn
+// block per (b,i), thread per channel c; the per-frame sums over c go through warp_reduce16 in groups of 8 frames
 __global__ void __launch_bounds__(RD)
 lnT_bwd_kernel(const float* __restrict__ y, const float* __restrict__ stats, const float* __restrict__ gamma,
                const float* __restrict__ dgn, float* __restrict__ dy /* accumulated */, __nv_bfloat16* __restrict__ dy16,
@@ -170,12 +197,25 @@ lnT_bwd_kernel(const float* __restrict__ y, const float* __restrict__ stats, con
   const float* yp = y + bi * T * RD + c;
   const float* dp = dgn + bi * T * RD + c;
   float m1 = 0.f, m2 = 0.f;
-  for (int t = 0; t < Tv; ++t) {
-    const float xh = (yp[(long)t * RD] - mean) * rstd, d = dp[(long)t * RD];
-    const float dxh = d * gamma[t];
-    m1 += dxh; m2 = fmaf(dxh, xh, m2);
-    const float a = warp_sum(d * xh), b2 = warp_sum(d);
-    if (lane == 0) { atomicAdd(&sh[t * 2], a); atomicAdd(&sh[t * 2 + 1], b2); }
+  for (int t0 = 0; t0 < Tv; t0 += 8) {
+    float v[16];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int t = t0 + u;
+      float xh = 0.f, d = 0.f;
+      if (t < Tv) {
+        xh = (yp[(long)t * RD] - mean) * rstd; d = dp[(long)t * RD];
+        const float dxh = d * gamma[t];
+        m1 += dxh; m2 = fmaf(dxh, xh, m2);
+      }
+      v[u] = d * xh; v[8 + u] = d;
+    }
+    const float tot = warp_reduce16(v, lane);
+    if ((lane & 1) == 0) {
+      const int idx = (lane >> 1) & 15;                    // 0..7: sum d*xh of frame t0+idx ; 8..15: sum d of frame t0+idx-8
+      const int t = t0 + (idx & 7);
+      if (t < Tv) atomicAdd(&sh[t * 2 + (idx >> 3)], tot);
+    }
   }
   m1 /= Tv; m2 /= Tv;
   float* op = dy + bi * T * RD + c;
@@ -377,25 +417,43 @@ int launch_gate_head_dw(const float* ds, const float* out, int B, int T, float* 
   }
 
 // gate head finish: r[b,j] = sum_t wr[t] s[b,t,j] + br ; gate = softmax(r) ; index = first argmax
-__global__ void gate_finish_kernel(const float* __restrict__ s, const float* __restrict__ wr, const float* __restrict__ br,
-                                   int B, int T, int I, float* __restrict__ r, float* __restrict__ gate,
-                                   int* __restrict__ index) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+gate_finish_kernel(const float* __restrict__ s, const float* __restrict__ wr, const float* __restrict__ br,
+                   int B, int T, int I, float* __restrict__ r, float* __restrict__ gate, int* __restrict__ index) {
+  // one warp per sample: lanes stride the (t, j) pairs of s[b] (contiguous), then a shuffle reduction per expert
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (b >= B) return;
+  float part[MRNB_MAX_EXPERTS];
+#pragma unroll
+  for (int j = 0; j < MRNB_MAX_EXPERTS; ++j) part[j] = 0.f;
+  const float* sb = s + (long)b * T * I;
+  for (int t = lane; t < T; t += 32) {
+    const float w = wr[t];
+#pragma unroll
+    for (int j = 0; j < MRNB_MAX_EXPERTS; ++j)
+      if (j < I) part[j] = fmaf(w, sb[t * I + j], part[j]);
+  }
   float rr[MRNB_MAX_EXPERTS];
   float mx = -INFINITY; int am = 0;
-  for (int j = 0; j < I; ++j) {
-    float a = 0.f;
-    for (int t = 0; t < T; ++t) a = fmaf(wr[t], s[((long)b * T + t) * I + j], a);
-    a += br[0];
-    rr[j] = a;
-    if (a > mx) { mx = a; am = j; }
+#pragma unroll
+  for (int j = 0; j < MRNB_MAX_EXPERTS; ++j) {
+    if (j < I) {
+      const float a = warp_sum(part[j]) + br[0];
+      rr[j] = a;
+      if (a > mx) { mx = a; am = j; }
+    }
   }
+  if (lane != 0) return;
   float sum = 0.f;
-  for (int j = 0; j < I; ++j) sum += expf(rr[j] - mx);
-  for (int j = 0; j < I; ++j) {
-    if (r) r[b * I + j] = rr[j];
-    if (gate) gate[b * I + j] = expf(rr[j] - mx) / sum;
+#pragma unroll
+  for (int j = 0; j < MRNB_MAX_EXPERTS; ++j) if (j < I) sum += expf(rr[j] - mx);
+#pragma unroll
+  for (int j = 0; j < MRNB_MAX_EXPERTS; ++j) {
+    if (j < I) {
+      if (r) r[b * I + j] = rr[j];
+      if (gate) gate[b * I + j] = expf(rr[j] - mx) / sum;
+    }
   }
   if (index) index[b] = am;
 }
@@ -501,9 +559,71 @@ RouterWs carve(char* base, int B, int I, int T, int D, bool bwd) {
     MRNB_CHECK_LAUNCH(#kernel);                                        \
   } while (0)
 
+// column sums for n-contiguous layouts: 64 x float4 columns per block, 4 row lanes, 4 rows in flight per thread
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const float* __restrict__ X, MrnbAxis am, MrnbAxis an, int M, int N, float* __restrict__ out) {
+  __shared__ float4 sh[4][64];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int n = (blockIdx.x * 64 + tx) * 4;
+  const int per = (M + gridDim.y - 1) / gridDim.y;
+  const int m0 = blockIdx.y * per, m1 = min(M, m0 + per);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n < N) {
+    const float* base = X + (long)(n / an.inner) * an.so + (long)(n % an.inner);
+    int m = m0 + ty;
+    for (; m + 12 < m1; m += 16) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int mm = m + 4 * u;
+        v[u] = *reinterpret_cast<const float4*>(base + (long)(mm / am.inner) * am.so + (long)(mm % am.inner) * am.si);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+    }
+    for (; m < m1; m += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(base + (long)(m / am.inner) * am.so + (long)(m % am.inner) * am.si);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  sh[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float4 t = sh[0][tx];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) { t.x += sh[k][tx].x; t.y += sh[k][tx].y; t.z += sh[k][tx].z; t.w += sh[k][tx].w; }
+    atomicAdd(out + n, t.x); atomicAdd(out + n + 1, t.y); atomicAdd(out + n + 2, t.z); atomicAdd(out + n + 3, t.w);
+  }
+}
+
+// out[r % period] += sum_c X[r, 0..255]  for contiguous rows of 256 (token sums over (b, c)): one warp per (n, b-chunk)
+__global__ void __launch_bounds__(256)
+rowsum256_kernel(const float* __restrict__ X, int period, int reps, float* __restrict__ out) {
+  const int n = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int per = (reps + gridDim.y * 8 - 1) / (gridDim.y * 8);
+  const int b0 = (blockIdx.y * 8 + w) * per, b1 = min(reps, b0 + per);
+  float s = 0.f;
+  for (int b = b0; b < b1; ++b) {
+    const float* row = X + ((long)b * period + n) * RD;
+    const float4 u = *reinterpret_cast<const float4*>(row + lane * 4), v = *reinterpret_cast<const float4*>(row + 128 + lane * 4);
+    s += (u.x + u.y) + (u.z + u.w) + (v.x + v.y) + (v.z + v.w);
+  }
+  s = warp_sum(s);
+  if (lane == 0 && b1 > b0) atomicAdd(out + n, s);
+}
+
 int colsum(const float* X, MrnbAxis am, MrnbAxis an, int M, int N, float* out, cudaStream_t st) {
   int msplit = M / 512; if (msplit < 1) msplit = 1; if (msplit > 64) msplit = 64;
   MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+  const bool vec = an.si == 1 && (an.inner % 4 == 0) && (N % 4 == 0) && (an.so % 4 == 0) && (am.si % 4 == 0) && (am.so % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  if (vec) {
+    const int gx = cdiv(N, 256);
+    int gy = 1184 / gx; if (gy < 1) gy = 1; if (gy > M / 16) gy = M / 16 > 0 ? M / 16 : 1;      // ~8 blocks per SM
+    colsum_vec_kernel<<<dim3(gx, gy), 256, 0, st>>>(X, am, an, M, N, out);
+    MRNB_CHECK_LAUNCH("colsum_vec_kernel");
+    return MRNB_OK;
+  }
   colsum_kernel<<<dim3(cdiv(N, 32), msplit), 256, 0, st>>>(X, am, an, M, N, out);
   MRNB_CHECK_LAUNCH("colsum_kernel");
   return MRNB_OK;
@@ -698,7 +818,7 @@ int router_forward(const float* P, const float* x, const Dims& d, float* out_use
       MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
       MRNB_DISPATCH_I(launch_gate_head, I, out, P + off[R_CR_W], P + off[R_CR_B], B, T, w.s, st);
     }
-    gate_finish_kernel<<<cdiv(B, 128), 128, 0, st>>>(w.s, P + off[R_ROUTE_W], P + off[R_ROUTE_B], B, T, I, scores, gate, index);
+    gate_finish_kernel<<<cdiv(B, 8), 256, 0, st>>>(w.s, P + off[R_ROUTE_W], P + off[R_ROUTE_B], B, T, I, scores, gate, index);
     MRNB_CHECK_LAUNCH("gate_finish_kernel");
   }
   if (out_user) cudaMemcpyAsync(out_user, out, (size_t)M * D * sizeof(float), cudaMemcpyDeviceToDevice, st);
@@ -816,7 +936,11 @@ int dm_router_backward_core(const float* P, const float* x, const Dims& d, float
     }
   }
   // dbs[n] = sum_(b,c) dv2[b,n,c]
-  MRNB_TRY(colsum(w.dv2, mrnb_axis2(D, 1, ITD), mrnb_axis(D), B * D, (int)IT, G + off[R_SP_B], st));
+  {  // dbs[n] = sum_(b,c) dv2[b,n,c]
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    rowsum256_kernel<<<dim3((int)IT, B >= 64 ? 2 : 1), 256, 0, st>>>(w.dv2, (int)IT, B, G + off[R_SP_B]);
+    MRNB_CHECK_LAUNCH("rowsum256_kernel");
+  }
   {  // vn = LN_D(GELU(a1v)); u = GELU(a1u)
     MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
     const int grid = (int)((M + 8 * 16 - 1) / (8 * 16));
