@@ -150,9 +150,11 @@ def run_reference(args):
     }))
 
 
-def ncu_traffic(kernel):
+def ncu_traffic(kernel, arch="svtr"):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
-    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py), or None."""
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py; captured on the SVTR workload), or None."""
+    if arch != "svtr":
+        return None
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         return t.get(kernel, {}).get("dram_bytes_per_launch")
@@ -283,11 +285,11 @@ def run_ours(args):
         # the binding roof is the one the kernel sits closer to (small-K contractions are traffic-limited)
         if frac_t >= frac_h:
             roofline = {"kernel": dom_name, "bound": "tensor", "achieved": d.get("tflops"), "peak": tf_peak, "unit": "TFLOP/s",
-                        "frac": round(frac_t, 4), "traffic": ncu_traffic(dom_name),
+                        "frac": round(frac_t, 4), "traffic": ncu_traffic(dom_name, args.arch),
                         "algorithmic_flops_per_launch": f["flops"] / n_launch, "peak_source": peak_src + ", sustained"}
         else:
             roofline = {"kernel": dom_name, "bound": "hbm", "achieved": d.get("gbs"), "peak": hbm_peak, "unit": "GB/s",
-                        "frac": round(frac_h, 4), "traffic": ncu_traffic(dom_name),
+                        "frac": round(frac_h, 4), "traffic": ncu_traffic(dom_name, args.arch),
                         "algorithmic_bytes_per_launch": f["bytes"] / n_launch, "peak_source": peak_src}
         roofline.update({"launches_per_step": f["calls"] // args.steps, "avg_launch_us": round(f["ms"] / n_launch * 1e3, 1),
                          "frac_tensor": round(frac_t, 4), "frac_hbm": round(frac_h, 4)})

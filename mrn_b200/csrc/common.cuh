@@ -103,6 +103,32 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+// Sum 16 per-lane values across the warp with recursive halving: 16 shuffles instead of 16 x 5.  Returns, in every
+// lane, the warp total of value index (lane >> 1) & 15.
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+  float w8[8], w4[4], w2[2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = b4 ? v[i] : v[i + 8], keep = b4 ? v[i + 8] : v[i];
+    w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = b3 ? w8[i] : w8[i + 4], keep = b3 ? w8[i + 4] : w8[i];
+    w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b2 ? w4[i] : w4[i + 2], keep = b2 ? w4[i + 2] : w4[i];
+    w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float send = b1 ? w2[0] : w2[1], keep = b1 ? w2[1] : w2[0];
+  float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

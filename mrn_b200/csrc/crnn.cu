@@ -23,10 +23,6 @@ constexpr int CT = 63;      // frames
 constexpr int CTP = 64;     // padded frame rows
 constexpr int LH = 256;     // LSTM hidden size (opt.hidden_size)
 
-template <typename AT> struct Vec8;     // 8 activations
-template <> struct Vec8<float> { float4 a, b; };
-template <> struct Vec8<__nv_bfloat16> { uint4 a; };
-
 template <typename AT> __device__ __forceinline__ void load8(const AT* p, float (&v)[8]);
 template <> __device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
@@ -66,7 +62,7 @@ __global__ void __launch_bounds__(256)
 vgg_conv0_kernel(const float* __restrict__ image, const float* __restrict__ w /*[I,64,4,3,3]*/,
                  const float* __restrict__ bias /*[I,64]*/, AT* __restrict__ out, int B) {
   __shared__ float s_in[4][4][260];      // [channel][row][col + 1], zero padded
-  __shared__ float s_w[64 * 36 + 64];
+  __shared__ __align__(16) float s_w[64 * 36 + 64];
   const int pr = blockIdx.x, b = blockIdx.y, e = blockIdx.z;
   for (int i = threadIdx.x; i < 4 * 4 * 260; i += 256) {
     const int col = i % 260, r = (i / 260) % 4, c = i / (260 * 4);
@@ -93,7 +89,13 @@ vgg_conv0_kernel(const float* __restrict__ image, const float* __restrict__ w /*
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int oc = half * 32 + c8 * 8 + u;
-      const float* wp = s_w + oc * 36;
+      const float4* wp4 = reinterpret_cast<const float4*>(s_w + oc * 36);     // 9 broadcast 16-byte loads per channel
+      float wreg[36];
+#pragma unroll
+      for (int k4 = 0; k4 < 9; ++k4) {
+        const float4 t = wp4[k4];
+        wreg[k4 * 4] = t.x; wreg[k4 * 4 + 1] = t.y; wreg[k4 * 4 + 2] = t.z; wreg[k4 * 4 + 3] = t.w;
+      }
       float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -101,7 +103,7 @@ vgg_conv0_kernel(const float* __restrict__ image, const float* __restrict__ w /*
         for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
-            const float wv = wp[(c * 3 + kh) * 3 + kw];
+            const float wv = wreg[(c * 3 + kh) * 3 + kw];
             a00 = fmaf(wv, win[c][kh][kw], a00);
             a01 = fmaf(wv, win[c][kh][kw + 1], a01);
             a10 = fmaf(wv, win[c][kh + 1][kw], a10);
@@ -113,28 +115,29 @@ vgg_conv0_kernel(const float* __restrict__ image, const float* __restrict__ w /*
   }
 }
 
-// MaxPool2d((ph, pw)) over NHWC, 8 channels per thread.  in [N,H,W,C] -> out [N,H/ph,W/pw,C]
+// MaxPool2d((ph, pw)) over NHWC, 8 channels per thread.  in [N,H,W,C] -> out [N,H/ph,W/pw,C]   (32-bit index math:
+// the 8-channel group count stays below 2^31 for every supported batch)
 template <typename AT>
-__global__ void pool_kernel(const AT* __restrict__ in, AT* __restrict__ out, int H, int W, int C, int ph, int pw, long total8) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void pool_kernel(const AT* __restrict__ in, AT* __restrict__ out, int H, int W, int C, int ph, int pw, unsigned total8) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total8) return;
-  const int c8 = C / 8, OW = W / pw, OH = H / ph;
-  const int c = (int)(i % c8) * 8;
-  long r = i / c8;
-  const int ow = (int)(r % OW); r /= OW;
-  const int oh = (int)(r % OH);
-  const long n = r / OH;
+  const unsigned c8 = C / 8, OW = W / pw, OH = H / ph;
+  const unsigned c = (i % c8) * 8;
+  unsigned r = i / c8;
+  const unsigned ow = r % OW; r /= OW;
+  const unsigned oh = r % OH;
+  const unsigned n = r / OH;
   float m[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
   for (int a = 0; a < ph; ++a)
     for (int b = 0; b < pw; ++b) {
       float v[8];
-      load8<AT>(in + (((n * H + oh * ph + a) * W) + ow * pw + b) * C + c, v);
+      load8<AT>(in + ((size_t)((n * H + oh * ph + a) * W) + ow * pw + b) * C + c, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
     }
-  store8<AT>(out + i * 8, m);
+  store8<AT>(out + (size_t)i * 8, m);
 }
 
 // fp32 mode: im2col of an NHWC activation, col[(n, oh, owp), (kh, kw, c)], stride 1, OWp >= OW columns (extra = pad)
@@ -180,28 +183,33 @@ bn_stats512_kernel(const AT* __restrict__ x, long rows, double* __restrict__ sta
 }
 
 // y = ReLU(x * scale + shift) (+ MaxPool (2,1) when pool_h == 2).  x [I][B][H][64][512] -> y [I][B][H/pool_h][64][512]
+// grid (row blocks, I); a thread owns 8 channels (scale / shift in registers) and walks output rows
 template <typename AT>
-__global__ void bn_relu_pool_kernel(const AT* __restrict__ x, const float* __restrict__ ss /*[I,512,2]*/, AT* __restrict__ y,
-                                    long rows_per_expert_out, int H, int pool_h, long total8) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total8) return;
-  const int c = (int)(i % 64) * 8;
-  const long orow = i / 64;                       // (e, b, oh, w)
-  const int e = (int)(orow / rows_per_expert_out);
-  const long w = orow % 64;
-  const long nh = orow / 64;                      // (e*B + b) * OH + oh
-  const int OH = H / pool_h;
-  const long n = nh / OH; const int oh = (int)(nh % OH);
-  float sc[8], sh[8], m[8];
+__global__ void __launch_bounds__(256)
+bn_relu_pool_kernel(const AT* __restrict__ x, const float* __restrict__ ss /*[I,512,2]*/, AT* __restrict__ y,
+                    unsigned rows_out /* per expert: B * OH * 64 */, int H, int pool_h) {
+  const int e = blockIdx.y;
+  const int c = (threadIdx.x & 63) * 8;
+  float sc[8], sh[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { sc[j] = ss[((long)e * 512 + c + j) * 2]; sh[j] = ss[((long)e * 512 + c + j) * 2 + 1]; m[j] = 0.f; }
-  for (int a = 0; a < pool_h; ++a) {
-    float v[8];
-    load8<AT>(x + (((n * H + oh * pool_h + a) * 64) + w) * 512 + c, v);
+  for (int j = 0; j < 8; ++j) { sc[j] = ss[((size_t)e * 512 + c + j) * 2]; sh[j] = ss[((size_t)e * 512 + c + j) * 2 + 1]; }
+  const unsigned OH = H / pool_h;
+  const AT* xe = x + (size_t)e * rows_out * pool_h * 512;
+  AT* ye = y + (size_t)e * rows_out * 512;
+  for (unsigned orow = blockIdx.x * 4 + (threadIdx.x >> 6); orow < rows_out; orow += gridDim.x * 4) {
+    const unsigned w = orow & 63, nh = orow >> 6;          // nh = b * OH + oh
+    const unsigned n = nh / OH, oh = nh % OH;
+    float m[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], fmaf(v[j], sc[j], sh[j]));     // max(0, .) == ReLU
+    for (int j = 0; j < 8; ++j) m[j] = 0.f;
+    for (int a = 0; a < pool_h; ++a) {
+      float v[8];
+      load8<AT>(xe + ((size_t)((n * H + oh * pool_h + a) * 64) + w) * 512 + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], fmaf(v[j], sc[j], sh[j]));     // max(0, .) == ReLU
+    }
+    store8<AT>(ye + (size_t)orow * 512 + c, m);
   }
-  store8<AT>(y + i * 8, m);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -213,13 +221,13 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __ex
 
 template <typename AT>
 __global__ void lstm_cell_kernel(const float* __restrict__ gates, const AT* __restrict__ pre, float* __restrict__ cst,
-                                 AT* __restrict__ hst, AT* __restrict__ rec, int I, int B, int s, long total) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+                                 AT* __restrict__ hst, AT* __restrict__ rec, int I, int B, int s, unsigned total) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int j = (int)(i % LH);
-  const long gb = i / LH;
-  const int b = (int)(gb % B);
-  const int g = (int)(gb / B);
+  const unsigned gb = i / LH;
+  const int b = (int)(gb % (unsigned)B);
+  const int g = (int)(gb / (unsigned)B);
   const int e = g >> 1, dir = g & 1;
   const int t = dir ? CT - 1 - s : s;
   const AT* pp = pre + (((long)e * B + b) * CTP + t) * (8 * LH) + dir * 4 * LH + j;
@@ -303,7 +311,8 @@ int conv_layer(const ConvSpec& c, int I, int B, const AT* in, const float* W32, 
 template <typename AT>
 int launch_pool(const AT* in, AT* out, long N, int H, int W, int C, int ph, int pw, cudaStream_t st) {
   const long total8 = N * (H / ph) * (W / pw) * C / 8;
-  pool_kernel<AT><<<cdiv(total8, 256), 256, 0, st>>>(in, out, H, W, C, ph, pw, total8);
+  MRNB_CHECK_ARG(total8 < (1L << 31) && N * H * W < (1L << 31), "crnn_forward: batch too large for the pooling kernels");
+  pool_kernel<AT><<<cdiv(total8, 256), 256, 0, st>>>(in, out, H, W, C, ph, pw, (unsigned)total8);
   MRNB_CHECK_LAUNCH("pool_kernel");
   return MRNB_OK;
 }
@@ -382,9 +391,9 @@ int crnn_forward_t(const MrnbCrnnPack& P, const float* image, int B, int bn_batc
       MRNB_CHECK_LAUNCH("bn_finalize_kernel");
       // layer 0: 12-13 -> X [4,64,512]; layer 1: 15-17 (+ MaxPool (2,1)) -> Y [2,64,512]
       const int pool_h = layer == 0 ? 1 : 2;
-      const long rows_out = (long)B * (4 / pool_h) * 64;
-      const long total8 = (long)I * rows_out * 64;
-      bn_relu_pool_kernel<AT><<<cdiv(total8, 256), 256, 0, st>>>(raw, ss, layer == 0 ? X : Y, rows_out, 4, pool_h, total8);
+      const unsigned rows_out = (unsigned)B * (4 / pool_h) * 64;
+      bn_relu_pool_kernel<AT><<<dim3(rows_out / 4 < 1184 ? rows_out / 4 : 1184, I), 256, 0, st>>>(raw, ss, layer == 0 ? X : Y, rows_out,
+                                                                                                 4, pool_h);
       MRNB_CHECK_LAUNCH("bn_relu_pool_kernel");
       mrnb_prof_end(MRNB_PROF_CONV, st);
     }
@@ -416,7 +425,7 @@ int crnn_forward_t(const MrnbCrnnPack& P, const float* image, int B, int bn_batc
         MRNB_TRY(linear<AT>(hh, st));
       }
       mrnb_prof_begin(MRNB_PROF_MISC, st, 0.0, 0.0);
-      lstm_cell_kernel<AT><<<cdiv(cells, 256), 256, 0, st>>>(gates, pre, cst, hst, rec, I, B, s, cells);
+      lstm_cell_kernel<AT><<<cdiv(cells, 256), 256, 0, st>>>(gates, pre, cst, hst, rec, I, B, s, (unsigned)cells);
       MRNB_CHECK_LAUNCH("lstm_cell_kernel");
       mrnb_prof_end(MRNB_PROF_MISC, st);
     }

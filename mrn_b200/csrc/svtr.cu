@@ -123,7 +123,7 @@ conv0_kernel(const float* __restrict__ img, const float* __restrict__ w /*[I,32,
              int B) {
   // grid: (16 output rows, B, I); block: 128 threads = 128 output columns
   const int oh = blockIdx.x, b = blockIdx.y, e = blockIdx.z, ow = threadIdx.x;
-  __shared__ float sw[32 * 36];
+  __shared__ __align__(16) float sw[32 * 36];
   __shared__ float sb[32];
   __shared__ float red[4][32][2];
   for (int k = threadIdx.x; k < 32 * 36; k += 128) sw[k] = w[(long)e * 32 * 36 + k];
@@ -142,26 +142,42 @@ conv0_kernel(const float* __restrict__ img, const float* __restrict__ w /*[I,32,
       }
   OT* o = out + ((((long)e * B + b) * 16 + oh) * 128 + ow) * 32;
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  for (int oc0 = 0; oc0 < 32; oc0 += 4) {
-    float r[4];
+  // 36 taps x 32 channels per thread; the weights come from shared memory as broadcast 16-byte loads (9 per channel)
+  float r[32];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float a = sb[oc0 + u];
+  for (int oc = 0; oc < 32; ++oc) {
+    const float4* w4 = reinterpret_cast<const float4*>(sw + oc * 36);
+    float a = sb[oc];
 #pragma unroll
-      for (int k = 0; k < 36; ++k) a = fmaf(in[k], sw[(oc0 + u) * 36 + k], a);
-      r[u] = a;
+    for (int k4 = 0; k4 < 9; ++k4) {
+      const float4 wv = w4[k4];
+      a = fmaf(in[k4 * 4], wv.x, a); a = fmaf(in[k4 * 4 + 1], wv.y, a);
+      a = fmaf(in[k4 * 4 + 2], wv.z, a); a = fmaf(in[k4 * 4 + 3], wv.w, a);
     }
+    r[oc] = a;
+  }
+#pragma unroll
+  for (int oc0 = 0; oc0 < 32; oc0 += 8) {
     if constexpr (sizeof(OT) == 4) {
-      *reinterpret_cast<float4*>(o + oc0) = make_float4(r[0], r[1], r[2], r[3]);
+      *reinterpret_cast<float4*>(o + oc0) = make_float4(r[oc0], r[oc0 + 1], r[oc0 + 2], r[oc0 + 3]);
+      *reinterpret_cast<float4*>(o + oc0 + 4) = make_float4(r[oc0 + 4], r[oc0 + 5], r[oc0 + 6], r[oc0 + 7]);
     } else {
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(r[0], r[1]), h1 = __floats2bfloat162_rn(r[2], r[3]);
-      *reinterpret_cast<uint2*>(o + oc0) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-    }
-    if (stats) {
+      uint32_t pk[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float s1 = warp_sum(r[u]), s2 = warp_sum(r[u] * r[u]);
-        if (lane == 0) { red[wp][oc0 + u][0] = s1; red[wp][oc0 + u][1] = s2; }
+        __nv_bfloat162 h = __floats2bfloat162_rn(r[oc0 + 2 * u], r[oc0 + 2 * u + 1]);
+        pk[u] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(o + oc0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    if (stats) {
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { v[u] = r[oc0 + u]; v[8 + u] = r[oc0 + u] * r[oc0 + u]; }
+      const float tot = warp_reduce16(v, lane);
+      if ((lane & 1) == 0) {
+        const int idx = (lane >> 1) & 15;
+        red[wp][oc0 + (idx & 7)][idx >> 3] = tot;
       }
     }
   }
