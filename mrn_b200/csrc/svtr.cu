@@ -24,10 +24,14 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // LayerNorm over the channel axis: one warp per row.  gamma/beta are [groups, D]; group = row / rows_per_group.
 // ------------------------------------------------------------------------------------------------
+// Optional second LayerNorm (y2, bf16): y2 = LN_2(LN_1(x)) in the same pass -- the SubSample norm followed by the next
+// stage's first norm1 (modules/svtr.py:311 then :201).
 template <typename OT, int D>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x, long x_gs, OT* y, long y_gs, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, long rows, long rows_per_group, float eps) {
+                 const float* __restrict__ beta, long rows, long rows_per_group, float eps,
+                 __nv_bfloat16* __restrict__ y2 = nullptr, long y2_gs = 0, const float* __restrict__ gamma2 = nullptr,
+                 const float* __restrict__ beta2 = nullptr, float eps2 = 0.f) {
   constexpr int VPT = D / 32;
   constexpr int RPW = 4;                       // rows per warp: all loads are issued before the first reduction
   const long row0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
@@ -76,6 +80,7 @@ layernorm_kernel(const float* x, long x_gs, OT* y, long y_gs, const float* __res
         const float4 g4 = *reinterpret_cast<const float4*>(g + idx), b4 = *reinterpret_cast<const float4*>(bt + idx);
         const float o0 = (v[r][c * 4] - mean) * rstd * g4.x + b4.x, o1 = (v[r][c * 4 + 1] - mean) * rstd * g4.y + b4.y;
         const float o2 = (v[r][c * 4 + 2] - mean) * rstd * g4.z + b4.z, o3 = (v[r][c * 4 + 3] - mean) * rstd * g4.w + b4.w;
+        v[r][c * 4] = o0; v[r][c * 4 + 1] = o1; v[r][c * 4 + 2] = o2; v[r][c * 4 + 3] = o3;      // kept for the second norm
         if constexpr (sizeof(OT) == 4) {
           *reinterpret_cast<float4*>(yr + idx) = make_float4(o0, o1, o2, o3);
         } else {
@@ -93,6 +98,27 @@ layernorm_kernel(const float* x, long x_gs, OT* y, long y_gs, const float* __res
         *reinterpret_cast<uint32_t*>(yr + idx) = *reinterpret_cast<uint32_t*>(&h0);
       }
     }
+    if constexpr (VPT >= 4) {
+      if (y2) {                                   // warp-uniform
+        float s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) s2 += v[r][j];
+        const float mean2 = warp_sum(s2) * (1.0f / D);
+        float q2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) { const float d = v[r][j] - mean2; q2 = fmaf(d, d, q2); }
+        const float rstd2 = rsqrtf(warp_sum(q2) * (1.0f / D) + eps2);
+        __nv_bfloat16* y2r = y2 + grp * y2_gs + (row % rows_per_group) * D;
+#pragma unroll
+        for (int c = 0; c < VPT / 4; ++c) {
+          const int idx = c * 128 + lane * 4;
+          const float4 g4 = *reinterpret_cast<const float4*>(gamma2 + grp * D + idx), b4 = *reinterpret_cast<const float4*>(beta2 + grp * D + idx);
+          __nv_bfloat162 h0 = __floats2bfloat162_rn((v[r][c * 4] - mean2) * rstd2 * g4.x + b4.x, (v[r][c * 4 + 1] - mean2) * rstd2 * g4.y + b4.y);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn((v[r][c * 4 + 2] - mean2) * rstd2 * g4.z + b4.z, (v[r][c * 4 + 3] - mean2) * rstd2 * g4.w + b4.w);
+          *reinterpret_cast<uint2*>(y2r + idx) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        }
+      }
+    }
   }
 }
 
@@ -108,6 +134,19 @@ int launch_layernorm(const float* x, long x_gs, OT* y, long y_gs, const float* g
     case 512: layernorm_kernel<OT, 512><<<grid, 256, 0, st>>>(x, x_gs, y, y_gs, gamma, beta, rows, rows_per_group, eps); break;
     default: mrnb_set_error("layernorm: unsupported D=%d", D); return MRNB_ERR_UNSUPPORTED;
   }
+  MRNB_CHECK_LAUNCH("layernorm_kernel");
+  return MRNB_OK;
+}
+
+// y = LN_1(x) in place-compatible fp32, y2 = LN_2(y) in bf16 (D = 128 / 256)
+int launch_layernorm2(const float* x, long x_gs, float* y, long y_gs, const float* gamma, const float* beta, float eps,
+                      __nv_bfloat16* y2, long y2_gs, const float* gamma2, const float* beta2, float eps2, long rows,
+                      long rows_per_group, int D, cudaStream_t st) {
+  const int grid = cdiv(rows, 8 * 4);
+  MrnbProfScope prof(MRNB_PROF_LN, st, 0.0, (double)rows * D * (4 + 4 + 2));
+  if (D == 128) layernorm_kernel<float, 128><<<grid, 256, 0, st>>>(x, x_gs, y, y_gs, gamma, beta, rows, rows_per_group, eps, y2, y2_gs, gamma2, beta2, eps2);
+  else if (D == 256) layernorm_kernel<float, 256><<<grid, 256, 0, st>>>(x, x_gs, y, y_gs, gamma, beta, rows, rows_per_group, eps, y2, y2_gs, gamma2, beta2, eps2);
+  else { mrnb_set_error("layernorm2: unsupported D=%d", D); return MRNB_ERR_UNSUPPORTED; }
   MRNB_CHECK_LAUNCH("layernorm_kernel");
   return MRNB_OK;
 }
@@ -304,10 +343,12 @@ bn_stats_rows_kernel(const float* __restrict__ x, long rows, double* __restrict_
 
 // tokens: x[e,b,n,c] = GELU(BN(conv1 raw)) + pos_embed[e,n,c]      (svtr.py:246-254,511)
 __global__ void embed_kernel(const float* __restrict__ raw, const float* __restrict__ ss1 /*[I,64,2]*/,
-                             const float* __restrict__ pos /*[I,512,64]*/, float* __restrict__ x, long per_expert) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;     // float4 index
+                             const float* __restrict__ pos /*[I,512,64]*/, float* __restrict__ x, long per_expert,
+                             __nv_bfloat16* __restrict__ ln_out /* optional: LN1 of blocks1.0, [I][rows][64] */,
+                             const float* __restrict__ ln_gamma /*[I,64]*/, const float* __restrict__ ln_beta, float ln_eps) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;     // float4 index; a token row = 16 consecutive threads
   const int e = blockIdx.y;
-  if (i * 4 >= per_expert) return;
+  if (i * 4 >= per_expert) return;                                // per_expert % 1024 == 0: whole warps leave together
   const long off = (long)e * per_expert + i * 4;
   const int c = (int)((i * 4) % 64);
   const long n = ((i * 4) / 64) % 512;
@@ -320,6 +361,21 @@ __global__ void embed_kernel(const float* __restrict__ raw, const float* __restr
   o.z = gelu_erf(fmaf(r.z, ss[4], ss[5])) + p.z;
   o.w = gelu_erf(fmaf(r.w, ss[6], ss[7])) + p.w;
   *reinterpret_cast<float4*>(x + off) = o;
+  if (ln_out) {
+    float s = (o.x + o.y) + (o.z + o.w);
+#pragma unroll
+    for (int k = 8; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+    const float mean = s * (1.0f / 64);
+    const float d0 = o.x - mean, d1 = o.y - mean, d2 = o.z - mean, d3 = o.w - mean;
+    float q = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
+#pragma unroll
+    for (int k = 8; k > 0; k >>= 1) q += __shfl_xor_sync(0xffffffffu, q, k);
+    const float rstd = rsqrtf(q * (1.0f / 64) + ln_eps);
+    const float4 g4 = *reinterpret_cast<const float4*>(ln_gamma + e * 64 + c), b4 = *reinterpret_cast<const float4*>(ln_beta + e * 64 + c);
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(d0 * rstd * g4.x + b4.x, d1 * rstd * g4.y + b4.y);
+    __nv_bfloat162 h1 = __floats2bfloat162_rn(d2 * rstd * g4.z + b4.z, d3 * rstd * g4.w + b4.w);
+    *reinterpret_cast<uint2*>(ln_out + off) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -494,6 +550,7 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
   AT* featat = W.take<AT>((size_t)I * Bc * 64 * 256);
   constexpr bool F32 = sizeof(AT) == 4;
 
+  bool ln1_ready = false;      // the first norm1 of the coming stage has already been written to lnout
   // ---- patch embedding on the full batch (train-mode BN needs whole-batch statistics)
   double* st0 = stats; double* st1 = stats + (size_t)I * 32 * 2;
   float* ss0 = ss; float* ss1 = ss + (size_t)I * 32 * 2;
@@ -553,7 +610,11 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
   MRNB_CHECK_LAUNCH("bn_finalize_kernel");
   {
     const long per_expert = (long)B * 32768;
-    embed_kernel<<<dim3(cdiv(per_expert / 4, 256), I), 256, 0, st>>>(conv1, ss1, P.p[MRNB_P_POS_EMBED], xall, per_expert);
+    // tensor-core mode without batch chunking: blocks1.0.norm1 is emitted here as well (one pass over the tokens)
+    ln1_ready = sizeof(AT) == 2 && Bc == B;
+    embed_kernel<<<dim3(cdiv(per_expert / 4, 256), I), 256, 0, st>>>(
+        conv1, ss1, P.p[MRNB_P_POS_EMBED], xall, per_expert, ln1_ready ? reinterpret_cast<__nv_bfloat16*>(lnout) : nullptr,
+        P.p[MRNB_P_BLOCK0 + MRNB_PB_NORM1_W], P.p[MRNB_P_BLOCK0 + MRNB_PB_NORM1_B], 1e-6f);
     MRNB_CHECK_LAUNCH("embed_kernel");
   }
   mrnb_prof_end(MRNB_PROF_CONV, st);
@@ -585,9 +646,10 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
         // tensor-core mode, d <= 128: the residual GEMMs (proj, fc2) own whole rows and emit the following LayerNorm
         const bool fuse_ln = sizeof(AT) == 2 && d <= 128 && (rows_g % 128) == 0;
         // LN1 (per expert: x groups are strided, outputs packed [I, rows_g, d]); fused into the previous block's fc2
-        if (!(fuse_ln && j > 0))
+        if (!(fuse_ln && j > 0) && !(j == 0 && ln1_ready))
           MRNB_TRY(launch_layernorm<AT>(x, x_gs, lnout, rows_g * d, P.p[pb + MRNB_PB_NORM1_W], P.p[pb + MRNB_PB_NORM1_B],
                                         rows_g * I, rows_g, d, 1e-6f, st));
+        if (j == 0) ln1_ready = false;
         LinearArgs a{};
         a.A = lnout; a.lda = d; a.a_gstride = rows_g * d;
         a.W32 = P.p[pb + MRNB_PB_QKV_W]; a.W16 = P.h[pb + MRNB_PB_QKV_W]; a.w_gstride = (long)3 * d * d;
@@ -715,8 +777,17 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
       }
       if (sidx < 2) {
         // LN in place (fp32 -> fp32) : next stage's residual stream
-        MRNB_TRY(launch_layernorm<float>(cvx, cv_gs, cvx, cv_gs, P.p[ps + MRNB_PS_NORM_W], P.p[ps + MRNB_PS_NORM_B],
-                                         orows_g * I, orows_g, Co, 1e-5f, st));
+        if constexpr (sizeof(AT) == 2) {
+          // SubSample norm in place + the next stage's first norm1 in the same pass
+          const int pn = MRNB_P_BLOCK0 + (blk) * MRNB_PB_COUNT;      // blk already points at the next stage's first block
+          MRNB_TRY(launch_layernorm2(cvx, cv_gs, cvx, cv_gs, P.p[ps + MRNB_PS_NORM_W], P.p[ps + MRNB_PS_NORM_B], 1e-5f,
+                                     reinterpret_cast<__nv_bfloat16*>(lnout), orows_g * Co, P.p[pn + MRNB_PB_NORM1_W],
+                                     P.p[pn + MRNB_PB_NORM1_B], 1e-6f, orows_g * I, orows_g, Co, st));
+          ln1_ready = true;
+        } else {
+          MRNB_TRY(launch_layernorm<float>(cvx, cv_gs, cvx, cv_gs, P.p[ps + MRNB_PS_NORM_W], P.p[ps + MRNB_PS_NORM_B],
+                                           orows_g * I, orows_g, Co, 1e-5f, st));
+        }
         x = cvx; x_gs = cv_gs;
       } else {
         // last merge: LN -> AT [I, bc*64, 512] visual feature (model.py:88-95 relabel), then Linear 512->256
