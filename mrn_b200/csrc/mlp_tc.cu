@@ -83,6 +83,7 @@ struct MlpParams {
   float* x; long x_gs;                                        // fp32 residual stream, in place: [g][rows][D]
   const float* rowscale; int rows_per_scale; long rowscale_gs;
   __nv_bfloat16* ln_out; long ln_gs; const float* ln_gamma; const float* ln_beta; float ln_eps;   // optional (D <= 128)
+  __nv_bfloat16* cast_out;   // optional bf16 copy of the new rows, [g][M][D] (stride ln_gs)
   int m_tiles, total_tiles;
   unsigned long long* trace;      // optional debug timeline (CTA 0), see MRNB_TRACE
 };
@@ -315,6 +316,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const float rs = ep.rowscale ? ep.rowscale[(long)g * ep.rowscale_gs + m0 / ep.rows_per_scale] : 1.0f;
       float4 keep[LNF ? NPASS * 8 : 1];
+      __nv_bfloat16* crow = (!LNF && ep.cast_out)
+                                ? ep.cast_out + (long)g * ep.ln_gs + (long)(m0 + q * 32 + rsel) * D + ch * OW + p8 * 4 : nullptr;
 #pragma unroll
       for (int ps = 0; ps < NPASS; ++ps) {
         uint32_t v[32];
@@ -343,6 +346,10 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           x.z = fmaf(x.z + b4.z, rs, rv[itr].z); x.w = fmaf(x.w + b4.w, rs, rv[itr].w);
           *reinterpret_cast<float4*>(xrow + ps * 32 + (long)itr * 4 * D) = x;
           if (LNF) keep[ps * 8 + itr] = x;
+          if (!LNF && crow) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
+            *reinterpret_cast<uint2*>(crow + ps * 32 + (long)itr * 4 * D) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+          }
         }
         if (ps + 1 < NPASS) {
 #pragma unroll
@@ -444,6 +451,7 @@ int launch_mlp(const MrnbMlp& p, cudaStream_t st) {
   ep.b1 = p.b1; ep.b2 = p.b2; ep.b_gs1 = 4 * D; ep.b_gs2 = D;
   ep.x = p.x; ep.x_gs = p.x_gstride;
   ep.rowscale = p.rowscale; ep.rows_per_scale = p.rows_per_scale > 0 ? p.rows_per_scale : 1; ep.rowscale_gs = p.rowscale_gstride;
+  ep.cast_out = (__nv_bfloat16*)p.cast_out;
   ep.ln_out = (__nv_bfloat16*)p.ln_out; ep.ln_gs = (long)p.M * D; ep.ln_gamma = p.ln_gamma; ep.ln_beta = p.ln_beta; ep.ln_eps = p.ln_eps;
   ep.m_tiles = p.M / BM; ep.total_tiles = ep.m_tiles * p.groups;
   ep.trace = (unsigned long long*)p.trace;
@@ -469,6 +477,7 @@ int mrnb_mlp_tc(const MrnbMlp& p, cudaStream_t st) {
   MRNB_CHECK_ARG(p.M % BM == 0 && (p.D == 64 || p.D == 128 || p.D == 256), "mlp_tc: need M %% 128 == 0 and D in {64,128,256}");
   MRNB_CHECK_ARG(!p.rowscale || p.rows_per_scale % BM == 0, "mlp_tc: DropPath scale must be uniform per 128-row tile");
   MRNB_CHECK_ARG(!p.ln_out || (p.D <= 128 && p.ln_gamma && p.ln_beta), "mlp_tc: fused LayerNorm needs D <= 128");
+  MRNB_CHECK_ARG(!(p.ln_out && p.cast_out), "mlp_tc: cast_out and ln_out are exclusive");
   MRNB_CHECK_ARG(p.x_gstride % 4 == 0, "mlp_tc: misaligned residual stream");
   const double M = (double)p.M * p.groups;
   MrnbProfScope prof(MRNB_PROF_MLP, st, 16.0 * M * p.D * p.D, M * p.D * (2.0 + 8.0 + (p.ln_out ? 2.0 : 0.0)));

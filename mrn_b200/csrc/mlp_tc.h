@@ -11,6 +11,7 @@ struct MrnbMlp {
   float* x; long x_gstride;                       // fp32 residual stream [g][M][D], updated in place
   const float* rowscale; int rows_per_scale; long rowscale_gstride;    // DropPath multipliers (tile-uniform)
   void* ln_out; const float* ln_gamma; const float* ln_beta; float ln_eps;   // optional next LayerNorm (D <= 128), may alias A
+  void* cast_out;         // optional bf16 copy of the updated x [groups][M][D] (feeds the SubSample implicit GEMM); not with ln_out
   int M, D, groups;
   void* trace;            // optional device buffer [10][64] u64: debug timeline of CTA 0 (tools/mlp_trace.py)
 };

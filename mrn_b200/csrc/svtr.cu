@@ -493,8 +493,10 @@ __global__ void cast_groups_kernel(const float* __restrict__ x, long x_gs, __nv_
   *reinterpret_cast<uint2*>(y + i * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
 }
 
-// features [I, Bc, T, D] (expert-major, AT) -> router layout [Bc, I, T, D] fp32   (torch.stack(...,1), model.py:400)
-__global__ void feature_scatter_kernel(const float* __restrict__ src, float* __restrict__ dst, int I, int Bc, long TD) {
+// features [I, Bc, T, D] (expert-major, fp32) -> router layout [Bc, I, T, D] fp32   (torch.stack(...,1), model.py:400)
+// and, in the same pass, the bf16 copy (expert-major) that feeds the classifier heads
+__global__ void feature_scatter_kernel(const float* __restrict__ src, float* __restrict__ dst, __nv_bfloat16* __restrict__ src16,
+                                       int I, int Bc, long TD) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = (long)I * Bc * TD / 4;
   if (i >= total) return;
@@ -502,7 +504,12 @@ __global__ void feature_scatter_kernel(const float* __restrict__ src, float* __r
   const long td = e4 % TD;
   const long b = (e4 / TD) % Bc;
   const long e = e4 / (TD * Bc);
-  *reinterpret_cast<float4*>(dst + (b * I + e) * TD + td) = *reinterpret_cast<const float4*>(src + e4);
+  const float4 v = *reinterpret_cast<const float4*>(src + e4);
+  if (dst) *reinterpret_cast<float4*>(dst + (b * I + e) * TD + td) = v;
+  if (src16) {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(src16 + e4) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+  }
 }
 
 template <typename AT>
@@ -707,6 +714,7 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
             const int pn = pb + MRNB_PB_COUNT;
             mp.ln_out = lnout; mp.ln_gamma = P.p[pn + MRNB_PB_NORM1_W]; mp.ln_beta = P.p[pn + MRNB_PB_NORM1_B]; mp.ln_eps = 1e-6f;
           }
+          if (j + 1 == DEPTH[sidx]) mp.cast_out = att;      // bf16 copy of the stage output = A operand of the SubSample conv
           mp.M = (int)rows_g; mp.D = d; mp.groups = I;
           MRNB_TRY(mrnb_mlp_tc(mp, st));
         } else {
@@ -744,10 +752,7 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
       const long cv_gs = (cv == xall) ? (long)B * 32768 : (long)bc * 32768;
       if constexpr (sizeof(AT) == 2) {
         // implicit GEMM: bf16 copy of the NHWC residual stream, A tiles gathered by TMA (zero fill = padding)
-        const long tot = (long)bc * 32768;
-        cast_groups_kernel<<<cdiv(tot / 4 * I, 256), 256, 0, st>>>(x, x_gs, reinterpret_cast<__nv_bfloat16*>(att), tot / 4,
-                                                                    tot / 4 * I);
-        MRNB_CHECK_LAUNCH("cast_groups_kernel");
+        // (att already holds the bf16 copy of x: written by the last block's fused-MLP epilogue)
         MrnbTcGemm g{};
         g.A = att; g.W = P.h[ps + MRNB_PS_CONV_W]; g.ldw = 9 * d; g.w_gstride = (long)Co * 9 * d;
         g.bias = P.p[ps + MRNB_PS_CONV_B]; g.bias_gstride = Co;
@@ -806,15 +811,12 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
     {
       const long TD = 64 * 256;
       const long total4 = (long)I * bc * TD / 4;
-      if (features) {
-        feature_scatter_kernel<<<cdiv(total4, 256), 256, 0, st>>>(feat32, features + (size_t)b0 * I * TD, I, bc, TD);
-        MRNB_CHECK_LAUNCH("feature_scatter_kernel");
-      }
       const void* fa = feat32;
-      if (!F32) {
-        cast_kernel<AT><<<cdiv(total4 * 4, 256), 256, 0, st>>>(feat32, featat, total4 * 4);
-        MRNB_CHECK_LAUNCH("cast_kernel");
-        fa = featat;
+      if (features || !F32) {
+        feature_scatter_kernel<<<cdiv(total4, 256), 256, 0, st>>>(feat32, features ? features + (size_t)b0 * I * TD : nullptr,
+                                                                  F32 ? nullptr : reinterpret_cast<__nv_bfloat16*>(featat), I, bc, TD);
+        MRNB_CHECK_LAUNCH("feature_scatter_kernel");
+        if (!F32) fa = featat;
       }
       if (logits) {
         for (int e = 0; e < I; ++e) {
