@@ -141,10 +141,12 @@ enum {
   MRNB_C_LSTM0 = 20,    /* 2 layers x MRNB_CL_COUNT slots: SequenceModeling.0, SequenceModeling.1 */
   MRNB_C_COUNT = 20 + 2 * 5
 };
-enum { /* per BidirectionalLSTM, Kin = 512 (layer 0) / 256 (layer 1), gate order i,f,g,o */
-  MRNB_CL_WIH = 0, /* [I,2048,Kin]   rows 0..1023 rnn.weight_ih_l0, 1024..2047 rnn.weight_ih_l0_reverse */
-  MRNB_CL_WHH,     /* [I,2,1024,256] rnn.weight_hh_l0, rnn.weight_hh_l0_reverse */
-  MRNB_CL_BIAS,    /* [I,2048]       bias_ih + bias_hh, forward then reverse */
+enum { /* per BidirectionalLSTM, Kin = 512 (layer 0) / 256 (layer 1).  The gate axis is INTERLEAVED per hidden unit:
+          packed row 4*j + k holds nn.LSTM row k*256 + j (k = i,f,g,o), so the four gates of a unit are adjacent columns
+          of the recurrent GEMM and its epilogue can apply the cell */
+  MRNB_CL_WIH = 0, /* [I,2048,Kin]   rows 0..1023 rnn.weight_ih_l0 (interleaved), 1024..2047 rnn.weight_ih_l0_reverse */
+  MRNB_CL_WHH,     /* [I,2,1024,256] rnn.weight_hh_l0, rnn.weight_hh_l0_reverse (interleaved rows) */
+  MRNB_CL_BIAS,    /* [I,2048]       bias_ih + bias_hh (interleaved), forward then reverse */
   MRNB_CL_LIN_W,   /* [I,256,512]    linear.weight */
   MRNB_CL_LIN_B,   /* [I,256] */
   MRNB_CL_COUNT

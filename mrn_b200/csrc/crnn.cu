@@ -214,7 +214,7 @@ bn_relu_pool_kernel(const AT* __restrict__ x, const float* __restrict__ ss /*[I,
 
 // ------------------------------------------------------------------------------------------------
 // LSTM cell, step s of every (expert, direction) chain.  gates [2I][B][4H] fp32 = h_{t-1} W_hh^T (ignored at s = 0),
-// pre [I][B*64][2*4H] AT = x W_ih^T + b_ih + b_hh for both directions; gate order i, f, g, o (nn.LSTM).
+// pre [I][B*64][2*4H] AT = x W_ih^T + b_ih + b_hh for both directions; gates i, f, g, o (nn.LSTM) interleaved per unit.
 // Writes c (fp32), h (AT, the next step's GEMM operand) and the [fwd | bwd] output row rec [I][B*64][2H].
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
@@ -230,15 +230,15 @@ __global__ void lstm_cell_kernel(const float* __restrict__ gates, const AT* __re
   const int g = (int)(gb / (unsigned)B);
   const int e = g >> 1, dir = g & 1;
   const int t = dir ? CT - 1 - s : s;
-  const AT* pp = pre + (((long)e * B + b) * CTP + t) * (8 * LH) + dir * 4 * LH + j;
+  // gate axis interleaved: column 4*j + {i, f, g, o} (the pack re-orders the LSTM weight rows accordingly)
+  const AT* pp = pre + (((long)e * B + b) * CTP + t) * (8 * LH) + dir * 4 * LH + 4 * j;
   float a[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) a[k] = to_f32<AT>(pp[k * LH]);
+  for (int k = 0; k < 4; ++k) a[k] = to_f32<AT>(pp[k]);
   float cprev = 0.f;
   if (s > 0) {
-    const float* gp = gates + ((long)g * B + b) * (4 * LH) + j;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) a[k] += gp[k * LH];
+    const float4 gq = *reinterpret_cast<const float4*>(gates + ((long)g * B + b) * (4 * LH) + 4 * j);
+    a[0] += gq.x; a[1] += gq.y; a[2] += gq.z; a[3] += gq.w;
     cprev = cst[i];
   }
   const float c = sigmoid_f(a[1]) * cprev + sigmoid_f(a[0]) * tanhf(a[2]);
@@ -415,7 +415,24 @@ int crnn_forward_t(const MrnbCrnnPack& P, const float* image, int B, int bn_batc
     ip.M = (int)rowsT; ip.N = 8 * LH; ip.K = Kin; ip.groups = I;
     MRNB_TRY(linear<AT>(ip, st));
     const long cells = (long)2 * I * B * LH;
+    // tensor-core mode with whole 128-sample tiles: the cell runs inside the epilogue of the recurrent GEMM
+    const bool fused_cell = !F32 && (B % 128) == 0;
     for (int s = 0; s < CT; ++s) {
+      if (s > 0 && fused_cell) {
+        MrnbTcGemm g{};
+        g.A = hst; g.lda = LH; g.a_gstride = (long)B * LH;
+        g.W = P.h[pl + MRNB_CL_WHH]; g.ldw = LH; g.w_gstride = 4L * LH * LH;
+        g.out = gates; g.ldo = 4 * LH; g.o_gstride = (long)B * 4 * LH; g.out_f32 = 1;      // not written in this mode
+        g.M = B; g.N = 4 * LH; g.K = LH; g.groups = 2 * I; g.rows_per_scale = 1;
+        g.lstm.enabled = 1; g.lstm.B = B;
+        g.lstm.pre = pre; g.lstm.pre_row = (long)CTP * 8 * LH; g.lstm.pre_e = (long)B * CTP * 8 * LH;
+        g.lstm.pre_off[0] = (long)s * 8 * LH; g.lstm.pre_off[1] = (long)(CT - 1 - s) * 8 * LH + 4 * LH;
+        g.lstm.cst = cst; g.lstm.hst = hst;
+        g.lstm.rec = rec; g.lstm.rec_row = (long)CTP * 2 * LH; g.lstm.rec_e = (long)B * CTP * 2 * LH;
+        g.lstm.rec_off[0] = (long)s * 2 * LH; g.lstm.rec_off[1] = (long)(CT - 1 - s) * 2 * LH + LH;
+        MRNB_TRY(mrnb_tc_gemm(g, st));
+        continue;
+      }
       if (s > 0) {
         LinearArgs hh{};
         hh.A = hst; hh.lda = LH; hh.a_gstride = (long)B * LH;

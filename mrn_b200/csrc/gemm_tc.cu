@@ -124,6 +124,7 @@ struct TcEpi {
   // implicit-GEMM convolution (see MrnbTcConv)
   int conv, rows_per_img, per_kh, cch, w_off, sh, imgs_per_group, ow_shift, pad_h;
   int relu;
+  MrnbTcLstm lstm;
 };
 
 constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each owning half of the tile columns
@@ -133,7 +134,14 @@ constexpr int STAGING_BYTES = EPI_WARPS * 32 * 32 * 4;    // 32x32 fp32 tile per
 // Persistent kernel: CTA c walks tiles c, c + gridDim.x, ... (n fastest so neighbouring CTAs share the A tile in L2).
 // The smem ring runs across tile boundaries, and the accumulator is double buffered in TMEM so the MMAs of tile i+1
 // overlap the epilogue of tile i.
-template <int BN, bool OUT_F32, bool GELU, bool LNF>
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int BN, bool OUT_F32, bool GELU, bool LNF, int MODE = 0>
 __global__ void __launch_bounds__(NTHREADS, LNF ? 1 : 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcEpi ep) {
   extern __shared__ uint8_t smem_raw[];
@@ -292,7 +300,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int itr = 0; itr < 8; ++itr) nx[itr] = *reinterpret_cast<const float4*>(ep.res + o0 + (ps + 1) * 32 + itr * ostep);
           }
-          if (OUT_F32) {
+          if constexpr (MODE == 1) {
+            // fused LSTM cell: x = (i, f, g, o) pre-activations of hidden unit j for sample b
+            const MrnbTcLstm& L = ep.lstm;
+            const int e = g >> 1, dir = g & 1;
+            const int col = colw + ps * 32;                    // interleaved gate column, multiple of 4
+            const int j = col >> 2;
+            const __nv_bfloat16* prep = reinterpret_cast<const __nv_bfloat16*>(L.pre) + (long)e * L.pre_e + L.pre_off[dir] + col;
+            __nv_bfloat16* recp = reinterpret_cast<__nv_bfloat16*>(L.rec) + (long)e * L.rec_e + L.rec_off[dir] + j;
+#pragma unroll
+            for (int itr = 0; itr < 8; ++itr) {
+              const int rl = itr * 4 + rsel;
+              const int b = m0 + q * 32 + rl;
+              float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((p8 ^ (rl & 7)) * 4));
+              const uint2 pv = *reinterpret_cast<const uint2*>(prep + (long)b * L.pre_row);
+              const __nv_bfloat162 p01 = *reinterpret_cast<const __nv_bfloat162*>(&pv.x), p23 = *reinterpret_cast<const __nv_bfloat162*>(&pv.y);
+              x.x += __low2float(p01); x.y += __high2float(p01); x.z += __low2float(p23); x.w += __high2float(p23);
+              const long ci = ((long)g * L.B + b) * 256 + j;
+              const float c = fmaf(sigmoid_fast(x.y), L.cst[ci], sigmoid_fast(x.x) * tanh_fast(x.z));
+              const float h = sigmoid_fast(x.w) * tanh_fast(c);
+              L.cst[ci] = c;
+              const __nv_bfloat16 hb = __float2bfloat16_rn(h);
+              reinterpret_cast<__nv_bfloat16*>(L.hst)[ci] = hb;
+              recp[(long)b * L.rec_row] = hb;
+            }
+          } else if (OUT_F32) {
             float* op = reinterpret_cast<float*>(ep.out) + o0 + ps * 32;
 #pragma unroll
             for (int itr = 0; itr < 8; ++itr) {
@@ -464,7 +496,7 @@ int make_conv_map(CUtensorMap* map, const void* ptr, const MrnbTcConv& c) {
   return MRNB_OK;
 }
 
-template <int BN, bool OUT_F32, bool GELU, bool LNF>
+template <int BN, bool OUT_F32, bool GELU, bool LNF, int MODE = 0>
 int launch_tc(const MrnbTcGemm& p, cudaStream_t st) {
   CUtensorMap tmA, tmW;
   if (p.conv.enabled) MRNB_TRY(make_conv_map(&tmA, p.A, p.conv));
@@ -481,13 +513,14 @@ int launch_tc(const MrnbTcGemm& p, cudaStream_t st) {
   ep.conv = p.conv.enabled; ep.rows_per_img = p.conv.rows_per_img; ep.per_kh = p.conv.per_kh; ep.cch = p.conv.cch;
   ep.w_off = p.conv.w_off; ep.sh = p.conv.sh; ep.imgs_per_group = p.conv.imgs_per_group;
   ep.ow_shift = p.conv.box_w == 128 ? 7 : 6; ep.pad_h = p.conv.pad_h; ep.relu = p.relu;
+  ep.lstm = p.lstm;
   ep.n_tiles = cdiv(p.N, BN); ep.m_tiles = cdiv(p.M, BM);
   ep.total_tiles = ep.n_tiles * ep.m_tiles * p.groups;
   const size_t smem = 1024 + (size_t)ep.stages * (A_STAGE_BYTES + BN * BK * 2) + STAGING_BYTES;
   static bool attr_set = false;
   static int num_sms = 148;
   if (!attr_set) {
-    cudaFuncSetAttribute(tc_gemm_kernel<BN, OUT_F32, GELU, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(tc_gemm_kernel<BN, OUT_F32, GELU, LNF, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          1024 + MAX_STAGES * (A_STAGE_BYTES + BN * BK * 2) + STAGING_BYTES);
     int dev = 0;
     cudaGetDevice(&dev);
@@ -496,7 +529,7 @@ int launch_tc(const MrnbTcGemm& p, cudaStream_t st) {
   }
   const int slots = (LNF ? 1 : 2) * num_sms;                                  // persistent CTAs: two per SM (one with fused LN)
   const int grid = ep.total_tiles < slots ? ep.total_tiles : slots;
-  tc_gemm_kernel<BN, OUT_F32, GELU, LNF><<<grid, NTHREADS, smem, st>>>(tmA, tmW, ep);
+  tc_gemm_kernel<BN, OUT_F32, GELU, LNF, MODE><<<grid, NTHREADS, smem, st>>>(tmA, tmW, ep);
   MRNB_CHECK_LAUNCH("tc_gemm_kernel");
   return MRNB_OK;
 }
@@ -511,6 +544,13 @@ int mrnb_tc_gemm(const MrnbTcGemm& p, cudaStream_t st) {
                      (double)p.groups * (2.0 * p.M * p.K + 2.0 * p.N * p.K + (double)p.M * p.N * (p.out_f32 ? 4 : 2) +
                                          (p.res ? 4.0 * p.M * p.N : 0.0)));
   const bool wide = p.N >= 128 && (p.N % 128 == 0 || p.N > 256);
+  if (p.lstm.enabled) {
+    MRNB_CHECK_ARG(p.M % BM == 0 && p.N % 128 == 0 && !p.bias && !p.res && !p.rowscale && !p.gelu && !p.relu && !p.ln_out &&
+                   p.lstm.pre && p.lstm.cst && p.lstm.hst && p.lstm.rec && p.lstm.pre_row % 4 == 0 && p.lstm.pre_e % 4 == 0 &&
+                   p.lstm.pre_off[0] % 4 == 0 && p.lstm.pre_off[1] % 4 == 0,
+                   "tc_gemm: fused LSTM cell needs M %% 128 == 0, N %% 128 == 0 and 8-byte aligned pre-activations");
+    return launch_tc<128, true, false, false, 1>(p, st);
+  }
   if (p.ln_out) {
     // fused LayerNorm: the tile must span whole rows and every tile must take the interior path
     MRNB_CHECK_ARG(p.out_f32 && !p.gelu && (p.N == 64 || p.N == 128) && p.M % BM == 0 && p.ldo % 4 == 0 && p.o_gstride % 4 == 0 &&

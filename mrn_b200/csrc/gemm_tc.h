@@ -19,6 +19,18 @@ struct MrnbTcConv {
   int box_w, pad_h;
 };
 
+// Fused LSTM-cell epilogue (crnn.cu): the GEMM is gates = h W_hh^T for group g = (expert, direction) with the gate axis
+// INTERLEAVED (column 4*j + {i,f,g,o}), so every float4 of the epilogue holds the four gates of one hidden unit.
+// The epilogue adds the input pre-activation, applies the cell and writes c (fp32), h (bf16, next step's operand) and
+// the [fwd | bwd] output row; nothing is written to `out`.  Needs M % 128 == 0.
+struct MrnbTcLstm {
+  int enabled;
+  const void* pre; long pre_row, pre_e, pre_off[2];     // bf16 [expert][sample*64 + t][2 * 1024]: element strides / per-direction offsets
+  float* cst; void* hst;                                  // [group][sample][256]
+  void* rec; long rec_row, rec_e, rec_off[2];           // bf16 [expert][sample*64 + t][512]
+  int B;
+};
+
 struct MrnbTcGemm {
   // out[g, m, n] = epi( sum_k A[g, m, k] * W[g, n, k] + bias[g, n] )     A, W: bf16, k-contiguous
   const void* A; long lda; long a_gstride;     // elements
@@ -31,6 +43,7 @@ struct MrnbTcGemm {
   int relu;                                            // ReLU on the biased accumulator (VGG convolutions)
   // optional fused LayerNorm of the fp32 output rows (N == 64 or 128): bf16 ln_out[g][m][N] = LN(out row) * gamma[g] + beta[g]
   void* ln_out; long ln_gstride; const float* ln_gamma; const float* ln_beta; float ln_eps;
+  MrnbTcLstm lstm;     // optional fused LSTM cell (replaces the store)
   MrnbTcConv conv;     // optional: A is an implicit im2col view (A / lda / a_gstride ignored except A as base pointer)
 };
 

@@ -334,16 +334,22 @@ class CrnnPack:
         for base, idx in ((L.C_BN4_W, 12), (L.C_BN5_W, 15)):
             for k, nm in enumerate(("weight", "bias", "running_mean", "running_var")):
                 put(base + k, stack(lambda i: get(i, cn + f"{idx}.{nm}")))
+        # gate axis interleaved per hidden unit: packed row 4*j + k <- nn.LSTM row k*256 + j (k = i,f,g,o)
+        perm = (torch.arange(4).view(1, 4) * 256 + torch.arange(256).view(256, 1)).reshape(-1).to(self.device)
+
+        def il(t):
+            return t.index_select(0, perm)
+
         for layer in range(2):
             q = f"model.SequenceModeling.{layer}."
             base = L.C_LSTM0 + layer * L.CL_COUNT
-            put(base + L.CL_WIH, stack(lambda i: torch.cat([get(i, q + "rnn.weight_ih_l0"),
-                                                            get(i, q + "rnn.weight_ih_l0_reverse")], 0)), gemm_weight=True)
-            put(base + L.CL_WHH, stack(lambda i: torch.stack([get(i, q + "rnn.weight_hh_l0"),
-                                                              get(i, q + "rnn.weight_hh_l0_reverse")], 0)), gemm_weight=True)
+            put(base + L.CL_WIH, stack(lambda i: torch.cat([il(get(i, q + "rnn.weight_ih_l0")),
+                                                            il(get(i, q + "rnn.weight_ih_l0_reverse"))], 0)), gemm_weight=True)
+            put(base + L.CL_WHH, stack(lambda i: torch.stack([il(get(i, q + "rnn.weight_hh_l0")),
+                                                              il(get(i, q + "rnn.weight_hh_l0_reverse"))], 0)), gemm_weight=True)
             put(base + L.CL_BIAS, stack(lambda i: torch.cat([
-                get(i, q + "rnn.bias_ih_l0") + get(i, q + "rnn.bias_hh_l0"),
-                get(i, q + "rnn.bias_ih_l0_reverse") + get(i, q + "rnn.bias_hh_l0_reverse")], 0)))
+                il(get(i, q + "rnn.bias_ih_l0") + get(i, q + "rnn.bias_hh_l0")),
+                il(get(i, q + "rnn.bias_ih_l0_reverse") + get(i, q + "rnn.bias_hh_l0_reverse"))], 0)))
             put(base + L.CL_LIN_W, stack(lambda i: get(i, q + "linear.weight")), gemm_weight=True)
             put(base + L.CL_LIN_B, stack(lambda i: get(i, q + "linear.bias")))
         for i in range(n_experts):

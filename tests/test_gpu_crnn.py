@@ -226,3 +226,22 @@ def test_crnn_stage1_step_bf16_tensor_core_router():
         ref = g["grad." + pname]
         scale = max(float(np.abs(ref).max()), 1e-3 * tn)
         assert np.abs(gview(got, g) - ref.reshape(-1)).max() / scale < 8e-2, pname
+
+
+def test_crnn_fused_lstm_cell_path_batch128():
+    """B % 128 == 0 in tensor-core mode switches the recurrence to the GEMM with the LSTM cell fused into its epilogue
+    (interleaved gate columns); compare the expert outputs with the fp32 oracle and with the unfused fp32 CUDA path."""
+    cc, B = (61,), 128
+    sd = _random_init_state_dict(cc, 13)
+    img, tgt, lens, dom = synth.synth_batch(B, cc, 13)
+    with torch.no_grad():
+        feat, pred = O.expert_forward(sd, 0, img)
+    net16, _ = build_net(cc, sd, precision="bf16")
+    net16.eval()
+    one16 = net16.model[0](img.cuda())
+    assert rel_err(one16["feature"].cpu().numpy(), feat.numpy()) < 2e-2
+    assert rel_err(one16["predict"].cpu().numpy(), pred.numpy()) < 2e-2
+    net32, _ = build_net(cc, sd, precision="fp32")
+    net32.eval()
+    one32 = net32.model[0](img[:8].cuda())
+    assert rel_err(one32["predict"].cpu().numpy(), pred[:8].numpy()) < 1e-4
