@@ -155,7 +155,8 @@ enum { /* per BidirectionalLSTM, Kin = 512 (layer 0) / 256 (layer 1).  The gate 
 typedef struct MrnbCrnnPack {
   int n_experts;
   const float* p[MRNB_C_COUNT]; /* fp32 parameters (always required) */
-  const void* h[MRNB_C_COUNT];  /* bf16 copies of the GEMM weight slots (conv1..6, W_ih, W_hh, linear); MRNB_PREC_BF16 only */
+  const void* h[MRNB_C_COUNT];  /* bf16 copies of the GEMM weight slots (conv1..6, W_ih, W_hh, linear) and conv0 as
+                                   [I,64,64] = 36 taps (c,kh,kw) zero-padded to 64; MRNB_PREC_BF16 only */
   const float* fc_w[MRNB_MAX_EXPERTS];  /* [C_i,256] model.{i}.fc.weight */
   const void* fc_w16[MRNB_MAX_EXPERTS]; /* bf16 copy; MRNB_PREC_BF16 only */
   const float* fc_b[MRNB_MAX_EXPERTS];  /* [C_i] */

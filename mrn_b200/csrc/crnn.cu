@@ -115,6 +115,31 @@ vgg_conv0_kernel(const float* __restrict__ image, const float* __restrict__ w /*
   }
 }
 
+// Tensor-core mode of conv0: im2col of the NCHW image shared by all experts, K = 36 taps (c, kh, kw) zero-padded to 64,
+// rows WINDOW-MAJOR: row = ((b*16 + ph)*128 + pw)*4 + (dy*2 + dx) is the conv output pixel (2ph+dy, 2pw+dx), so the
+// 2x2 max-pool is a max over 4 consecutive GEMM rows (MrnbTcGemm::pool4).  One thread per (row, 8-tap group).
+__global__ void __launch_bounds__(256)
+vgg_im2col0_kernel(const float* __restrict__ image, __nv_bfloat16* __restrict__ col, unsigned total) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const unsigned kg = i & 7, row = i >> 3;
+  const unsigned win = row & 3, pw = (row >> 2) & 127, ph = (row >> 9) & 15, b = row >> 13;
+  const int oh = 2 * ph + (win >> 1), ow = 2 * pw + (win & 1);
+  float v[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int k = kg * 8 + u;
+    float x = 0.f;
+    if (k < 36) {
+      const int c = k / 9, kh = (k % 9) / 3, kw = k % 3;
+      const int ih = oh - 1 + kh, iw = ow - 1 + kw;
+      if (ih >= 0 && ih < 32 && iw >= 0 && iw < 256) x = __ldg(image + (((size_t)b * 4 + c) * 32 + ih) * 256 + iw);
+    }
+    v[u] = x;
+  }
+  store8<__nv_bfloat16>(col + (size_t)i * 8, v);
+}
+
 // MaxPool2d((ph, pw)) over NHWC, 8 channels per thread.  in [N,H,W,C] -> out [N,H/ph,W/pw,C]   (32-bit index math:
 // the 8-channel group count stays below 2^31 for every supported batch)
 template <typename AT>
@@ -321,7 +346,7 @@ template <typename AT>
 size_t crnn_workspace_bytes_t(int I, int B) {
   const size_t u = (size_t)I * B;
   size_t s = 0;
-  s += align_up(u * 262144 * sizeof(AT));      // X
+  s += align_up((u * 262144 > (size_t)B * 524288 ? u * 262144 : (size_t)B * 524288) * sizeof(AT));      // X (also the conv0 im2col)
   s += align_up(u * 131072 * sizeof(AT));      // Y
   s += align_up(u * 131072 * sizeof(AT));      // Z
   if (sizeof(AT) == 4) s += align_up((size_t)B * 2048 * 576 * 4);   // im2col of one expert (largest: 1 179 648 per sample)
@@ -342,7 +367,7 @@ int crnn_forward_t(const MrnbCrnnPack& P, const float* image, int B, int bn_batc
   constexpr bool F32 = sizeof(AT) == 4;
   Workspace W{(char*)ws, 0, ws_bytes};
   const size_t u = (size_t)I * B;
-  AT* X = W.take<AT>(u * 262144);
+  AT* X = W.take<AT>(u * 262144 > (size_t)B * 524288 ? u * 262144 : (size_t)B * 524288);
   AT* Y = W.take<AT>(u * 131072);
   AT* Z = W.take<AT>(u * 131072);
   float* col = F32 ? W.take<float>((size_t)B * 2048 * 576) : nullptr;
@@ -355,10 +380,30 @@ int crnn_forward_t(const MrnbCrnnPack& P, const float* image, int B, int bn_batc
   const long N = (long)I * B;
 
   // ---- VGG (feature_extraction.py:19-47); Sequential index in the comments
-  mrnb_prof_begin(MRNB_PROF_CONV, st, 0.0, 0.0);
-  vgg_conv0_kernel<AT><<<dim3(16, B, I), 256, 0, st>>>(image, P.p[MRNB_C_CONV0_W], P.p[MRNB_C_CONV0_B], Y, B);   // 0-2 -> Y [16,128,64]
-  MRNB_CHECK_LAUNCH("vgg_conv0_kernel");
-  mrnb_prof_end(MRNB_PROF_CONV, st);
+  if constexpr (!F32) {
+    // 0-2 on the tensor cores: shared im2col (X, 64 bf16 per conv pixel) -> per expert GEMM [B*8192 x 64] x [64 x 64]
+    // with bias + ReLU + 2x2 max-pool in the epilogue -> Y [16,128,64]
+    MRNB_CHECK_ARG(P.h[MRNB_C_CONV0_W], "crnn_forward: bf16 mode needs the GEMM-packed conv0 weight in h[MRNB_C_CONV0_W]");
+    MRNB_CHECK_ARG((long)B * 8192 * 8 < (1L << 32), "crnn_forward: batch too large for the conv0 im2col");
+    mrnb_prof_begin(MRNB_PROF_CONV, st, 0.0, 0.0);
+    const unsigned total = (unsigned)B * 8192u * 8u;
+    vgg_im2col0_kernel<<<cdiv(total, 256), 256, 0, st>>>(image, reinterpret_cast<__nv_bfloat16*>(X), total);
+    MRNB_CHECK_LAUNCH("vgg_im2col0_kernel");
+    mrnb_prof_end(MRNB_PROF_CONV, st);
+    for (int e = 0; e < I; ++e) {
+      MrnbTcGemm g{};
+      g.A = X; g.lda = 64; g.W = reinterpret_cast<const __nv_bfloat16*>(P.h[MRNB_C_CONV0_W]) + (size_t)e * 64 * 64; g.ldw = 64;
+      g.bias = P.p[MRNB_C_CONV0_B] + e * 64;
+      g.out = reinterpret_cast<__nv_bfloat16*>(Y) + (size_t)e * B * 2048 * 64; g.ldo = 64; g.out_f32 = 0;
+      g.M = B * 8192; g.N = 64; g.K = 64; g.groups = 1; g.rows_per_scale = 1; g.pool4 = 1;
+      MRNB_TRY(mrnb_tc_gemm(g, st));
+    }
+  } else {
+    mrnb_prof_begin(MRNB_PROF_CONV, st, 0.0, 0.0);
+    vgg_conv0_kernel<AT><<<dim3(16, B, I), 256, 0, st>>>(image, P.p[MRNB_C_CONV0_W], P.p[MRNB_C_CONV0_B], Y, B);   // 0-2 -> Y [16,128,64]
+    MRNB_CHECK_LAUNCH("vgg_conv0_kernel");
+    mrnb_prof_end(MRNB_PROF_CONV, st);
+  }
   {
     const ConvSpec c1{16, 128, 64, 128, 3, 1, 16, 128, 1};                                                 // 3-4 -> X [16,128,128]
     MRNB_TRY(conv_layer<AT>(c1, I, B, Y, P.p[MRNB_C_CONV1_W], P.h[MRNB_C_CONV1_W], P.p[MRNB_C_CONV1_B], X, col, st));

@@ -324,6 +324,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               reinterpret_cast<__nv_bfloat16*>(L.hst)[ci] = hb;
               recp[(long)b * L.rec_row] = hb;
             }
+          } else if constexpr (MODE == 2) {
+            // bias + ReLU + max over each group of 4 consecutive rows (a 2x2 pooling window: the im2col rows are
+            // window-major), bf16 output [M/4, N].  Rows 4*itr .. 4*itr+3 sit in the lanes rsel = 0..3 of one step.
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ep.out) + gbase + (long)((m0 + q * 32) >> 2) * ep.ldo + colw + ps * 32;
+#pragma unroll
+            for (int itr = 0; itr < 8; ++itr) {
+              const int rl = itr * 4 + rsel;
+              float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((p8 ^ (rl & 7)) * 4));
+#pragma unroll
+              for (int o = 8; o <= 16; o <<= 1) {
+                x.x = fmaxf(x.x, __shfl_xor_sync(0xffffffffu, x.x, o)); x.y = fmaxf(x.y, __shfl_xor_sync(0xffffffffu, x.y, o));
+                x.z = fmaxf(x.z, __shfl_xor_sync(0xffffffffu, x.z, o)); x.w = fmaxf(x.w, __shfl_xor_sync(0xffffffffu, x.w, o));
+              }
+              if (rsel == 0) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(fmaxf(x.x + b4.x, 0.f), fmaxf(x.y + b4.y, 0.f));
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(fmaxf(x.z + b4.z, 0.f), fmaxf(x.w + b4.w, 0.f));
+                *reinterpret_cast<uint2*>(op + (long)itr * ep.ldo) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+              }
+            }
           } else if (OUT_F32) {
             float* op = reinterpret_cast<float*>(ep.out) + o0 + ps * 32;
 #pragma unroll
@@ -550,6 +569,11 @@ int mrnb_tc_gemm(const MrnbTcGemm& p, cudaStream_t st) {
                    p.lstm.pre_off[0] % 4 == 0 && p.lstm.pre_off[1] % 4 == 0,
                    "tc_gemm: fused LSTM cell needs M %% 128 == 0, N %% 128 == 0 and 8-byte aligned pre-activations");
     return launch_tc<128, true, false, false, 1>(p, st);
+  }
+  if (p.pool4) {
+    MRNB_CHECK_ARG(!p.out_f32 && p.M % BM == 0 && (p.N == 64 || p.N % 128 == 0) && p.ldo % 4 == 0 && p.o_gstride % 4 == 0 && !p.res &&
+                   !p.rowscale && !p.gelu && !p.ln_out, "tc_gemm: pooled epilogue needs bf16 output, M %% 128 == 0, N == 64 or N %% 128 == 0");
+    return p.N == 64 ? launch_tc<64, false, false, false, 2>(p, st) : launch_tc<128, false, false, false, 2>(p, st);
   }
   if (p.ln_out) {
     // fused LayerNorm: the tile must span whole rows and every tile must take the interior path

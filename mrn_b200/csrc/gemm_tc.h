@@ -41,6 +41,7 @@ struct MrnbTcGemm {
   const float* rowscale; int rows_per_scale; long rowscale_gstride;   // DropPath: * rowscale[g*gs + m / rows_per_scale]
   int M, N, K, groups, gelu;
   int relu;                                            // ReLU on the biased accumulator (VGG convolutions)
+  int pool4;                                           // bf16 out [M/4, N] = ReLU(max over each group of 4 consecutive rows + bias): 2x2 max-pool of window-major rows
   // optional fused LayerNorm of the fp32 output rows (N == 64 or 128): bf16 ln_out[g][m][N] = LN(out row) * gamma[g] + beta[g]
   void* ln_out; long ln_gstride; const float* ln_gamma; const float* ln_beta; float ln_eps;
   MrnbTcLstm lstm;     // optional fused LSTM cell (replaces the store)

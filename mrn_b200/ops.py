@@ -326,6 +326,13 @@ class CrnnPack:
 
         cn = "model.FeatureExtraction.ConvNet."
         put(L.C_CONV0_W, stack(lambda i: get(i, cn + "0.weight")))
+        if prec == L.PREC_BF16:
+            # tensor-core conv0: [64, (c,kh,kw) = 36 taps zero-padded to 64] bf16 (im2col GEMM, crnn.cu)
+            w0 = torch.zeros(n_experts, 64, 64, device=self.device, dtype=torch.float32)
+            w0[:, :, :36] = self.slot_tensors[L.C_CONV0_W].reshape(n_experts, 64, 36)
+            h0 = cast_bf16(w0.contiguous())
+            self.tensors.append(h0)
+            self.struct.h[L.C_CONV0_W] = h0.data_ptr()
         put(L.C_CONV0_B, stack(lambda i: get(i, cn + "0.bias")))
         for wslot, bslot, idx in _VGG_GEMM_CONVS:
             put(wslot, stack(lambda i: get(i, cn + f"{idx}.weight").permute(0, 2, 3, 1)), gemm_weight=True)
