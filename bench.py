@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--arch", default="svtr", choices=["svtr", "crnn"],
                     help="expert recogniser: svtr = headline (BASELINE.json configs[3-4]); crnn = VGG+BiLSTM (configs[1])")
+    ap.add_argument("--sweep", default="", help="infer mode only: comma-separated per-GPU batch sizes (BASELINE configs[4]: 1..4096); "
+                                               "adds a `sweep` array to the JSON line")
     ap.add_argument("--mode", default="train", choices=["train", "infer"],
                     help="train: router-training step (the BASELINE metric); infer: hard-routed forward + greedy decode (cfg 5)")
     return ap.parse_args()
@@ -160,6 +162,42 @@ def ncu_traffic(kernel, arch="svtr"):
         return t.get(kernel, {}).get("dram_bytes_per_launch")
     except Exception:
         return None
+
+
+def infer_sweep(learner, batches, dev):
+    """BASELINE configs[4]: hard-routed inference + device greedy decode over a range of batch sizes (resident inputs,
+    CUDA events, 3 warm-up + >=5 timed steps per size; two rotating input batches)."""
+    from mrn_b200 import synth
+    rows = []
+    for B in batches:
+        imgs = [synth.synth_batch(B, CLASS_COUNTS, 2000 + k)[0].to(dev) for k in range(2)]
+        for k in range(3):
+            learner.infer_batch(imgs[k % 2], "TF")
+        torch.cuda.synchronize()
+        steps = 20 if B <= 256 else (8 if B <= 1024 else 5)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(steps):
+            r = learner.infer_batch(imgs[k % 2], "TF")
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        row = {"batch": B, "ms_per_batch": round(ms, 3), "samples_per_s": round(B * 1000.0 / ms, 1)}
+        if B <= 128:                    # launch-bound sizes: the same call replayed from a CUDA graph
+            for k in range(3):
+                learner.infer_batch_graphed(imgs[k % 2], "TF")
+            torch.cuda.synchronize()
+            e0.record()
+            for k in range(steps):
+                r = learner.infer_batch_graphed(imgs[k % 2], "TF")
+            e1.record()
+            torch.cuda.synchronize()
+            msg = e0.elapsed_time(e1) / steps
+            row.update({"graph_ms_per_batch": round(msg, 3), "graph_samples_per_s": round(B * 1000.0 / msg, 1)})
+        rows.append(row)
+        del imgs, r
+        torch.cuda.empty_cache()
+    return rows
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -321,6 +359,8 @@ def run_ours(args):
     if infer:
         out["config"]["workload"] = ("%s-MRN 6-expert hard-routed inference + device greedy decode, B=%d/GPU, union charset 5153"
                                      % (args.arch.upper(), B))
+        if args.sweep:
+            out["sweep"] = infer_sweep(learner, [int(x) for x in args.sweep.split(",") if x], dev)
     if world == 1 and not args.no_cpu_baseline and not infer:
         v, ms, cores = cpu_stage1(args.cpu_sample, 2, 1, args.arch)
         out["cpu_baseline"] = {"value": round(v, 3), "unit": "samples/s", "cores": cores, "kind": "port",

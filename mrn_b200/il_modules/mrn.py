@@ -258,6 +258,34 @@ class MRN(object):
         ids, lens, conf = ops.greedy_decode(r["amax"], r["maxprob"])
         return dict(ids=ids, lens=lens, conf=conf, index=index, loss=loss)
 
+    def infer_batch_graphed(self, image, val_choose="TF"):
+        """infer_batch replayed from a CUDA graph captured per (batch size, route): small batches are launch-bound
+        (~95 kernels), and a replay costs one launch.  The graph owns static input / output buffers; the returned
+        tensors are views of the static outputs and stay valid until the next replay for the same batch size.
+        Eval-mode experts only (train-mode BatchNorm / DropPath state is not captured)."""
+        if self.net._experts_train_mode():
+            raise RuntimeError("infer_batch_graphed needs eval-mode experts (call model.eval() first)")
+        key = (int(image.shape[0]), val_choose, str(image.device))
+        cache = self.__dict__.setdefault("_infer_graphs", {})
+        ent = cache.get(key)
+        if ent is None:
+            static_in = image.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):             # warm-up on a side stream: lazy allocations, attribute setup, packs
+                for _ in range(2):
+                    self.infer_batch(static_in, val_choose)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.infer_batch(static_in, val_choose)
+            ent = cache[key] = (graph, static_in, out)
+        graph, static_in, out = ent
+        static_in.copy_(image, non_blocking=True)
+        graph.replay()
+        return out
+
     def validation(self, eval_loader, val_choose="TF"):
         """test.py:139-279 with the decode / confidence on the device."""
         n_correct, norm_ED, length_of_data, infer_time = 0, 0.0, 0, 0.0

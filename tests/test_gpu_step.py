@@ -205,3 +205,23 @@ def test_full_size_properties_6_experts():
     for b in range(4):      # a decoded sequence never contains blank or adjacent repeats of the raw path... it is collapsed
         seq = ids[b, :int(n[b])].tolist()
         assert 0 not in seq and -1 not in seq
+
+
+def test_infer_batch_cuda_graph_replay_matches_eager():
+    """The per-batch-size CUDA graph of the hard-routed inference call returns exactly what the eager call returns, for
+    fresh inputs on every replay."""
+    from mrn_b200.il_modules.mrn import MRN, RankLocal
+    g, cc, B, seed, sd, img, tgt, lens, dom = _case("svtr_mrn_i3_b3")
+    net, opt = build_net(cc, sd)
+    learner = MRN(opt)
+    learner.model = RankLocal(net)
+    learner.model.eval()
+    for k in range(3):
+        x = synth.synth_batch(B, cc, 50 + k)[0].cuda()
+        eager = learner.infer_batch(x, "TF")
+        ref = {n: eager[n].clone() for n in ("ids", "lens", "conf", "index")}
+        rep = learner.infer_batch_graphed(x, "TF")
+        torch.cuda.synchronize()
+        for n in ref:
+            assert torch.equal(rep[n], ref[n]), n
+    assert len(learner._infer_graphs) == 1
