@@ -215,6 +215,46 @@ class MRN(object):
         self.optimizer.step()                            # clip_grad_norm_(5) + Adam + OneCycle
         return c["loss"], taski_loss
 
+    def train_step_stage1_graphed(self, image, labels_index, labels_length, indexs):
+        """train_step_stage1 with the device work up to the router gradients (experts, router forward, combine + CTC,
+        router backward: ~115 launches) replayed from a CUDA graph captured per batch size; the gradient all-reduce
+        and the optimiser step stay eager (NCCL and the host-side OneCycle schedule are not captured).  The first call
+        for a batch size runs eagerly (lazy allocations, attribute setup), the second captures, later ones replay.
+        Steady-state loop only: re-capture (`reset_graphs()`) after the experts' weights or train / eval mode change."""
+        net = self.net
+        B = int(image.shape[0])
+        cache = self.__dict__.setdefault("_train_graphs", {})
+        key = (B, str(image.device), bool(net._experts_train_mode()))
+        ent = cache.get(key)
+        if ent is None:
+            cache[key] = "warm"
+            return self.train_step_stage1(image, labels_index, labels_length, indexs)
+        if ent == "warm":
+            st_in = tuple(t.clone() for t in (image, labels_index, labels_length, indexs))
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                r = net.route_and_combine(st_in[0], is_train=True, want_logits=False, targets=st_in[1], lengths=st_in[2],
+                                          want_E=True, with_backward=True)
+                c = ops.ctc_lattice(r["lpe"], st_in[1], st_in[2], r["zlab"], r["E"], grad_scale=float(self.pi) / B,
+                                    want_dgate=True)
+                taski_loss = ops.router_backward(net.router_arena(), r["features"], r["gate"], c["dgate"], st_in[3],
+                                                 net.router_grad_arena(), net._rws, prec=_precision(net.opt))
+            ent = cache[key] = (graph, st_in, c["loss"], taski_loss)
+        graph, st_in, loss, taski_loss = ent
+        for dst, src in zip(st_in, (image, labels_index, labels_length, indexs)):
+            dst.copy_(src, non_blocking=True)
+        graph.replay()
+        if key[2] and net._cache.pack is not None:
+            net._cache.pack.bn_dirty = True              # train-mode experts updated their BN running statistics
+        mdist.allreduce_mean_(net.router_grad_arena())
+        self.optimizer.step()
+        return loss, taski_loss
+
+    def reset_graphs(self):
+        self.__dict__.pop("_train_graphs", None)
+        self.__dict__.pop("_infer_graphs", None)
+
     def _update_representation(self, start_iter, taski, train_loader, valid_loader, pi=15):
         self.pi = pi
         train_loss_avg, train_taski_loss_avg = Averager(), Averager()

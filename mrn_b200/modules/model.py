@@ -173,9 +173,15 @@ def _experts_forward(experts, image, opt, train_mode, cache=None, drop_scales=No
     return feats, logits
 
 
+_RATES_CACHE = {}
+
+
 def sample_drop_scales(n_experts, B, rates, device, generator=None):
     """DropPath multipliers [I,12,2,B]: Bernoulli(keep)/keep per sample, block and branch (modules/svtr.py:7-22)."""
-    rates_t = torch.tensor(rates, dtype=torch.float32, device=device).view(1, -1, 1, 1)
+    key = (tuple(float(r) for r in rates), str(device))
+    rates_t = _RATES_CACHE.get(key)
+    if rates_t is None:                     # device-resident once: no host-to-device copy per step (CUDA-graph safe)
+        rates_t = _RATES_CACHE[key] = torch.tensor(rates, dtype=torch.float32, device=device).view(1, -1, 1, 1)
     u = torch.rand(n_experts, len(rates), 2, B, device=device, generator=generator)
     keep = (u >= rates_t).float()
     return (keep / (1.0 - rates_t)).contiguous()

@@ -225,3 +225,31 @@ def test_infer_batch_cuda_graph_replay_matches_eager():
         for n in ref:
             assert torch.equal(rep[n], ref[n]), n
     assert len(learner._infer_graphs) == 1
+
+
+def test_train_step_cuda_graph_replay_matches_eager():
+    """Stage-1 steps replayed from the CUDA graph update the router exactly like eager steps on the same batches
+    (eval-mode experts: no DropPath randomness)."""
+    from mrn_b200.il_modules.mrn import MRN, RankLocal, FusedAdam
+    g, cc, B, seed, sd, img, tgt, lens, dom = _case("svtr_mrn_i2_b4")
+    arenas, losses = [], []
+    for graphed in (False, True):
+        net, opt = build_net(cc, sd)
+        learner = MRN(opt)
+        learner.model = RankLocal(net)
+        learner.model.eval()
+        learner.optimizer = FusedAdam(net, 5e-4, 100, grad_clip=5, schedule="super")
+        step = learner.train_step_stage1_graphed if graphed else learner.train_step_stage1
+        ls = []
+        for k in range(4):
+            x, t, l, d = synth.synth_batch(B, cc, 70 + k)
+            a, b = step(x.cuda(), t.cuda(), l.cuda(), d.cuda())
+            ls.append((float(a), float(b)))
+        arenas.append(net.router_arena().clone())
+        losses.append(ls)
+        if graphed:
+            assert isinstance(learner._train_graphs[(B, "cuda:0", False)], tuple)
+    # split-K fp32 atomics make the weight gradients run-to-run non-deterministic at the 1e-6 level: compare with tolerance
+    assert torch.allclose(arenas[0], arenas[1], rtol=1e-4, atol=2e-5)
+    for (a0, b0), (a1, b1) in zip(*losses):
+        assert abs(a0 - a1) < 1e-4 * abs(a0) + 1e-6 and abs(b0 - b1) < 1e-4
