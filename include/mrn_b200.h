@@ -114,6 +114,24 @@ int mrnb_svtr_experts_forward(const MrnbSvtrPack* pack, const float* image, int 
                               cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Stage-0 expert training: one SVTR expert, activation-keeping forward + full backward.
+ * Replaces il_modules/mrn.py:225-279 (_init_train: model(image, cross=False)['logits'] -> loss.backward()), i.e. the
+ * autograd graph of modules/model.py:351-353 -> :133-148 -> modules/svtr.py:500-528 in train mode.
+ *
+ * `pack` holds exactly ONE expert (n_experts == 1) in the slot layout above; `grads` has the same slots pointing into a
+ * flat fp32 gradient arena [n_arena] (BN running-stat slots unused) that the backward zeroes and fills -- the same arena
+ * layout serves mrnb_clip_adam and the NCCL all-reduce.  The workspace carries the saved activations from the forward
+ * to the backward call (same pointer, same B).  drop_scales: NULL or [12,2,B] DropPath multipliers.
+ * logits / dlogits: [B,64,ld] fp32, first n_class[0] columns valid (dlogits from mrnb_ctc_dense_grad). */
+size_t mrnb_svtr_train_workspace_bytes(int B, int prec);
+int mrnb_svtr_train_forward(const MrnbSvtrPack* pack, const float* image, int B, int prec, int bn_batch_stats,
+                            int update_running, const float* drop_scales, float* logits, long ld_logits, void* workspace,
+                            size_t workspace_bytes, cudaStream_t stream);
+int mrnb_svtr_train_backward(const MrnbSvtrPack* pack, const MrnbSvtrPack* grads, const float* image, const float* dlogits,
+                             long ld_dlogits, int B, int prec, int bn_batch_stats, const float* drop_scales,
+                             float* grad_arena, long n_arena, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * CRNN expert recognisers (VGG + 2 x BidirectionalLSTM + CTC head), T = 63 frames.
  * Replaces modules/feature_extraction.py:19-47 (VGG_FeatureExtractor.forward), modules/sequence_modeling.py:12-22
  * (BidirectionalLSTM.forward, x2), modules/model.py:82-101 (Model_Extractor.forward) and :133-148 (Model.forward),

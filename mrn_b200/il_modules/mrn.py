@@ -6,8 +6,10 @@ What runs where
     grouped frozen experts -> DM-Router -> gate -> fused combine + CTC -> analytic gate gradient -> router backward
     -> [NCCL all-reduce of the gradient arena] -> clip + Adam.  No autograd graph, no host sync inside the step.
   * validation (test.py:139-279) uses the hard route + device-side greedy decode (one D2H copy per batch).
-  * stage 0 (training a new expert end to end, il_modules/mrn.py:225-279) needs the expert backward, which is the
-    "next" row of SURVEY.md §8(f)3: it raises NotImplementedError here rather than falling back to PyTorch.
+  * stage 0 (training the newest expert end to end, il_modules/mrn.py:225-279) for SVTR experts:
+    activation-keeping forward -> fused log-softmax + CTC -> dense CTC gradient -> hand-written backward to every
+    parameter of the expert (mrnb_svtr_train_forward / _backward) -> [NCCL all-reduce of the expert's gradient arena]
+    -> clip + Adam on the arena.  CRNN experts (VGG + BiLSTM BPTT) are not implemented and raise.
 Host-side schedule / logging logic follows il_modules/base.py.
 """
 import math
@@ -18,7 +20,7 @@ import torch
 
 from .. import dist as mdist
 from .. import ops
-from ..modules.model import MRNNet, _precision
+from ..modules.model import MRNNet, _arch, _precision, sample_drop_scales
 from ..utils import Averager, CTCLabelConverter
 
 
@@ -35,6 +37,11 @@ def one_cycle_lr(step, total_steps, max_lr, div_factor=20.0, final_div_factor=10
     if step <= end1:
         return cos(initial, max_lr, step / end1)
     return cos(max_lr, min_lr, (step - end1) / (end2 - end1))
+
+
+def L_PREC_TRAIN(opt):
+    """Arithmetic mode of the stage-0 step: the expert backward currently runs in the fp32 mode only."""
+    return ops.L.PREC_FP32
 
 
 def edit_distance(a, b):
@@ -88,6 +95,33 @@ class FusedAdam:
         self.steps += 1
         ops.clip_adam(self.net.router_arena(), self.net.router_grad_arena(), self.exp_avg, self.exp_avg_sq, lr, self.steps,
                       max_norm=self.grad_clip, scratch=self.scratch, norm_out=self.norm)
+        self.param_groups[0]["lr"] = self.current_lr()
+
+
+class ArenaAdam:
+    """clip_grad_norm_ + Adam over one flat (params, grads) arena pair with the OneCycleLR bookkeeping of
+    il_modules/base.py:84-108 (stage 0: total_steps = num_iter)."""
+
+    def __init__(self, params, grads, lr, total_steps, grad_clip=5.0, schedule="super"):
+        self.params, self.grads = params, grads
+        self.max_lr, self.total_steps, self.grad_clip, self.schedule = lr, total_steps, grad_clip, schedule
+        self.exp_avg = torch.zeros_like(params)
+        self.exp_avg_sq = torch.zeros_like(params)
+        self.scratch = torch.empty(4096, dtype=torch.uint8, device=params.device)
+        self.norm = torch.zeros(1, dtype=torch.float32, device=params.device)
+        self.steps = 0
+        self.param_groups = [{"lr": self.current_lr()}]
+
+    def current_lr(self):
+        if "super" in str(self.schedule):
+            return one_cycle_lr(min(self.steps, self.total_steps - 1), self.total_steps, self.max_lr)
+        return self.max_lr
+
+    def step(self):
+        lr = self.current_lr()
+        self.steps += 1
+        ops.clip_adam(self.params, self.grads, self.exp_avg, self.exp_avg_sq, lr, self.steps, max_norm=self.grad_clip,
+                      scratch=self.scratch, norm_out=self.norm)
         self.param_groups[0]["lr"] = self.current_lr()
 
 
@@ -185,18 +219,101 @@ class MRN(object):
             path = f"./saved_models/{self.opt.exp_name}/{name}_{taski}_{step}_best_score.pth"
             self.model.load_state_dict(torch.load(path, map_location=self.device), strict=True)
             return
-        if taski == 0 or step == 0:
+        if taski == 0:
             self._init_train(start_iter, taski, train_loader, valid_loader, cross=False)
+        elif step == 0:
+            self.update_step1(start_iter, taski, train_loader, valid_loader)
         else:
             self._update_representation(start_iter, taski, train_loader, valid_loader)
 
+    # ---- stage 0: the newest expert trained end to end ---------------------------------------------
+    def begin_expert_training(self, total_steps=None):
+        """Moves the newest expert's parameters into a flat training arena (ops.SvtrTrainPack) and builds the fused
+        optimiser over it (Adam + OneCycle over num_iter steps, il_modules/base.py:84-108)."""
+        net = self.net
+        if _arch(net.opt) != "svtr":
+            raise NotImplementedError("stage-0 training is implemented for SVTR experts; the CRNN expert backward "
+                                      "(VGG convolutions + BiLSTM BPTT) is not. No PyTorch fallback.")
+        expert = net.model[-1]
+        net._sync_bn()
+        sd = {k: v for k, v in expert.state_dict().items()}
+        self._tp = ops.SvtrTrainPack(sd, self.device, L_PREC_TRAIN(net.opt))
+        self.optimizer = ArenaAdam(self._tp.params, self._tp.grads, self.opt.lr,
+                                   int(total_steps or self.opt.num_iter), grad_clip=self.opt.grad_clip,
+                                   schedule=getattr(self.opt, "schedule", "super"))
+        self.scheduler = self.optimizer
+        self._tp_steps = 0
+        return self._tp
+
+    def end_expert_training(self):
+        """Writes the trained arena (and BatchNorm running statistics) back into the expert's nn.Module parameters, so
+        that state_dict() / checkpoints / the grouped inference pack see the new weights."""
+        tp = self._tp
+        expert = self.net.model[-1]
+        with torch.no_grad():
+            own = dict(expert.named_parameters())
+            for key, t in tp.state().items():
+                own[key].copy_(t)                       # bumps the version counter -> inference packs are rebuilt
+            cn = expert.model.FeatureExtraction.ConvNet
+            for bn, (sm, sv) in ((cn.patch_embed.proj[1], (ops.L.P_BN0_MEAN, ops.L.P_BN0_VAR)),
+                                 (cn.patch_embed.proj[4], (ops.L.P_BN1_MEAN, ops.L.P_BN1_VAR))):
+                bn.running_mean.copy_(tp.bn_stats[sm].reshape(-1))
+                bn.running_var.copy_(tp.bn_stats[sv].reshape(-1))
+                bn.num_batches_tracked += self._tp_steps
+        self._tp_steps = 0
+        self.net._cache.key = None                      # BN buffers changed without a parameter version bump
+        self.reset_graphs()
+
+    def train_step_stage0(self, image, labels_index, labels_length, drop_scales=None):
+        """One expert-training iteration (il_modules/mrn.py:236-267) on the device: forward of the newest expert in its
+        current mode (train: BatchNorm batch statistics + DropPath), mean CTC loss, full backward, gradient all-reduce,
+        clip + Adam.  Returns the loss as a 1-element device tensor."""
+        tp = self._tp
+        expert = self.net.model[-1]
+        train_mode = bool(expert.training)
+        B = image.shape[0]
+        if train_mode and drop_scales is None and getattr(self.opt, "drop_path", True):
+            rates = expert.model.FeatureExtraction.ConvNet.drop_path_rates()
+            drop_scales = sample_drop_scales(1, B, rates, image.device)[0].contiguous()
+        image = image.contiguous().float()
+        logits = ops.svtr_train_forward(tp, image, bn_batch_stats=train_mode, update_running=train_mode,
+                                        drop_scales=drop_scales)
+        gate = self.__dict__.get("_ones")
+        if gate is None or gate.shape[0] != B or gate.device != image.device:
+            gate = self._ones = torch.ones(B, 1, device=image.device, dtype=torch.float32)
+        r = ops.gate_combine([logits], gate, labels_index, labels_length)        # row log-sum-exp + label gathers
+        c = ops.ctc_lattice(r["lpe"], labels_index, labels_length, want_occ=True)
+        dlogits = ops.ctc_dense_grad(logits, r["lse"], c["occ"], c["nll"], labels_index, labels_length, 1.0 / B)
+        ops.svtr_train_backward(tp, image, dlogits, bn_batch_stats=train_mode, drop_scales=drop_scales)
+        mdist.allreduce_mean_(tp.grads)                  # the ONE exchange step (28 MB; replaces nn.DataParallel)
+        self.optimizer.step()                            # clip_grad_norm_(5) + Adam + OneCycle
+        if train_mode:
+            self._tp_steps += 1
+        return c["loss"]
+
     def _init_train(self, start_iter, taski, train_loader, valid_loader, cross=False):
-        raise NotImplementedError(
-            "stage-0 expert training (il_modules/mrn.py:225-279) needs the SVTR expert backward, the 'next' row of "
-            "SURVEY.md §8(f)3; load stage-0 checkpoints with opt.start_task instead.  No PyTorch fallback.")
+        """il_modules/mrn.py:225-279."""
+        train_loss_avg = Averager()
+        start_time = time.time()
+        best_score = -1
+        self.begin_expert_training()
+        for iteration in range(start_iter + 1, self.opt.num_iter + 1):
+            image_tensors, labels = train_loader.get_batch()
+            image = image_tensors.to(self.device, non_blocking=True)
+            labels_index, labels_length = self.converter.encode(labels, batch_max_length=self.opt.batch_max_length)
+            loss = self.train_step_stage0(image, labels_index, labels_length)
+            train_loss_avg.add(loss)
+            if iteration % self.opt.val_interval == 0 or iteration == self.opt.num_iter:
+                self.end_expert_training()
+                self.val(valid_loader, self.opt, best_score, start_time, iteration, train_loss_avg, None, taski, 0, "FF")
+                train_loss_avg.reset()
+        self.end_expert_training()
 
     def update_step1(self, start_iter, taski, train_loader, valid_loader):
         self._init_train(start_iter, taski, train_loader, valid_loader, cross=False)
+        for p in self.net.model[-1].parameters():       # il_modules/mrn.py:284-287
+            p.requires_grad = False
+        self.net.model[-1].eval()
 
     def train_step_stage1(self, image, labels_index, labels_length, indexs, drop_scales=None):
         """One router-training iteration (il_modules/mrn.py:338-371) entirely on the device.

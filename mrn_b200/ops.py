@@ -283,6 +283,140 @@ def svtr_experts_forward(pack: SvtrPack, image: torch.Tensor, bn_batch_stats: bo
     return feats, logits
 
 
+# ------------------------------------------------------------------------------------------------ stage-0 expert training
+def _train_slots():
+    """[(slot, key relative to the expert's Model, permute)] for every trainable SVTR slot, in arena order."""
+    cn = "model.FeatureExtraction.ConvNet."
+    out = [(L.P_POS_EMBED, cn + "pos_embed", None), (L.P_CONV0_W, cn + "patch_embed.proj.0.weight", None),
+           (L.P_CONV0_B, cn + "patch_embed.proj.0.bias", None), (L.P_BN0_W, cn + "patch_embed.proj.1.weight", None),
+           (L.P_BN0_B, cn + "patch_embed.proj.1.bias", None),
+           (L.P_CONV1_W, cn + "patch_embed.proj.3.weight", (0, 2, 3, 1)), (L.P_CONV1_B, cn + "patch_embed.proj.3.bias", None),
+           (L.P_BN1_W, cn + "patch_embed.proj.4.weight", None), (L.P_BN1_B, cn + "patch_embed.proj.4.bias", None)]
+    for b, name in enumerate(_BLOCK_NAMES):
+        for k, key in enumerate(_BLOCK_KEYS):
+            out.append((L.P_BLOCK0 + b * L.PB_COUNT + k, f"{cn}{name}.{key}", None))
+    for s_ in range(3):
+        base = L.P_SUB0 + s_ * L.PS_COUNT
+        out += [(base + L.PS_CONV_W, f"{cn}sub_sample{s_ + 1}.conv.weight", (0, 2, 3, 1)),
+                (base + L.PS_CONV_B, f"{cn}sub_sample{s_ + 1}.conv.bias", None),
+                (base + L.PS_NORM_W, f"{cn}sub_sample{s_ + 1}.norm.weight", None),
+                (base + L.PS_NORM_B, f"{cn}sub_sample{s_ + 1}.norm.bias", None)]
+    out += [(L.P_SEQ_W, "model.SequenceModeling.0.weight", None), (L.P_SEQ_B, "model.SequenceModeling.0.bias", None)]
+    return out
+
+
+_BN_STAT_SLOTS = ((L.P_BN0_MEAN, "patch_embed.proj.1.running_mean"), (L.P_BN0_VAR, "patch_embed.proj.1.running_var"),
+                  (L.P_BN1_MEAN, "patch_embed.proj.4.running_mean"), (L.P_BN1_VAR, "patch_embed.proj.4.running_var"))
+
+
+class SvtrTrainPack:
+    """ONE expert's trainable parameters in a single flat fp32 arena laid out in MrnbSvtrPack slots (n_experts = 1;
+    conv weights as [Cout,kh,kw,Cin]), a gradient arena with the same layout, and the BatchNorm running statistics.
+    The arena is what mrnb_clip_adam updates and what the data-parallel all-reduce averages (stage 0,
+    il_modules/mrn.py:225-279).  `entries` maps each arena slice back to its state_dict key."""
+
+    def __init__(self, expert_sd: Dict[str, torch.Tensor], device, prec: int = L.PREC_FP32):
+        self.device = torch.device(device)
+        self.prec = prec
+        slots = _train_slots() + [("fc_w", "fc.weight", None), ("fc_b", "fc.bias", None)]
+        self.entries = []                         # (slot, key, permute, offset, kernel-layout shape)
+        off = 0
+        for slot, key, perm in slots:
+            shp = tuple(expert_sd[key].shape)
+            if perm is not None:
+                shp = tuple(shp[a] for a in perm)
+            self.entries.append((slot, key, perm, off, shp))
+            n = 1
+            for v in shp:
+                n *= v
+            off += round_up(n, 8)
+        self.numel = off
+        self.params = torch.zeros(off, device=self.device, dtype=torch.float32)
+        self.grads = torch.zeros(off, device=self.device, dtype=torch.float32)
+        cn = "model.FeatureExtraction.ConvNet."
+        self.bn_stats = {slot: expert_sd[cn + key].detach().to(self.device, torch.float32).clone().contiguous()
+                         for slot, key in _BN_STAT_SLOTS}
+        self.n_class = int(expert_sd["fc.weight"].shape[0])
+        self.struct = L.MrnbSvtrPack()
+        self.gstruct = L.MrnbSvtrPack()
+        for st_, arena in ((self.struct, self.params), (self.gstruct, self.grads)):
+            st_.n_experts = 1
+            st_.n_class[0] = self.n_class
+            for slot, key, perm, o, shp in self.entries:
+                ptr = arena.data_ptr() + 4 * o
+                if slot == "fc_w":
+                    st_.fc_w[0] = ptr
+                elif slot == "fc_b":
+                    st_.fc_b[0] = ptr
+                else:
+                    st_.p[slot] = ptr
+        for slot, t in self.bn_stats.items():
+            self.struct.p[slot] = t.data_ptr()
+        self.load_state(expert_sd)
+        self._ws: Optional[torch.Tensor] = None
+        self._ws_B = 0
+
+    def view(self, arena, entry):
+        slot, key, perm, o, shp = entry
+        n = 1
+        for v in shp:
+            n *= v
+        return arena[o:o + n].view(shp)
+
+    def load_state(self, expert_sd):
+        with torch.no_grad():
+            for e in self.entries:
+                t = expert_sd[e[1]].detach().to(self.device, torch.float32)
+                if e[2] is not None:
+                    t = t.permute(*e[2])
+                self.view(self.params, e).copy_(t)
+
+    def state(self, arena=None) -> Dict[str, torch.Tensor]:
+        """{state_dict key: tensor in the reference's layout} read back from the arena (params by default)."""
+        arena = self.params if arena is None else arena
+        out = {}
+        for e in self.entries:
+            t = self.view(arena, e)
+            if e[2] is not None:
+                inv = [0] * len(e[2])
+                for a, b in enumerate(e[2]):
+                    inv[b] = a
+                t = t.permute(*inv)
+            out[e[1]] = t
+        return out
+
+    def workspace(self, B):
+        need = int(L.load().mrnb_svtr_train_workspace_bytes(B, self.prec))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+
+def svtr_train_forward(tp: SvtrTrainPack, image, bn_batch_stats=True, update_running=True, drop_scales=None):
+    """Activation-keeping forward of the expert being trained.  Returns logits [B,64,C] (a view of a padded buffer)."""
+    _chk_f32(image, drop_scales)
+    B = image.shape[0]
+    ld = round_up(tp.n_class, 4)
+    buf = torch.empty(B, T_FRAMES, ld, device=image.device, dtype=torch.float32)
+    ws = tp.workspace(B)
+    L.check(L.load().mrnb_svtr_train_forward(C.byref(tp.struct), _p(image), B, tp.prec, int(bn_batch_stats),
+                                             int(update_running), _p(drop_scales), _p(buf), ld, _p(ws), ws.numel(),
+                                             _stream()), "svtr_train_forward")
+    return buf[:, :, :tp.n_class]
+
+
+def svtr_train_backward(tp: SvtrTrainPack, image, dlogits, bn_batch_stats=True, drop_scales=None):
+    """Fills tp.grads (overwritten) from d loss / d logits [B,64,C]; must follow svtr_train_forward on the same batch."""
+    _chk_f32(image, drop_scales)
+    assert dlogits.dtype == torch.float32 and dlogits.stride(2) == 1 and dlogits.stride(0) == dlogits.shape[1] * dlogits.stride(1)
+    B = image.shape[0]
+    ws = tp.workspace(B)
+    L.check(L.load().mrnb_svtr_train_backward(C.byref(tp.struct), C.byref(tp.gstruct), _p(image), _p(dlogits),
+                                              dlogits.stride(1), B, tp.prec, int(bn_batch_stats), _p(drop_scales),
+                                              _p(tp.grads), tp.numel, _p(ws), ws.numel(), _stream()), "svtr_train_backward")
+    return tp.grads
+
+
 # ------------------------------------------------------------------------------------------------ CRNN experts
 T_FRAMES_CRNN = 63          # modules/model.py:322-323
 

@@ -25,10 +25,10 @@ SUB = 11    # stride of the subsample kept for tensors above MAX_FULL elements
 MAX_FULL = 16384
 
 
-def keep(t: torch.Tensor) -> np.ndarray:
+def keep(t: torch.Tensor, sub: int = SUB, max_full: int = MAX_FULL) -> np.ndarray:
     a = t.detach().cpu().numpy()
-    if a.size > MAX_FULL:
-        return np.ascontiguousarray(a.reshape(-1)[::SUB])
+    if a.size > max_full:
+        return np.ascontiguousarray(a.reshape(-1)[::sub])
     return a.copy()
 
 
@@ -163,6 +163,71 @@ def run_case(name, class_counts, B, seed, arch="svtr"):
     print(name, "->", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def run_stage0_case(name, class_counts, B, seed, bn_train=True):
+    """One stage-0 iteration of the unmodified reference (il_modules/mrn.py:236-267): the newest expert trained end to
+    end through `model(image, cross=False)` with CTC, earlier experts frozen (mrn.py:154-157).  Train mode (BatchNorm
+    batch statistics, DropPath masks injected so the run is reproducible)."""
+    I = len(class_counts)
+    sd = synth.synth_state_dict(class_counts, seed, arch="svtr")
+    img, tgt, lens, dom = synth.synth_batch(B, class_counts, seed)
+    tgt = tgt.clamp(max=class_counts[-1] - 1)
+    rates = [0.1 * i / 11 for i in range(12)]
+    drop = synth.synth_drop_scales(I, B, rates, seed)
+    g = {}
+    with reference_modules() as ref:
+        net = build_ref_net(ref, class_counts, sd, "svtr")
+        crit = torch.nn.CTCLoss(reduction="mean", zero_infinity=True)       # il_modules/base.py:131
+        for i in range(I - 1):
+            for p in net.model[i].parameters():
+                p.requires_grad = False                                      # mrn.py:154-157
+        net.train(bn_train)
+        queue = []
+        orig_drop = ref.svtr.drop_path
+
+        def injected(x, drop_prob=0., training=False, scale_by_keep=True):
+            s = queue.pop(0)
+            return x * s.view(-1, 1, 1)
+        if bn_train:
+            ref.svtr.drop_path = injected
+            for j in range(12):
+                if rates[j] > 0:
+                    queue.append(drop[I - 1, j, 0]); queue.append(drop[I - 1, j, 1])
+        try:
+            preds = net(img, False)["logits"]                                # mrn.py:246
+            assert not queue
+        finally:
+            ref.svtr.drop_path = orig_drop
+        psize = torch.IntTensor([preds.size(1)] * B)
+        loss = crit(preds.log_softmax(2).permute(1, 0, 2), tgt, psize, lens)  # mrn.py:249-252
+        net.zero_grad()
+        loss.backward()                                                      # mrn.py:260
+        g["logits"] = keep(preds)
+        g["loss"] = np.float64(loss.item())
+        for n_, p in net.named_parameters():
+            if p.grad is not None:
+                g["grad." + n_] = keep(p.grad, 101, 2048)
+                g["gradnorm." + n_] = np.float64(p.grad.double().norm().item())
+        total_norm = torch.nn.utils.clip_grad_norm_(net.parameters(), 5)     # mrn.py:261-263
+        g["grad_total_norm"] = np.float64(float(total_norm))
+        params = [p for p in net.parameters() if p.requires_grad]            # count_param(), base.py:84-108
+        opt_ = torch.optim.Adam(params, lr=5e-4)
+        opt_.step()                                                          # mrn.py:264
+        for n_, p in net.named_parameters():
+            if p.grad is not None:
+                g["adam1." + n_] = keep(p.detach(), 101, 2048)
+        bn = net.model[I - 1].model.FeatureExtraction.ConvNet.patch_embed.proj
+        g["bn0_running_mean"] = bn[1].running_mean.numpy().copy(); g["bn0_running_var"] = bn[1].running_var.numpy().copy()
+        g["bn1_running_mean"] = bn[4].running_mean.numpy().copy(); g["bn1_running_var"] = bn[4].running_var.numpy().copy()
+    g["class_counts"] = np.array(class_counts); g["B"] = np.int64(B); g["seed"] = np.int64(seed)
+    g["bn_train"] = np.int64(int(bn_train))
+    g["sub"] = np.int64(SUB); g["max_full"] = np.int64(MAX_FULL)
+    g["psub"] = np.int64(101); g["pmax_full"] = np.int64(2048)
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **g)
+    print(name, "->", path, os.path.getsize(path) // 1024, "KiB")
+
+
 def run_router_case(name, I, B, seed):
     """DM_Router alone on random features (modules/dm_router.py:50-67) incl. input gradient."""
     shapes = synth.router_shapes(I)
@@ -197,6 +262,9 @@ if __name__ == "__main__":
         # BASELINE.json configs[0] in miniature: CRNN-MRN (VGG + BiLSTM + CTC), 2 tasks; and a 3-task case
         run_case("crnn_mrn_i2_b4", (53, 80), 4, 21, arch="crnn")
         run_case("crnn_mrn_i3_b2", (37, 61, 96), 2, 33, arch="crnn")
+    if not only or "stage0" in only:
+        run_stage0_case("svtr_stage0_i2_b3", (37, 61), 3, 17)
+        run_stage0_case("svtr_stage0_i1_b2_eval", (45,), 2, 29, bn_train=False)
     if only and "router" not in only:
         sys.exit(0)
     run_router_case("dm_router_i3_b2", 3, 2, 5)

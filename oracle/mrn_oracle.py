@@ -537,3 +537,46 @@ def stage1_step_cpu(sd, n_experts, state, image, targets, target_lengths, domain
     params = {k: sd[k] for k in ROUTER_KEYS}
     clip_and_adam(params, r["grads"], state, lr)
     return float(r["loss_clf"]), float(r["taski_loss"])
+
+
+# ----------------------------------------------------------------------------------------------
+# Stage 0: training the newest expert end to end (il_modules/mrn.py:225-279)
+# ----------------------------------------------------------------------------------------------
+
+def expert_param_keys(sd, i: int) -> List[str]:
+    """Trainable tensors of expert i that receive a gradient in stage 0: everything under model.{i}. except the
+    BatchNorm buffers, the aliased Prediction.* (same object as fc, modules/model.py:181) and the three modules the SVTR
+    forward never touches (modules/svtr.py:464-479: linear, last_conv, norm)."""
+    p = f"model.{i}."
+    dead = (p + "model.FeatureExtraction.ConvNet.linear.", p + "model.FeatureExtraction.ConvNet.last_conv.",
+            p + "model.FeatureExtraction.ConvNet.norm.")
+    return [k for k in sd if k.startswith(p) and not k.startswith(p + "Prediction.") and not k.startswith(dead)
+            and "running_" not in k and "num_batches_tracked" not in k]
+
+
+def stage0_loss_and_grads(sd, i: int, image, targets, target_lengths, bn_mode="batch", drop_scales=None,
+                          dtype=torch.float64):
+    """One stage-0 objective evaluation (il_modules/mrn.py:246-260): preds = model(image, cross=False)['logits'] is the
+    LAST expert's "predict" (modules/model.py:351-353); loss = CTCLoss(mean, zero_infinity)(log_softmax(preds));
+    gradients by autograd over this restatement.  drop_scales: None or [12,2,B] for this expert."""
+    keys = expert_param_keys(sd, i)
+    sd2 = {k: (v.detach().to(dtype) if v.is_floating_point() else v) for k, v in sd.items() if k.startswith(f"model.{i}.")}
+    for k in keys:
+        sd2[k].requires_grad_(True)
+    _, logits = expert_forward(sd2, i, image.to(dtype), bn_mode, drop_scales)
+    B, T = logits.shape[0], logits.shape[1]
+    lp = logits.log_softmax(2).permute(1, 0, 2)
+    loss = F.ctc_loss(lp, targets, torch.full((B,), T, dtype=torch.int32), target_lengths.to(torch.int32), blank=0,
+                      reduction="mean", zero_infinity=True)
+    grads = torch.autograd.grad(loss, [sd2[k] for k in keys], allow_unused=True)
+    return dict(loss=loss.detach(), logits=logits.detach(),
+                grads={k: (g if g is not None else torch.zeros_like(sd2[k])) for k, g in zip(keys, grads)})
+
+
+def stage0_step_cpu(sd, i: int, state, image, targets, target_lengths, lr=5e-4, bn_mode="batch", drop_scales=None):
+    """il_modules/mrn.py:236-267 on the host in fp32: forward, CTC, backward, clip_grad_norm_(5), Adam.  Updates the
+    expert's entries of `sd` in place (BatchNorm running statistics are not tracked here).  Returns the loss."""
+    r = stage0_loss_and_grads(sd, i, image, targets, target_lengths, bn_mode, drop_scales, dtype=torch.float32)
+    params = {k: sd[k] for k in r["grads"]}
+    clip_and_adam(params, r["grads"], state, lr)
+    return float(r["loss"])

@@ -1,0 +1,181 @@
+"""Stage-0 expert training (il_modules/mrn.py:225-279) on the GPU through the C ABI: the activation-keeping forward,
+the hand-written backward to every parameter of the newest SVTR expert, clip + Adam on the arena -- against the golden
+fixtures produced by the unmodified reference (autograd) and against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mrn_oracle as O
+from oracle import synth
+from conftest import load_golden, gview, rel_err
+from test_gpu_step import build_net, make_opt
+from test_oracle_pinning import STAGE0_CASES, pview, stage0_case
+
+pytestmark = pytest.mark.gpu
+
+# analytically zero gradients (a conv bias in front of a batch-statistics BatchNorm; the key third of qkv.bias):
+# what is left is round-off, compared on the scale of the whole gradient
+def _abs_scale_only(key, bn_train):
+    return bn_train and key.endswith(("patch_embed.proj.0.bias", "patch_embed.proj.3.bias"))
+
+
+def _run_step(name, lr=None):
+    from mrn_b200 import ops
+    g, cc, B, sd, img, tgt, lens, bn_train, drop = stage0_case(name)
+    i = len(cc) - 1
+    pre = f"model.{i}."
+    esd = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+    tp = ops.SvtrTrainPack(esd, "cuda")
+    x = img.cuda()
+    dsc = drop.cuda().contiguous() if drop is not None else None
+    logits = ops.svtr_train_forward(tp, x, bn_batch_stats=bn_train, update_running=bn_train, drop_scales=dsc)
+    t, l = tgt.cuda(), lens.cuda()
+    r = ops.gate_combine([logits], torch.ones(B, 1, device="cuda"), t, l)
+    c = ops.ctc_lattice(r["lpe"], t, l, want_occ=True)
+    dlogits = ops.ctc_dense_grad(logits, r["lse"], c["occ"], c["nll"], t, l, 1.0 / B)
+    ops.svtr_train_backward(tp, x, dlogits, bn_batch_stats=bn_train, drop_scales=dsc)
+    torch.cuda.synchronize()
+    return g, cc, sd, tp, logits, c, bn_train, pre
+
+
+@pytest.mark.parametrize("name", STAGE0_CASES)
+def test_stage0_forward_loss_and_every_gradient_match_reference_golden(name):
+    g, cc, sd, tp, logits, c, bn_train, pre = _run_step(name)
+    assert rel_err(gview(logits.cpu(), g), g["logits"]) < 1e-4
+    assert abs(float(c["loss"]) - float(g["loss"])) / abs(float(g["loss"])) < 1e-4
+    tn = float(g["grad_total_norm"])
+    grads = tp.state(tp.grads)
+    total = 0.0
+    bad = []
+    for key, gg in grads.items():
+        gk = "grad." + pre + key
+        ref = g[gk]
+        total += float((gg.double() ** 2).sum())
+        scale = max(float(np.abs(ref).max()), 1e-4 * tn)
+        if _abs_scale_only(key, bn_train):
+            scale = tn
+        err = np.abs(pview(gg.contiguous().cpu(), g) - ref).max() / scale
+        nerr = abs(float(gg.double().norm()) - float(g["gradnorm." + pre + key])) / max(float(g["gradnorm." + pre + key]), 1e-4 * tn)
+        if err > 1e-3 or (nerr > 1e-3 and not _abs_scale_only(key, bn_train)):
+            bad.append((key, float(err), float(nerr)))
+    assert not bad, bad
+    assert abs(total ** 0.5 - tn) / tn < 5e-4
+    if bn_train:                                   # running statistics, momentum 0.1 (nn.BatchNorm2d in .train())
+        from mrn_b200 import _lib as L
+        for slot, gk in ((L.P_BN0_MEAN, "bn0_running_mean"), (L.P_BN0_VAR, "bn0_running_var"),
+                         (L.P_BN1_MEAN, "bn1_running_mean"), (L.P_BN1_VAR, "bn1_running_var")):
+            assert rel_err(tp.bn_stats[slot].cpu().numpy().reshape(-1), g[gk]) < 1e-4, gk
+
+
+@pytest.mark.parametrize("name", STAGE0_CASES)
+def test_stage0_clip_and_adam_step_matches_reference_golden(name):
+    from mrn_b200 import ops
+    g, cc, sd, tp, logits, c, bn_train, pre = _run_step(name)
+    m, v = torch.zeros_like(tp.params), torch.zeros_like(tp.params)
+    norm = ops.clip_adam(tp.params, tp.grads, m, v, 5e-4, 1, max_norm=5.0)
+    assert abs(float(norm) - float(g["grad_total_norm"])) / float(g["grad_total_norm"]) < 5e-4
+    for key, p in tp.state().items():
+        d = np.abs(pview(p.contiguous().cpu(), g) - g["adam1." + pre + key])
+        if _abs_scale_only(key, bn_train):
+            continue
+        if key.endswith("qkv.bias"):
+            n = d.size // 3
+            d = np.concatenate([d[:n], d[2 * n:]])
+        assert d.max() <= 5e-4 * 2.01 and (d > 2e-5).mean() < 2e-2, key
+
+
+def test_stage0_matches_oracle_on_a_fresh_batch_with_edge_case_targets():
+    """Oracle (autograd over the CPU restatement, fp64) vs the CUDA path on inputs that are not in the fixtures:
+    repeated labels, an empty target and an infeasible (too long for T with repeats) target."""
+    from mrn_b200 import ops
+    cc, B, seed = (41, 77), 4, 5
+    sd = synth.synth_state_dict(cc, seed)
+    img, tgt, lens, dom = synth.synth_batch(B, cc, seed)
+    tgt[0, :6] = torch.tensor([5, 5, 5, 9, 9, 5]); lens[0] = 6
+    lens[1] = 0; tgt[1] = 1
+    drop = synth.synth_drop_scales(2, B, O.svtr_drop_path_rates(), seed)[1]
+    r = O.stage0_loss_and_grads(sd, 1, img, tgt, lens, "batch", drop)
+    esd = {k[len("model.1."):]: v for k, v in sd.items() if k.startswith("model.1.")}
+    tp = ops.SvtrTrainPack(esd, "cuda")
+    x, t, l, dsc = img.cuda(), tgt.cuda(), lens.cuda(), drop.cuda().contiguous()
+    logits = ops.svtr_train_forward(tp, x, True, True, dsc)
+    rr = ops.gate_combine([logits], torch.ones(B, 1, device="cuda"), t, l)
+    c = ops.ctc_lattice(rr["lpe"], t, l, want_occ=True)
+    dlogits = ops.ctc_dense_grad(logits, rr["lse"], c["occ"], c["nll"], t, l, 1.0 / B)
+    ops.svtr_train_backward(tp, x, dlogits, True, dsc)
+    assert rel_err(logits.cpu().double().numpy(), r["logits"].numpy()) < 1e-4
+    assert abs(float(c["loss"]) - float(r["loss"])) / abs(float(r["loss"])) < 1e-4
+    tn = sum(float((v.double() ** 2).sum()) for v in r["grads"].values()) ** 0.5
+    for key, gg in tp.state(tp.grads).items():
+        ref = r["grads"]["model.1." + key].numpy()
+        scale = max(float(np.abs(ref).max()), 1e-4 * tn)
+        if _abs_scale_only(key, True):
+            scale = tn
+        assert np.abs(gg.cpu().double().numpy() - ref).max() / scale < 1e-3, key
+
+
+class _Loader:
+    """Stands in for data/data_manage.py's loader: get_batch() -> (images [B,4,32,256], label strings)."""
+
+    def __init__(self, images, labels):
+        self.images, self.labels, self.k = images, labels, 0
+
+    def get_batch(self):
+        self.k += 1
+        return self.images, self.labels
+
+    def __iter__(self):
+        yield self.images, self.labels
+
+
+def test_learner_init_train_follows_the_oracle_for_three_iterations(tmp_path, monkeypatch):
+    """MRN._init_train (reference API) on a fixed batch: per-iteration losses follow the CPU oracle's
+    stage0_step_cpu (same DropPath masks, OneCycle learning rates), the trained weights land back in the nn.Module
+    tree (state_dict keys unchanged) and the FF validation path sees them."""
+    from mrn_b200.il_modules.mrn import MRN, RankLocal, one_cycle_lr
+    from mrn_b200 import ops
+    monkeypatch.chdir(tmp_path)
+    cc, B, seed = (30,), 3, 3
+    chars = [chr(0x4E00 + i) for i in range(cc[0] - 4)]
+    sd = synth.synth_state_dict(cc, seed)
+    img, tgt, lens, dom = synth.synth_batch(B, cc, seed)
+    opt = make_opt()
+    opt.num_iter, opt.val_interval, opt.lan_list, opt.drop_path = 3, 100, ["x"], True
+    learner = MRN(opt)
+    learner.character = chars
+    learner.converter = learner.build_converter()
+    idx2ch = learner.converter.character
+    labels = ["".join(idx2ch[int(c)] for c in tgt[b, :int(lens[b])]) for b in range(B)]
+    learner.build_model()
+    learner.net.load_state_dict(sd, strict=True)
+    learner.model = RankLocal(learner.net).cuda()
+    learner.model.train()
+    # fixed DropPath masks for both sides
+    drops = [synth.synth_drop_scales(1, B, O.svtr_drop_path_rates(), 100 + k)[0] for k in range(3)]
+    import mrn_b200.il_modules.mrn as M
+    it = iter(drops)
+    monkeypatch.setattr(M, "sample_drop_scales", lambda n, b, rates, dev: next(it).unsqueeze(0).to(dev))
+    losses = []
+    orig = MRN.train_step_stage0
+
+    def spy(self, *a, **k):
+        out = orig(self, *a, **k)
+        losses.append(float(out))
+        return out
+    monkeypatch.setattr(MRN, "train_step_stage0", spy)
+    learner._init_train(0, 0, _Loader(img, labels), _Loader(img, labels))
+    # oracle
+    sdo = {k: v.clone() for k, v in sd.items()}
+    state = dict(step=0, m={}, v={})
+    ref_losses = []
+    for k in range(3):
+        ref_losses.append(O.stage0_step_cpu(sdo, 0, state, img, tgt, lens, lr=one_cycle_lr(k, 3, opt.lr), bn_mode="batch",
+                                            drop_scales=drops[k]))
+    assert np.allclose(losses, ref_losses, rtol=2e-3), (losses, ref_losses)
+    new_sd = learner.model.state_dict()
+    assert set(new_sd) == {"module." + k for k in sd}
+    w = "model.0.model.FeatureExtraction.ConvNet.blocks2.3.mlp.fc1.weight"
+    assert float((new_sd["module." + w].cpu() - sd[w]).abs().max()) > 1e-5            # it trained
+    assert rel_err(new_sd["module." + w].cpu().numpy(), sdo[w].numpy()) < 2e-2
+    out = learner.net(img.cuda(), cross=False, is_train=False)
+    assert torch.isfinite(out["logits"]).all()
