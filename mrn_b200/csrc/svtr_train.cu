@@ -706,7 +706,7 @@ TrainWs<AT> carve_train_ws(char* base, int B) {
   w.vis = W.take<AT>(u);
   w.feat = W.take<AT>((size_t)B * 64 * 256);
   w.big = W.take<AT>(u * 9 / 2);
-  w.dxa = W.take<float>(u); w.dy = W.take<float>(u); w.dbig = W.take<float>(u * 9 / 2);
+  w.dxa = W.take<float>(u); w.dy = W.take<float>(u * 2); w.dbig = W.take<float>(u * 9 / 2);
   w.dqkv = W.take<float>(u * 3); w.datt = W.take<float>(u); w.dln = W.take<float>(u); w.Dbuf = W.take<float>(u / 32);
   w.dfeat = W.take<float>((size_t)B * 64 * 256);
   w.bytes = W.off + 4096;
