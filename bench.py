@@ -50,8 +50,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph replay of the step")
     ap.add_argument("--sweep", default="", help="infer mode only: comma-separated per-GPU batch sizes (BASELINE configs[4]: 1..4096); "
                                                "adds a `sweep` array to the JSON line")
-    ap.add_argument("--mode", default="train", choices=["train", "infer"],
-                    help="train: router-training step (the BASELINE metric); infer: hard-routed forward + greedy decode (cfg 5)")
+    ap.add_argument("--mode", default="train", choices=["train", "infer", "stage0"],
+                    help="train: router-training step (the BASELINE metric); infer: hard-routed forward + greedy decode (cfg 5); "
+                         "stage0: expert-training step of the newest expert (SURVEY.md §8(f)3, il_modules/mrn.py:225-279)")
     return ap.parse_args()
 
 
@@ -131,6 +132,26 @@ def cpu_stage1(sample, steps, warmup, arch="svtr"):
     t0 = time.perf_counter()
     for _ in range(steps):
         O.stage1_step_cpu(sd, 6, state, img, tgt, lens, dom, drop_scales=drop)
+    dt = time.perf_counter() - t0
+    return sample * steps / dt, dt / steps * 1000.0, torch.get_num_threads()
+
+
+def cpu_stage0(sample, steps, warmup):
+    """Stage-0 expert-training step of the oracle port (torch CPU autograd) on a bounded sample."""
+    from oracle import mrn_oracle as O
+    from mrn_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cc = CLASS_COUNTS[-1:]
+    sd = synth.synth_state_dict(cc, 111)
+    img, tgt, lens, dom = synth.synth_batch(sample, cc, 111)
+    drop = synth.synth_drop_scales(1, sample, O.svtr_drop_path_rates(), 111)[0]
+    state = dict(step=0, m={}, v={})
+    for _ in range(warmup):
+        O.stage0_step_cpu(sd, 0, state, img, tgt, lens, drop_scales=drop)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.stage0_step_cpu(sd, 0, state, img, tgt, lens, drop_scales=drop)
     dt = time.perf_counter() - t0
     return sample * steps / dt, dt / steps * 1000.0, torch.get_num_threads()
 
@@ -240,10 +261,18 @@ def run_ours(args):
     h2d = sum(t.numel() * t.element_size() for t in host[0])
 
     infer = args.mode == "infer"
+    stage0 = args.mode == "stage0"
+    if stage0:
+        if args.arch != "svtr":
+            raise RuntimeError("--mode stage0 is implemented for SVTR experts")
+        opt.num_iter = 1000000
+        learner.begin_expert_training()                 # newest expert (C = 5153) -> flat training arena + fused Adam
+        mdist.broadcast_(learner._tp.params)
+        use_graph = False
     if infer:
         learner.model.eval()                            # validation(): model.eval(), hard route, greedy decode (test.py:139-221)
 
-    use_graph = not args.no_graph
+    use_graph = not args.no_graph and not stage0
     train_step = learner.train_step_stage1_graphed if use_graph else learner.train_step_stage1
     infer_step = learner.infer_batch_graphed if use_graph else learner.infer_batch
 
@@ -252,6 +281,9 @@ def run_ours(args):
         if infer:
             r = (learner.infer_batch if eager else infer_step)(img, "TF")
             return r["conf"], r["lens"]
+        if stage0:
+            l0 = learner.train_step_stage0(img, tgt, lens)
+            return l0, l0
         return (learner.train_step_stage1 if eager else train_step)(img, tgt, lens, dom)
 
     def step_e2e(k):
@@ -260,6 +292,9 @@ def run_ours(args):
             r = infer_step(img, "TF")
             ids = r["ids"].cpu()                        # the single D2H copy of the decoded ids (+ lengths, confidences)
             return float(r["conf"].sum()), float(r["lens"].sum()) + float(ids[0, 0])
+        if stage0:
+            l0 = float(learner.train_step_stage0(img, tgt, lens))
+            return l0, l0
         l1, l2 = train_step(img, tgt, lens, dom)
         return float(l1), float(l2)                     # D2H read of both losses (the reference logs them)
 
@@ -385,12 +420,24 @@ def run_ours(args):
         "ctc_router_ms_per_batch": round(ctc_router_ms, 3),
         "loss_clf": float(last[0]), "taski_loss": float(last[1]),
     }
+    if stage0:
+        out["metric"] = "MRN-SVTR stage-0 expert-training samples/s"
+        out["dtype"] = "f32" if learner._tp.prec == 0 else "bf16"
+        out["config"]["workload"] = ("SVTR-MRN stage-0 step: newest expert (C=5153) forward + CTC + full backward + clip/Adam, "
+                                     "B=%d/GPU, train mode (BN batch stats + DropPath)" % B)
+        out["config"]["expert_precision"] = out["dtype"]
+        out.pop("taski_loss", None)
     if infer:
         out["config"]["workload"] = ("%s-MRN 6-expert hard-routed inference + device greedy decode, B=%d/GPU, union charset 5153"
                                      % (args.arch.upper(), B))
         if args.sweep:
             out["sweep"] = infer_sweep(learner, [int(x) for x in args.sweep.split(",") if x], dev)
-    if world == 1 and not args.no_cpu_baseline and not infer:
+    if world == 1 and not args.no_cpu_baseline and stage0:
+        v, ms, cores = cpu_stage0(args.cpu_sample, 2, 1)
+        out["cpu_baseline"] = {"value": round(v, 3), "unit": "samples/s", "cores": cores, "kind": "port",
+                               "sample": "2 timed expert-training steps of %d samples, oracle port (torch CPU autograd), fp32, "
+                                         "%d threads" % (args.cpu_sample, cores)}
+    elif world == 1 and not args.no_cpu_baseline and not infer:
         v, ms, cores = cpu_stage1(args.cpu_sample, 2, 1, args.arch)
         out["cpu_baseline"] = {"value": round(v, 3), "unit": "samples/s", "cores": cores, "kind": "port",
                                "sample": "2 timed router-training steps of %d samples (same config, batch reduced from 256), "

@@ -122,8 +122,10 @@ int mrnb_svtr_experts_forward(const MrnbSvtrPack* pack, const float* image, int 
  * flat fp32 gradient arena [n_arena] (BN running-stat slots unused) that the backward zeroes and fills -- the same arena
  * layout serves mrnb_clip_adam and the NCCL all-reduce.  The workspace carries the saved activations from the forward
  * to the backward call (same pointer, same B).  drop_scales: NULL or [12,2,B] DropPath multipliers.
+ * MRNB_PREC_BF16: pack->h[] / fc_w16[0] must hold bf16 copies of the GEMM weights (qkv, proj, fc1, fc2, merge convs,
+ * seq, fc) refreshed after every optimiser step; the patch embedding and all statistics stay fp32.
  * logits / dlogits: [B,64,ld] fp32, first n_class[0] columns valid (dlogits from mrnb_ctc_dense_grad). */
-size_t mrnb_svtr_train_workspace_bytes(int B, int prec);
+size_t mrnb_svtr_train_workspace_bytes(int B, int n_class, int prec);
 int mrnb_svtr_train_forward(const MrnbSvtrPack* pack, const float* image, int B, int prec, int bn_batch_stats,
                             int update_running, const float* drop_scales, float* logits, long ld_logits, void* workspace,
                             size_t workspace_bytes, cudaStream_t stream);

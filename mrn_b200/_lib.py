@@ -63,7 +63,7 @@ _SIGNATURES = {
     "mrnb_svtr_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mrnb_svtr_experts_forward": (_i, [C.POINTER(MrnbSvtrPack), _vp, _i, _i, _i, _i, _i, _vp, _vp, C.POINTER(_vp),
                                        C.POINTER(_l), _vp, _sz, _vp]),
-    "mrnb_svtr_train_workspace_bytes": (_sz, [_i, _i]),
+    "mrnb_svtr_train_workspace_bytes": (_sz, [_i, _i, _i]),
     "mrnb_svtr_train_forward": (_i, [C.POINTER(MrnbSvtrPack), _vp, _i, _i, _i, _i, _vp, _vp, _l, _vp, _sz, _vp]),
     "mrnb_svtr_train_backward": (_i, [C.POINTER(MrnbSvtrPack), C.POINTER(MrnbSvtrPack), _vp, _vp, _l, _i, _i, _i, _vp,
                                       _vp, _l, _vp, _sz, _vp]),

@@ -640,9 +640,28 @@ int attention_train_bwd(const AT* qkv, const AT* o, const float* dO, const float
 }
 
 // ------------------------------------------------------------------------------------------------
-// Backward GEMMs.  dX[M,K] = dY[M,N] . W[N,K];   dW[N,K] (+)= dY[M,N]^T . X[M,K]  (split over the M rows, atomics into a
-// zeroed dW).  fp32: CUDA cores (gemm_f32.cu); bf16: the general tcgen05 engine reading every tensor where it lies.
+// GEMM dispatch.  Forward Linear: linear<AT>() (CUDA cores fp32 / persistent tcgen05 bf16).  Backward:
+//   dX[M,K] = dY[M,N] . W[N,K];   dW[N,K] (+)= dY[M,N]^T . X[M,K]  (split over the M rows, atomics into a zeroed dW).
+// fp32: gemm_f32.cu.  bf16: the general tcgen05 engine (gemm_tc2.cu) reading every tensor where it lies -- dY K-major
+// and W MN-major for dX; dY and X both MN-major for dW -- so no transposed copy is ever made.  A contraction length
+// that is not a multiple of 64 (the ragged charset C) is rounded up: TMA zero-fills both operands beyond their extent.
 // ------------------------------------------------------------------------------------------------
+typedef __nv_bfloat16 bf16;
+
+template <typename AT>
+int lin(const AT* A, long lda, const float* W32, const void* W16, const float* bias, void* out, long ldo, bool out_f32,
+        int M, int N, int K, const float* res, const float* rowscale, int rows_per_scale, cudaStream_t st) {
+  LinearArgs a{};
+  a.A = A; a.lda = lda; a.a_gstride = (long)M * lda;
+  a.W32 = W32; a.W16 = W16; a.w_gstride = (long)N * K;
+  a.bias = bias; a.bias_gstride = N;
+  a.out = out; a.ldo = ldo; a.o_gstride = (long)M * ldo; a.out_is_f32 = out_f32 ? 1 : 0;
+  a.res = res; a.rowscale = rowscale; a.rows_per_scale = rows_per_scale;
+  a.M = M; a.N = N; a.K = K; a.groups = 1;
+  if (sizeof(AT) == 2) MRNB_CHECK_ARG(W16, "svtr_train: bf16 mode needs the 16-bit weight shadow (pack->h / fc_w16)");
+  return linear<AT>(a, st);
+}
+
 int gemm_dx_f32(const float* dY, long ldy, const float* W, float* dX, long ldx, int M, int N, int K, cudaStream_t st) {
   MrnbGemm g{};
   g.A = dY; g.am = mrnb_axis(ldy); g.ak = mrnb_axis(1); g.a_kfast = 1;
@@ -666,6 +685,42 @@ int gemm_dw_f32(const float* dY, long ldy, const float* X, long ldx, float* dW, 
   g.splitk = (int)sk;
   return mrnb_sgemm(g, st);
 }
+int gemm_dx_tc(const bf16* dY, long ldy, const void* W16, float* dX, bf16* dX16, long ldx, int M, int N, int K, cudaStream_t st) {
+  MrnbTcGemm2 g{};
+  g.a = mrnb_operand_k2d(dY, M, N, ldy, 128, 1);
+  g.b = mrnb_operand_mn2d(W16, K, N, K, 1);
+  g.out32 = dX; g.out16 = dX16; g.cm = mrnb_axis(ldx); g.cn = mrnb_axis(1);
+  g.M = M; g.N = K; g.K = (N + 63) / 64 * 64; g.groups = 1; g.splitk = 1; g.alpha = 1.f;
+  return mrnb_tc_gemm2(g, st);
+}
+int gemm_dw_tc(const bf16* dY, long ldy, const bf16* X, long ldx, float* dW, int rows, int N, int K, cudaStream_t st) {
+  MRNB_CHECK_ARG(rows % 64 == 0, "svtr_train: dW contraction length %d must be a multiple of 64", rows);
+  MrnbTcGemm2 g{};
+  g.a = mrnb_operand_mn2d(dY, N, rows, ldy, 1);
+  g.b = mrnb_operand_mn2d(X, K, rows, ldx, 1);
+  g.out32 = dW; g.cm = mrnb_axis(K); g.cn = mrnb_axis(1);
+  g.M = N; g.N = K; g.K = rows; g.groups = 1; g.alpha = 1.f;
+  const long tiles = (long)cdiv(N, 128) * cdiv(K, K >= 128 ? 128 : 64);
+  long sk = (148L * 3 + tiles - 1) / tiles;
+  const long maxsk = rows / 256 > 0 ? rows / 256 : 1;
+  if (sk > maxsk) sk = maxsk;
+  if (sk < 1) sk = 1;
+  g.splitk = (int)sk;
+  return mrnb_tc_gemm2(g, st);
+}
+// one gradient tensor in both flavours: fp32 (elementwise math, bias sums) and, in bf16 mode, its 16-bit GEMM operand
+struct Grad { const float* f; const bf16* h; long ld; };
+
+template <typename AT>
+int gemm_dx(const Grad& dY, const float* W32, const void* W16, float* dX, bf16* dX16, long ldx, int M, int N, int K, cudaStream_t st) {
+  if constexpr (sizeof(AT) == 4) return gemm_dx_f32(dY.f, dY.ld, W32, dX, ldx, M, N, K, st);
+  else return gemm_dx_tc(dY.h, dY.ld, W16, dX, dX16, ldx, M, N, K, st);
+}
+template <typename AT>
+int gemm_dw(const Grad& dY, const AT* X, long ldx, float* dW, int rows, int N, int K, cudaStream_t st) {
+  if constexpr (sizeof(AT) == 4) return gemm_dw_f32(dY.f, dY.ld, X, ldx, dW, rows, N, K, st);
+  else return gemm_dw_tc(dY.h, dY.ld, X, ldx, dW, rows, N, K, st);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Workspace
@@ -681,11 +736,12 @@ struct TrainWs {
   AT *vis, *feat, *big;
   // backward scratch
   float *dxa, *dy, *dbig, *dqkv, *datt, *dln, *Dbuf, *dfeat;
+  bf16 *dy16, *dbig16, *dqkv16, *dfeat16, *dlog16;       // bf16 mode: GEMM-operand copies of the gradients
   size_t bytes;
 };
 
 template <typename AT>
-TrainWs<AT> carve_train_ws(char* base, int B) {
+TrainWs<AT> carve_train_ws(char* base, int B, int n_class) {
   TrainWs<AT> w{};
   Workspace W{base, 0, (size_t)-1};
   const size_t u = (size_t)B * 32768;
@@ -707,27 +763,45 @@ TrainWs<AT> carve_train_ws(char* base, int B) {
   w.feat = W.take<AT>((size_t)B * 64 * 256);
   w.big = W.take<AT>(u * 9 / 2);
   w.dxa = W.take<float>(u); w.dy = W.take<float>(u * 2); w.dbig = W.take<float>(u * 9 / 2);
-  w.dqkv = W.take<float>(u * 3); w.datt = W.take<float>(u); w.dln = W.take<float>(u); w.Dbuf = W.take<float>(u / 32);
+  w.datt = W.take<float>(u); w.dln = W.take<float>(u); w.Dbuf = W.take<float>(u / 32);
   w.dfeat = W.take<float>((size_t)B * 64 * 256);
+  if (sizeof(AT) == 4) {
+    w.dqkv = W.take<float>(u * 3);
+  } else {
+    w.dy16 = W.take<bf16>(u); w.dbig16 = W.take<bf16>(u * 4); w.dqkv16 = W.take<bf16>(u * 3);
+    w.dfeat16 = W.take<bf16>((size_t)B * 64 * 256);
+    w.dlog16 = W.take<bf16>((size_t)B * 64 * ((n_class + 7) / 8 * 8));
+  }
   w.bytes = W.off + 4096;
   return w;
 }
 
 inline float* gp(const MrnbSvtrPack& G, int slot) { return const_cast<float*>(G.p[slot]); }
 
+// fp32 [rows, C] (ld) -> bf16 [rows, ld16], columns C..ld16 zero
+__global__ void cast_pad_rows_kernel(const float* __restrict__ x, long ld, int C, bf16* __restrict__ y, long ld16, long total) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long r = i / ld16;
+  const int c = (int)(i % ld16);
+  y[i] = __float2bfloat16_rn(c < C ? x[r * ld + c] : 0.f);
+}
+
 // ------------------------------------------------------------------------------------------------
-// Forward (fp32 mode)
+// Forward
 // ------------------------------------------------------------------------------------------------
-int train_forward_f32(const MrnbSvtrPack& P, const float* image, int B, int bn_batch, int update_running,
-                      const float* drop /*[12,2,B] or null*/, float* logits, long ld, void* ws, size_t ws_bytes,
-                      cudaStream_t st) {
-  typedef float AT;
-  TrainWs<AT> w = carve_train_ws<AT>((char*)ws, B);
+template <typename AT>
+int train_forward_t(const MrnbSvtrPack& P, const float* image, int B, int bn_batch, int update_running,
+                    const float* drop /*[12,2,B] or null*/, float* logits, long ld, void* ws, size_t ws_bytes,
+                    cudaStream_t st) {
+  TrainWs<AT> w = carve_train_ws<AT>((char*)ws, B, P.n_class[0]);
   MRNB_CHECK_ARG(ws_bytes >= w.bytes, "svtr_train_forward: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
   const long u = (long)B * 32768;
-  // ---- patch embedding: conv0 -> BN -> GELU -> conv1 -> BN -> GELU -> + pos_embed
+  // ---- patch embedding: conv0 -> BN -> GELU -> conv1 -> BN -> GELU -> + pos_embed  (fp32 in both modes: K = 36 / 288,
+  //      0.9 % of the step's FLOPs, and the BatchNorm statistics want the fp32 convolution output)
   if (bn_batch) cudaMemsetAsync(w.stats, 0, 96 * 2 * sizeof(double), st);
   {
+    mrnb_prof_begin(MRNB_PROF_CONV, st, 0.0, 0.0);
     const long total = (long)B * 2048 * 36;
     im2col_img_kernel<<<cdiv(total, 256), 256, 0, st>>>(image, w.colf, total);
     MRNB_CHECK_LAUNCH("im2col_img_kernel");
@@ -755,108 +829,102 @@ int train_forward_f32(const MrnbSvtrPack& P, const float* image, int B, int bn_b
     MRNB_CHECK_LAUNCH("bn_finalize_train_kernel");
     bn_gelu_kernel<<<cdiv(u / 4, 256), 256, 0, st>>>(w.raw1, w.ss + 64, P.p[MRNB_P_POS_EMBED], 512, w.stage_in[0], 64, u / 4);
     MRNB_CHECK_LAUNCH("bn_gelu_kernel");
+    mrnb_prof_end(MRNB_PROF_CONV, st);
   }
   int blk = 0;
   for (int s = 0; s < 3; ++s) {
     const int d = DIMS[s], N = 32768 / d, heads = HEADS[s], H = GH[s], Wd = 64;
-    const long rows = (long)B * N;
+    const int rows = B * N;
     for (int j = 0; j < DEPTH[s]; ++j, ++blk) {
       const int pb = MRNB_P_BLOCK0 + blk * MRNB_PB_COUNT;
       const float* xin = j == 0 ? w.stage_in[s] : w.xout[blk - 1];
       MRNB_TRY(launch_ln_fwd<AT>(xin, w.ln1[blk], P.p[pb + MRNB_PB_NORM1_W], P.p[pb + MRNB_PB_NORM1_B], rows, d, 1e-6f, st));
-      {
-        MrnbGemm g = mrnb_gemm_nt(w.ln1[blk], d, P.p[pb + MRNB_PB_QKV_W], d, w.qkv[blk], 3 * d, (int)rows, 3 * d, d);
-        g.bias_n = P.p[pb + MRNB_PB_QKV_B];
-        MRNB_TRY(mrnb_sgemm(g, st));
-      }
+      MRNB_TRY(lin<AT>(w.ln1[blk], d, P.p[pb + MRNB_PB_QKV_W], P.h[pb + MRNB_PB_QKV_W], P.p[pb + MRNB_PB_QKV_B], w.qkv[blk],
+                       3 * d, false, rows, 3 * d, d, nullptr, nullptr, 1, st));
       MRNB_TRY(attention_train_fwd<AT>(w.qkv[blk], w.att[blk], w.lse[blk], B, N, d, heads, H, Wd, blk < 6, st));
-      {
-        MrnbGemm g = mrnb_gemm_nt(w.att[blk], d, P.p[pb + MRNB_PB_PROJ_W], d, w.xmid[blk], d, (int)rows, d, d);
-        g.bias_n = P.p[pb + MRNB_PB_PROJ_B]; g.res = xin;
-        if (drop) { g.rowscale = drop + ((size_t)blk * 2 + 0) * B; g.rows_per_scale = N; }
-        MRNB_TRY(mrnb_sgemm(g, st));
-      }
+      MRNB_TRY(lin<AT>(w.att[blk], d, P.p[pb + MRNB_PB_PROJ_W], P.h[pb + MRNB_PB_PROJ_W], P.p[pb + MRNB_PB_PROJ_B],
+                       w.xmid[blk], d, true, rows, d, d, xin, drop ? drop + ((size_t)blk * 2 + 0) * B : nullptr, N, st));
       MRNB_TRY(launch_ln_fwd<AT>(w.xmid[blk], w.ln2[blk], P.p[pb + MRNB_PB_NORM2_W], P.p[pb + MRNB_PB_NORM2_B], rows, d, 1e-6f, st));
-      {
-        MrnbGemm g = mrnb_gemm_nt(w.ln2[blk], d, P.p[pb + MRNB_PB_FC1_W], d, w.hpre[blk], 4 * d, (int)rows, 4 * d, d);
-        g.bias_n = P.p[pb + MRNB_PB_FC1_B];
-        MRNB_TRY(mrnb_sgemm(g, st));
-        const long n = rows * 4 * d;
-        gelu_fwd_kernel<AT><<<cdiv(n, 256), 256, 0, st>>>(w.hpre[blk], w.hact[blk], n);
-        MRNB_CHECK_LAUNCH("gelu_fwd_kernel");
-        MrnbGemm g2 = mrnb_gemm_nt(w.hact[blk], 4 * d, P.p[pb + MRNB_PB_FC2_W], 4 * d, w.xout[blk], d, (int)rows, d, 4 * d);
-        g2.bias_n = P.p[pb + MRNB_PB_FC2_B]; g2.res = w.xmid[blk];
-        if (drop) { g2.rowscale = drop + ((size_t)blk * 2 + 1) * B; g2.rows_per_scale = N; }
-        MRNB_TRY(mrnb_sgemm(g2, st));
-      }
+      MRNB_TRY(lin<AT>(w.ln2[blk], d, P.p[pb + MRNB_PB_FC1_W], P.h[pb + MRNB_PB_FC1_W], P.p[pb + MRNB_PB_FC1_B], w.hpre[blk],
+                       4 * d, false, rows, 4 * d, d, nullptr, nullptr, 1, st));
+      const long n = (long)rows * 4 * d;
+      gelu_fwd_kernel<AT><<<cdiv(n, 256), 256, 0, st>>>(w.hpre[blk], w.hact[blk], n);
+      MRNB_CHECK_LAUNCH("gelu_fwd_kernel");
+      MRNB_TRY(lin<AT>(w.hact[blk], 4 * d, P.p[pb + MRNB_PB_FC2_W], P.h[pb + MRNB_PB_FC2_W], P.p[pb + MRNB_PB_FC2_B],
+                       w.xout[blk], d, true, rows, d, 4 * d, w.xmid[blk], drop ? drop + ((size_t)blk * 2 + 1) * B : nullptr, N, st));
     }
     // SubSample: conv 3x3 stride (2,1) -> LN(eps 1e-5)
     const int Co = OUTS[s], Ho = H / 2;
-    const long orows = (long)B * Ho * Wd;
+    const int orows = B * Ho * Wd;
     const int ps = MRNB_P_SUB0 + s * MRNB_PS_COUNT;
-    const long c4 = orows * 9 * d / 4;
+    const long c4 = (long)orows * 9 * d / 4;
     im2col_nhwc_kernel<AT><<<cdiv(c4, 256), 256, 0, st>>>(w.xout[blk - 1], w.big, H, Wd, d, Ho, Wd, 2, 1, c4);
     MRNB_CHECK_LAUNCH("im2col_nhwc_kernel");
-    MrnbGemm g = mrnb_gemm_nt(w.big, 9 * d, P.p[ps + MRNB_PS_CONV_W], 9 * d, w.cv[s], Co, (int)orows, Co, 9 * d);
-    g.bias_n = P.p[ps + MRNB_PS_CONV_B];
-    MRNB_TRY(mrnb_sgemm(g, st));
+    MRNB_TRY(lin<AT>(w.big, 9 * d, P.p[ps + MRNB_PS_CONV_W], P.h[ps + MRNB_PS_CONV_W], P.p[ps + MRNB_PS_CONV_B], w.cv[s], Co,
+                     true, orows, Co, 9 * d, nullptr, nullptr, 1, st));
     if (s < 2) MRNB_TRY(launch_ln_fwd<float>(w.cv[s], w.stage_in[s + 1], P.p[ps + MRNB_PS_NORM_W], P.p[ps + MRNB_PS_NORM_B], orows, Co, 1e-5f, st));
     else MRNB_TRY(launch_ln_fwd<AT>(w.cv[s], w.vis, P.p[ps + MRNB_PS_NORM_W], P.p[ps + MRNB_PS_NORM_B], orows, Co, 1e-5f, st));
   }
-  {
-    const int M = B * 64;
-    MrnbGemm g = mrnb_gemm_nt(w.vis, 512, P.p[MRNB_P_SEQ_W], 512, w.feat, 256, M, 256, 512);
-    g.bias_n = P.p[MRNB_P_SEQ_B];
-    MRNB_TRY(mrnb_sgemm(g, st));
-    MrnbGemm h = mrnb_gemm_nt(w.feat, 256, P.fc_w[0], 256, logits, ld, M, P.n_class[0], 256);
-    h.bias_n = P.fc_b[0];
-    MRNB_TRY(mrnb_sgemm(h, st));
-  }
+  const int M = B * 64;
+  MRNB_TRY(lin<AT>(w.vis, 512, P.p[MRNB_P_SEQ_W], P.h[MRNB_P_SEQ_W], P.p[MRNB_P_SEQ_B], w.feat, 256, false, M, 256, 512,
+                   nullptr, nullptr, 1, st));
+  MRNB_TRY(lin<AT>(w.feat, 256, P.fc_w[0], P.fc_w16[0], P.fc_b[0], logits, ld, true, M, P.n_class[0], 256, nullptr, nullptr, 1, st));
   return MRNB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
-// Backward (fp32 mode).  G holds the gradient pointers in the same slots; the caller passes the flat gradient arena
-// so it is zeroed with one memset (split-K GEMMs, LayerNorm / bias sums accumulate with atomics).
+// Backward.  G holds the gradient pointers in the same slots; the caller passes the flat gradient arena so that it is
+// zeroed with one memset (split-K GEMMs, LayerNorm / bias sums accumulate with atomics).
 // ------------------------------------------------------------------------------------------------
-int train_backward_f32(const MrnbSvtrPack& P, const MrnbSvtrPack& G, const float* image, const float* dlogits, long ldg,
-                       int B, int bn_batch, const float* drop, float* grad_arena, long n_arena, void* ws, size_t ws_bytes,
-                       cudaStream_t st) {
-  typedef float AT;
-  TrainWs<AT> w = carve_train_ws<AT>((char*)ws, B);
+template <typename AT>
+int train_backward_t(const MrnbSvtrPack& P, const MrnbSvtrPack& G, const float* image, const float* dlogits, long ldg,
+                     int B, int bn_batch, const float* drop, float* grad_arena, long n_arena, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+  constexpr bool TC = sizeof(AT) == 2;
+  TrainWs<AT> w = carve_train_ws<AT>((char*)ws, B, P.n_class[0]);
   MRNB_CHECK_ARG(ws_bytes >= w.bytes, "svtr_train_backward: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
   cudaMemsetAsync(grad_arena, 0, (size_t)n_arena * sizeof(float), st);
   const long u = (long)B * 32768;
   const int M = B * 64, C = P.n_class[0];
   // ---- CTC head and the 512 -> 256 Linear
+  Grad dlog{dlogits, nullptr, ldg};
+  if (TC) {
+    const long ld16 = (C + 7) / 8 * 8;
+    const long total = (long)M * ld16;
+    cast_pad_rows_kernel<<<cdiv(total, 256), 256, 0, st>>>(dlogits, ldg, C, w.dlog16, ld16, total);
+    MRNB_CHECK_LAUNCH("cast_pad_rows_kernel");
+    dlog = Grad{dlogits, w.dlog16, ld16};
+  }
   MRNB_TRY(launch_colsum<float>(dlogits, ldg, M, C, const_cast<float*>(G.fc_b[0]), st));
-  MRNB_TRY(gemm_dw_f32(dlogits, ldg, w.feat, 256, const_cast<float*>(G.fc_w[0]), M, C, 256, st));
-  MRNB_TRY(gemm_dx_f32(dlogits, ldg, P.fc_w[0], w.dfeat, 256, M, C, 256, st));
+  MRNB_TRY(gemm_dw<AT>(dlog, w.feat, 256, const_cast<float*>(G.fc_w[0]), M, C, 256, st));
+  MRNB_TRY(gemm_dx<AT>(dlog, P.fc_w[0], P.fc_w16[0], w.dfeat, w.dfeat16, 256, M, C, 256, st));
+  Grad dfe{w.dfeat, w.dfeat16, 256};
   MRNB_TRY(launch_colsum<float>(w.dfeat, 256, M, 256, gp(G, MRNB_P_SEQ_B), st));
-  MRNB_TRY(gemm_dw_f32(w.dfeat, 256, w.vis, 512, gp(G, MRNB_P_SEQ_W), M, 256, 512, st));
-  MRNB_TRY(gemm_dx_f32(w.dfeat, 256, P.p[MRNB_P_SEQ_W], w.dln, 512, M, 256, 512, st));       // d vis
+  MRNB_TRY(gemm_dw<AT>(dfe, w.vis, 512, gp(G, MRNB_P_SEQ_W), M, 256, 512, st));
+  MRNB_TRY(gemm_dx<AT>(dfe, P.p[MRNB_P_SEQ_W], P.h[MRNB_P_SEQ_W], w.dln, nullptr, 512, M, 256, 512, st));       // d vis
   float* dx = w.dxa;          // gradient w.r.t. the residual stream
-  float* dcv = w.dy;          // gradient w.r.t. a SubSample conv output
+  float* dcv = w.dy;          // gradient w.r.t. a SubSample conv output (+ its 16-bit copy in dy16)
   {
     const int ps = MRNB_P_SUB0 + 2 * MRNB_PS_COUNT;
-    MRNB_TRY(launch_ln_bwd(w.cv[2], w.dln, P.p[ps + MRNB_PS_NORM_W], nullptr, dcv, nullptr, gp(G, ps + MRNB_PS_NORM_W),
+    MRNB_TRY(launch_ln_bwd(w.cv[2], w.dln, P.p[ps + MRNB_PS_NORM_W], nullptr, dcv, w.dy16, gp(G, ps + MRNB_PS_NORM_W),
                            gp(G, ps + MRNB_PS_NORM_B), M, 512, 1e-5f, st));
   }
   int blk = 12;
   for (int s = 2; s >= 0; --s) {
     const int d = DIMS[s], N = 32768 / d, heads = HEADS[s], H = GH[s], Wd = 64;
-    const long rows = (long)B * N;
+    const int rows = B * N;
     const int Co = OUTS[s], Ho = H / 2;
-    const long orows = (long)B * Ho * Wd;
+    const int orows = B * Ho * Wd;
     const int ps = MRNB_P_SUB0 + s * MRNB_PS_COUNT;
     // ---- SubSample conv backward (im2col recomputed from the stage output)
     {
+      Grad gcv{dcv, w.dy16, Co};
       MRNB_TRY(launch_colsum<float>(dcv, Co, orows, Co, gp(G, ps + MRNB_PS_CONV_B), st));
-      const long c4 = orows * 9 * d / 4;
+      const long c4 = (long)orows * 9 * d / 4;
       im2col_nhwc_kernel<AT><<<cdiv(c4, 256), 256, 0, st>>>(w.xout[blk - 1], w.big, H, Wd, d, Ho, Wd, 2, 1, c4);
       MRNB_CHECK_LAUNCH("im2col_nhwc_kernel");
-      MRNB_TRY(gemm_dw_f32(dcv, Co, w.big, 9 * d, gp(G, ps + MRNB_PS_CONV_W), (int)orows, Co, 9 * d, st));
-      MRNB_TRY(gemm_dx_f32(dcv, Co, P.p[ps + MRNB_PS_CONV_W], w.dbig, 9 * d, (int)orows, Co, 9 * d, st));
+      MRNB_TRY(gemm_dw<AT>(gcv, w.big, 9 * d, gp(G, ps + MRNB_PS_CONV_W), orows, Co, 9 * d, st));
+      MRNB_TRY(gemm_dx<AT>(gcv, P.p[ps + MRNB_PS_CONV_W], P.h[ps + MRNB_PS_CONV_W], w.dbig, nullptr, 9 * d, orows, Co, 9 * d, st));
       col2im_nhwc_kernel<<<cdiv(u / 4, 256), 256, 0, st>>>(w.dbig, dx, H, Wd, d, Ho, Wd, 2, 1, u / 4);
       MRNB_CHECK_LAUNCH("col2im_nhwc_kernel");
     }
@@ -865,49 +933,60 @@ int train_backward_f32(const MrnbSvtrPack& P, const MrnbSvtrPack& G, const float
       const int pb = MRNB_P_BLOCK0 + blk * MRNB_PB_COUNT;
       const float* xin = j == 0 ? w.stage_in[s] : w.xout[blk - 1];
       // ---- MLP branch: xout = xmid + ds1 * (GELU(LN2(xmid) W1^T + b1) W2^T + b2)
-      const float* dyv = dx;
-      if (drop) {
-        scale_rows_kernel<<<cdiv(u, 256), 256, 0, st>>>(dx, drop + ((size_t)blk * 2 + 1) * B, N, d, w.dy, nullptr, u);
+      Grad gy{dx, w.dy16, d};
+      if (drop || TC) {
+        scale_rows_kernel<<<cdiv(u, 256), 256, 0, st>>>(dx, drop ? drop + ((size_t)blk * 2 + 1) * B : nullptr, N, d,
+                                                        drop ? w.dy : nullptr, w.dy16, u);
         MRNB_CHECK_LAUNCH("scale_rows_kernel");
-        dyv = w.dy;
+        if (drop) gy.f = w.dy;
       }
-      MRNB_TRY(launch_colsum<float>(dyv, d, rows, d, gp(G, pb + MRNB_PB_FC2_B), st));
-      MRNB_TRY(gemm_dw_f32(dyv, d, w.hact[blk], 4 * d, gp(G, pb + MRNB_PB_FC2_W), (int)rows, d, 4 * d, st));
-      MRNB_TRY(gemm_dx_f32(dyv, d, P.p[pb + MRNB_PB_FC2_W], w.dbig, 4 * d, (int)rows, d, 4 * d, st));
-      gelu_bwd_kernel<AT><<<cdiv(u * 4, 256), 256, 0, st>>>(w.hpre[blk], w.dbig, nullptr, u * 4);
+      MRNB_TRY(launch_colsum<float>(gy.f, d, rows, d, gp(G, pb + MRNB_PB_FC2_B), st));
+      MRNB_TRY(gemm_dw<AT>(gy, w.hact[blk], 4 * d, gp(G, pb + MRNB_PB_FC2_W), rows, d, 4 * d, st));
+      MRNB_TRY(gemm_dx<AT>(gy, P.p[pb + MRNB_PB_FC2_W], P.h[pb + MRNB_PB_FC2_W], w.dbig, nullptr, 4 * d, rows, d, 4 * d, st));
+      gelu_bwd_kernel<AT><<<cdiv(u * 4, 256), 256, 0, st>>>(w.hpre[blk], w.dbig, w.dbig16, u * 4);
       MRNB_CHECK_LAUNCH("gelu_bwd_kernel");
+      Grad gh{w.dbig, w.dbig16, 4L * d};
       MRNB_TRY(launch_colsum<float>(w.dbig, 4 * d, rows, 4 * d, gp(G, pb + MRNB_PB_FC1_B), st));
-      MRNB_TRY(gemm_dw_f32(w.dbig, 4 * d, w.ln2[blk], d, gp(G, pb + MRNB_PB_FC1_W), (int)rows, 4 * d, d, st));
-      MRNB_TRY(gemm_dx_f32(w.dbig, 4 * d, P.p[pb + MRNB_PB_FC1_W], w.dln, d, (int)rows, 4 * d, d, st));
+      MRNB_TRY(gemm_dw<AT>(gh, w.ln2[blk], d, gp(G, pb + MRNB_PB_FC1_W), rows, 4 * d, d, st));
+      MRNB_TRY(gemm_dx<AT>(gh, P.p[pb + MRNB_PB_FC1_W], P.h[pb + MRNB_PB_FC1_W], w.dln, nullptr, d, rows, 4 * d, d, st));
       MRNB_TRY(launch_ln_bwd(w.xmid[blk], w.dln, P.p[pb + MRNB_PB_NORM2_W], dx, dx, nullptr, gp(G, pb + MRNB_PB_NORM2_W),
                              gp(G, pb + MRNB_PB_NORM2_B), rows, d, 1e-6f, st));
       // ---- mixer branch: xmid = xin + ds0 * (Attn(LN1(xin)) Wp^T + bp)
-      dyv = dx;
-      if (drop) {
-        scale_rows_kernel<<<cdiv(u, 256), 256, 0, st>>>(dx, drop + ((size_t)blk * 2 + 0) * B, N, d, w.dy, nullptr, u);
+      gy = Grad{dx, w.dy16, d};
+      if (drop || TC) {
+        scale_rows_kernel<<<cdiv(u, 256), 256, 0, st>>>(dx, drop ? drop + ((size_t)blk * 2 + 0) * B : nullptr, N, d,
+                                                        drop ? w.dy : nullptr, w.dy16, u);
         MRNB_CHECK_LAUNCH("scale_rows_kernel");
-        dyv = w.dy;
+        if (drop) gy.f = w.dy;
       }
-      MRNB_TRY(launch_colsum<float>(dyv, d, rows, d, gp(G, pb + MRNB_PB_PROJ_B), st));
-      MRNB_TRY(gemm_dw_f32(dyv, d, w.att[blk], d, gp(G, pb + MRNB_PB_PROJ_W), (int)rows, d, d, st));
-      MRNB_TRY(gemm_dx_f32(dyv, d, P.p[pb + MRNB_PB_PROJ_W], w.datt, d, (int)rows, d, d, st));
-      MRNB_TRY((attention_train_bwd<AT, float>(w.qkv[blk], w.att[blk], w.datt, w.lse[blk], w.Dbuf, w.dqkv, B, N, d, heads, H,
-                                               Wd, blk < 6, st)));
-      MRNB_TRY(launch_colsum<float>(w.dqkv, 3 * d, rows, 3 * d, gp(G, pb + MRNB_PB_QKV_B), st));
-      MRNB_TRY(gemm_dw_f32(w.dqkv, 3 * d, w.ln1[blk], d, gp(G, pb + MRNB_PB_QKV_W), (int)rows, 3 * d, d, st));
-      MRNB_TRY(gemm_dx_f32(w.dqkv, 3 * d, P.p[pb + MRNB_PB_QKV_W], w.dln, d, (int)rows, 3 * d, d, st));
+      MRNB_TRY(launch_colsum<float>(gy.f, d, rows, d, gp(G, pb + MRNB_PB_PROJ_B), st));
+      MRNB_TRY(gemm_dw<AT>(gy, w.att[blk], d, gp(G, pb + MRNB_PB_PROJ_W), rows, d, d, st));
+      MRNB_TRY(gemm_dx<AT>(gy, P.p[pb + MRNB_PB_PROJ_W], P.h[pb + MRNB_PB_PROJ_W], w.datt, nullptr, d, rows, d, d, st));
+      Grad gq{w.dqkv, w.dqkv16, 3L * d};
+      if constexpr (TC) {
+        MRNB_TRY((attention_train_bwd<AT, bf16>(w.qkv[blk], w.att[blk], w.datt, w.lse[blk], w.Dbuf, w.dqkv16, B, N, d, heads,
+                                                H, Wd, blk < 6, st)));
+        MRNB_TRY(launch_colsum<bf16>(w.dqkv16, 3 * d, rows, 3 * d, gp(G, pb + MRNB_PB_QKV_B), st));
+      } else {
+        MRNB_TRY((attention_train_bwd<AT, float>(w.qkv[blk], w.att[blk], w.datt, w.lse[blk], w.Dbuf, w.dqkv, B, N, d, heads,
+                                                 H, Wd, blk < 6, st)));
+        MRNB_TRY(launch_colsum<float>(w.dqkv, 3 * d, rows, 3 * d, gp(G, pb + MRNB_PB_QKV_B), st));
+      }
+      MRNB_TRY(gemm_dw<AT>(gq, w.ln1[blk], d, gp(G, pb + MRNB_PB_QKV_W), rows, 3 * d, d, st));
+      MRNB_TRY(gemm_dx<AT>(gq, P.p[pb + MRNB_PB_QKV_W], P.h[pb + MRNB_PB_QKV_W], w.dln, nullptr, d, rows, 3 * d, d, st));
       MRNB_TRY(launch_ln_bwd(xin, w.dln, P.p[pb + MRNB_PB_NORM1_W], dx, dx, nullptr, gp(G, pb + MRNB_PB_NORM1_W),
                              gp(G, pb + MRNB_PB_NORM1_B), rows, d, 1e-6f, st));
     }
     if (s > 0) {
       // stage input = LN(conv output of the previous merge)
       const int pq = MRNB_P_SUB0 + (s - 1) * MRNB_PS_COUNT;
-      MRNB_TRY(launch_ln_bwd(w.cv[s - 1], dx, P.p[pq + MRNB_PS_NORM_W], nullptr, dcv, nullptr, gp(G, pq + MRNB_PS_NORM_W),
+      MRNB_TRY(launch_ln_bwd(w.cv[s - 1], dx, P.p[pq + MRNB_PS_NORM_W], nullptr, dcv, w.dy16, gp(G, pq + MRNB_PS_NORM_W),
                              gp(G, pq + MRNB_PS_NORM_B), rows, d, 1e-5f, st));
     }
   }
-  // ---- patch embedding backward: dx is the gradient w.r.t. x0 = GELU(BN1(conv1)) + pos_embed
+  // ---- patch embedding backward (fp32): dx is the gradient w.r.t. x0 = GELU(BN1(conv1)) + pos_embed
   {
+    mrnb_prof_begin(MRNB_PROF_CONV, st, 0.0, 0.0);
     const long per = 512L * 64;
     pos_grad_kernel<<<cdiv(per, 256), 256, 0, st>>>(dx, gp(G, MRNB_P_POS_EMBED), B, per);
     MRNB_CHECK_LAUNCH("pos_grad_kernel");
@@ -941,15 +1020,16 @@ int train_backward_f32(const MrnbSvtrPack& P, const MrnbSvtrPack& G, const float
     im2col_img_kernel<<<cdiv(total, 256), 256, 0, st>>>(image, w.colf, total);
     MRNB_CHECK_LAUNCH("im2col_img_kernel");
     MRNB_TRY(gemm_dw_f32(dact0, 32, w.colf, 36, gp(G, MRNB_P_CONV0_W), (int)r0, 32, 36, st));
+    mrnb_prof_end(MRNB_PROF_CONV, st);
   }
   return MRNB_OK;
 }
 
 }  // namespace
 
-extern "C" size_t mrnb_svtr_train_workspace_bytes(int B, int prec) {
-  (void)prec;
-  return carve_train_ws<float>(nullptr, B).bytes;
+extern "C" size_t mrnb_svtr_train_workspace_bytes(int B, int n_class, int prec) {
+  return prec == MRNB_PREC_BF16 ? carve_train_ws<__nv_bfloat16>(nullptr, B, n_class).bytes
+                                : carve_train_ws<float>(nullptr, B, n_class).bytes;
 }
 
 extern "C" int mrnb_svtr_train_forward(const MrnbSvtrPack* pack, const float* image, int B, int prec, int bn_batch_stats,
@@ -961,10 +1041,13 @@ extern "C" int mrnb_svtr_train_forward(const MrnbSvtrPack* pack, const float* im
   MRNB_CHECK_ARG(!bn_batch_stats || (long)B * 512 > 1, "svtr_train_forward: batch statistics need more than one value");
   for (int k = 0; k < MRNB_P_COUNT; ++k) MRNB_CHECK_ARG(pack->p[k], "svtr_train_forward: parameter slot %d is null", k);
   if (prec == MRNB_PREC_FP32)
-    return train_forward_f32(*pack, image, B, bn_batch_stats, update_running, drop_scales, logits, ld_logits, workspace,
-                             workspace_bytes, stream);
-  mrnb_set_error("svtr_train_forward: precision %d not implemented", prec);
-  return MRNB_ERR_UNSUPPORTED;
+    return train_forward_t<float>(*pack, image, B, bn_batch_stats, update_running, drop_scales, logits, ld_logits, workspace,
+                                  workspace_bytes, stream);
+  if (prec == MRNB_PREC_BF16)
+    return train_forward_t<__nv_bfloat16>(*pack, image, B, bn_batch_stats, update_running, drop_scales, logits, ld_logits,
+                                          workspace, workspace_bytes, stream);
+  mrnb_set_error("svtr_train_forward: unknown precision %d", prec);
+  return MRNB_ERR_ARG;
 }
 
 extern "C" int mrnb_svtr_train_backward(const MrnbSvtrPack* pack, const MrnbSvtrPack* grads, const float* image,
@@ -979,8 +1062,11 @@ extern "C" int mrnb_svtr_train_backward(const MrnbSvtrPack* pack, const MrnbSvtr
   }
   MRNB_CHECK_ARG(grads->fc_w[0] && grads->fc_b[0], "svtr_train_backward: classifier gradient slots are null");
   if (prec == MRNB_PREC_FP32)
-    return train_backward_f32(*pack, *grads, image, dlogits, ld_dlogits, B, bn_batch_stats, drop_scales, grad_arena, n_arena,
-                              workspace, workspace_bytes, stream);
-  mrnb_set_error("svtr_train_backward: precision %d not implemented", prec);
-  return MRNB_ERR_UNSUPPORTED;
+    return train_backward_t<float>(*pack, *grads, image, dlogits, ld_dlogits, B, bn_batch_stats, drop_scales, grad_arena,
+                                   n_arena, workspace, workspace_bytes, stream);
+  if (prec == MRNB_PREC_BF16)
+    return train_backward_t<__nv_bfloat16>(*pack, *grads, image, dlogits, ld_dlogits, B, bn_batch_stats, drop_scales,
+                                           grad_arena, n_arena, workspace, workspace_bytes, stream);
+  mrnb_set_error("svtr_train_backward: unknown precision %d", prec);
+  return MRNB_ERR_ARG;
 }

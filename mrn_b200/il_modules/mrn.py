@@ -40,8 +40,8 @@ def one_cycle_lr(step, total_steps, max_lr, div_factor=20.0, final_div_factor=10
 
 
 def L_PREC_TRAIN(opt):
-    """Arithmetic mode of the stage-0 step: the expert backward currently runs in the fp32 mode only."""
-    return ops.L.PREC_FP32
+    """Arithmetic mode of the stage-0 step: opt.precision ('fp32' parity mode / 'bf16' tensor-core GEMMs)."""
+    return _precision(opt)
 
 
 def edit_distance(a, b):

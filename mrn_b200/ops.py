@@ -352,9 +352,18 @@ class SvtrTrainPack:
                     st_.p[slot] = ptr
         for slot, t in self.bn_stats.items():
             self.struct.p[slot] = t.data_ptr()
+        self.shadow16: Optional[torch.Tensor] = None
+        if prec == L.PREC_BF16:
+            # bf16 copies of the GEMM weights at the same element offsets (refreshed after every optimiser step)
+            self.shadow16 = torch.zeros(off, device=self.device, dtype=torch.bfloat16)
+            for slot, key, perm, o, shp in self.entries:
+                ptr = self.shadow16.data_ptr() + 2 * o
+                if slot == "fc_w":
+                    self.struct.fc_w16[0] = ptr
+                elif slot != "fc_b":
+                    self.struct.h[slot] = ptr
         self.load_state(expert_sd)
         self._ws: Optional[torch.Tensor] = None
-        self._ws_B = 0
 
     def view(self, arena, entry):
         slot, key, perm, o, shp = entry
@@ -385,8 +394,12 @@ class SvtrTrainPack:
             out[e[1]] = t
         return out
 
+    def refresh_shadow(self):
+        if self.shadow16 is not None:
+            L.check(L.load().mrnb_cast_f32_to_bf16(_p(self.params), _p(self.shadow16), self.numel, _stream()), "cast")
+
     def workspace(self, B):
-        need = int(L.load().mrnb_svtr_train_workspace_bytes(B, self.prec))
+        need = int(L.load().mrnb_svtr_train_workspace_bytes(B, self.n_class, self.prec))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
@@ -399,6 +412,7 @@ def svtr_train_forward(tp: SvtrTrainPack, image, bn_batch_stats=True, update_run
     ld = round_up(tp.n_class, 4)
     buf = torch.empty(B, T_FRAMES, ld, device=image.device, dtype=torch.float32)
     ws = tp.workspace(B)
+    tp.refresh_shadow()
     L.check(L.load().mrnb_svtr_train_forward(C.byref(tp.struct), _p(image), B, tp.prec, int(bn_batch_stats),
                                              int(update_running), _p(drop_scales), _p(buf), ld, _p(ws), ws.numel(),
                                              _stream()), "svtr_train_forward")
