@@ -86,12 +86,18 @@ __device__ __forceinline__ void recipe_coords(const MrnbTmaRecipe& r, int mn, in
 struct Epi2 {
   float* out32; __nv_bfloat16* out16;     // either or both
   MrnbAxis cm, cn; long c_gs;
+  int g_inner; long c_gs2;
   const float* bias_n; const float* bias_m;
   const float* mul; const float* res;
   int M, N, KB_total, kb_per_split, splits, gelu;
+  int tiles_n, tiles_m; long total_tiles;
   float alpha;
 };
 
+// Persistent: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n-tile fastest, then m-tile, then
+// group x split).  Barriers, TMEM and the tensor-map prefetch are set up once; the accumulator is double buffered in
+// TMEM (2 x BN columns) so the epilogue of tile i overlaps the loads and MMAs of tile i + 1 -- the router / backward
+// GEMMs have 1..8 k-blocks per tile, where the per-tile fixed cost used to dominate.
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(192)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -102,26 +108,23 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_sh;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-  const int g = blockIdx.z / ep.splits, split = blockIdx.z % ep.splits;
-  const int kb0 = split * ep.kb_per_split;
-  int kb1 = kb0 + ep.kb_per_split;
-  if (kb1 > ep.KB_total) kb1 = ep.KB_total;
-  const int KB = kb1 - kb0;                     // host guarantees KB >= 1
+  const int tiles_n = ep.tiles_n, tiles_m = ep.tiles_m;
+  const long total = ep.total_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"((uint32_t)(2 * BN)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -129,35 +132,53 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_sh;
 
+  auto tile_coords = [&](long t, int& n0, int& m0, int& g, int& kb0, int& KB) {
+    n0 = (int)(t % tiles_n) * BN;
+    long r = t / tiles_n;
+    m0 = (int)(r % tiles_m) * BM;
+    const int z = (int)(r / tiles_m);
+    g = z / ep.splits;
+    const int split = z % ep.splits;
+    kb0 = split * ep.kb_per_split;
+    int kb1 = kb0 + ep.kb_per_split;
+    if (kb1 > ep.KB_total) kb1 = ep.KB_total;
+    KB = kb1 - kb0;                               // host guarantees KB >= 1
+  };
+
   if (warp == 0) {
     if (lane == 0) {
-      for (int i = 0; i < KB; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
-        const int k0 = (kb0 + i) * BK;
-        int c[4];
-        if (A_MN) {
+      uint32_t it = 0;
+      for (long t = blockIdx.x; t < total; t += gridDim.x) {
+        int n0, m0, g, kb0, KB;
+        tile_coords(t, n0, m0, g, kb0, KB);
+        for (int i = 0; i < KB; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
+          const int k0 = (kb0 + i) * BK;
+          int c[4];
+          if (A_MN) {
 #pragma unroll
-          for (int ch = 0; ch < BM / 64; ++ch) {
-            recipe_coords(ra, m0 + ch * 64, k0, g, c);
-            tma_load_4d(sa + ch * (BK * 128), &tmA, &full_bar[s], c[0], c[1], c[2], c[3]);
+            for (int ch = 0; ch < BM / 64; ++ch) {
+              recipe_coords(ra, m0 + ch * 64, k0, g, c);
+              tma_load_4d(sa + ch * (BK * 128), &tmA, &full_bar[s], c[0], c[1], c[2], c[3]);
+            }
+          } else {
+            recipe_coords(ra, m0, k0, g, c);
+            tma_load_4d(sa, &tmA, &full_bar[s], c[0], c[1], c[2], c[3]);
           }
-        } else {
-          recipe_coords(ra, m0, k0, g, c);
-          tma_load_4d(sa, &tmA, &full_bar[s], c[0], c[1], c[2], c[3]);
-        }
-        if (B_MN) {
+          if (B_MN) {
 #pragma unroll
-          for (int ch = 0; ch < BN / 64; ++ch) {
-            recipe_coords(rb, n0 + ch * 64, k0, g, c);
-            tma_load_4d(sa + A_BYTES + ch * (BK * 128), &tmB, &full_bar[s], c[0], c[1], c[2], c[3]);
+            for (int ch = 0; ch < BN / 64; ++ch) {
+              recipe_coords(rb, n0 + ch * 64, k0, g, c);
+              tma_load_4d(sa + A_BYTES + ch * (BK * 128), &tmB, &full_bar[s], c[0], c[1], c[2], c[3]);
+            }
+          } else {
+            recipe_coords(rb, n0, k0, g, c);
+            tma_load_4d(sa + A_BYTES, &tmB, &full_bar[s], c[0], c[1], c[2], c[3]);
           }
-        } else {
-          recipe_coords(rb, n0, k0, g, c);
-          tma_load_4d(sa + A_BYTES, &tmB, &full_bar[s], c[0], c[1], c[2], c[3]);
         }
       }
     }
@@ -165,95 +186,117 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0) {
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                  ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      for (int i = 0; i < KB; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, ti = 0;
+      for (long t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
+        int n0, m0, g, kb0, KB;
+        tile_coords(t, n0, m0, g, kb0, KB);
+        const uint32_t acc = ti & 1u;
+        mbar_wait(&tmem_empty_bar[acc], ((ti >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-        const uint64_t adesc = make_desc(sa, A_MN ? BK * 128 : 16);
-        const uint64_t bdesc = make_desc(sa + A_BYTES, B_MN ? BK * 128 : 16);
+        const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN;
+        for (int i = 0; i < KB; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint64_t adesc = make_desc(sa, A_MN ? BK * 128 : 16);
+          const uint64_t bdesc = make_desc(sa + A_BYTES, B_MN ? BK * 128 : 16);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // K-major: +32 B inside the swizzled row; MN-major: +16 k-rows of 128 B
-          const uint64_t aoff = A_MN ? (uint64_t)(k * UMMA_K * 128 >> 4) : (uint64_t)(k * 2);
-          const uint64_t boff = B_MN ? (uint64_t)(k * UMMA_K * 128 >> 4) : (uint64_t)(k * 2);
-          umma_bf16(tmem_base, adesc + aoff, bdesc + boff, idesc, (i | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: +32 B inside the swizzled row; MN-major: +16 k-rows of 128 B
+            const uint64_t aoff = A_MN ? (uint64_t)(k * UMMA_K * 128 >> 4) : (uint64_t)(k * 2);
+            const uint64_t boff = B_MN ? (uint64_t)(k * UMMA_K * 128 >> 4) : (uint64_t)(k * 2);
+            umma_bf16(tmem_d, adesc + aoff, bdesc + boff, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit(&tmem_full_bar[acc]);
       }
-      umma_commit(&tmem_full_bar);
     }
   } else {
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
-    mbar_wait(&tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const bool rok = row < ep.M;
-    const long om = rok ? (long)g * ep.c_gs + (long)(row / ep.cm.inner) * ep.cm.so + (long)(row % ep.cm.inner) * ep.cm.si : 0;
-    const float bm = (ep.bias_m && rok) ? ep.bias_m[row] : 0.f;
     const bool plain = ep.splits == 1;
+    uint32_t ti = 0;
+    for (long t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
+      int n0, m0, g, kb0, KB;
+      tile_coords(t, n0, m0, g, kb0, KB);
+      const uint32_t acc = ti & 1u;
+      const int row = m0 + q * 32 + lane;
+      mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const bool rok = row < ep.M;
+      const long og = ep.g_inner > 0 ? (long)(g / ep.g_inner) * ep.c_gs + (long)(g % ep.g_inner) * ep.c_gs2 : (long)g * ep.c_gs;
+      const long om = rok ? og + (long)(row / ep.cm.inner) * ep.cm.so + (long)(row % ep.cm.inner) * ep.cm.si : 0;
+      const float bm = (ep.bias_m && rok) ? ep.bias_m[row] : 0.f;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      const int col0 = n0 + c0;
-      if (!rok || col0 >= ep.N) continue;
-      // contiguous run of 16 columns?
-      const bool contig = ep.cn.si == 1 && (col0 % ep.cn.inner) + 16 <= ep.cn.inner && col0 + 16 <= ep.N;
-      const long on0 = (long)(col0 / ep.cn.inner) * ep.cn.so + (long)(col0 % ep.cn.inner) * ep.cn.si;
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float x = __uint_as_float(r[j]) * ep.alpha;
-        if (plain) {
-          x += bm;
-          if (ep.bias_n && col0 + j < ep.N) x += __ldg(ep.bias_n + col0 + j);
-          if (ep.gelu) x = gelu_erf(x);
-        }
-        v[j] = x;
-      }
-      if (!plain) {
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)BN + (uint32_t)c0, r);
+        const int col0 = n0 + c0;
+        if (!rok || col0 >= ep.N) continue;
+        // contiguous run of 16 columns?
+        const bool contig = ep.cn.si == 1 && (col0 % ep.cn.inner) + 16 <= ep.cn.inner && col0 + 16 <= ep.N;
+        const long on0 = (long)(col0 / ep.cn.inner) * ep.cn.so + (long)(col0 % ep.cn.inner) * ep.cn.si;
+        float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int col = col0 + j;
-          if (col >= ep.N) break;
-          const long o = om + (contig ? on0 + j : (long)(col / ep.cn.inner) * ep.cn.so + (long)(col % ep.cn.inner) * ep.cn.si);
-          atomicAdd(ep.out32 + o, v[j]);
+          float x = __uint_as_float(r[j]) * ep.alpha;
+          if (plain) {
+            x += bm;
+            if (ep.bias_n && col0 + j < ep.N) x += __ldg(ep.bias_n + col0 + j);
+            if (ep.gelu) x = gelu_erf(x);
+          }
+          v[j] = x;
         }
-        continue;
-      }
-      if (contig && ((om + on0) & 3) == 0) {
-        const long o = om + on0;
+        if (!plain) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float4 t = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          if (ep.mul) { const float4 mm = *reinterpret_cast<const float4*>(ep.mul + o + j); t.x *= mm.x; t.y *= mm.y; t.z *= mm.z; t.w *= mm.w; }
-          if (ep.res) { const float4 rr = *reinterpret_cast<const float4*>(ep.res + o + j); t.x += rr.x; t.y += rr.y; t.z += rr.z; t.w += rr.w; }
-          if (ep.out32) *reinterpret_cast<float4*>(ep.out32 + o + j) = t;
-          if (ep.out16) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(t.x, t.y), h1 = __floats2bfloat162_rn(t.z, t.w);
-            *reinterpret_cast<uint2*>(ep.out16 + o + j) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+          for (int j = 0; j < 16; ++j) {
+            const int col = col0 + j;
+            if (col >= ep.N) break;
+            const long o = om + (contig ? on0 + j : (long)(col / ep.cn.inner) * ep.cn.so + (long)(col % ep.cn.inner) * ep.cn.si);
+            atomicAdd(ep.out32 + o, v[j]);
+          }
+          continue;
+        }
+        if (contig && ((om + on0) & 3) == 0) {
+          const long o = om + on0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 tt = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (ep.mul) { const float4 mm = *reinterpret_cast<const float4*>(ep.mul + o + j); tt.x *= mm.x; tt.y *= mm.y; tt.z *= mm.z; tt.w *= mm.w; }
+            if (ep.res) { const float4 rr = *reinterpret_cast<const float4*>(ep.res + o + j); tt.x += rr.x; tt.y += rr.y; tt.z += rr.z; tt.w += rr.w; }
+            if (ep.out32) *reinterpret_cast<float4*>(ep.out32 + o + j) = tt;
+            if (ep.out16) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(tt.x, tt.y), h1 = __floats2bfloat162_rn(tt.z, tt.w);
+              *reinterpret_cast<uint2*>(ep.out16 + o + j) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+            }
+          }
+        } else {
+          for (int j = 0; j < 16; ++j) {
+            const int col = col0 + j;
+            if (col >= ep.N) break;
+            const long o = om + (long)(col / ep.cn.inner) * ep.cn.so + (long)(col % ep.cn.inner) * ep.cn.si;
+            float x = v[j];
+            if (ep.mul) x *= ep.mul[o];
+            if (ep.res) x += ep.res[o];
+            if (ep.out32) ep.out32[o] = x;
+            if (ep.out16) ep.out16[o] = __float2bfloat16_rn(x);
           }
         }
-      } else {
-        for (int j = 0; j < 16; ++j) {
-          const int col = col0 + j;
-          if (col >= ep.N) break;
-          const long o = om + (long)(col / ep.cn.inner) * ep.cn.so + (long)(col % ep.cn.inner) * ep.cn.si;
-          float x = v[j];
-          if (ep.mul) x *= ep.mul[o];
-          if (ep.res) x += ep.res[o];
-          if (ep.out32) ep.out32[o] = x;
-          if (ep.out16) ep.out16[o] = __float2bfloat16_rn(x);
-        }
+      }
+      // this warp has read its 32 lanes of the accumulator: hand the buffer back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
       }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
   }
 }
 
@@ -298,6 +341,7 @@ int launch2(const MrnbTcGemm2& p, cudaStream_t st) {
   MRNB_TRY(encode(&tmB, p.b));
   Epi2 ep{};
   ep.out32 = p.out32; ep.out16 = (__nv_bfloat16*)p.out16; ep.cm = p.cm; ep.cn = p.cn; ep.c_gs = p.c_gstride;
+  ep.g_inner = p.g_inner; ep.c_gs2 = p.c_gstride2;
   ep.bias_n = p.bias_n; ep.bias_m = p.bias_m; ep.mul = p.mul; ep.res = p.res;
   ep.M = p.M; ep.N = p.N; ep.gelu = p.gelu; ep.alpha = p.alpha == 0.f ? 1.f : p.alpha;
   ep.KB_total = p.K / BK;
@@ -309,7 +353,12 @@ int launch2(const MrnbTcGemm2& p, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)STAGES * (A_BYTES + BN * BK * 2);
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(tc_gemm2_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-  dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM), p.groups * splits);
+  ep.tiles_n = cdiv(p.N, BN); ep.tiles_m = cdiv(p.M, BM);
+  ep.total_tiles = (long)ep.tiles_n * ep.tiles_m * p.groups * splits;
+  static int n_sm = 0;
+  if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+  const long cap = 2L * n_sm;                    // two CTAs per SM: 2 x (2 x BN <= 256) TMEM columns, 2 x <= 97 KiB smem
+  const int grid = (int)(ep.total_tiles < cap ? ep.total_tiles : cap);
   tc_gemm2_kernel<BN, A_MN, B_MN><<<grid, 192, smem, st>>>(tmA, tmB, p.a.recipe, p.b.recipe, ep);
   MRNB_CHECK_LAUNCH("tc_gemm2_kernel");
   return MRNB_OK;

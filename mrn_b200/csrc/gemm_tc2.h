@@ -22,6 +22,7 @@ struct MrnbTcGemm2 {
   MrnbTcOperand a, b;
   float* out32; void* out16;            // fp32 and / or bf16 output at the same element offsets
   MrnbAxis cm, cn; long c_gstride;      // two-level output addressing (elements)
+  int g_inner; long c_gstride2;         // g_inner > 0: group offset = (g / g_inner) * c_gstride + (g % g_inner) * c_gstride2
   const float* bias_n; const float* bias_m; const float* mul; const float* res;
   int M, N, K, groups, splitk, gelu;
   float alpha;
@@ -47,6 +48,20 @@ static inline MrnbTcOperand mrnb_operand_mn2d(const void* p, long MN, long K, lo
   o.strides[0] = ld; o.strides[1] = gstride; o.strides[2] = gstride * groups;
   o.box[0] = 64; o.box[1] = 64; o.box[2] = 1; o.box[3] = 1;
   o.recipe = MrnbTmaRecipe{{MRNB_SRC_MN, MRNB_SRC_K, MRNB_SRC_G, MRNB_SRC_ZERO}, {1, 1, 1, 1}, {0, 0, 0, 0}};
+  return o;
+}
+
+// One attention head of a [groups][rows][ld] tensor whose heads are 32-wide column slices: (row, k) of group g = b * heads + h
+// is ptr[(b * rows + row) * ld + h * 32 + k].  K-major: k walks the head dimension; MN-major: the head dimension is m / n.
+// The 64-wide TMA box is half outside the 32-wide slice: the hardware zero-fills it (the GEMM runs with K or N padded).
+static inline MrnbTcOperand mrnb_operand_head(const void* p, long rows, long ld, int heads, long batch, int mn_major, int box_rows) {
+  MrnbTcOperand o{};
+  o.ptr = p; o.mn_major = mn_major;
+  o.dims[0] = 32; o.dims[1] = rows; o.dims[2] = heads; o.dims[3] = batch;
+  o.strides[0] = ld; o.strides[1] = 32; o.strides[2] = rows * ld;
+  o.box[0] = 64; o.box[1] = mn_major ? 64 : box_rows; o.box[2] = 1; o.box[3] = 1;
+  if (mn_major) o.recipe = MrnbTmaRecipe{{MRNB_SRC_MN, MRNB_SRC_K, MRNB_SRC_G, MRNB_SRC_G}, {1, 1, 1, heads}, {0, 0, heads, 0}};
+  else o.recipe = MrnbTmaRecipe{{MRNB_SRC_K, MRNB_SRC_MN, MRNB_SRC_G, MRNB_SRC_G}, {1, 1, 1, heads}, {0, 0, heads, 0}};
   return o;
 }
 
