@@ -73,6 +73,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+      "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ void recipe_coords(const MrnbTmaRecipe& r, int mn, int k, int g, int (&c)[4]) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -91,6 +106,7 @@ struct Epi2 {
   const float* mul; const float* res;
   int M, N, KB_total, kb_per_split, splits, gelu;
   int tiles_n, tiles_m; long total_tiles;
+  int simple;      // plain row-major output, no bias / mul / res / gelu: the lean epilogue (straight stores or vector reductions)
   float alpha;
 };
 
@@ -229,6 +245,58 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const long og = ep.g_inner > 0 ? (long)(g / ep.g_inner) * ep.c_gs + (long)(g % ep.g_inner) * ep.c_gs2 : (long)g * ep.c_gs;
       const long om = rok ? og + (long)(row / ep.cm.inner) * ep.cm.so + (long)(row % ep.cm.inner) * ep.cm.si : 0;
       const float bm = (ep.bias_m && rok) ? ep.bias_m[row] : 0.f;
+      if (ep.simple) {
+        // lean epilogue: 32 columns per TMEM load, a whole 128-byte line of the row per thread, no index arithmetic
+        const long orow = og + (long)row * ep.cm.si;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          const int col0 = n0 + c0;
+          if (col0 >= ep.N) break;                                    // warp-uniform
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)BN + (uint32_t)c0, r);
+          if (!rok) continue;
+          const long o = orow + col0;
+          if (col0 + 32 <= ep.N && (o & 3) == 0) {
+            if (!plain) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                red_add_v4(ep.out32 + o + j, __uint_as_float(r[j]) * ep.alpha, __uint_as_float(r[j + 1]) * ep.alpha,
+                           __uint_as_float(r[j + 2]) * ep.alpha, __uint_as_float(r[j + 3]) * ep.alpha);
+            } else {
+              if (ep.out32) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(ep.out32 + o + j) =
+                      make_float4(__uint_as_float(r[j]) * ep.alpha, __uint_as_float(r[j + 1]) * ep.alpha,
+                                  __uint_as_float(r[j + 2]) * ep.alpha, __uint_as_float(r[j + 3]) * ep.alpha);
+              }
+              if (ep.out16) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  uint32_t pk[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[j + 2 * u]) * ep.alpha,
+                                                             __uint_as_float(r[j + 2 * u + 1]) * ep.alpha);
+                    pk[u] = *reinterpret_cast<uint32_t*>(&h);
+                  }
+                  *reinterpret_cast<uint4*>(ep.out16 + o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+              }
+            }
+          } else {
+            for (int j = 0; j < 32; ++j) {
+              if (col0 + j >= ep.N) break;
+              const float x = __uint_as_float(r[j]) * ep.alpha;
+              if (!plain) atomicAdd(ep.out32 + o + j, x);
+              else {
+                if (ep.out32) ep.out32[o + j] = x;
+                if (ep.out16) ep.out16[o + j] = __float2bfloat16_rn(x);
+              }
+            }
+          }
+        }
+      } else
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 16) {
         uint32_t r[16];
@@ -353,6 +421,7 @@ int launch2(const MrnbTcGemm2& p, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)STAGES * (A_BYTES + BN * BK * 2);
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(tc_gemm2_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  ep.simple = (!p.bias_n && !p.bias_m && !p.mul && !p.res && !p.gelu && p.cn.si == 1 && p.cn.inner >= p.N && p.cm.inner >= p.M) ? 1 : 0;
   ep.tiles_n = cdiv(p.N, BN); ep.tiles_m = cdiv(p.M, BM);
   ep.total_tiles = (long)ep.tiles_n * ep.tiles_m * p.groups * splits;
   static int n_sm = 0;
