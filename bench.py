@@ -13,7 +13,8 @@ router backward -> [NCCL all-reduce] -> clip + Adam.
 
 value  = samples/s with the batch resident in HBM (CUDA events, max over ranks).
 e2e    = same metric through MRN.train_step_stage1 with pinned-host inputs copied H2D and both losses read back D2H
-         every step (what il_modules/mrn.py's loop does).
+         every step (what il_modules/mrn.py's loop does); the copy of batch k+1 is issued on the learner's staging
+         stream (mrn_b200.utils.DevicePrefetcher) while batch k computes -- every copy is inside the timed region.
 roofline / kernel_families = CUDA-event time per kernel family recorded on the launching stream inside the timed region.
 """
 import argparse
@@ -286,8 +287,14 @@ def run_ours(args):
             return l0, l0
         return (learner.train_step_stage1 if eager else train_step)(img, tgt, lens, dom)
 
+    from mrn_b200.utils import DevicePrefetcher
+    pf = DevicePrefetcher(dev)              # the learner's own staging: batch k+1 is copied while batch k computes
+
     def step_e2e(k):
-        img, tgt, lens, dom = (t.to(dev, non_blocking=True) for t in host[k % n_batches])
+        if pf.pending is None:
+            pf.submit(host[k % n_batches])
+        img, tgt, lens, dom = pf.take()
+        pf.submit(host[(k + 1) % n_batches])
         if infer:
             r = infer_step(img, "TF")
             ids = r["ids"].cpu()                        # the single D2H copy of the decoded ids (+ lengths, confidences)

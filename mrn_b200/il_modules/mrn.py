@@ -21,7 +21,7 @@ import torch
 from .. import dist as mdist
 from .. import ops
 from ..modules.model import MRNNet, _arch, _precision, sample_drop_scales
-from ..utils import Averager, CTCLabelConverter
+from ..utils import Averager, CTCLabelConverter, DevicePrefetcher
 
 
 def one_cycle_lr(step, total_steps, max_lr, div_factor=20.0, final_div_factor=1000.0, pct_start=0.3):
@@ -42,6 +42,14 @@ def one_cycle_lr(step, total_steps, max_lr, div_factor=20.0, final_div_factor=10
 def L_PREC_TRAIN(opt):
     """Arithmetic mode of the stage-0 step: opt.precision ('fp32' parity mode / 'bf16' tensor-core GEMMs)."""
     return _precision(opt)
+
+
+def _domain_ids(indexs):
+    """get_batch2() returns one index tensor per underlying loader (data/data_manage.py:174-196); the reference
+    flattens them with torch.LongTensor(indexs).squeeze() (il_modules/mrn.py:333)."""
+    if isinstance(indexs, (list, tuple)) and indexs and isinstance(indexs[0], torch.Tensor):
+        return torch.cat([t.reshape(-1) for t in indexs]).to(torch.long).cpu()
+    return torch.as_tensor(indexs, dtype=torch.long).reshape(-1).cpu()
 
 
 def edit_distance(a, b):
@@ -214,17 +222,43 @@ class MRN(object):
             self._train(0, taski, train_loader, valid_loader, step=1)
 
     def _train(self, start_iter, taski, train_loader, valid_loader, step=0):
+        """il_modules/mrn.py:180-223.  The loader objects follow the reference's protocol when they implement it
+        (Dataset_Manager.get_dataset, Val_Dataset.create_dataset / create_list_dataset); plain loaders are used as is."""
+        def dataset(memory):
+            if hasattr(train_loader, "get_dataset"):
+                train_loader.get_dataset(taski, memory=memory)
+
+        def rehearsal():
+            if getattr(self.opt, "memory", None) is not None and hasattr(train_loader, "get_dataset"):
+                self.build_rehearsal_memory(train_loader, taski)
+            else:
+                dataset(getattr(self.opt, "memory", None))
+
         if self.opt.start_task > taski + step * 0.5:
             name = self.opt.lan_list[taski]
             path = f"./saved_models/{self.opt.exp_name}/{name}_{taski}_{step}_best_score.pth"
             self.model.load_state_dict(torch.load(path, map_location=self.device), strict=True)
+            self.net._cache.key = None
+            if taski > 0 and step == 0:
+                dataset(None)
+            elif taski > 0 and step == 1:
+                rehearsal()
             return
+        single = valid_loader.create_dataset() if hasattr(valid_loader, "create_dataset") else valid_loader
         if taski == 0:
-            self._init_train(start_iter, taski, train_loader, valid_loader, cross=False)
+            self._init_train(start_iter, taski, train_loader, single, cross=False)
         elif step == 0:
-            self.update_step1(start_iter, taski, train_loader, valid_loader)
+            dataset(None)
+            self.update_step1(start_iter, taski, train_loader, single)
         else:
-            self._update_representation(start_iter, taski, train_loader, valid_loader)
+            rehearsal()
+            multi = valid_loader.create_list_dataset() if hasattr(valid_loader, "create_list_dataset") else valid_loader
+            self._update_representation(start_iter, taski, train_loader, multi)
+
+    def build_rehearsal_memory(self, train_loader, taski):
+        """il_modules/mrn.py:169-178 (random rehearsal memory: memory_num / taski samples per earlier task; the index
+        bookkeeping lives in the dataset layer)."""
+        train_loader.get_dataset(taski, memory=self.opt.memory, index_list=getattr(self, "memory_index", None))
 
     # ---- stage 0: the newest expert trained end to end ---------------------------------------------
     def begin_expert_training(self, total_steps=None):
@@ -381,11 +415,20 @@ class MRN(object):
         start_time = time.time()
         best_score = -1
         n_iter = int(self.opt.num_iter // 2)
+        pf = DevicePrefetcher(self.device)
+
+        def stage(batch):
+            image_tensors, labels, indexs = batch
+            li, ll = self.converter.encode(labels, batch_max_length=self.opt.batch_max_length, device="cpu")
+            pf.submit((image_tensors.pin_memory() if not image_tensors.is_pinned() else image_tensors,
+                       li.pin_memory(), ll.pin_memory(),
+                       _domain_ids(indexs).pin_memory()))
+        if start_iter + 1 <= n_iter:
+            stage(train_loader.get_batch2())
         for iteration in range(start_iter + 1, n_iter + 1):
-            image_tensors, labels, indexs = train_loader.get_batch2()
-            indexs = torch.as_tensor(indexs, dtype=torch.long).reshape(-1).to(self.device, non_blocking=True)
-            image = image_tensors.to(self.device, non_blocking=True)
-            labels_index, labels_length = self.converter.encode(labels, batch_max_length=self.opt.batch_max_length)
+            image, labels_index, labels_length, indexs = pf.take()
+            if iteration < n_iter:
+                stage(train_loader.get_batch2())            # H2D of the next batch overlaps this step's kernels
             loss_clf, taski_loss = self.train_step_stage1(image, labels_index, labels_length, indexs)
             train_loss_avg.add(loss_clf)
             train_taski_loss_avg.add(taski_loss)
@@ -497,5 +540,38 @@ class MRN(object):
         return current_score
 
     def test(self, AlignCollate_valid, valid_datas, best_scores, ned_scores, taski, val_choose="test"):
-        raise NotImplementedError("benchmark evaluation needs the LMDB datasets (data/dataset.py), out of scope of the "
-                                  "hot path (SURVEY.md §8f.2); use MRN.validation(loader) with any (images, labels) iterable")
+        """il_modules/mrn.py:448-515: reload the best checkpoint of the task (strict=True), evaluate every benchmark set
+        with the last expert (task 0, "FF") or the hard route (later tasks, "TF"), append the averages.
+
+        valid_datas: list of loaders -- iterables of (images [B,4,32,256], label strings).  (The reference builds them
+        from LMDB paths with hierarchical_dataset + AlignCollate_valid; that dataset layer is outside the hot path,
+        SURVEY.md §8f.2, so the caller passes the loaders; AlignCollate_valid is accepted and unused.)"""
+        val_choose, step = ("FF", 0) if taski == 0 else ("TF", 1)
+        os.makedirs(f"./result/{self.opt.exp_name}", exist_ok=True)
+        name = self.opt.lan_list[taski]
+        path = f"./saved_models/{self.opt.exp_name}/{name}_{taski}_{step}_best_score.pth"
+        if not isinstance(self.model, RankLocal):
+            self.model = RankLocal(self.net).to(self.device)
+        self.model.load_state_dict(torch.load(path, map_location=self.device), strict=True)
+        self.net._cache.key = None
+        self.reset_graphs()
+        task_accs, ned_accs = [], []
+        self.model.eval()
+        for loader in valid_datas:
+            _, current_score, ned_score, *_ = self.validation(loader, val_choose=val_choose)
+            task_accs.append(round(current_score, 2))
+            ned_accs.append(round(ned_score, 2))
+        if (taski + 1) * 2 == len(task_accs):            # MLT17 / MLT19 pairs (double_write, il_modules/base.py)
+            score17 = round(sum(task_accs[0::2]) / len(task_accs[0::2]), 2)
+            score19 = round(sum(task_accs[1::2]) / len(task_accs[1::2]), 2)
+            best_scores.append(score17)
+            ned_scores.append(score19)
+            acc_log = f"Task {taski} Avg Incremental Acc:  17: {score17}    19: {score19}\n"
+        else:
+            best_scores.append(round(sum(task_accs) / max(len(task_accs), 1), 2))
+            ned_scores.append(round(sum(ned_accs) / max(len(ned_accs), 1), 2))
+            acc_log = (f"Task {taski} Test Average Incremental Accuracy: {best_scores[taski]} \n Task {taski} Incremental "
+                       f"Accuracy: {task_accs}\n ned_acc: {ned_accs}\n")
+        self.write_log(acc_log)
+        print(acc_log)
+        return best_scores, ned_scores

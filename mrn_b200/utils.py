@@ -15,15 +15,17 @@ class CTCLabelConverter(object):
         self.character = ["[CTCblank]"] + dict_character
         self.device = device
 
-    def encode(self, word_string, batch_max_length=25):
+    def encode(self, word_string, batch_max_length=25, device=None):
+        """tools/utils.py:35-60.  device="cpu" keeps the tensors on the host (for the prefetcher)."""
         word_length = [len(word) for word in word_string]
         word_index = torch.full((len(word_string), batch_max_length), self.dict["[PAD]"], dtype=torch.long)
         for i, word in enumerate(word_string):
             idx = [self.dict.get(ch, self.dict["[UNK]"]) for ch in word]
             word_index[i, :len(idx)] = torch.tensor(idx, dtype=torch.long)
         lens = torch.tensor(word_length, dtype=torch.int32)
-        if self.device is not None:
-            word_index, lens = word_index.to(self.device, non_blocking=True), lens.to(self.device, non_blocking=True)
+        target = self.device if device is None else (None if str(device) == "cpu" else device)
+        if target is not None:
+            word_index, lens = word_index.to(target, non_blocking=True), lens.to(target, non_blocking=True)
         return word_index, lens
 
     def decode(self, word_index, word_length):
@@ -61,3 +63,32 @@ class Averager(object):
         if self.n_count == 0:
             return 0.0
         return float(self.sum) / float(self.n_count)
+
+
+class DevicePrefetcher:
+    """Double-buffered host -> device staging on a side stream: batch k+1 is copied (from pinned memory, non-blocking)
+    while the kernels of batch k run, and the compute stream only waits on the copy's event.  Replaces the blocking
+    `image_tensors.to(device)` at the top of the reference loops (il_modules/mrn.py:236-238,331-335)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self.pending = None
+
+    def submit(self, tensors):
+        """Start copying a tuple of host tensors; returns nothing.  Call take() to obtain the device tensors."""
+        with torch.cuda.stream(self.stream):
+            dev = tuple(t.to(self.device, non_blocking=True) if isinstance(t, torch.Tensor) else t for t in tensors)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.pending = (dev, ev)
+
+    def take(self):
+        dev, ev = self.pending
+        self.pending = None
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for t in dev:
+            if isinstance(t, torch.Tensor):
+                t.record_stream(cur)
+        return dev
