@@ -258,6 +258,18 @@ int mrnb_greedy_decode(const int* amax, const float* maxprob, int B, int T, int*
                        cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Image preparation on the device.  Replaces data/dataset.py:235-246 (ResizeNormalize: PIL Image.resize((imgW, imgH),
+ * BICUBIC) on the RGBA crop -> torchvision ToTensor -> sub_(0.5).div_(0.5)) as applied per image by AlignCollate
+ * (data/dataset.py:169-197); output bytes are identical to Pillow's (premultiplied-alpha two-pass fixed-point resampling).
+ * pixels: packed RGBA rows of all images (device); offsets [B] (bytes, multiples of 4), widths / heights [B]: DEVICE
+ * arrays.  max_w / max_h: the largest width / height in the batch (host values; bound the tap count and the
+ * intermediate).  out: [B,4,out_h,out_w] fp32.  workspace: >= mrnb_resize_workspace_bytes(B, max_h, out_w). */
+size_t mrnb_resize_workspace_bytes(int B, int max_h, int out_w);
+int mrnb_resize_normalize_rgba(const unsigned char* pixels, const long long* offsets, const int* widths, const int* heights,
+                               int B, int max_w, int max_h, int out_h, int out_w, float* out, void* workspace,
+                               size_t workspace_bytes, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * clip_grad_norm_(5) + Adam on a flat arena.  Replaces il_modules/mrn.py:364-367 (torch foreach kernels).
  * state: exp_avg, exp_avg_sq [n]; norm_out: device scalar receiving the pre-clip L2 norm.  step is 1-based. */
 int mrnb_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n, float lr, float beta1,
