@@ -137,16 +137,16 @@ def cpu_stage1(sample, steps, warmup, arch="svtr"):
     return sample * steps / dt, dt / steps * 1000.0, torch.get_num_threads()
 
 
-def cpu_stage0(sample, steps, warmup):
+def cpu_stage0(sample, steps, warmup, arch="svtr"):
     """Stage-0 expert-training step of the oracle port (torch CPU autograd) on a bounded sample."""
     from oracle import mrn_oracle as O
     from mrn_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     cc = CLASS_COUNTS[-1:]
-    sd = synth.synth_state_dict(cc, 111)
+    sd = synth.synth_state_dict(cc, 111, arch=arch)
     img, tgt, lens, dom = synth.synth_batch(sample, cc, 111)
-    drop = synth.synth_drop_scales(1, sample, O.svtr_drop_path_rates(), 111)[0]
+    drop = synth.synth_drop_scales(1, sample, O.svtr_drop_path_rates(), 111)[0] if arch == "svtr" else None
     state = dict(step=0, m={}, v={})
     for _ in range(warmup):
         O.stage0_step_cpu(sd, 0, state, img, tgt, lens, drop_scales=drop)
@@ -264,8 +264,6 @@ def run_ours(args):
     infer = args.mode == "infer"
     stage0 = args.mode == "stage0"
     if stage0:
-        if args.arch != "svtr":
-            raise RuntimeError("--mode stage0 is implemented for SVTR experts")
         opt.num_iter = 1000000
         learner.begin_expert_training()                 # newest expert (C = 5153) -> flat training arena + fused Adam
         mdist.broadcast_(learner._tp.params)
@@ -428,10 +426,10 @@ def run_ours(args):
         "loss_clf": float(last[0]), "taski_loss": float(last[1]),
     }
     if stage0:
-        out["metric"] = "MRN-SVTR stage-0 expert-training samples/s"
+        out["metric"] = "MRN-%s stage-0 expert-training samples/s" % args.arch.upper()
         out["dtype"] = "f32" if learner._tp.prec == 0 else "bf16"
-        out["config"]["workload"] = ("SVTR-MRN stage-0 step: newest expert (C=5153) forward + CTC + full backward + clip/Adam, "
-                                     "B=%d/GPU, train mode (BN batch stats + DropPath)" % B)
+        out["config"]["workload"] = ("%s-MRN stage-0 step: newest expert (C=5153) forward + CTC + full backward + clip/Adam, "
+                                     "B=%d/GPU, train mode (BN batch stats%s)" % (args.arch.upper(), B, " + DropPath" if args.arch == "svtr" else ""))
         out["config"]["expert_precision"] = out["dtype"]
         out.pop("taski_loss", None)
     if infer:
@@ -440,7 +438,7 @@ def run_ours(args):
         if args.sweep:
             out["sweep"] = infer_sweep(learner, [int(x) for x in args.sweep.split(",") if x], dev)
     if world == 1 and not args.no_cpu_baseline and stage0:
-        v, ms, cores = cpu_stage0(args.cpu_sample, 2, 1)
+        v, ms, cores = cpu_stage0(args.cpu_sample, 2, 1, args.arch)
         out["cpu_baseline"] = {"value": round(v, 3), "unit": "samples/s", "cores": cores, "kind": "port",
                                "sample": "2 timed expert-training steps of %d samples, oracle port (torch CPU autograd), fp32, "
                                          "%d threads" % (args.cpu_sample, cores)}

@@ -192,6 +192,53 @@ int mrnb_crnn_experts_forward(const MrnbCrnnPack* pack, const float* image, int 
                               void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Stage-0 expert training: one CRNN expert (VGG + 2 x BidirectionalLSTM + CTC head), forward keeping activations +
+ * full backward (convolution / pooling / BatchNorm gradients, BPTT through both LSTM layers).
+ * Replaces il_modules/mrn.py:225-279 for FeatureExtraction="VGG", SequenceModeling="BiLSTM": the autograd graph of
+ * modules/feature_extraction.py:19-47, modules/sequence_modeling.py:12-22, modules/model.py:82-101,133-148.
+ *
+ * Slots point into one flat fp32 arena (gradients: same slots in a second arena).  Convolution weights are
+ * [Cout,kh,kw,Cin] (conv0 included); LSTM tensors keep nn.LSTM's gate order (i,f,g,o) with the forward direction
+ * followed by the reverse direction IN THE SAME SLOT (adjacent in the arena). */
+enum {
+  MRNB_T_CONV0_W = 0, MRNB_T_CONV0_B, /* [64,3,3,4], [64]        ConvNet.0 */
+  MRNB_T_CONV1_W, MRNB_T_CONV1_B,     /* [128,3,3,64]            ConvNet.3 */
+  MRNB_T_CONV2_W, MRNB_T_CONV2_B,     /* [256,3,3,128]           ConvNet.6 */
+  MRNB_T_CONV3_W, MRNB_T_CONV3_B,     /* [256,3,3,256]           ConvNet.8 */
+  MRNB_T_CONV4_W, MRNB_T_BN4_W, MRNB_T_BN4_B, /* [512,3,3,256] (no bias), ConvNet.12 weight / bias */
+  MRNB_T_CONV5_W, MRNB_T_BN5_W, MRNB_T_BN5_B, /* [512,3,3,512] (no bias), ConvNet.15 weight / bias */
+  MRNB_T_CONV6_W, MRNB_T_CONV6_B,     /* [512,2,2,512]           ConvNet.18 */
+  MRNB_T_LSTM0 = 16,                  /* 2 layers x MRNB_TL_COUNT slots: SequenceModeling.0, SequenceModeling.1 */
+  MRNB_T_FC_W = 16 + 2 * 6, MRNB_T_FC_B, /* [C,256], [C]         fc */
+  MRNB_T_COUNT
+};
+enum { /* per BidirectionalLSTM, Kin = 512 / 256 */
+  MRNB_TL_WIH = 0, /* [2,1024,Kin]  rnn.weight_ih_l0, rnn.weight_ih_l0_reverse */
+  MRNB_TL_WHH,     /* [2,1024,256]  rnn.weight_hh_l0, rnn.weight_hh_l0_reverse */
+  MRNB_TL_BIH,     /* [2,1024]      rnn.bias_ih_l0, rnn.bias_ih_l0_reverse */
+  MRNB_TL_BHH,     /* [2,1024]      rnn.bias_hh_l0, rnn.bias_hh_l0_reverse */
+  MRNB_TL_LIN_W,   /* [256,512]     linear.weight */
+  MRNB_TL_LIN_B,   /* [256] */
+  MRNB_TL_COUNT
+};
+typedef struct MrnbCrnnTrainPack {
+  const float* p[MRNB_T_COUNT]; /* fp32 parameters (or gradients) */
+  const void* h[MRNB_T_COUNT];  /* bf16 copies of the GEMM weights at the same element offsets; MRNB_PREC_BF16 only */
+  float* bn_mean[2];            /* ConvNet.12 / ConvNet.15 running_mean [512] (updated in train mode) */
+  float* bn_var[2];
+  int n_class;
+} MrnbCrnnTrainPack;
+
+size_t mrnb_crnn_train_workspace_bytes(int B, int n_class, int prec);
+/* logits / dlogits: [B,63,ld] fp32.  MRNB_PREC_BF16 needs B % 64 == 0 (GEMM contraction over B*63 rows). */
+int mrnb_crnn_train_forward(const MrnbCrnnTrainPack* pack, const float* image, int B, int prec, int bn_batch_stats,
+                            int update_running, float* logits, long ld_logits, void* workspace, size_t workspace_bytes,
+                            cudaStream_t stream);
+int mrnb_crnn_train_backward(const MrnbCrnnTrainPack* pack, const MrnbCrnnTrainPack* grads, const float* dlogits,
+                             long ld_dlogits, int B, int prec, int bn_batch_stats, float* grad_arena, long n_arena,
+                             void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * DM-Router + gate head.   Replaces modules/dm_router.py:50-67 (DM_Router.forward, both gating blocks) and
  * modules/model.py:402-406 (train) / :371-377 (eval): rearrange -> channel_route -> route -> softmax / argmax.
  *

@@ -50,6 +50,25 @@ class MrnbCrnnPack(C.Structure):
                 ("n_class", C.c_int * MAX_EXPERTS)]
 
 
+# CRNN training pack slots (include/mrn_b200.h MRNB_T_*)
+(T_CONV0_W, T_CONV0_B, T_CONV1_W, T_CONV1_B, T_CONV2_W, T_CONV2_B, T_CONV3_W, T_CONV3_B, T_CONV4_W, T_BN4_W, T_BN4_B,
+ T_CONV5_W, T_BN5_W, T_BN5_B, T_CONV6_W, T_CONV6_B) = range(16)
+T_LSTM0 = 16
+TL_COUNT = 6
+TL_WIH, TL_WHH, TL_BIH, TL_BHH, TL_LIN_W, TL_LIN_B = range(6)
+T_FC_W = T_LSTM0 + 2 * TL_COUNT
+T_FC_B = T_FC_W + 1
+T_COUNT = T_FC_B + 1
+
+
+class MrnbCrnnTrainPack(C.Structure):
+    _fields_ = [("p", C.c_void_p * T_COUNT),
+                ("h", C.c_void_p * T_COUNT),
+                ("bn_mean", C.c_void_p * 2),
+                ("bn_var", C.c_void_p * 2),
+                ("n_class", C.c_int)]
+
+
 _vp, _i, _l, _f, _sz = C.c_void_p, C.c_int, C.c_long, C.c_float, C.c_size_t
 
 _SIGNATURES = {
@@ -67,6 +86,10 @@ _SIGNATURES = {
     "mrnb_svtr_train_forward": (_i, [C.POINTER(MrnbSvtrPack), _vp, _i, _i, _i, _i, _vp, _vp, _l, _vp, _sz, _vp]),
     "mrnb_svtr_train_backward": (_i, [C.POINTER(MrnbSvtrPack), C.POINTER(MrnbSvtrPack), _vp, _vp, _l, _i, _i, _i, _vp,
                                       _vp, _l, _vp, _sz, _vp]),
+    "mrnb_crnn_train_workspace_bytes": (_sz, [_i, _i, _i]),
+    "mrnb_crnn_train_forward": (_i, [C.POINTER(MrnbCrnnTrainPack), _vp, _i, _i, _i, _i, _vp, _l, _vp, _sz, _vp]),
+    "mrnb_crnn_train_backward": (_i, [C.POINTER(MrnbCrnnTrainPack), C.POINTER(MrnbCrnnTrainPack), _vp, _l, _i, _i, _i, _vp,
+                                      _l, _vp, _sz, _vp]),
     "mrnb_crnn_workspace_bytes": (_sz, [_i, _i, _i]),
     "mrnb_crnn_experts_forward": (_i, [C.POINTER(MrnbCrnnPack), _vp, _i, _i, _i, _i, _vp, C.POINTER(_vp), C.POINTER(_l),
                                        _vp, _sz, _vp]),

@@ -155,7 +155,8 @@ int mrnb_sgemm(const MrnbGemm& p, cudaStream_t st) {
   const int z = p.splitk > 1 ? p.splitk : p.batch;
   MrnbProfScope prof(MRNB_PROF_SGEMM, st, 2.0 * p.M * p.N * p.K * p.batch,
                      4.0 * p.batch * ((double)p.M * p.K + (double)p.N * p.K + (double)p.M * p.N));
-  if (p.M >= 96 && p.N >= 96) {
+  // 128 x 128 tiles only when they fill the machine; small problems (the LSTM recurrences) take 64 x 64 tiles
+  if (p.M >= 96 && p.N >= 96 && (long)cdiv(p.N, 128) * cdiv(p.M, 128) * z >= 148) {
     dim3 grid(cdiv(p.N, 128), cdiv(p.M, 128), z);
     sgemm_kernel<128, 128, 8, 8><<<grid, 256, 0, st>>>(p);
   } else {

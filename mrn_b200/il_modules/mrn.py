@@ -265,13 +265,11 @@ class MRN(object):
         """Moves the newest expert's parameters into a flat training arena (ops.SvtrTrainPack) and builds the fused
         optimiser over it (Adam + OneCycle over num_iter steps, il_modules/base.py:84-108)."""
         net = self.net
-        if _arch(net.opt) != "svtr":
-            raise NotImplementedError("stage-0 training is implemented for SVTR experts; the CRNN expert backward "
-                                      "(VGG convolutions + BiLSTM BPTT) is not. No PyTorch fallback.")
         expert = net.model[-1]
         net._sync_bn()
         sd = {k: v for k, v in expert.state_dict().items()}
-        self._tp = ops.SvtrTrainPack(sd, self.device, L_PREC_TRAIN(net.opt))
+        pack_cls = ops.SvtrTrainPack if _arch(net.opt) == "svtr" else ops.CrnnTrainPack
+        self._tp = pack_cls(sd, self.device, L_PREC_TRAIN(net.opt))
         self.optimizer = ArenaAdam(self._tp.params, self._tp.grads, self.opt.lr,
                                    int(total_steps or self.opt.num_iter), grad_clip=self.opt.grad_clip,
                                    schedule=getattr(self.opt, "schedule", "super"))
@@ -289,10 +287,15 @@ class MRN(object):
             for key, t in tp.state().items():
                 own[key].copy_(t)                       # bumps the version counter -> inference packs are rebuilt
             cn = expert.model.FeatureExtraction.ConvNet
-            for bn, (sm, sv) in ((cn.patch_embed.proj[1], (ops.L.P_BN0_MEAN, ops.L.P_BN0_VAR)),
-                                 (cn.patch_embed.proj[4], (ops.L.P_BN1_MEAN, ops.L.P_BN1_VAR))):
-                bn.running_mean.copy_(tp.bn_stats[sm].reshape(-1))
-                bn.running_var.copy_(tp.bn_stats[sv].reshape(-1))
+            if getattr(tp, "arch", "svtr") == "crnn":
+                pairs = ((cn[12], tp.bn_stats[(0, "mean")], tp.bn_stats[(0, "var")]),
+                         (cn[15], tp.bn_stats[(1, "mean")], tp.bn_stats[(1, "var")]))
+            else:
+                pairs = ((cn.patch_embed.proj[1], tp.bn_stats[ops.L.P_BN0_MEAN], tp.bn_stats[ops.L.P_BN0_VAR]),
+                         (cn.patch_embed.proj[4], tp.bn_stats[ops.L.P_BN1_MEAN], tp.bn_stats[ops.L.P_BN1_VAR]))
+            for bn, mean, var in pairs:
+                bn.running_mean.copy_(mean.reshape(-1))
+                bn.running_var.copy_(var.reshape(-1))
                 bn.num_batches_tracked += self._tp_steps
         self._tp_steps = 0
         self.net._cache.key = None                      # BN buffers changed without a parameter version bump
@@ -306,19 +309,26 @@ class MRN(object):
         expert = self.net.model[-1]
         train_mode = bool(expert.training)
         B = image.shape[0]
-        if train_mode and drop_scales is None and getattr(self.opt, "drop_path", True):
+        crnn = getattr(tp, "arch", "svtr") == "crnn"
+        if not crnn and train_mode and drop_scales is None and getattr(self.opt, "drop_path", True):
             rates = expert.model.FeatureExtraction.ConvNet.drop_path_rates()
             drop_scales = sample_drop_scales(1, B, rates, image.device)[0].contiguous()
         image = image.contiguous().float()
-        logits = ops.svtr_train_forward(tp, image, bn_batch_stats=train_mode, update_running=train_mode,
-                                        drop_scales=drop_scales)
+        if crnn:
+            logits = ops.crnn_train_forward(tp, image, bn_batch_stats=train_mode, update_running=train_mode)
+        else:
+            logits = ops.svtr_train_forward(tp, image, bn_batch_stats=train_mode, update_running=train_mode,
+                                            drop_scales=drop_scales)
         gate = self.__dict__.get("_ones")
         if gate is None or gate.shape[0] != B or gate.device != image.device:
             gate = self._ones = torch.ones(B, 1, device=image.device, dtype=torch.float32)
         r = ops.gate_combine([logits], gate, labels_index, labels_length)        # row log-sum-exp + label gathers
         c = ops.ctc_lattice(r["lpe"], labels_index, labels_length, want_occ=True)
         dlogits = ops.ctc_dense_grad(logits, r["lse"], c["occ"], c["nll"], labels_index, labels_length, 1.0 / B)
-        ops.svtr_train_backward(tp, image, dlogits, bn_batch_stats=train_mode, drop_scales=drop_scales)
+        if crnn:
+            ops.crnn_train_backward(tp, dlogits, B, bn_batch_stats=train_mode)
+        else:
+            ops.svtr_train_backward(tp, image, dlogits, bn_batch_stats=train_mode, drop_scales=drop_scales)
         mdist.allreduce_mean_(tp.grads)                  # the ONE exchange step (28 MB; replaces nn.DataParallel)
         self.optimizer.step()                            # clip_grad_norm_(5) + Adam + OneCycle
         if train_mode:

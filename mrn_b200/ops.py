@@ -13,6 +13,7 @@ import torch
 from . import _lib as L
 
 T_FRAMES = 64      # MRNNet.patch for SVTR (modules/model.py:324)
+T_FRAMES_CRNN = 63  # MRNNet.patch for CRNN (modules/model.py:322-323)
 D_FEAT = 256       # opt.hidden_size
 
 
@@ -431,8 +432,107 @@ def svtr_train_backward(tp: SvtrTrainPack, image, dlogits, bn_batch_stats=True, 
     return tp.grads
 
 
+class CrnnTrainPack:
+    """ONE CRNN expert's trainable parameters in a single flat fp32 arena (MrnbCrnnTrainPack slots: conv weights as
+    [Cout,kh,kw,Cin]; each LSTM tensor = forward direction then reverse direction), a gradient arena with the same
+    layout and the two BatchNorm running statistics.  `entries` maps arena slices back to state_dict keys."""
+
+    arch = "crnn"
+    n_frames = 63
+
+    def __init__(self, expert_sd: Dict[str, torch.Tensor], device, prec: int = L.PREC_FP32):
+        self.device = torch.device(device)
+        self.prec = prec
+        cn = "model.FeatureExtraction.ConvNet."
+        hwc = (0, 2, 3, 1)
+        slots = [(L.T_CONV0_W, [(cn + "0.weight", hwc)]), (L.T_CONV0_B, [(cn + "0.bias", None)]),
+                 (L.T_CONV1_W, [(cn + "3.weight", hwc)]), (L.T_CONV1_B, [(cn + "3.bias", None)]),
+                 (L.T_CONV2_W, [(cn + "6.weight", hwc)]), (L.T_CONV2_B, [(cn + "6.bias", None)]),
+                 (L.T_CONV3_W, [(cn + "8.weight", hwc)]), (L.T_CONV3_B, [(cn + "8.bias", None)]),
+                 (L.T_CONV4_W, [(cn + "11.weight", hwc)]), (L.T_BN4_W, [(cn + "12.weight", None)]), (L.T_BN4_B, [(cn + "12.bias", None)]),
+                 (L.T_CONV5_W, [(cn + "14.weight", hwc)]), (L.T_BN5_W, [(cn + "15.weight", None)]), (L.T_BN5_B, [(cn + "15.bias", None)]),
+                 (L.T_CONV6_W, [(cn + "18.weight", hwc)]), (L.T_CONV6_B, [(cn + "18.bias", None)])]
+        for k in range(2):
+            q = f"model.SequenceModeling.{k}."
+            base = L.T_LSTM0 + k * L.TL_COUNT
+            for sl, nm in ((L.TL_WIH, "weight_ih_l0"), (L.TL_WHH, "weight_hh_l0"), (L.TL_BIH, "bias_ih_l0"), (L.TL_BHH, "bias_hh_l0")):
+                slots.append((base + sl, [(q + "rnn." + nm, None), (q + "rnn." + nm + "_reverse", None)]))
+            slots += [(base + L.TL_LIN_W, [(q + "linear.weight", None)]), (base + L.TL_LIN_B, [(q + "linear.bias", None)])]
+        slots += [(L.T_FC_W, [("fc.weight", None)]), (L.T_FC_B, [("fc.bias", None)])]
+        self.entries = []                         # (slot, key, permute, offset, kernel-layout shape)
+        self.slot_offset = {}
+        off = 0
+        for slot, parts in slots:
+            self.slot_offset[slot] = off
+            for key, perm in parts:
+                shp = tuple(expert_sd[key].shape)
+                if perm is not None:
+                    shp = tuple(shp[a] for a in perm)
+                self.entries.append((slot, key, perm, off, shp))
+                n = 1
+                for v in shp:
+                    n *= v
+                assert n % 8 == 0 or len(parts) == 1, key
+                off += n
+            off = round_up(off, 8)
+        self.numel = off
+        self.params = torch.zeros(off, device=self.device, dtype=torch.float32)
+        self.grads = torch.zeros(off, device=self.device, dtype=torch.float32)
+        self.shadow16 = torch.zeros(off, device=self.device, dtype=torch.bfloat16) if prec == L.PREC_BF16 else None
+        self.bn_stats = {}
+        for q, idx in enumerate((12, 15)):
+            self.bn_stats[(q, "mean")] = expert_sd[cn + f"{idx}.running_mean"].detach().to(self.device, torch.float32).clone().contiguous()
+            self.bn_stats[(q, "var")] = expert_sd[cn + f"{idx}.running_var"].detach().to(self.device, torch.float32).clone().contiguous()
+        self.n_class = int(expert_sd["fc.weight"].shape[0])
+        self.struct = L.MrnbCrnnTrainPack()
+        self.gstruct = L.MrnbCrnnTrainPack()
+        for st_, arena in ((self.struct, self.params), (self.gstruct, self.grads)):
+            st_.n_class = self.n_class
+            for slot, o in self.slot_offset.items():
+                st_.p[slot] = arena.data_ptr() + 4 * o
+                if self.shadow16 is not None and st_ is self.struct:
+                    st_.h[slot] = self.shadow16.data_ptr() + 2 * o
+            for q in range(2):
+                st_.bn_mean[q] = self.bn_stats[(q, "mean")].data_ptr()
+                st_.bn_var[q] = self.bn_stats[(q, "var")].data_ptr()
+        self.load_state(expert_sd)
+        self._ws: Optional[torch.Tensor] = None
+
+    view = SvtrTrainPack.view
+    load_state = SvtrTrainPack.load_state
+    state = SvtrTrainPack.state
+    refresh_shadow = SvtrTrainPack.refresh_shadow
+
+    def workspace(self, B):
+        need = int(L.load().mrnb_crnn_train_workspace_bytes(B, self.n_class, self.prec))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+
+def crnn_train_forward(tp: CrnnTrainPack, image, bn_batch_stats=True, update_running=True):
+    """Activation-keeping forward of the CRNN expert being trained.  Returns logits [B,63,C]."""
+    _chk_f32(image)
+    B = image.shape[0]
+    ld = round_up(tp.n_class, 4)
+    buf = torch.empty(B, T_FRAMES_CRNN, ld, device=image.device, dtype=torch.float32)
+    ws = tp.workspace(B)
+    tp.refresh_shadow()
+    L.check(L.load().mrnb_crnn_train_forward(C.byref(tp.struct), _p(image), B, tp.prec, int(bn_batch_stats), int(update_running),
+                                             _p(buf), ld, _p(ws), ws.numel(), _stream()), "crnn_train_forward")
+    return buf[:, :, :tp.n_class]
+
+
+def crnn_train_backward(tp: CrnnTrainPack, dlogits, B, bn_batch_stats=True):
+    assert dlogits.dtype == torch.float32 and dlogits.stride(2) == 1 and dlogits.stride(0) == dlogits.shape[1] * dlogits.stride(1)
+    ws = tp.workspace(B)
+    L.check(L.load().mrnb_crnn_train_backward(C.byref(tp.struct), C.byref(tp.gstruct), _p(dlogits), dlogits.stride(1), B, tp.prec,
+                                              int(bn_batch_stats), _p(tp.grads), tp.numel, _p(ws), ws.numel(), _stream()),
+            "crnn_train_backward")
+    return tp.grads
+
+
 # ------------------------------------------------------------------------------------------------ CRNN experts
-T_FRAMES_CRNN = 63          # modules/model.py:322-323
 
 _VGG_GEMM_CONVS = ((L.C_CONV1_W, L.C_CONV1_B, 3), (L.C_CONV2_W, L.C_CONV2_B, 6), (L.C_CONV3_W, L.C_CONV3_B, 8),
                    (L.C_CONV4_W, None, 11), (L.C_CONV5_W, None, 14), (L.C_CONV6_W, L.C_CONV6_B, 18))

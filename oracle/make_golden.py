@@ -163,19 +163,19 @@ def run_case(name, class_counts, B, seed, arch="svtr"):
     print(name, "->", path, os.path.getsize(path) // 1024, "KiB")
 
 
-def run_stage0_case(name, class_counts, B, seed, bn_train=True):
+def run_stage0_case(name, class_counts, B, seed, bn_train=True, arch="svtr"):
     """One stage-0 iteration of the unmodified reference (il_modules/mrn.py:236-267): the newest expert trained end to
     end through `model(image, cross=False)` with CTC, earlier experts frozen (mrn.py:154-157).  Train mode (BatchNorm
     batch statistics, DropPath masks injected so the run is reproducible)."""
     I = len(class_counts)
-    sd = synth.synth_state_dict(class_counts, seed, arch="svtr")
+    sd = synth.synth_state_dict(class_counts, seed, arch=arch)
     img, tgt, lens, dom = synth.synth_batch(B, class_counts, seed)
     tgt = tgt.clamp(max=class_counts[-1] - 1)
     rates = [0.1 * i / 11 for i in range(12)]
     drop = synth.synth_drop_scales(I, B, rates, seed)
     g = {}
     with reference_modules() as ref:
-        net = build_ref_net(ref, class_counts, sd, "svtr")
+        net = build_ref_net(ref, class_counts, sd, arch)
         crit = torch.nn.CTCLoss(reduction="mean", zero_infinity=True)       # il_modules/base.py:131
         for i in range(I - 1):
             for p in net.model[i].parameters():
@@ -187,7 +187,7 @@ def run_stage0_case(name, class_counts, B, seed, bn_train=True):
         def injected(x, drop_prob=0., training=False, scale_by_keep=True):
             s = queue.pop(0)
             return x * s.view(-1, 1, 1)
-        if bn_train:
+        if bn_train and arch == "svtr":
             ref.svtr.drop_path = injected
             for j in range(12):
                 if rates[j] > 0:
@@ -215,11 +215,12 @@ def run_stage0_case(name, class_counts, B, seed, bn_train=True):
         for n_, p in net.named_parameters():
             if p.grad is not None:
                 g["adam1." + n_] = keep(p.detach(), 101, 2048)
-        bn = net.model[I - 1].model.FeatureExtraction.ConvNet.patch_embed.proj
-        g["bn0_running_mean"] = bn[1].running_mean.numpy().copy(); g["bn0_running_var"] = bn[1].running_var.numpy().copy()
-        g["bn1_running_mean"] = bn[4].running_mean.numpy().copy(); g["bn1_running_var"] = bn[4].running_var.numpy().copy()
+        cn = net.model[I - 1].model.FeatureExtraction.ConvNet
+        bn = (cn.patch_embed.proj[1], cn.patch_embed.proj[4]) if arch == "svtr" else (cn[12], cn[15])
+        g["bn0_running_mean"] = bn[0].running_mean.numpy().copy(); g["bn0_running_var"] = bn[0].running_var.numpy().copy()
+        g["bn1_running_mean"] = bn[1].running_mean.numpy().copy(); g["bn1_running_var"] = bn[1].running_var.numpy().copy()
     g["class_counts"] = np.array(class_counts); g["B"] = np.int64(B); g["seed"] = np.int64(seed)
-    g["bn_train"] = np.int64(int(bn_train))
+    g["bn_train"] = np.int64(int(bn_train)); g["arch"] = np.array(arch)
     g["sub"] = np.int64(SUB); g["max_full"] = np.int64(MAX_FULL)
     g["psub"] = np.int64(101); g["pmax_full"] = np.int64(2048)
     os.makedirs(OUT, exist_ok=True)
@@ -265,6 +266,8 @@ if __name__ == "__main__":
     if not only or "stage0" in only:
         run_stage0_case("svtr_stage0_i2_b3", (37, 61), 3, 17)
         run_stage0_case("svtr_stage0_i1_b2_eval", (45,), 2, 29, bn_train=False)
+        run_stage0_case("crnn_stage0_i2_b3", (37, 61), 3, 19, arch="crnn")
+        run_stage0_case("crnn_stage0_i1_b2_eval", (45,), 2, 31, bn_train=False, arch="crnn")
     if only and "router" not in only:
         sys.exit(0)
     run_router_case("dm_router_i3_b2", 3, 2, 5)

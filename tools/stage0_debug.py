@@ -16,5 +16,5 @@ for name in sys.argv[1:] or ["svtr_stage0_i2_b3"]:
         ref = g["grad." + pre + key]
         scale = max(float(np.abs(ref).max()), 1e-4 * tn)
         err = np.abs(pview(gg.contiguous().cpu(), g) - ref).max() / scale
-        if err > (1e-4 if PREC == 0 else 3e-2):
+        if err > (1e-4 if PREC == 0 else 3e-2) or os.environ.get('ALL'):
             print("%-70s err %.3e  |ref| %.3e |got| %.3e" % (key, err, float(g["gradnorm." + pre + key]), float(gg.norm())))
