@@ -267,11 +267,10 @@ def run_ours(args):
         opt.num_iter = 1000000
         learner.begin_expert_training()                 # newest expert (C = 5153) -> flat training arena + fused Adam
         mdist.broadcast_(learner._tp.params)
-        use_graph = False
     if infer:
         learner.model.eval()                            # validation(): model.eval(), hard route, greedy decode (test.py:139-221)
 
-    use_graph = not args.no_graph and not stage0
+    use_graph = not args.no_graph
     train_step = learner.train_step_stage1_graphed if use_graph else learner.train_step_stage1
     infer_step = learner.infer_batch_graphed if use_graph else learner.infer_batch
 
@@ -281,7 +280,7 @@ def run_ours(args):
             r = (learner.infer_batch if eager else infer_step)(img, "TF")
             return r["conf"], r["lens"]
         if stage0:
-            l0 = learner.train_step_stage0(img, tgt, lens)
+            l0 = (learner.train_step_stage0 if (eager or not use_graph) else learner.train_step_stage0_graphed)(img, tgt, lens)
             return l0, l0
         return (learner.train_step_stage1 if eager else train_step)(img, tgt, lens, dom)
 
@@ -298,7 +297,7 @@ def run_ours(args):
             ids = r["ids"].cpu()                        # the single D2H copy of the decoded ids (+ lengths, confidences)
             return float(r["conf"].sum()), float(r["lens"].sum()) + float(ids[0, 0])
         if stage0:
-            l0 = float(learner.train_step_stage0(img, tgt, lens))
+            l0 = float((learner.train_step_stage0_graphed if use_graph else learner.train_step_stage0)(img, tgt, lens))
             return l0, l0
         l1, l2 = train_step(img, tgt, lens, dom)
         return float(l1), float(l2)                     # D2H read of both losses (the reference logs them)

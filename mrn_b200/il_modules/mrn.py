@@ -301,10 +301,9 @@ class MRN(object):
         self.net._cache.key = None                      # BN buffers changed without a parameter version bump
         self.reset_graphs()
 
-    def train_step_stage0(self, image, labels_index, labels_length, drop_scales=None):
-        """One expert-training iteration (il_modules/mrn.py:236-267) on the device: forward of the newest expert in its
-        current mode (train: BatchNorm batch statistics + DropPath), mean CTC loss, full backward, gradient all-reduce,
-        clip + Adam.  Returns the loss as a 1-element device tensor."""
+    def _stage0_device(self, image, labels_index, labels_length, drop_scales=None):
+        """Forward of the newest expert (keeping activations), mean CTC loss, full backward into the gradient arena.
+        Pure device work on the current stream (capturable in a CUDA graph).  Returns the loss (1-element tensor)."""
         tp = self._tp
         expert = self.net.model[-1]
         train_mode = bool(expert.training)
@@ -329,11 +328,47 @@ class MRN(object):
             ops.crnn_train_backward(tp, dlogits, B, bn_batch_stats=train_mode)
         else:
             ops.svtr_train_backward(tp, image, dlogits, bn_batch_stats=train_mode, drop_scales=drop_scales)
-        mdist.allreduce_mean_(tp.grads)                  # the ONE exchange step (28 MB; replaces nn.DataParallel)
-        self.optimizer.step()                            # clip_grad_norm_(5) + Adam + OneCycle
-        if train_mode:
-            self._tp_steps += 1
         return c["loss"]
+
+    def train_step_stage0(self, image, labels_index, labels_length, drop_scales=None):
+        """One expert-training iteration (il_modules/mrn.py:236-267) on the device: forward of the newest expert in its
+        current mode (train: BatchNorm batch statistics + DropPath), mean CTC loss, full backward, gradient all-reduce,
+        clip + Adam.  Returns the loss as a 1-element device tensor."""
+        loss = self._stage0_device(image, labels_index, labels_length, drop_scales)
+        mdist.allreduce_mean_(self._tp.grads)            # the ONE exchange step (28 MB; replaces nn.DataParallel)
+        self.optimizer.step()                            # clip_grad_norm_(5) + Adam + OneCycle
+        if self.net.model[-1].training:
+            self._tp_steps += 1
+        return loss
+
+    def train_step_stage0_graphed(self, image, labels_index, labels_length):
+        """train_step_stage0 with the device work up to the gradients (450 - 740 launches, many of them the tiny
+        sequential LSTM steps of a CRNN expert) replayed from a CUDA graph captured per batch size; the gradient
+        all-reduce and the optimiser step stay eager.  First call eager (lazy allocations), second captures, later ones
+        replay.  DropPath masks are drawn inside the graph by torch's graph-safe generator."""
+        B = int(image.shape[0])
+        cache = self.__dict__.setdefault("_train_graphs", {})
+        key = ("stage0", B, str(image.device), bool(self.net.model[-1].training))
+        ent = cache.get(key)
+        if ent is None:
+            cache[key] = "warm"
+            return self.train_step_stage0(image, labels_index, labels_length)
+        if ent == "warm":
+            st_in = tuple(t.clone() for t in (image, labels_index, labels_length))
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                loss = self._stage0_device(*st_in)
+            ent = cache[key] = (graph, st_in, loss)
+        graph, st_in, loss = ent
+        for dst, src in zip(st_in, (image, labels_index, labels_length)):
+            dst.copy_(src, non_blocking=True)
+        graph.replay()
+        mdist.allreduce_mean_(self._tp.grads)
+        self.optimizer.step()
+        if key[3]:
+            self._tp_steps += 1
+        return loss
 
     def _init_train(self, start_iter, taski, train_loader, valid_loader, cross=False):
         """il_modules/mrn.py:225-279."""
@@ -345,7 +380,8 @@ class MRN(object):
             image_tensors, labels = train_loader.get_batch()
             image = image_tensors.to(self.device, non_blocking=True)
             labels_index, labels_length = self.converter.encode(labels, batch_max_length=self.opt.batch_max_length)
-            loss = self.train_step_stage0(image, labels_index, labels_length)
+            step = self.train_step_stage0_graphed if getattr(self.opt, "cuda_graph", True) else self.train_step_stage0
+            loss = step(image, labels_index, labels_length)
             train_loss_avg.add(loss)
             if iteration % self.opt.val_interval == 0 or iteration == self.opt.num_iter:
                 self.end_expert_training()

@@ -259,3 +259,38 @@ def test_crnn_stage0_bf16_tensor_core_mode_tracks_fp32_mode_at_batch_64():
         if e > budget or cos < 0.97:
             bad.append((k, e, cos))
     assert not bad, bad
+
+
+@pytest.mark.parametrize("arch", ["svtr", "crnn"])
+def test_stage0_cuda_graph_replay_matches_eager(arch):
+    """train_step_stage0_graphed (forward + CTC + backward replayed from a CUDA graph) == the eager step, over three
+    iterations on rotating batches (DropPath off: the graph draws its masks from torch's graph-safe generator)."""
+    from mrn_b200.il_modules.mrn import MRN, RankLocal
+    cc, B = (40,), 4
+    sd = synth.synth_state_dict(cc, 13, arch=arch)
+    batches = [synth.synth_batch(B, cc, 50 + k) for k in range(2)]
+    outs = []
+    for graphed in (False, True):
+        opt = make_opt()
+        opt.drop_path, opt.num_iter, opt.schedule = False, 100, "const"
+        if arch == "crnn":
+            opt.FeatureExtraction, opt.SequenceModeling = "VGG", "BiLSTM"
+        net, _ = build_net(cc, sd) if arch == "svtr" else (None, None)
+        learner = MRN(opt)
+        learner.model.update_fc(opt.hidden_size, cc[0]); learner.model.build_prediction(opt, cc[0])
+        learner.model.load_state_dict(sd, strict=True)
+        learner.model = RankLocal(learner.net).cuda()
+        learner.model.train()
+        learner.begin_expert_training()
+        losses = []
+        for k in range(4):
+            img, tgt, lens, _ = batches[k % 2]
+            step = learner.train_step_stage0_graphed if graphed else learner.train_step_stage0
+            losses.append(float(step(img.cuda(), tgt.cuda(), lens.cuda())))
+        torch.cuda.synchronize()
+        outs.append((losses, learner._tp.params.clone()))
+    (l0, p0), (l1, p1) = outs
+    # split-K atomics reorder the fp32 sums; Adam's first steps (lr * sign-like) amplify that round-off in later losses
+    assert np.allclose(l0[:2], l1[:2], rtol=1e-5) and np.allclose(l0, l1, rtol=1e-3), (l0, l1)
+    d = (p0 - p1).abs()
+    assert float(d.max()) <= 5e-4 * 4.01 and float((d > 5e-5).float().mean()) < 2e-2
