@@ -106,7 +106,7 @@ struct Epi2 {
   const float* mul; const float* res;
   int M, N, KB_total, kb_per_split, splits, gelu;
   int tiles_n, tiles_m; long total_tiles;
-  int simple;      // plain row-major output, no bias / mul / res / gelu: the lean epilogue (straight stores or vector reductions)
+  int simple;      // plain row-major output addressing: the lean epilogue (whole-line vector loads / stores / reductions)
   float alpha;
 };
 
@@ -263,12 +263,38 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 red_add_v4(ep.out32 + o + j, __uint_as_float(r[j]) * ep.alpha, __uint_as_float(r[j + 1]) * ep.alpha,
                            __uint_as_float(r[j + 2]) * ep.alpha, __uint_as_float(r[j + 3]) * ep.alpha);
             } else {
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha + bm;
+              if (ep.bias_n) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias_n + col0 + j));
+                  v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                }
+              }
+              if (ep.gelu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+              }
+              if (ep.mul) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 m4 = *reinterpret_cast<const float4*>(ep.mul + o + j);
+                  v[j] *= m4.x; v[j + 1] *= m4.y; v[j + 2] *= m4.z; v[j + 3] *= m4.w;
+                }
+              }
+              if (ep.res) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 r4 = *reinterpret_cast<const float4*>(ep.res + o + j);
+                  v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+                }
+              }
               if (ep.out32) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
-                  *reinterpret_cast<float4*>(ep.out32 + o + j) =
-                      make_float4(__uint_as_float(r[j]) * ep.alpha, __uint_as_float(r[j + 1]) * ep.alpha,
-                                  __uint_as_float(r[j + 2]) * ep.alpha, __uint_as_float(r[j + 3]) * ep.alpha);
+                  *reinterpret_cast<float4*>(ep.out32 + o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
               }
               if (ep.out16) {
 #pragma unroll
@@ -276,8 +302,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                   uint32_t pk[4];
 #pragma unroll
                   for (int u = 0; u < 4; ++u) {
-                    __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[j + 2 * u]) * ep.alpha,
-                                                             __uint_as_float(r[j + 2 * u + 1]) * ep.alpha);
+                    __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * u], v[j + 2 * u + 1]);
                     pk[u] = *reinterpret_cast<uint32_t*>(&h);
                   }
                   *reinterpret_cast<uint4*>(ep.out16 + o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -287,12 +312,15 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           } else {
             for (int j = 0; j < 32; ++j) {
               if (col0 + j >= ep.N) break;
-              const float x = __uint_as_float(r[j]) * ep.alpha;
-              if (!plain) atomicAdd(ep.out32 + o + j, x);
-              else {
-                if (ep.out32) ep.out32[o + j] = x;
-                if (ep.out16) ep.out16[o + j] = __float2bfloat16_rn(x);
-              }
+              float x = __uint_as_float(r[j]) * ep.alpha;
+              if (!plain) { atomicAdd(ep.out32 + o + j, x); continue; }
+              x += bm;
+              if (ep.bias_n) x += __ldg(ep.bias_n + col0 + j);
+              if (ep.gelu) x = gelu_erf(x);
+              if (ep.mul) x *= ep.mul[o + j];
+              if (ep.res) x += ep.res[o + j];
+              if (ep.out32) ep.out32[o + j] = x;
+              if (ep.out16) ep.out16[o + j] = __float2bfloat16_rn(x);
             }
           }
         }
@@ -421,7 +449,7 @@ int launch2(const MrnbTcGemm2& p, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)STAGES * (A_BYTES + BN * BK * 2);
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(tc_gemm2_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-  ep.simple = (!p.bias_n && !p.bias_m && !p.mul && !p.res && !p.gelu && p.cn.si == 1 && p.cn.inner >= p.N && p.cm.inner >= p.M) ? 1 : 0;
+  ep.simple = (p.cn.si == 1 && p.cn.inner >= p.N && p.cm.inner >= p.M) ? 1 : 0;
   ep.tiles_n = cdiv(p.N, BN); ep.tiles_m = cdiv(p.M, BM);
   ep.total_tiles = (long)ep.tiles_n * ep.tiles_m * p.groups * splits;
   static int n_sm = 0;
