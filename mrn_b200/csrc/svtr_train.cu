@@ -20,6 +20,12 @@
 #include "train_util.cuh"
 #include "svtr.h"
 
+// attn_train_tc.cu: fused score / softmax and dP / dS kernels
+int mrnb_attn_scores_softmax(const void* qkv, void* P, int B, int N, int d, int heads, int W, int local, float scale,
+                             cudaStream_t st);
+int mrnb_attn_dp_ds(const void* dO16, const void* qkv, const float* dO, const void* O, const void* P, void* dS, int B, int N,
+                    int d, int heads, cudaStream_t st);
+
 namespace {
 
 constexpr int KV_LD = 36;
@@ -575,70 +581,10 @@ int attention_train_bwd(const AT* qkv, const AT* o, const float* dO, const float
 //   backward: dP = dO V^T -> dS = P (dP - D), D = dO.O -> dV = P^T dO, dQ = scale dS K, dK = scale dS^T Q
 // The Local mixer (modules/svtr.py:116-128) is the same dense path with masked probabilities set to zero.
 // ------------------------------------------------------------------------------------------------
-template <int N>
-__global__ void __launch_bounds__(256)
-softmax_rows_kernel(const float* __restrict__ S, bf16* __restrict__ P, long rows, int W, int local) {
-  constexpr int VPT = N / 32;
-  const long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (r >= rows) return;
-  const int n = (int)(r % N), nh = n / W, nw = n % W;
-  float v[VPT];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < VPT; ++i) {
-    const int m = lane + 32 * i;
-    float x = S[r * N + m];
-    if (local) {
-      const int dh = m / W - nh, dw = m % W - nw;
-      if (dh < -3 || dh > 3 || dw < -5 || dw > 5) x = -INFINITY;
-    }
-    v[i] = x; mx = fmaxf(mx, x);
-  }
-  mx = warp_max(mx);
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < VPT; ++i) { v[i] = __expf(v[i] - mx); sum += v[i]; }
-  const float inv = 1.0f / warp_sum(sum);
-#pragma unroll
-  for (int i = 0; i < VPT; ++i) P[r * N + lane + 32 * i] = __float2bfloat16_rn(v[i] * inv);
-}
-
-template <int N>
-__global__ void __launch_bounds__(256)
-attn_ds_kernel(const bf16* __restrict__ P, const float* __restrict__ dP, const float* __restrict__ dO,
-               const bf16* __restrict__ O, bf16* __restrict__ dS, long rows, int d, int heads) {
-  constexpr int VPT = N / 32;
-  const long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (r >= rows) return;
-  const long gh = r / N;
-  const int n = (int)(r % N);
-  const long base = ((gh / heads) * N + n) * d + (gh % heads) * 32 + lane;
-  const float D = warp_sum(dO[base] * __bfloat162float(O[base]));
-#pragma unroll
-  for (int i = 0; i < VPT; ++i) {
-    const long o = r * N + lane + 32 * i;
-    dS[o] = __float2bfloat16_rn(__bfloat162float(P[o]) * (dP[o] - D));
-  }
-}
-
-int attn_tc_forward(const bf16* qkv, float* S, bf16* P, bf16* att, int B, int N, int d, int heads, int W, bool local, cudaStream_t st) {
+int attn_tc_forward(const bf16* qkv, bf16* P, bf16* att, int B, int N, int d, int heads, int W, bool local, cudaStream_t st) {
   const long GH = (long)B * heads;
-  MrnbTcGemm2 g{};
-  g.a = mrnb_operand_head(qkv, N, 3L * d, heads, B, 0, 128);
-  g.b = mrnb_operand_head(qkv + d, N, 3L * d, heads, B, 0, 128);
-  g.out32 = S; g.cm = mrnb_axis(N); g.cn = mrnb_axis(1); g.c_gstride = (long)N * N;
-  g.M = N; g.N = N; g.K = 64; g.groups = (int)GH; g.splitk = 1; g.alpha = ATT_SCALE;
-  MRNB_TRY(mrnb_tc_gemm2(g, st));
-  {
-    MrnbProfScope prof(MRNB_PROF_ATTN, st, 0.0, (double)GH * N * N * 6);
-    const long rows = GH * N;
-    if (N == 512) softmax_rows_kernel<512><<<cdiv(rows, 8), 256, 0, st>>>(S, P, rows, W, local);
-    else if (N == 256) softmax_rows_kernel<256><<<cdiv(rows, 8), 256, 0, st>>>(S, P, rows, W, local);
-    else softmax_rows_kernel<128><<<cdiv(rows, 8), 256, 0, st>>>(S, P, rows, W, local);
-    MRNB_CHECK_LAUNCH("softmax_rows_kernel");
-  }
+  // P = softmax(scale Q K^T + Local mask): scores accumulate in TMEM and the row epilogue is fused (attn_train_tc.cu)
+  MRNB_TRY(mrnb_attn_scores_softmax(qkv, P, B, N, d, heads, W, local ? 1 : 0, ATT_SCALE, st));
   MrnbTcGemm2 o{};
   o.a = mrnb_operand_k2d(P, N, N, N, 128, GH);
   o.b = mrnb_operand_head(qkv + 2 * d, N, 3L * d, heads, B, 1, 64);
@@ -647,23 +593,11 @@ int attn_tc_forward(const bf16* qkv, float* S, bf16* P, bf16* att, int B, int N,
   return mrnb_tc_gemm2(o, st);
 }
 
-int attn_tc_backward(const bf16* qkv, const bf16* att, const float* dO, const bf16* dO16, const bf16* P, float* dP, bf16* dS,
+int attn_tc_backward(const bf16* qkv, const bf16* att, const float* dO, const bf16* dO16, const bf16* P, bf16* dS,
                      bf16* dqkv, int B, int N, int d, int heads, cudaStream_t st) {
   const long GH = (long)B * heads;
-  MrnbTcGemm2 g{};
-  g.a = mrnb_operand_head(dO16, N, d, heads, B, 0, 128);
-  g.b = mrnb_operand_head(qkv + 2 * d, N, 3L * d, heads, B, 0, 128);
-  g.out32 = dP; g.cm = mrnb_axis(N); g.cn = mrnb_axis(1); g.c_gstride = (long)N * N;
-  g.M = N; g.N = N; g.K = 64; g.groups = (int)GH; g.splitk = 1; g.alpha = 1.f;
-  MRNB_TRY(mrnb_tc_gemm2(g, st));
-  {
-    MrnbProfScope prof(MRNB_PROF_ATTN, st, 0.0, (double)GH * N * N * 8);
-    const long rows = GH * N;
-    if (N == 512) attn_ds_kernel<512><<<cdiv(rows, 8), 256, 0, st>>>(P, dP, dO, att, dS, rows, d, heads);
-    else if (N == 256) attn_ds_kernel<256><<<cdiv(rows, 8), 256, 0, st>>>(P, dP, dO, att, dS, rows, d, heads);
-    else attn_ds_kernel<128><<<cdiv(rows, 8), 256, 0, st>>>(P, dP, dO, att, dS, rows, d, heads);
-    MRNB_CHECK_LAUNCH("attn_ds_kernel");
-  }
+  // dS = P (dO V^T - dO.O): dP accumulates in TMEM, fused row epilogue
+  MRNB_TRY(mrnb_attn_dp_ds(dO16, qkv, dO, att, P, dS, B, N, d, heads, st));
   auto head_out = [&](MrnbTcGemm2& q, int col0, float alpha) {
     q.out16 = dqkv + col0; q.cm = mrnb_axis(3L * d); q.cn = mrnb_axis(1); q.g_inner = heads; q.c_gstride = (long)N * 3 * d;
     q.c_gstride2 = 32; q.M = N; q.N = 32; q.K = N; q.groups = (int)GH; q.splitk = 1; q.alpha = alpha;
@@ -701,7 +635,6 @@ struct TrainWs {
   float *dxa, *dy, *dbig, *dqkv, *datt, *dln, *Dbuf, *dfeat;
   bf16 *dy16, *dbig16, *dqkv16, *dfeat16, *dlog16, *datt16;   // bf16 mode: GEMM-operand copies of the gradients
   bf16 *P[12], *dS16;                                    // bf16 mode: attention probabilities (kept), dS scratch
-  float* S32;                                            // bf16 mode: attention scores / dP scratch
   size_t bytes;
 };
 
@@ -741,7 +674,6 @@ TrainWs<AT> carve_train_ws(char* base, int B, int n_class) {
     for (int s = 0; s < 3; ++s)
       for (int j = 0; j < DEPTH[s]; ++j, ++k) w.P[k] = W.take<bf16>((size_t)B * 32768 / DIMS[s] * (32768 / DIMS[s]) * HEADS[s]);
     w.dS16 = W.take<bf16>((size_t)B * 2 * 512 * 512);
-    w.S32 = W.take<float>((size_t)B * 2 * 512 * 512);
   }
   w.bytes = W.off + 4096;
   return w;
@@ -804,7 +736,7 @@ int train_forward_t(const MrnbSvtrPack& P, const float* image, int B, int bn_bat
       MRNB_TRY(lin<AT>(w.ln1[blk], d, P.p[pb + MRNB_PB_QKV_W], P.h[pb + MRNB_PB_QKV_W], P.p[pb + MRNB_PB_QKV_B], w.qkv[blk],
                        3 * d, false, rows, 3 * d, d, nullptr, nullptr, 1, st));
       if constexpr (sizeof(AT) == 2)
-        MRNB_TRY(attn_tc_forward(w.qkv[blk], w.S32, w.P[blk], w.att[blk], B, N, d, heads, Wd, blk < 6, st));
+        MRNB_TRY(attn_tc_forward(w.qkv[blk], w.P[blk], w.att[blk], B, N, d, heads, Wd, blk < 6, st));
       else
         MRNB_TRY(attention_train_fwd<AT>(w.qkv[blk], w.att[blk], w.lse[blk], B, N, d, heads, H, Wd, blk < 6, st));
       MRNB_TRY(lin<AT>(w.att[blk], d, P.p[pb + MRNB_PB_PROJ_W], P.h[pb + MRNB_PB_PROJ_W], P.p[pb + MRNB_PB_PROJ_B],
@@ -929,7 +861,7 @@ int train_backward_t(const MrnbSvtrPack& P, const MrnbSvtrPack& G, const float* 
       MRNB_TRY(gemm_dx<AT>(gy, P.p[pb + MRNB_PB_PROJ_W], P.h[pb + MRNB_PB_PROJ_W], w.datt, w.datt16, d, rows, d, d, st));
       Grad gq{w.dqkv, w.dqkv16, 3L * d};
       if constexpr (TC) {
-        MRNB_TRY(attn_tc_backward(w.qkv[blk], w.att[blk], w.datt, w.datt16, w.P[blk], w.S32, w.dS16, w.dqkv16, B, N, d, heads, st));
+        MRNB_TRY(attn_tc_backward(w.qkv[blk], w.att[blk], w.datt, w.datt16, w.P[blk], w.dS16, w.dqkv16, B, N, d, heads, st));
         MRNB_TRY(launch_colsum<bf16>(w.dqkv16, 3 * d, rows, 3 * d, gp(G, pb + MRNB_PB_QKV_B), st));
       } else {
         MRNB_TRY((attention_train_bwd<AT, float>(w.qkv[blk], w.att[blk], w.datt, w.lse[blk], w.Dbuf, w.dqkv, B, N, d, heads,
