@@ -93,6 +93,9 @@ constexpr int EPI_WARPS = 16, NTHREADS = 64 + EPI_WARPS * 32;
 
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
 
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// MODE 0: forward, all keys visible.  MODE 2: forward, Local window.  MODE 1: backward (dP -> dS).
 template <int N, int MODE>
 __global__ void __launch_bounds__(NTHREADS)
 attn_sp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SpArgs a) {
@@ -176,12 +179,14 @@ attn_sp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tmem_full_bar, it & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-      if (MODE == 0) {
+      if (MODE != 1) {
+        constexpr bool LOCAL = MODE == 2;
+        const float sc2 = a.scale * 1.4426950408889634f;            // exp(scale x - m) = 2^(sc2 x - m2)
         const int wmask = (1 << a.wshift) - 1;
         const int nh = n >> a.wshift, nw = n & wmask;
         // visibility of the 32 keys of chunk c0 as a bit mask (a chunk lies inside one row of the key grid: W >= 32)
         auto chunk_mask = [&](int c0) -> uint32_t {
-          if (!a.local) return 0xffffffffu;
+          if (!LOCAL) return 0xffffffffu;
           const int dh = (c0 >> a.wshift) - nh;
           if (dh < -3 || dh > 3) return 0u;
           const int base = c0 & wmask;
@@ -197,11 +202,11 @@ attn_sp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t vm = chunk_mask(c0);
           if (vm == 0u) continue;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if ((vm >> j) & 1u) mx = fmaxf(mx, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; ++j) if (!LOCAL || ((vm >> j) & 1u)) mx = fmaxf(mx, __uint_as_float(r[j]));
         }
         red_max[cg][rr] = mx;
         epi_sync();
-        mx = fmaxf(fmaxf(red_max[0][rr], red_max[1][rr]), fmaxf(red_max[2][rr], red_max[3][rr])) * a.scale;
+        mx = fmaxf(fmaxf(red_max[0][rr], red_max[1][rr]), fmaxf(red_max[2][rr], red_max[3][rr])) * sc2;
         float sum = 0.f;
 #pragma unroll 1
         for (int c0 = cg * CW; c0 < (cg + 1) * CW; c0 += 32) {
@@ -210,7 +215,7 @@ attn_sp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t vm = chunk_mask(c0);
           if (vm == 0u) continue;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if ((vm >> j) & 1u) sum += __expf(fmaf(__uint_as_float(r[j]), a.scale, -mx));
+          for (int j = 0; j < 32; ++j) if (!LOCAL || ((vm >> j) & 1u)) sum += ex2f(fmaf(__uint_as_float(r[j]), sc2, -mx));
         }
         red_sum[cg][rr] = sum;
         epi_sync();
@@ -229,8 +234,8 @@ attn_sp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            const float p0 = ((vm >> j) & 1u) ? __expf(fmaf(__uint_as_float(r[j]), a.scale, -mx)) * inv : 0.f;
-            const float p1 = ((vm >> (j + 1)) & 1u) ? __expf(fmaf(__uint_as_float(r[j + 1]), a.scale, -mx)) * inv : 0.f;
+            const float p0 = (!LOCAL || ((vm >> j) & 1u)) ? ex2f(fmaf(__uint_as_float(r[j]), sc2, -mx)) * inv : 0.f;
+            const float p1 = (!LOCAL || ((vm >> (j + 1)) & 1u)) ? ex2f(fmaf(__uint_as_float(r[j + 1]), sc2, -mx)) * inv : 0.f;
             __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
             pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
           }
@@ -347,6 +352,11 @@ int mrnb_attn_scores_softmax(const void* qkv, void* P, int B, int N, int d, int 
   a.P = (bf16*)P; a.heads = heads; a.d = d; a.wshift = ws; a.local = local; a.scale = scale;
   a.items = (long)B * heads * (N / BM);
   MrnbProfScope prof(MRNB_PROF_ATTN, st, 2.0 * 2 * 32 * (double)N * N * B * heads / 2, (double)B * heads * N * N * 2);
+  if (local) {
+    if (N == 512) return launch_sp<512, 2>(tmA, tmB, a, st);
+    if (N == 256) return launch_sp<256, 2>(tmA, tmB, a, st);
+    return launch_sp<128, 2>(tmA, tmB, a, st);
+  }
   if (N == 512) return launch_sp<512, 0>(tmA, tmB, a, st);
   if (N == 256) return launch_sp<256, 0>(tmA, tmB, a, st);
   return launch_sp<128, 0>(tmA, tmB, a, st);
