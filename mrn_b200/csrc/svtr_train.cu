@@ -155,7 +155,8 @@ bn_bwd_reduce_kernel(const float* __restrict__ raw, float* __restrict__ d, const
 // dgamma = S2, dbeta = S1
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ raw, float* __restrict__ d, const float* __restrict__ ss,
                                     const float* __restrict__ mr, const double* __restrict__ sums, double count,
-                                    int use_batch, float* __restrict__ dgamma, float* __restrict__ dbeta, int C, long total) {
+                                    int use_batch, float* __restrict__ dgamma, float* __restrict__ dbeta, int C, long total,
+                                    __nv_bfloat16* __restrict__ d16 = nullptr) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < C) { dgamma[i] = (float)sums[i * 2 + 1]; dbeta[i] = (float)sums[i * 2]; }
   if (i >= total) return;
@@ -167,6 +168,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ raw, float* __rest
     dz = dz - (float)(sums[c * 2] / count) - xh * (float)(sums[c * 2 + 1] / count);
   }
   d[i] = sc * dz;
+  if (d16) d16[i] = __float2bfloat16_rn(sc * dz);
 }
 
 // dpos[n,c] = sum_b dx[b,n,c]
@@ -711,11 +713,24 @@ int train_forward_t(const MrnbSvtrPack& P, const float* image, int B, int bn_bat
     bn_gelu_kernel<<<cdiv(t4, 256), 256, 0, st>>>(w.raw0, w.ss, nullptr, 1, w.act0, 32, t4);
     MRNB_CHECK_LAUNCH("bn_gelu_kernel");
     const long c4 = (long)B * 512 * 288 / 4;
-    im2col_nhwc_kernel<float><<<cdiv(c4, 256), 256, 0, st>>>(w.act0, w.colf, 16, 128, 32, 8, 64, 2, 2, c4);
-    MRNB_CHECK_LAUNCH("im2col_nhwc_kernel");
-    MrnbGemm g1 = mrnb_gemm_nt(w.colf, 288, P.p[MRNB_P_CONV1_W], 288, w.raw1, 64, B * 512, 64, 288);
-    g1.bias_n = P.p[MRNB_P_CONV1_B];
-    MRNB_TRY(mrnb_sgemm(g1, st));
+    if constexpr (sizeof(AT) == 2) {
+      // conv1 (K = 288) on the tensor cores: bf16 im2col, the contraction rounded up to 320 (TMA zero-fills both operands)
+      MRNB_CHECK_ARG(P.h[MRNB_P_CONV1_W], "svtr_train: bf16 mode needs the 16-bit weight shadow");
+      im2col_nhwc_kernel<AT><<<cdiv(c4, 256), 256, 0, st>>>(w.act0, w.big, 16, 128, 32, 8, 64, 2, 2, c4);
+      MRNB_CHECK_LAUNCH("im2col_nhwc_kernel");
+      MrnbTcGemm2 g1{};
+      g1.a = mrnb_operand_k2d(w.big, (long)B * 512, 288, 288, 128, 1);
+      g1.b = mrnb_operand_k2d(P.h[MRNB_P_CONV1_W], 64, 288, 288, 64, 1);
+      g1.out32 = w.raw1; g1.cm = mrnb_axis(64); g1.cn = mrnb_axis(1); g1.bias_n = P.p[MRNB_P_CONV1_B];
+      g1.M = B * 512; g1.N = 64; g1.K = 320; g1.groups = 1; g1.splitk = 1; g1.alpha = 1.f;
+      MRNB_TRY(mrnb_tc_gemm2(g1, st));
+    } else {
+      im2col_nhwc_kernel<float><<<cdiv(c4, 256), 256, 0, st>>>(w.act0, w.colf, 16, 128, 32, 8, 64, 2, 2, c4);
+      MRNB_CHECK_LAUNCH("im2col_nhwc_kernel");
+      MrnbGemm g1 = mrnb_gemm_nt(w.colf, 288, P.p[MRNB_P_CONV1_W], 288, w.raw1, 64, B * 512, 64, 288);
+      g1.bias_n = P.p[MRNB_P_CONV1_B];
+      MRNB_TRY(mrnb_sgemm(g1, st));
+    }
     if (bn_batch) MRNB_TRY(launch_colstats(w.raw1, (long)B * 512, 64, w.stats + 64, st));
     bn_finalize_train_kernel<<<1, 64, 0, st>>>(w.stats + 64, P.p[MRNB_P_BN1_W], P.p[MRNB_P_BN1_B],
                                                (float*)P.p[MRNB_P_BN1_MEAN], (float*)P.p[MRNB_P_BN1_VAR], w.ss + 64,
@@ -892,14 +907,21 @@ int train_backward_t(const MrnbSvtrPack& P, const MrnbSvtrPack& G, const float* 
     bn_bwd_reduce_kernel<<<dim3(2, chunks), dim3(32, 8), 0, st>>>(w.raw1, dx, w.ss + 64, w.mr + 64, r1, 64, w.bsums + 64);
     MRNB_CHECK_LAUNCH("bn_bwd_reduce_kernel");
     bn_bwd_apply_kernel<<<cdiv(u, 256), 256, 0, st>>>(w.raw1, dx, w.ss + 64, w.mr + 64, w.bsums + 64, (double)r1, bn_batch,
-                                                      gp(G, MRNB_P_BN1_W), gp(G, MRNB_P_BN1_B), 64, u);
+                                                      gp(G, MRNB_P_BN1_W), gp(G, MRNB_P_BN1_B), 64, u, TC ? w.dy16 : nullptr);
     MRNB_CHECK_LAUNCH("bn_bwd_apply_kernel");
     MRNB_TRY(launch_colsum<float>(dx, 64, r1, 64, gp(G, MRNB_P_CONV1_B), st));
     const long c4 = r1 * 288 / 4;
-    im2col_nhwc_kernel<float><<<cdiv(c4, 256), 256, 0, st>>>(w.act0, w.colf, 16, 128, 32, 8, 64, 2, 2, c4);
-    MRNB_CHECK_LAUNCH("im2col_nhwc_kernel");
-    MRNB_TRY(gemm_dw_f32(dx, 64, w.colf, 288, gp(G, MRNB_P_CONV1_W), (int)r1, 64, 288, st));
-    MRNB_TRY(gemm_dx_f32(dx, 64, P.p[MRNB_P_CONV1_W], w.dbig, 288, (int)r1, 64, 288, st));
+    if constexpr (TC) {
+      im2col_nhwc_kernel<AT><<<cdiv(c4, 256), 256, 0, st>>>(w.act0, w.big, 16, 128, 32, 8, 64, 2, 2, c4);
+      MRNB_CHECK_LAUNCH("im2col_nhwc_kernel");
+      MRNB_TRY(gemm_dw_tc(w.dy16, 64, w.big, 288, gp(G, MRNB_P_CONV1_W), (int)r1, 64, 288, st));
+      MRNB_TRY(gemm_dx_tc(w.dy16, 64, P.h[MRNB_P_CONV1_W], w.dbig, nullptr, 288, (int)r1, 64, 288, st));
+    } else {
+      im2col_nhwc_kernel<float><<<cdiv(c4, 256), 256, 0, st>>>(w.act0, w.colf, 16, 128, 32, 8, 64, 2, 2, c4);
+      MRNB_CHECK_LAUNCH("im2col_nhwc_kernel");
+      MRNB_TRY(gemm_dw_f32(dx, 64, w.colf, 288, gp(G, MRNB_P_CONV1_W), (int)r1, 64, 288, st));
+      MRNB_TRY(gemm_dx_f32(dx, 64, P.p[MRNB_P_CONV1_W], w.dbig, 288, (int)r1, 64, 288, st));
+    }
     float* dact0 = w.dy;                                   // [B,16,128,32]
     const long n0 = (long)B * 2048 * 32;
     col2im_nhwc_kernel<<<cdiv(n0 / 4, 256), 256, 0, st>>>(w.dbig, dact0, 16, 128, 32, 8, 64, 2, 2, n0 / 4);
