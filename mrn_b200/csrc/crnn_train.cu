@@ -219,7 +219,8 @@ __global__ void lstm_cell_fwd_kernel(float* __restrict__ G, float* __restrict__ 
 // BPTT step s (direction 0 at t = 62 - s, direction 1 at t = s): dh = drec[t] + dh_next; writes the gate
 // pre-activation gradients over the activated gates in G and carries dc.
 __global__ void lstm_cell_bwd_kernel(float* __restrict__ G, const float* __restrict__ c, const float* __restrict__ drec,
-                                     const float* __restrict__ dhn, float* __restrict__ dcn, int B, int s) {
+                                     const float* __restrict__ dhn, float* __restrict__ dcn, int B, int s,
+                                     bf16* __restrict__ G16) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * B * HID) return;
   const int j = i % HID, b = (i / HID) % B, dir = i / (HID * B);
@@ -233,10 +234,14 @@ __global__ void lstm_cell_bwd_kernel(float* __restrict__ G, const float* __restr
   const float dh = drec[o] + (s > 0 ? dhn[i] : 0.f);
   const float tc = tanhf(ct);
   const float dc = dh * go * (1.f - tc * tc) + (s > 0 ? dcn[i] : 0.f);
-  g[0] = dc * gg * gi * (1.f - gi);
-  g[HID] = dc * cp * gf * (1.f - gf);
-  g[2 * HID] = dc * gi * (1.f - gg * gg);
-  g[3 * HID] = dh * tc * go * (1.f - go);
+  const float ai = dc * gg * gi * (1.f - gi), af = dc * cp * gf * (1.f - gf), ag = dc * gi * (1.f - gg * gg),
+              ao = dh * tc * go * (1.f - go);
+  g[0] = ai; g[HID] = af; g[2 * HID] = ag; g[3 * HID] = ao;
+  if (G16) {
+    bf16* h = G16 + ((long)b * T63 + t) * 2048 + dir * 1024 + j;
+    h[0] = __float2bfloat16_rn(ai); h[HID] = __float2bfloat16_rn(af); h[2 * HID] = __float2bfloat16_rn(ag);
+    h[3 * HID] = __float2bfloat16_rn(ao);
+  }
   dcn[i] = dc * gf;
 }
 
@@ -394,13 +399,28 @@ int crnn_train_forward_t(const MrnbCrnnTrainPack& P, const float* image, int B, 
     cudaMemsetAsync(w.hseq[k], 0, (size_t)M * 512 * sizeof(AT), st);
     for (int s = 0; s < T63; ++s) {
       if (s > 0) {
-        // G[:, t_dir, dir] += h_prev[dir] W_hh[dir]^T   (both directions: batch = 2, fp32)
         const int tf = s, tr = T63 - 1 - s;
-        MrnbGemm g = mrnb_gemm_nt(w.rec[k] + (long)(tf - 1) * 512, (long)T63 * 512, P.p[s0 + MRNB_TL_WHH], HID,
-                                  w.G[k] + (long)tf * 2048, (long)T63 * 2048, B, 1024, HID);
-        g.batch = 2; g.sAb = HID + (long)((tr + 1) - (tf - 1)) * 512; g.sBb = 1024L * HID;
-        g.sCb = 1024 + (long)(tr - tf) * 2048; g.accumulate = 1;
-        MRNB_TRY(mrnb_sgemm(g, st));
+        if constexpr (TC) {
+          // G[:, t_dir, dir] += h_prev[dir] W_hh[dir]^T on the tensor cores: h_prev is the bf16 hidden sequence the
+          // previous cell wrote at this position; the accumulate is the epilogue's residual at the output address
+          const int tpos[2] = {tf, tr};
+          for (int dir = 0; dir < 2; ++dir) {
+            MrnbTcGemm2 g{};
+            g.a = mrnb_operand_k2d(w.hseq[k] + (long)tpos[dir] * 512 + dir * HID, B, HID, (long)T63 * 512, 128, 1);
+            g.b = mrnb_operand_k2d((const bf16*)P.h[s0 + MRNB_TL_WHH] + (long)dir * 1024 * HID, 1024, HID, HID, 128, 1);
+            float* c = w.G[k] + (long)tpos[dir] * 2048 + dir * 1024;
+            g.out32 = c; g.res = c; g.cm = mrnb_axis((long)T63 * 2048); g.cn = mrnb_axis(1);
+            g.M = B; g.N = 1024; g.K = HID; g.groups = 1; g.splitk = 1; g.alpha = 1.f;
+            MRNB_TRY(mrnb_tc_gemm2(g, st));
+          }
+        } else {
+          // both directions in one fp32 launch (batch = 2)
+          MrnbGemm g = mrnb_gemm_nt(w.rec[k] + (long)(tf - 1) * 512, (long)T63 * 512, P.p[s0 + MRNB_TL_WHH], HID,
+                                    w.G[k] + (long)tf * 2048, (long)T63 * 2048, B, 1024, HID);
+          g.batch = 2; g.sAb = HID + (long)((tr + 1) - (tf - 1)) * 512; g.sBb = 1024L * HID;
+          g.sCb = 1024 + (long)(tr - tf) * 2048; g.accumulate = 1;
+          MRNB_TRY(mrnb_sgemm(g, st));
+        }
       }
       lstm_cell_fwd_kernel<AT><<<cdiv(2 * B * HID, 256), 256, 0, st>>>(w.G[k], w.c[k], w.rec[k], w.hseq[k], B, s);
       MRNB_CHECK_LAUNCH("lstm_cell_fwd_kernel");
@@ -461,26 +481,33 @@ int crnn_train_backward_t(const MrnbCrnnTrainPack& P, const MrnbCrnnTrainPack& G
         // dh_next[dir] = dgates[:, t_prev_processed, dir] . W_hh[dir]      (fp32; one split-K launch per direction so that
         // the [B,256] x K = 1024 product spreads over the SMs)
         const int tpos[2] = {T63 - s, s - 1};         // positions processed at step s - 1
-        cudaMemsetAsync(w.dhn, 0, (size_t)2 * B * HID * sizeof(float), st);
-        for (int dir = 0; dir < 2; ++dir) {
-          MrnbGemm g{};
-          g.A = w.G[k] + (long)tpos[dir] * 2048 + dir * 1024; g.am = mrnb_axis((long)T63 * 2048); g.ak = mrnb_axis(1); g.a_kfast = 1;
-          g.B = P.p[s0 + MRNB_TL_WHH] + (long)dir * 1024 * HID; g.bk = mrnb_axis(HID); g.bn = mrnb_axis(1); g.b_kfast = 0;
-          g.C = w.dhn + (long)dir * B * HID; g.cm = mrnb_axis(HID); g.cn = mrnb_axis(1);
-          g.M = B; g.N = HID; g.K = 1024; g.batch = 1; g.splitk = 8; g.alpha = 1.f; g.rows_per_scale = 1;
-          MRNB_TRY(mrnb_sgemm(g, st));
+        if constexpr (TC) {
+          for (int dir = 0; dir < 2; ++dir) {          // bf16 gate gradients (written by the cell kernel) x W_hh read MN-major
+            MrnbTcGemm2 g{};
+            g.a = mrnb_operand_k2d(w.dG16 + (long)tpos[dir] * 2048 + dir * 1024, B, 1024, (long)T63 * 2048, 128, 1);
+            g.b = mrnb_operand_mn2d((const bf16*)P.h[s0 + MRNB_TL_WHH] + (long)dir * 1024 * HID, HID, 1024, HID, 1);
+            g.out32 = w.dhn + (long)dir * B * HID; g.cm = mrnb_axis(HID); g.cn = mrnb_axis(1);
+            g.M = B; g.N = HID; g.K = 1024; g.groups = 1; g.splitk = 1; g.alpha = 1.f;
+            MRNB_TRY(mrnb_tc_gemm2(g, st));
+          }
+        } else {
+          cudaMemsetAsync(w.dhn, 0, (size_t)2 * B * HID * sizeof(float), st);
+          for (int dir = 0; dir < 2; ++dir) {
+            MrnbGemm g{};
+            g.A = w.G[k] + (long)tpos[dir] * 2048 + dir * 1024; g.am = mrnb_axis((long)T63 * 2048); g.ak = mrnb_axis(1); g.a_kfast = 1;
+            g.B = P.p[s0 + MRNB_TL_WHH] + (long)dir * 1024 * HID; g.bk = mrnb_axis(HID); g.bn = mrnb_axis(1); g.b_kfast = 0;
+            g.C = w.dhn + (long)dir * B * HID; g.cm = mrnb_axis(HID); g.cn = mrnb_axis(1);
+            g.M = B; g.N = HID; g.K = 1024; g.batch = 1; g.splitk = 8; g.alpha = 1.f; g.rows_per_scale = 1;
+            MRNB_TRY(mrnb_sgemm(g, st));
+          }
         }
       }
-      lstm_cell_bwd_kernel<<<cdiv(2 * B * HID, 256), 256, 0, st>>>(w.G[k], w.c[k], w.drec, w.dhn, w.dcn, B, s);
+      lstm_cell_bwd_kernel<<<cdiv(2 * B * HID, 256), 256, 0, st>>>(w.G[k], w.c[k], w.drec, w.dhn, w.dcn, B, s, TC ? w.dG16 : nullptr);
       MRNB_CHECK_LAUNCH("lstm_cell_bwd_kernel");
     }
     // G now holds d(gate pre-activations) [M, 2048] for both directions
     Grad gG{w.G[k], nullptr, 2048};
-    if (TC) {
-      cast_to_kernel<bf16><<<cdiv((long)M * 2048, 256), 256, 0, st>>>(w.G[k], w.dG16, (long)M * 2048);
-      MRNB_CHECK_LAUNCH("cast_to_kernel");
-      gG.h = w.dG16;
-    }
+    if (TC) gG.h = w.dG16;                     // written step by step by the cell kernel
     MRNB_TRY(launch_colsum<float>(w.G[k], 2048, M, 2048, gpt(G, s0 + MRNB_TL_BIH), st));
     cudaMemcpyAsync(gpt(G, s0 + MRNB_TL_BHH), gpt(G, s0 + MRNB_TL_BIH), 2048 * sizeof(float), cudaMemcpyDeviceToDevice, st);
     const AT* xin = k == 0 ? (TC ? w.vis16 : reinterpret_cast<const AT*>(w.act[6])) : w.out16[0];
