@@ -295,3 +295,32 @@ def test_stage0_cuda_graph_replay_matches_eager(arch):
     assert np.allclose(l0[:2], l1[:2], rtol=1e-5) and np.allclose(l0, l1, rtol=1e-3), (l0, l1)
     d = (p0 - p1).abs()
     assert float(d.max()) <= 5e-4 * 4.01 and float((d > 5e-5).float().mean()) < 2e-2
+
+
+@pytest.mark.parametrize("arch,precision", [("svtr", "fp32"), ("svtr", "bf16"), ("crnn", "fp32")])
+def test_stage0_training_reduces_the_loss_on_a_fixed_batch(arch, precision):
+    """Sixty expert-training iterations on one batch (constant learning rate): the CTC loss must fall well below its
+    starting value -- gradients, clip + Adam and the arena write-back work together."""
+    from mrn_b200.il_modules.mrn import MRN, RankLocal
+    cc, B = (40,), 8
+    sd = synth.synth_state_dict(cc, 21, arch=arch)
+    img, tgt, lens, _ = synth.synth_batch(B, cc, 77)
+    lens = lens.clamp(max=8); tgt[:, 8:] = 1
+    opt = make_opt(precision)
+    opt.drop_path, opt.num_iter, opt.schedule, opt.lr = False, 1000, "const", 5e-4
+    if arch == "crnn":
+        opt.FeatureExtraction, opt.SequenceModeling = "VGG", "BiLSTM"
+    learner = MRN(opt)
+    learner.model.update_fc(opt.hidden_size, cc[0]); learner.model.build_prediction(opt, cc[0])
+    learner.model.load_state_dict(sd, strict=True)
+    learner.model = RankLocal(learner.net).cuda()
+    learner.model.train()
+    learner.begin_expert_training()
+    x, t, l = img.cuda(), tgt.cuda(), lens.cuda()
+    losses = [float(learner.train_step_stage0(x, t, l)) for _ in range(60)]
+    print(arch, precision, [round(v, 2) for v in losses[::5]])
+    assert all(np.isfinite(losses)), losses
+    assert np.mean(losses[-10:]) < 0.8 * losses[0], (losses[0], losses[-10:])
+    learner.end_expert_training()
+    out = learner.net(x, cross=False, is_train=False)          # the inference path sees the trained weights
+    assert torch.isfinite(out["logits"]).all()
