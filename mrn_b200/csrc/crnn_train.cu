@@ -48,8 +48,12 @@ __global__ void im2col_s1_kernel(const float* __restrict__ x, OT* __restrict__ c
   const int ih = oh - pad + tap / KW, iw = ow - pad + tap % KW;
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = *reinterpret_cast<const float4*>(x + ((b * H + ih) * W + iw) * C + c);
-  OT* o = col + i * 4;
-  o[0] = from_f32<OT>(v.x); o[1] = from_f32<OT>(v.y); o[2] = from_f32<OT>(v.z); o[3] = from_f32<OT>(v.w);
+  if constexpr (sizeof(OT) == 4) {
+    *reinterpret_cast<float4*>(col + i * 4) = v;
+  } else {                                        // four bf16 values = one 8-byte store
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(col + i * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+  }
 }
 
 // transpose: dx[b,ih,iw,c] = sum over taps of dcol[(b, ih + pad - kh, iw + pad - kw), (kh,kw,c)]
@@ -482,12 +486,13 @@ int crnn_train_backward_t(const MrnbCrnnTrainPack& P, const MrnbCrnnTrainPack& G
         // the [B,256] x K = 1024 product spreads over the SMs)
         const int tpos[2] = {T63 - s, s - 1};         // positions processed at step s - 1
         if constexpr (TC) {
-          for (int dir = 0; dir < 2; ++dir) {          // bf16 gate gradients (written by the cell kernel) x W_hh read MN-major
-            MrnbTcGemm2 g{};
+          cudaMemsetAsync(w.dhn, 0, (size_t)2 * B * HID * sizeof(float), st);
+          for (int dir = 0; dir < 2; ++dir) {          // bf16 gate gradients (written by the cell kernel) x W_hh read MN-major;
+            MrnbTcGemm2 g{};                           // K = 1024 split 8 ways so that 32 CTAs share the 16 k-blocks
             g.a = mrnb_operand_k2d(w.dG16 + (long)tpos[dir] * 2048 + dir * 1024, B, 1024, (long)T63 * 2048, 128, 1);
             g.b = mrnb_operand_mn2d((const bf16*)P.h[s0 + MRNB_TL_WHH] + (long)dir * 1024 * HID, HID, 1024, HID, 1);
             g.out32 = w.dhn + (long)dir * B * HID; g.cm = mrnb_axis(HID); g.cn = mrnb_axis(1);
-            g.M = B; g.N = HID; g.K = 1024; g.groups = 1; g.splitk = 1; g.alpha = 1.f;
+            g.M = B; g.N = HID; g.K = 1024; g.groups = 1; g.splitk = 8; g.alpha = 1.f;
             MRNB_TRY(mrnb_tc_gemm2(g, st));
           }
         } else {

@@ -67,8 +67,12 @@ __global__ void im2col_nhwc_kernel(const float* __restrict__ x, OT* __restrict__
   const int ih = oh * sh - 1 + tap / 3, iw = ow * sw - 1 + tap % 3;
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = *reinterpret_cast<const float4*>(x + ((b * H + ih) * W + iw) * C + c);
-  OT* o = col + i * 4;
-  o[0] = from_f32<OT>(v.x); o[1] = from_f32<OT>(v.y); o[2] = from_f32<OT>(v.z); o[3] = from_f32<OT>(v.w);
+  if constexpr (sizeof(OT) == 4) {
+    *reinterpret_cast<float4*>(col + i * 4) = v;
+  } else {                                        // four bf16 values = one 8-byte store
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(col + i * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+  }
 }
 
 // transpose of the above: dx[b,ih,iw,c] = sum over the (oh,ow,tap) that read this pixel of dcol
