@@ -230,7 +230,7 @@ typedef struct MrnbCrnnTrainPack {
 } MrnbCrnnTrainPack;
 
 size_t mrnb_crnn_train_workspace_bytes(int B, int n_class, int prec);
-/* logits / dlogits: [B,63,ld] fp32.  MRNB_PREC_BF16 needs B % 64 == 0 (GEMM contraction over B*63 rows). */
+/* logits / dlogits: [B,63,ld] fp32. */
 int mrnb_crnn_train_forward(const MrnbCrnnTrainPack* pack, const float* image, int B, int prec, int bn_batch_stats,
                             int update_running, float* logits, long ld_logits, void* workspace, size_t workspace_bytes,
                             cudaStream_t stream);

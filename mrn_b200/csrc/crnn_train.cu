@@ -333,7 +333,6 @@ int crnn_train_forward_t(const MrnbCrnnTrainPack& P, const float* image, int B, 
   constexpr bool TC = sizeof(AT) == 2;
   CrnnWs<AT> w = carve_crnn_ws<AT>((char*)ws, B, P.n_class);
   MRNB_CHECK_ARG(ws_bytes >= w.bytes, "crnn_train_forward: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
-  MRNB_CHECK_ARG(!TC || (B * T63) % 64 == 0, "crnn_train: the bf16 mode needs B * 63 to be a multiple of 64 (B %% 64 == 0)");
   {
     const long px = (long)B * 32 * 256;
     nchw_to_nhwc4_kernel<<<cdiv(px, 256), 256, 0, st>>>(image, w.img4, 32 * 256, px);

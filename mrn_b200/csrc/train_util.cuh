@@ -137,12 +137,12 @@ int gemm_dx_tc(const bf16* dY, long ldy, const void* W16, float* dX, bf16* dX16,
   return mrnb_tc_gemm2(g, st);
 }
 int gemm_dw_tc(const bf16* dY, long ldy, const bf16* X, long ldx, float* dW, int rows, int N, int K, cudaStream_t st) {
-  MRNB_CHECK_ARG(rows % 64 == 0, "svtr_train: dW contraction length %d must be a multiple of 64", rows);
+  // a contraction length (rows) that is not a multiple of 64 is rounded up: both MN-major operands are zero-filled by TMA
   MrnbTcGemm2 g{};
   g.a = mrnb_operand_mn2d(dY, N, rows, ldy, 1);
   g.b = mrnb_operand_mn2d(X, K, rows, ldx, 1);
   g.out32 = dW; g.cm = mrnb_axis(K); g.cn = mrnb_axis(1);
-  g.M = N; g.N = K; g.K = rows; g.groups = 1; g.alpha = 1.f;
+  g.M = N; g.N = K; g.K = (rows + 63) / 64 * 64; g.groups = 1; g.alpha = 1.f;
   const long tiles = (long)cdiv(N, 128) * cdiv(K, K >= 128 ? 128 : 64);
   long sk = (148L * 3 + tiles - 1) / tiles;
   const long maxsk = rows / 256 > 0 ? rows / 256 : 1;

@@ -98,6 +98,25 @@ def test_stage0_clip_and_adam_step_matches_reference_golden(name):
         assert d.max() <= 5e-4 * 2.01 and (d > 2e-5).sum() <= max(2, 0.02 * d.size), key
 
 
+@pytest.mark.parametrize("name", STAGE0_CRNN_CASES)
+def test_crnn_stage0_bf16_mode_runs_at_ragged_batch_sizes(name):
+    """CRNN bf16 mode at B = 2 / 3 (B * 63 rows is not a multiple of the 64-wide contraction block: TMA zero-fill pads
+    it): loss within 2e-2 of the reference, head / LSTM gradients within 5e-2, total norm within 5e-2."""
+    g, cc, sd, tp, logits, c, bn_train, pre = _run_step(name, prec=1)
+    assert abs(float(c["loss"]) - float(g["loss"])) / abs(float(g["loss"])) < 2e-2
+    tn = float(g["grad_total_norm"])
+    total = 0.0
+    for key, gg in tp.state(tp.grads).items():
+        total += float((gg.double() ** 2).sum())
+        if "ConvNet" in key:
+            continue
+        ref = g["grad." + pre + key]
+        diff = np.linalg.norm(pview(gg.contiguous().cpu(), g) - ref)
+        scale = max(np.linalg.norm(ref), 2e-3 * tn * (ref.size / max(gg.numel(), 1)) ** 0.5)
+        assert diff / scale < 5e-2, (key, diff / scale)
+    assert abs(total ** 0.5 - tn) / tn < 5e-2
+
+
 @pytest.mark.parametrize("name", STAGE0_CASES)
 def test_stage0_bf16_tensor_core_mode_within_budget(name):
     """MRNB_PREC_BF16: every GEMM of the expert forward and backward on tcgen05 (bf16 operands, fp32 accumulation).
@@ -226,7 +245,7 @@ def test_learner_init_train_follows_the_oracle_for_three_iterations(tmp_path, mo
 
 def test_crnn_stage0_bf16_tensor_core_mode_tracks_fp32_mode_at_batch_64():
     """CRNN expert training in MRNB_PREC_BF16 (every conv / Linear / LSTM input-projection GEMM and its gradients on
-    tcgen05; B * 63 must be a multiple of 64) against the fp32 parity mode on the same batch: loss within 2e-2; the
+    tcgen05) against the fp32 parity mode on the same batch: loss within 2e-2; the
     gradients of the CTC head and both BidirectionalLSTMs within 3e-2 in relative Frobenius norm.  Through the seven
     ReLU convolution layers below them the bf16 operand rounding compounds on these random-init weights (measured
     2 % at ConvNet.18 growing to 19 % at ConvNet.0, while the bf16 forward moves the logits by 1.3 %): those tensors
