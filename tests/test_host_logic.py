@@ -130,3 +130,53 @@ def test_no_cpu_fallback_and_unsupported_configs_fail_loudly():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="CUDA"):
             MRN(opt)
+
+
+# ---- stage-0 training arenas, driver glue (host logic only) ---------------------------------------------------------
+@pytest.mark.parametrize("arch", ["svtr", "crnn"])
+def test_train_pack_arena_round_trips_the_expert_state_dict(arch):
+    """ops.SvtrTrainPack / CrnnTrainPack: every trainable tensor of the expert lands in the flat arena exactly once (conv
+    weights permuted to [Cout,kh,kw,Cin], LSTM directions adjacent) and state() returns the reference layout again."""
+    import torch
+    from mrn_b200 import ops
+    from oracle import mrn_oracle as O
+    from oracle import synth
+    sd = synth.synth_state_dict((33,), 3, arch=arch)
+    esd = {k[len("model.0."):]: v for k, v in sd.items() if k.startswith("model.0.")}
+    cls = ops.SvtrTrainPack if arch == "svtr" else ops.CrnnTrainPack
+    tp = cls(esd, "cpu")
+    keys = [k[len("model.0."):] for k in O.expert_param_keys(sd, 0)]
+    back = tp.state()
+    assert sorted(back) == sorted(keys)                      # exactly the tensors that receive a gradient in stage 0
+    for k in keys:
+        assert torch.equal(back[k], esd[k]), k
+    n_params = sum(esd[k].numel() for k in keys)
+    assert n_params <= tp.numel <= n_params + 8 * len(tp.entries)      # slots padded to 8 floats
+    offs = sorted((e[3], e[3] + int(torch.tensor(e[4]).prod())) for e in tp.entries)
+    assert all(a1 <= b0 for (a0, a1), (b0, b1) in zip(offs, offs[1:]))       # no overlap
+    # gradient arena shares the layout: a write through the view shows up under the reference key
+    tp.grads.zero_()
+    tp.view(tp.grads, tp.entries[1]).fill_(2.0)
+    g = tp.state(tp.grads)
+    assert float(g[tp.entries[1][1]].sum()) == 2.0 * g[tp.entries[1][1]].numel()
+    assert sum(float(v.abs().sum()) for k, v in g.items() if k != tp.entries[1][1]) == 0.0
+
+
+def test_load_config_on_the_reference_configs_when_present():
+    import os
+    from mrn_b200 import tiny_train
+    root = "/root/reference/config"
+    if not os.path.isdir(root):
+        pytest.skip("reference tree not present")
+    for name, fe in (("svtr_mrn.py", "SVTR"), ("crnn_mrn.py", "VGG")):
+        opt = tiny_train.load_config(os.path.join(root, name))
+        assert opt.il == "mrn" and opt.FeatureExtraction == fe and opt.Prediction == "CTC"
+        assert opt.batch_size == 256 and opt.imgH == 32 and opt.imgW == 256 and len(opt.lan_list) == 6
+
+
+def test_domain_ids_flatten_like_the_reference():
+    import torch
+    from mrn_b200.il_modules.mrn import _domain_ids
+    a = _domain_ids([torch.tensor([0, 1, 1]), torch.tensor([2])])
+    assert a.dtype == torch.long and a.tolist() == [0, 1, 1, 2]
+    assert _domain_ids([3, 0, 1]).tolist() == [3, 0, 1]
