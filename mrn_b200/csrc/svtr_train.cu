@@ -232,7 +232,7 @@ template <int D>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
               const float* add, float* dx, __nv_bfloat16* __restrict__ dx16, float* __restrict__ dgamma,
-              float* __restrict__ dbeta, long rows, float eps) {
+              float* __restrict__ dbeta, long rows, float eps, const float* __restrict__ scale16, int rows_per_scale) {
   constexpr int VPT = D / 32;
   __shared__ float red[8][D];
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
@@ -264,7 +264,7 @@ ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const f
       float r = rstd * (d[j] - s1 - v[j] * s2);
       if (add) r += add[o];
       dx[o] = r;
-      if (dx16) dx16[o] = __float2bfloat16_rn(r);
+      if (dx16) dx16[o] = __float2bfloat16_rn(scale16 ? r * scale16[row / rows_per_scale] : r);
     }
   }
 #pragma unroll
@@ -288,17 +288,20 @@ ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const f
   }
 }
 
+// dx16 (optional): 16-bit copy of dx, multiplied by scale16[row / rows_per_scale] when given -- the DropPath-scaled GEMM
+// operand of the branch that consumes dx next
 int launch_ln_bwd(const float* x, const float* dy, const float* gamma, const float* add, float* dx, __nv_bfloat16* dx16,
-                  float* dgamma, float* dbeta, long rows, int D, float eps, cudaStream_t st) {
+                  float* dgamma, float* dbeta, long rows, int D, float eps, cudaStream_t st, const float* scale16 = nullptr,
+                  int rows_per_scale = 1) {
   int grid = cdiv(rows, 8 * 8);
   if (grid > 148 * 4) grid = 148 * 4;
   if (grid < 1) grid = 1;
   MrnbProfScope prof(MRNB_PROF_LN, st, 0.0, (double)rows * D * 16);
   switch (D) {
-    case 64: ln_bwd_kernel<64><<<grid, 256, 0, st>>>(x, dy, gamma, add, dx, dx16, dgamma, dbeta, rows, eps); break;
-    case 128: ln_bwd_kernel<128><<<grid, 256, 0, st>>>(x, dy, gamma, add, dx, dx16, dgamma, dbeta, rows, eps); break;
-    case 256: ln_bwd_kernel<256><<<grid, 256, 0, st>>>(x, dy, gamma, add, dx, dx16, dgamma, dbeta, rows, eps); break;
-    case 512: ln_bwd_kernel<512><<<grid, 256, 0, st>>>(x, dy, gamma, add, dx, dx16, dgamma, dbeta, rows, eps); break;
+    case 64: ln_bwd_kernel<64><<<grid, 256, 0, st>>>(x, dy, gamma, add, dx, dx16, dgamma, dbeta, rows, eps, scale16, rows_per_scale); break;
+    case 128: ln_bwd_kernel<128><<<grid, 256, 0, st>>>(x, dy, gamma, add, dx, dx16, dgamma, dbeta, rows, eps, scale16, rows_per_scale); break;
+    case 256: ln_bwd_kernel<256><<<grid, 256, 0, st>>>(x, dy, gamma, add, dx, dx16, dgamma, dbeta, rows, eps, scale16, rows_per_scale); break;
+    case 512: ln_bwd_kernel<512><<<grid, 256, 0, st>>>(x, dy, gamma, add, dx, dx16, dgamma, dbeta, rows, eps, scale16, rows_per_scale); break;
     default: mrnb_set_error("ln_bwd: unsupported D=%d", D); return MRNB_ERR_UNSUPPORTED;
   }
   MRNB_CHECK_LAUNCH("ln_bwd_kernel");
@@ -826,10 +829,12 @@ int train_backward_t(const MrnbSvtrPack& P, const MrnbSvtrPack& G, const float* 
                            gp(G, ps + MRNB_PS_NORM_B), M, 512, 1e-5f, st));
   }
   int blk = 12;
+  bool dy16_ready = false;      // bf16 mode: w.dy16 already holds the scaled operand of the next branch
   for (int s = 2; s >= 0; --s) {
     const int d = DIMS[s], N = 32768 / d, heads = HEADS[s], H = GH[s], Wd = 64;
     const int rows = B * N;
     const int Co = OUTS[s], Ho = H / 2;
+    dy16_ready = false;         // the stage starts from the col2im output
     const int orows = B * Ho * Wd;
     const int ps = MRNB_P_SUB0 + s * MRNB_PS_COUNT;
     // ---- SubSample conv backward (im2col recomputed from the stage output)
@@ -850,13 +855,16 @@ int train_backward_t(const MrnbSvtrPack& P, const MrnbSvtrPack& G, const float* 
       const float* xin = j == 0 ? w.stage_in[s] : w.xout[blk - 1];
       // ---- MLP branch: xout = xmid + ds1 * (GELU(LN2(xmid) W1^T + b1) W2^T + b2)
       Grad gy{dx, w.dy16, d};
-      if (drop || TC) {
+      if (TC && dy16_ready) {
+        // the LayerNorm backward that produced dx already wrote its DropPath-scaled bf16 copy
+      } else if (drop || TC) {
         scale_rows_kernel<<<cdiv(u, 256), 256, 0, st>>>(dx, drop ? drop + ((size_t)blk * 2 + 1) * B : nullptr, N, d,
-                                                        drop ? w.dy : nullptr, w.dy16, u);
+                                                        (drop && !TC) ? w.dy : nullptr, w.dy16, u);
         MRNB_CHECK_LAUNCH("scale_rows_kernel");
-        if (drop) gy.f = w.dy;
+        if (drop && !TC) gy.f = w.dy;
       }
-      MRNB_TRY(launch_colsum<float>(gy.f, d, rows, d, gp(G, pb + MRNB_PB_FC2_B), st));
+      if constexpr (TC) MRNB_TRY(launch_colsum<bf16>(w.dy16, d, rows, d, gp(G, pb + MRNB_PB_FC2_B), st));
+      else MRNB_TRY(launch_colsum<float>(gy.f, d, rows, d, gp(G, pb + MRNB_PB_FC2_B), st));
       MRNB_TRY(gemm_dw<AT>(gy, w.hact[blk], 4 * d, gp(G, pb + MRNB_PB_FC2_W), rows, d, 4 * d, st));
       MRNB_TRY(gemm_dx<AT>(gy, P.p[pb + MRNB_PB_FC2_W], P.h[pb + MRNB_PB_FC2_W], w.dbig, nullptr, 4 * d, rows, d, 4 * d, st));
       gelu_bwd_kernel<AT><<<cdiv(u * 4, 256), 256, 0, st>>>(w.hpre[blk], w.dbig, w.dbig16, u * 4);
@@ -865,17 +873,19 @@ int train_backward_t(const MrnbSvtrPack& P, const MrnbSvtrPack& G, const float* 
       MRNB_TRY(launch_colsum<float>(w.dbig, 4 * d, rows, 4 * d, gp(G, pb + MRNB_PB_FC1_B), st));
       MRNB_TRY(gemm_dw<AT>(gh, w.ln2[blk], d, gp(G, pb + MRNB_PB_FC1_W), rows, 4 * d, d, st));
       MRNB_TRY(gemm_dx<AT>(gh, P.p[pb + MRNB_PB_FC1_W], P.h[pb + MRNB_PB_FC1_W], w.dln, nullptr, d, rows, 4 * d, d, st));
-      MRNB_TRY(launch_ln_bwd(w.xmid[blk], w.dln, P.p[pb + MRNB_PB_NORM2_W], dx, dx, nullptr, gp(G, pb + MRNB_PB_NORM2_W),
-                             gp(G, pb + MRNB_PB_NORM2_B), rows, d, 1e-6f, st));
+      // (bf16 mode: the same pass emits the mixer branch's GEMM operand, dx * ds0, in bf16)
+      MRNB_TRY(launch_ln_bwd(w.xmid[blk], w.dln, P.p[pb + MRNB_PB_NORM2_W], dx, dx, TC ? w.dy16 : nullptr,
+                             gp(G, pb + MRNB_PB_NORM2_W), gp(G, pb + MRNB_PB_NORM2_B), rows, d, 1e-6f, st,
+                             drop ? drop + ((size_t)blk * 2 + 0) * B : nullptr, N));
       // ---- mixer branch: xmid = xin + ds0 * (Attn(LN1(xin)) Wp^T + bp)
       gy = Grad{dx, w.dy16, d};
-      if (drop || TC) {
-        scale_rows_kernel<<<cdiv(u, 256), 256, 0, st>>>(dx, drop ? drop + ((size_t)blk * 2 + 0) * B : nullptr, N, d,
-                                                        drop ? w.dy : nullptr, w.dy16, u);
+      if (drop && !TC) {
+        scale_rows_kernel<<<cdiv(u, 256), 256, 0, st>>>(dx, drop + ((size_t)blk * 2 + 0) * B, N, d, w.dy, nullptr, u);
         MRNB_CHECK_LAUNCH("scale_rows_kernel");
-        if (drop) gy.f = w.dy;
+        gy.f = w.dy;
       }
-      MRNB_TRY(launch_colsum<float>(gy.f, d, rows, d, gp(G, pb + MRNB_PB_PROJ_B), st));
+      if constexpr (TC) MRNB_TRY(launch_colsum<bf16>(w.dy16, d, rows, d, gp(G, pb + MRNB_PB_PROJ_B), st));
+      else MRNB_TRY(launch_colsum<float>(gy.f, d, rows, d, gp(G, pb + MRNB_PB_PROJ_B), st));
       MRNB_TRY(gemm_dw<AT>(gy, w.att[blk], d, gp(G, pb + MRNB_PB_PROJ_W), rows, d, d, st));
       MRNB_TRY(gemm_dx<AT>(gy, P.p[pb + MRNB_PB_PROJ_W], P.h[pb + MRNB_PB_PROJ_W], w.datt, w.datt16, d, rows, d, d, st));
       Grad gq{w.dqkv, w.dqkv16, 3L * d};
@@ -889,8 +899,11 @@ int train_backward_t(const MrnbSvtrPack& P, const MrnbSvtrPack& G, const float* 
       }
       MRNB_TRY(gemm_dw<AT>(gq, w.ln1[blk], d, gp(G, pb + MRNB_PB_QKV_W), rows, 3 * d, d, st));
       MRNB_TRY(gemm_dx<AT>(gq, P.p[pb + MRNB_PB_QKV_W], P.h[pb + MRNB_PB_QKV_W], w.dln, nullptr, d, rows, 3 * d, d, st));
-      MRNB_TRY(launch_ln_bwd(xin, w.dln, P.p[pb + MRNB_PB_NORM1_W], dx, dx, nullptr, gp(G, pb + MRNB_PB_NORM1_W),
-                             gp(G, pb + MRNB_PB_NORM1_B), rows, d, 1e-6f, st));
+      // (bf16 mode, not the first block of the stage: also emit dx * ds1 of the previous block, its MLP branch's operand)
+      dy16_ready = TC && j > 0;
+      MRNB_TRY(launch_ln_bwd(xin, w.dln, P.p[pb + MRNB_PB_NORM1_W], dx, dx, dy16_ready ? w.dy16 : nullptr,
+                             gp(G, pb + MRNB_PB_NORM1_W), gp(G, pb + MRNB_PB_NORM1_B), rows, d, 1e-6f, st,
+                             (drop && j > 0) ? drop + ((size_t)(blk - 1) * 2 + 1) * B : nullptr, N));
     }
     if (s > 0) {
       // stage input = LN(conv output of the previous merge)
