@@ -312,18 +312,44 @@ int launch_ln_bwd(const float* x, const float* dy, const float* gamma, const flo
 // Elementwise: GELU forward / backward, DropPath row scaling
 // ------------------------------------------------------------------------------------------------
 template <typename AT>
-__global__ void gelu_fwd_kernel(const AT* __restrict__ pre, AT* __restrict__ act, long n) {
+__global__ void gelu_fwd_kernel(const AT* __restrict__ pre, AT* __restrict__ act, long n4) {       // four elements per thread
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) act[i] = from_f32<AT>(gelu_erf(to_f32<AT>(pre[i])));
+  if (i >= n4) return;
+  if constexpr (sizeof(AT) == 4) {
+    const float4 p = reinterpret_cast<const float4*>(pre)[i];
+    reinterpret_cast<float4*>(act)[i] = make_float4(gelu_erf(p.x), gelu_erf(p.y), gelu_erf(p.z), gelu_erf(p.w));
+  } else {
+    const uint2 p = reinterpret_cast<const uint2*>(pre)[i];
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&p.x), b = *reinterpret_cast<const __nv_bfloat162*>(&p.y);
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(gelu_erf(__bfloat162float(a.x)), gelu_erf(__bfloat162float(a.y)));
+    __nv_bfloat162 h1 = __floats2bfloat162_rn(gelu_erf(__bfloat162float(b.x)), gelu_erf(__bfloat162float(b.y)));
+    reinterpret_cast<uint2*>(act)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+  }
 }
-// d <- d * GELU'(pre)  (in place, fp32) + optional 16-bit copy
+// d * GELU'(pre): fp32 in place (fp32 mode) or bf16 only (bf16 mode: the result is a GEMM operand and the source of the
+// bias sum; the fp32 tensor is not written back).  Four elements per thread.
 template <typename AT>
-__global__ void gelu_bwd_kernel(const AT* __restrict__ pre, float* __restrict__ d, __nv_bfloat16* __restrict__ d16, long n) {
+__global__ void gelu_bwd_kernel(const AT* __restrict__ pre, float* __restrict__ d, __nv_bfloat16* __restrict__ d16, long n4) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float v = d[i] * gelu_erf_grad(to_f32<AT>(pre[i]));
-  d[i] = v;
-  if (d16) d16[i] = __float2bfloat16_rn(v);
+  if (i >= n4) return;
+  const float4 g = reinterpret_cast<const float4*>(d)[i];
+  float x[4];
+  if constexpr (sizeof(AT) == 4) {
+    const float4 p = reinterpret_cast<const float4*>(pre)[i];
+    x[0] = p.x; x[1] = p.y; x[2] = p.z; x[3] = p.w;
+  } else {
+    const uint2 p = reinterpret_cast<const uint2*>(pre)[i];
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&p.x), b = *reinterpret_cast<const __nv_bfloat162*>(&p.y);
+    x[0] = __bfloat162float(a.x); x[1] = __bfloat162float(a.y); x[2] = __bfloat162float(b.x); x[3] = __bfloat162float(b.y);
+  }
+  const float v0 = g.x * gelu_erf_grad(x[0]), v1 = g.y * gelu_erf_grad(x[1]), v2 = g.z * gelu_erf_grad(x[2]),
+              v3 = g.w * gelu_erf_grad(x[3]);
+  if (d16) {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
+    reinterpret_cast<uint2*>(d16)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+  } else {
+    reinterpret_cast<float4*>(d)[i] = make_float4(v0, v1, v2, v3);
+  }
 }
 // y[r,:] = x[r,:] * scale[r / rows_per_scale]   (+ optional 16-bit copy); scale may be null (copy / cast only)
 __global__ void scale_rows_kernel(const float* __restrict__ x, const float* __restrict__ scale, int rows_per_scale, int D,
@@ -766,8 +792,8 @@ int train_forward_t(const MrnbSvtrPack& P, const float* image, int B, int bn_bat
       MRNB_TRY(launch_ln_fwd<AT>(w.xmid[blk], w.ln2[blk], P.p[pb + MRNB_PB_NORM2_W], P.p[pb + MRNB_PB_NORM2_B], rows, d, 1e-6f, st));
       MRNB_TRY(lin<AT>(w.ln2[blk], d, P.p[pb + MRNB_PB_FC1_W], P.h[pb + MRNB_PB_FC1_W], P.p[pb + MRNB_PB_FC1_B], w.hpre[blk],
                        4 * d, false, rows, 4 * d, d, nullptr, nullptr, 1, st));
-      const long n = (long)rows * 4 * d;
-      gelu_fwd_kernel<AT><<<cdiv(n, 256), 256, 0, st>>>(w.hpre[blk], w.hact[blk], n);
+      const long n4 = (long)rows * d;                      // rows * 4d elements, four per thread
+      gelu_fwd_kernel<AT><<<cdiv(n4, 256), 256, 0, st>>>(w.hpre[blk], w.hact[blk], n4);
       MRNB_CHECK_LAUNCH("gelu_fwd_kernel");
       MRNB_TRY(lin<AT>(w.hact[blk], 4 * d, P.p[pb + MRNB_PB_FC2_W], P.h[pb + MRNB_PB_FC2_W], P.p[pb + MRNB_PB_FC2_B],
                        w.xout[blk], d, true, rows, d, 4 * d, w.xmid[blk], drop ? drop + ((size_t)blk * 2 + 1) * B : nullptr, N, st));
@@ -867,10 +893,11 @@ int train_backward_t(const MrnbSvtrPack& P, const MrnbSvtrPack& G, const float* 
       else MRNB_TRY(launch_colsum<float>(gy.f, d, rows, d, gp(G, pb + MRNB_PB_FC2_B), st));
       MRNB_TRY(gemm_dw<AT>(gy, w.hact[blk], 4 * d, gp(G, pb + MRNB_PB_FC2_W), rows, d, 4 * d, st));
       MRNB_TRY(gemm_dx<AT>(gy, P.p[pb + MRNB_PB_FC2_W], P.h[pb + MRNB_PB_FC2_W], w.dbig, nullptr, 4 * d, rows, d, 4 * d, st));
-      gelu_bwd_kernel<AT><<<cdiv(u * 4, 256), 256, 0, st>>>(w.hpre[blk], w.dbig, w.dbig16, u * 4);
+      gelu_bwd_kernel<AT><<<cdiv(u, 256), 256, 0, st>>>(w.hpre[blk], w.dbig, w.dbig16, u);
       MRNB_CHECK_LAUNCH("gelu_bwd_kernel");
       Grad gh{w.dbig, w.dbig16, 4L * d};
-      MRNB_TRY(launch_colsum<float>(w.dbig, 4 * d, rows, 4 * d, gp(G, pb + MRNB_PB_FC1_B), st));
+      if constexpr (TC) MRNB_TRY(launch_colsum<bf16>(w.dbig16, 4 * d, rows, 4 * d, gp(G, pb + MRNB_PB_FC1_B), st));
+      else MRNB_TRY(launch_colsum<float>(w.dbig, 4 * d, rows, 4 * d, gp(G, pb + MRNB_PB_FC1_B), st));
       MRNB_TRY(gemm_dw<AT>(gh, w.ln2[blk], d, gp(G, pb + MRNB_PB_FC1_W), rows, 4 * d, d, st));
       MRNB_TRY(gemm_dx<AT>(gh, P.p[pb + MRNB_PB_FC1_W], P.h[pb + MRNB_PB_FC1_W], w.dln, nullptr, d, rows, 4 * d, d, st));
       // (bf16 mode: the same pass emits the mixer branch's GEMM operand, dx * ds0, in bf16)
