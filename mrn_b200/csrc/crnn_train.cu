@@ -56,6 +56,52 @@ __global__ void im2col_s1_kernel(const float* __restrict__ x, OT* __restrict__ c
   }
 }
 
+// bf16 im2col for the GEMM convolutions, eight channels per thread (two 16-byte loads, one 16-byte store); the channel
+// count and the tap count are template parameters so that only the (row -> b, oh, ow) split divides by runtime values.
+template <int C, int KH, int KW>
+__global__ void __launch_bounds__(256)
+im2col_s1_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ col, int H, int W, int pad, int Ho, int Wo, long pairs) {
+  constexpr int G = C / 8, KK = KH * KW;
+  const long pair = (long)blockIdx.x * (256 / G) + threadIdx.x / G;      // (output pixel, tap)
+  if (pair >= pairs) return;
+  const int c = (threadIdx.x % G) * 8;
+  const int tap = (int)(pair % KK);
+  long r = pair / KK;
+  const int ow = (int)(r % Wo); r /= Wo;
+  const int oh = (int)(r % Ho);
+  const long b = r / Ho;
+  const int ih = oh - pad + tap / KW, iw = ow - pad + tap % KW;
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+    const float4* src = reinterpret_cast<const float4*>(x + ((b * H + ih) * W + iw) * C + c);
+    const float4 v0 = src[0], v1 = src[1];
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v0.x, v0.y), h1 = __floats2bfloat162_rn(v0.z, v0.w);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v1.x, v1.y), h3 = __floats2bfloat162_rn(v1.z, v1.w);
+    o = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2),
+                   *reinterpret_cast<uint32_t*>(&h3));
+  }
+  *reinterpret_cast<uint4*>(col + pair * C + c) = o;
+}
+
+template <typename AT>
+int launch_im2col(const float* x, AT* col, int H, int W, int C, int KH, int KW, int pad, int Ho, int Wo, long rows, cudaStream_t st) {
+  if constexpr (sizeof(AT) == 2) {
+    const long pairs = rows * KH * KW;
+#define IM2COL_CASE(C_, KH_, KW_)                                                                                        \
+    if (C == C_ && KH == KH_ && KW == KW_) {                                                                             \
+      im2col_s1_bf16_kernel<C_, KH_, KW_><<<cdiv(pairs, 256 / (C_ / 8)), 256, 0, st>>>(x, col, H, W, pad, Ho, Wo, pairs); \
+      MRNB_CHECK_LAUNCH("im2col_s1_bf16_kernel");                                                                         \
+      return MRNB_OK;                                                                                                    \
+    }
+    IM2COL_CASE(64, 3, 3) IM2COL_CASE(128, 3, 3) IM2COL_CASE(256, 3, 3) IM2COL_CASE(512, 3, 3) IM2COL_CASE(512, 2, 2)
+#undef IM2COL_CASE
+  }
+  const long c4 = rows * KH * KW * C / 4;
+  im2col_s1_kernel<AT><<<cdiv(c4, 256), 256, 0, st>>>(x, col, H, W, C, KH, KW, pad, Ho, Wo, c4);
+  MRNB_CHECK_LAUNCH("im2col_s1_kernel");
+  return MRNB_OK;
+}
+
 // transpose: dx[b,ih,iw,c] = sum over taps of dcol[(b, ih + pad - kh, iw + pad - kw), (kh,kw,c)]
 __global__ void col2im_s1_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int H, int W, int C, int KH, int KW,
                                  int pad, int Ho, int Wo, long total4) {
@@ -103,44 +149,55 @@ __global__ void bn_relu_kernel(const float* __restrict__ raw, const float* __res
   const int c = (int)(i % C);
   y[i] = fmaxf(fmaf(raw[i], ss[c * 2], ss[c * 2 + 1]), 0.f);
 }
-// max-pool ph x pw (stride = window) over NHWC
-__global__ void maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int C, int ph, int pw, long total) {
+// max-pool ph x pw (stride = window) over NHWC, four channels per thread
+__global__ void maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int C, int ph, int pw, long total4) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c = (int)(i % C);
-  long r = i / C;
+  if (i >= total4) return;
+  const int c4 = C / 4;
+  const int c = (int)(i % c4) * 4;
+  long r = i / c4;
   const int Wo = W / pw, Ho = H / ph;
   const int ow = (int)(r % Wo); r /= Wo;
   const int oh = (int)(r % Ho);
   const long b = r / Ho;
-  float m = -INFINITY;
+  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
   for (int dy = 0; dy < ph; ++dy)
-    for (int dx = 0; dx < pw; ++dx) m = fmaxf(m, x[((b * H + oh * ph + dy) * W + ow * pw + dx) * C + c]);
-  y[i] = m;
+    for (int dx = 0; dx < pw; ++dx) {
+      const float4 v = *reinterpret_cast<const float4*>(x + ((b * H + oh * ph + dy) * W + ow * pw + dx) * C + c);
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+  *reinterpret_cast<float4*>(y + i * 4) = m;
 }
 // backward of relu -> max-pool: the first maximal element of each window receives the gradient if it is positive
-// (windows do not overlap; ties among zeros are irrelevant because relu' = 0 there)
+// (windows do not overlap; ties among zeros are irrelevant because relu' = 0 there).  Four channels per thread.
 __global__ void maxpool_relu_bwd_kernel(const float* __restrict__ a, const float* __restrict__ dy, float* __restrict__ da, int H,
-                                        int W, int C, int ph, int pw, long total) {
+                                        int W, int C, int ph, int pw, long total4) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c = (int)(i % C);
-  long r = i / C;
+  if (i >= total4) return;
+  const int c4 = C / 4;
+  const int c = (int)(i % c4) * 4;
+  long r = i / c4;
   const int Wo = W / pw, Ho = H / ph;
   const int ow = (int)(r % Wo); r /= Wo;
   const int oh = (int)(r % Ho);
   const long b = r / Ho;
-  float m = -INFINITY;
-  int arg = 0;
+  float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  int arg[4] = {0, 0, 0, 0};
   for (int dy_ = 0; dy_ < ph; ++dy_)
     for (int dx_ = 0; dx_ < pw; ++dx_) {
-      const float v = a[((b * H + oh * ph + dy_) * W + ow * pw + dx_) * C + c];
-      if (v > m) { m = v; arg = dy_ * pw + dx_; }
+      const float4 v4 = *reinterpret_cast<const float4*>(a + ((b * H + oh * ph + dy_) * W + ow * pw + dx_) * C + c);
+      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (v[k] > m[k]) { m[k] = v[k]; arg[k] = dy_ * pw + dx_; }
     }
-  const float g = m > 0.f ? dy[i] : 0.f;
+  const float4 g4 = *reinterpret_cast<const float4*>(dy + i * 4);
+  const float g[4] = {m[0] > 0.f ? g4.x : 0.f, m[1] > 0.f ? g4.y : 0.f, m[2] > 0.f ? g4.z : 0.f, m[3] > 0.f ? g4.w : 0.f};
   for (int dy_ = 0; dy_ < ph; ++dy_)
-    for (int dx_ = 0; dx_ < pw; ++dx_)
-      da[((b * H + oh * ph + dy_) * W + ow * pw + dx_) * C + c] = (dy_ * pw + dx_ == arg) ? g : 0.f;
+    for (int dx_ = 0; dx_ < pw; ++dx_) {
+      const int p = dy_ * pw + dx_;
+      *reinterpret_cast<float4*>(da + ((b * H + oh * ph + dy_) * W + ow * pw + dx_) * C + c) =
+          make_float4(p == arg[0] ? g[0] : 0.f, p == arg[1] ? g[1] : 0.f, p == arg[2] ? g[2] : 0.f, p == arg[3] ? g[3] : 0.f);
+    }
 }
 
 // BatchNorm backward (d already carries the relu mask): S1 = sum d, S2 = sum d * xhat per channel (fp64 atomics)
@@ -355,8 +412,7 @@ int crnn_train_forward_t(const MrnbCrnnTrainPack& P, const float* image, int B, 
       g.bias_n = P.p[L.b_slot]; g.act = 2;
       MRNB_TRY(mrnb_sgemm(g, st));
     } else {
-      im2col_s1_kernel<AT><<<cdiv(c4, 256), 256, 0, st>>>(in, w.col, L.H, L.W, L.Cin, L.KH, L.KW, L.pad, Ho, Wo, c4);
-      MRNB_CHECK_LAUNCH("im2col_s1_kernel");
+      MRNB_TRY(launch_im2col<AT>(in, w.col, L.H, L.W, L.Cin, L.KH, L.KW, L.pad, Ho, Wo, rows, st));
       MRNB_TRY(lin<AT>(w.col, K, P.p[L.w_slot], P.h[L.w_slot], L.b_slot >= 0 ? P.p[L.b_slot] : nullptr, dst, L.Cout, true, rows,
                        L.Cout, K, nullptr, nullptr, 1, st));
       if (L.bn < 0) {
@@ -376,7 +432,7 @@ int crnn_train_forward_t(const MrnbCrnnTrainPack& P, const float* image, int B, 
     }
     if (L.ph * L.pw > 1) {
       const long np = n / (L.ph * L.pw);
-      maxpool_kernel<<<cdiv(np, 256), 256, 0, st>>>(w.act[l], w.pool[l], Ho, Wo, L.Cout, L.ph, L.pw, np);
+      maxpool_kernel<<<cdiv(np / 4, 256), 256, 0, st>>>(w.act[l], w.pool[l], Ho, Wo, L.Cout, L.ph, L.pw, np / 4);
       MRNB_CHECK_LAUNCH("maxpool_kernel");
     }
     in = w.pool[l];
@@ -535,7 +591,7 @@ int crnn_train_backward_t(const MrnbCrnnTrainPack& P, const MrnbCrnnTrainPack& G
     // through pool + relu (or relu alone) to the conv / BN output
     if (L.ph * L.pw > 1) {
       const long np = n / (L.ph * L.pw);
-      maxpool_relu_bwd_kernel<<<cdiv(np, 256), 256, 0, st>>>(w.act[l], d, other, Ho, Wo, L.Cout, L.ph, L.pw, np);
+      maxpool_relu_bwd_kernel<<<cdiv(np / 4, 256), 256, 0, st>>>(w.act[l], d, other, Ho, Wo, L.Cout, L.ph, L.pw, np / 4);
       MRNB_CHECK_LAUNCH("maxpool_relu_bwd_kernel");
       float* t = d; d = other; other = t;
       if (d16 && L.bn < 0) {
@@ -568,8 +624,7 @@ int crnn_train_backward_t(const MrnbCrnnTrainPack& P, const MrnbCrnnTrainPack& G
       break;                                   // no gradient w.r.t. the image
     }
     Grad gd{d, d16, L.Cout};
-    im2col_s1_kernel<AT><<<cdiv(c4, 256), 256, 0, st>>>(in, w.col, L.H, L.W, L.Cin, L.KH, L.KW, L.pad, Ho, Wo, c4);
-    MRNB_CHECK_LAUNCH("im2col_s1_kernel");
+    MRNB_TRY(launch_im2col<AT>(in, w.col, L.H, L.W, L.Cin, L.KH, L.KW, L.pad, Ho, Wo, rows, st));
     MRNB_TRY(gemm_dw<AT>(gd, w.col, K, gpt(G, L.w_slot), rows, L.Cout, K, st));
     MRNB_TRY(gemm_dx<AT>(gd, P.p[L.w_slot], P.h[L.w_slot], w.dcol, nullptr, K, rows, L.Cout, K, st));
     const long in4 = (long)B * L.H * L.W * L.Cin / 4;
