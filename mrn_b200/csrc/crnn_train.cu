@@ -462,16 +462,19 @@ int crnn_train_forward_t(const MrnbCrnnTrainPack& P, const float* image, int B, 
         if constexpr (TC) {
           // G[:, t_dir, dir] += h_prev[dir] W_hh[dir]^T on the tensor cores: h_prev is the bf16 hidden sequence the
           // previous cell wrote at this position; the accumulate is the epilogue's residual at the output address
-          const int tpos[2] = {tf, tr};
-          for (int dir = 0; dir < 2; ++dir) {
-            MrnbTcGemm2 g{};
-            g.a = mrnb_operand_k2d(w.hseq[k] + (long)tpos[dir] * 512 + dir * HID, B, HID, (long)T63 * 512, 128, 1);
-            g.b = mrnb_operand_k2d((const bf16*)P.h[s0 + MRNB_TL_WHH] + (long)dir * 1024 * HID, 1024, HID, HID, 128, 1);
-            float* c = w.G[k] + (long)tpos[dir] * 2048 + dir * 1024;
-            g.out32 = c; g.res = c; g.cm = mrnb_axis((long)T63 * 2048); g.cn = mrnb_axis(1);
-            g.M = B; g.N = 1024; g.K = HID; g.groups = 1; g.splitk = 1; g.alpha = 1.f;
-            MRNB_TRY(mrnb_tc_gemm2(g, st));
-          }
+          // one launch for both directions (groups = 2): the two operand slices sit at different time positions, so the
+          // A map walks them in address order and the recipe mirrors the group index when the reverse direction is lower
+          const long pa[2] = {(long)tf * 512, (long)tr * 512 + HID};
+          const long pc[2] = {(long)tf * 2048, (long)tr * 2048 + 1024};
+          const bool up = pa[1] > pa[0];
+          MrnbTcGemm2 g{};
+          g.a = mrnb_operand_k2d(w.hseq[k] + (up ? pa[0] : pa[1]), B, HID, (long)T63 * 512, 128, 2, up ? pa[1] - pa[0] : pa[0] - pa[1]);
+          if (!up) g.a.recipe.flip[2] = 2;
+          g.b = mrnb_operand_k2d(P.h[s0 + MRNB_TL_WHH], 1024, HID, HID, 128, 2, 1024L * HID);
+          float* c = w.G[k] + pc[0];
+          g.out32 = c; g.res = c; g.cm = mrnb_axis((long)T63 * 2048); g.cn = mrnb_axis(1); g.c_gstride = pc[1] - pc[0];
+          g.M = B; g.N = 1024; g.K = HID; g.groups = 2; g.splitk = 1; g.alpha = 1.f;
+          MRNB_TRY(mrnb_tc_gemm2(g, st));
         } else {
           // both directions in one fp32 launch (batch = 2)
           MrnbGemm g = mrnb_gemm_nt(w.rec[k] + (long)(tf - 1) * 512, (long)T63 * 512, P.p[s0 + MRNB_TL_WHH], HID,
@@ -541,15 +544,18 @@ int crnn_train_backward_t(const MrnbCrnnTrainPack& P, const MrnbCrnnTrainPack& G
         // the [B,256] x K = 1024 product spreads over the SMs)
         const int tpos[2] = {T63 - s, s - 1};         // positions processed at step s - 1
         if constexpr (TC) {
+          // bf16 gate gradients (written by the cell kernel) x W_hh read MN-major; both directions in one launch
+          // (groups = 2, mirrored group index when the reverse direction's slice is lower), K = 1024 split 8 ways
           cudaMemsetAsync(w.dhn, 0, (size_t)2 * B * HID * sizeof(float), st);
-          for (int dir = 0; dir < 2; ++dir) {          // bf16 gate gradients (written by the cell kernel) x W_hh read MN-major;
-            MrnbTcGemm2 g{};                           // K = 1024 split 8 ways so that 32 CTAs share the 16 k-blocks
-            g.a = mrnb_operand_k2d(w.dG16 + (long)tpos[dir] * 2048 + dir * 1024, B, 1024, (long)T63 * 2048, 128, 1);
-            g.b = mrnb_operand_mn2d((const bf16*)P.h[s0 + MRNB_TL_WHH] + (long)dir * 1024 * HID, HID, 1024, HID, 1);
-            g.out32 = w.dhn + (long)dir * B * HID; g.cm = mrnb_axis(HID); g.cn = mrnb_axis(1);
-            g.M = B; g.N = HID; g.K = 1024; g.groups = 1; g.splitk = 8; g.alpha = 1.f;
-            MRNB_TRY(mrnb_tc_gemm2(g, st));
-          }
+          const long pa[2] = {(long)tpos[0] * 2048, (long)tpos[1] * 2048 + 1024};
+          const bool up = pa[1] > pa[0];
+          MrnbTcGemm2 g{};
+          g.a = mrnb_operand_k2d(w.dG16 + (up ? pa[0] : pa[1]), B, 1024, (long)T63 * 2048, 128, 2, up ? pa[1] - pa[0] : pa[0] - pa[1]);
+          if (!up) g.a.recipe.flip[2] = 2;
+          g.b = mrnb_operand_mn2d(P.h[s0 + MRNB_TL_WHH], HID, 1024, HID, 2, 1024L * HID);
+          g.out32 = w.dhn; g.cm = mrnb_axis(HID); g.cn = mrnb_axis(1); g.c_gstride = (long)B * HID;
+          g.M = B; g.N = HID; g.K = 1024; g.groups = 2; g.splitk = 8; g.alpha = 1.f;
+          MRNB_TRY(mrnb_tc_gemm2(g, st));
         } else {
           cudaMemsetAsync(w.dhn, 0, (size_t)2 * B * HID * sizeof(float), st);
           for (int dir = 0; dir < 2; ++dir) {

@@ -94,6 +94,7 @@ __device__ __forceinline__ void recipe_coords(const MrnbTmaRecipe& r, int mn, in
     int v = r.src[j] == MRNB_SRC_MN ? mn : (r.src[j] == MRNB_SRC_K ? k : (r.src[j] == MRNB_SRC_G ? g : 0));
     if (r.div[j] > 1) v /= r.div[j];
     if (r.mod[j] > 0) v %= r.mod[j];
+    if (r.flip[j] > 0) v = r.flip[j] - 1 - v;
     c[j] = v;
   }
 }

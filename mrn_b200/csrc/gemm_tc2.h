@@ -5,8 +5,10 @@
 
 enum { MRNB_SRC_ZERO = 0, MRNB_SRC_MN = 1, MRNB_SRC_K = 2, MRNB_SRC_G = 3 };
 
-// TMA coordinate j of a tile = ((value of src[j]) / div[j]) % mod[j]   (div <= 1: no division, mod == 0: no modulo)
-struct MrnbTmaRecipe { int src[4]; int div[4]; int mod[4]; };
+// TMA coordinate j of a tile = ((value of src[j]) / div[j]) % mod[j]   (div <= 1: no division, mod == 0: no modulo);
+// flip[j] > 0 mirrors it afterwards: flip[j] - 1 - coordinate (walks a dimension backwards, e.g. groups stored in
+// descending address order)
+struct MrnbTmaRecipe { int src[4]; int div[4]; int mod[4]; int flip[4]; };
 
 // A bf16 operand seen through a rank-4 TMA tensor map (dim 0 contiguous, 64 elements = 128 B inner box).
 struct MrnbTcOperand {
