@@ -280,7 +280,7 @@ __global__ void lstm_cell_fwd_kernel(float* __restrict__ G, float* __restrict__ 
 // BPTT step s (direction 0 at t = 62 - s, direction 1 at t = s): dh = drec[t] + dh_next; writes the gate
 // pre-activation gradients over the activated gates in G and carries dc.
 __global__ void lstm_cell_bwd_kernel(float* __restrict__ G, const float* __restrict__ c, const float* __restrict__ drec,
-                                     const float* __restrict__ dhn, float* __restrict__ dcn, int B, int s,
+                                     float* __restrict__ dhn, float* __restrict__ dcn, int B, int s,
                                      bf16* __restrict__ G16) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * B * HID) return;
@@ -293,6 +293,7 @@ __global__ void lstm_cell_bwd_kernel(float* __restrict__ G, const float* __restr
   const float ct = c[o];
   const float cp = has_prev ? c[((long)b * T63 + tp) * 512 + dir * HID + j] : 0.f;
   const float dh = drec[o] + (s > 0 ? dhn[i] : 0.f);
+  dhn[i] = 0.f;                       // the next step's split-K GEMM accumulates dh_next with reductions onto zero
   const float tc = tanhf(ct);
   const float dc = dh * go * (1.f - tc * tc) + (s > 0 ? dcn[i] : 0.f);
   const float ai = dc * gg * gi * (1.f - gi), af = dc * cp * gf * (1.f - gf), ag = dc * gi * (1.f - gg * gg),
@@ -546,7 +547,6 @@ int crnn_train_backward_t(const MrnbCrnnTrainPack& P, const MrnbCrnnTrainPack& G
         if constexpr (TC) {
           // bf16 gate gradients (written by the cell kernel) x W_hh read MN-major; both directions in one launch
           // (groups = 2, mirrored group index when the reverse direction's slice is lower), K = 1024 split 8 ways
-          cudaMemsetAsync(w.dhn, 0, (size_t)2 * B * HID * sizeof(float), st);
           const long pa[2] = {(long)tpos[0] * 2048, (long)tpos[1] * 2048 + 1024};
           const bool up = pa[1] > pa[0];
           MrnbTcGemm2 g{};
@@ -557,7 +557,6 @@ int crnn_train_backward_t(const MrnbCrnnTrainPack& P, const MrnbCrnnTrainPack& G
           g.M = B; g.N = HID; g.K = 1024; g.groups = 2; g.splitk = 8; g.alpha = 1.f;
           MRNB_TRY(mrnb_tc_gemm2(g, st));
         } else {
-          cudaMemsetAsync(w.dhn, 0, (size_t)2 * B * HID * sizeof(float), st);
           for (int dir = 0; dir < 2; ++dir) {
             MrnbGemm g{};
             g.A = w.G[k] + (long)tpos[dir] * 2048 + dir * 1024; g.am = mrnb_axis((long)T63 * 2048); g.ak = mrnb_axis(1); g.a_kfast = 1;
