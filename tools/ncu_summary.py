@@ -3,7 +3,10 @@ usage: python tools/ncu_summary.py launches.csv [--detail]"""
 import collections
 import csv
 import re
+import signal
 import sys
+
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)      # `| head` closes the pipe early
 
 
 def short(name):

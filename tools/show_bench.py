@@ -1,6 +1,9 @@
 """Pretty-print the JSON line of bench.py (stdin or file)."""
 import json
+import signal
 import sys
+
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)      # `| head` closes the pipe early
 src = open(sys.argv[1]).read() if len(sys.argv) > 1 else sys.stdin.read()
 line = [l for l in src.splitlines() if l.startswith("{")][-1]
 d = json.loads(line)
