@@ -343,3 +343,48 @@ def test_stage0_training_reduces_the_loss_on_a_fixed_batch(arch, precision):
     learner.end_expert_training()
     out = learner.net(x, cross=False, is_train=False)          # the inference path sees the trained weights
     assert torch.isfinite(out["logits"]).all()
+
+
+@pytest.mark.parametrize("arch", ["svtr", "crnn"])
+def test_stage0_full_size_properties(arch):
+    """BASELINE.json's full size (B = 256, union charset C = 5153, bf16 tensor-core mode), where the oracle is too slow:
+    size-independent properties of the step.  (1) softmax - occupancy sums to zero over the classes of every frame, so
+    the fc.bias gradient sums to zero; (2) the gradient of the mean loss is linear in the per-sample weights: the step
+    on the batch equals the average of the steps on its two halves for every parameter that does not see batch
+    statistics (eval-mode BatchNorm); (3) two runs agree up to the order of the split-K reductions."""
+    from mrn_b200 import ops
+    cc, B = (5153,), 256
+    sd = synth.synth_state_dict(cc, 111, arch=arch)
+    img, tgt, lens, _ = synth.synth_batch(B, cc, 2024)
+    esd = {k[len("model.0."):]: v for k, v in sd.items() if k.startswith("model.0.")}
+    x, t, l = img.cuda(), tgt.cuda(), lens.cuda()
+    tp = (ops.SvtrTrainPack if arch == "svtr" else ops.CrnnTrainPack)(esd, "cuda", 1)
+
+    def run(lo, hi):
+        xs, ts, ls = x[lo:hi].contiguous(), t[lo:hi].contiguous(), l[lo:hi].contiguous()
+        n = hi - lo
+        if arch == "svtr":
+            logits = ops.svtr_train_forward(tp, xs, False, False, None)
+        else:
+            logits = ops.crnn_train_forward(tp, xs, False, False)
+        rr = ops.gate_combine([logits], torch.ones(n, 1, device="cuda"), ts, ls)
+        c = ops.ctc_lattice(rr["lpe"], ts, ls, want_occ=True)
+        dlogits = ops.ctc_dense_grad(logits, rr["lse"], c["occ"], c["nll"], ts, ls, 1.0 / n)
+        if arch == "svtr":
+            ops.svtr_train_backward(tp, xs, dlogits, False, None)
+        else:
+            ops.crnn_train_backward(tp, dlogits, n, False)
+        torch.cuda.synchronize()
+        return float(c["loss"]), tp.grads.clone()
+
+    loss, g = run(0, B)
+    loss2, g2 = run(0, B)
+    la, ga = run(0, B // 2)
+    lb, gb = run(B // 2, B)
+    assert np.isfinite(loss) and torch.isfinite(g).all()
+    gn = float(g.double().norm())
+    fcb = tp.state(g)["fc.bias"].double()
+    assert abs(float(fcb.sum())) < 1e-3 * float(fcb.abs().sum())                   # (1)
+    assert abs(0.5 * (la + lb) - loss) / abs(loss) < 2e-3                          # (2) mean of the half-batch means
+    assert float((0.5 * (ga + gb) - g).double().norm()) / gn < 2e-2
+    assert abs(loss2 - loss) / abs(loss) < 1e-5 and float((g2 - g).double().norm()) / gn < 1e-3      # (3)
