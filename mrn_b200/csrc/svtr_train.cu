@@ -351,6 +351,24 @@ __global__ void gelu_bwd_kernel(const AT* __restrict__ pre, float* __restrict__ 
     reinterpret_cast<float4*>(d)[i] = make_float4(v0, v1, v2, v3);
   }
 }
+// bf16 mode: d16 <- d16 * GELU'(pre) in place (the fc2 input gradient leaves its GEMM as bf16; eight elements per thread)
+__global__ void gelu_bwd16_kernel(const __nv_bfloat16* __restrict__ pre, __nv_bfloat16* __restrict__ d16, long n8) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 p = reinterpret_cast<const uint4*>(pre)[i];
+  uint4 g = reinterpret_cast<uint4*>(d16)[i];
+  const uint32_t pw[4] = {p.x, p.y, p.z, p.w};
+  uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(&pw[k]);
+    const __nv_bfloat162 d = *reinterpret_cast<const __nv_bfloat162*>(&gw[k]);
+    __nv_bfloat162 o = __floats2bfloat162_rn(__bfloat162float(d.x) * gelu_erf_grad(__bfloat162float(x.x)),
+                                             __bfloat162float(d.y) * gelu_erf_grad(__bfloat162float(x.y)));
+    gw[k] = *reinterpret_cast<uint32_t*>(&o);
+  }
+  reinterpret_cast<uint4*>(d16)[i] = make_uint4(gw[0], gw[1], gw[2], gw[3]);
+}
 // y[r,:] = x[r,:] * scale[r / rows_per_scale]   (+ optional 16-bit copy); scale may be null (copy / cast only)
 __global__ void scale_rows_kernel(const float* __restrict__ x, const float* __restrict__ scale, int rows_per_scale, int D,
                                   float* __restrict__ y, __nv_bfloat16* __restrict__ y16, long n) {
@@ -892,9 +910,16 @@ int train_backward_t(const MrnbSvtrPack& P, const MrnbSvtrPack& G, const float* 
       if constexpr (TC) MRNB_TRY(launch_colsum<bf16>(w.dy16, d, rows, d, gp(G, pb + MRNB_PB_FC2_B), st));
       else MRNB_TRY(launch_colsum<float>(gy.f, d, rows, d, gp(G, pb + MRNB_PB_FC2_B), st));
       MRNB_TRY(gemm_dw<AT>(gy, w.hact[blk], 4 * d, gp(G, pb + MRNB_PB_FC2_W), rows, d, 4 * d, st));
-      MRNB_TRY(gemm_dx<AT>(gy, P.p[pb + MRNB_PB_FC2_W], P.h[pb + MRNB_PB_FC2_W], w.dbig, nullptr, 4 * d, rows, d, 4 * d, st));
-      gelu_bwd_kernel<AT><<<cdiv(u, 256), 256, 0, st>>>(w.hpre[blk], w.dbig, w.dbig16, u);
-      MRNB_CHECK_LAUNCH("gelu_bwd_kernel");
+      if constexpr (TC) {
+        // d(GELU output) leaves the GEMM as bf16 only; GELU' is applied in place on the bf16 tensor
+        MRNB_TRY(gemm_dx_tc(gy.h, gy.ld, P.h[pb + MRNB_PB_FC2_W], nullptr, w.dbig16, 4 * d, rows, d, 4 * d, st));
+        gelu_bwd16_kernel<<<cdiv(u / 2, 256), 256, 0, st>>>(w.hpre[blk], w.dbig16, u / 2);
+        MRNB_CHECK_LAUNCH("gelu_bwd16_kernel");
+      } else {
+        MRNB_TRY(gemm_dx<AT>(gy, P.p[pb + MRNB_PB_FC2_W], P.h[pb + MRNB_PB_FC2_W], w.dbig, nullptr, 4 * d, rows, d, 4 * d, st));
+        gelu_bwd_kernel<AT><<<cdiv(u, 256), 256, 0, st>>>(w.hpre[blk], w.dbig, w.dbig16, u);
+        MRNB_CHECK_LAUNCH("gelu_bwd_kernel");
+      }
       Grad gh{w.dbig, w.dbig16, 4L * d};
       if constexpr (TC) MRNB_TRY(launch_colsum<bf16>(w.dbig16, 4 * d, rows, 4 * d, gp(G, pb + MRNB_PB_FC1_B), st));
       else MRNB_TRY(launch_colsum<float>(w.dbig, 4 * d, rows, 4 * d, gp(G, pb + MRNB_PB_FC1_B), st));
