@@ -520,7 +520,7 @@ int crnn_train_backward_t(const MrnbCrnnTrainPack& P, const MrnbCrnnTrainPack& G
   Grad dlog{dlogits, nullptr, ldg};
   if (TC) {
     const long ld16 = (C + 7) / 8 * 8, total = (long)M * ld16;
-    cast_pad_rows_kernel<<<cdiv(total, 256), 256, 0, st>>>(dlogits, ldg, C, w.dlog16, ld16, total);
+    cast_pad_rows_kernel<<<cdiv(total / 8, 256), 256, 0, st>>>(dlogits, ldg, C, w.dlog16, ld16, total);
     MRNB_CHECK_LAUNCH("cast_pad_rows_kernel");
     dlog = Grad{dlogits, w.dlog16, ld16};
   }

@@ -204,13 +204,36 @@ int gemm_dw(const Grad& dY, const AT* X, long ldx, float* dW, int rows, int N, i
   else return gemm_dw_tc(dY.h, dY.ld, X, ldx, dW, rows, N, K, st);
 }
 
-// fp32 [rows, C] (ld) -> bf16 [rows, ld16], columns C..ld16 zero
+// fp32 [rows, C] (ld; vector loads when it is a multiple of 4) -> bf16 [rows, ld16] (a multiple of 8), columns C..ld16 zero; eight columns per thread
 __global__ void cast_pad_rows_kernel(const float* __restrict__ x, long ld, int C, bf16* __restrict__ y, long ld16, long total) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const long r = i / ld16;
-  const int c = (int)(i % ld16);
-  y[i] = __float2bfloat16_rn(c < C ? x[r * ld + c] : 0.f);
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;          // one group of 8 output columns
+  const long per_row = ld16 / 8;
+  if (i >= total / 8) return;
+  const long r = i / per_row;
+  const int c = (int)(i % per_row) * 8;
+  float v[8];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int cc = c + 4 * h;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((ld & 3) == 0 && cc + 4 <= ld) {
+      t = *reinterpret_cast<const float4*>(x + r * ld + cc);
+    } else {                                               // unaligned rows: scalar loads
+      const float* s = x + r * ld + cc;
+      if (cc < C) t.x = s[0];
+      if (cc + 1 < C) t.y = s[1];
+      if (cc + 2 < C) t.z = s[2];
+      if (cc + 3 < C) t.w = s[3];
+    }
+    v[4 * h] = cc < C ? t.x : 0.f; v[4 * h + 1] = cc + 1 < C ? t.y : 0.f;
+    v[4 * h + 2] = cc + 2 < C ? t.z : 0.f; v[4 * h + 3] = cc + 3 < C ? t.w : 0.f;
+  }
+  uint32_t pk[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * u], v[2 * u + 1]);
+    pk[u] = *reinterpret_cast<uint32_t*>(&hh);
+  }
+  *reinterpret_cast<uint4*>(y + r * ld16 + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
-
 }  // namespace

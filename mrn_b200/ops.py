@@ -787,11 +787,12 @@ def ctc_lattice(lpe, targets, lengths, zlab=None, E=None, grad_scale=0.0, want_d
 
 def ctc_dense_grad(logits_view, lse, occ, nll, targets, lengths, grad_scale):
     B, T, Cc = logits_view.shape
-    grad = torch.empty(B, T, Cc, device=lse.device, dtype=torch.float32)
+    ld = round_up(Cc, 4)                     # 16-byte aligned rows for the consumers' vector loads
+    buf = torch.empty(B, T, ld, device=lse.device, dtype=torch.float32)
     L.check(L.load().mrnb_ctc_dense_grad(_p(logits_view), logits_view.stride(1), _p(lse), _p(occ), _p(nll), _p(targets),
-                                         _p(lengths), targets.shape[1], B, T, Cc, float(grad_scale), _p(grad), Cc, _stream()),
+                                         _p(lengths), targets.shape[1], B, T, Cc, float(grad_scale), _p(buf), ld, _stream()),
             "ctc_dense_grad")
-    return grad
+    return buf[:, :, :Cc]
 
 
 def greedy_decode(amax, maxprob):
