@@ -72,3 +72,33 @@ def test_cuda_resize_rejects_unsupported_shrink_factor():
     from mrn_b200 import data
     with pytest.raises(RuntimeError, match="shrinks"):
         data.resize_normalize_batch([np.zeros((8, 9000, 4), dtype=np.uint8)], 256, 32)
+
+
+@pytest.mark.gpu
+def test_cuda_resize_randomised_sizes_and_extremes_match_the_oracle():
+    """Forty-odd ragged sizes incl. the extremes the tap tables allow (1 x 1, one-pixel-wide / -high strips, 3900-pixel
+    wide lines that shrink 15x, 1000-pixel tall crops, the identity size, constant and saturated images, every alpha
+    pattern): every output byte equals the Pillow-pinned oracle."""
+    from mrn_b200 import data
+    rng = np.random.default_rng(2025)
+    sizes = [(1, 1), (1, 300), (300, 1), (3900, 10), (40, 1000), (256, 32), (255, 32), (256, 31), (257, 33), (512, 64),
+             (128, 16), (2, 2), (7, 5), (1024, 128), (33, 999)]
+    sizes += [(int(rng.integers(1, 1200)), int(rng.integers(1, 200))) for _ in range(28)]
+    imgs = []
+    for k, (w, h) in enumerate(sizes):
+        kind = k % 5
+        if kind == 0:
+            im = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8)
+        elif kind == 1:
+            im = np.full((h, w, 4), 255, dtype=np.uint8)
+        elif kind == 2:
+            im = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8); im[..., 3] = 255
+        elif kind == 3:
+            im = rng.integers(0, 2, size=(h, w, 4), dtype=np.uint8) * 255
+        else:
+            im = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8); im[..., 3] = rng.integers(0, 4, size=(h, w)) * 85
+        imgs.append(np.ascontiguousarray(im))
+    got = data.resize_normalize_batch(imgs, 256, 32).cpu().numpy()
+    for k, im in enumerate(imgs):
+        ref = R.resize_normalize(im, 256, 32)
+        assert np.array_equal(got[k], ref), (sizes[k], float(np.abs(got[k] - ref).max()))
