@@ -24,8 +24,11 @@ def test_oracle_matches_committed_pillow_outputs_bit_exactly():
 def test_oracle_matches_live_pillow_and_torch_normalisation():
     Image = pytest.importorskip("PIL.Image")
     rng = np.random.default_rng(3)
-    for (w, h) in [(77, 21), (256, 32), (410, 64), (3, 200), (256, 16)]:
+    for (w, h) in [(77, 21), (256, 32), (410, 64), (3, 200), (256, 16), (1, 1), (1, 300), (300, 1), (3900, 10), (40, 1000),
+                   (33, 999), (257, 33)]:
         im = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8)
+        if (w + h) % 2:
+            im[..., 3] = rng.integers(0, 4, size=(h, w)) * 85
         ref = np.array(Image.fromarray(im, "RGBA").resize((256, 32), Image.BICUBIC))
         assert np.array_equal(R.resize_rgba_bicubic(im, 256, 32), ref), (w, h)
         t = torch.from_numpy(ref).permute(2, 0, 1).contiguous().to(torch.float32).div(255)      # torchvision ToTensor
