@@ -466,9 +466,9 @@ class MRN(object):
         def stage(batch):
             image_tensors, labels, indexs = batch
             li, ll = self.converter.encode(labels, batch_max_length=self.opt.batch_max_length, device="cpu")
-            pf.submit((image_tensors.pin_memory() if not image_tensors.is_pinned() else image_tensors,
-                       li.pin_memory(), ll.pin_memory(),
-                       _domain_ids(indexs).pin_memory()))
+            # images come pinned from a DataLoader(pin_memory=True) (then the copy overlaps the running step); pageable
+            # batches are copied synchronously by the driver -- pinning 33 MB per step here would cost more than it saves
+            pf.submit((image_tensors, li, ll, _domain_ids(indexs)))
         if start_iter + 1 <= n_iter:
             stage(train_loader.get_batch2())
         for iteration in range(start_iter + 1, n_iter + 1):
