@@ -376,10 +376,18 @@ class MRN(object):
         start_time = time.time()
         best_score = -1
         self.begin_expert_training()
+        pf = DevicePrefetcher(self.device)
+
+        def stage(batch):
+            image_tensors, labels = batch
+            li, ll = self.converter.encode(labels, batch_max_length=self.opt.batch_max_length, device="cpu")
+            pf.submit((image_tensors, li, ll))
+        if start_iter + 1 <= self.opt.num_iter:
+            stage(train_loader.get_batch())
         for iteration in range(start_iter + 1, self.opt.num_iter + 1):
-            image_tensors, labels = train_loader.get_batch()
-            image = image_tensors.to(self.device, non_blocking=True)
-            labels_index, labels_length = self.converter.encode(labels, batch_max_length=self.opt.batch_max_length)
+            image, labels_index, labels_length = pf.take()
+            if iteration < self.opt.num_iter:
+                stage(train_loader.get_batch())             # H2D of the next batch overlaps this step's kernels
             step = self.train_step_stage0_graphed if getattr(self.opt, "cuda_graph", True) else self.train_step_stage0
             loss = step(image, labels_index, labels_length)
             train_loss_avg.add(loss)
