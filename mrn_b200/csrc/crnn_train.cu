@@ -102,6 +102,49 @@ int launch_im2col(const float* x, AT* col, int H, int W, int C, int KH, int KW, 
   return MRNB_OK;
 }
 
+// conv0 on the tensor cores (bf16 mode): 3x3 pad-1 im2col of the 4-channel NHWC image with the 36 taps zero-padded to
+// K = 64 (one 128-byte swizzle row): col[(b,oh,ow), (kh,kw,c) | 0...].  Thread = (output pixel, group of 8 columns).
+__global__ void im2col_c4_pad64_kernel(const float* __restrict__ x, bf16* __restrict__ col, int H, int W, long rows) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 8) return;
+  const int j = (int)(i & 7);
+  long r = i >> 3;
+  const int ow = (int)(r % W); r /= W;
+  const int oh = (int)(r % H);
+  const long b = r / H;
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int tap = 2 * j + h;
+    if (tap < 9) {
+      const int ih = oh - 1 + tap / 3, iw = ow - 1 + tap % 3;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+        const float4 t = *reinterpret_cast<const float4*>(x + ((b * H + ih) * W + iw) * 4);
+        v[4 * h] = t.x; v[4 * h + 1] = t.y; v[4 * h + 2] = t.z; v[4 * h + 3] = t.w;
+      }
+    }
+  }
+  uint32_t pk[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * u], v[2 * u + 1]);
+    pk[u] = *reinterpret_cast<uint32_t*>(&hh);
+  }
+  *reinterpret_cast<uint4*>(col + i * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+// [64, 36] fp32 -> [64, 64] bf16 (zero padded);  and back: [64, 64] fp32 gradient -> its first 36 columns
+__global__ void pad_w0_kernel(const float* __restrict__ w, bf16* __restrict__ wp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 64) return;
+  const int o = i >> 6, k = i & 63;
+  wp[i] = __float2bfloat16_rn(k < 36 ? w[o * 36 + k] : 0.f);
+}
+__global__ void unpad_dw0_kernel(const float* __restrict__ dwp, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 36) return;
+  dw[i] = dwp[(i / 36) * 64 + i % 36];
+}
+
 // transpose: dx[b,ih,iw,c] = sum over taps of dcol[(b, ih + pad - kh, iw + pad - kw), (kh,kw,c)]
 __global__ void col2im_s1_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int H, int W, int C, int KH, int KW,
                                  int pad, int Ho, int Wo, long total4) {
@@ -337,7 +380,8 @@ struct CrnnWs {
   float* bsum;            // [2][2048]  b_ih + b_hh
   float *dhn, *dcn;       // [2][B][256]
   float *d0, *d1;         // gradient ping-pong (largest activation)
-  bf16 *d16, *dlog16, *dG16;
+  bf16 *d16, *dlog16, *dG16, *w0pad16;   // w0pad16: conv0 weight [64,64] (36 taps zero padded)
+  float* dw0pad;                         // its gradient [64,64]
   float *dout, *drec;     // [B*63,256], [B*63,512]
   size_t bytes;
 };
@@ -375,6 +419,8 @@ CrnnWs<AT> carve_crnn_ws(char* base, int B, int n_class) {
     w.d16 = W.take<bf16>(max_act);
     w.dlog16 = W.take<bf16>(b * T63 * ((n_class + 7) / 8 * 8));
     w.dG16 = W.take<bf16>(b * T63 * 2048);
+    w.w0pad16 = W.take<bf16>(64 * 64);
+    w.dw0pad = W.take<float>(64 * 64);
   }
   w.bytes = W.off + 4096;
   return w;
@@ -405,7 +451,19 @@ int crnn_train_forward_t(const MrnbCrnnTrainPack& P, const float* image, int B, 
     const long c4 = (long)rows * K / 4;
     const long n = (long)rows * L.Cout;
     float* dst = L.bn >= 0 ? w.raw[L.bn] : w.act[l];
-    if (l == 0) {          // K = 36: CUDA cores in both modes
+    if (l == 0 && TC) {    // K = 36 zero-padded to 64: one swizzled k-block on the tensor cores
+      im2col_c4_pad64_kernel<<<cdiv((long)rows * 8, 256), 256, 0, st>>>(in, reinterpret_cast<bf16*>(w.col), L.H, L.W, rows);
+      MRNB_CHECK_LAUNCH("im2col_c4_pad64_kernel");
+      pad_w0_kernel<<<16, 256, 0, st>>>(P.p[L.w_slot], w.w0pad16);
+      MRNB_CHECK_LAUNCH("pad_w0_kernel");
+      LinearArgs a{};
+      a.A = w.col; a.lda = 64; a.a_gstride = (long)rows * 64;
+      a.W16 = w.w0pad16; a.w_gstride = 64 * 64;
+      a.bias = P.p[L.b_slot]; a.bias_gstride = 64;
+      a.out = dst; a.ldo = 64; a.o_gstride = (long)rows * 64; a.out_is_f32 = 1; a.relu = 1;
+      a.M = rows; a.N = 64; a.K = 64; a.groups = 1;
+      MRNB_TRY(linear<AT>(a, st));
+    } else if (l == 0) {   // fp32 mode: CUDA cores
       float* colf = reinterpret_cast<float*>(w.dcol);
       im2col_s1_kernel<float><<<cdiv(c4, 256), 256, 0, st>>>(in, colf, L.H, L.W, L.Cin, L.KH, L.KW, L.pad, Ho, Wo, c4);
       MRNB_CHECK_LAUNCH("im2col_s1_kernel");
@@ -592,7 +650,7 @@ int crnn_train_backward_t(const MrnbCrnnTrainPack& P, const MrnbCrnnTrainPack& G
     const int Ho = out_h(L), Wo = out_w(L), K = L.KH * L.KW * L.Cin;
     const int rows = B * Ho * Wo;
     const long n = (long)rows * L.Cout;
-    bf16* d16 = TC && l > 0 ? w.d16 : nullptr;
+    bf16* d16 = TC ? w.d16 : nullptr;
     // through pool + relu (or relu alone) to the conv / BN output
     if (L.ph * L.pw > 1) {
       const long np = n / (L.ph * L.pw);
@@ -621,6 +679,15 @@ int crnn_train_backward_t(const MrnbCrnnTrainPack& P, const MrnbCrnnTrainPack& G
     if (L.b_slot >= 0) MRNB_TRY(launch_colsum<float>(d, L.Cout, rows, L.Cout, gpt(G, L.b_slot), st));
     const float* in = l == 0 ? w.img4 : w.pool[l - 1];
     const long c4 = (long)rows * K / 4;
+    if (l == 0 && TC) {
+      im2col_c4_pad64_kernel<<<cdiv((long)rows * 8, 256), 256, 0, st>>>(in, reinterpret_cast<bf16*>(w.col), L.H, L.W, rows);
+      MRNB_CHECK_LAUNCH("im2col_c4_pad64_kernel");
+      cudaMemsetAsync(w.dw0pad, 0, 64 * 64 * sizeof(float), st);
+      MRNB_TRY(gemm_dw_tc(d16, 64, reinterpret_cast<const bf16*>(w.col), 64, w.dw0pad, rows, 64, 64, st));
+      unpad_dw0_kernel<<<9, 256, 0, st>>>(w.dw0pad, gpt(G, L.w_slot));
+      MRNB_CHECK_LAUNCH("unpad_dw0_kernel");
+      break;
+    }
     if (l == 0) {
       float* colf = w.dcol;
       im2col_s1_kernel<float><<<cdiv(c4, 256), 256, 0, st>>>(in, colf, L.H, L.W, L.Cin, L.KH, L.KW, L.pad, Ho, Wo, c4);
