@@ -51,6 +51,47 @@ __global__ void im2col_img_kernel(const float* __restrict__ img, float* __restri
   col[i] = (ih >= 0 && ih < 32 && iw >= 0 && iw < 256) ? __ldg(img + ((b * 4 + c) * 32 + ih) * 256 + iw) : 0.f;
 }
 
+// the same columns in bf16, zero-padded from 36 to K = 64 (one swizzled k-block of the tensor-core GEMM); thread = 8 columns
+__global__ void im2col_img_pad64_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ col, long rows) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 8) return;
+  const int j = (int)(i & 7);
+  long r = i >> 3;
+  const int ow = (int)(r % 128); r /= 128;
+  const int oh = (int)(r % 16);
+  const long b = r / 16;
+  uint32_t pk[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int k = j * 8 + u * 2 + e;
+      v[e] = 0.f;
+      if (k < 36) {
+        const int c = k / 9, kh = (k % 9) / 3, kw = k % 3;
+        const int ih = oh * 2 - 1 + kh, iw = ow * 2 - 1 + kw;
+        if (ih >= 0 && ih < 32 && iw >= 0 && iw < 256) v[e] = __ldg(img + ((b * 4 + c) * 32 + ih) * 256 + iw);
+      }
+    }
+    __nv_bfloat162 hh = __floats2bfloat162_rn(v[0], v[1]);
+    pk[u] = *reinterpret_cast<uint32_t*>(&hh);
+  }
+  *reinterpret_cast<uint4*>(col + i * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+// conv0 weight [32, 36] fp32 -> [32, 64] bf16 zero padded; its gradient [32, 64] fp32 -> the first 36 columns
+__global__ void pad_w0_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 32 * 64) return;
+  const int o = i >> 6, k = i & 63;
+  wp[i] = __float2bfloat16_rn(k < 36 ? w[o * 36 + k] : 0.f);
+}
+__global__ void unpad_dw0_kernel(const float* __restrict__ dwp, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 32 * 36) return;
+  dw[i] = dwp[(i / 36) * 64 + i % 36];
+}
+
 // 3x3 pad-1 convolution with stride (sh, sw) over NHWC x[B,H,W,C]: col[(b,oh,ow), (kh,kw,c)]
 template <typename OT>
 __global__ void im2col_nhwc_kernel(const float* __restrict__ x, OT* __restrict__ col, int H, int W, int C, int Ho, int Wo,
@@ -688,6 +729,7 @@ struct TrainWs {
   float *dxa, *dy, *dbig, *dqkv, *datt, *dln, *Dbuf, *dfeat;
   bf16 *dy16, *dbig16, *dqkv16, *dfeat16, *dlog16, *datt16;   // bf16 mode: GEMM-operand copies of the gradients
   bf16 *P[12], *dS16;                                    // bf16 mode: attention probabilities (kept), dS scratch
+  bf16* w0pad16; float* dw0pad;                          // bf16 mode: conv0 weight [32,64] (36 taps zero padded) / its gradient
   size_t bytes;
 };
 
@@ -727,6 +769,7 @@ TrainWs<AT> carve_train_ws(char* base, int B, int n_class) {
     for (int s = 0; s < 3; ++s)
       for (int j = 0; j < DEPTH[s]; ++j, ++k) w.P[k] = W.take<bf16>((size_t)B * 32768 / DIMS[s] * (32768 / DIMS[s]) * HEADS[s]);
     w.dS16 = W.take<bf16>((size_t)B * 2 * 512 * 512);
+    w.w0pad16 = W.take<bf16>(32 * 64); w.dw0pad = W.take<float>(32 * 64);
   }
   w.bytes = W.off + 4096;
   return w;
@@ -749,12 +792,27 @@ int train_forward_t(const MrnbSvtrPack& P, const float* image, int B, int bn_bat
   if (bn_batch) cudaMemsetAsync(w.stats, 0, 96 * 2 * sizeof(double), st);
   {
     mrnb_prof_begin(MRNB_PROF_CONV, st, 0.0, 0.0);
-    const long total = (long)B * 2048 * 36;
-    im2col_img_kernel<<<cdiv(total, 256), 256, 0, st>>>(image, w.colf, total);
-    MRNB_CHECK_LAUNCH("im2col_img_kernel");
-    MrnbGemm g = mrnb_gemm_nt(w.colf, 36, P.p[MRNB_P_CONV0_W], 36, w.raw0, 32, B * 2048, 32, 36);
-    g.bias_n = P.p[MRNB_P_CONV0_B];
-    MRNB_TRY(mrnb_sgemm(g, st));
+    if constexpr (sizeof(AT) == 2) {
+      // conv0 (K = 36) on the tensor cores: bf16 im2col zero-padded to one 64-wide k-block, N = 32 inside a 64-wide tile
+      const long rows0 = (long)B * 2048;
+      im2col_img_pad64_kernel<<<cdiv(rows0 * 8, 256), 256, 0, st>>>(image, w.big, rows0);
+      MRNB_CHECK_LAUNCH("im2col_img_pad64_kernel");
+      pad_w0_kernel<<<8, 256, 0, st>>>(P.p[MRNB_P_CONV0_W], w.w0pad16);
+      MRNB_CHECK_LAUNCH("pad_w0_kernel");
+      MrnbTcGemm2 g0{};
+      g0.a = mrnb_operand_k2d(w.big, rows0, 64, 64, 128, 1);
+      g0.b = mrnb_operand_k2d(w.w0pad16, 32, 64, 64, 64, 1);
+      g0.out32 = w.raw0; g0.cm = mrnb_axis(32); g0.cn = mrnb_axis(1); g0.bias_n = P.p[MRNB_P_CONV0_B];
+      g0.M = (int)rows0; g0.N = 32; g0.K = 64; g0.groups = 1; g0.splitk = 1; g0.alpha = 1.f;
+      MRNB_TRY(mrnb_tc_gemm2(g0, st));
+    } else {
+      const long total = (long)B * 2048 * 36;
+      im2col_img_kernel<<<cdiv(total, 256), 256, 0, st>>>(image, w.colf, total);
+      MRNB_CHECK_LAUNCH("im2col_img_kernel");
+      MrnbGemm g = mrnb_gemm_nt(w.colf, 36, P.p[MRNB_P_CONV0_W], 36, w.raw0, 32, B * 2048, 32, 36);
+      g.bias_n = P.p[MRNB_P_CONV0_B];
+      MRNB_TRY(mrnb_sgemm(g, st));
+    }
     if (bn_batch) MRNB_TRY(launch_colstats(w.raw0, (long)B * 2048, 32, w.stats, st));
     bn_finalize_train_kernel<<<1, 64, 0, st>>>(w.stats, P.p[MRNB_P_BN0_W], P.p[MRNB_P_BN0_B], (float*)P.p[MRNB_P_BN0_MEAN],
                                                (float*)P.p[MRNB_P_BN0_VAR], w.ss, w.mr, 32, (double)B * 2048, bn_batch,
@@ -1000,13 +1058,22 @@ int train_backward_t(const MrnbSvtrPack& P, const MrnbSvtrPack& G, const float* 
     bn_bwd_reduce_kernel<<<dim3(1, chunks), dim3(32, 8), 0, st>>>(w.raw0, dact0, w.ss, w.mr, r0, 32, w.bsums);
     MRNB_CHECK_LAUNCH("bn_bwd_reduce_kernel");
     bn_bwd_apply_kernel<<<cdiv(n0, 256), 256, 0, st>>>(w.raw0, dact0, w.ss, w.mr, w.bsums, (double)r0, bn_batch,
-                                                       gp(G, MRNB_P_BN0_W), gp(G, MRNB_P_BN0_B), 32, n0);
+                                                       gp(G, MRNB_P_BN0_W), gp(G, MRNB_P_BN0_B), 32, n0, TC ? w.dbig16 : nullptr);
     MRNB_CHECK_LAUNCH("bn_bwd_apply_kernel");
     MRNB_TRY(launch_colsum<float>(dact0, 32, r0, 32, gp(G, MRNB_P_CONV0_B), st));
-    const long total = r0 * 36;
-    im2col_img_kernel<<<cdiv(total, 256), 256, 0, st>>>(image, w.colf, total);
-    MRNB_CHECK_LAUNCH("im2col_img_kernel");
-    MRNB_TRY(gemm_dw_f32(dact0, 32, w.colf, 36, gp(G, MRNB_P_CONV0_W), (int)r0, 32, 36, st));
+    if constexpr (TC) {
+      im2col_img_pad64_kernel<<<cdiv(r0 * 8, 256), 256, 0, st>>>(image, w.big, r0);
+      MRNB_CHECK_LAUNCH("im2col_img_pad64_kernel");
+      cudaMemsetAsync(w.dw0pad, 0, 32 * 64 * sizeof(float), st);
+      MRNB_TRY(gemm_dw_tc(w.dbig16, 32, w.big, 64, w.dw0pad, (int)r0, 32, 64, st));
+      unpad_dw0_kernel<<<5, 256, 0, st>>>(w.dw0pad, gp(G, MRNB_P_CONV0_W));
+      MRNB_CHECK_LAUNCH("unpad_dw0_kernel");
+    } else {
+      const long total = r0 * 36;
+      im2col_img_kernel<<<cdiv(total, 256), 256, 0, st>>>(image, w.colf, total);
+      MRNB_CHECK_LAUNCH("im2col_img_kernel");
+      MRNB_TRY(gemm_dw_f32(dact0, 32, w.colf, 36, gp(G, MRNB_P_CONV0_W), (int)r0, 32, 36, st));
+    }
     mrnb_prof_end(MRNB_PROF_CONV, st);
   }
   return MRNB_OK;
