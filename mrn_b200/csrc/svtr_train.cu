@@ -787,8 +787,9 @@ int train_forward_t(const MrnbSvtrPack& P, const float* image, int B, int bn_bat
   TrainWs<AT> w = carve_train_ws<AT>((char*)ws, B, P.n_class[0]);
   MRNB_CHECK_ARG(ws_bytes >= w.bytes, "svtr_train_forward: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
   const long u = (long)B * 32768;
-  // ---- patch embedding: conv0 -> BN -> GELU -> conv1 -> BN -> GELU -> + pos_embed  (fp32 in both modes: K = 36 / 288,
-  //      0.9 % of the step's FLOPs, and the BatchNorm statistics want the fp32 convolution output)
+  // ---- patch embedding: conv0 -> BN -> GELU -> conv1 -> BN -> GELU -> + pos_embed.  bf16 mode: both convolutions are
+  //      bf16 im2col x tcgen05 GEMM (K = 36 zero-padded to 64, K = 288 rounded up by TMA zero-fill) with fp32 outputs;
+  //      the BatchNorm statistics are taken from those fp32 outputs in fp64.
   if (bn_batch) cudaMemsetAsync(w.stats, 0, 96 * 2 * sizeof(double), st);
   {
     mrnb_prof_begin(MRNB_PROF_CONV, st, 0.0, 0.0);
