@@ -63,3 +63,45 @@ def test_mean_of_shard_means_equals_global_mean():
     full = (nll / lens).mean()
     halves = [(nll[i * 32:(i + 1) * 32] / lens[i * 32:(i + 1) * 32]).mean() for i in range(2)]
     assert abs(float(full) - float(sum(halves) / 2)) < 1e-12
+
+
+def _worker_stage0(rank, world, port, out):
+    """Each rank: oracle stage-0 gradients of its shard (eval-mode BatchNorm) flattened into one arena, averaged over gloo."""
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    from mrn_b200 import dist as mdist
+    from oracle import mrn_oracle as O
+    from oracle import synth
+    mdist.init_from_env("gloo")
+    cc, B, seed = (29,), 4, 41
+    sd = synth.synth_state_dict(cc, seed, arch="crnn")
+    img, tgt, lens, _ = synth.synth_batch(B, cc, seed)
+    lo, hi = mdist.shard_bounds(B, rank, world)
+    r = O.stage0_loss_and_grads(sd, 0, img[lo:hi], tgt[lo:hi], lens[lo:hi], "eval", None, dtype=torch.float64)
+    keys = sorted(r["grads"])
+    arena = torch.cat([r["grads"][k].reshape(-1) for k in keys] + [r["loss"].reshape(1)])      # the loss rides along
+    mdist.allreduce_mean_(arena)
+    out[rank] = arena
+    torch.distributed.destroy_process_group()
+
+
+def test_gloo_world2_stage0_gradient_arena_equals_the_full_batch():
+    """The stage-0 exchange step (one all-reduce of the expert's flat gradient arena) on two gloo ranks:
+    the averaged shard gradients and loss equal the full-batch oracle step (running-statistics BatchNorm; batch
+    statistics stay per rank, as under nn.DataParallel)."""
+    from oracle import mrn_oracle as O
+    from oracle import synth
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_stage0, args=(world, port, out), nprocs=world, join=True)
+    cc, B, seed = (29,), 4, 41
+    sd = synth.synth_state_dict(cc, seed, arch="crnn")
+    img, tgt, lens, _ = synth.synth_batch(B, cc, seed)
+    r = O.stage0_loss_and_grads(sd, 0, img, tgt, lens, "eval", None, dtype=torch.float64)
+    keys = sorted(r["grads"])
+    ref = torch.cat([r["grads"][k].reshape(-1) for k in keys] + [r["loss"].reshape(1)])
+    assert torch.equal(out[0], out[1])
+    assert float((out[0] - ref).abs().max()) < 1e-9 * max(1.0, float(ref.abs().max()))
