@@ -116,6 +116,52 @@ __global__ void im2col_nhwc_kernel(const float* __restrict__ x, OT* __restrict__
   }
 }
 
+// bf16 variant, eight channels per thread (two 16-byte loads, one 16-byte store), channel count as a template parameter
+template <int C>
+__global__ void __launch_bounds__(256)
+im2col_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int H, int W, int Ho, int Wo, int sh,
+                        int sw, long pairs) {
+  constexpr int G = C / 8;
+  const long pair = (long)blockIdx.x * (256 / G) + threadIdx.x / G;      // (output pixel, tap)
+  if (pair >= pairs) return;
+  const int c = (threadIdx.x % G) * 8;
+  const int tap = (int)(pair % 9);
+  long r = pair / 9;
+  const int ow = (int)(r % Wo); r /= Wo;
+  const int oh = (int)(r % Ho);
+  const long b = r / Ho;
+  const int ih = oh * sh - 1 + tap / 3, iw = ow * sw - 1 + tap % 3;
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+    const float4* src = reinterpret_cast<const float4*>(x + ((b * H + ih) * W + iw) * C + c);
+    const float4 v0 = src[0], v1 = src[1];
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v0.x, v0.y), h1 = __floats2bfloat162_rn(v0.z, v0.w);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(v1.x, v1.y), h3 = __floats2bfloat162_rn(v1.z, v1.w);
+    o = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2),
+                   *reinterpret_cast<uint32_t*>(&h3));
+  }
+  *reinterpret_cast<uint4*>(col + pair * C + c) = o;
+}
+
+template <typename AT>
+int launch_im2col_nhwc(const float* x, AT* col, int H, int W, int C, int Ho, int Wo, int sh, int sw, long rows, cudaStream_t st) {
+  if constexpr (sizeof(AT) == 2) {
+    const long pairs = rows * 9;
+#define IM2COL_CASE(C_)                                                                                             \
+    if (C == C_) {                                                                                                  \
+      im2col_nhwc_bf16_kernel<C_><<<cdiv(pairs, 256 / (C_ / 8)), 256, 0, st>>>(x, col, H, W, Ho, Wo, sh, sw, pairs); \
+      MRNB_CHECK_LAUNCH("im2col_nhwc_bf16_kernel");                                                                  \
+      return MRNB_OK;                                                                                               \
+    }
+    IM2COL_CASE(32) IM2COL_CASE(64) IM2COL_CASE(128) IM2COL_CASE(256)
+#undef IM2COL_CASE
+  }
+  const long c4 = rows * 9 * C / 4;
+  im2col_nhwc_kernel<AT><<<cdiv(c4, 256), 256, 0, st>>>(x, col, H, W, C, Ho, Wo, sh, sw, c4);
+  MRNB_CHECK_LAUNCH("im2col_nhwc_kernel");
+  return MRNB_OK;
+}
+
 // transpose of the above: dx[b,ih,iw,c] = sum over the (oh,ow,tap) that read this pixel of dcol
 __global__ void col2im_nhwc_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int H, int W, int C, int Ho,
                                    int Wo, int sh, int sw, long total4) {
@@ -826,8 +872,7 @@ int train_forward_t(const MrnbSvtrPack& P, const float* image, int B, int bn_bat
     if constexpr (sizeof(AT) == 2) {
       // conv1 (K = 288) on the tensor cores: bf16 im2col, the contraction rounded up to 320 (TMA zero-fills both operands)
       MRNB_CHECK_ARG(P.h[MRNB_P_CONV1_W], "svtr_train: bf16 mode needs the 16-bit weight shadow");
-      im2col_nhwc_kernel<AT><<<cdiv(c4, 256), 256, 0, st>>>(w.act0, w.big, 16, 128, 32, 8, 64, 2, 2, c4);
-      MRNB_CHECK_LAUNCH("im2col_nhwc_kernel");
+      MRNB_TRY(launch_im2col_nhwc<AT>(w.act0, w.big, 16, 128, 32, 8, 64, 2, 2, (long)B * 512, st));
       MrnbTcGemm2 g1{};
       g1.a = mrnb_operand_k2d(w.big, (long)B * 512, 288, 288, 128, 1);
       g1.b = mrnb_operand_k2d(P.h[MRNB_P_CONV1_W], 64, 288, 288, 64, 1);
@@ -880,8 +925,7 @@ int train_forward_t(const MrnbSvtrPack& P, const float* image, int B, int bn_bat
     const int orows = B * Ho * Wd;
     const int ps = MRNB_P_SUB0 + s * MRNB_PS_COUNT;
     const long c4 = (long)orows * 9 * d / 4;
-    im2col_nhwc_kernel<AT><<<cdiv(c4, 256), 256, 0, st>>>(w.xout[blk - 1], w.big, H, Wd, d, Ho, Wd, 2, 1, c4);
-    MRNB_CHECK_LAUNCH("im2col_nhwc_kernel");
+    MRNB_TRY(launch_im2col_nhwc<AT>(w.xout[blk - 1], w.big, H, Wd, d, Ho, Wd, 2, 1, (long)orows, st));
     MRNB_TRY(lin<AT>(w.big, 9 * d, P.p[ps + MRNB_PS_CONV_W], P.h[ps + MRNB_PS_CONV_W], P.p[ps + MRNB_PS_CONV_B], w.cv[s], Co,
                      true, orows, Co, 9 * d, nullptr, nullptr, 1, st));
     if (s < 2) MRNB_TRY(launch_ln_fwd<float>(w.cv[s], w.stage_in[s + 1], P.p[ps + MRNB_PS_NORM_W], P.p[ps + MRNB_PS_NORM_B], orows, Co, 1e-5f, st));
@@ -945,8 +989,7 @@ int train_backward_t(const MrnbSvtrPack& P, const MrnbSvtrPack& G, const float* 
       Grad gcv{dcv, w.dy16, Co};
       MRNB_TRY(launch_colsum<float>(dcv, Co, orows, Co, gp(G, ps + MRNB_PS_CONV_B), st));
       const long c4 = (long)orows * 9 * d / 4;
-      im2col_nhwc_kernel<AT><<<cdiv(c4, 256), 256, 0, st>>>(w.xout[blk - 1], w.big, H, Wd, d, Ho, Wd, 2, 1, c4);
-      MRNB_CHECK_LAUNCH("im2col_nhwc_kernel");
+      MRNB_TRY(launch_im2col_nhwc<AT>(w.xout[blk - 1], w.big, H, Wd, d, Ho, Wd, 2, 1, (long)orows, st));
       MRNB_TRY(gemm_dw<AT>(gcv, w.big, 9 * d, gp(G, ps + MRNB_PS_CONV_W), orows, Co, 9 * d, st));
       MRNB_TRY(gemm_dx<AT>(gcv, P.p[ps + MRNB_PS_CONV_W], P.h[ps + MRNB_PS_CONV_W], w.dbig, nullptr, 9 * d, orows, Co, 9 * d, st));
       col2im_nhwc_kernel<<<cdiv(u / 4, 256), 256, 0, st>>>(w.dbig, dx, H, Wd, d, Ho, Wd, 2, 1, u / 4);
@@ -1040,8 +1083,7 @@ int train_backward_t(const MrnbSvtrPack& P, const MrnbSvtrPack& G, const float* 
     MRNB_TRY(launch_colsum<float>(dx, 64, r1, 64, gp(G, MRNB_P_CONV1_B), st));
     const long c4 = r1 * 288 / 4;
     if constexpr (TC) {
-      im2col_nhwc_kernel<AT><<<cdiv(c4, 256), 256, 0, st>>>(w.act0, w.big, 16, 128, 32, 8, 64, 2, 2, c4);
-      MRNB_CHECK_LAUNCH("im2col_nhwc_kernel");
+      MRNB_TRY(launch_im2col_nhwc<AT>(w.act0, w.big, 16, 128, 32, 8, 64, 2, 2, (long)B * 512, st));
       MRNB_TRY(gemm_dw_tc(w.dy16, 64, w.big, 288, gp(G, MRNB_P_CONV1_W), (int)r1, 64, 288, st));
       MRNB_TRY(gemm_dx_tc(w.dy16, 64, P.h[MRNB_P_CONV1_W], w.dbig, nullptr, 288, (int)r1, 64, 288, st));
     } else {
