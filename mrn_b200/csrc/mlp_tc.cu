@@ -241,7 +241,10 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     constexpr int OW = D / 2;                                  // output columns per warp
     constexpr int NPASS = OW / 32;                             // 32-column passes of the final epilogue: 1, 2, 4
     const int p8 = lane & 7, rsel = lane >> 3;                 // final epilogue: 8 lanes per 32-column row segment
-    float* stg = reinterpret_cast<float*>(sP) + (size_t)ew * 1024;   // 32 rows x 32 floats, 16B pieces XOR-swizzled by row
+    // 32 rows x 32 floats, 16B pieces XOR-swizzled by row.  The staging tile aliases exactly the 4 KiB of sP this warp
+    // itself writes P into (rows q*32.. of K-half ch): a warp that runs ahead into the next tile's first P chunk can
+    // then only overwrite its own (already consumed) staging, never a slower warp's.
+    float* stg = reinterpret_cast<float*>(sP + (size_t)ch * TILE16K + (size_t)q * 4096);
     int i = 0;
     int cur_g = -1;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
