@@ -3,7 +3,7 @@
 
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
-    python bench.py --impl reference ...      # the reference algorithm's CPU path (oracle port) on the host cores
+    python bench.py --impl reference ...      # the UNMODIFIED reference (baseline/_ref) running its own stage-1 loop on the host cores
 
 Workload (BASELINE.json configs[3], SURVEY.md §8d cfg 4): SVTR-MRN, I = 6 experts, union charset C_i =
 [1899, 2224, 3844, 4968, 5041, 5153], per-GPU batch 256 (weak scaling), synthetic 32x256x4 crops, one
@@ -44,8 +44,12 @@ def parse():
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (config/svtr_mrn.py: batch_size=256)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--chunk", type=int, default=0, help="samples per expert-forward chunk (0 = whole batch)")
-    ap.add_argument("--cpu-sample", type=int, default=32, help="samples per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="samples per CPU step (0 = the full per-GPU batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the eager-torch reference on the same GPU (N=1 only)")
+    ap.add_argument("--no-parity-probe", action="store_true", help="skip the first-step comparison with the CPU oracle (N=1 only)")
+    ap.add_argument("--init", default="ctor", choices=["ctor", "synth"],
+                    help="ctor: random-init weights from the constructors (BASELINE north_star, soft gates); synth: gate-spreading fixtures")
     ap.add_argument("--arch", default="svtr", choices=["svtr", "crnn"],
                     help="expert recogniser: svtr = headline (BASELINE.json configs[3-4]); crnn = VGG+BiLSTM (configs[1])")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph replay of the step")
@@ -157,22 +161,72 @@ def cpu_stage0(sample, steps, warmup, arch="svtr"):
     return sample * steps / dt, dt / steps * 1000.0, torch.get_num_threads()
 
 
+def workload_config(arch, B, world, chunk, precision):
+    return {"workload": "%s-MRN 6-expert stage-1 (router-training) step, B=%d/GPU, union charset 5153, 32x256x4 crops, "
+                        "experts frozen in train mode (BN batch stats%s)" % (arch.upper(), B, " + DropPath" if arch == "svtr" else ""),
+            "global_batch": B * world, "parallelism": "dp%d" % world, "expert_chunk": chunk,
+            "init": "random-init weights from the constructors (soft gates)",
+            "l2": "4 rotating input batches; >1 GB of activations streamed per step (>> 126 MB L2), no explicit flush",
+            "router_precision": "bf16 operands / fp32 accumulate (tcgen05)" if precision == "bf16" else "fp32",
+            "expert_precision": precision}
+
+
+def ref_arm(device, B, steps, warmup, gpu_index=0, timeout=1500):
+    """Runs baseline/ref_arm.py (the unmodified reference's own stage-1 loop from baseline/_ref) in a child process and
+    returns its JSON dict; {"unavailable": why} when the reference is not staged."""
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    if device == "cuda":
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        env["CUDA_VISIBLE_DEVICES"] = vis.split(",")[gpu_index] if vis else str(gpu_index)
+    cmd = [sys.executable, os.path.join(ROOT, "baseline", "ref_arm.py"), "--device", device, "--batch", str(B),
+           "--steps", str(steps), "--warmup", str(warmup)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=timeout)
+        line = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+        if not line:
+            return {"unavailable": "reference arm printed no result (rc %d): %s" % (r.returncode, r.stderr[-300:])}
+        return json.loads(line[-1])
+    except Exception as ex:                              # noqa: BLE001
+        return {"unavailable": "reference arm failed: %s" % (ex,)}
+
+
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores.  SVTR: the
+    unmodified reference from baseline/_ref driving MRN._update_representation (kind "reference"); if it is not staged,
+    or for --arch crnn, the oracle port (kind "port")."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    sample = args.cpu_sample
-    v, ms, cores = cpu_stage1(sample, max(1, args.steps), max(0, args.warmup), args.arch)
-    desc = "%d-sample router-training step per iteration (same config, B reduced from 256), fp32, %d threads" % (sample, cores)
-    print(json.dumps({
+    B = args.batch
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    sample = args.cpu_sample or B
+    if not args.cpu_sample and steps + warmup > 30:      # keep the whole run within a few minutes
+        sample = max(32, B // 2)
+    res = ref_arm("cpu", sample, steps, warmup) if args.arch == "svtr" else {"unavailable": "crnn arm uses the port"}
+    if "unavailable" not in res:
+        v, ms, cores, kind = res["samples_per_s"], res["ms_per_step"], res["threads"], "reference"
+        desc = ("%d-sample iterations of the UNMODIFIED reference loop (baseline/_ref: il_modules/mrn.py::_update_representation, "
+                "MRNNet.cross_forward, CTCLoss, Adam, OneCycleLR), fp32, %d threads, torch %s" % (sample, cores, res["torch"]))
+    else:
+        sys.stderr.write("bench.py: %s; timing the oracle port instead\n" % res["unavailable"])
+        sample = min(sample, 32)
+        v, ms, cores = cpu_stage1(sample, steps, warmup, args.arch)
+        kind, desc = "port", "%d-sample router-training step per iteration, oracle port, fp32, %d threads" % (sample, cores)
+    cfg = workload_config(args.arch, B, 1, 0, "fp32")
+    cfg.update({"per_step_samples": sample, "parallelism": "cpu", "router_precision": "fp32", "expert_precision": "fp32"})
+    out = {
         "impl": "reference", "metric": METRIC.replace("SVTR", args.arch.upper()), "value": round(v, 3), "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 2), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s-MRN 6-expert stage-1 (router-training) step, union charset 5153, 32x256x4 crops" % args.arch.upper(),
-                   "per_step_samples": sample, "parallelism": "cpu"},
-        "cpu_baseline": {"value": round(v, 3), "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": round(v, 3), "unit": "samples/s", "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": round(v, 3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }
+    if "unavailable" not in res:
+        out["loss_first"] = {"loss_clf": res.get("loss_clf_first"), "taski_loss": res.get("taski_loss_first")}
+        out["reference_flags"] = res.get("flags")
+    print(json.dumps(out))
 
 
 def ncu_traffic(kernel, arch="svtr"):
@@ -236,7 +290,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     B = args.batch
     opt = make_opt(args.precision, args.chunk, args.arch)
-    sd = synth.synth_state_dict(CLASS_COUNTS, 111, arch=args.arch)
+    sd = (synth.ctor_state_dict if args.init == "ctor" else synth.synth_state_dict)(CLASS_COUNTS, 111, arch=args.arch)
     T = 64 if args.arch == "svtr" else 63
     net = MRNNet(opt)
     for c in CLASS_COUNTS:
@@ -302,6 +356,32 @@ def run_ours(args):
         l1, l2 = train_step(img, tgt, lens, dom)
         return float(l1), float(l2)                     # D2H read of both losses (the reference logs them)
 
+    # ---- parity probe (N = 1, stage-1 train): the FIRST step runs eagerly with injected DropPath masks and is compared
+    # with the fp32 CPU oracle of the same step on the same batch / masks / weights (2e-2 bf16 budget of north_star)
+    probe = None
+    if world == 1 and not infer and not stage0 and not args.no_parity_probe:
+        from oracle import mrn_oracle as O
+        drop = synth.synth_drop_scales(6, B, O.svtr_drop_path_rates(), 111) if args.arch == "svtr" else None
+        sd_o = {k: v.clone() for k, v in sd.items()}
+        img, tgt, lens, dom = resident[0]
+        l1, l2 = learner.train_step_stage1(img, tgt, lens, dom, drop_scales=None if drop is None else drop.to(dev))
+        got = (float(l1), float(l2))
+        torch.set_num_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        ref = O.stage1_step_cpu(sd_o, 6, dict(step=0, m={}, v={}), *host[0], drop_scales=drop)
+        probe = {"loss_first": {"loss_clf": got[0], "taski_loss": got[1]},
+                 "oracle_loss_first": {"loss_clf": ref[0], "taski_loss": ref[1]},
+                 "rel_err_loss_clf": abs(got[0] - ref[0]) / max(abs(ref[0]), 1e-30), "abs_err_taski": abs(got[1] - ref[1]),
+                 "tolerance": 2e-2 if args.precision == "bf16" else 1e-4, "oracle_cpu_s": round(time.perf_counter() - t0, 2)}
+        probe["ok"] = bool(probe["rel_err_loss_clf"] < probe["tolerance"] and probe["abs_err_taski"] < probe["tolerance"])
+        del sd_o
+
+    hist = torch.zeros(3, max(args.steps, 1), 2, device=dev)      # losses of every timed step (checked after each region)
+
+    def record(phase, k, loss):
+        hist[phase, k, 0].copy_(loss[0].float().sum(), non_blocking=True)
+        hist[phase, k, 1].copy_(loss[1].float().sum(), non_blocking=True)
+
     try:
         for k in range(max(3, args.warmup)):
             step_resident(k)
@@ -327,6 +407,7 @@ def run_ours(args):
     e0.record()
     for k in range(args.steps):
         loss = step_resident(k, eager=True)
+        record(0, k, loss)
     e1.record()
     mdist.barrier(); torch.cuda.synchronize()
     ops.profile_enable(False)
@@ -342,6 +423,7 @@ def run_ours(args):
         e0.record()
         for k in range(args.steps):
             loss = step_resident(k)
+            record(1, k, loss)
         e1.record()
         mdist.barrier(); torch.cuda.synchronize()
         ms_total = mdist.max_over_ranks(e0.elapsed_time(e1), dev)
@@ -350,11 +432,22 @@ def run_ours(args):
         step_e2e(k)
     mdist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
+    e2e_losses = []
     for k in range(args.steps):
         last = step_e2e(k)
+        e2e_losses.append(last)
     torch.cuda.synchronize()
     e2e_ms = mdist.max_over_ranks((time.perf_counter() - t0) * 1000.0, dev)
     clocks = sampler.stop() if rank == 0 else None
+    # ---- a step that computes on NaNs is not a measurement: every loss of every timed step must be finite
+    hist_h = hist[: 2 if use_graph else 1, :args.steps].cpu()
+    bad = (not bool(torch.isfinite(hist_h).all())) or any(not (v[0] == v[0] and abs(v[0]) != float("inf") and v[1] == v[1]
+                                                                 and abs(v[1]) != float("inf")) for v in e2e_losses)
+    if bad:
+        sys.stderr.write("bench.py: NON-FINITE LOSS inside the timed region (rank %d): eager %s graph %s e2e %s -- no value is reported\n"
+                         % (rank, hist_h[0].tolist(), hist_h[1].tolist() if use_graph else None, e2e_losses))
+        sys.stderr.flush()
+        os._exit(3)
     if rank != 0:
         return
 
@@ -380,15 +473,23 @@ def run_ours(args):
         if f["bytes"] > 0 and f["ms"] > 0:
             d["gbs"] = round(f["bytes"] / f["ms"] / 1e6, 1)
         fams[name] = d
+    # the expert / router contractions are bounded by the tensor cores, everything else on the path
+    # (gated combine, log-softmax / CTC, LayerNorm, router element-wise stages, optimiser) by HBM bandwidth.
+    TENSOR_BOUND = {"tc_gemm_kernel", "tc_gemm2_kernel", "attn_tc_kernel", "mlp_tc_kernel", "sgemm_kernel", "mixer_tc_kernel",
+                    "patch_embed"}
     dom_name = max(fams, key=lambda k: fams[k]["ms_per_step"]) if fams else None
     roofline = None
+    traffic_db = {}
+    try:
+        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
     if dom_name:
         d, f = fams[dom_name], fam[dom_name]
         n_launch = max(1, f["calls"])
         frac_t = d.get("tflops", 0.0) / tf_peak
         frac_h = d.get("gbs", 0.0) / hbm_peak
-        # the binding roof is the one the kernel sits closer to (small-K contractions are traffic-limited)
-        if frac_t >= frac_h:
+        if dom_name in TENSOR_BOUND:
             roofline = {"kernel": dom_name, "bound": "tensor", "achieved": d.get("tflops"), "peak": tf_peak, "unit": "TFLOP/s",
                         "frac": round(frac_t, 4), "traffic": ncu_traffic(dom_name, args.arch),
                         "algorithmic_flops_per_launch": f["flops"] / n_launch, "peak_source": peak_src + ", sustained"}
@@ -396,22 +497,28 @@ def run_ours(args):
             roofline = {"kernel": dom_name, "bound": "hbm", "achieved": d.get("gbs"), "peak": hbm_peak, "unit": "GB/s",
                         "frac": round(frac_h, 4), "traffic": ncu_traffic(dom_name, args.arch),
                         "algorithmic_bytes_per_launch": f["bytes"] / n_launch, "peak_source": peak_src}
-        roofline.update({"launches_per_step": f["calls"] // args.steps, "avg_launch_us": round(f["ms"] / n_launch * 1e3, 1),
+        roofline.update({"bound_source": "SURVEY.md 8(d)", "launches_per_step": f["calls"] // args.steps,
+                         "avg_launch_us": round(f["ms"] / n_launch * 1e3, 1),
                          "frac_tensor": round(frac_t, 4), "frac_hbm": round(frac_h, 4)})
+        if not infer and not stage0 and args.arch == "svtr":
+            # whole step against the tensor roof: SURVEY.md 8(d) counts 15.20 GFLOP per sample (dense-equivalent attention)
+            step_tf = 15.20e9 * B / (ms_step * 1e-3) / 1e12
+            roofline["step"] = {"gflop_per_sample": 15.20, "tflops": round(step_tf, 1),
+                                "frac_tensor_sustained": round(step_tf / tf_peak, 4),
+                                "dram_bytes_per_step_ncu": traffic_db.get("_step", {}).get("dram_bytes_per_step"),
+                                "dram_bytes_per_step_algorithmic": int(B * (4 * 32 * 256 * 4 + 5.92e6) + 43.4e6 * 2)}
     ctc_router_ms = sum(fams.get(k, {}).get("ms_per_step", 0.0) for k in ("sgemm_kernel", "tc_gemm2_kernel", "router_elementwise",
                                                                           "combine_row_kernel", "ctc_lattice_kernel"))
+    cfg = workload_config(args.arch, B, world, args.chunk, args.precision)
+    if args.init != "ctor":
+        cfg["init"] = "synthetic gate-spreading fixtures (mrn_b200/synth.py)"
     out = {
         "metric": (METRIC if not infer else "MRN-SVTR 6-expert inference + greedy decode samples/s").replace("SVTR", args.arch.upper()),
         "value": round(value, 2),
         "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": "%s-MRN 6-expert stage-1 (router-training) step, B=%d/GPU, union charset 5153, 32x256x4 crops, "
-                               "experts frozen in train mode (BN batch stats%s)" % (args.arch.upper(), B, " + DropPath" if args.arch == "svtr" else ""),
-                   "global_batch": B * world, "parallelism": "dp%d" % world, "expert_chunk": args.chunk,
-                   "l2": "4 rotating input batches; >1 GB of activations streamed per step (>> 126 MB L2), no explicit flush",
-                   "router_precision": "bf16 operands / fp32 accumulate (tcgen05)" if args.precision == "bf16" else "fp32",
-                   "expert_precision": args.precision},
+        "config": cfg,
         "e2e": {"value": round(e2e_value, 2), "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": 8 if not infer else B * T * 4 + B * 8,
                 "ms_per_step": round(e2e_ms / args.steps, 3)},
@@ -423,7 +530,11 @@ def run_ours(args):
         "kernel_families": fams,
         "ctc_router_ms_per_batch": round(ctc_router_ms, 3),
         "loss_clf": float(last[0]), "taski_loss": float(last[1]),
+        "losses_finite": True,
+        "loss_last": {"loss_clf": float(last[0]), "taski_loss": float(last[1])},
     }
+    if probe:
+        out.update({"loss_first": probe["loss_first"], "oracle_loss_first": probe["oracle_loss_first"], "parity_probe": probe})
     if stage0:
         out["metric"] = "MRN-%s stage-0 expert-training samples/s" % args.arch.upper()
         out["dtype"] = "f32" if learner._tp.prec == 0 else "bf16"
@@ -437,15 +548,39 @@ def run_ours(args):
         if args.sweep:
             out["sweep"] = infer_sweep(learner, [int(x) for x in args.sweep.split(",") if x], dev)
     if world == 1 and not args.no_cpu_baseline and stage0:
-        v, ms, cores = cpu_stage0(args.cpu_sample, 2, 1, args.arch)
+        cs = args.cpu_sample or 32
+        v, ms, cores = cpu_stage0(cs, 2, 1, args.arch)
         out["cpu_baseline"] = {"value": round(v, 3), "unit": "samples/s", "cores": cores, "kind": "port",
                                "sample": "2 timed expert-training steps of %d samples, oracle port (torch CPU autograd), fp32, "
-                                         "%d threads" % (args.cpu_sample, cores)}
+                                         "%d threads" % (cs, cores)}
     elif world == 1 and not args.no_cpu_baseline and not infer:
-        v, ms, cores = cpu_stage1(args.cpu_sample, 2, 1, args.arch)
-        out["cpu_baseline"] = {"value": round(v, 3), "unit": "samples/s", "cores": cores, "kind": "port",
-                               "sample": "2 timed router-training steps of %d samples (same config, batch reduced from 256), "
-                                         "oracle port of the reference algorithm, fp32, %d threads" % (args.cpu_sample, cores)}
+        cs = args.cpu_sample or B
+        res = ref_arm("cpu", cs, 2, 1) if args.arch == "svtr" else {"unavailable": "crnn uses the port"}
+        if "unavailable" not in res:
+            out["cpu_baseline"] = {"value": round(res["samples_per_s"], 3), "unit": "samples/s", "cores": res["threads"], "kind": "reference",
+                                   "sample": "1 warm-up + 2 timed %d-sample iterations of the unmodified reference loop (baseline/_ref: "
+                                             "MRN._update_representation), fp32, %d threads" % (cs, res["threads"]),
+                                   "ms_per_step": round(res["ms_per_step"], 1)}
+        else:
+            cs = min(cs, 32)
+            v, ms, cores = cpu_stage1(cs, 2, 1, args.arch)
+            out["cpu_baseline"] = {"value": round(v, 3), "unit": "samples/s", "cores": cores, "kind": "port",
+                                   "sample": "2 timed router-training steps of %d samples (batch reduced from %d), oracle port of the "
+                                             "reference algorithm, fp32, %d threads; %s" % (cs, B, cores, res["unavailable"])}
+    if world == 1 and not args.no_gpu_reference and not infer and not stage0 and args.arch == "svtr":
+        # the GPU bar: the same unmodified reference loop, eager torch library kernels, on this B200
+        del learner, resident
+        torch.cuda.empty_cache()
+        res = ref_arm("cuda", B, 10, 3, gpu_index=local_rank)
+        if "unavailable" in res:
+            out["gpu_eager_reference"] = res
+        else:
+            out["gpu_eager_reference"] = {"value": round(res["samples_per_s"], 2), "unit": "samples/s", "ms_per_step": round(res["ms_per_step"], 3),
+                                          "batch": B, "steps": res["steps"], "warmup": res["warmup"], "flags": res["flags"],
+                                          "torch": res["torch"], "peak_mem_gb": res.get("peak_mem_gb"), "code": res["code"],
+                                          "timing": "wall clock between loader calls with cuda.synchronize (H2D of the batch and loss D2H inside, as in e2e)",
+                                          "speedup_e2e": round(e2e_value / res["samples_per_s"], 2),
+                                          "speedup_resident": round(value / res["samples_per_s"], 2)}
     print(json.dumps(out))
 
 

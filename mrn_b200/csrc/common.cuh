@@ -152,7 +152,7 @@ __device__ __forceinline__ bool mrnb_wait_expired(uint64_t& t0) {
 
 // log(exp(a)+exp(b)) with -inf handling
 __device__ __forceinline__ float log_add(float a, float b) {
-  const float m = fmaxf(a, b);
-  if (m == -INFINITY) return -INFINITY;
+  const float m = fmaxf(a, b);            // fmaxf drops a NaN operand ...
+  if (m == -INFINITY) return a + b;       // ... so (-inf, -inf) -> -inf but (NaN, -inf) -> NaN: a NaN never turns into "impossible"
   return m + log1pf(expf(-fabsf(a - b)));
 }

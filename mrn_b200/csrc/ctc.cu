@@ -636,8 +636,10 @@ ctc_lattice_kernel(const float* __restrict__ lpe,    // [B,T,S1]
   float e_last = __shfl_sync(0xffffffffu, a0, L);
   float e_prev = (L > 0) ? __shfl_sync(0xffffffffu, a1, L - 1) : -INFINITY;
   const float ll = log_add(e_last, e_prev);
-  const bool feasible = (ll != -INFINITY) && isfinite(ll);
-  if (lane == 0) nll[b] = feasible ? -ll : 0.f;          // zero_infinity=True
+  // zero_infinity=True zeroes only an infinite loss (ll == -inf: no valid alignment), exactly like torch.nn.CTCLoss;
+  // a NaN log-likelihood (non-finite logits upstream) must stay visible in the loss and in the gradient.
+  const bool feasible = (ll != -INFINITY);
+  if (lane == 0) nll[b] = feasible ? -ll : 0.f;
   if (!dgate && !occ_col) return;
 
   const float scale = feasible ? grad_scale / (float)max(L, 1) : 0.f;
@@ -732,7 +734,7 @@ ctc_dense_grad_kernel(const float* __restrict__ logits, long ldl, const float* _
       tot = s;
     }
     __syncthreads();
-    feasible = tot > 0.5f;      // occupancies of a feasible row sum to 1
+    feasible = !(tot <= 0.5f);  // occupancies of a feasible row sum to 1; NaN occupancies (NaN loss) stay "feasible" and propagate
   }
   (void)occ0; (void)nll;
   const float scale = feasible ? grad_scale / (float)max(L, 1) : 0.f;

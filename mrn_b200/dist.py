@@ -44,8 +44,11 @@ def allreduce_mean_(arena: torch.Tensor):
     """In-place average of a flat gradient arena across ranks (no-op for a single rank)."""
     w = world_size()
     if w > 1:
-        dist.all_reduce(arena, op=dist.ReduceOp.SUM)
-        arena.div_(w)
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(arena, op=dist.ReduceOp.AVG)      # averaged inside the collective: no separate div_ launch
+        else:                                                 # gloo (CPU tests of the host logic) has no AVG
+            dist.all_reduce(arena, op=dist.ReduceOp.SUM)
+            arena.div_(w)
     return arena
 
 

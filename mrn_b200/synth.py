@@ -192,3 +192,33 @@ def synth_drop_scales(n_experts: int, B: int, rates: Sequence[float], seed: int 
         keep = g.random(size=(n_experts, 2, B)) >= p
         out[:, j] = keep.astype(np.float32) / np.float32(1.0 - p)
     return torch.from_numpy(out)
+
+
+def ctor_state_dict(class_counts: Sequence[int], seed: int = 111, arch: str = "svtr") -> "OrderedDict[str, torch.Tensor]":
+    """Random-init weights drawn by the mirror modules' own constructors, which restate the reference's initialisers
+    (modules/svtr.py:488-498 trunc_normal / LayerNorm bias 1.0 / kaiming convs; nn.Linear, nn.Conv2d and nn.LSTM defaults
+    elsewhere; router rebuilt by update_fc, modules/model.py:437-452) -- the "random-init weights" BASELINE.json's
+    tolerances and metric are quoted on.  Gates come out soft (~1/I), unlike the gate-spreading synth_state_dict.
+    Deterministic on the CPU generator for a given (seed, class_counts, arch)."""
+    import argparse
+    from .modules.model import MRNNet
+    opt = argparse.Namespace(Transformation="None", FeatureExtraction="SVTR" if arch == "svtr" else "VGG",
+                             SequenceModeling="None" if arch == "svtr" else "BiLSTM", Prediction="CTC", num_fiducial=20,
+                             input_channel=4, output_channel=512, hidden_size=256, imgH=32, imgW=256, batch_max_length=25,
+                             precision="fp32")
+    gen_state = torch.get_rng_state()
+    torch.manual_seed(seed)
+    try:
+        net = MRNNet(opt)
+        for c in class_counts:
+            net.update_fc(opt.hidden_size, c)
+            net.build_prediction(opt, c)
+        sd = OrderedDict((k, v.detach().clone()) for k, v in net.state_dict().items())
+        for k in sd:                        # non-trivial BatchNorm running statistics (eval-mode experts use them)
+            if k.endswith("running_var"):
+                sd[k] = 0.5 + torch.rand_like(sd[k])
+            elif k.endswith("running_mean"):
+                sd[k] = 0.1 * torch.randn_like(sd[k])
+    finally:
+        torch.set_rng_state(gen_state)
+    return sd
