@@ -100,11 +100,15 @@ typedef struct MrnbSvtrPack {
   int n_class[MRNB_MAX_EXPERTS];
 } MrnbSvtrPack;
 
+#define MRNB_ALL_EXPERTS (-1)
 size_t mrnb_svtr_workspace_bytes(int n_experts, int B, int chunk, int prec);
 
 /* image [B,4,32,256] fp32 NCHW.  chunk: samples processed together after the patch embedding (0 = all).
- * bn_batch_stats = 1: nn.BatchNorm2d in .train() (batch statistics; update_running = 1 also applies the momentum
- * update, reference quirk il_modules/mrn.py:401); 0: running statistics.
+ * bn_batch_stats / update_running are per-expert BIT MASKS (bit e = expert e; MRNB_ALL_EXPERTS = every expert, 0 = none):
+ * bit set in bn_batch_stats: that expert's nn.BatchNorm2d runs as in .train() (batch statistics; the same bit in
+ * update_running also applies the momentum update, reference quirk il_modules/mrn.py:401); clear: running statistics.
+ * (The reference can hold experts in different modes: after update_step1 the newest expert is .eval() while the frozen
+ * older ones are still in .train(), il_modules/mrn.py:284-287 vs :107.)
  * drop_scales: NULL or [I,12,2,B] DropPath multipliers (modules/svtr.py:7-22).
  * features: NULL or [B,I,64,256] fp32 (router input).  logits: host array of I device pointers (NULL entries are
  * skipped), logits[i] is [B,64,ld_logits[i]] fp32 with the first C_i columns written (model.{i} "predict"). */

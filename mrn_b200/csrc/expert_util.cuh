@@ -63,6 +63,7 @@ struct Workspace {
 
 // BN finalize: scale/shift per (expert, channel) from batch statistics (train) or running statistics (eval);
 // in train mode also the running-stat update with momentum 0.1 and the unbiased variance (nn.BatchNorm2d).
+// use_batch_stats / update_running are per-expert bit masks (bit e = expert e).
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ run_mean,
                                    float* __restrict__ run_var, float* __restrict__ scale_shift /*[I,C,2]*/, int I, int C,
@@ -70,12 +71,13 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, const float
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= I * C) return;
   float mean, var;
-  if (use_batch_stats) {
+  const int e = idx / C;
+  if ((use_batch_stats >> e) & 1) {
     const double m = stats[idx * 2] / count;
     double v = stats[idx * 2 + 1] / count - m * m;
     if (v < 0) v = 0;
     mean = (float)m; var = (float)v;
-    if (update_running) {
+    if ((update_running >> e) & 1) {
       run_mean[idx] = 0.9f * run_mean[idx] + 0.1f * mean;
       run_var[idx] = 0.9f * run_var[idx] + 0.1f * (float)(v * count / (count - 1.0));
     }

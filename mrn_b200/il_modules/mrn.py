@@ -16,6 +16,7 @@ import math
 import os
 import time
 
+import numpy as np
 import torch
 
 from .. import dist as mdist
@@ -146,6 +147,7 @@ class MRN(object):
         self.optimizer = None
         self.character = None
         self.converter = None
+        self.memory_index = []                 # il_modules/base.py:40: one rehearsal index array per earlier task
         self.pi = 15
 
     # ---- reference plumbing ------------------------------------------------------------------------
@@ -203,6 +205,7 @@ class MRN(object):
         self.optimizer = FusedAdam(self.net, self.opt.lr * scale, self.opt.num_iter * the,
                                    grad_clip=self.opt.grad_clip, schedule=schedule)
         self.scheduler = self.optimizer
+        mdist.broadcast_(self.net.router_arena())     # the freshly built router (modules/model.py:437-452) is rank 0's on every rank
 
     # ---- training ------------------------------------------------------------------------------------
     def incremental_train(self, taski, character, train_loader, valid_loader):
@@ -229,7 +232,8 @@ class MRN(object):
                 train_loader.get_dataset(taski, memory=memory)
 
         def rehearsal():
-            if getattr(self.opt, "memory", None) is not None and hasattr(train_loader, "get_dataset"):
+            if getattr(self.opt, "memory", None) is not None and hasattr(train_loader, "get_dataset") \
+                    and hasattr(train_loader, "rehearsal_prev_model"):
                 self.build_rehearsal_memory(train_loader, taski)
             else:
                 dataset(getattr(self.opt, "memory", None))
@@ -237,6 +241,7 @@ class MRN(object):
         if self.opt.start_task > taski + step * 0.5:
             name = self.opt.lan_list[taski]
             path = f"./saved_models/{self.opt.exp_name}/{name}_{taski}_{step}_best_score.pth"
+            mdist.barrier()
             self.model.load_state_dict(torch.load(path, map_location=self.device), strict=True)
             self.net._cache.key = None
             if taski > 0 and step == 0:
@@ -256,9 +261,18 @@ class MRN(object):
             self._update_representation(start_iter, taski, train_loader, multi)
 
     def build_rehearsal_memory(self, train_loader, taski):
-        """il_modules/mrn.py:169-178 (random rehearsal memory: memory_num / taski samples per earlier task; the index
-        bookkeeping lives in the dataset layer)."""
-        train_loader.get_dataset(taski, memory=self.opt.memory, index_list=getattr(self, "memory_index", None))
+        """Random rehearsal memory (il_modules/mrn.py:169-178; il_modules/base.py:292-302): `memory_index` holds one
+        index array per earlier task.  Entering stage 1 of task `taski` draws a sample of the task-(taski-1) dataset
+        without replacement (numpy global RNG, as the reference) and, when memory_num < 5000, trims every earlier
+        task's array so that the total stays at memory_num; the arrays are then handed to the dataset layer."""
+        memory_num = int(self.opt.memory_num)
+        per_task = memory_num if memory_num >= 5000 else int(memory_num / taski)
+        _, n_prev = train_loader.rehearsal_prev_model(taski)
+        self.memory_index.append(np.random.choice(range(n_prev), per_task, replace=False))
+        if memory_num < 5000 and len(self.memory_index) * len(self.memory_index[0]) > memory_num:
+            self.memory_index[:taski] = [ix[:per_task] for ix in self.memory_index[:taski]]
+        train_loader.get_dataset(taski, memory=self.opt.memory, index_list=self.memory_index)
+        print("Is using rehearsal memory, has {} prev datasets, each has {}\n".format(len(self.memory_index), self.memory_index[0].size))
 
     # ---- stage 0: the newest expert trained end to end ---------------------------------------------
     def begin_expert_training(self, total_steps=None):
@@ -275,6 +289,7 @@ class MRN(object):
                                    schedule=getattr(self.opt, "schedule", "super"))
         self.scheduler = self.optimizer
         self._tp_steps = 0
+        mdist.broadcast_(self._tp.params)      # replicas start stage 0 from rank 0's weights (per-rank RNG may differ)
         return self._tp
 
     def end_expert_training(self):
@@ -429,7 +444,7 @@ class MRN(object):
         net = self.net
         B = int(image.shape[0])
         cache = self.__dict__.setdefault("_train_graphs", {})
-        key = (B, str(image.device), bool(net._experts_train_mode()))
+        key = (B, str(image.device), net._experts_train_mode())
         ent = cache.get(key)
         if ent is None:
             cache[key] = "warm"
@@ -450,8 +465,10 @@ class MRN(object):
         for dst, src in zip(st_in, (image, labels_index, labels_length, indexs)):
             dst.copy_(src, non_blocking=True)
         graph.replay()
-        if key[2] and net._cache.pack is not None:
+        if any(key[2]) and net._cache.pack is not None:
             net._cache.pack.bn_dirty = True              # train-mode experts updated their BN running statistics
+            from ..modules.model import _count_bn_steps
+            _count_bn_steps(net._cache.pack, key[2])
         mdist.allreduce_mean_(net.router_grad_arena())
         self.optimizer.step()
         return loss, taski_loss
@@ -517,7 +534,7 @@ class MRN(object):
         (~95 kernels), and a replay costs one launch.  The graph owns static input / output buffers; the returned
         tensors are views of the static outputs and stay valid until the next replay for the same batch size.
         Eval-mode experts only (train-mode BatchNorm / DropPath state is not captured)."""
-        if self.net._experts_train_mode():
+        if any(self.net._experts_train_mode()):
             raise RuntimeError("infer_batch_graphed needs eval-mode experts (call model.eval() first)")
         key = (int(image.shape[0]), val_choose, str(image.device))
         cache = self.__dict__.setdefault("_infer_graphs", {})
@@ -583,6 +600,7 @@ class MRN(object):
             if mdist.env_world()[0] == 0:
                 torch.save(self.model.state_dict(),
                            f"./saved_models/{opt.exp_name}/{opt.lan_list[taski]}_{taski}_{step}_best_score.pth")
+            mdist.barrier()                   # no rank reads the checkpoint before rank 0 has finished writing it
         lr = self.optimizer.param_groups[0]["lr"] if self.optimizer else 0.0
         log = (f"\n[{iteration}/{opt.num_iter}] Train_loss_clf: {train_loss_avg.val():0.5f}, Valid_loss: {valid_loss:0.5f} \n "
                + (f'{"":9s}Train_taski_loss: {train_taski_loss_avg.val():0.5f}\n' if train_taski_loss_avg is not None else "")
@@ -606,6 +624,7 @@ class MRN(object):
         path = f"./saved_models/{self.opt.exp_name}/{name}_{taski}_{step}_best_score.pth"
         if not isinstance(self.model, RankLocal):
             self.model = RankLocal(self.net).to(self.device)
+        mdist.barrier()
         self.model.load_state_dict(torch.load(path, map_location=self.device), strict=True)
         self.net._cache.key = None
         self.reset_graphs()

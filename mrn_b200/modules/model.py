@@ -145,16 +145,37 @@ def _precision(opt):
     return L.PREC_BF16 if str(p).lower() in ("bf16", "bfloat16") else L.PREC_FP32
 
 
+def _count_bn_steps(pack, modes):
+    steps = getattr(pack, "bn_steps", None)
+    if steps is None or len(steps) != len(modes):
+        steps = pack.bn_steps = [0] * len(modes)
+    for e, t in enumerate(modes):
+        steps[e] += int(bool(t))
+
+
+def _mode_mask(train_mode, n):
+    """Per-expert train / eval modes -> bit mask (bit e = expert e in .train()).  A bool applies to every expert."""
+    if isinstance(train_mode, (bool, int)):
+        return ((1 << n) - 1) if train_mode else 0
+    return sum(1 << e for e, t in enumerate(train_mode) if t)
+
+
 def _experts_forward(experts, image, opt, train_mode, cache=None, drop_scales=None, want_logits=True, chunk=None):
+    """train_mode: bool or one bool per expert (the reference can hold experts in different modes: after update_step1
+    the newest expert is .eval() while the frozen older ones are still .train(), il_modules/mrn.py:284-287 vs :107)."""
     if not image.is_cuda:
         raise RuntimeError("mrn_b200 needs CUDA tensors: there is no CPU fallback")
     cache = cache or _solo_cache
     pack = cache.get(experts, image.device, _precision(opt))
+    modes = [bool(train_mode)] * len(experts) if isinstance(train_mode, (bool, int)) else [bool(t) for t in train_mode]
+    mask = _mode_mask(modes, len(experts))
+    train_mode = mask != 0
     if pack.arch == "crnn":
-        feats, logits = ops.crnn_experts_forward(pack, image.contiguous().float(), bn_batch_stats=train_mode,
-                                                 update_running=train_mode, want_logits=want_logits)
+        feats, logits = ops.crnn_experts_forward(pack, image.contiguous().float(), bn_batch_stats=mask,
+                                                 update_running=mask, want_logits=want_logits)
         if train_mode:
             pack.bn_dirty = True
+            _count_bn_steps(pack, modes)
             if cache is _solo_cache:
                 _writeback_bn(experts, pack)
         return feats, logits
@@ -163,11 +184,16 @@ def _experts_forward(experts, image, opt, train_mode, cache=None, drop_scales=No
     if train_mode and drop_scales is None and getattr(opt, "drop_path", True):
         drop_scales = sample_drop_scales(len(experts), image.shape[0], experts[0].model.FeatureExtraction.ConvNet.drop_path_rates(),
                                          image.device)
-    feats, logits = ops.svtr_experts_forward(pack, image.contiguous().float(), bn_batch_stats=train_mode,
-                                             update_running=train_mode, drop_scales=drop_scales, chunk=chunk,
+        if not all(modes):                  # DropPath is the identity for the experts that are in .eval()
+            for e, t in enumerate(modes):
+                if not t:
+                    drop_scales[e].fill_(1.0)
+    feats, logits = ops.svtr_experts_forward(pack, image.contiguous().float(), bn_batch_stats=mask,
+                                             update_running=mask, drop_scales=drop_scales, chunk=chunk,
                                              want_logits=want_logits)
     if train_mode:
         pack.bn_dirty = True
+        _count_bn_steps(pack, modes)
         if cache is _solo_cache:
             _writeback_bn(experts, pack)
     return feats, logits
@@ -195,10 +221,15 @@ def _writeback_bn(experts, pack):
         for i, m in enumerate(experts):
             cn = m.model.FeatureExtraction.ConvNet
             bns = (cn[12], cn[15]) if pack.arch == "crnn" else (cn.patch_embed.proj[1], cn.patch_embed.proj[4])
+            steps = getattr(pack, "bn_steps", None)
+            n_fwd = steps[i] if steps is not None else 1     # train-mode forwards of this expert since the last write-back
+            if n_fwd == 0:
+                continue
             for bn, mean, var in ((bns[0], m0, v0), (bns[1], m1, v1)):
                 bn.running_mean.data = mean[i].clone()
                 bn.running_var.data = var[i].clone()
-                bn.num_batches_tracked += 1
+                bn.num_batches_tracked += n_fwd
+    pack.bn_steps = [0] * len(experts)
     pack.bn_dirty = False
 
 
@@ -310,7 +341,8 @@ class MRNNet(nn.Module):
         return super().state_dict(*args, **kwargs)
 
     def _experts_train_mode(self):
-        return bool(self.model[-1].training) if len(self.model) else False
+        """One flag per expert (nn.Module.training of each Model), as a tuple so it can key graph caches."""
+        return tuple(bool(m.training) for m in self.model)
 
     # -- forward ---------------------------------------------------------------------------------
     def forward(self, image, cross=True, text=None, is_train=True):

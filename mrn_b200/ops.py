@@ -153,6 +153,13 @@ _BLOCK_NAMES = [f"blocks1.{j}" for j in range(3)] + [f"blocks2.{j}" for j in ran
 _GEMM_W_SLOTS = {L.PB_QKV_W, L.PB_PROJ_W, L.PB_FC1_W, L.PB_FC2_W}
 
 
+def _mask(flag):
+    """bool -> every expert / none; int -> per-expert bit mask as is (include/mrn_b200.h: MRNB_ALL_EXPERTS)."""
+    if isinstance(flag, bool):
+        return -1 if flag else 0
+    return int(flag)
+
+
 def round_up(v, a):
     return (v + a - 1) // a * a
 
@@ -277,8 +284,8 @@ def svtr_experts_forward(pack: SvtrPack, image: torch.Tensor, bn_batch_stats: bo
             ptrs[i] = None
             logits.append(None)
     ws = pack.workspace(B, chunk)
-    rc = L.load().mrnb_svtr_experts_forward(C.byref(pack.struct), _p(image), B, int(chunk), pack.prec, int(bn_batch_stats),
-                                            int(update_running), _p(drop_scales), _p(feats), ptrs, lds, _p(ws),
+    rc = L.load().mrnb_svtr_experts_forward(C.byref(pack.struct), _p(image), B, int(chunk), pack.prec, _mask(bn_batch_stats),
+                                            _mask(update_running), _p(drop_scales), _p(feats), ptrs, lds, _p(ws),
                                             ws.numel(), _stream())
     L.check(rc, "svtr_experts_forward")
     return feats, logits
@@ -654,8 +661,8 @@ def crnn_experts_forward(pack: CrnnPack, image: torch.Tensor, bn_batch_stats: bo
             ptrs[i] = None
             logits.append(None)
     ws = pack.workspace(B)
-    rc = L.load().mrnb_crnn_experts_forward(C.byref(pack.struct), _p(image), B, pack.prec, int(bn_batch_stats),
-                                            int(update_running), _p(feats), ptrs, lds, _p(ws), ws.numel(), _stream())
+    rc = L.load().mrnb_crnn_experts_forward(C.byref(pack.struct), _p(image), B, pack.prec, _mask(bn_batch_stats),
+                                            _mask(update_running), _p(feats), ptrs, lds, _p(ws), ws.numel(), _stream())
     L.check(rc, "crnn_experts_forward")
     return feats, logits
 

@@ -86,6 +86,9 @@ def main(argv=None):
     seed_everything(opt.manual_seed)
     if not torch.cuda.is_available():
         raise RuntimeError("mrn_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    from . import dist as mdist
+    _, local_rank, _ = mdist.init_from_env()     # one process per GPU under torchrun; a no-op for a single process
+    torch.cuda.set_device(local_rank)
     try:                                    # the reference's dataset layer, if the reference tree is importable
         from data.data_manage import Dataset_Manager, Val_Dataset
         from data.dataset import AlignCollate, hierarchical_dataset

@@ -248,8 +248,95 @@ def test_train_step_cuda_graph_replay_matches_eager():
         arenas.append(net.router_arena().clone())
         losses.append(ls)
         if graphed:
-            assert isinstance(learner._train_graphs[(B, "cuda:0", False)], tuple)
+            assert isinstance(learner._train_graphs[(B, "cuda:0", (False,) * len(cc))], tuple)
     # split-K fp32 atomics make the weight gradients run-to-run non-deterministic at the 1e-6 level: compare with tolerance
     assert torch.allclose(arenas[0], arenas[1], rtol=1e-4, atol=2e-5)
     for (a0, b0), (a1, b1) in zip(*losses):
         assert abs(a0 - a1) < 1e-4 * abs(a0) + 1e-6 and abs(b0 - b1) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ bf16 twins
+def _oracle_stage1(sd, cc, img, tgt, lens, dom, bn_mode, drop):
+    with torch.no_grad():
+        feats, preds = [], []
+        for i in range(len(cc)):
+            f, z = O.expert_forward(sd, i, img, bn_mode, None if drop is None else drop[i])
+            feats.append(f)
+            preds.append(z)
+    return O.stage1_router_grads(sd, torch.stack(feats, 1), preds, tgt, lens, dom, dtype=torch.float32), preds
+
+
+@pytest.mark.parametrize("weights", ["ctor", "golden_fixture"])
+def test_bf16_train_mode_experts_match_oracle(weights):
+    """bf16 tensor-core twin of test_train_mode_experts_match_oracle: BN batch statistics + injected DropPath masks
+    through svtr_experts_forward in the mode bench.py times.  Random-init weights: north_star's 2e-2 budget on logits and
+    gates.  Gate-spreading golden fixture: per-expert logits within 2e-2; the soft-routed sum is as gate-sensitive as the
+    reference under autocast, so it is bounded loosely."""
+    cc, B, seed = (37, 61, 96), 3, 111
+    sd = synth.ctor_state_dict(cc, seed) if weights == "ctor" else synth.synth_state_dict(cc, seed)
+    img, tgt, lens, dom = synth.synth_batch(B, cc, seed)
+    drop = synth.synth_drop_scales(len(cc), B, O.svtr_drop_path_rates(), seed)
+    ref, preds = _oracle_stage1(sd, cc, img, tgt, lens, dom, "batch", drop)
+    net, opt = build_net(cc, sd, precision="bf16")
+    net.train()
+    r = net.route_and_combine(img.cuda(), is_train=True, want_logits=True, drop_scales=drop.cuda())
+    for i, z in enumerate(r["expert_logits"]):
+        assert rel_err(z.cpu().numpy(), preds[i].numpy()) < 2e-2, i
+    gate_dev = float((r["gate"].cpu() - ref["gate"]).abs().max())
+    lerr = rel_err(r["logits"].cpu().numpy(), ref["logits"].numpy())
+    print("bf16 train-mode (%s): gate dev %.2e, soft logits rel err %.2e" % (weights, gate_dev, lerr))
+    if weights == "ctor":
+        assert gate_dev < 2e-2 and lerr < 2e-2
+    else:
+        assert gate_dev < 0.25 and lerr < 0.25
+
+
+def test_bf16_stage1_step_matches_oracle():
+    """bf16 twin of test_stage1_step_matches_reference_golden on random-init weights: losses within 2e-2, router
+    gradients (bf16 router GEMMs, fp32 accumulation) within 5e-2 of the fp32 oracle's, grad norm within 2e-2."""
+    from mrn_b200 import ops
+    from mrn_b200.il_modules.mrn import MRN, RankLocal, FusedAdam
+    cc, B, seed = (37, 61, 96), 4, 7
+    sd = synth.ctor_state_dict(cc, seed)
+    img, tgt, lens, dom = synth.synth_batch(B, cc, seed)
+    ref, _ = _oracle_stage1(sd, cc, img, tgt, lens, dom, "eval", None)
+    net, opt = build_net(cc, sd, precision="bf16")
+    learner = MRN(opt)
+    learner.model = RankLocal(net)
+    learner.model.eval()
+    learner.optimizer = FusedAdam(net, 5e-4, 20000, grad_clip=5, schedule="const")
+    loss_clf, taski = learner.train_step_stage1(img.cuda(), tgt.cuda(), lens.cuda(), dom.cuda())
+    assert abs(float(loss_clf) - float(ref["loss_clf"])) / abs(float(ref["loss_clf"])) < 2e-2
+    assert abs(float(taski) - float(ref["taski_loss"])) < 2e-2
+    tn = float(torch.sqrt(sum((g.double() ** 2).sum() for g in ref["grads"].values())))
+    assert abs(float(learner.optimizer.norm) - tn) / tn < 2e-2
+    n, off = ops.router_param_offsets(len(cc))
+    grads = net.router_grad_arena().cpu()
+    worst = 0.0
+    for k, pname in enumerate(ops.ROUTER_PARAM_NAMES):
+        g_ref = ref["grads"][pname].reshape(-1)
+        got = grads[off[k]:off[k] + g_ref.numel()]
+        scale = max(float(g_ref.abs().max()), 1e-3 * tn)
+        worst = max(worst, float((got - g_ref).abs().max()) / scale)
+    print("bf16 stage-1 step: worst router-gradient deviation %.2e of its parameter's max" % worst)
+    assert worst < 5e-2
+
+
+def test_mixed_expert_modes_follow_each_modules_flag():
+    """The reference can hold experts in different modes (newest expert .eval() after update_step1 while the frozen older
+    ones are still .train(), il_modules/mrn.py:284-287 vs :107): each expert's BatchNorm follows its own module flag."""
+    cc, B, seed = (37, 61, 96), 3, 111
+    sd = synth.synth_state_dict(cc, seed)
+    img = synth.synth_batch(B, cc, seed)[0]
+    net, opt = build_net(cc, sd)
+    net.train()
+    net.model[-1].eval()
+    assert net._experts_train_mode() == (True, True, False)
+    r = net.route_and_combine(img.cuda(), is_train=True, want_logits=True)
+    with torch.no_grad():
+        want = [O.expert_forward(sd, i, img, "batch" if i < 2 else "eval", None)[1] for i in range(3)]
+    for i in range(3):
+        assert rel_err(r["expert_logits"][i].cpu().numpy(), want[i].numpy()) < 1e-4, i
+    sd2 = net.state_dict()
+    k = "model.%d.model.FeatureExtraction.ConvNet.patch_embed.proj.1.num_batches_tracked"
+    assert int(sd2[k % 0]) == 1 and int(sd2[k % 2]) == 0          # only the train-mode experts updated their statistics

@@ -180,3 +180,42 @@ def test_domain_ids_flatten_like_the_reference():
     a = _domain_ids([torch.tensor([0, 1, 1]), torch.tensor([2])])
     assert a.dtype == torch.long and a.tolist() == [0, 1, 1, 2]
     assert _domain_ids([3, 0, 1]).tolist() == [3, 0, 1]
+
+
+def test_rehearsal_memory_index_bookkeeping():
+    """build_rehearsal_memory keeps one index array per earlier task, trims them to memory_num / taski and hands the list
+    to the dataset layer (il_modules/mrn.py:169-178, il_modules/base.py:292-302)."""
+    import numpy as np
+    from mrn_b200.il_modules.mrn import MRN
+
+    class FakeLoader:
+        def __init__(self):
+            self.calls = []
+
+        def rehearsal_prev_model(self, taski):
+            return None, 10000 + taski
+
+        def get_dataset(self, taski, memory=None, index_list=None):
+            self.calls.append((taski, memory, [np.array(ix) for ix in index_list]))
+
+    learner = MRN.__new__(MRN)                      # host logic only: no device, no model
+    learner.opt = argparse.Namespace(memory="random", memory_num=2000)
+    learner.memory_index = []
+    loader = FakeLoader()
+    np.random.seed(111)
+    for taski in (1, 2, 3):
+        learner.build_rehearsal_memory(loader, taski)
+        t, memory, idx = loader.calls[-1]
+        assert t == taski and memory == "random" and len(idx) == taski
+        per = int(2000 / taski)
+        assert all(ix.size == per for ix in idx)
+        assert all(len(set(ix.tolist())) == per for ix in idx)                 # drawn without replacement
+        assert all(ix.max() < 10000 + k + 1 for k, ix in enumerate(idx))       # task k's array indexes task k's dataset
+    first = loader.calls[0][2][0]
+    assert (loader.calls[-1][2][0] == first[: int(2000 / 3)]).all()            # earlier arrays are trimmed, not redrawn
+    big = MRN.__new__(MRN)
+    big.opt = argparse.Namespace(memory="random", memory_num=5000)
+    big.memory_index = []
+    for taski in (1, 2):
+        big.build_rehearsal_memory(loader, taski)
+    assert [ix.size for ix in loader.calls[-1][2]] == [5000, 5000]             # memory_num >= 5000: per task, never trimmed
