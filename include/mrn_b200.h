@@ -187,6 +187,15 @@ typedef struct MrnbCrnnPack {
   int n_class[MRNB_MAX_EXPERTS];
 } MrnbCrnnPack;
 
+/* Classifier heads fc_i (modules/model.py:164,181) on the features left in `workspace` by the last
+ * mrnb_svtr_experts_forward call (chunk = 0, same pack / B / prec; logits = NULL there).  route_index = NULL: every
+ * expert for every sample.  route_index = device int32 [B] (the hard route of modules/model.py:383-393): only the
+ * routed expert's head is evaluated per sample -- 1 / I of the classifier FLOPs and of the logits traffic; logits rows
+ * of the other (expert, sample) pairs are left untouched, and mrnb_gate_combine never reads them for a one-hot gate.
+ * Tensor-core mode runs all heads (ragged C_i) as ONE grouped launch when the bf16 weights fc_w16[i] are slices of one
+ * allocation in expert order. */
+int mrnb_svtr_heads(const MrnbSvtrPack* pack, int B, int prec, const int* route_index, float* const* logits,
+                    const long* ld_logits, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t mrnb_crnn_workspace_bytes(int n_experts, int B, int prec);
 
 /* image [B,4,32,256] fp32 NCHW.  bn_batch_stats / update_running as in mrnb_svtr_experts_forward.
@@ -344,6 +353,14 @@ int mrnb_tc_gemm_general(const void* A, int a_mn, const void* B, int b_mn, float
 int mrnb_mlp_bf16(const void* A, const void* W1, const float* b1, const void* W2, const float* b2, float* x,
                   const float* rowscale, int rows_per_scale, void* ln_out, const float* ln_gamma, const float* ln_beta,
                   float ln_eps, int M, int D, cudaStream_t stream);
+/* Fused SVTR mixer branch of one Block on the tensor cores (bf16 mode), one group of `units` samples:
+ *   x <- x + rowscale[u] * ( proj( softmax(q k^T [+ Local 7x11 window]) v ) + bproj ),  q|k|v = A Wqkv^T + bqkv (q * 32^-0.5)
+ * A = LN1(x) bf16 [units, N, D] with N = 32768 / D tokens on an (N/64) x 64 grid, head_dim 32; Wqkv bf16 [3D, D], Wproj
+ * bf16 [D, D]; x fp32 [units, N, D] updated in place; optional ln_out = LN(x) (bf16, D <= 128, may alias A).
+ * q, k, v, scores and probabilities stay on chip.  Replaces modules/svtr.py:133-152 + :201-203 (first branch). */
+int mrnb_mixer_bf16(const void* A, const void* Wqkv, const float* bqkv, const void* Wproj, const float* bproj, float* x,
+                    const float* rowscale, void* ln_out, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                    int units, int D, int local, cudaStream_t stream);
 int mrnb_layernorm_f32(const float* x, float* y, const float* gamma, const float* beta, long rows, int D, float eps,
                        cudaStream_t stream);
 int mrnb_svtr_attention_f32(const float* qkv, float* out, int groups, int N, int d, int heads, int H, int W, int local,

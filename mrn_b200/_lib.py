@@ -80,6 +80,7 @@ _SIGNATURES = {
     "mrnb_profile_reset": (None, []),
     "mrnb_profile_read": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mrnb_svtr_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "mrnb_svtr_heads": (_i, [C.POINTER(MrnbSvtrPack), _i, _i, _vp, C.POINTER(_vp), C.POINTER(_l), _vp, _sz, _vp]),
     "mrnb_svtr_experts_forward": (_i, [C.POINTER(MrnbSvtrPack), _vp, _i, _i, _i, _i, _i, _vp, _vp, C.POINTER(_vp),
                                        C.POINTER(_l), _vp, _sz, _vp]),
     "mrnb_svtr_train_workspace_bytes": (_sz, [_i, _i, _i]),
@@ -110,6 +111,7 @@ _SIGNATURES = {
     "mrnb_linear_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "mrnb_tc_gemm_general": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "mrnb_mlp_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _f, _i, _i, _vp]),
+    "mrnb_mixer_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp]),
     "mrnb_layernorm_f32": (_i, [_vp, _vp, _vp, _vp, _l, _i, _f, _vp]),
     "mrnb_svtr_attention_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mrnb_svtr_attention_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

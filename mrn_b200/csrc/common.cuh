@@ -45,7 +45,7 @@ extern "C" void mrnb_count_launch(int n);   // launch counter (bench.py's gpu_la
 // Optional per-kernel-family timing with CUDA events on the launching stream (bench.py roofline); off by default.
 enum { MRNB_PROF_TCGEMM = 0, MRNB_PROF_SGEMM, MRNB_PROF_ATTN, MRNB_PROF_LN, MRNB_PROF_CONV, MRNB_PROF_COMBINE,
        MRNB_PROF_CTC, MRNB_PROF_ROUTER_EW, MRNB_PROF_OPTIM, MRNB_PROF_MISC, MRNB_PROF_MLP, MRNB_PROF_TCGEMM2,
-       MRNB_PROF_COUNT };
+       MRNB_PROF_MIXER, MRNB_PROF_COUNT };
 void mrnb_prof_begin(int family, cudaStream_t st, double flops, double bytes);
 void mrnb_prof_end(int family, cudaStream_t st);
 struct MrnbProfScope {

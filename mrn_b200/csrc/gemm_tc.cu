@@ -125,7 +125,25 @@ struct TcEpi {
   int conv, rows_per_img, per_kh, cch, w_off, sh, imgs_per_group, ow_shift, pad_h;
   int relu;
   MrnbTcLstm lstm;
+  MrnbTcHeads heads;       // MODE 3: ragged classifier heads of all experts in one launch (+ hard-route tile skip)
 };
+
+// MODE 3 tile decode: flat tile t -> (expert e, m0, n0); returns false when the hard route sends none of the tile's samples
+// to expert e (the tile is skipped by all three warp roles alike).
+__device__ __forceinline__ bool heads_tile(const MrnbTcHeads& H, int t, int& e, int& m0, int& n0) {
+  e = 0;
+#pragma unroll
+  for (int k = 1; k < 8; ++k) if (k < H.n_experts && t >= H.tile_prefix[k]) e = k;
+  const int tl = t - H.tile_prefix[e], nt = H.n_tiles[e];
+  m0 = (tl / nt) * 128; n0 = (tl % nt) * 128;
+  if (H.route) {
+    const int s0 = m0 / H.rows_per_sample, s1 = (m0 + 127) / H.rows_per_sample;
+    bool any = false;
+    for (int sidx = s0; sidx <= s1 && sidx < H.n_samples; ++sidx) any = any || (H.route[sidx] == e);
+    return any;
+  }
+  return true;
+}
 
 constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, each owning half of the tile columns
 constexpr int NTHREADS = 64 + EPI_WARPS * 32;      // warp 0 TMA, warp 1 MMA + TMEM, warps 2..9 epilogue
@@ -184,7 +202,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       uint32_t it = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int n0 = (t % n_tiles) * BN, m0 = ((t / n_tiles) % m_tiles) * BM, g = t / (n_tiles * m_tiles);
+        int n0 = (t % n_tiles) * BN, m0 = ((t / n_tiles) % m_tiles) * BM, g = t / (n_tiles * m_tiles);
+        int wrow = n0, wg = g;
+        if constexpr (MODE == 3) {
+          if (!heads_tile(ep.heads, t, g, m0, n0)) continue;
+          wrow = ep.heads.woff[g] + n0; wg = 0;                 // the heads' weights are one stacked [sum C_i, K] matrix
+        }
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % stages;
           const uint32_t ph = (it / stages) & 1u;
@@ -199,7 +222,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             tma_load_3d(sa, &tmA, &full_bar[s], kb * BK, m0, g);
           }
-          tma_load_3d(sa + A_STAGE_BYTES, &tmW, &full_bar[s], kb * BK, n0, g);
+          tma_load_3d(sa + A_STAGE_BYTES, &tmW, &full_bar[s], kb * BK, wrow, wg);
         }
       }
     }
@@ -209,6 +232,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t it = 0;
       int i = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
+        if constexpr (MODE == 3) {
+          int e_, m_, n_;
+          if (!heads_tile(ep.heads, t, e_, m_, n_)) { --i; continue; }         // skipped tiles do not consume an accumulator
+        }
         const int buf = i & 1;
         mbar_wait(&tmem_empty_bar[buf], (((uint32_t)i >> 1) & 1u) ^ 1u);      // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -246,22 +273,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int p8 = lane & 7, rsel = lane >> 3;
     int i = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
-      const int n0 = (t % n_tiles) * BN, m0 = ((t / n_tiles) % m_tiles) * BM, g = t / (n_tiles * m_tiles);
+      int n0 = (t % n_tiles) * BN, m0 = ((t / n_tiles) % m_tiles) * BM, g = t / (n_tiles * m_tiles);
+      // output of this tile: the launch-wide description, or (MODE 3) the head of expert g
+      void* t_out = ep.out; long t_ldo = ep.ldo; int t_N = ep.N; long gbase = (long)g * ep.o_gs;
+      const float* bias = ep.bias ? ep.bias + (long)g * ep.bias_gs : nullptr;
+      if constexpr (MODE == 3) {
+        if (!heads_tile(ep.heads, t, g, m0, n0)) { --i; continue; }
+        t_out = ep.heads.out[g]; t_ldo = ep.heads.ldo[g]; t_N = ep.heads.N[g]; gbase = 0; bias = ep.heads.bias[g];
+      }
       const int buf = i & 1;
       const int colw = n0 + ch * CW + p8 * 4;                  // this lane's first column in pass 0
-      const long gbase = (long)g * ep.o_gs;
       // interior tile with aligned rows: branch-free path (pointer increments, tile-uniform DropPath scale)
-      const bool interior = (m0 + BM <= ep.M) && (n0 + BN <= ep.N) && ((ep.ldo & 3) == 0) && ((gbase & 3) == 0) &&
+      const bool interior = (m0 + BM <= ep.M) && (n0 + BN <= t_N) && ((t_ldo & 3) == 0) && ((gbase & 3) == 0) &&
                             (!ep.rowscale || (ep.rows_per_scale % BM) == 0);
-      const long o0 = gbase + (long)(m0 + q * 32 + rsel) * ep.ldo + colw;
-      const long ostep = 4L * ep.ldo;
+      const long o0 = gbase + (long)(m0 + q * 32 + rsel) * t_ldo + colw;
+      const long ostep = 4L * t_ldo;
       const bool pre_res = OUT_F32 && interior && ep.res != nullptr;
       float4 rv[8];
       if (pre_res) {
 #pragma unroll
         for (int itr = 0; itr < 8; ++itr) rv[itr] = *reinterpret_cast<const float4*>(ep.res + o0 + itr * ostep);
       }
-      const float* bias = ep.bias ? ep.bias + (long)g * ep.bias_gs : nullptr;
       const float rs = (interior && ep.rowscale) ? ep.rowscale[(long)g * ep.rowscale_gs + m0 / ep.rows_per_scale] : 1.0f;
       mbar_wait(&tmem_full_bar[buf], ((uint32_t)i >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -284,14 +316,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
         const int col = colw + ps * 32;
-        const bool cfull = col + 4 <= ep.N;
+        const bool cfull = col + 4 <= t_N;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias && col < ep.N) {
+        if (bias && col < t_N) {
           if (cfull) b4 = *reinterpret_cast<const float4*>(bias + col);
           else {
             b4.x = bias[col];
-            if (col + 1 < ep.N) b4.y = bias[col + 1];
-            if (col + 2 < ep.N) b4.z = bias[col + 2];
+            if (col + 1 < t_N) b4.y = bias[col + 1];
+            if (col + 2 < t_N) b4.z = bias[col + 2];
           }
         }
         if (interior) {
@@ -344,7 +376,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           } else if (OUT_F32) {
-            float* op = reinterpret_cast<float*>(ep.out) + o0 + ps * 32;
+            float* op = reinterpret_cast<float*>(t_out) + o0 + ps * 32;
 #pragma unroll
             for (int itr = 0; itr < 8; ++itr) {
               const int rl = itr * 4 + rsel;
@@ -358,7 +390,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (LNF) keep[ps * 8 + itr] = x;
             }
           } else {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ep.out) + o0 + ps * 32;
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(t_out) + o0 + ps * 32;
 #pragma unroll
             for (int itr = 0; itr < 8; ++itr) {
               const int rl = itr * 4 + rsel;
@@ -380,21 +412,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int itr = 0; itr < 8; ++itr) {
             const int rl = itr * 4 + rsel;
             const int row = m0 + q * 32 + rl;
-            if (row >= ep.M || col >= ep.N) continue;
+            if (row >= ep.M || col >= t_N) continue;
             const float4 xs = *reinterpret_cast<const float4*>(stg + rl * 32 + ((p8 ^ (rl & 7)) * 4));
             float xv[4] = {xs.x + b4.x, xs.y + b4.y, xs.z + b4.z, xs.w + b4.w};
             const float rsr = ep.rowscale ? ep.rowscale[(long)g * ep.rowscale_gs + row / ep.rows_per_scale] : 1.0f;
-            const long o = gbase + (long)row * ep.ldo + col;
-            for (int j = 0; j < 4 && col + j < ep.N; ++j) {
+            const long o = gbase + (long)row * t_ldo + col;
+            for (int j = 0; j < 4 && col + j < t_N; ++j) {
               float x = xv[j];
               if (GELU) x = OUT_F32 ? gelu_erf(x) : gelu_fast(x);
               if (relu) x = fmaxf(x, 0.f);
               x *= rsr;
               if (OUT_F32) {
                 if (ep.res) x += ep.res[o + j];
-                reinterpret_cast<float*>(ep.out)[o + j] = x;
+                reinterpret_cast<float*>(t_out)[o + j] = x;
               } else {
-                reinterpret_cast<__nv_bfloat16*>(ep.out)[o + j] = __float2bfloat16_rn(x);
+                reinterpret_cast<__nv_bfloat16*>(t_out)[o + j] = __float2bfloat16_rn(x);
               }
             }
           }
@@ -588,6 +620,47 @@ int mrnb_tc_gemm(const MrnbTcGemm& p, cudaStream_t st) {
   if (wide) { MRNB_GO(128) }
   MRNB_GO(64)
 #undef MRNB_GO
+}
+
+int mrnb_tc_heads(const void* A, long lda, long a_gstride, const void* Wall, long w_rows, int M, int K, MrnbTcHeads H, cudaStream_t st) {
+  MRNB_CHECK_ARG(A && Wall && M > 0 && K > 0 && K % BK == 0 && H.n_experts >= 1 && H.n_experts <= 8, "tc_heads: bad argument");
+  MRNB_CHECK_ARG(!H.route || (H.rows_per_sample > 0 && H.n_samples > 0), "tc_heads: route needs rows_per_sample / n_samples");
+  const int m_tiles = cdiv(M, BM);
+  double flops = 0, bytes = 0;
+  H.tile_prefix[0] = 0;
+  for (int e = 0; e < H.n_experts; ++e) {
+    MRNB_CHECK_ARG(H.out[e] && H.N[e] > 0 && H.ldo[e] >= H.N[e] && H.woff[e] >= 0 && H.woff[e] + H.N[e] <= w_rows, "tc_heads: bad expert %d", e);
+    H.n_tiles[e] = cdiv(H.N[e], 128);
+    H.tile_prefix[e + 1] = H.tile_prefix[e] + H.n_tiles[e] * m_tiles;
+    const double frac = H.route ? 1.0 / H.n_experts : 1.0;     // hard route: ~1 / I of the (expert, sample) pairs are computed
+    flops += 2.0 * M * H.N[e] * K * frac;
+    bytes += (2.0 * M * K + 2.0 * H.N[e] * K) + 4.0 * M * H.N[e] * frac;
+  }
+  MrnbProfScope prof(MRNB_PROF_TCGEMM, st, flops, bytes);
+  CUtensorMap tmA, tmW;
+  MRNB_TRY(make_map(&tmA, A, K, M, H.n_experts, lda, a_gstride, BM));
+  MRNB_TRY(make_map(&tmW, Wall, K, w_rows, 1, K, 0, 128));
+  TcEpi ep{};
+  ep.M = M; ep.N = 0; ep.KB = K / BK; ep.stages = ep.KB < MAX_STAGES ? ep.KB : MAX_STAGES;
+  ep.rows_per_scale = 1; ep.n_tiles = 1; ep.m_tiles = m_tiles; ep.total_tiles = H.tile_prefix[H.n_experts];
+  ep.heads = H;
+  constexpr int BN_ = 128;
+  const size_t smem = 1024 + (size_t)ep.stages * (A_STAGE_BYTES + BN_ * BK * 2) + STAGING_BYTES;
+  static bool attr_set = false;
+  static int num_sms = 148;
+  if (!attr_set) {
+    cudaFuncSetAttribute(tc_gemm_kernel<BN_, true, false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         1024 + MAX_STAGES * (A_STAGE_BYTES + BN_ * BK * 2) + STAGING_BYTES);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    attr_set = true;
+  }
+  const int slots = 2 * num_sms;
+  const int grid = ep.total_tiles < slots ? ep.total_tiles : slots;
+  tc_gemm_kernel<BN_, true, false, false, 3><<<grid, NTHREADS, smem, st>>>(tmA, tmW, ep);
+  MRNB_CHECK_LAUNCH("tc_gemm_kernel");
+  return MRNB_OK;
 }
 
 extern "C" int mrnb_linear_bf16(const void* A, const void* W, const float* bias, const float* residual, void* out,

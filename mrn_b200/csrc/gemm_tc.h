@@ -31,6 +31,21 @@ struct MrnbTcLstm {
   int B;
 };
 
+// Ragged classifier heads of all experts in ONE launch (modules/model.py:164,181: fc = Linear(256, C_i), C_i differs per
+// expert): flat tile list over (expert, m tile, n tile).  The experts' bf16 weights are one stacked [sum C_i, K] matrix
+// (expert e at row woff[e]); outputs / biases are per expert.  route != NULL: hard-routed inference
+// (modules/model.py:383-393) -- a 128-row tile of expert e is computed only if the route sends one of its samples to e.
+struct MrnbTcHeads {
+  int n_experts;
+  int tile_prefix[9];      // first flat tile of expert e; [n_experts] = total
+  int n_tiles[8];          // n tiles (128 columns) of expert e
+  int N[8];                // C_e
+  int woff[8];             // first row of expert e in the stacked weight matrix
+  float* out[8]; long ldo[8]; const float* bias[8];
+  const int* route;        // device [n_samples] expert index per sample, or NULL
+  int rows_per_sample, n_samples;
+};
+
 struct MrnbTcGemm {
   // out[g, m, n] = epi( sum_k A[g, m, k] * W[g, n, k] + bias[g, n] )     A, W: bf16, k-contiguous
   const void* A; long lda; long a_gstride;     // elements
@@ -49,3 +64,5 @@ struct MrnbTcGemm {
 };
 
 int mrnb_tc_gemm(const MrnbTcGemm& g, cudaStream_t st);
+// out[e][m, :C_e] = A[e][m, :] . Wall[woff[e] + n, :]^T + bias[e]   for every expert e (fp32 out); H.tile_prefix / n_tiles are filled here
+int mrnb_tc_heads(const void* A, long lda, long a_gstride, const void* Wall, long w_rows, int M, int K, MrnbTcHeads H, cudaStream_t st);

@@ -14,6 +14,8 @@
 #include "gemm_f32.h"
 #include "gemm_tc.h"
 #include "mlp_tc.h"
+#include "mixer_tc.h"
+#include <stdlib.h>
 #include "svtr.h"
 #include "expert_util.cuh"
 
@@ -512,6 +514,13 @@ __global__ void feature_scatter_kernel(const float* __restrict__ src, float* __r
   }
 }
 
+// MRNB_MIXER=0 selects the unfused qkv GEMM / attention / proj GEMM sequence (kept for A/B measurements and tests)
+bool use_fused_mixer() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MRNB_MIXER"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 template <typename AT>
 size_t svtr_workspace_bytes_t(int I, int B, int Bc) {
   size_t s = 0;
@@ -533,28 +542,83 @@ size_t svtr_workspace_bytes_t(int I, int B, int Bc) {
 }
 
 template <typename AT>
+struct SvtrWs {
+  float* conv0; __nv_bfloat16* act0p; float* conv1; double* stats; float* ss; float* xall; float* xb;
+  AT* lnout; AT* qkv; AT* att; AT* big; float* feat32; AT* featat;
+};
+template <typename AT>
+SvtrWs<AT> carve_svtr(void* ws, size_t ws_bytes, int I, int B, int Bc) {
+  Workspace W{(char*)ws, 0, ws_bytes};
+  SvtrWs<AT> w{};
+  w.conv0 = W.take<float>((size_t)I * B * 16 * 128 * 32);
+  w.act0p = nullptr;
+  if (sizeof(AT) == 2) w.act0p = W.take<__nv_bfloat16>((size_t)I * B * 16 * 130 * 32);
+  w.conv1 = W.take<float>((size_t)I * B * 8 * 64 * 64);
+  w.stats = W.take<double>((size_t)I * 96 * 2);
+  w.ss = W.take<float>((size_t)I * 96 * 2);
+  w.xall = W.take<float>((size_t)I * B * 32768);
+  const size_t u = (size_t)I * Bc * 32768;
+  w.xb = W.take<float>(u);
+  w.lnout = W.take<AT>(u);
+  w.qkv = W.take<AT>(u * 3);
+  w.att = W.take<AT>(u);
+  w.big = W.take<AT>(u * 9 / 2);
+  w.feat32 = W.take<float>((size_t)I * Bc * 64 * 256);
+  w.featat = W.take<AT>((size_t)I * Bc * 64 * 256);
+  return w;
+}
+
+// Classifier heads fc_i = Linear(256, C_i) of every expert (modules/model.py:164,181) on the expert-major features
+// [I][bc * 64][256].  Tensor-core mode: ONE grouped launch over the ragged (expert, m tile, n tile) list when the bf16
+// weights are stacked in one allocation (ops.SvtrPack); route != NULL computes only the (expert, sample) pairs the hard
+// route selects (modules/model.py:383-393: the other experts' logits are never read).  logits[e] == NULL skips expert e.
+template <typename AT>
+int svtr_heads(const MrnbSvtrPack& P, const void* fa, int bc, int b0, float* const* logits, const long* ld_logits,
+               const int* route, cudaStream_t st) {
+  const int I = P.n_experts;
+  const long TD = 64 * 256;
+  bool grouped = sizeof(AT) == 2;
+  long w_rows = 0;
+  MrnbTcHeads H{};
+  if (grouped) {
+    H.n_experts = I;
+    for (int e = 0; e < I; ++e) {
+      const long diff = (const char*)P.fc_w16[e] - (const char*)P.fc_w16[0];
+      if (!logits[e] || !P.fc_w16[e] || diff < 0 || diff % 512 != 0 || diff / 512 > (1 << 24)) { grouped = false; break; }
+      H.woff[e] = (int)(diff / 512); H.N[e] = P.n_class[e];
+      H.out[e] = logits[e] + (size_t)b0 * 64 * ld_logits[e]; H.ldo[e] = ld_logits[e]; H.bias[e] = P.fc_b[e];
+      if (H.woff[e] + H.N[e] > w_rows) w_rows = H.woff[e] + H.N[e];
+    }
+  }
+  if (grouped) {
+    H.route = route; H.rows_per_sample = 64; H.n_samples = bc;
+    return mrnb_tc_heads(fa, 256, (long)bc * TD, P.fc_w16[0], w_rows, bc * 64, 256, H, st);
+  }
+  for (int e = 0; e < I; ++e) {
+    if (!logits[e]) continue;
+    LinearArgs fc{};
+    fc.A = (const char*)fa + (size_t)e * bc * TD * sizeof(AT); fc.lda = 256;
+    fc.W32 = P.fc_w[e]; fc.W16 = P.fc_w16[e]; fc.bias = P.fc_b[e];
+    fc.out = logits[e] + (size_t)b0 * 64 * ld_logits[e]; fc.ldo = ld_logits[e]; fc.out_is_f32 = 1;
+    fc.M = bc * 64; fc.N = P.n_class[e]; fc.K = 256; fc.groups = 1;
+    MRNB_TRY(linear<AT>(fc, st));
+  }
+  return MRNB_OK;
+}
+
+template <typename AT>
 int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int bn_batch_stats, int update_running,
                    const float* drop_scales /*[I,12,2,B] or null*/, float* features /*[B,I,T,256]*/,
                    float* const* logits, const long* ld_logits, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int I = P.n_experts;
   MRNB_CHECK_ARG(ws_bytes >= svtr_workspace_bytes_t<AT>(I, B, Bc), "svtr_forward: workspace too small (%zu < %zu)",
                  ws_bytes, svtr_workspace_bytes_t<AT>(I, B, Bc));
-  Workspace W{(char*)ws, 0, ws_bytes};
-  float* conv0 = W.take<float>((size_t)I * B * 16 * 128 * 32);
-  __nv_bfloat16* act0p = nullptr;
-  if (sizeof(AT) == 2) act0p = W.take<__nv_bfloat16>((size_t)I * B * 16 * 130 * 32);
-  float* conv1 = W.take<float>((size_t)I * B * 8 * 64 * 64);
-  double* stats = W.take<double>((size_t)I * 96 * 2);
-  float* ss = W.take<float>((size_t)I * 96 * 2);
-  float* xall = W.take<float>((size_t)I * B * 32768);
+  SvtrWs<AT> wsp = carve_svtr<AT>(ws, ws_bytes, I, B, Bc);
+  float* conv0 = wsp.conv0; __nv_bfloat16* act0p = wsp.act0p; float* conv1 = wsp.conv1; double* stats = wsp.stats; float* ss = wsp.ss;
+  float* xall = wsp.xall; float* xb = wsp.xb; AT* lnout = wsp.lnout; AT* qkv = wsp.qkv; AT* att = wsp.att; AT* big = wsp.big;
+  float* feat32 = wsp.feat32; AT* featat = wsp.featat;
   const size_t u = (size_t)I * Bc * 32768;
-  float* xb = W.take<float>(u);
-  AT* lnout = W.take<AT>(u);
-  AT* qkv = W.take<AT>(u * 3);
-  AT* att = W.take<AT>(u);
-  AT* big = W.take<AT>(u * 9 / 2);
-  float* feat32 = W.take<float>((size_t)I * Bc * 64 * 256);
-  AT* featat = W.take<AT>((size_t)I * Bc * 64 * 256);
+  (void)u;
   constexpr bool F32 = sizeof(AT) == 4;
 
   bool ln1_ready = false;      // the first norm1 of the coming stage has already been written to lnout
@@ -657,46 +721,59 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
           MRNB_TRY(launch_layernorm<AT>(x, x_gs, lnout, rows_g * d, P.p[pb + MRNB_PB_NORM1_W], P.p[pb + MRNB_PB_NORM1_B],
                                         rows_g * I, rows_g, d, 1e-6f, st));
         if (j == 0) ln1_ready = false;
-        LinearArgs a{};
-        a.A = lnout; a.lda = d; a.a_gstride = rows_g * d;
-        a.W32 = P.p[pb + MRNB_PB_QKV_W]; a.W16 = P.h[pb + MRNB_PB_QKV_W]; a.w_gstride = (long)3 * d * d;
-        a.bias = P.p[pb + MRNB_PB_QKV_B]; a.bias_gstride = 3 * d;
-        a.out = qkv; a.ldo = 3 * d; a.o_gstride = rows_g * 3 * d; a.out_is_f32 = F32;
-        a.M = (int)rows_g; a.N = 3 * d; a.K = d; a.groups = I;
-        MRNB_TRY(linear<AT>(a, st));
-        {
-          const size_t smem = (size_t)2 * N * KV_LD * sizeof(float);
-          dim3 grid(I * bc, heads);
-          double pairs = (double)N * N;
-          if (local) {
-            double sh = 0, sw = 0;
-            for (int h = 0; h < H; ++h) sh += (h + 3 < H ? h + 3 : H - 1) - (h - 3 > 0 ? h - 3 : 0) + 1;
-            for (int w2 = 0; w2 < Wd; ++w2) sw += (w2 + 5 < Wd ? w2 + 5 : Wd - 1) - (w2 - 5 > 0 ? w2 - 5 : 0) + 1;
-            pairs = sh * sw;
+        if (sizeof(AT) == 2 && use_fused_mixer()) {
+          // tensor-core mode: the whole first branch (qkv GEMM -> attention -> proj + DropPath + residual [+ norm2]) is
+          // one persistent kernel; q, k, v, scores and probabilities never reach HBM (mixer_tc.cu)
+          MrnbMixer mx{};
+          mx.A = lnout; mx.Wqkv = P.h[pb + MRNB_PB_QKV_W]; mx.bqkv = P.p[pb + MRNB_PB_QKV_B];
+          mx.Wproj = P.h[pb + MRNB_PB_PROJ_W]; mx.bproj = P.p[pb + MRNB_PB_PROJ_B];
+          mx.x = x; mx.x_gstride = x_gs;
+          if (drop_scales) { mx.rowscale = drop_scales + ((size_t)blk * 2 + 0) * B + b0; mx.rowscale_gstride = (long)12 * 2 * B; }
+          if (fuse_ln) { mx.ln_out = lnout; mx.ln_gamma = P.p[pb + MRNB_PB_NORM2_W]; mx.ln_beta = P.p[pb + MRNB_PB_NORM2_B]; mx.ln_eps = 1e-6f; }
+          mx.D = d; mx.groups = I; mx.units_per_group = bc; mx.local = local ? 1 : 0;
+          MRNB_TRY(mrnb_mixer_tc(mx, st));
+        } else {
+          LinearArgs a{};
+          a.A = lnout; a.lda = d; a.a_gstride = rows_g * d;
+          a.W32 = P.p[pb + MRNB_PB_QKV_W]; a.W16 = P.h[pb + MRNB_PB_QKV_W]; a.w_gstride = (long)3 * d * d;
+          a.bias = P.p[pb + MRNB_PB_QKV_B]; a.bias_gstride = 3 * d;
+          a.out = qkv; a.ldo = 3 * d; a.o_gstride = rows_g * 3 * d; a.out_is_f32 = F32;
+          a.M = (int)rows_g; a.N = 3 * d; a.K = d; a.groups = I;
+          MRNB_TRY(linear<AT>(a, st));
+          {
+            const size_t smem = (size_t)2 * N * KV_LD * sizeof(float);
+            dim3 grid(I * bc, heads);
+            double pairs = (double)N * N;
+            if (local) {
+              double sh = 0, sw = 0;
+              for (int h = 0; h < H; ++h) sh += (h + 3 < H ? h + 3 : H - 1) - (h - 3 > 0 ? h - 3 : 0) + 1;
+              for (int w2 = 0; w2 < Wd; ++w2) sw += (w2 + 5 < Wd ? w2 + 5 : Wd - 1) - (w2 - 5 > 0 ? w2 - 5 : 0) + 1;
+              pairs = sh * sw;
+            }
+            MrnbProfScope prof(MRNB_PROF_ATTN, st, 4.0 * 32 * pairs * heads * I * bc,
+                               (double)I * bc * N * d * 4 * sizeof(AT));
+            if constexpr (sizeof(AT) == 2) {
+              MRNB_TRY(mrnb_attention_tc(qkv, att, I * bc, N, d, heads, H, Wd, local ? 1 : 0, st));     // tcgen05 path
+            } else {
+              if (local) attention_kernel<AT, true><<<grid, N, smem, st>>>(qkv, att, N, d, heads, H, Wd);
+              else attention_kernel<AT, false><<<grid, N, smem, st>>>(qkv, att, N, d, heads, H, Wd);
+              MRNB_CHECK_LAUNCH("attention_kernel");
+            }
           }
-          MrnbProfScope prof(MRNB_PROF_ATTN, st, 4.0 * 32 * pairs * heads * I * bc,
-                             (double)I * bc * N * d * 4 * sizeof(AT));
-          if constexpr (sizeof(AT) == 2) {
-            MRNB_TRY(mrnb_attention_tc(qkv, att, I * bc, N, d, heads, H, Wd, local ? 1 : 0, st));     // tcgen05 path
-          } else {
-            if (local) attention_kernel<AT, true><<<grid, N, smem, st>>>(qkv, att, N, d, heads, H, Wd);
-            else attention_kernel<AT, false><<<grid, N, smem, st>>>(qkv, att, N, d, heads, H, Wd);
-            MRNB_CHECK_LAUNCH("attention_kernel");
+          // proj + DropPath scale + residual (in place on x)
+          LinearArgs pr{};
+          pr.A = att; pr.lda = d; pr.a_gstride = rows_g * d;
+          pr.W32 = P.p[pb + MRNB_PB_PROJ_W]; pr.W16 = P.h[pb + MRNB_PB_PROJ_W]; pr.w_gstride = (long)d * d;
+          pr.bias = P.p[pb + MRNB_PB_PROJ_B]; pr.bias_gstride = d;
+          pr.out = x; pr.ldo = d; pr.o_gstride = x_gs; pr.out_is_f32 = 1; pr.res = x;
+          if (drop_scales) {
+            pr.rowscale = drop_scales + ((size_t)blk * 2 + 0) * B + b0; pr.rows_per_scale = N;
+            pr.rowscale_gstride = (long)12 * 2 * B;
           }
+          pr.M = (int)rows_g; pr.N = d; pr.K = d; pr.groups = I;
+          if (fuse_ln) { pr.ln_out = lnout; pr.ln_gamma = P.p[pb + MRNB_PB_NORM2_W]; pr.ln_beta = P.p[pb + MRNB_PB_NORM2_B]; pr.ln_eps = 1e-6f; }
+          MRNB_TRY(linear<AT>(pr, st));
         }
-        // proj + DropPath scale + residual (in place on x)
-        LinearArgs pr{};
-        pr.A = att; pr.lda = d; pr.a_gstride = rows_g * d;
-        pr.W32 = P.p[pb + MRNB_PB_PROJ_W]; pr.W16 = P.h[pb + MRNB_PB_PROJ_W]; pr.w_gstride = (long)d * d;
-        pr.bias = P.p[pb + MRNB_PB_PROJ_B]; pr.bias_gstride = d;
-        pr.out = x; pr.ldo = d; pr.o_gstride = x_gs; pr.out_is_f32 = 1; pr.res = x;
-        if (drop_scales) {
-          pr.rowscale = drop_scales + ((size_t)blk * 2 + 0) * B + b0; pr.rows_per_scale = N;
-          pr.rowscale_gstride = (long)12 * 2 * B;
-        }
-        pr.M = (int)rows_g; pr.N = d; pr.K = d; pr.groups = I;
-        if (fuse_ln) { pr.ln_out = lnout; pr.ln_gamma = P.p[pb + MRNB_PB_NORM2_W]; pr.ln_beta = P.p[pb + MRNB_PB_NORM2_B]; pr.ln_eps = 1e-6f; }
-        MRNB_TRY(linear<AT>(pr, st));
         if (!fuse_ln)
           MRNB_TRY(launch_layernorm<AT>(x, x_gs, lnout, rows_g * d, P.p[pb + MRNB_PB_NORM2_W], P.p[pb + MRNB_PB_NORM2_B],
                                         rows_g * I, rows_g, d, 1e-6f, st));
@@ -819,15 +896,9 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
         if (!F32) fa = featat;
       }
       if (logits) {
-        for (int e = 0; e < I; ++e) {
-          if (!logits[e]) continue;
-          LinearArgs fc{};
-          fc.A = (const char*)fa + (size_t)e * bc * TD * sizeof(AT); fc.lda = 256;
-          fc.W32 = P.fc_w[e]; fc.W16 = P.fc_w16[e]; fc.bias = P.fc_b[e];
-          fc.out = logits[e] + (size_t)b0 * 64 * ld_logits[e]; fc.ldo = ld_logits[e]; fc.out_is_f32 = 1;
-          fc.M = bc * 64; fc.N = P.n_class[e]; fc.K = 256; fc.groups = 1;
-          MRNB_TRY(linear<AT>(fc, st));
-        }
+        bool any = false;
+        for (int e = 0; e < I; ++e) any = any || logits[e] != nullptr;
+        if (any) MRNB_TRY(svtr_heads<AT>(P, fa, bc, b0, logits, ld_logits, nullptr, st));
       }
     }
   }
@@ -859,6 +930,29 @@ extern "C" int mrnb_svtr_experts_forward(const MrnbSvtrPack* pack, const float* 
                                  ld_logits, workspace, workspace_bytes, stream);
   }
   mrnb_set_error("svtr_experts_forward: unknown precision %d", prec);
+  return MRNB_ERR_ARG;
+}
+
+// Classifier heads on the features left in `workspace` by the last mrnb_svtr_experts_forward call (chunk = 0) with the
+// same (pack, B, prec).  route_index: NULL = every expert for every sample; device int32 [B] = hard route
+// (modules/model.py:383-393): only the routed expert's head is evaluated per sample, logits rows of the other
+// (expert, sample) pairs are left untouched (mrnb_gate_combine never reads them for a one-hot gate).
+extern "C" int mrnb_svtr_heads(const MrnbSvtrPack* pack, int B, int prec, const int* route_index, float* const* logits,
+                               const long* ld_logits, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  MRNB_CHECK_ARG(pack && logits && ld_logits && workspace && B > 0, "svtr_heads: null/empty argument");
+  MRNB_CHECK_ARG(pack->n_experts >= 1 && pack->n_experts <= MRNB_MAX_EXPERTS, "svtr_heads: n_experts out of range");
+  const int I = pack->n_experts;
+  if (prec == MRNB_PREC_BF16) {
+    MRNB_CHECK_ARG(workspace_bytes >= svtr_workspace_bytes_t<__nv_bfloat16>(I, B, B), "svtr_heads: workspace too small");
+    SvtrWs<__nv_bfloat16> w = carve_svtr<__nv_bfloat16>(workspace, workspace_bytes, I, B, B);
+    return svtr_heads<__nv_bfloat16>(*pack, w.featat, B, 0, logits, ld_logits, route_index, stream);
+  } else if (prec == MRNB_PREC_FP32) {
+    MRNB_CHECK_ARG(workspace_bytes >= svtr_workspace_bytes_t<float>(I, B, B), "svtr_heads: workspace too small");
+    SvtrWs<float> w = carve_svtr<float>(workspace, workspace_bytes, I, B, B);
+    // parity mode: plain fp32 GEMMs for every (expert, sample) pair (identical logits; the route only saves work)
+    return svtr_heads<float>(*pack, w.feat32, B, 0, logits, ld_logits, nullptr, stream);
+  }
+  mrnb_set_error("svtr_heads: unknown precision %d", prec);
   return MRNB_ERR_ARG;
 }
 

@@ -370,8 +370,12 @@ class MRNNet(nn.Module):
         """Experts -> DM-Router -> gate -> fused combine.  Soft route when is_train (modules/model.py:397-423),
         hard route otherwise (:366-395)."""
         experts = list(self.model)
+        # Hard route (eval): route FIRST, then evaluate only the routed expert's classifier head per sample (SURVEY K8e;
+        # modules/model.py:383-393 keeps padded_{index[b]}[b] and discards the other five heads' logits).  The soft
+        # route needs every head.
+        sparse = (not is_train) and _arch(self.opt) == "svtr" and not int(getattr(self.opt, "expert_chunk", 0) or 0)
         feats, logits = _experts_forward(experts, image, self.opt, self._experts_train_mode(), self._cache,
-                                         drop_scales=drop_scales)
+                                         drop_scales=drop_scales, want_logits=not sparse)
         arena = self.router_arena(image.device)
         _, scores, gate, index = ops.router_forward(arena, feats, self._rws, with_backward=with_backward,
                                                     prec=_precision(self.opt), want_out=False)
@@ -380,6 +384,8 @@ class MRNNet(nn.Module):
         else:
             g = torch.nn.functional.one_hot(index.long(), len(experts)).float()
             idx_out = index.long()
+            if sparse:
+                logits = ops.svtr_heads(self._cache.pack, image.shape[0], index)
         r = ops.gate_combine(logits, g, targets, lengths, want_logits=want_logits, want_E=want_E, want_decode=want_decode)
         r.update(index=idx_out, gate=gate, scores=scores, features=feats, expert_logits=logits)
         return r

@@ -44,7 +44,8 @@ def reset_launch_count() -> None:
 
 
 PROFILE_FAMILIES = ("tc_gemm_kernel", "sgemm_kernel", "attn_tc_kernel", "layernorm_kernel", "patch_embed", "combine_row_kernel",
-                    "ctc_lattice_kernel", "router_elementwise", "optimizer", "misc", "mlp_tc_kernel", "tc_gemm2_kernel")
+                    "ctc_lattice_kernel", "router_elementwise", "optimizer", "misc", "mlp_tc_kernel", "tc_gemm2_kernel",
+                    "mixer_tc_kernel")
 
 
 def profile_enable(on: bool):
@@ -117,6 +118,19 @@ def mlp_bf16(a16, w1_16, b1, w2_16, b2, x, rowscale=None, rows_per_scale=1, ln_g
     ln_out = torch.empty(M, D, device=x.device, dtype=torch.bfloat16) if ln_gamma is not None else None
     L.check(L.load().mrnb_mlp_bf16(_p(a16), _p(w1_16), _p(b1), _p(w2_16), _p(b2), _p(x), _p(rowscale), int(rows_per_scale),
                                    _p(ln_out), _p(ln_gamma), _p(ln_beta), float(ln_eps), M, D, _stream()), "mlp_bf16")
+    return ln_out
+
+
+def mixer_bf16(a16, wqkv16, bqkv, wproj16, bproj, x, local, rowscale=None, ln_gamma=None, ln_beta=None, ln_eps=1e-6):
+    """Fused mixer branch (qkv GEMM -> attention -> proj + DropPath + residual [+ LayerNorm]); x [units,N,D] fp32 is
+    updated IN PLACE.  a16 = LN1(x) bf16 [units,N,D].  Returns the fused LayerNorm output (bf16) or None."""
+    assert a16.dtype == torch.bfloat16 and wqkv16.dtype == torch.bfloat16 and wproj16.dtype == torch.bfloat16
+    _chk_f32(bqkv, bproj, x, rowscale, ln_gamma, ln_beta)
+    units, N, D = x.shape
+    assert N * D == 32768 and a16.shape == x.shape and a16.is_contiguous()
+    ln_out = torch.empty(units, N, D, device=x.device, dtype=torch.bfloat16) if ln_gamma is not None else None
+    L.check(L.load().mrnb_mixer_bf16(_p(a16), _p(wqkv16), _p(bqkv), _p(wproj16), _p(bproj), _p(x), _p(rowscale), _p(ln_out),
+                                     _p(ln_gamma), _p(ln_beta), float(ln_eps), units, D, int(local), _stream()), "mixer_bf16")
     return ln_out
 
 
@@ -237,19 +251,29 @@ class SvtrPack:
                              for i in range(n_experts)], 0).contiguous()
         put(L.P_SEQ_W, seq_w, gemm_weight=True)
         put(L.P_SEQ_B, seq_b)
+        fc_ws = [sd[f"{prefix}model.{i}.fc.weight"].detach().to(self.device, torch.float32).contiguous() for i in range(n_experts)]
+        # bf16 heads stacked in ONE allocation in expert order: mrnb_svtr_heads / the forward run every ragged head
+        # (C_i differs per expert) as a single grouped tcgen05 launch over one TMA map
+        stacked16 = None
+        if prec == L.PREC_BF16:
+            stacked16 = torch.zeros(sum(int(w.shape[0]) for w in fc_ws) + 128, fc_ws[0].shape[1], device=self.device, dtype=torch.bfloat16)
+            self.tensors.append(stacked16)
+        row = 0
         for i in range(n_experts):
-            w = sd[f"{prefix}model.{i}.fc.weight"].detach().to(self.device, torch.float32).contiguous()
+            w = fc_ws[i]
             b = sd[f"{prefix}model.{i}.fc.bias"].detach().to(self.device, torch.float32).contiguous()
             self.tensors += [w, b]
             self.struct.fc_w[i] = w.data_ptr()
             self.struct.fc_b[i] = b.data_ptr()
             self.struct.n_class[i] = w.shape[0]
             self.n_class.append(int(w.shape[0]))
-            if prec == L.PREC_BF16:
-                h = cast_bf16(w)
-                self.tensors.append(h)
+            if stacked16 is not None:
+                h = stacked16[row:row + w.shape[0]]
+                L.check(L.load().mrnb_cast_f32_to_bf16(_p(w), C.c_void_p(h.data_ptr()), w.numel(), _stream()), "cast")
                 self.struct.fc_w16[i] = h.data_ptr()
+                row += int(w.shape[0])
         self._ws: Optional[torch.Tensor] = None
+        self._ws_key = None
 
     def bn_running_stats(self):
         """(mean0, var0, mean1, var1), each [I, C]: updated in place by train-mode forwards."""
@@ -260,6 +284,39 @@ class SvtrPack:
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
+
+
+def _logit_buffers(pack, B, device, want, T=T_FRAMES):
+    I = pack.n_experts
+    ptrs = (C.c_void_p * I)()
+    lds = (C.c_long * I)()
+    logits = []
+    for i in range(I):
+        ld = round_up(pack.n_class[i], 4)
+        lds[i] = ld
+        if want:
+            buf = torch.empty(B, T, ld, device=device, dtype=torch.float32)
+            ptrs[i] = buf.data_ptr()
+            logits.append(buf[:, :, :pack.n_class[i]])
+        else:
+            ptrs[i] = None
+            logits.append(None)
+    return ptrs, lds, logits
+
+
+def svtr_heads(pack: SvtrPack, B: int, route_index: Optional[torch.Tensor] = None):
+    """Classifier heads on the features the last svtr_experts_forward(pack, image[B], chunk=0) left in the pack's
+    workspace.  route_index int32 [B]: hard route -- only the routed expert's head is evaluated per sample; the other
+    (expert, sample) rows of the returned buffers are uninitialised and must not be read (gate_combine with the matching
+    one-hot gate never does).  Returns [logits_i [B,64,C_i] views]."""
+    if pack._ws is None or pack._ws_key != (B, 0):
+        raise RuntimeError("svtr_heads: no features of a B=%d, chunk=0 forward in the pack's workspace" % B)
+    if route_index is not None and (route_index.dtype != torch.int32 or not route_index.is_cuda or route_index.numel() != B):
+        raise RuntimeError("svtr_heads: route_index must be a CUDA int32 tensor [B]")
+    ptrs, lds, logits = _logit_buffers(pack, B, pack._ws.device, True)
+    L.check(L.load().mrnb_svtr_heads(C.byref(pack.struct), B, pack.prec, _p(route_index), ptrs, lds, _p(pack._ws),
+                                     pack._ws.numel(), _stream()), "svtr_heads")
+    return logits
 
 
 def svtr_experts_forward(pack: SvtrPack, image: torch.Tensor, bn_batch_stats: bool = False, update_running: bool = False,
@@ -284,6 +341,7 @@ def svtr_experts_forward(pack: SvtrPack, image: torch.Tensor, bn_batch_stats: bo
             ptrs[i] = None
             logits.append(None)
     ws = pack.workspace(B, chunk)
+    pack._ws_key = (B, int(chunk) if 0 < int(chunk) < B else 0)
     rc = L.load().mrnb_svtr_experts_forward(C.byref(pack.struct), _p(image), B, int(chunk), pack.prec, _mask(bn_batch_stats),
                                             _mask(update_running), _p(drop_scales), _p(feats), ptrs, lds, _p(ws),
                                             ws.numel(), _stream())

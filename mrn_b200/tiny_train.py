@@ -89,12 +89,10 @@ def main(argv=None):
     from . import dist as mdist
     _, local_rank, _ = mdist.init_from_env()     # one process per GPU under torchrun; a no-op for a single process
     torch.cuda.set_device(local_rank)
-    try:                                    # the reference's dataset layer, if the reference tree is importable
-        from data.data_manage import Dataset_Manager, Val_Dataset
-        from data.dataset import AlignCollate, hierarchical_dataset
-    except Exception as ex:                 # pragma: no cover
-        raise RuntimeError("the dataset layer (data/data_manage.py, LMDB) is not part of mrn_b200 (SURVEY.md §8f.2): run "
-                           "from the reference tree so that `data` is importable (%s)" % (ex,))
+    # the input pipeline with the reference's protocol (LMDB readers, rehearsal memory, get_batch / get_batch2) and the
+    # device-side AlignCollate: mrn_b200/data_manage.py
+    from .data_manage import Dataset_Manager, Val_Dataset, hierarchical_dataset
+    from .data import AlignCollate
     char = {}
     chars = {}
 
@@ -113,12 +111,13 @@ def main(argv=None):
         return Val_Dataset(valid_datas, opt)
 
     def make_test_loaders(k):
-        collate = AlignCollate(opt, mode="test")
+        from .data_manage import _Collated, _passthrough
+        collate = AlignCollate(opt, mode="test")             # device-side resize in the main process
         out = []
         for v in valid_datas:
             ds, _ = hierarchical_dataset(root=v, opt=opt, mode="test")
-            out.append(torch.utils.data.DataLoader(ds, batch_size=opt.batch_size, shuffle=True, num_workers=int(opt.workers),
-                                                   collate_fn=collate, pin_memory=True))
+            out.append(_Collated(torch.utils.data.DataLoader(ds, batch_size=opt.batch_size, shuffle=True, num_workers=int(opt.workers),
+                                                             collate_fn=_passthrough, pin_memory=False), collate))
         return out
 
     log = open(f"./saved_models/{opt.exp_name}/log_train.txt", "a") if os.path.isdir(f"./saved_models/{opt.exp_name}") else None
