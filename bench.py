@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the eager-torch reference on the same GPU (N=1 only)")
     ap.add_argument("--no-parity-probe", action="store_true", help="skip the first-step comparison with the CPU oracle (N=1 only)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch samples per GPU (the headline); strong: --batch is the GLOBAL batch, split over the ranks "
+                         "(what nn.DataParallel does with batch_size=256, il_modules/mrn.py:106,133)")
     ap.add_argument("--init", default="ctor", choices=["ctor", "synth"],
                     help="ctor: random-init weights from the constructors (BASELINE north_star, soft gates); synth: gate-spreading fixtures")
     ap.add_argument("--arch", default="svtr", choices=["svtr", "crnn"],
@@ -289,6 +292,10 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     B = args.batch
+    if args.scaling == "strong":
+        if B % world:
+            raise SystemExit("--scaling strong needs --batch divisible by the number of GPUs")
+        B = B // world
     opt = make_opt(args.precision, args.chunk, args.arch)
     sd = (synth.ctor_state_dict if args.init == "ctor" else synth.synth_state_dict)(CLASS_COUNTS, 111, arch=args.arch)
     T = 64 if args.arch == "svtr" else 63
@@ -516,7 +523,7 @@ def run_ours(args):
         "metric": (METRIC if not infer else "MRN-SVTR 6-expert inference + greedy decode samples/s").replace("SVTR", args.arch.upper()),
         "value": round(value, 2),
         "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
+        "warmup": max(3, args.warmup), "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": cfg,
         "e2e": {"value": round(e2e_value, 2), "unit": "samples/s", "h2d_bytes_per_step": int(h2d),

@@ -19,6 +19,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-I", os.path.join(HERE, "..", "include")]
 # extern "C" entry points must stay visible with -fvisibility=hidden
 FLAGS += ["-Xcompiler", "-fvisibility=default"]
+FLAGS += os.environ.get("MRNB_NVCC_EXTRA", "").split()      # e.g. -DMRNB_WAIT_TRAP_NS=600000000000ull for sanitizer builds
 
 
 def _sources():

@@ -24,6 +24,7 @@
 #include "mixer_tc.h"
 #include <cuda.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace {
 
@@ -167,7 +168,17 @@ struct MixParams {
   __nv_bfloat16* ln_out; const float* ln_gamma; const float* ln_beta; float ln_eps;
   int upg, total;                                           // units per group (expert), total units
   int dbg;                                                  // MRNB_MIXER_DBG bits (bottleneck experiments only; results are wrong)
+  unsigned long long* trace;                                // optional debug timeline of CTA 0 (tools/mixer_trace.py): [16][256] globaltimer stamps
 };
+
+#define MIX_TRACE(slot_, idx_)                                                                     \
+  do {                                                                                             \
+    if (ep.trace && blockIdx.x == 0 && (idx_) < 256) {                                             \
+      unsigned long long now__;                                                                    \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now__));                                    \
+      ep.trace[(slot_) * 256 + (idx_)] = now__;                                                    \
+    }                                                                                              \
+  } while (0)
 
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -307,13 +318,16 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               int nqt = qt, nkr = kr + 1;
               if (nkr >= kr_hi(qt)) { nqt = qt + 2; nkr = nqt < K::NT ? kr_lo(nqt) : 0; }
               const bool has_next = nqt < K::NT, last_of_tile = nqt != qt, first_of_tile = kr == kr_lo(qt);
+              if (s == 0) MIX_TRACE(0, pc);                    // MMA0: start of pair
               if (has_next) {
                 mbar_wait(&s_empty[s], pc & 1u);             // the stream has pulled S of the current pair out of TMEM
                 tc_fence_after();
                 issue_s(nqt, nkr);
               }
+              if (s == 0) MIX_TRACE(1, pc);                    // MMA0: S(next) issued, waiting for P
               mbar_wait(&p_full[s], pc & 1u);
               tc_fence_after();
+              if (s == 0) MIX_TRACE(2, pc);                    // MMA0: P available
               {
                 // O (+)= P V: the accumulator lives in TMEM for the whole query tile (the softmax warps rescale it in
                 // place on the rare occasions the running reference maximum moves)
@@ -324,6 +338,7 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                   umma_bf16(tmem_base + o_col, pd + (uint64_t)(k * 2), vd + (uint64_t)((k * 16 * 64) >> 4), idesc_o, (!first_of_tile) || k != 0);
                 umma_commit(&o_full[s]);
               }
+              if (s == 0) MIX_TRACE(3, pc);                    // MMA0: PV issued
               ++pc;
               if (last_of_tile) {
                 // the stream has normalised the head output of this query tile into its tile buffer:
@@ -409,23 +424,27 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int qt = ch; qt < K::NT; qt += 2, ++qc, ++pc) {
           const int qh = 2 * qt + (r >> 6), qw = r & 63;       // grid row / column of this query
           float m = -INFINITY, l = 0.f;                        // running reference maximum (log2 units) / normaliser
-          mbar_wait(&so_empty[ch], (qc & 1u) ^ 1u);            // the previous proj MMA has consumed the tile buffer
           const int j0 = kr_lo(qt), j1 = kr_hi(qt);
           for (int kr = j0; kr < j1; ++kr) {
             if (kr > j0) ++pc;
+            const bool tr = warp == 4 && lane == 0;
+            if (tr) MIX_TRACE(4, pc);                          // softmax: start of pair (waiting for S)
             mbar_wait(&s_full[ch], pc & 1u);
             tc_fence_after();
+            if (tr) MIX_TRACE(5, pc);                          // softmax: S ready
             // the 64 scores of this row go to registers once; TMEM is released at once so S of the next pair overlaps
-            uint32_t sv[2][32];
+            uint32_t sv[64];
             if (!(ep.dbg & 4)) {
-              tmem_ld32(lane_addr + s_col, sv[0]);
-              tmem_ld32(lane_addr + s_col + 32u, sv[1]);
+              tmem_ld32(lane_addr + s_col, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+              tmem_ld32(lane_addr + s_col + 32u, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
             } else {
 #pragma unroll
-              for (int k2 = 0; k2 < 32; ++k2) { sv[0][k2] = 0u; sv[1][k2] = 0u; }
+              for (int k2 = 0; k2 < 64; ++k2) sv[k2] = 0u;
             }
             tc_fence_before();
             mbar_arrive(&s_empty[ch]);
+            if (tr) MIX_TRACE(6, pc);                          // softmax: S in registers
+            // Local window: key column kw is visible from query column qw iff |kw - qw| <= 5, key row iff |kr - qh| <= 3
             uint32_t vmask[2] = {0xffffffffu, 0xffffffffu};
             if (LOCAL) {
               const int dh = kr - qh;
@@ -441,59 +460,74 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 vmask[cc] = mk;
               }
             }
-            // block maximum (unmasked inside a visible chunk: any reference >= the true maximum is valid)
-            float bmax = -INFINITY;
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              if (LOCAL && vmask[cc] == 0u) continue;
-#pragma unroll
-              for (int k2 = 0; k2 < 32; k2 += 2) bmax = max3(bmax, __uint_as_float(sv[cc][k2]), __uint_as_float(sv[cc][k2 + 1]));
-            }
-            // Lazy rescaling: O accumulates in TMEM against the reference m; p = 2^(s - m) may exceed 1 by up to 2^8 before
-            // the reference is moved.  Only then is the O row rescaled in place (tcgen05.ld / st), which is rare.
-            bmax *= sl2;                                       // reference in log2 units of the scaled scores (sl2 > 0 keeps the order)
-            float factor = 1.0f;
-            bool move = false;
-            if (m == -INFINITY) m = bmax;                      // nothing accumulated yet for this row (its O row is exactly 0)
-            else if (bmax > m + 8.0f) { move = true; factor = ex2_approx(m - bmax); l *= factor; m = bmax; }
-            if (kr > j0) {
-              mbar_wait(&o_full[ch], (pc - 1u) & 1u);          // P V of the previous block has retired: O is stable, the P tile is free
-              tc_fence_after();
-              if (__any_sync(0xffffffffu, move)) {
-                uint32_t o[32];
-                tmem_ld32(lane_addr + o_col, o);
-#pragma unroll
-                for (int k2 = 0; k2 < HD; ++k2) o[k2] = __float_as_uint(__uint_as_float(o[k2]) * factor);
-                tmem_st32(lane_addr + o_col, o);
-                tc_fence_before();
-              }
-            }
-            const float mref = (m == -INFINITY) ? 0.f : m;
-            float bsum = 0.f;
             uint8_t* prow = ptile + r * 128;
+            float bsum = 0.f;
+            // One pair for the key columns [CB, CB + NC): the Global mixer takes all 64; in a Local block a warp's 32 queries
+            // (consecutive grid columns qb .. qb+31) only see key columns qb-5 .. qb+36, i.e. 48 of the 64: columns 0..47 for
+            // the warps on the left half of the grid row, 16..63 on the right half (warp-uniform, compile-time ranges).
+            auto block = [&](auto cb_, auto nc_) {
+              constexpr int CB = decltype(cb_)::value, NC = decltype(nc_)::value;
+              // block maximum (unmasked inside the visited columns: any reference >= the true maximum is valid); 4 chains
+              float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              uint32_t pk[16];
+              for (int c = CB; c < CB + NC; c += 8) {
+                b0 = max3(b0, __uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
+                b1 = max3(b1, __uint_as_float(sv[c + 2]), __uint_as_float(sv[c + 3]));
+                b2 = max3(b2, __uint_as_float(sv[c + 4]), __uint_as_float(sv[c + 5]));
+                b3 = max3(b3, __uint_as_float(sv[c + 6]), __uint_as_float(sv[c + 7]));
+              }
+              float bmax = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3)) * sl2;   // log2 units of the scaled scores (sl2 > 0 keeps the order)
+              if (LOCAL && (vmask[0] | vmask[1]) == 0u) bmax = -INFINITY;   // nothing visible for this query in this key row
+              // Lazy rescaling: O accumulates in TMEM against the reference m; p = 2^(s - m) may exceed 1 by up to 2^8
+              // before the reference is moved.  Only then is the O row rescaled in place (tcgen05.ld / st), which is rare.
+              float factor = 1.0f;
+              bool move = false;
+              if (m == -INFINITY) m = bmax;                    // nothing accumulated yet for this row (its O row is exactly 0)
+              else if (bmax > m + 8.0f) { move = true; factor = ex2_approx(m - bmax); l *= factor; m = bmax; }
+              if (tr) MIX_TRACE(7, pc);                        // softmax: max done, waiting for PV(prev)
+              if (kr > j0) {
+                mbar_wait(&o_full[ch], (pc - 1u) & 1u);        // P V of the previous block has retired: O is stable, the P tile is free
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, move)) {
+                  uint32_t o[32];
+                  tmem_ld32(lane_addr + o_col, o);
 #pragma unroll
-              for (int k2 = 0; k2 < 32; k2 += 2) {
-                float p0 = ex2_approx(fmaf(__uint_as_float(sv[cc][k2]), sl2, -mref));
-                float p1 = ex2_approx(fmaf(__uint_as_float(sv[cc][k2 + 1]), sl2, -mref));
-                if (ep.dbg & 1) { p0 = 0.25f; p1 = 0.25f; }
-                if (LOCAL) {
-                  if (!((vmask[cc] >> k2) & 1u)) p0 = 0.f;
-                  if (!((vmask[cc] >> (k2 + 1)) & 1u)) p1 = 0.f;
+                  for (int k2 = 0; k2 < HD; ++k2) o[k2] = __float_as_uint(__uint_as_float(o[k2]) * factor);
+                  tmem_st32(lane_addr + o_col, o);
+                  tc_fence_before();
                 }
-                bsum += p0 + p1;
-                pk[k2 >> 1] = pack_bf16(p0, p1);
-              }
+              } else {
+                mbar_wait(&so_empty[ch], (qc & 1u) ^ 1u);      // first block of a query tile: the previous proj MMA has consumed
+              }                                                // the tile buffer (waited here, not at the tile start: its latency hides behind the loads above)
+              if (tr) MIX_TRACE(8, pc);                        // softmax: PV(prev) done
+              const float nm = (m == -INFINITY) ? 0.f : -m;
 #pragma unroll
-              for (int p4 = 0; p4 < 4; ++p4) {
-                const int piece = (cc * 4 + p4) ^ (r & 7);
-                *reinterpret_cast<uint4*>(prow + piece * 16) = make_uint4(pk[p4 * 4], pk[p4 * 4 + 1], pk[p4 * 4 + 2], pk[p4 * 4 + 3]);
+              for (int pcs = 0; pcs < 8; ++pcs) {              // 16-byte pieces of 8 key columns
+                uint32_t pk[4] = {0u, 0u, 0u, 0u};
+                if (pcs * 8 >= CB && pcs * 8 < CB + NC) {
+#pragma unroll
+                  for (int k2 = 0; k2 < 8; k2 += 2) {
+                    const int c = pcs * 8 + k2;
+                    float p0 = ex2_approx(fmaf(__uint_as_float(sv[c]), sl2, nm));
+                    float p1 = ex2_approx(fmaf(__uint_as_float(sv[c + 1]), sl2, nm));
+                    if (LOCAL) {
+                      if (!((vmask[c >> 5] >> (c & 31)) & 1u)) p0 = 0.f;
+                      if (!((vmask[(c + 1) >> 5] >> ((c + 1) & 31)) & 1u)) p1 = 0.f;
+                    }
+                    bsum += p0 + p1;
+                    pk[k2 >> 1] = pack_bf16(p0, p1);
+                  }
+                }
+                *reinterpret_cast<uint4*>(prow + ((pcs ^ (r & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               }
-            }
+            };
+            if (!LOCAL) block(std::integral_constant<int, 0>{}, std::integral_constant<int, 64>{});
+            else if (q & 1) block(std::integral_constant<int, 16>{}, std::integral_constant<int, 48>{});
+            else block(std::integral_constant<int, 0>{}, std::integral_constant<int, 48>{});
+            if (tr) MIX_TRACE(9, pc);                          // softmax: exps + P stores issued
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(&p_full[ch]);
+            if (tr) MIX_TRACE(10, pc);                         // softmax: P published
             l += bsum;
           }
           // last block of this query tile: O of the whole tile, normalise, head output -> tile buffer (64B-swizzled [128 x 32] bf16)
@@ -625,6 +659,8 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+void* g_mixer_trace = nullptr;
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -666,6 +702,7 @@ int launch_mixer(const MrnbMixer& p, cudaStream_t st) {
   ep.ln_out = (__nv_bfloat16*)p.ln_out; ep.ln_gamma = p.ln_gamma; ep.ln_beta = p.ln_beta; ep.ln_eps = p.ln_eps;
   ep.upg = p.units_per_group; ep.total = (int)units;
   { const char* e = getenv("MRNB_MIXER_DBG"); ep.dbg = e ? atoi(e) : 0; }
+  ep.trace = (unsigned long long*)g_mixer_trace;
   static bool attr = false;
   static int num_sms = 148;
   if (!attr) {
@@ -699,6 +736,8 @@ int mrnb_mixer_tc(const MrnbMixer& p, cudaStream_t st) {
   return launch_mixer<256, false, false>(p, st);
 #undef MRNB_MIX
 }
+
+extern "C" void mrnb_mixer_set_trace(void* device_buffer) { g_mixer_trace = device_buffer; }
 
 // C-ABI test entry: one group.  x [units][N][D] fp32 is updated in place; ln_out (bf16 [units][N][D]) optional.
 extern "C" int mrnb_mixer_bf16(const void* A, const void* Wqkv, const float* bqkv, const void* Wproj, const float* bproj,

@@ -514,11 +514,13 @@ __global__ void feature_scatter_kernel(const float* __restrict__ src, float* __r
   }
 }
 
-// MRNB_MIXER=0 selects the unfused qkv GEMM / attention / proj GEMM sequence (kept for A/B measurements and tests)
-bool use_fused_mixer() {
+// First branch of a Block in tensor-core mode: the fused mixer kernel (mixer_tc.cu) or the unfused qkv GEMM / attention /
+// proj GEMM sequence.  MRNB_MIXER = 0: never fused, 1: fused for the 64- and 128-wide stages (default: at d = 256 a sample
+// is one query tile, only one softmax stream has work and the unfused sequence is a few percent faster), 2: always fused.
+bool use_fused_mixer(int d) {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MRNB_MIXER"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v != 0;
+  if (v < 0) { const char* e = getenv("MRNB_MIXER"); v = e ? atoi(e) : 1; }
+  return v >= 2 || (v == 1 && d <= 128);
 }
 
 template <typename AT>
@@ -721,7 +723,7 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
           MRNB_TRY(launch_layernorm<AT>(x, x_gs, lnout, rows_g * d, P.p[pb + MRNB_PB_NORM1_W], P.p[pb + MRNB_PB_NORM1_B],
                                         rows_g * I, rows_g, d, 1e-6f, st));
         if (j == 0) ln1_ready = false;
-        if (sizeof(AT) == 2 && use_fused_mixer()) {
+        if (sizeof(AT) == 2 && use_fused_mixer(d)) {
           // tensor-core mode: the whole first branch (qkv GEMM -> attention -> proj + DropPath + residual [+ norm2]) is
           // one persistent kernel; q, k, v, scores and probabilities never reach HBM (mixer_tc.cu)
           MrnbMixer mx{};

@@ -26,7 +26,8 @@ def timeit(fn, n=10):
     return e0.elapsed_time(e1) / n
 
 
-for D, local in ((64, 1), (128, 1), (128, 0), (256, 0)):
+SHAPES = [tuple(int(v) for v in t.split(":")) for t in os.environ.get("SHAPES", "64:1,128:1,128:0,256:0").split(",")]
+for D, local in SHAPES:
     N, heads = 32768 // D, D // 32
     x = torch.randn(units, N, D, device="cuda")
     a16 = ops.cast_bf16(torch.randn(units, N, D, device="cuda"))
@@ -43,7 +44,7 @@ for D, local in ((64, 1), (128, 1), (128, 0), (256, 0)):
         qkv = ops.linear_bf16(a2, wqkv, bqkv, None, False, out_f32=False)
         att = ops.svtr_attention_bf16(qkv.view(units, N, 3 * D), heads, N // 64, 64, local)
         return ops.linear_bf16(att.view(units * N, D), wp, bp, x.view(units * N, D), False, out_f32=True)
-    t_u = timeit(unfused)
+    t_u = timeit(unfused) if not os.environ.get("FUSED_ONLY") else float("nan")
     flops = units * (8.0 * N * D * D + 4.0 * N * N * D)
     print("D=%3d N=%3d local=%d: fused %.3f ms (%.0f TFLOP/s dense-eq) | unfused qkv+attn+proj %.3f ms | ratio %.2f" %
           (D, N, local, t_f, flops / t_f / 1e9, t_u, t_u / t_f), flush=True)
