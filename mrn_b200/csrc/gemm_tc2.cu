@@ -105,6 +105,7 @@ struct Epi2 {
   int g_inner; long c_gs2;
   const float* bias_n; const float* bias_m;
   const float* mul; const float* res;
+  float* pre32;                           // optional: the value before `mul` / `res` (same element offsets)
   int M, N, KB_total, kb_per_split, splits, gelu;
   int tiles_n, tiles_m; long total_tiles;
   int simple;      // plain row-major output addressing: the lean epilogue (whole-line vector loads / stores / reductions)
@@ -278,6 +279,11 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
               }
+              if (ep.pre32) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(ep.pre32 + o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              }
               if (ep.mul) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
@@ -318,6 +324,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               x += bm;
               if (ep.bias_n) x += __ldg(ep.bias_n + col0 + j);
               if (ep.gelu) x = gelu_erf(x);
+              if (ep.pre32) ep.pre32[o + j] = x;
               if (ep.mul) x *= ep.mul[o + j];
               if (ep.res) x += ep.res[o + j];
               if (ep.out32) ep.out32[o + j] = x;
@@ -361,6 +368,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             float4 tt = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (ep.pre32) *reinterpret_cast<float4*>(ep.pre32 + o + j) = tt;
             if (ep.mul) { const float4 mm = *reinterpret_cast<const float4*>(ep.mul + o + j); tt.x *= mm.x; tt.y *= mm.y; tt.z *= mm.z; tt.w *= mm.w; }
             if (ep.res) { const float4 rr = *reinterpret_cast<const float4*>(ep.res + o + j); tt.x += rr.x; tt.y += rr.y; tt.z += rr.z; tt.w += rr.w; }
             if (ep.out32) *reinterpret_cast<float4*>(ep.out32 + o + j) = tt;
@@ -375,6 +383,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (col >= ep.N) break;
             const long o = om + (long)(col / ep.cn.inner) * ep.cn.so + (long)(col % ep.cn.inner) * ep.cn.si;
             float x = v[j];
+            if (ep.pre32) ep.pre32[o] = x;
             if (ep.mul) x *= ep.mul[o];
             if (ep.res) x += ep.res[o];
             if (ep.out32) ep.out32[o] = x;
@@ -439,7 +448,7 @@ int launch2(const MrnbTcGemm2& p, cudaStream_t st) {
   Epi2 ep{};
   ep.out32 = p.out32; ep.out16 = (__nv_bfloat16*)p.out16; ep.cm = p.cm; ep.cn = p.cn; ep.c_gs = p.c_gstride;
   ep.g_inner = p.g_inner; ep.c_gs2 = p.c_gstride2;
-  ep.bias_n = p.bias_n; ep.bias_m = p.bias_m; ep.mul = p.mul; ep.res = p.res;
+  ep.bias_n = p.bias_n; ep.bias_m = p.bias_m; ep.mul = p.mul; ep.res = p.res; ep.pre32 = p.pre32;
   ep.M = p.M; ep.N = p.N; ep.gelu = p.gelu; ep.alpha = p.alpha == 0.f ? 1.f : p.alpha;
   ep.KB_total = p.K / BK;
   int splits = p.splitk > 1 ? p.splitk : 1;
@@ -467,7 +476,7 @@ int launch2(const MrnbTcGemm2& p, cudaStream_t st) {
 int mrnb_tc_gemm2(const MrnbTcGemm2& p, cudaStream_t st) {
   MRNB_CHECK_ARG(p.a.ptr && p.b.ptr && (p.out32 || p.out16) && p.M > 0 && p.N > 0 && p.K > 0 && p.groups > 0, "tc_gemm2: bad argument");
   MRNB_CHECK_ARG(p.K % BK == 0, "tc_gemm2: K=%d must be a multiple of 64", p.K);
-  MRNB_CHECK_ARG(p.splitk <= 1 || (p.out32 && !p.out16 && !p.bias_n && !p.bias_m && !p.mul && !p.res && !p.gelu),
+  MRNB_CHECK_ARG(p.splitk <= 1 || (p.out32 && !p.out16 && !p.pre32 && !p.bias_n && !p.bias_m && !p.mul && !p.res && !p.gelu),
                  "tc_gemm2: split-K supports a raw fp32 accumulate only");
   MrnbProfScope prof(MRNB_PROF_TCGEMM2, st, 2.0 * p.M * p.N * p.K * p.groups,
                      (double)p.groups * (2.0 * p.M * p.K + 2.0 * p.N * p.K + 4.0 * p.M * p.N));

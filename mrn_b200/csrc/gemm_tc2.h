@@ -26,6 +26,7 @@ struct MrnbTcGemm2 {
   MrnbAxis cm, cn; long c_gstride;      // two-level output addressing (elements)
   int g_inner; long c_gstride2;         // g_inner > 0: group offset = (g / g_inner) * c_gstride + (g % g_inner) * c_gstride2
   const float* bias_n; const float* bias_m; const float* mul; const float* res;
+  float* pre32;                         // optional fp32 copy of the value before `mul` / `res` (same element offsets)
   int M, N, K, groups, splitk, gelu;
   float alpha;
 };

@@ -211,14 +211,15 @@ __global__ void __launch_bounds__(256)
 ln_rows_bwd_kernel(const float* __restrict__ xin, long ldx, const float* __restrict__ stats,
                    const float* __restrict__ gamma, const float* __restrict__ dyn, float* __restrict__ dxin,
                    __nv_bfloat16* __restrict__ dxin16, long lddx, const float* __restrict__ add1, const float* __restrict__ add2, float* __restrict__ dgamma,
-                   float* __restrict__ dbeta, long rows) {
-  __shared__ float sg[RD], sb[RD];
-  for (int k = threadIdx.x; k < RD; k += 256) { sg[k] = 0.f; sb[k] = 0.f; }
+                   float* __restrict__ dbeta, long rows, float* __restrict__ dcol = nullptr) {
+  // dcol (optional): column sums of the produced gradient dxin (the bias gradient of the Linear that made xin)
+  __shared__ float sg[RD], sb[RD], sc[RD];
+  for (int k = threadIdx.x; k < RD; k += 256) { sg[k] = 0.f; sb[k] = 0.f; sc[k] = 0.f; }
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float ag[8], ab[8];
+  float ag[8], ab[8], ac[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { ag[j] = 0.f; ab[j] = 0.f; }
+  for (int j = 0; j < 8; ++j) { ag[j] = 0.f; ab[j] = 0.f; ac[j] = 0.f; }
   for (long row = (long)blockIdx.x * 8 + w; row < rows; row += (long)gridDim.x * 8) {
     const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
     float xh[8], dxh[8], pre[8];
@@ -235,16 +236,22 @@ ln_rows_bwd_kernel(const float* __restrict__ xin, long ldx, const float* __restr
       m1 += dxh[j]; m2 = fmaf(dxh[j], xh[j], m2);
     }
     m1 = warp_sum(m1) * (1.0f / RD); m2 = warp_sum(m2) * (1.0f / RD);
-    if (dxin) {
+    if (dxin || dxin16) {
+      float g[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int idx = (j / 4) * 128 + lane * 4 + (j % 4);
-        float g = rstd * (dxh[j] - m1 - xh[j] * m2);
-        if (GELU_IN) g *= gelu_erf_grad(pre[j]);
-        if (add1) g += add1[row * RD + idx];
-        if (add2) g += add2[row * RD + idx];
-        dxin[row * lddx + idx] = g;
-        if (dxin16) dxin16[row * lddx + idx] = __float2bfloat16_rn(g);
+        g[j] = rstd * (dxh[j] - m1 - xh[j] * m2);
+        if (GELU_IN) g[j] *= gelu_erf_grad(pre[j]);
+        if (add1) g[j] += add1[row * RD + idx];
+        if (add2) g[j] += add2[row * RD + idx];
+        ac[j] += g[j];
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const long o = row * lddx + c * 128 + lane * 4;
+        if (dxin) *reinterpret_cast<float4*>(dxin + o) = make_float4(g[c * 4], g[c * 4 + 1], g[c * 4 + 2], g[c * 4 + 3]);
+        if (dxin16) store_bf16x4(dxin16 + o, make_float4(g[c * 4], g[c * 4 + 1], g[c * 4 + 2], g[c * 4 + 3]));
       }
     }
   }
@@ -252,9 +259,13 @@ ln_rows_bwd_kernel(const float* __restrict__ xin, long ldx, const float* __restr
   for (int j = 0; j < 8; ++j) {
     const int idx = (j / 4) * 128 + lane * 4 + (j % 4);
     atomicAdd(&sg[idx], ag[j]); atomicAdd(&sb[idx], ab[j]);
+    if (dcol) atomicAdd(&sc[idx], ac[j]);
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < RD; k += 256) { atomicAdd(dgamma + k, sg[k]); atomicAdd(dbeta + k, sb[k]); }
+  for (int k = threadIdx.x; k < RD; k += 256) {
+    atomicAdd(dgamma + k, sg[k]); atomicAdd(dbeta + k, sb[k]);
+    if (dcol) atomicAdd(dcol + k, sc[k]);
+  }
 }
 
 // da1[:, :D] = du * GELU'(a1[:, :D])
@@ -499,6 +510,7 @@ struct RouterWs {
   float *stats1, *xn, *a1, *u, *vn, *stats2, *v2, *g1, *y, *statsT, *gn, *g2, *y2, *out, *s;
   // backward temporaries
   float *dr, *ds, *dout, *dy2, *dy, *dg2, *dgn, *dg1, *du, *dv2, *dvn, *da1, *dxn;
+  float *gq, *gp, *ow, *y2w;            // gate-head driven backward: [B*I, D] each
   // bf16 shadows (tensor-core mode): GEMM operands only
   bf16 *w16, *xn16, *vn16, *g116, *gn16, *y216, *dout16, *dg216, *dy16, *dv216, *da116;
   size_t bytes;
@@ -522,6 +534,7 @@ RouterWs carve(char* base, int B, int I, int T, int D, bool bwd) {
     w.dg2 = take(MD); w.dgn = take(MD); w.dg1 = take(MD); w.du = take(MD); w.dv2 = take(MD); w.dvn = take(MD);
     w.da1 = take(MD * 2); w.dxn = take(MD);
     w.dout16 = take16(MD); w.dg216 = take16(MD); w.dy16 = take16(MD); w.dv216 = take16(MD); w.da116 = take16(MD * 2);
+    w.gq = take((size_t)B * I * D); w.gp = take((size_t)B * I * D); w.ow = take((size_t)B * I * D); w.y2w = take((size_t)B * I * D);
   }
   w.bytes = o + 256;
   return w;
@@ -603,6 +616,208 @@ int colsum(const float* X, MrnbAxis am, MrnbAxis an, int M, int N, float* out, c
   return MRNB_OK;
 }
 
+// =====================================================================================================================
+// Gate-head driven backward of the training step (tensor-core mode).
+//
+// The only consumer of the router output in training is the gate head (modules/model.py:402-405): s = out Wcr^T + bcr over
+// k = (i,c), then r = s^T wr + br over the frames.  Its input gradient is therefore RANK ONE along the frame axis:
+//     dout[b,i,t,c] = wr[t] * q[b,(i,c)],    q[b,:] = dr[b,:] Wcr                                     (q: [B, I*D])
+// and every contraction of the last Linear (out = y2 W3^T + b3 + x) collapses from M = B*I*T rows to B*I rows:
+//     dy2[b,i,t,:] = wr[t] * p[b,i,:],  p = q W3          dW3 = q^T y2w,  y2w[b,i,:] = sum_t wr[t] y2[b,i,t,:]
+//     db3 = (sum_t wr[t]) * sum_(b,i) q[b,i,:]             dWcr[j,(i,c)] = sum_b dr[b,j] ow[b,i,c],  ow = sum_t wr[t] out
+//     dbcr[j] = (sum_t wr[t]) * sum_b dr[b,j]
+// so dout / dy2 are never materialised, two M-row GEMMs and four passes over [M, D] tensors disappear, and the frame-
+// weighted sums ow / y2w ride in the pass that produces dg2 = dy2 * y.
+// =====================================================================================================================
+
+// q[b,i,:] = sum_j dr[b,j] Wcr[j,(i,:)] ;  p[b,i,:] = q[b,i,:] W3 ;  db3 += wsum * q ;  dbcr += wsum * dr      (block per (b,i))
+__global__ void __launch_bounds__(RD)
+gate_qp_kernel(const float* __restrict__ dr, const float* __restrict__ Wcr, const float* __restrict__ W3,
+               const float* __restrict__ wr, int I, int T, float* __restrict__ q, float* __restrict__ p,
+               float* __restrict__ db3, float* __restrict__ dbcr) {
+  __shared__ float sq[RD];
+  __shared__ float swsum;
+  const int bi = blockIdx.x, b = bi / I, i = bi % I, c = threadIdx.x;
+  if (threadIdx.x < 32) {
+    float s = 0.f;
+    for (int t = threadIdx.x; t < T; t += 32) s += wr[t];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) swsum = s;
+  }
+  float acc = 0.f;
+  for (int j = 0; j < I; ++j) acc = fmaf(dr[b * I + j], Wcr[(long)j * I * RD + (long)i * RD + c], acc);
+  sq[c] = acc;
+  q[(long)bi * RD + c] = acc;
+  __syncthreads();
+  const float wsum = swsum;
+  atomicAdd(db3 + c, acc * wsum);
+  if (i == 0 && c < I) atomicAdd(dbcr + c, dr[b * I + c] * wsum);
+  float pk = 0.f;
+#pragma unroll 8
+  for (int n = 0; n < RD; ++n) pk = fmaf(sq[n], W3[(long)n * RD + c], pk);
+  p[(long)bi * RD + c] = pk;
+}
+
+// One pass over out / y2 / y per (b,i):  ow = sum_t wr[t] out,  y2w = sum_t wr[t] y2,  dg2 = wr[t] p y (bf16 GEMM operand),
+// dbc[(i,c)] += sum_t dg2.   128 threads x 2 channels.
+__global__ void __launch_bounds__(128)
+tsum_dg2_kernel(const float* __restrict__ out, const __nv_bfloat16* __restrict__ y216, const float* __restrict__ y,
+                const float* __restrict__ p, const float* __restrict__ wr, int I, int T, float* __restrict__ ow,
+                float* __restrict__ y2w, __nv_bfloat16* __restrict__ dg216, float* __restrict__ dbc) {
+  __shared__ float swr[128];
+  const long bi = blockIdx.x;
+  const int i = (int)(bi % I), c = threadIdx.x * 2;
+  if (threadIdx.x < T) swr[threadIdx.x] = wr[threadIdx.x];
+  __syncthreads();
+  const float2 pp = *reinterpret_cast<const float2*>(p + bi * RD + c);
+  float2 aow = make_float2(0.f, 0.f), ay = make_float2(0.f, 0.f), ad = make_float2(0.f, 0.f);
+  const long base = bi * T * RD + c;
+#pragma unroll 4
+  for (int t = 0; t < T; ++t) {
+    const float w = swr[t];
+    const long o = base + (long)t * RD;
+    const float2 ov = *reinterpret_cast<const float2*>(out + o);
+    const float2 hv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(y216 + o));
+    const float2 yv = *reinterpret_cast<const float2*>(y + o);
+    aow.x = fmaf(w, ov.x, aow.x); aow.y = fmaf(w, ov.y, aow.y);
+    ay.x = fmaf(w, hv.x, ay.x); ay.y = fmaf(w, hv.y, ay.y);
+    const float dx = w * pp.x * yv.x, dy = w * pp.y * yv.y;
+    ad.x += dx; ad.y += dy;
+    *reinterpret_cast<__nv_bfloat162*>(dg216 + o) = __floats2bfloat162_rn(dx, dy);
+  }
+  *reinterpret_cast<float2*>(ow + bi * RD + c) = aow;
+  *reinterpret_cast<float2*>(y2w + bi * RD + c) = ay;
+  atomicAdd(dbc + (long)i * RD + c, ad.x);
+  atomicAdd(dbc + (long)i * RD + c + 1, ad.y);
+}
+
+// dWcr[j, k] += sum_b dr[b,j] ow[b,k]   (k = (i,c) over I*D; grid (cdiv(ID,256), b-chunks))
+__global__ void __launch_bounds__(256)
+gate_dwcr_kernel(const float* __restrict__ dr, const float* __restrict__ ow, int B, int I, long ID, float* __restrict__ dW) {
+  const long k = (long)blockIdx.x * 256 + threadIdx.x;
+  const int per = (B + gridDim.y - 1) / gridDim.y;
+  const int b0 = blockIdx.y * per, b1 = min(B, b0 + per);
+  if (k >= ID) return;
+  float acc[MRNB_MAX_EXPERTS];
+#pragma unroll
+  for (int j = 0; j < MRNB_MAX_EXPERTS; ++j) acc[j] = 0.f;
+  for (int b = b0; b < b1; ++b) {
+    const float z = ow[(long)b * ID + k];
+#pragma unroll
+    for (int j = 0; j < MRNB_MAX_EXPERTS; ++j)
+      if (j < I) acc[j] = fmaf(__ldg(dr + b * I + j), z, acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < MRNB_MAX_EXPERTS; ++j)
+    if (j < I) atomicAdd(dW + (long)j * ID + k, acc[j]);
+}
+
+// Backward of gn = LN_T(y) with the upstream gradient of y = y * g2 recomputed in place (dy_a = wr[t] p g2):
+//   dy = wr[t] p g2 + rstd (dxh - mean_t dxh - xh mean_t(dxh xh)),  dxh = dgn gamma[t]
+//   -> dy16 (bf16 GEMM operand);  dgamma[t] += sum d xh;  dbeta[t] += sum d;  db2[c] += sum_(b,i,t) dy   (bias of W2's Linear)
+// block per (b,i), 128 threads x 2 channels, two passes over the 64 frames (the second one hits L2).
+__global__ void __launch_bounds__(128)
+lnT_bwd2_kernel(const float* __restrict__ y, const float* __restrict__ stats, const float* __restrict__ gamma,
+                const float* __restrict__ dgn, const float* __restrict__ g2, const float* __restrict__ p,
+                const float* __restrict__ wr, __nv_bfloat16* __restrict__ dy16, float* __restrict__ dgamma,
+                float* __restrict__ dbeta, float* __restrict__ db2, int T, int Tv) {
+  __shared__ float sh[128 * 2];        // [T][2] block partials
+  __shared__ float sgam[128], swr[128];
+  const long bi = blockIdx.x;
+  const int c = threadIdx.x * 2, lane = threadIdx.x & 31;
+  for (int k = threadIdx.x; k < 2 * T; k += 128) sh[k] = 0.f;
+  if (threadIdx.x < T) { sgam[threadIdx.x] = gamma[threadIdx.x]; swr[threadIdx.x] = wr[threadIdx.x]; }
+  __syncthreads();
+  const float4 st4 = *reinterpret_cast<const float4*>(stats + (bi * RD + c) * 2);     // mean0, rstd0, mean1, rstd1
+  const float2 pp = *reinterpret_cast<const float2*>(p + bi * RD + c);
+  const long base = bi * T * RD + c;
+  float m1x = 0.f, m2x = 0.f, m1y = 0.f, m2y = 0.f;
+  for (int t0 = 0; t0 < Tv; t0 += 8) {
+    float v[16];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int t = t0 + u;
+      float a = 0.f, d = 0.f;
+      if (t < Tv) {
+        const float2 yv = *reinterpret_cast<const float2*>(y + base + (long)t * RD);
+        const float2 dv = *reinterpret_cast<const float2*>(dgn + base + (long)t * RD);
+        const float xh0 = (yv.x - st4.x) * st4.y, xh1 = (yv.y - st4.z) * st4.w;
+        const float g = sgam[t];
+        const float dx0 = dv.x * g, dx1 = dv.y * g;
+        m1x += dx0; m2x = fmaf(dx0, xh0, m2x); m1y += dx1; m2y = fmaf(dx1, xh1, m2y);
+        a = fmaf(dv.x, xh0, dv.y * xh1); d = dv.x + dv.y;
+      }
+      v[u] = a; v[8 + u] = d;
+    }
+    const float tot = warp_reduce16(v, lane);
+    if ((lane & 1) == 0) {
+      const int idx = (lane >> 1) & 15;                    // 0..7: sum d*xh of frame t0+idx ; 8..15: sum d of frame t0+idx-8
+      const int t = t0 + (idx & 7);
+      if (t < Tv) atomicAdd(&sh[t * 2 + (idx >> 3)], tot);
+    }
+  }
+  const float inv = 1.0f / Tv;
+  m1x *= inv; m2x *= inv; m1y *= inv; m2y *= inv;
+  float sx = 0.f, sy = 0.f;
+#pragma unroll 4
+  for (int t = 0; t < T; ++t) {
+    const long o = base + (long)t * RD;
+    const float2 gv = *reinterpret_cast<const float2*>(g2 + o);
+    const float w = swr[t];
+    float ox = w * pp.x * gv.x, oy = w * pp.y * gv.y;
+    if (t < Tv) {
+      const float2 yv = *reinterpret_cast<const float2*>(y + o);
+      const float2 dv = *reinterpret_cast<const float2*>(dgn + o);
+      const float xh0 = (yv.x - st4.x) * st4.y, xh1 = (yv.y - st4.z) * st4.w;
+      const float g = sgam[t];
+      ox += st4.y * (dv.x * g - m1x - xh0 * m2x);
+      oy += st4.w * (dv.y * g - m1y - xh1 * m2y);
+    }
+    sx += ox; sy += oy;
+    *reinterpret_cast<__nv_bfloat162*>(dy16 + o) = __floats2bfloat162_rn(ox, oy);
+  }
+  atomicAdd(db2 + c, sx); atomicAdd(db2 + c + 1, sy);
+  __syncthreads();
+  for (int k = threadIdx.x; k < T; k += 128) { atomicAdd(dgamma + k, sh[k * 2]); atomicAdd(dbeta + k, sh[k * 2 + 1]); }
+}
+
+// g1 = u * v2 and u = GELU(a1[:, :D]) in one pass (warp per row, grid-stride):
+//   du = dg1 v2 -> da1[:, :D] = du GELU'(a1[:, :D]) (bf16) ; dv2 = dg1 u (bf16) ; dbs[n] += sum_c dv2 ; db1[:D] += sum_rows da1
+__global__ void __launch_bounds__(256)
+dg1_fused_kernel(const float* __restrict__ dg1, const float* __restrict__ v2, const float* __restrict__ u,
+                 const float* __restrict__ a1, __nv_bfloat16* __restrict__ da116, __nv_bfloat16* __restrict__ dv216,
+                 float* __restrict__ dbs, float* __restrict__ db1, long rows, int IT) {
+  __shared__ float sc[RD];
+  for (int k = threadIdx.x; k < RD; k += 256) sc[k] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float ac[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ac[j] = 0.f;
+  for (long row = (long)blockIdx.x * 8 + w; row < rows; row += (long)gridDim.x * 8) {
+    float rs = 0.f;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const long o = row * RD + c * 128 + lane * 4, o2 = row * 2 * RD + c * 128 + lane * 4;
+      const float4 g = *reinterpret_cast<const float4*>(dg1 + o), vv = *reinterpret_cast<const float4*>(v2 + o),
+                   uu = *reinterpret_cast<const float4*>(u + o), aa = *reinterpret_cast<const float4*>(a1 + o2);
+      const float4 da = make_float4(g.x * vv.x * gelu_erf_grad(aa.x), g.y * vv.y * gelu_erf_grad(aa.y),
+                                    g.z * vv.z * gelu_erf_grad(aa.z), g.w * vv.w * gelu_erf_grad(aa.w));
+      const float4 dv = make_float4(g.x * uu.x, g.y * uu.y, g.z * uu.z, g.w * uu.w);
+      ac[c * 4] += da.x; ac[c * 4 + 1] += da.y; ac[c * 4 + 2] += da.z; ac[c * 4 + 3] += da.w;
+      rs += (dv.x + dv.y) + (dv.z + dv.w);
+      store_bf16x4(da116 + o2, da);
+      store_bf16x4(dv216 + o, dv);
+    }
+    rs = warp_sum(rs);
+    if (lane == 0) atomicAdd(dbs + (int)(row % IT), rs);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(&sc[(j / 4) * 128 + lane * 4 + (j % 4)], ac[j]);
+  __syncthreads();
+  for (int k = threadIdx.x; k < RD; k += 256) atomicAdd(db1 + k, sc[k]);
+}
+
 // Dimensions shared by every contraction of the router.
 struct Dims {
   int B, I, T, D;
@@ -654,6 +869,9 @@ MrnbTcOperand nogroup(MrnbTcOperand o) {          // shared weight: ignore the g
   return o;
 }
 inline int bn_for(int N) { return N >= 128 ? 128 : 64; }
+// split-K factor of a weight-gradient GEMM with `tiles` output tiles: the largest split whose tiles x split work items
+// still fit ONE wave of the 2 x 148 persistent CTAs (a second, partly filled wave costs a whole tile duration)
+inline int splitk_for(int tiles) { const int s = 296 / (tiles > 0 ? tiles : 1); return s < 1 ? 1 : s; }
 
 // out[rows, Nout] = A[rows, K] . W[Nout, K]^T (+bias, +res)   -- plain row-major Linear
 int linear_rows(const Dims& d, const float* A32, const bf16* A16, long lda, const float* W32, const bf16* W16, int Nout, int K,
@@ -698,8 +916,7 @@ int dw_rows(const Dims& d, const float* dY32, const bf16* dY16, long ldy, int No
     g.b = mrnb_operand_mn2d(X16, Nin, d.M, ldx, 1);
     g.out32 = dW; g.cm = mrnb_axis(Nin); g.cn = mrnb_axis(1);
     g.M = Nout; g.N = Nin; g.K = (int)d.M; g.groups = 1; g.alpha = 1.f;
-    const int tiles = cdiv(Nout, 128) * cdiv(Nin, bn_for(Nin));
-    g.splitk = (296 + tiles - 1) / tiles;
+    g.splitk = splitk_for(cdiv(Nout, 128) * cdiv(Nin, bn_for(Nin)));
     return mrnb_tc_gemm2(g, st);
   }
   MrnbGemm g{};
@@ -740,8 +957,9 @@ int router_forward(const float* P, const float* x, const Dims& d, float* out_use
     MrnbTcGemm2 g{};
     g.a = nogroup(mrnb_operand_k2d(W16 + off[R_SP_W], IT, IT, IT, 128, 1));
     g.b = op_tok_c_mnmajor(w.vn16, d);
-    g.out32 = w.v2; g.cm = mrnb_axis(D); g.cn = mrnb_axis(1); g.c_gstride = ITD;
+    g.cm = mrnb_axis(D); g.cn = mrnb_axis(1); g.c_gstride = ITD;
     g.bias_m = P + off[R_SP_B]; g.M = (int)IT; g.N = D; g.K = (int)IT; g.groups = B; g.alpha = 1.f;
+    g.pre32 = w.v2; g.mul = w.u; g.out16 = w.g116;          // epilogue: v2 kept for the backward, g1 = u * v2 as the next operand
     MRNB_TRY(mrnb_tc_gemm2(g, st));
   } else {
     MrnbGemm g{};
@@ -752,9 +970,9 @@ int router_forward(const float* P, const float* x, const Dims& d, float* out_use
     g.bias_m = P + off[R_SP_B];
     MRNB_TRY(mrnb_sgemm(g, st));
   }
-  {
+  if (!tc) {
     MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
-    LAUNCH_EW(mul_kernel, M * D / 4, w.u, w.v2, tc ? nullptr : w.g1, tc ? w.g116 : nullptr, M * D / 4);
+    LAUNCH_EW(mul_kernel, M * D / 4, w.u, w.v2, w.g1, nullptr, M * D / 4);
   }
   // y = g1 W2^T + b2 + x
   MRNB_TRY(linear_rows(d, w.g1, w.g116, D, P + off[R_P2_W], W16 + off[R_P2_W], D, D, P + off[R_P2_B], x, w.y, D, st));
@@ -769,8 +987,9 @@ int router_forward(const float* P, const float* x, const Dims& d, float* out_use
     MrnbTcGemm2 g{};
     g.a = op_bt_ic_kmajor(w.gn16, d);
     g.b = mrnb_operand_k2d(W16 + off[R_CP_W], ID, ID, ID, 128, 1);
-    g.out32 = w.g2; g.cm = mrnb_axis2(T, D, ITD); g.cn = mrnb_axis2(D, 1, TD);
+    g.cm = mrnb_axis2(T, D, ITD); g.cn = mrnb_axis2(D, 1, TD);
     g.bias_n = P + off[R_CP_B]; g.M = B * T; g.N = (int)ID; g.K = (int)ID; g.groups = 1; g.alpha = 1.f;
+    g.pre32 = w.g2; g.mul = w.y; g.out16 = w.y216;          // epilogue: g2 kept for the backward, y2 = y * g2 as the next operand
     MRNB_TRY(mrnb_tc_gemm2(g, st));
   } else {
     MrnbGemm g{};
@@ -781,9 +1000,9 @@ int router_forward(const float* P, const float* x, const Dims& d, float* out_use
     g.bias_n = P + off[R_CP_B];
     MRNB_TRY(mrnb_sgemm(g, st));
   }
-  {
+  if (!tc) {
     MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
-    LAUNCH_EW(mul_kernel, M * D / 4, w.y, w.g2, tc ? nullptr : w.y2, tc ? w.y216 : nullptr, M * D / 4);
+    LAUNCH_EW(mul_kernel, M * D / 4, w.y, w.g2, w.y2, nullptr, M * D / 4);
   }
   // out = y2 W3^T + b3 + x
   MRNB_TRY(linear_rows(d, w.y2, w.y216, D, P + off[R_P3_W], W16 + off[R_P3_W], D, D, P + off[R_P3_B], x, out, D, st));
@@ -831,8 +1050,7 @@ int dm_router_backward_core(const float* P, const float* x, const Dims& d, float
       g.b = op_ic_bt_mnmajor(w.gn16, d);
       g.out32 = G + off[R_CP_W]; g.cm = mrnb_axis(ID); g.cn = mrnb_axis(1);
       g.M = (int)ID; g.N = (int)ID; g.K = B * T; g.groups = 1; g.alpha = 1.f;
-      const int tiles = cdiv(ID, 128) * cdiv(ID, 128);
-      g.splitk = (296 + tiles - 1) / tiles;
+      g.splitk = splitk_for(cdiv(ID, 128) * cdiv(ID, 128));
       MRNB_TRY(mrnb_tc_gemm2(g, st));
     }
   } else {
@@ -886,8 +1104,7 @@ int dm_router_backward_core(const float* P, const float* x, const Dims& d, float
       g.b = op_tok_bc_kmajor(w.vn16, d, bn_for((int)IT));
       g.out32 = G + off[R_SP_W]; g.cm = mrnb_axis(IT); g.cn = mrnb_axis(1);
       g.M = (int)IT; g.N = (int)IT; g.K = B * D; g.groups = 1; g.alpha = 1.f;
-      const int tiles = cdiv(IT, 128) * cdiv(IT, bn_for((int)IT));
-      g.splitk = (296 + tiles - 1) / tiles;
+      g.splitk = splitk_for(cdiv(IT, 128) * cdiv(IT, bn_for((int)IT)));
       MRNB_TRY(mrnb_tc_gemm2(g, st));
     }
   } else {
@@ -934,6 +1151,106 @@ int dm_router_backward_core(const float* P, const float* x, const Dims& d, float
     ln_rows_bwd_kernel<false><<<grid > 0 ? grid : 1, 256, 0, st>>>(x, D, w.stats1, P + off[R_N_W], w.dxn, dx, nullptr, D,
                                                                      dx ? w.dy : nullptr, dx ? w.dout : nullptr,
                                                                      G + off[R_N_W], G + off[R_N_B], M);
+    MRNB_CHECK_LAUNCH("ln_rows_bwd_kernel");
+  }
+  return MRNB_OK;
+}
+
+// Training-step backward in tensor-core mode: gate head + DM_Router parameter gradients from dL/dr (w.dr), with the
+// rank-one structure of the gate head's input gradient exploited (see the kernel section above).  18 launches; no
+// [M, D] fp32 gradient is written except the four GEMM outputs (dgn, dg1, dvn, dxn).  G = zeroed gradient arena.
+int router_backward_gate_tc(const float* P, const float* x, const Dims& d, float* G, RouterWs& w, cudaStream_t st) {
+  long off[MRNB_ROUTER_NPARAMS + 1];
+  router_offsets(d.I, d.T, d.D, off);
+  const int B = d.B, I = d.I, T = d.T, D = d.D;
+  const long M = d.M, IT = d.IT, ID = d.ID, TD = d.TD, ITD = d.ITD;
+  const bf16* W16 = w.w16;
+  const float* wr = P + off[R_ROUTE_W];
+  {
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    gate_qp_kernel<<<B * I, RD, 0, st>>>(w.dr, P + off[R_CR_W], P + off[R_P3_W], wr, I, T, w.gq, w.gp, G + off[R_P3_B],
+                                         G + off[R_CR_B]);
+    MRNB_CHECK_LAUNCH("gate_qp_kernel");
+    tsum_dg2_kernel<<<B * I, 128, 0, st>>>(w.out, w.y216, w.y, w.gp, wr, I, T, w.ow, w.y2w, w.dg216, G + off[R_CP_B]);
+    MRNB_CHECK_LAUNCH("tsum_dg2_kernel");
+    gate_dwcr_kernel<<<dim3(cdiv(ID, 256), B >= 64 ? 8 : 1), 256, 0, st>>>(w.dr, w.ow, B, I, ID, G + off[R_CR_W]);
+    MRNB_CHECK_LAUNCH("gate_dwcr_kernel");
+  }
+  {  // dW3[n,k] = sum_(b,i) q[(b,i),n] y2w[(b,i),k]   (B*I rows: fp32 on the CUDA cores)
+    MrnbGemm g{};
+    g.A = w.gq; g.am = mrnb_axis(1); g.ak = mrnb_axis(D); g.a_kfast = 0;
+    g.B = w.y2w; g.bk = mrnb_axis(D); g.bn = mrnb_axis(1); g.b_kfast = 0;
+    g.C = G + off[R_P3_W]; g.cm = mrnb_axis(D); g.cn = mrnb_axis(1);
+    g.M = D; g.N = D; g.K = B * I; g.batch = 1; g.alpha = 1.f; g.rows_per_scale = 1;
+    g.splitk = (B * I + 127) / 128; if (g.splitk > 16) g.splitk = 16; if (g.splitk < 1) g.splitk = 1;
+    MRNB_TRY(mrnb_sgemm(g, st));
+  }
+  {  // dgn[(b,t), j] = sum_k dg2[(b,t),k] Wc[k,j]
+    MrnbTcGemm2 g{};
+    g.a = op_bt_ic_kmajor(w.dg216, d);
+    g.b = mrnb_operand_mn2d(W16 + off[R_CP_W], ID, ID, ID, 1);
+    g.out32 = w.dgn; g.cm = mrnb_axis2(T, D, ITD); g.cn = mrnb_axis2(D, 1, TD);
+    g.M = B * T; g.N = (int)ID; g.K = (int)ID; g.groups = 1; g.alpha = 1.f;
+    MRNB_TRY(mrnb_tc_gemm2(g, st));
+  }
+  {  // dWc[k,j] = sum_(b,t) dg2[(b,t),k] gn[(b,t),j]
+    MrnbTcGemm2 g{};
+    g.a = op_ic_bt_mnmajor(w.dg216, d);
+    g.b = op_ic_bt_mnmajor(w.gn16, d);
+    g.out32 = G + off[R_CP_W]; g.cm = mrnb_axis(ID); g.cn = mrnb_axis(1);
+    g.M = (int)ID; g.N = (int)ID; g.K = B * T; g.groups = 1; g.alpha = 1.f;
+    g.splitk = splitk_for(cdiv(ID, 128) * cdiv(ID, 128));
+    MRNB_TRY(mrnb_tc_gemm2(g, st));
+  }
+  {
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    lnT_bwd2_kernel<<<B * I, 128, 0, st>>>(w.y, w.statsT, P + off[R_CN_W], w.dgn, w.g2, w.gp, wr, w.dy16, G + off[R_CN_W],
+                                           G + off[R_CN_B], G + off[R_P2_B], T, d.Tv);
+    MRNB_CHECK_LAUNCH("lnT_bwd2_kernel");
+  }
+  // y = g1 W2^T + b2 + x
+  MRNB_TRY(dx_rows(d, nullptr, w.dy16, D, D, P + off[R_P2_W], W16 + off[R_P2_W], D, w.dg1, D, st));
+  MRNB_TRY(dw_rows(d, nullptr, w.dy16, D, D, nullptr, w.g116, D, D, G + off[R_P2_W], st));
+  {
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    const int grid = (int)((M + 8 * 16 - 1) / (8 * 16));
+    dg1_fused_kernel<<<grid > 0 ? grid : 1, 256, 0, st>>>(w.dg1, w.v2, w.u, w.a1, w.da116, w.dv216, G + off[R_SP_B],
+                                                          G + off[R_P1_B], M, (int)IT);
+    MRNB_CHECK_LAUNCH("dg1_fused_kernel");
+  }
+  {  // dvn[b,m,:] = sum_n Ws[n,m] dv2[b,n,:]
+    MrnbTcGemm2 g{};
+    g.a = nogroup(mrnb_operand_mn2d(W16 + off[R_SP_W], IT, IT, IT, 1));
+    g.b = op_tok_c_mnmajor(w.dv216, d);
+    g.out32 = w.dvn; g.cm = mrnb_axis(D); g.cn = mrnb_axis(1); g.c_gstride = ITD;
+    g.M = (int)IT; g.N = D; g.K = (int)IT; g.groups = B; g.alpha = 1.f;
+    MRNB_TRY(mrnb_tc_gemm2(g, st));
+  }
+  {  // dWs[n,m] = sum_(b,c) dv2[b,n,c] vn[b,m,c]
+    MrnbTcGemm2 g{};
+    g.a = op_tok_bc_kmajor(w.dv216, d, 128);
+    g.b = op_tok_bc_kmajor(w.vn16, d, bn_for((int)IT));
+    g.out32 = G + off[R_SP_W]; g.cm = mrnb_axis(IT); g.cn = mrnb_axis(1);
+    g.M = (int)IT; g.N = (int)IT; g.K = B * D; g.groups = 1; g.alpha = 1.f;
+    g.splitk = splitk_for(cdiv(IT, 128) * cdiv(IT, bn_for((int)IT)));
+    MRNB_TRY(mrnb_tc_gemm2(g, st));
+  }
+  {  // vn = LN_D(GELU(a1v)): da1[:, D:] (bf16 only), db1[D:], dgamma / dbeta
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    const int grid = (int)((M + 8 * 16 - 1) / (8 * 16));
+    ln_rows_bwd_kernel<true><<<grid > 0 ? grid : 1, 256, 0, st>>>(w.a1 + D, 2 * D, w.stats2, P + off[R_SN_W], w.dvn, nullptr,
+                                                                    w.da116 + D, 2 * D, nullptr, nullptr, G + off[R_SN_W],
+                                                                    G + off[R_SN_B], M, G + off[R_P1_B] + D);
+    MRNB_CHECK_LAUNCH("ln_rows_bwd_kernel");
+  }
+  // a1 = xn W1^T + b1
+  MRNB_TRY(dw_rows(d, nullptr, w.da116, 2 * D, 2 * D, nullptr, w.xn16, D, D, G + off[R_P1_W], st));
+  MRNB_TRY(dx_rows(d, nullptr, w.da116, 2 * D, 2 * D, P + off[R_P1_W], W16 + off[R_P1_W], D, w.dxn, D, st));
+  {  // xn = LN_D(x): dgamma / dbeta
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    const int grid = (int)((M + 8 * 16 - 1) / (8 * 16));
+    ln_rows_bwd_kernel<false><<<grid > 0 ? grid : 1, 256, 0, st>>>(x, D, w.stats1, P + off[R_N_W], w.dxn, nullptr, nullptr, D,
+                                                                     nullptr, nullptr, G + off[R_N_W], G + off[R_N_B], M);
     MRNB_CHECK_LAUNCH("ln_rows_bwd_kernel");
   }
   return MRNB_OK;
@@ -1113,17 +1430,21 @@ extern "C" int mrnb_router_backward(const float* params, const float* x, const f
                                         grads + off[R_ROUTE_B]);
     MRNB_CHECK_LAUNCH("route_bwd_kernel");
   }
-  {  // dWcr[j,(i,c)] = sum_(b,t) ds[(b,t),j] out[b,i,t,c]
-    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
-    MRNB_DISPATCH_I(launch_gate_head_dw, I, w.ds, w.out, B, T, grads + off[R_CR_W], st);
+  if (d.tc) {
+    MRNB_TRY(router_backward_gate_tc(params, x, d, grads, w, st));
+  } else {
+    {  // dWcr[j,(i,c)] = sum_(b,t) ds[(b,t),j] out[b,i,t,c]
+      MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+      MRNB_DISPATCH_I(launch_gate_head_dw, I, w.ds, w.out, B, T, grads + off[R_CR_W], st);
+    }
+    MRNB_TRY(colsum(w.ds, mrnb_axis(I), mrnb_axis(1), B * T, I, grads + off[R_CR_B], st));
+    {  // dout[b,i,t,c] = sum_j ds[(b,t),j] Wcr[j,(i,c)]
+      MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+      const long total4 = d.M * D / 4;
+      LAUNCH_EW(dout_kernel, total4, w.ds, params + off[R_CR_W], I, T, total4, w.dout, nullptr);
+    }
+    MRNB_TRY(dm_router_backward_core(params, x, d, grads, nullptr, w, st));
   }
-  MRNB_TRY(colsum(w.ds, mrnb_axis(I), mrnb_axis(1), B * T, I, grads + off[R_CR_B], st));
-  {  // dout[b,i,t,c] = sum_j ds[(b,t),j] Wcr[j,(i,c)]
-    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
-    const long total4 = d.M * D / 4;
-    LAUNCH_EW(dout_kernel, total4, w.ds, params + off[R_CR_W], I, T, total4, w.dout, d.tc ? w.dout16 : nullptr);
-  }
-  MRNB_TRY(dm_router_backward_core(params, x, d, grads, nullptr, w, st));
   if (padded) {
     MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
     const RepackTable tb = make_table(I, Tu, Tp, D);
