@@ -87,6 +87,18 @@ __device__ __forceinline__ __half2 gelu_fast_h2(__half2 x) {
   const __half2 h = __hmul2(x, __float2half2_rn(0.5f));
   return __hfma2(h, t, h);
 }
+// d/dx [x Phi(x)] = Phi(x) + x phi(x) with the same minimax Phi as gelu_fast and phi through ex2.approx: for gradients
+// that are rounded to bf16 GEMM operands (tensor-core mode); |error| < 1e-4.
+__device__ __forceinline__ float gelu_fast_grad(float x) {
+  const float xx = x * x;
+  const float x2 = fminf(xx, 49.0f);
+  float p = fmaf(x2, -3.51516867e-4f, 3.70056465e-2f);
+  p = fmaf(x2, p, 0.797507884f);
+  float t, e;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * p));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xx * -0.72134752044448170368f));     // exp(-x^2 / 2)
+  return fmaf(0.5f, t, 0.5f) + x * 0.39894228040143267794f * e;
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
   const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);

@@ -88,6 +88,20 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// the k-dependent coordinates only (dims sourced from k), the others are left as they are: the producer computes the
+// m/n- and group-sourced coordinates once per tile and refreshes only these per k-block (a single thread issues every
+// TMA of the CTA: its integer divisions were the limiter of the MN-major weight-gradient GEMMs)
+__device__ __forceinline__ void recipe_coords_k(const MrnbTmaRecipe& r, int k, int (&c)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (r.src[j] != MRNB_SRC_K) continue;
+    int v = k;
+    if (r.div[j] > 1) v /= r.div[j];
+    if (r.mod[j] > 0) v %= r.mod[j];
+    if (r.flip[j] > 0) v = r.flip[j] - 1 - v;
+    c[j] = v;
+  }
+}
 __device__ __forceinline__ void recipe_coords(const MrnbTmaRecipe& r, int mn, int k, int g, int (&c)[4]) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -169,34 +183,31 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (long t = blockIdx.x; t < total; t += gridDim.x) {
         int n0, m0, g, kb0, KB;
         tile_coords(t, n0, m0, g, kb0, KB);
+        constexpr int ACH = A_MN ? BM / 64 : 1, BCH = B_MN ? BN / 64 : 1;
+        int ca[ACH][4], cb[BCH][4];
+#pragma unroll
+        for (int ch = 0; ch < ACH; ++ch) recipe_coords(ra, m0 + ch * 64, kb0 * BK, g, ca[ch]);
+#pragma unroll
+        for (int ch = 0; ch < BCH; ++ch) recipe_coords(rb, n0 + ch * 64, kb0 * BK, g, cb[ch]);
         for (int i = 0; i < KB; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
+          const int k0 = (kb0 + i) * BK;
+          if (i > 0) {
+#pragma unroll
+            for (int ch = 0; ch < ACH; ++ch) recipe_coords_k(ra, k0, ca[ch]);
+#pragma unroll
+            for (int ch = 0; ch < BCH; ++ch) recipe_coords_k(rb, k0, cb[ch]);
+          }
           mbar_wait(&empty_bar[s], ph ^ 1u);
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
-          const int k0 = (kb0 + i) * BK;
-          int c[4];
-          if (A_MN) {
 #pragma unroll
-            for (int ch = 0; ch < BM / 64; ++ch) {
-              recipe_coords(ra, m0 + ch * 64, k0, g, c);
-              tma_load_4d(sa + ch * (BK * 128), &tmA, &full_bar[s], c[0], c[1], c[2], c[3]);
-            }
-          } else {
-            recipe_coords(ra, m0, k0, g, c);
-            tma_load_4d(sa, &tmA, &full_bar[s], c[0], c[1], c[2], c[3]);
-          }
-          if (B_MN) {
+          for (int ch = 0; ch < ACH; ++ch)
+            tma_load_4d(sa + ch * (BK * 128), &tmA, &full_bar[s], ca[ch][0], ca[ch][1], ca[ch][2], ca[ch][3]);
 #pragma unroll
-            for (int ch = 0; ch < BN / 64; ++ch) {
-              recipe_coords(rb, n0 + ch * 64, k0, g, c);
-              tma_load_4d(sa + A_BYTES + ch * (BK * 128), &tmB, &full_bar[s], c[0], c[1], c[2], c[3]);
-            }
-          } else {
-            recipe_coords(rb, n0, k0, g, c);
-            tma_load_4d(sa + A_BYTES, &tmB, &full_bar[s], c[0], c[1], c[2], c[3]);
-          }
+          for (int ch = 0; ch < BCH; ++ch)
+            tma_load_4d(sa + A_BYTES + ch * (BK * 128), &tmB, &full_bar[s], cb[ch][0], cb[ch][1], cb[ch][2], cb[ch][3]);
         }
       }
     }
@@ -248,8 +259,11 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const long om = rok ? og + (long)(row / ep.cm.inner) * ep.cm.so + (long)(row % ep.cm.inner) * ep.cm.si : 0;
       const float bm = (ep.bias_m && rok) ? ep.bias_m[row] : 0.f;
       if (ep.simple) {
-        // lean epilogue: 32 columns per TMEM load, a whole 128-byte line of the row per thread, no index arithmetic
-        const long orow = og + (long)row * ep.cm.si;
+        // lean epilogue: 32 columns per TMEM load, a whole 128-byte line of the row per thread, no index arithmetic.
+        // simple == 1: plain row-major output; simple == 2: two-level addressing whose BN columns of a tile are contiguous
+        // (cn.si == 1, cn.inner a multiple of BN): the row base takes the two-level row offset + the tile's column base
+        const long orow = ep.simple == 1 ? og + (long)row * ep.cm.si
+                                         : om + (long)(n0 / ep.cn.inner) * ep.cn.so + (long)(n0 % ep.cn.inner) - n0;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           const int col0 = n0 + c0;
@@ -460,11 +474,15 @@ int launch2(const MrnbTcGemm2& p, cudaStream_t st) {
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(tc_gemm2_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
   ep.simple = (p.cn.si == 1 && p.cn.inner >= p.N && p.cm.inner >= p.M) ? 1 : 0;
+  if (!ep.simple && p.cn.si == 1 && p.cn.inner % BN == 0 && p.N % BN == 0 && (p.cn.so % 4) == 0 && (p.cm.si % 4) == 0 &&
+      (p.cm.so % 4) == 0 && p.splitk <= 1)
+    ep.simple = 2;
   ep.tiles_n = cdiv(p.N, BN); ep.tiles_m = cdiv(p.M, BM);
   ep.total_tiles = (long)ep.tiles_n * ep.tiles_m * p.groups * splits;
   static int n_sm = 0;
   if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
-  const long cap = 2L * n_sm;                    // two CTAs per SM: 2 x (2 x BN <= 256) TMEM columns, 2 x <= 97 KiB smem
+  // BN <= 128: two CTAs per SM (2 x (2 x BN <= 256) TMEM columns, 2 x <= 97 KiB smem); BN = 256: one (512 columns, 145 KiB)
+  const long cap = (BN > 128 ? 1L : 2L) * n_sm;
   const int grid = (int)(ep.total_tiles < cap ? ep.total_tiles : cap);
   tc_gemm2_kernel<BN, A_MN, B_MN><<<grid, 192, smem, st>>>(tmA, tmB, p.a.recipe, p.b.recipe, ep);
   MRNB_CHECK_LAUNCH("tc_gemm2_kernel");
@@ -480,13 +498,14 @@ int mrnb_tc_gemm2(const MrnbTcGemm2& p, cudaStream_t st) {
                  "tc_gemm2: split-K supports a raw fp32 accumulate only");
   MrnbProfScope prof(MRNB_PROF_TCGEMM2, st, 2.0 * p.M * p.N * p.K * p.groups,
                      (double)p.groups * (2.0 * p.M * p.K + 2.0 * p.N * p.K + 4.0 * p.M * p.N));
-  const bool wide = p.N >= 128;
+  const int bn = p.bn ? p.bn : (p.N >= 128 ? 128 : 64);
+  MRNB_CHECK_ARG(bn == 64 || bn == 128 || bn == 256, "tc_gemm2: tile width %d", bn);
 #define GO(BN_)                                                                                   \
   if (p.a.mn_major && p.b.mn_major) return launch2<BN_, true, true>(p, st);                       \
   if (p.a.mn_major) return launch2<BN_, true, false>(p, st);                                      \
   if (p.b.mn_major) return launch2<BN_, false, true>(p, st);                                      \
   return launch2<BN_, false, false>(p, st);
-  if (wide) { GO(128) } else { GO(64) }
+  if (bn == 256) { GO(256) } else if (bn == 128) { GO(128) } else { GO(64) }
 #undef GO
 }
 

@@ -206,7 +206,7 @@ lnT_bwd_kernel(const float* __restrict__ y, const float* __restrict__ stats, con
 
 // Row-LN backward (D=256, warp per row).  xin is the LN input (or its pre-GELU activation when GELU_IN):
 //   dxin = LNbwd(dyn) [* GELU'(pre)]  (+ add1 + add2);  dgamma/dbeta accumulated with block partials + atomics.
-template <bool GELU_IN>
+template <bool GELU_IN, bool FAST = false>
 __global__ void __launch_bounds__(256)
 ln_rows_bwd_kernel(const float* __restrict__ xin, long ldx, const float* __restrict__ stats,
                    const float* __restrict__ gamma, const float* __restrict__ dyn, float* __restrict__ dxin,
@@ -228,7 +228,7 @@ ln_rows_bwd_kernel(const float* __restrict__ xin, long ldx, const float* __restr
     for (int j = 0; j < 8; ++j) {
       const int idx = (j / 4) * 128 + lane * 4 + (j % 4);
       pre[j] = xin[row * ldx + idx];
-      const float xv = GELU_IN ? gelu_erf(pre[j]) : pre[j];
+      const float xv = GELU_IN ? (FAST ? gelu_fast(pre[j]) : gelu_erf(pre[j])) : pre[j];
       xh[j] = (xv - mean) * rstd;
       const float d = dyn[row * RD + idx];
       dxh[j] = d * gamma[idx];
@@ -242,7 +242,7 @@ ln_rows_bwd_kernel(const float* __restrict__ xin, long ldx, const float* __restr
       for (int j = 0; j < 8; ++j) {
         const int idx = (j / 4) * 128 + lane * 4 + (j % 4);
         g[j] = rstd * (dxh[j] - m1 - xh[j] * m2);
-        if (GELU_IN) g[j] *= gelu_erf_grad(pre[j]);
+        if (GELU_IN) g[j] *= FAST ? gelu_fast_grad(pre[j]) : gelu_erf_grad(pre[j]);
         if (add1) g[j] += add1[row * RD + idx];
         if (add2) g[j] += add2[row * RD + idx];
         ac[j] += g[j];
@@ -630,32 +630,54 @@ int colsum(const float* X, MrnbAxis am, MrnbAxis an, int M, int N, float* out, c
 // weighted sums ow / y2w ride in the pass that produces dg2 = dy2 * y.
 // =====================================================================================================================
 
-// q[b,i,:] = sum_j dr[b,j] Wcr[j,(i,:)] ;  p[b,i,:] = q[b,i,:] W3 ;  db3 += wsum * q ;  dbcr += wsum * dr      (block per (b,i))
+// q[b,i,:] = sum_j dr[b,j] Wcr[j,(i,:)] ;  p[b,i,:] = q[b,i,:] W3 ;  db3 += wsum * q ;  dbcr += wsum * dr
+// QR (b,i) rows per block so that W3 streams from L2 once per QR rows; thread = channel.
+constexpr int QR = 8;
 __global__ void __launch_bounds__(RD)
 gate_qp_kernel(const float* __restrict__ dr, const float* __restrict__ Wcr, const float* __restrict__ W3,
-               const float* __restrict__ wr, int I, int T, float* __restrict__ q, float* __restrict__ p,
+               const float* __restrict__ wr, int I, int T, int rows, float* __restrict__ q, float* __restrict__ p,
                float* __restrict__ db3, float* __restrict__ dbcr) {
-  __shared__ float sq[RD];
+  __shared__ float sq[QR][RD];
   __shared__ float swsum;
-  const int bi = blockIdx.x, b = bi / I, i = bi % I, c = threadIdx.x;
+  const int c = threadIdx.x, r0 = blockIdx.x * QR;
   if (threadIdx.x < 32) {
     float s = 0.f;
     for (int t = threadIdx.x; t < T; t += 32) s += wr[t];
     s = warp_sum(s);
     if (threadIdx.x == 0) swsum = s;
   }
-  float acc = 0.f;
-  for (int j = 0; j < I; ++j) acc = fmaf(dr[b * I + j], Wcr[(long)j * I * RD + (long)i * RD + c], acc);
-  sq[c] = acc;
-  q[(long)bi * RD + c] = acc;
+  float qs = 0.f;
+#pragma unroll
+  for (int r = 0; r < QR; ++r) {
+    const int bi = r0 + r;
+    float acc = 0.f;
+    if (bi < rows) {
+      const int b = bi / I, i = bi % I;
+      for (int j = 0; j < I; ++j) acc = fmaf(dr[b * I + j], Wcr[(long)j * I * RD + (long)i * RD + c], acc);
+      q[(long)bi * RD + c] = acc;
+    }
+    sq[r][c] = acc;
+    qs += acc;
+  }
   __syncthreads();
   const float wsum = swsum;
-  atomicAdd(db3 + c, acc * wsum);
-  if (i == 0 && c < I) atomicAdd(dbcr + c, dr[b * I + c] * wsum);
-  float pk = 0.f;
-#pragma unroll 8
-  for (int n = 0; n < RD; ++n) pk = fmaf(sq[n], W3[(long)n * RD + c], pk);
-  p[(long)bi * RD + c] = pk;
+  atomicAdd(db3 + c, qs * wsum);
+  if (c < QR * I) {                                    // dbcr[j] += wsum * dr[b,j] once per sample (from its i == 0 row)
+    const int bi = r0 + c / I, j = c % I;
+    if (bi < rows && bi % I == 0) atomicAdd(dbcr + j, dr[(bi / I) * I + j] * wsum);
+  }
+  float pk[QR];
+#pragma unroll
+  for (int r = 0; r < QR; ++r) pk[r] = 0.f;
+#pragma unroll 4
+  for (int n = 0; n < RD; ++n) {
+    const float wv = W3[(long)n * RD + c];
+#pragma unroll
+    for (int r = 0; r < QR; ++r) pk[r] = fmaf(sq[r][n], wv, pk[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < QR; ++r)
+    if (r0 + r < rows) p[(long)(r0 + r) * RD + c] = pk[r];
 }
 
 // One pass over out / y2 / y per (b,i):  ow = sum_t wr[t] out,  y2w = sum_t wr[t] y2,  dg2 = wr[t] p y (bf16 GEMM operand),
@@ -801,8 +823,8 @@ dg1_fused_kernel(const float* __restrict__ dg1, const float* __restrict__ v2, co
       const long o = row * RD + c * 128 + lane * 4, o2 = row * 2 * RD + c * 128 + lane * 4;
       const float4 g = *reinterpret_cast<const float4*>(dg1 + o), vv = *reinterpret_cast<const float4*>(v2 + o),
                    uu = *reinterpret_cast<const float4*>(u + o), aa = *reinterpret_cast<const float4*>(a1 + o2);
-      const float4 da = make_float4(g.x * vv.x * gelu_erf_grad(aa.x), g.y * vv.y * gelu_erf_grad(aa.y),
-                                    g.z * vv.z * gelu_erf_grad(aa.z), g.w * vv.w * gelu_erf_grad(aa.w));
+      const float4 da = make_float4(g.x * vv.x * gelu_fast_grad(aa.x), g.y * vv.y * gelu_fast_grad(aa.y),
+                                    g.z * vv.z * gelu_fast_grad(aa.z), g.w * vv.w * gelu_fast_grad(aa.w));
       const float4 dv = make_float4(g.x * uu.x, g.y * uu.y, g.z * uu.z, g.w * uu.w);
       ac[c * 4] += da.x; ac[c * 4 + 1] += da.y; ac[c * 4 + 2] += da.z; ac[c * 4 + 3] += da.w;
       rs += (dv.x + dv.y) + (dv.z + dv.w);
@@ -871,7 +893,10 @@ MrnbTcOperand nogroup(MrnbTcOperand o) {          // shared weight: ignore the g
 inline int bn_for(int N) { return N >= 128 ? 128 : 64; }
 // split-K factor of a weight-gradient GEMM with `tiles` output tiles: the largest split whose tiles x split work items
 // still fit ONE wave of the 2 x 148 persistent CTAs (a second, partly filled wave costs a whole tile duration)
-inline int splitk_for(int tiles) { const int s = 296 / (tiles > 0 ? tiles : 1); return s < 1 ? 1 : s; }
+inline int splitk_for(int tiles, int ctas = 296) { const int s = ctas / (tiles > 0 ? tiles : 1); return s < 1 ? 1 : s; }
+// channel mixing (K = N = I*D >= 1024): 128 x 256 tiles, one CTA per SM
+inline int bn_chan(long) { return 128; }   // 128 x 256 tiles at one CTA per SM measured slower (175 -> 246 us forward): the
+                                            // second co-resident CTA hides more latency than the wider tile saves in L2 traffic
 
 // out[rows, Nout] = A[rows, K] . W[Nout, K]^T (+bias, +res)   -- plain row-major Linear
 int linear_rows(const Dims& d, const float* A32, const bf16* A16, long lda, const float* W32, const bf16* W16, int Nout, int K,
@@ -957,9 +982,8 @@ int router_forward(const float* P, const float* x, const Dims& d, float* out_use
     MrnbTcGemm2 g{};
     g.a = nogroup(mrnb_operand_k2d(W16 + off[R_SP_W], IT, IT, IT, 128, 1));
     g.b = op_tok_c_mnmajor(w.vn16, d);
-    g.cm = mrnb_axis(D); g.cn = mrnb_axis(1); g.c_gstride = ITD;
+    g.out32 = w.v2; g.cm = mrnb_axis(D); g.cn = mrnb_axis(1); g.c_gstride = ITD;
     g.bias_m = P + off[R_SP_B]; g.M = (int)IT; g.N = D; g.K = (int)IT; g.groups = B; g.alpha = 1.f;
-    g.pre32 = w.v2; g.mul = w.u; g.out16 = w.g116;          // epilogue: v2 kept for the backward, g1 = u * v2 as the next operand
     MRNB_TRY(mrnb_tc_gemm2(g, st));
   } else {
     MrnbGemm g{};
@@ -970,9 +994,9 @@ int router_forward(const float* P, const float* x, const Dims& d, float* out_use
     g.bias_m = P + off[R_SP_B];
     MRNB_TRY(mrnb_sgemm(g, st));
   }
-  if (!tc) {
+  {   // g1 = u * v2 (a separate streaming pass: measured faster than a multiplier read in the GEMM's row-per-thread epilogue)
     MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
-    LAUNCH_EW(mul_kernel, M * D / 4, w.u, w.v2, w.g1, nullptr, M * D / 4);
+    LAUNCH_EW(mul_kernel, M * D / 4, w.u, w.v2, tc ? nullptr : w.g1, tc ? w.g116 : nullptr, M * D / 4);
   }
   // y = g1 W2^T + b2 + x
   MRNB_TRY(linear_rows(d, w.g1, w.g116, D, P + off[R_P2_W], W16 + off[R_P2_W], D, D, P + off[R_P2_B], x, w.y, D, st));
@@ -986,10 +1010,10 @@ int router_forward(const float* P, const float* x, const Dims& d, float* out_use
   if (tc) {
     MrnbTcGemm2 g{};
     g.a = op_bt_ic_kmajor(w.gn16, d);
-    g.b = mrnb_operand_k2d(W16 + off[R_CP_W], ID, ID, ID, 128, 1);
-    g.cm = mrnb_axis2(T, D, ITD); g.cn = mrnb_axis2(D, 1, TD);
+    g.bn = bn_chan(ID);
+    g.b = mrnb_operand_k2d(W16 + off[R_CP_W], ID, ID, ID, g.bn, 1);
+    g.out32 = w.g2; g.cm = mrnb_axis2(T, D, ITD); g.cn = mrnb_axis2(D, 1, TD);
     g.bias_n = P + off[R_CP_B]; g.M = B * T; g.N = (int)ID; g.K = (int)ID; g.groups = 1; g.alpha = 1.f;
-    g.pre32 = w.g2; g.mul = w.y; g.out16 = w.y216;          // epilogue: g2 kept for the backward, y2 = y * g2 as the next operand
     MRNB_TRY(mrnb_tc_gemm2(g, st));
   } else {
     MrnbGemm g{};
@@ -1000,9 +1024,9 @@ int router_forward(const float* P, const float* x, const Dims& d, float* out_use
     g.bias_n = P + off[R_CP_B];
     MRNB_TRY(mrnb_sgemm(g, st));
   }
-  if (!tc) {
+  {
     MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
-    LAUNCH_EW(mul_kernel, M * D / 4, w.y, w.g2, w.y2, nullptr, M * D / 4);
+    LAUNCH_EW(mul_kernel, M * D / 4, w.y, w.g2, tc ? nullptr : w.y2, tc ? w.y216 : nullptr, M * D / 4);
   }
   // out = y2 W3^T + b3 + x
   MRNB_TRY(linear_rows(d, w.y2, w.y216, D, P + off[R_P3_W], W16 + off[R_P3_W], D, D, P + off[R_P3_B], x, out, D, st));
@@ -1041,7 +1065,7 @@ int dm_router_backward_core(const float* P, const float* x, const Dims& d, float
       g.a = op_bt_ic_kmajor(w.dg216, d);
       g.b = mrnb_operand_mn2d(W16 + off[R_CP_W], ID, ID, ID, 1);
       g.out32 = w.dgn; g.cm = mrnb_axis2(T, D, ITD); g.cn = mrnb_axis2(D, 1, TD);
-      g.M = B * T; g.N = (int)ID; g.K = (int)ID; g.groups = 1; g.alpha = 1.f;
+      g.M = B * T; g.N = (int)ID; g.K = (int)ID; g.groups = 1; g.alpha = 1.f; g.bn = bn_chan(ID);
       MRNB_TRY(mrnb_tc_gemm2(g, st));
     }
     {  // dWc[k,j] = sum_(b,t) dg2[(b,t),k] gn[(b,t),j]
@@ -1050,7 +1074,8 @@ int dm_router_backward_core(const float* P, const float* x, const Dims& d, float
       g.b = op_ic_bt_mnmajor(w.gn16, d);
       g.out32 = G + off[R_CP_W]; g.cm = mrnb_axis(ID); g.cn = mrnb_axis(1);
       g.M = (int)ID; g.N = (int)ID; g.K = B * T; g.groups = 1; g.alpha = 1.f;
-      g.splitk = splitk_for(cdiv(ID, 128) * cdiv(ID, 128));
+      g.bn = bn_chan(ID);
+      g.splitk = g.bn == 256 ? splitk_for(cdiv(ID, 128) * cdiv(ID, 256), 148) : splitk_for(cdiv(ID, 128) * cdiv(ID, 128));
       MRNB_TRY(mrnb_tc_gemm2(g, st));
     }
   } else {
@@ -1168,12 +1193,12 @@ int router_backward_gate_tc(const float* P, const float* x, const Dims& d, float
   const float* wr = P + off[R_ROUTE_W];
   {
     MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
-    gate_qp_kernel<<<B * I, RD, 0, st>>>(w.dr, P + off[R_CR_W], P + off[R_P3_W], wr, I, T, w.gq, w.gp, G + off[R_P3_B],
-                                         G + off[R_CR_B]);
+    gate_qp_kernel<<<cdiv((long)B * I, QR), RD, 0, st>>>(w.dr, P + off[R_CR_W], P + off[R_P3_W], wr, I, T, B * I, w.gq, w.gp,
+                                                         G + off[R_P3_B], G + off[R_CR_B]);
     MRNB_CHECK_LAUNCH("gate_qp_kernel");
     tsum_dg2_kernel<<<B * I, 128, 0, st>>>(w.out, w.y216, w.y, w.gp, wr, I, T, w.ow, w.y2w, w.dg216, G + off[R_CP_B]);
     MRNB_CHECK_LAUNCH("tsum_dg2_kernel");
-    gate_dwcr_kernel<<<dim3(cdiv(ID, 256), B >= 64 ? 8 : 1), 256, 0, st>>>(w.dr, w.ow, B, I, ID, G + off[R_CR_W]);
+    gate_dwcr_kernel<<<dim3(cdiv(ID, 256), B >= 64 ? 32 : 1), 256, 0, st>>>(w.dr, w.ow, B, I, ID, G + off[R_CR_W]);
     MRNB_CHECK_LAUNCH("gate_dwcr_kernel");
   }
   {  // dW3[n,k] = sum_(b,i) q[(b,i),n] y2w[(b,i),k]   (B*I rows: fp32 on the CUDA cores)
@@ -1190,7 +1215,7 @@ int router_backward_gate_tc(const float* P, const float* x, const Dims& d, float
     g.a = op_bt_ic_kmajor(w.dg216, d);
     g.b = mrnb_operand_mn2d(W16 + off[R_CP_W], ID, ID, ID, 1);
     g.out32 = w.dgn; g.cm = mrnb_axis2(T, D, ITD); g.cn = mrnb_axis2(D, 1, TD);
-    g.M = B * T; g.N = (int)ID; g.K = (int)ID; g.groups = 1; g.alpha = 1.f;
+    g.M = B * T; g.N = (int)ID; g.K = (int)ID; g.groups = 1; g.alpha = 1.f; g.bn = bn_chan(ID);
     MRNB_TRY(mrnb_tc_gemm2(g, st));
   }
   {  // dWc[k,j] = sum_(b,t) dg2[(b,t),k] gn[(b,t),j]
@@ -1199,7 +1224,8 @@ int router_backward_gate_tc(const float* P, const float* x, const Dims& d, float
     g.b = op_ic_bt_mnmajor(w.gn16, d);
     g.out32 = G + off[R_CP_W]; g.cm = mrnb_axis(ID); g.cn = mrnb_axis(1);
     g.M = (int)ID; g.N = (int)ID; g.K = B * T; g.groups = 1; g.alpha = 1.f;
-    g.splitk = splitk_for(cdiv(ID, 128) * cdiv(ID, 128));
+    g.bn = bn_chan(ID);
+    g.splitk = g.bn == 256 ? splitk_for(cdiv(ID, 128) * cdiv(ID, 256), 148) : splitk_for(cdiv(ID, 128) * cdiv(ID, 128));
     MRNB_TRY(mrnb_tc_gemm2(g, st));
   }
   {
@@ -1238,9 +1264,9 @@ int router_backward_gate_tc(const float* P, const float* x, const Dims& d, float
   {  // vn = LN_D(GELU(a1v)): da1[:, D:] (bf16 only), db1[D:], dgamma / dbeta
     MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
     const int grid = (int)((M + 8 * 16 - 1) / (8 * 16));
-    ln_rows_bwd_kernel<true><<<grid > 0 ? grid : 1, 256, 0, st>>>(w.a1 + D, 2 * D, w.stats2, P + off[R_SN_W], w.dvn, nullptr,
-                                                                    w.da116 + D, 2 * D, nullptr, nullptr, G + off[R_SN_W],
-                                                                    G + off[R_SN_B], M, G + off[R_P1_B] + D);
+    ln_rows_bwd_kernel<true, true><<<grid > 0 ? grid : 1, 256, 0, st>>>(w.a1 + D, 2 * D, w.stats2, P + off[R_SN_W], w.dvn, nullptr,
+                                                                          w.da116 + D, 2 * D, nullptr, nullptr, G + off[R_SN_W],
+                                                                          G + off[R_SN_B], M, G + off[R_P1_B] + D);
     MRNB_CHECK_LAUNCH("ln_rows_bwd_kernel");
   }
   // a1 = xn W1^T + b1
