@@ -64,10 +64,48 @@ ln_rows_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int idx = (j / 4) * 128 + lane * 4 + (j % 4);
-    const float o = (v[j] - mean) * rstd * gamma[idx] + beta[idx];
+    float o = (v[j] - mean) * rstd;
+    if (gamma) o = o * gamma[idx] + beta[idx];          // gamma == nullptr: plain x-hat (the affine is folded into the next Linear)
     if (y) y[row * RD + idx] = o;
     if (y16) y16[row * RD + idx] = __float2bfloat16_rn(o);
   }
+}
+
+// Tensor-core mode folds LayerNorm 1's affine into proj_1 (xn W1^T + b1 = xhat (W1 diag(gamma))^T + (b1 + W1 beta)):
+//   forward:  W16[n,c] = bf16(W1[n,c] gamma[c]),  b1f[n] = b1[n] + sum_c W1[n,c] beta[c]            (block per output row n)
+__global__ void __launch_bounds__(RD)
+fold_ln_w1_kernel(const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, __nv_bfloat16* __restrict__ W16, float* __restrict__ b1f) {
+  __shared__ float sh[8];
+  const int n = blockIdx.x, c = threadIdx.x;
+  const float wv = W1[(long)n * RD + c];
+  W16[(long)n * RD + c] = __float2bfloat16_rn(wv * gamma[c]);
+  float s = warp_sum(wv * beta[c]);
+  if ((c & 31) == 0) sh[c >> 5] = s;
+  __syncthreads();
+  if (c == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k];
+    b1f[n] = b1[n] + t;
+  }
+}
+//   backward: with S = da1^T xhat [2D, D]:  dW1 = S diag(gamma) + db1 (x) beta,  dgamma[c] = sum_n W1[n,c] S[n,c],
+//             dbeta[c] = sum_n db1[n] W1[n,c]   -- the M-row GEMM dxn = da1 W1 and the LayerNorm-backward pass over x are
+//             not needed for the parameter gradients.   grid = row chunks of 32 output rows, thread = c
+__global__ void __launch_bounds__(RD)
+fold_ln_w1_bwd_kernel(const float* __restrict__ S, const float* __restrict__ db1, const float* __restrict__ W1,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, int nrows, float* __restrict__ dW1,
+                      float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = threadIdx.x, n0 = blockIdx.x * 32;
+  const float g = gamma[c], bt = beta[c];
+  float ag = 0.f, ab = 0.f;
+  for (int n = n0; n < n0 + 32 && n < nrows; ++n) {
+    const float sv = S[(long)n * RD + c], wv = W1[(long)n * RD + c], d = db1[n];
+    dW1[(long)n * RD + c] = fmaf(sv, g, d * bt);
+    ag = fmaf(wv, sv, ag); ab = fmaf(d, wv, ab);
+  }
+  atomicAdd(dgamma + c, ag); atomicAdd(dbeta + c, ab);
 }
 
 // a1 [rows, 2D] -> u = GELU(a1[:, :D]) ; vn = LN_D(GELU(a1[:, D:])) + stats
@@ -231,7 +269,7 @@ ln_rows_bwd_kernel(const float* __restrict__ xin, long ldx, const float* __restr
       const float xv = GELU_IN ? (FAST ? gelu_fast(pre[j]) : gelu_erf(pre[j])) : pre[j];
       xh[j] = (xv - mean) * rstd;
       const float d = dyn[row * RD + idx];
-      dxh[j] = d * gamma[idx];
+      dxh[j] = gamma ? d * gamma[idx] : d;
       ag[j] = fmaf(d, xh[j], ag[j]); ab[j] += d;
       m1 += dxh[j]; m2 = fmaf(dxh[j], xh[j], m2);
     }
@@ -258,12 +296,12 @@ ln_rows_bwd_kernel(const float* __restrict__ xin, long ldx, const float* __restr
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int idx = (j / 4) * 128 + lane * 4 + (j % 4);
-    atomicAdd(&sg[idx], ag[j]); atomicAdd(&sb[idx], ab[j]);
+    if (dgamma) { atomicAdd(&sg[idx], ag[j]); atomicAdd(&sb[idx], ab[j]); }
     if (dcol) atomicAdd(&sc[idx], ac[j]);
   }
   __syncthreads();
   for (int k = threadIdx.x; k < RD; k += 256) {
-    atomicAdd(dgamma + k, sg[k]); atomicAdd(dbeta + k, sb[k]);
+    if (dgamma) { atomicAdd(dgamma + k, sg[k]); atomicAdd(dbeta + k, sb[k]); }
     if (dcol) atomicAdd(dcol + k, sc[k]);
   }
 }
@@ -510,7 +548,8 @@ struct RouterWs {
   float *stats1, *xn, *a1, *u, *vn, *stats2, *v2, *g1, *y, *statsT, *gn, *g2, *y2, *out, *s;
   // backward temporaries
   float *dr, *ds, *dout, *dy2, *dy, *dg2, *dgn, *dg1, *du, *dv2, *dvn, *da1, *dxn;
-  float *gq, *gp, *ow, *y2w;            // gate-head driven backward: [B*I, D] each
+  float *gp, *ow; bf16 *gq16, *y2w16;   // gate-head driven backward: [B*I, D] each
+  float *b1f, *S1;                      // folded proj_1 bias [2D]; S = da1^T xhat [2D, D]
   // bf16 shadows (tensor-core mode): GEMM operands only
   bf16 *w16, *xn16, *vn16, *g116, *gn16, *y216, *dout16, *dg216, *dy16, *dv216, *da116;
   size_t bytes;
@@ -528,13 +567,15 @@ RouterWs carve(char* base, int B, int I, int T, int D, bool bwd) {
   w.v2 = take(MD); w.g1 = take(MD); w.y = take(MD); w.statsT = take((size_t)B * I * D * 2); w.gn = take(MD);
   w.g2 = take(MD); w.y2 = take(MD); w.out = take(MD); w.s = take((size_t)B * T * I);
   w.w16 = take16(nparam); w.xn16 = take16(MD); w.vn16 = take16(MD); w.g116 = take16(MD); w.gn16 = take16(MD);
-  w.y216 = take16(MD);
+  w.y216 = take16(MD); w.b1f = take((size_t)2 * D);
   if (bwd) {
     w.dr = take((size_t)B * I); w.ds = take((size_t)B * T * I); w.dout = take(MD); w.dy2 = take(MD); w.dy = take(MD);
     w.dg2 = take(MD); w.dgn = take(MD); w.dg1 = take(MD); w.du = take(MD); w.dv2 = take(MD); w.dvn = take(MD);
     w.da1 = take(MD * 2); w.dxn = take(MD);
     w.dout16 = take16(MD); w.dg216 = take16(MD); w.dy16 = take16(MD); w.dv216 = take16(MD); w.da116 = take16(MD * 2);
-    w.gq = take((size_t)B * I * D); w.gp = take((size_t)B * I * D); w.ow = take((size_t)B * I * D); w.y2w = take((size_t)B * I * D);
+    w.S1 = take((size_t)2 * D * D);
+    const size_t rows_p = ((size_t)B * I + 127) / 128 * 128;   // the collapsed GEMMs run on B*I rows padded to a row tile
+    w.gp = take(rows_p * D); w.ow = take((size_t)B * I * D); w.gq16 = take16(rows_p * D); w.y2w16 = take16(rows_p * D);
   }
   w.bytes = o + 256;
   return w;
@@ -630,62 +671,33 @@ int colsum(const float* X, MrnbAxis am, MrnbAxis an, int M, int N, float* out, c
 // weighted sums ow / y2w ride in the pass that produces dg2 = dy2 * y.
 // =====================================================================================================================
 
-// q[b,i,:] = sum_j dr[b,j] Wcr[j,(i,:)] ;  p[b,i,:] = q[b,i,:] W3 ;  db3 += wsum * q ;  dbcr += wsum * dr
-// QR (b,i) rows per block so that W3 streams from L2 once per QR rows; thread = channel.
-constexpr int QR = 8;
+// q[b,i,:] = sum_j dr[b,j] Wcr[j,(i,:)] (fp32 + bf16 GEMM operand) ;  db3 += wsum * q ;  dbcr += wsum * dr   (block per (b,i))
 __global__ void __launch_bounds__(RD)
-gate_qp_kernel(const float* __restrict__ dr, const float* __restrict__ Wcr, const float* __restrict__ W3,
-               const float* __restrict__ wr, int I, int T, int rows, float* __restrict__ q, float* __restrict__ p,
-               float* __restrict__ db3, float* __restrict__ dbcr) {
-  __shared__ float sq[QR][RD];
+gate_q_kernel(const float* __restrict__ dr, const float* __restrict__ Wcr, const float* __restrict__ wr, int I, int T,
+              __nv_bfloat16* __restrict__ q16, float* __restrict__ db3, float* __restrict__ dbcr) {
   __shared__ float swsum;
-  const int c = threadIdx.x, r0 = blockIdx.x * QR;
+  const int bi = blockIdx.x, b = bi / I, i = bi % I, c = threadIdx.x;
   if (threadIdx.x < 32) {
     float s = 0.f;
     for (int t = threadIdx.x; t < T; t += 32) s += wr[t];
     s = warp_sum(s);
     if (threadIdx.x == 0) swsum = s;
   }
-  float qs = 0.f;
-#pragma unroll
-  for (int r = 0; r < QR; ++r) {
-    const int bi = r0 + r;
-    float acc = 0.f;
-    if (bi < rows) {
-      const int b = bi / I, i = bi % I;
-      for (int j = 0; j < I; ++j) acc = fmaf(dr[b * I + j], Wcr[(long)j * I * RD + (long)i * RD + c], acc);
-      q[(long)bi * RD + c] = acc;
-    }
-    sq[r][c] = acc;
-    qs += acc;
-  }
+  float acc = 0.f;
+  for (int j = 0; j < I; ++j) acc = fmaf(dr[b * I + j], Wcr[(long)j * I * RD + (long)i * RD + c], acc);
+  q16[(long)bi * RD + c] = __float2bfloat16_rn(acc);
   __syncthreads();
   const float wsum = swsum;
-  atomicAdd(db3 + c, qs * wsum);
-  if (c < QR * I) {                                    // dbcr[j] += wsum * dr[b,j] once per sample (from its i == 0 row)
-    const int bi = r0 + c / I, j = c % I;
-    if (bi < rows && bi % I == 0) atomicAdd(dbcr + j, dr[(bi / I) * I + j] * wsum);
-  }
-  float pk[QR];
-#pragma unroll
-  for (int r = 0; r < QR; ++r) pk[r] = 0.f;
-#pragma unroll 4
-  for (int n = 0; n < RD; ++n) {
-    const float wv = W3[(long)n * RD + c];
-#pragma unroll
-    for (int r = 0; r < QR; ++r) pk[r] = fmaf(sq[r][n], wv, pk[r]);
-  }
-#pragma unroll
-  for (int r = 0; r < QR; ++r)
-    if (r0 + r < rows) p[(long)(r0 + r) * RD + c] = pk[r];
+  atomicAdd(db3 + c, acc * wsum);
+  if (i == 0 && c < I) atomicAdd(dbcr + c, dr[b * I + c] * wsum);
 }
 
-// One pass over out / y2 / y per (b,i):  ow = sum_t wr[t] out,  y2w = sum_t wr[t] y2,  dg2 = wr[t] p y (bf16 GEMM operand),
+// One pass over out / y2 / y per (b,i):  ow = sum_t wr[t] out,  y2w = sum_t wr[t] y2 (bf16 GEMM operand),  dg2 = wr[t] p y (bf16),
 // dbc[(i,c)] += sum_t dg2.   128 threads x 2 channels.
 __global__ void __launch_bounds__(128)
 tsum_dg2_kernel(const float* __restrict__ out, const __nv_bfloat16* __restrict__ y216, const float* __restrict__ y,
                 const float* __restrict__ p, const float* __restrict__ wr, int I, int T, float* __restrict__ ow,
-                float* __restrict__ y2w, __nv_bfloat16* __restrict__ dg216, float* __restrict__ dbc) {
+                __nv_bfloat16* __restrict__ y2w16, __nv_bfloat16* __restrict__ dg216, float* __restrict__ dbc) {
   __shared__ float swr[128];
   const long bi = blockIdx.x;
   const int i = (int)(bi % I), c = threadIdx.x * 2;
@@ -708,7 +720,7 @@ tsum_dg2_kernel(const float* __restrict__ out, const __nv_bfloat16* __restrict__
     *reinterpret_cast<__nv_bfloat162*>(dg216 + o) = __floats2bfloat162_rn(dx, dy);
   }
   *reinterpret_cast<float2*>(ow + bi * RD + c) = aow;
-  *reinterpret_cast<float2*>(y2w + bi * RD + c) = ay;
+  *reinterpret_cast<__nv_bfloat162*>(y2w16 + bi * RD + c) = __floats2bfloat162_rn(ay.x, ay.y);
   atomicAdd(dbc + (long)i * RD + c, ad.x);
   atomicAdd(dbc + (long)i * RD + c + 1, ad.y);
 }
@@ -964,13 +976,20 @@ int router_forward(const float* P, const float* x, const Dims& d, float* out_use
   float* out = w.out;   // kept in the workspace for the backward; copied to the caller's buffer at the end
   {
     MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
-    if (tc) LAUNCH_EW(cast16_kernel, nparam, P, w.w16, nparam);
-    ln_rows_fwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(x, P + off[R_N_W], P + off[R_N_B], tc ? nullptr : w.xn, tc ? w.xn16 : nullptr,
-                                                   w.stats1, M, 1e-5f);
+    if (tc) {
+      LAUNCH_EW(cast16_kernel, nparam, P, w.w16, nparam);
+      fold_ln_w1_kernel<<<2 * D, RD, 0, st>>>(P + off[R_P1_W], P + off[R_P1_B], P + off[R_N_W], P + off[R_N_B],
+                                              w.w16 + off[R_P1_W], w.b1f);
+      MRNB_CHECK_LAUNCH("fold_ln_w1_kernel");
+    }
+    // tensor-core mode: xn16 holds the plain x-hat, LayerNorm 1's affine lives in the folded proj_1 weights / bias
+    ln_rows_fwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(x, tc ? nullptr : P + off[R_N_W], P + off[R_N_B], tc ? nullptr : w.xn,
+                                                   tc ? w.xn16 : nullptr, w.stats1, M, 1e-5f);
     MRNB_CHECK_LAUNCH("ln_rows_fwd_kernel");
   }
   // a1 = xn W1^T + b1
-  MRNB_TRY(linear_rows(d, w.xn, w.xn16, D, P + off[R_P1_W], W16 + off[R_P1_W], 2 * D, D, P + off[R_P1_B], nullptr, w.a1, 2 * D, st));
+  MRNB_TRY(linear_rows(d, w.xn, w.xn16, D, P + off[R_P1_W], W16 + off[R_P1_W], 2 * D, D, tc ? w.b1f : P + off[R_P1_B], nullptr,
+                       w.a1, 2 * D, st));
   {
     MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
     gelu_ln_fwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(w.a1, P + off[R_SN_W], P + off[R_SN_B], w.u, tc ? nullptr : w.vn,
@@ -1039,6 +1058,19 @@ int router_forward(const float* P, const float* x, const Dims& d, float* out_use
     MRNB_CHECK_LAUNCH("gate_finish_kernel");
   }
   if (out_user) cudaMemcpyAsync(out_user, out, (size_t)M * D * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  return MRNB_OK;
+}
+
+// Tensor-core mode, proj_1 + LayerNorm 1 parameter gradients from da1 (bf16) and db1 = G[R_P1_B] (complete):
+// S = da1^T xhat on tcgen05 (split-K), then the [2D, D] fold kernel.
+int ln1_fold_backward(const float* P, const long* off, const Dims& d, float* G, RouterWs& w, cudaStream_t st) {
+  const int D = d.D;
+  cudaMemsetAsync(w.S1, 0, (size_t)2 * D * D * sizeof(float), st);
+  MRNB_TRY(dw_rows(d, nullptr, w.da116, 2 * D, 2 * D, nullptr, w.xn16, D, D, w.S1, st));
+  MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+  fold_ln_w1_bwd_kernel<<<cdiv(2 * D, 32), RD, 0, st>>>(w.S1, G + off[R_P1_B], P + off[R_P1_W], P + off[R_N_W], P + off[R_N_B],
+                                                        2 * D, G + off[R_P1_W], G + off[R_N_W], G + off[R_N_B]);
+  MRNB_CHECK_LAUNCH("fold_ln_w1_bwd_kernel");
   return MRNB_OK;
 }
 
@@ -1167,8 +1199,20 @@ int dm_router_backward_core(const float* P, const float* x, const Dims& d, float
     LAUNCH_EW(gelu_bwd_kernel, M * D, w.a1, w.du, w.da1, tc ? w.da116 : nullptr, M);
   }
   // a1 = xn W1^T + b1
-  MRNB_TRY(dw_rows(d, w.da1, w.da116, 2 * D, 2 * D, w.xn, w.xn16, D, D, G + off[R_P1_W], st));
   MRNB_TRY(colsum(w.da1, mrnb_axis(2 * D), mrnb_axis(1), (int)M, 2 * D, G + off[R_P1_B], st));
+  if (tc) {
+    MRNB_TRY(ln1_fold_backward(P, off, d, G, w, st));
+    if (dx) {   // dxhat = da1 (W1 diag(gamma)): the folded bf16 weights already carry gamma
+      MRNB_TRY(dx_rows(d, w.da1, w.da116, 2 * D, 2 * D, P + off[R_P1_W], W16 + off[R_P1_W], D, w.dxn, D, st));
+      MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+      const int grid = (int)((M + 8 * 16 - 1) / (8 * 16));
+      ln_rows_bwd_kernel<false><<<grid > 0 ? grid : 1, 256, 0, st>>>(x, D, w.stats1, nullptr, w.dxn, dx, nullptr, D, w.dy, w.dout,
+                                                                       nullptr, nullptr, M);
+      MRNB_CHECK_LAUNCH("ln_rows_bwd_kernel");
+    }
+    return MRNB_OK;
+  }
+  MRNB_TRY(dw_rows(d, w.da1, w.da116, 2 * D, 2 * D, w.xn, w.xn16, D, D, G + off[R_P1_W], st));
   MRNB_TRY(dx_rows(d, w.da1, w.da116, 2 * D, 2 * D, P + off[R_P1_W], W16 + off[R_P1_W], D, w.dxn, D, st));
   {  // xn = LN_D(x): dgamma/dbeta (+ dx = LNbwd + dy + dout when requested)
     MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
@@ -1191,25 +1235,28 @@ int router_backward_gate_tc(const float* P, const float* x, const Dims& d, float
   const long M = d.M, IT = d.IT, ID = d.ID, TD = d.TD, ITD = d.ITD;
   const bf16* W16 = w.w16;
   const float* wr = P + off[R_ROUTE_W];
+  Dims dq = d;                        // the collapsed last Linear: B*I rows (zero-padded to a 128-row tile) instead of B*I*T
+  dq.M = ((long)B * I + 127) / 128 * 128;
+  if (dq.M > (long)B * I) {
+    cudaMemsetAsync(w.gq16 + (long)B * I * D, 0, (size_t)(dq.M - (long)B * I) * D * sizeof(bf16), st);
+    cudaMemsetAsync(w.y2w16 + (long)B * I * D, 0, (size_t)(dq.M - (long)B * I) * D * sizeof(bf16), st);
+  }
   {
     MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
-    gate_qp_kernel<<<cdiv((long)B * I, QR), RD, 0, st>>>(w.dr, P + off[R_CR_W], P + off[R_P3_W], wr, I, T, B * I, w.gq, w.gp,
-                                                         G + off[R_P3_B], G + off[R_CR_B]);
-    MRNB_CHECK_LAUNCH("gate_qp_kernel");
-    tsum_dg2_kernel<<<B * I, 128, 0, st>>>(w.out, w.y216, w.y, w.gp, wr, I, T, w.ow, w.y2w, w.dg216, G + off[R_CP_B]);
+    gate_q_kernel<<<B * I, RD, 0, st>>>(w.dr, P + off[R_CR_W], wr, I, T, w.gq16, G + off[R_P3_B], G + off[R_CR_B]);
+    MRNB_CHECK_LAUNCH("gate_q_kernel");
+  }
+  // p = q W3   ([B*I, D] x [D, D], W3 read MN-major where it lies)
+  MRNB_TRY(dx_rows(dq, nullptr, w.gq16, D, D, P + off[R_P3_W], W16 + off[R_P3_W], D, w.gp, D, st));
+  {
+    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    tsum_dg2_kernel<<<B * I, 128, 0, st>>>(w.out, w.y216, w.y, w.gp, wr, I, T, w.ow, w.y2w16, w.dg216, G + off[R_CP_B]);
     MRNB_CHECK_LAUNCH("tsum_dg2_kernel");
     gate_dwcr_kernel<<<dim3(cdiv(ID, 256), B >= 64 ? 32 : 1), 256, 0, st>>>(w.dr, w.ow, B, I, ID, G + off[R_CR_W]);
     MRNB_CHECK_LAUNCH("gate_dwcr_kernel");
   }
-  {  // dW3[n,k] = sum_(b,i) q[(b,i),n] y2w[(b,i),k]   (B*I rows: fp32 on the CUDA cores)
-    MrnbGemm g{};
-    g.A = w.gq; g.am = mrnb_axis(1); g.ak = mrnb_axis(D); g.a_kfast = 0;
-    g.B = w.y2w; g.bk = mrnb_axis(D); g.bn = mrnb_axis(1); g.b_kfast = 0;
-    g.C = G + off[R_P3_W]; g.cm = mrnb_axis(D); g.cn = mrnb_axis(1);
-    g.M = D; g.N = D; g.K = B * I; g.batch = 1; g.alpha = 1.f; g.rows_per_scale = 1;
-    g.splitk = (B * I + 127) / 128; if (g.splitk > 16) g.splitk = 16; if (g.splitk < 1) g.splitk = 1;
-    MRNB_TRY(mrnb_sgemm(g, st));
-  }
+  // dW3[n,k] = sum_(b,i) q[(b,i),n] y2w[(b,i),k]
+  MRNB_TRY(dw_rows(dq, nullptr, w.gq16, D, D, nullptr, w.y2w16, D, D, G + off[R_P3_W], st));
   {  // dgn[(b,t), j] = sum_k dg2[(b,t),k] Wc[k,j]
     MrnbTcGemm2 g{};
     g.a = op_bt_ic_kmajor(w.dg216, d);
@@ -1269,16 +1316,8 @@ int router_backward_gate_tc(const float* P, const float* x, const Dims& d, float
                                                                           G + off[R_SN_B], M, G + off[R_P1_B] + D);
     MRNB_CHECK_LAUNCH("ln_rows_bwd_kernel");
   }
-  // a1 = xn W1^T + b1
-  MRNB_TRY(dw_rows(d, nullptr, w.da116, 2 * D, 2 * D, nullptr, w.xn16, D, D, G + off[R_P1_W], st));
-  MRNB_TRY(dx_rows(d, nullptr, w.da116, 2 * D, 2 * D, P + off[R_P1_W], W16 + off[R_P1_W], D, w.dxn, D, st));
-  {  // xn = LN_D(x): dgamma / dbeta
-    MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
-    const int grid = (int)((M + 8 * 16 - 1) / (8 * 16));
-    ln_rows_bwd_kernel<false><<<grid > 0 ? grid : 1, 256, 0, st>>>(x, D, w.stats1, P + off[R_N_W], w.dxn, nullptr, nullptr, D,
-                                                                     nullptr, nullptr, G + off[R_N_W], G + off[R_N_B], M);
-    MRNB_CHECK_LAUNCH("ln_rows_bwd_kernel");
-  }
+  // a1 = xhat (W1 gamma)^T + b1f: proj_1 and LayerNorm 1 gradients from S = da1^T xhat (no M-row dxn GEMM, no pass over x)
+  MRNB_TRY(ln1_fold_backward(P, off, d, G, w, st));
   return MRNB_OK;
 }
 
