@@ -17,7 +17,9 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 64, UMMA_K = 16, STAGES = 3;
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+// operand ring depth: 3 x 32 KiB for the two co-resident CTAs of the <= 128-wide tiles, 4 x 48 KiB for the single 256-wide CTA
+__host__ __device__ constexpr int stages_for(int bn) { return bn > 128 ? 4 : 3; }
 constexpr int A_BYTES = BM * BK * 2;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -137,6 +139,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGES = stages_for(BN);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
@@ -470,7 +473,7 @@ int launch2(const MrnbTcGemm2& p, cudaStream_t st) {
   ep.kb_per_split = (ep.KB_total + splits - 1) / splits;
   splits = (ep.KB_total + ep.kb_per_split - 1) / ep.kb_per_split;     // no empty split
   ep.splits = splits;
-  const size_t smem = 1024 + (size_t)STAGES * (A_BYTES + BN * BK * 2);
+  const size_t smem = 1024 + (size_t)stages_for(BN) * (A_BYTES + BN * BK * 2);
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(tc_gemm2_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
   ep.simple = (p.cn.si == 1 && p.cn.inner >= p.N && p.cm.inner >= p.M) ? 1 : 0;

@@ -14,6 +14,7 @@
 // v1 engine: fp32 CUDA-core GEMM (gemm_f32.cu) for both precisions -- gate weights are an fp32 quantity
 // (1e-4 tolerance); the tensor-core port of these contractions is tracked in DESIGN.md.
 #include "common.cuh"
+#include <stdlib.h>
 #include "gemm_f32.h"
 #include "gemm_tc2.h"
 #include "gemm_tc.h"
@@ -62,12 +63,18 @@ ln_rows_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
   const float rstd = rsqrtf(warp_sum(q) * (1.0f / RD) + eps);
   if (lane == 0) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int idx = (j / 4) * 128 + lane * 4 + (j % 4);
-    float o = (v[j] - mean) * rstd;
-    if (gamma) o = o * gamma[idx] + beta[idx];          // gamma == nullptr: plain x-hat (the affine is folded into the next Linear)
-    if (y) y[row * RD + idx] = o;
-    if (y16) y16[row * RD + idx] = __float2bfloat16_rn(o);
+  for (int c = 0; c < 2; ++c) {
+    const int idx = c * 128 + lane * 4;
+    float4 o = make_float4((v[c * 4] - mean) * rstd, (v[c * 4 + 1] - mean) * rstd, (v[c * 4 + 2] - mean) * rstd, (v[c * 4 + 3] - mean) * rstd);
+    if (gamma) {                                        // gamma == nullptr: plain x-hat (the affine is folded into the next Linear)
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + idx)), b4 = __ldg(reinterpret_cast<const float4*>(beta + idx));
+      o = make_float4(o.x * g4.x + b4.x, o.y * g4.y + b4.y, o.z * g4.z + b4.z, o.w * g4.w + b4.w);
+    }
+    if (y) *reinterpret_cast<float4*>(y + row * RD + idx) = o;
+    if (y16) {
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+      *reinterpret_cast<uint2*>(y16 + row * RD + idx) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+    }
   }
 }
 
@@ -108,7 +115,13 @@ fold_ln_w1_bwd_kernel(const float* __restrict__ S, const float* __restrict__ db1
   atomicAdd(dgamma + c, ag); atomicAdd(dbeta + c, ab);
 }
 
-// a1 [rows, 2D] -> u = GELU(a1[:, :D]) ; vn = LN_D(GELU(a1[:, D:])) + stats
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+}
+// a1 [rows, 2D] -> u = GELU(a1[:, :D]) ; vn = LN_D(GELU(a1[:, D:])) + stats.   FAST: minimax-tanh GELU (tensor-core mode,
+// the values end as bf16 operands; the backward recomputes with the same form)
+template <bool FAST>
 __global__ void __launch_bounds__(256)
 gelu_ln_fwd_kernel(const float* __restrict__ a1, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float* __restrict__ u, float* __restrict__ vn, __nv_bfloat16* __restrict__ vn16,
@@ -117,14 +130,14 @@ gelu_ln_fwd_kernel(const float* __restrict__ a1, const float* __restrict__ gamma
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float* ar = a1 + row * 2 * RD;
+  auto act = [](float x) { return FAST ? gelu_fast(x) : gelu_erf(x); };
   float v[8];
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     const float4 tu = *reinterpret_cast<const float4*>(ar + c * 128 + lane * 4);
-    *reinterpret_cast<float4*>(u + row * RD + c * 128 + lane * 4) =
-        make_float4(gelu_erf(tu.x), gelu_erf(tu.y), gelu_erf(tu.z), gelu_erf(tu.w));
+    *reinterpret_cast<float4*>(u + row * RD + c * 128 + lane * 4) = make_float4(act(tu.x), act(tu.y), act(tu.z), act(tu.w));
     const float4 tv = *reinterpret_cast<const float4*>(ar + RD + c * 128 + lane * 4);
-    v[c * 4] = gelu_erf(tv.x); v[c * 4 + 1] = gelu_erf(tv.y); v[c * 4 + 2] = gelu_erf(tv.z); v[c * 4 + 3] = gelu_erf(tv.w);
+    v[c * 4] = act(tv.x); v[c * 4 + 1] = act(tv.y); v[c * 4 + 2] = act(tv.z); v[c * 4 + 3] = act(tv.w);
   }
   float s = 0.f;
 #pragma unroll
@@ -136,18 +149,16 @@ gelu_ln_fwd_kernel(const float* __restrict__ a1, const float* __restrict__ gamma
   const float rstd = rsqrtf(warp_sum(q) * (1.0f / RD) + eps);
   if (lane == 0) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int idx = (j / 4) * 128 + lane * 4 + (j % 4);
-    const float o = (v[j] - mean) * rstd * gamma[idx] + beta[idx];
-    if (vn) vn[row * RD + idx] = o;
-    if (vn16) vn16[row * RD + idx] = __float2bfloat16_rn(o);
+  for (int c = 0; c < 2; ++c) {
+    const int idx = c * 128 + lane * 4;
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + idx)), b4 = __ldg(reinterpret_cast<const float4*>(beta + idx));
+    const float4 o = make_float4((v[c * 4] - mean) * rstd * g4.x + b4.x, (v[c * 4 + 1] - mean) * rstd * g4.y + b4.y,
+                                 (v[c * 4 + 2] - mean) * rstd * g4.z + b4.z, (v[c * 4 + 3] - mean) * rstd * g4.w + b4.w);
+    if (vn) *reinterpret_cast<float4*>(vn + row * RD + idx) = o;
+    if (vn16) store_bf16x4(vn16 + row * RD + idx, o);
   }
 }
 
-__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* p, float4 v) {
-  __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
-  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-}
 __global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ c,
                            __nv_bfloat16* __restrict__ c16, long n4) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -907,6 +918,8 @@ inline int bn_for(int N) { return N >= 128 ? 128 : 64; }
 // still fit ONE wave of the 2 x 148 persistent CTAs (a second, partly filled wave costs a whole tile duration)
 inline int splitk_for(int tiles, int ctas = 296) { const int s = ctas / (tiles > 0 ? tiles : 1); return s < 1 ? 1 : s; }
 // channel mixing (K = N = I*D >= 1024): 128 x 256 tiles, one CTA per SM
+// 128 x 256 tiles (one CTA per SM, 4-stage ring) measured against 128 x 128 (two CTAs per SM): forward 137 vs 135 us,
+// dgn 204 vs 164 us, dWc 218 vs 165 us -- the second co-resident CTA hides more latency than the wider tile saves in L2 traffic
 inline int bn_chan(long) { return 128; }   // 128 x 256 tiles at one CTA per SM measured slower (175 -> 246 us forward): the
                                             // second co-resident CTA hides more latency than the wider tile saves in L2 traffic
 
@@ -992,8 +1005,8 @@ int router_forward(const float* P, const float* x, const Dims& d, float* out_use
                        w.a1, 2 * D, st));
   {
     MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
-    gelu_ln_fwd_kernel<<<cdiv(M, 8), 256, 0, st>>>(w.a1, P + off[R_SN_W], P + off[R_SN_B], w.u, tc ? nullptr : w.vn,
-                                                   tc ? w.vn16 : nullptr, w.stats2, M, 1e-5f);
+    if (tc) gelu_ln_fwd_kernel<true><<<cdiv(M, 8), 256, 0, st>>>(w.a1, P + off[R_SN_W], P + off[R_SN_B], w.u, nullptr, w.vn16, w.stats2, M, 1e-5f);
+    else gelu_ln_fwd_kernel<false><<<cdiv(M, 8), 256, 0, st>>>(w.a1, P + off[R_SN_W], P + off[R_SN_B], w.u, w.vn, nullptr, w.stats2, M, 1e-5f);
     MRNB_CHECK_LAUNCH("gelu_ln_fwd_kernel");
   }
   // v2[b] = Ws . vn[b] + bs  (token mixing over n = i*T+t)
@@ -1192,9 +1205,12 @@ int dm_router_backward_core(const float* P, const float* x, const Dims& d, float
   {  // vn = LN_D(GELU(a1v)); u = GELU(a1u)
     MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
     const int grid = (int)((M + 8 * 16 - 1) / (8 * 16));
-    ln_rows_bwd_kernel<true><<<grid > 0 ? grid : 1, 256, 0, st>>>(w.a1 + D, 2 * D, w.stats2, P + off[R_SN_W], w.dvn, w.da1 + D,
-                                                                    tc ? w.da116 + D : nullptr, 2 * D, nullptr, nullptr,
-                                                                    G + off[R_SN_W], G + off[R_SN_B], M);
+    if (tc) ln_rows_bwd_kernel<true, true><<<grid > 0 ? grid : 1, 256, 0, st>>>(w.a1 + D, 2 * D, w.stats2, P + off[R_SN_W], w.dvn, w.da1 + D,
+                                                                                 w.da116 + D, 2 * D, nullptr, nullptr,
+                                                                                 G + off[R_SN_W], G + off[R_SN_B], M);
+    else ln_rows_bwd_kernel<true><<<grid > 0 ? grid : 1, 256, 0, st>>>(w.a1 + D, 2 * D, w.stats2, P + off[R_SN_W], w.dvn, w.da1 + D,
+                                                                        nullptr, 2 * D, nullptr, nullptr,
+                                                                        G + off[R_SN_W], G + off[R_SN_B], M);
     MRNB_CHECK_LAUNCH("ln_rows_bwd_kernel");
     LAUNCH_EW(gelu_bwd_kernel, M * D, w.a1, w.du, w.da1, tc ? w.da116 : nullptr, M);
   }
@@ -1277,6 +1293,8 @@ int router_backward_gate_tc(const float* P, const float* x, const Dims& d, float
   }
   {
     MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
+    // (capping the resident blocks so that the second pass over y / dgn hits L2 cut the DRAM reads from 500 to 400 MB but
+    // ran slower -- 147 vs 121 us: too few loads in flight per SM)
     lnT_bwd2_kernel<<<B * I, 128, 0, st>>>(w.y, w.statsT, P + off[R_CN_W], w.dgn, w.g2, w.gp, wr, w.dy16, G + off[R_CN_W],
                                            G + off[R_CN_B], G + off[R_P2_B], T, d.Tv);
     MRNB_CHECK_LAUNCH("lnT_bwd2_kernel");
