@@ -8,7 +8,12 @@
 //                  O  += P W2_c^T  (tcgen05, TMEM accumulator of width d)
 // and the final epilogue adds b2, the DropPath scale and the fp32 residual, stores x in place and (d <= 128)
 // emits the next LayerNorm.  Per tile HBM traffic: A (bf16) + x in + x out (+ LN out) instead of two GEMM round trips
-// through a [M,4d] tensor.  Warp roles: 0 = TMA producer, 1 = TMEM + MMA issuer, 2..9 = epilogue.
+// through a [M,4d] tensor.
+// Warp roles (four warpgroups, register budgets re-balanced with setmaxnreg): WG0 = control (warp 0 TMA producer, warp 1
+// TMEM + MMA issuer), WG1 / WG2 = the eight GELU warps (S_c -> P_c), WG3 = output epilogue (O -> x, LayerNorm).  The output
+// epilogue of tile i runs while the GELU warps already work on tile i + 1 (ncu source view of the previous single-epilogue
+// version: 31 % of the epilogue warps' samples sat in the O -> x / LayerNorm code, serialised with the GELU chunks); the
+// O accumulator is double buffered in TMEM for d <= 128.
 #include "common.cuh"
 #include "mlp_tc.h"
 #include <cuda.h>
@@ -16,7 +21,8 @@
 namespace {
 
 constexpr int BM = 128, BK = 64, HC = 128;       // rows per tile, k-block, hidden chunk
-constexpr int EPI_WARPS = 8, NTHREADS = 64 + EPI_WARPS * 32;
+constexpr int EPI_WARPS = 8, NTHREADS = 512;
+constexpr int REGS_CTRL = 80, REGS_GELU = 168, REGS_OUT = 96;       // 128 * (80 + 2 * 168 + 96) = 65536
 constexpr int TILE16K = 128 * 64 * 2;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -74,6 +80,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
@@ -108,9 +130,12 @@ struct Cfg {
   static constexpr int W2ROWS = D / NH;
   static constexpr int A_BYTES = KB * TILE16K;
   static constexpr int P_BYTES = 2 * TILE16K;          // [128 x 128] bf16 as two 64-wide K halves
-  static constexpr int BIAS_BYTES = 5 * D * 4;
-  static constexpr int SMEM = 1024 + A_BYTES + P_BYTES + RS * SLOT + BIAS_BYTES;
-  static constexpr uint32_t O_COL = 256;               // TMEM: S buffers at 0 / 128, O at 256
+  static constexpr int BIAS_BYTES = 4 * D * 4;
+  static constexpr int STG_BYTES = 4 * 2048;           // output-epilogue staging: 32 rows x 16 fp32 per warp
+  static constexpr int XT_BYTES = D <= 128 ? BM * D * 4 : 0;   // new rows of the tile for the fused LayerNorm (D <= 128)
+  static constexpr int SMEM = 1024 + A_BYTES + P_BYTES + RS * SLOT + BIAS_BYTES + STG_BYTES + XT_BYTES;
+  static constexpr uint32_t O_COL = 256;               // TMEM: S buffers at 0 / 128, O at 256 (+ D for the second buffer)
+  static constexpr int OB = D <= 128 ? 2 : 1;          // O accumulators
 };
 
 template <int D, bool LNF>
@@ -124,10 +149,10 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint8_t* sP = smem + K::A_BYTES;
   uint8_t* ring = sP + K::P_BYTES;
   float* sb1 = reinterpret_cast<float*>(ring + K::RS * K::SLOT);
-  float* sb2 = sb1 + 4 * D;
-  __shared__ __align__(8) uint64_t a_full, a_empty, w_full[8], w_empty[8], s_full[2], s_empty[2], p_full, p_empty, o_full, o_empty;
+  uint8_t* sStg = reinterpret_cast<uint8_t*>(sb1 + 4 * D);
+  float* sXt = reinterpret_cast<float*>(sStg + K::STG_BYTES);   // [128][D] fp32, 16-byte pieces XOR-swizzled by row (LNF only)
+  __shared__ __align__(8) uint64_t a_full, a_empty, w_full[8], w_empty[8], s_full[2], s_empty[2], p_full, p_empty, o_full[2], o_empty[2];
   __shared__ uint32_t tmem_base_sh;
-  __shared__ float ln_part[2][4][2][32];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = ep.total_tiles, m_tiles = ep.m_tiles;
@@ -137,7 +162,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     for (int s = 0; s < K::RS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], EPI_WARPS); }
     mbar_init(&p_full, EPI_WARPS); mbar_init(&p_empty, 1);
-    mbar_init(&o_full, 1); mbar_init(&o_empty, EPI_WARPS);
+    for (int b = 0; b < 2; ++b) { mbar_init(&o_full[b], 1); mbar_init(&o_empty[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW1)) : "memory");
@@ -152,6 +177,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_sh;
 
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
   if (warp == 0) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
@@ -163,17 +189,25 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         tma_load_3d(ring + (size_t)s * K::SLOT, map, &w_full[s], c0, c1, g);
         ++it;
       };
-      int i = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
+      // Ring order = consumption order of the MMA issuer: A_0, W1_0 ; then per tile, per chunk c:
+      //   { W1_{c+1}  |  at the last chunk: A and W1_0 of the NEXT tile (its S_0 is issued before this tile's last P W2) } ; W2_c
+      auto load_a = [&](int ti, int t) {
         const int g = t / m_tiles, m0 = (t % m_tiles) * BM;
-        mbar_wait(&a_empty, ((uint32_t)i & 1u) ^ 1u);
+        mbar_wait(&a_empty, ((uint32_t)ti & 1u) ^ 1u);
         mbar_expect_tx(&a_full, K::A_BYTES);
         for (int kb = 0; kb < K::KB; ++kb) tma_load_3d(sA + kb * TILE16K, &tmA, &a_full, kb * BK, m0, g);
-        // weights in consumption order: W1_0 ; then per chunk { W1_{c+1} ; W2_c }
         for (int kb = 0; kb < K::KB; ++kb) load_w(&tmW1, kb * BK, 0, g, TILE16K);
+      };
+      int i = 0;
+      if ((int)blockIdx.x < total) load_a(0, blockIdx.x);
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
+        const int g = t / m_tiles;
         for (int c = 0; c < K::C; ++c) {
-          if (c + 1 < K::C)
+          if (c + 1 < K::C) {
             for (int kb = 0; kb < K::KB; ++kb) load_w(&tmW1, kb * BK, (c + 1) * HC, g, TILE16K);
+          } else if (t + (int)gridDim.x < total) {
+            load_a(i + 1, t + gridDim.x);
+          }
           for (int kk = 0; kk < 2; ++kk)
             for (int nh = 0; nh < K::NH; ++nh) load_w(&tmW2, c * HC + kk * BK, nh * K::W2ROWS, g, K::W2ROWS * BK * 2);
         }
@@ -186,10 +220,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       constexpr uint32_t idesc_o = make_idesc(K::W2ROWS) & ~((7u << 7) | (7u << 10));   // second GEMM in f16 x f16: P (GELU output) and W2 are f16
       uint32_t it = 0;
       int i = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
-        auto issue_s = [&](int c) {
+      auto issue_s = [&](int ti, int c) {
           const int b = c & 1;
-          const uint32_t u = (uint32_t)(i * (K::C / 2) + (c >> 1));
+          const uint32_t u = (uint32_t)(ti * (K::C / 2) + (c >> 1));
           mbar_wait(&s_empty[b], (u & 1u) ^ 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           for (int kb = 0; kb < K::KB; ++kb, ++it) {
@@ -202,17 +235,25 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             umma_commit(&w_empty[s]);
           }
           umma_commit(&s_full[b]);
-        };
-        mbar_wait(&a_full, (uint32_t)i & 1u);
-        issue_s(0);
+      };
+      if ((int)blockIdx.x < total) { mbar_wait(&a_full, 0u); issue_s(0, 0); }
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
         for (int c = 0; c < K::C; ++c) {
-          if (c + 1 < K::C) issue_s(c + 1);
-          if (c + 1 == K::C - 1 || K::C == 1) umma_commit(&a_empty);      // last S issued: A tile is free once it retires
+          if (c + 1 < K::C) {
+            issue_s(i, c + 1);
+          } else if (t + (int)gridDim.x < total) {
+            // S_0 of the NEXT tile goes out before this tile's last P W2: the GELU warps find it ready at the tile boundary
+            mbar_wait(&a_full, (uint32_t)(i + 1) & 1u);
+            issue_s(i + 1, 0);
+          }
+          if (c + 1 == K::C - 1) umma_commit(&a_empty);                   // last S of this tile issued: A is free once it retires
           const uint32_t up = (uint32_t)(i * K::C + c);
           MRNB_TRACE(0, (int)up);                          // MMA: S_{c+1} issued, start waiting for P_c
           mbar_wait(&p_full, up & 1u);
           MRNB_TRACE(1, (int)up);                          // MMA: P_c available
-          if (c == 0) mbar_wait(&o_empty, ((uint32_t)i & 1u) ^ 1u);
+          // O accumulator of this tile: buffer i % OB, free once the output epilogue of tile i - OB has drained it
+          const uint32_t ob = K::OB == 2 ? ((uint32_t)i & 1u) : 0u, on = K::OB == 2 ? ((uint32_t)i >> 1) : (uint32_t)i;
+          if (c == 0) mbar_wait(&o_empty[ob], (on & 1u) ^ 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           for (int kk = 0; kk < 2; ++kk) {
             for (int nh = 0; nh < K::NH; ++nh, ++it) {
@@ -222,61 +263,40 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               const uint64_t ad = make_desc(smem_u32(sP + kk * TILE16K)), bd = make_desc(smem_u32(ring + (size_t)s * K::SLOT));
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_bf16(tmem_base + K::O_COL + (uint32_t)(nh * K::W2ROWS), ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc_o,
-                          (c | kk | k) != 0);
+                umma_bf16(tmem_base + K::O_COL + ob * (uint32_t)D + (uint32_t)(nh * K::W2ROWS), ad + (uint64_t)(k * 2),
+                          bd + (uint64_t)(k * 2), idesc_o, (c | kk | k) != 0);
               umma_commit(&w_empty[s]);
             }
           }
           umma_commit(&p_empty);
           MRNB_TRACE(2, (int)up);                          // MMA: PV_c issued
-          if (c == K::C - 1) umma_commit(&o_full);
+          if (c == K::C - 1) umma_commit(&o_full[ob]);
         }
       }
     }
-  } else {
-    // ============================== epilogue warps ==============================
-    const int ew = warp - 2, q = warp & 3, ch = ew >> 2;
+  } else if (warp >= 4 && warp < 12) {
+    // ============================== GELU warps: S_c -> +b1 -> GELU -> f16 P_c ==============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_GELU));
+    const int ew = warp - 4, q = warp & 3, ch = ew >> 2;
     const int r = q * 32 + lane;                               // row inside the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    constexpr int OW = D / 2;                                  // output columns per warp
-    constexpr int NPASS = OW / 32;                             // 32-column passes of the final epilogue: 1, 2, 4
-    const int p8 = lane & 7, rsel = lane >> 3;                 // final epilogue: 8 lanes per 32-column row segment
-    // 32 rows x 32 floats, 16B pieces XOR-swizzled by row.  The staging tile aliases exactly the 4 KiB of sP this warp
-    // itself writes P into (rows q*32.. of K-half ch): a warp that runs ahead into the next tile's first P chunk can
-    // then only overwrite its own (already consumed) staging, never a slower warp's.
-    float* stg = reinterpret_cast<float*>(sP + (size_t)ch * TILE16K + (size_t)q * 4096);
     int i = 0;
     int cur_g = -1;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
-      const int g = t / m_tiles, m0 = (t % m_tiles) * BM;
-      if (warp == 2 && lane == 0) MRNB_TRACE(9, i);                // epi: tile start
-      if (g != cur_g) {                                        // (re)load the biases of this expert
-        asm volatile("bar.sync 5, 256;" ::: "memory");         // everyone done with the previous expert's biases
-        for (int k = threadIdx.x - 64; k < 4 * D; k += EPI_WARPS * 32) sb1[k] = ep.b1[(long)g * ep.b_gs1 + k];
-        for (int k = threadIdx.x - 64; k < D; k += EPI_WARPS * 32) sb2[k] = ep.b2[(long)g * ep.b_gs2 + k];
+      const int g = t / m_tiles;
+      if (warp == 4 && lane == 0) MRNB_TRACE(9, i);                // epi: tile start
+      if (g != cur_g) {                                        // (re)load the fc1 bias of this expert
+        asm volatile("bar.sync 5, 256;" ::: "memory");         // everyone done with the previous expert's bias
+        for (int k = threadIdx.x - 128; k < 4 * D; k += EPI_WARPS * 32) sb1[k] = ep.b1[(long)g * ep.b_gs1 + k];
         asm volatile("bar.sync 5, 256;" ::: "memory");
         cur_g = g;
       }
-      // residual rows of pass 0 can be fetched long before they are needed
-      float* xrow = ep.x + (long)g * ep.x_gs + (long)(m0 + q * 32 + rsel) * D + ch * OW + p8 * 4;
-      float4 rv[8];
-#pragma unroll
-      for (int itr = 0; itr < 8; ++itr) rv[itr] = *reinterpret_cast<const float4*>(xrow + (long)itr * 4 * D);
-      if (NPASS > 1 && p8 == 0) {                              // later passes: pull the rows into L2 now (one lane per 128 B)
-#pragma unroll
-        for (int ps = 1; ps < NPASS; ++ps)
-#pragma unroll
-          for (int itr = 0; itr < 8; ++itr)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(xrow + ps * 32 + (long)itr * 4 * D));
-      }
-
-      // ---- hidden chunks: S_c -> +b1 -> GELU -> bf16 P
       for (int c = 0; c < K::C; ++c) {
         const int b = c & 1;
         const uint32_t u = (uint32_t)(i * (K::C / 2) + (c >> 1));
-        if (warp == 2 && lane == 0) MRNB_TRACE(3, i * K::C + c);   // epi: start waiting for S_c
+        if (warp == 4 && lane == 0) MRNB_TRACE(3, i * K::C + c);   // epi: start waiting for S_c
         mbar_wait(&s_full[b], u & 1u);
-        if (warp == 2 && lane == 0) MRNB_TRACE(4, i * K::C + c);   // epi: S_c ready
+        if (warp == 4 && lane == 0) MRNB_TRACE(4, i * K::C + c);   // epi: S_c ready
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t v0[32], v1[32];
         tmem_ld32(lane_addr + (uint32_t)(b * HC + ch * 64), v0);
@@ -300,9 +320,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           pk[e4 * 2 + 1] = *reinterpret_cast<const uint32_t*>(&g1);
         }
         const uint32_t up = (uint32_t)(i * K::C + c);
-        if (warp == 2 && lane == 0) MRNB_TRACE(5, (int)up);        // epi: GELU done
+        if (warp == 4 && lane == 0) MRNB_TRACE(5, (int)up);        // epi: GELU done
         mbar_wait(&p_empty, (up & 1u) ^ 1u);                   // previous P has been consumed by its MMAs (GELU already done)
-        if (warp == 2 && lane == 0) MRNB_TRACE(6, (int)up);        // epi: P buffer free
+        if (warp == 4 && lane == 0) MRNB_TRACE(6, (int)up);        // epi: P buffer free
         uint8_t* prow = sP + ch * TILE16K + r * 128;
 #pragma unroll
         for (int pc = 0; pc < 8; ++pc)                          // 8 pieces of 8 columns (16 B of bf16), XOR-swizzled by row
@@ -310,102 +330,112 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full);
-        if (warp == 2 && lane == 0) MRNB_TRACE(7, (int)up);        // epi: P_c published
+        if (warp == 4 && lane == 0) MRNB_TRACE(7, (int)up);        // epi: P_c published
       }
-
-      // ---- final epilogue: O -> +b2, DropPath scale, + residual -> x (in place) [+ fused LayerNorm]
-      mbar_wait(&o_full, (uint32_t)i & 1u);
-      if (warp == 2 && lane == 0) MRNB_TRACE(8, i);                // epi: O ready
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+  } else if (warp >= 12) {
+    // ============================== output epilogue warpgroup ==============================
+    // O -> +b2, DropPath scale, + fp32 residual -> x (in place) [+ bf16 copy | + LayerNorm of the next block], one warp
+    // per TMEM lane quarter, while the other warpgroups already work on the next tile.  16 accumulator columns of the
+    // warp's 32 rows are transposed through a 2 KiB staging tile (16-byte pieces XOR-swizzled by row) so that global
+    // accesses are 64-byte row segments: lane = (row in a group of 8, float4 of the 16).  (32-column steps with 8 lanes per
+    // row segment measured slower: register spills under the 96-register budget of this warpgroup.)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_OUT));
+    const int q = warp & 3;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* stg = reinterpret_cast<float*>(sStg + q * 2048);
+    const int rsub = lane >> 2, c4 = lane & 3;
+    int i = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
+      const int g = t / m_tiles, m0 = (t % m_tiles) * BM;
+      const uint32_t ob = K::OB == 2 ? ((uint32_t)i & 1u) : 0u, on = K::OB == 2 ? ((uint32_t)i >> 1) : (uint32_t)i;
       const float rs = ep.rowscale ? ep.rowscale[(long)g * ep.rowscale_gs + m0 / ep.rows_per_scale] : 1.0f;
-      float4 keep[LNF ? NPASS * 8 : 1];
-      __nv_bfloat16* crow = (!LNF && ep.cast_out)
-                                ? ep.cast_out + (long)g * ep.ln_gs + (long)(m0 + q * 32 + rsel) * D + ch * OW + p8 * 4 : nullptr;
+      float* xt = ep.x + (long)g * ep.x_gs + (long)(m0 + q * 32) * D;        // the warp's 32 rows
+      const float* b2p = ep.b2 + (long)g * ep.b_gs2;
+      {
+        // idle until the tile's last P W2 MMA retires: start the trip of the residual rows (32 x D fp32) to L2 now
+        const char* xl2 = reinterpret_cast<const char*>(xt);
 #pragma unroll
-      for (int ps = 0; ps < NPASS; ++ps) {
-        uint32_t v[32];
-        tmem_ld32(lane_addr + K::O_COL + (uint32_t)(ch * OW + ps * 32), v);
-        if (ps == NPASS - 1) {
+        for (int k = 0; k < D / 32; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(xl2 + (long)(k * 32 + lane) * 128));
+      }
+      mbar_wait(&o_full[ob], on & 1u);
+      if (warp == 12 && lane == 0) MRNB_TRACE(8, i);               // out: O ready
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      __nv_bfloat16* ct = (!LNF && ep.cast_out) ? ep.cast_out + (long)g * ep.ln_gs + (long)(m0 + q * 32) * D : nullptr;
+      float sum[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+      float* xs = sXt + (size_t)(q * 32) * D;                  // this warp's rows of the staged tile (LNF)
+      float4 xin[4], xnx[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) xin[it] = *reinterpret_cast<const float4*>(xt + (long)(it * 8 + rsub) * D + c4 * 4);
+#pragma unroll 1
+      for (int c = 0; c < D / 16; ++c) {
+        if (c + 1 < D / 16) {                                  // residual rows of the next 16 columns: in flight during this step
+#pragma unroll
+          for (int it = 0; it < 4; ++it) xnx[it] = *reinterpret_cast<const float4*>(xt + (long)(it * 8 + rsub) * D + (c + 1) * 16 + c4 * 4);
+        }
+        uint32_t v[16];
+        tmem_ld16(lane_addr + K::O_COL + ob * (uint32_t)D + (uint32_t)(c * 16), v);
+        if (c == D / 16 - 1) {
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(&o_empty);                // accumulator drained: next tile may overwrite it
+          if (lane == 0) mbar_arrive(&o_empty[ob]);            // accumulator drained: a later tile may overwrite it
         }
 #pragma unroll
-        for (int pc = 0; pc < 8; ++pc)
-          *reinterpret_cast<float4*>(stg + lane * 32 + ((pc ^ (lane & 7)) * 4)) =
+        for (int pc = 0; pc < 4; ++pc)
+          *reinterpret_cast<float4*>(stg + lane * 16 + ((pc ^ (lane & 3)) * 4)) =
               make_float4(__uint_as_float(v[4 * pc]), __uint_as_float(v[4 * pc + 1]), __uint_as_float(v[4 * pc + 2]), __uint_as_float(v[4 * pc + 3]));
         __syncwarp();
-        const float4 b4 = *reinterpret_cast<const float4*>(sb2 + ch * OW + ps * 32 + p8 * 4);
-        float4 nx[8];
-        if (ps + 1 < NPASS) {                                  // prefetch the next pass' residual rows
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2p + c * 16 + c4 * 4));
 #pragma unroll
-          for (int itr = 0; itr < 8; ++itr) nx[itr] = *reinterpret_cast<const float4*>(xrow + (ps + 1) * 32 + (long)itr * 4 * D);
-        }
-#pragma unroll
-        for (int itr = 0; itr < 8; ++itr) {
-          const int rl = itr * 4 + rsel;
-          float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((p8 ^ (rl & 7)) * 4));
-          x.x = fmaf(x.x + b4.x, rs, rv[itr].x); x.y = fmaf(x.y + b4.y, rs, rv[itr].y);
-          x.z = fmaf(x.z + b4.z, rs, rv[itr].z); x.w = fmaf(x.w + b4.w, rs, rv[itr].w);
-          *reinterpret_cast<float4*>(xrow + ps * 32 + (long)itr * 4 * D) = x;
-          if (LNF) keep[ps * 8 + itr] = x;
-          if (!LNF && crow) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
-            *reinterpret_cast<uint2*>(crow + ps * 32 + (long)itr * 4 * D) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        for (int it = 0; it < 4; ++it) {
+          const int rl = it * 8 + rsub;
+          const float4 a = *reinterpret_cast<const float4*>(stg + rl * 16 + ((c4 ^ (rl & 3)) * 4));
+          float4 o;
+          o.x = fmaf(a.x + b4.x, rs, xin[it].x); o.y = fmaf(a.y + b4.y, rs, xin[it].y);
+          o.z = fmaf(a.z + b4.z, rs, xin[it].z); o.w = fmaf(a.w + b4.w, rs, xin[it].w);
+          *reinterpret_cast<float4*>(xt + (long)rl * D + c * 16 + c4 * 4) = o;
+          if (LNF) {
+            sum[it] += (o.x + o.y) + (o.z + o.w); sq[it] += fmaf(o.x, o.x, o.y * o.y) + fmaf(o.z, o.z, o.w * o.w);
+            *reinterpret_cast<float4*>(xs + rl * D + (((c * 4 + c4) ^ (rl & 7)) * 4)) = o;
+          }
+          if (!LNF && ct) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+            *reinterpret_cast<uint2*>(ct + (long)rl * D + c * 16 + c4 * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
           }
         }
-        if (ps + 1 < NPASS) {
 #pragma unroll
-          for (int itr = 0; itr < 8; ++itr) rv[itr] = nx[itr];
-        }
+        for (int it = 0; it < 4; ++it) xin[it] = xnx[it];
         __syncwarp();
       }
       if (LNF) {
-        // LayerNorm of the new rows for the next block (two-pass statistics; the two warps of a row exchange partials)
-        const float invn = 1.0f / (float)D;
-        float mean[8], rstd[8];
+        // LayerNorm of the new rows for the next block: the four lanes of a row hold its partial sums; the second pass
+        // reads the rows back from the warp's own shared-memory tile
+        const float* gam = ep.ln_gamma + (long)g * D;
+        const float* bet = ep.ln_beta + (long)g * D;
+        float mean[4], rstd[4];
 #pragma unroll
-        for (int itr = 0; itr < 8; ++itr) {
-          float sres = 0.f;
-#pragma unroll
-          for (int ps = 0; ps < NPASS; ++ps) { const float4 x = keep[ps * 8 + itr]; sres += (x.x + x.y) + (x.z + x.w); }
-#pragma unroll
-          for (int o = 4; o > 0; o >>= 1) sres += __shfl_xor_sync(0xffffffffu, sres, o);
-          if (p8 == 0) ln_part[0][q][ch][itr * 4 + rsel] = sres;
+        for (int it = 0; it < 4; ++it) {
+          float s1 = sum[it], s2 = sq[it];
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+          mean[it] = s1 * (1.0f / D);
+          rstd[it] = rsqrtf(fmaxf(s2 * (1.0f / D) - mean[it] * mean[it], 0.f) + ep.ln_eps);
         }
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        __nv_bfloat16* lt = ep.ln_out + (long)g * ep.ln_gs + (long)(m0 + q * 32) * D;
+#pragma unroll 2
+        for (int c = 0; c < D / 16; ++c) {
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(gam + c * 16 + c4 * 4));
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(bet + c * 16 + c4 * 4));
 #pragma unroll
-        for (int itr = 0; itr < 8; ++itr) {
-          const int rl = itr * 4 + rsel;
-          mean[itr] = (ln_part[0][q][0][rl] + ln_part[0][q][1][rl]) * invn;
-          float sq = 0.f;
-#pragma unroll
-          for (int ps = 0; ps < NPASS; ++ps) {
-            const float4 x = keep[ps * 8 + itr];
-            const float d0 = x.x - mean[itr], d1 = x.y - mean[itr], d2 = x.z - mean[itr], d3 = x.w - mean[itr];
-            sq += fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3);
-          }
-#pragma unroll
-          for (int o = 4; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-          if (p8 == 0) ln_part[1][q][ch][rl] = sq;
-        }
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-        __nv_bfloat16* lrow = ep.ln_out + (long)g * ep.ln_gs + (long)(m0 + q * 32 + rsel) * D + ch * OW + p8 * 4;
-#pragma unroll
-        for (int itr = 0; itr < 8; ++itr) {
-          const int rl = itr * 4 + rsel;
-          rstd[itr] = rsqrtf((ln_part[1][q][0][rl] + ln_part[1][q][1][rl]) * invn + ep.ln_eps);
-#pragma unroll
-          for (int ps = 0; ps < NPASS; ++ps) {
-            const int col = ch * OW + ps * 32 + p8 * 4;
-            const float4 g4 = *reinterpret_cast<const float4*>(ep.ln_gamma + (long)g * D + col);
-            const float4 t4 = *reinterpret_cast<const float4*>(ep.ln_beta + (long)g * D + col);
-            const float4 x = keep[ps * 8 + itr];
-            __nv_bfloat162 h0 = __floats2bfloat162_rn((x.x - mean[itr]) * rstd[itr] * g4.x + t4.x, (x.y - mean[itr]) * rstd[itr] * g4.y + t4.y);
-            __nv_bfloat162 h1 = __floats2bfloat162_rn((x.z - mean[itr]) * rstd[itr] * g4.z + t4.z, (x.w - mean[itr]) * rstd[itr] * g4.w + t4.w);
-            *reinterpret_cast<uint2*>(lrow + ps * 32 + (long)itr * 4 * D) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+          for (int it = 0; it < 4; ++it) {
+            const int rl = it * 8 + rsub;
+            const float4 xv = *reinterpret_cast<const float4*>(xs + rl * D + (((c * 4 + c4) ^ (rl & 7)) * 4));
+            __nv_bfloat162 h0 = __floats2bfloat162_rn((xv.x - mean[it]) * rstd[it] * g4.x + t4.x, (xv.y - mean[it]) * rstd[it] * g4.y + t4.y);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn((xv.z - mean[it]) * rstd[it] * g4.z + t4.z, (xv.w - mean[it]) * rstd[it] * g4.w + t4.w);
+            *reinterpret_cast<uint2*>(lt + (long)rl * D + c * 16 + c4 * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
           }
         }
+        __syncwarp();
       }
     }
   }
