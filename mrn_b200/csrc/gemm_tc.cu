@@ -288,19 +288,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             (!ep.rowscale || (ep.rows_per_scale % BM) == 0);
       const long o0 = gbase + (long)(m0 + q * 32 + rsel) * t_ldo + colw;
       const long ostep = 4L * t_ldo;
-      const bool pre_res = OUT_F32 && interior && ep.res != nullptr;
+      const bool pre_res = MODE != 3 && OUT_F32 && interior && ep.res != nullptr;
       float4 rv[8];
       if (pre_res) {
 #pragma unroll
         for (int itr = 0; itr < 8; ++itr) rv[itr] = *reinterpret_cast<const float4*>(ep.res + o0 + itr * ostep);
+        if (NP > 1 && p8 == 0) {                               // later passes: start their trip to L2 now (one lane per 128 B)
+#pragma unroll
+          for (int ps = 1; ps < NP; ++ps)
+#pragma unroll
+            for (int itr = 0; itr < 8; ++itr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.res + o0 + ps * 32 + itr * ostep));
+        }
       }
-      const float rs = (interior && ep.rowscale) ? ep.rowscale[(long)g * ep.rowscale_gs + m0 / ep.rows_per_scale] : 1.0f;
+      const float rs = (MODE != 3 && interior && ep.rowscale) ? ep.rowscale[(long)g * ep.rowscale_gs + m0 / ep.rows_per_scale] : 1.0f;
       mbar_wait(&tmem_full_bar[buf], ((uint32_t)i >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + ch * CW);
       float4 keep[LNF ? NP * 8 : 1];
 #pragma unroll
       for (int ps = 0; ps < NP; ++ps) {
+        if (pre_res && ps > 0) {                               // this pass' residual rows: in flight during the TMEM load / staging
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr) rv[itr] = *reinterpret_cast<const float4*>(ep.res + o0 + ps * 32 + itr * ostep);
+        }
         {
           uint32_t r[32];
           tmem_ld32(tcol + (uint32_t)(ps * 32), r);
@@ -326,12 +336,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (col + 2 < t_N) b4.z = bias[col + 2];
           }
         }
-        if (interior) {
-          float4 nx[8];
-          if (pre_res && ps + 1 < NP) {                        // next pass' residual rows
+        if constexpr (MODE == 3) {
+          // classifier heads: bias + store only (no residual / scale / activation); the ragged last column tile of an
+          // expert (C_e % 128 != 0) keeps the vector path for its full float4s -- row pitches are multiples of 4 floats
+          if ((m0 + BM <= ep.M) && ((t_ldo & 3) == 0)) {
+            float* op = reinterpret_cast<float*>(t_out) + o0 + ps * 32;
+            if (cfull) {
 #pragma unroll
-            for (int itr = 0; itr < 8; ++itr) nx[itr] = *reinterpret_cast<const float4*>(ep.res + o0 + (ps + 1) * 32 + itr * ostep);
+              for (int itr = 0; itr < 8; ++itr) {
+                const int rl = itr * 4 + rsel;
+                float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((p8 ^ (rl & 7)) * 4));
+                x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+                *reinterpret_cast<float4*>(op + itr * ostep) = x;
+              }
+            } else if (col < t_N) {
+#pragma unroll
+              for (int itr = 0; itr < 8; ++itr) {
+                const int rl = itr * 4 + rsel;
+                const float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((p8 ^ (rl & 7)) * 4));
+                float* o = op + itr * ostep;
+                o[0] = x.x + b4.x;
+                if (col + 1 < t_N) o[1] = x.y + b4.y;
+                if (col + 2 < t_N) o[2] = x.z + b4.z;
+              }
+            }
+            __syncwarp();
+            continue;
           }
+        }
+        if (MODE != 3 && interior) {
           if constexpr (MODE == 1) {
             // fused LSTM cell: x = (i, f, g, o) pre-activations of hidden unit j for sample b
             const MrnbTcLstm& L = ep.lstm;
@@ -402,10 +435,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
               *reinterpret_cast<uint2*>(op + itr * ostep) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
             }
-          }
-          if (pre_res && ps + 1 < NP) {
-#pragma unroll
-            for (int itr = 0; itr < 8; ++itr) rv[itr] = nx[itr];
           }
         } else {
           // edge tiles / unaligned outputs: guarded scalar path
