@@ -194,7 +194,9 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmWp, const MixParams ep) {
   using K = MCfg<D>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1 KiB alignment by OFFSET (not by integer round-trip of the pointer): the compiler keeps the shared address space,
+  // so staging / operand tiles are accessed with LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sQ = sA + K::A_BYTES;                            // [N rows x 64 B]; then sK, sV
   uint8_t* sK = sQ + K::NT * K::HT_BYTES;

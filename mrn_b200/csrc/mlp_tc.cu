@@ -144,7 +144,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               const __grid_constant__ CUtensorMap tmW2, const MlpParams ep) {
   using K = Cfg<D>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1 KiB alignment by OFFSET (not by integer round-trip of the pointer): the compiler keeps the shared address space,
+  // so staging / operand tiles are accessed with LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sP = smem + K::A_BYTES;
   uint8_t* ring = sP + K::P_BYTES;
