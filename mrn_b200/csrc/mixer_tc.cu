@@ -28,6 +28,9 @@
 
 namespace {
 
+#ifndef MRNB_MIXER_OVL
+#define MRNB_MIXER_OVL 0
+#endif
 constexpr int HD = 32;
 // Four warpgroups with re-balanced register budgets (setmaxnreg): WG0 = control (warp 0 TMA producer, warp 1 MMA issuer of
 // stream 0 + phase 1, warp 2 MMA issuer of stream 1), WG1 / WG2 = softmax streams 0 / 1, WG3 = Y epilogue.
@@ -35,6 +38,7 @@ constexpr int EPI_WARPS = 8, NTHREADS = 512;
 constexpr int REGS_CTRL = 80, REGS_SOFTMAX = 168, REGS_EPI = 96;       // 128 * (80 + 2 * 168 + 96) = 65536
 // TMEM columns: Y accumulator; per-stream S (64 keys) and O (32 dims); phase-1 staging buffers alias the S / O columns
 constexpr uint32_t Y_COL = 0, S0_COL = 256, S1_COL = 320, O0_COL = 384, O1_COL = 416, STG0_COL = 256, STG1_COL = 352;
+constexpr uint32_t STGX_COL = 448;      // OVL: dedicated 64-column staging of the q|k (64) / v (32) parts of one 128-token tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -147,16 +151,23 @@ struct MCfg {
   static constexpr int KR = N / 64;                         // key blocks = rows of the 64-wide token grid: 8 / 4 / 2
   static constexpr int HEADS = D / HD;
   static constexpr int KB = D / 64;                         // k-blocks of the q|k|v GEMM
-  static constexpr int A_BYTES = N * D * 2;                 // 64 KiB
+  static constexpr int A_BYTES = ((D == 128 && MRNB_MIXER_OVL) ? 128 : N) * D * 2;   // resident unit (64 KiB) or, OVL, one 128-token tile (32 KiB)
   static constexpr int HT_BYTES = 128 * HD * 2;             // one [128 x 32] bf16 head tile: 8 KiB
-  static constexpr int QKV_BYTES = 3 * NT * HT_BYTES;
+  // OVL (D = 128): the q|k|v GEMM + drain of head h + 1 overlaps the attention of head h.  q/k/v tiles are double buffered
+  // by head parity, A is streamed one 128-token tile at a time (re-read per head from L2) instead of resident, a dedicated
+  // thread issues the q|k|v MMAs into their own TMEM staging columns and the Y-epilogue warpgroup drains them.  (D = 64:
+  // two q/k/v buffers of 96 KiB do not fit; D = 256 runs unfused.)
+  static constexpr bool OVL = D == 128 && MRNB_MIXER_OVL;
+  static constexpr int QKV1_BYTES = 3 * NT * HT_BYTES;      // q, k, v of one head for all tokens
+  static constexpr int QKV_BYTES = (OVL ? 2 : 1) * QKV1_BYTES;
   static constexpr int P_TILE = 128 * 64 * 2;               // one stream's probability tile [128 q x 64 keys]: 16 KiB
   static constexpr int P_BYTES = 2 * P_TILE;
   static constexpr int WQ_KB_BYTES = 96 * 128;              // q|k|v rows of one head, one 64-wide k-block
   static constexpr int WQ_BYTES = KB * WQ_KB_BYTES;
   static constexpr int WP_BYTES = D * HD * 2;
   static constexpr int STG_BYTES = 4 * 2048;                // Y-epilogue staging: 32 rows x 16 fp32 per warp
-  static constexpr int SMEM = 1024 + A_BYTES + QKV_BYTES + P_BYTES + WQ_BYTES + 2 * WP_BYTES + STG_BYTES;
+  static constexpr int BIAS_BYTES = OVL ? 4 * 3 * D * 4 : 0; // OVL: q|k|v bias of the drained expert, one copy per drain warp
+  static constexpr int SMEM = 1024 + A_BYTES + QKV_BYTES + P_BYTES + WQ_BYTES + 2 * WP_BYTES + STG_BYTES + BIAS_BYTES;
   static_assert(NT * D == 256, "Y accumulator spans 256 TMEM columns");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
@@ -201,12 +212,13 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* sQ = sA + K::A_BYTES;                            // [N rows x 64 B]; then sK, sV
   uint8_t* sK = sQ + K::NT * K::HT_BYTES;
   uint8_t* sV = sK + K::NT * K::HT_BYTES;
-  uint8_t* sP = sV + K::NT * K::HT_BYTES;                   // two streams x 16 KiB (also: head-output tile, epilogue staging)
+  uint8_t* sP = sQ + K::QKV_BYTES;                          // two streams x 16 KiB (also: head-output tile, epilogue staging)
   uint8_t* sWq = sP + K::P_BYTES;
   uint8_t* sWp = sWq + K::WQ_BYTES;
   uint8_t* sStg = sWp + 2 * K::WP_BYTES;
+  float* sBias = reinterpret_cast<float*>(sStg + K::STG_BYTES);   // OVL: [4 drain warps][3 * D]
   __shared__ __align__(8) uint64_t a_full, a_empty, wq_full, wq_empty, wp_full[2], wp_empty[2], stg_full[2], stg_empty[2], qkv_ready,
-      s_full[2], s_empty[2], p_full[2], o_full[2], so_full[2], so_empty[2], y_full, y_empty, st1_done;
+      s_full[2], s_empty[2], p_full[2], o_full[2], so_full[2], so_empty[2], y_full, y_empty[4], st1_done, qkvr[2], qkvf[2];
   __shared__ uint32_t tmem_base_sh;
   __shared__ float ln_part[2][4][2][32];
 
@@ -217,11 +229,13 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     mbar_init(&a_full, 1); mbar_init(&a_empty, 1); mbar_init(&wq_full, 1); mbar_init(&wq_empty, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&wp_full[b], 1); mbar_init(&wp_empty[b], 2);
-      mbar_init(&stg_full[b], 1); mbar_init(&stg_empty[b], EPI_WARPS);
+      mbar_init(&stg_full[b], 1); mbar_init(&stg_empty[b], K::OVL ? 4 : EPI_WARPS);
+      mbar_init(&qkvr[b], 128); mbar_init(&qkvf[b], 2);
       mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 128); mbar_init(&p_full[b], 128); mbar_init(&o_full[b], 1);
       mbar_init(&so_full[b], 128); mbar_init(&so_empty[b], 1);
     }
-    mbar_init(&qkv_ready, EPI_WARPS * 32); mbar_init(&y_full, 2); mbar_init(&y_empty, 4); mbar_init(&st1_done, 1);
+    mbar_init(&qkv_ready, EPI_WARPS * 32); mbar_init(&y_full, 2); mbar_init(&st1_done, 1);
+    for (int b = 0; b < 4; ++b) mbar_init(&y_empty[b], 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWq)) : "memory");
@@ -245,6 +259,29 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
+      if constexpr (K::OVL) {
+        // per head: Wq_h, Wp_h, then the A tiles of the unit one at a time (consumed by the q|k|v issuer, warp 3)
+        uint32_t hc = 0, tc = 0;
+        for (int u = blockIdx.x; u < total; u += gridDim.x) {
+          const int e = u / upg;
+          for (int h = 0; h < K::HEADS; ++h, ++hc) {
+            mbar_wait(&wq_empty, (hc & 1u) ^ 1u);
+            mbar_expect_tx(&wq_full, K::WQ_BYTES);
+            for (int kb = 0; kb < K::KB; ++kb)
+              for (int part = 0; part < 3; ++part)
+                tma_load_3d(sWq + kb * K::WQ_KB_BYTES + part * 4096, &tmWq, &wq_full, kb * 64, part * D + h * HD, e);
+            const int buf = hc & 1u;
+            mbar_wait(&wp_empty[buf], ((hc >> 1) & 1u) ^ 1u);
+            mbar_expect_tx(&wp_full[buf], K::WP_BYTES);
+            tma_load_3d(sWp + buf * K::WP_BYTES, &tmWp, &wp_full[buf], h * HD, 0, e);
+            for (int mt = 0; mt < K::NT; ++mt, ++tc) {
+              mbar_wait(&a_empty, (tc & 1u) ^ 1u);
+              mbar_expect_tx(&a_full, K::A_BYTES);
+              for (int kb = 0; kb < K::KB; ++kb) tma_load_3d(sA + kb * 16384, &tmA, &a_full, kb * 64, mt * 128, u);
+            }
+          }
+        }
+      } else {
       uint32_t hc = 0;
       int i = 0;
       for (int u = blockIdx.x; u < total; u += gridDim.x, ++i) {
@@ -265,6 +302,42 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tma_load_3d(sWp + buf * K::WP_BYTES, &tmWp, &wp_full[buf], h * HD, 0, e);
         }
       }
+      }
+    }
+  } else if (warp == 3) {
+    // ============================== q|k|v MMA issuer (OVL) ==============================
+    // Runs ahead of the attention: per head and 128-token tile two parts -- q|k (N = 64) and v (N = 32) -- into the
+    // dedicated staging columns; the Y-epilogue warpgroup drains each part into the q/k/v buffer of the head's parity.
+    if constexpr (K::OVL) {
+      if (lane == 0) {
+        constexpr uint32_t idesc_qk = make_idesc(64), idesc_v = make_idesc(32);
+        uint32_t hc = 0, tc = 0, pc = 0;
+        for (int u = blockIdx.x; u < total; u += gridDim.x) {
+          for (int h = 0; h < K::HEADS; ++h, ++hc) {
+            mbar_wait(&wq_full, hc & 1u);
+            tc_fence_after();
+            for (int mt = 0; mt < K::NT; ++mt, ++tc) {
+              mbar_wait(&a_full, tc & 1u);
+              tc_fence_after();
+#pragma unroll
+              for (int part = 0; part < 2; ++part, ++pc) {
+                mbar_wait(&stg_empty[0], (pc & 1u) ^ 1u);
+                tc_fence_after();
+                for (int kb = 0; kb < K::KB; ++kb) {
+                  const uint64_t ad = make_desc(smem_u32(sA + kb * 16384), 1024, 2);
+                  const uint64_t bd = make_desc(smem_u32(sWq + kb * K::WQ_KB_BYTES + part * 8192), 1024, 2);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_base + STGX_COL, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), part ? idesc_v : idesc_qk, (kb | k) != 0);
+                }
+                umma_commit(&stg_full[0]);
+              }
+              umma_commit(&a_empty);                         // this A tile is free once its q|k and v MMAs retire
+            }
+            umma_commit(&wq_empty);
+          }
+        }
+      }
     }
   } else if (warp == 1 || warp == 2) {
     // ============================== MMA issuers ==============================
@@ -277,10 +350,9 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t hc = 0, mc = 0, pc = 0, qc = 0;
       int i = 0;
       for (int u = blockIdx.x; u < total; u += gridDim.x, ++i) {
-        if (s == 0) { mbar_wait(&a_full, (uint32_t)i & 1u); tc_fence_after(); }
-        bool y_free = false;                                 // the previous unit's epilogue has drained Y
+        if (!K::OVL && s == 0) { mbar_wait(&a_full, (uint32_t)i & 1u); tc_fence_after(); }
         for (int h = 0; h < K::HEADS; ++h, ++hc) {
-          if (s == 0) {
+          if (!K::OVL && s == 0) {
             // ---- phase 1: q|k|v of this head for every 128-token tile -> staging columns (two buffers over the S / O
             // columns of both streams: stream 1 must have retired the previous head first)
             mbar_wait(&wq_full, hc & 1u);
@@ -302,13 +374,17 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (h == K::HEADS - 1) umma_commit(&a_empty);    // ... and so is A after the last head
           }
           // ---- phase 2: this stream's query tiles s, s+2, ..
-          mbar_wait(&qkv_ready, hc & 1u);
           const int buf = hc & 1u;
+          if constexpr (K::OVL) mbar_wait(&qkvr[buf], (hc >> 1) & 1u);      // q/k/v of this head drained into buffer hc % 2
+          else mbar_wait(&qkv_ready, hc & 1u);
           mbar_wait(&wp_full[buf], (hc >> 1) & 1u);
           tc_fence_after();
+          uint8_t* const sQh = sQ + (K::OVL ? buf * K::QKV1_BYTES : 0);
+          uint8_t* const sKh = sK + (K::OVL ? buf * K::QKV1_BYTES : 0);
+          uint8_t* const sVh = sV + (K::OVL ? buf * K::QKV1_BYTES : 0);
           auto issue_s = [&](int qt, int kr) {
-            const uint64_t qd = make_desc(smem_u32(sQ + qt * K::HT_BYTES), 512, 4);
-            const uint64_t kd = make_desc(smem_u32(sK + kr * 4096), 512, 4);
+            const uint64_t qd = make_desc(smem_u32(sQh + qt * K::HT_BYTES), 512, 4);
+            const uint64_t kd = make_desc(smem_u32(sKh + kr * 4096), 512, 4);
 #pragma unroll
             for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + s_col, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_s, k);
             umma_commit(&s_full[s]);
@@ -334,7 +410,7 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 // O (+)= P V: the accumulator lives in TMEM for the whole query tile (the softmax warps rescale it in
                 // place on the rare occasions the running reference maximum moves)
                 const uint64_t pd = make_desc(smem_u32(sP + s * K::P_TILE), 1024, 2);
-                const uint64_t vd = make_desc(smem_u32(sV + kr * 4096), 512, 4);
+                const uint64_t vd = make_desc(smem_u32(sVh + kr * 4096), 512, 4);
 #pragma unroll
                 for (int k = 0; k < 64 / 16; ++k)             // P: +32 B per 16 keys inside the 128 B row; V: +16 key rows of 64 B
                   umma_bf16(tmem_base + o_col, pd + (uint64_t)(k * 2), vd + (uint64_t)((k * 16 * 64) >> 4), idesc_o, (!first_of_tile) || k != 0);
@@ -347,7 +423,8 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 // Y[qt] (+)= O_h Wproj[:, h*32 : h*32+32]^T
                 mbar_wait(&so_full[s], qc & 1u);
                 tc_fence_after();
-                if (h == 0 && !y_free) { mbar_wait(&y_empty, ((uint32_t)i & 1u) ^ 1u); tc_fence_after(); y_free = true; }
+                // first head: the previous unit's epilogue must have drained THIS tile's Y columns (released tile by tile)
+                if (h == 0) { mbar_wait(&y_empty[qt], ((uint32_t)i & 1u) ^ 1u); tc_fence_after(); }
                 const uint64_t od = make_desc(smem_u32(sP + s * K::P_TILE), 512, 4);
                 const uint64_t wd = make_desc(smem_u32(sWp + buf * K::WP_BYTES), 512, 4);
 #pragma unroll
@@ -362,6 +439,7 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           umma_commit(&wp_empty[buf]);
           if (s == 1) umma_commit(&st1_done);
+          if constexpr (K::OVL) umma_commit(&qkvf[buf]);      // this stream has retired the head: its q/k/v buffer may be refilled
         }
         umma_commit(&y_full);
       }
@@ -385,6 +463,7 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int u = blockIdx.x; u < total; u += gridDim.x, ++i) {
       const int e = u / upg, b = u % upg;
       for (int h = 0; h < K::HEADS; ++h, ++hc) {
+        if constexpr (!K::OVL) {
         // ---- phase 1 (all eight warps): staging columns -> (+bias, q scaled) -> bf16 -> 64B-swizzled K-major head tiles
         float bias[3][16];
 #pragma unroll
@@ -422,6 +501,7 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(&qkv_ready);
 
+        }
         // ---- phase 2: stream ch owns query tiles ch, ch+2, ..; one thread = one query row, one key block = 64 keys
         for (int qt = ch; qt < K::NT; qt += 2, ++qc, ++pc) {
           const int qh = 2 * qt + (r >> 6), qw = r & 63;       // grid row / column of this query
@@ -571,6 +651,64 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // XOR-swizzled by row), so that global accesses are 64-byte row segments: lane = (row in a group of 8, float4 of the 16)
     float* stg = reinterpret_cast<float*>(sStg + q * 2048);
     const int rsub = lane >> 2, c4 = lane & 3;
+    // ---- OVL: this warpgroup also drains the q|k|v staging parts (one warp per TMEM lane quarter) into the q/k/v buffer of
+    // the head's parity.  Never blocking: a drain runs only when its part is complete in TMEM and (first part of a head)
+    // the target buffer has been retired by both attention streams; otherwise the warp goes back to the Y epilogue, which
+    // the attention of a later head may be waiting for (y_empty).
+    int d_u = blockIdx.x, d_h = 0, d_part = 0, d_e = -1;       // next drain: unit, head, part (2 per 128-token tile)
+    uint32_t d_pc = 0, d_hc = 0;                               // staging phase counter, global head counter
+    float* wbias = sBias + q * 3 * D;                          // this warp's copy of the expert's q|k|v bias
+    auto try_drain = [&]() -> bool {
+      if constexpr (!K::OVL) return false;
+      if (d_u >= total) return false;
+      if (!mbar_test(&stg_full[0], d_pc & 1u)) return false;
+      const int hb = d_hc & 1u;
+      if (d_part == 0) {
+        if (!mbar_test(&qkvf[hb], ((d_hc >> 1) & 1u) ^ 1u)) return false;
+        const int e = d_u / upg;
+        if (e != d_e) {
+          __syncwarp();
+          for (int k = lane; k < 3 * D; k += 32) wbias[k] = ep.bqkv[(long)e * 3 * D + k];
+          __syncwarp();
+          d_e = e;
+        }
+      }
+      tc_fence_after();
+      const int mt = d_part >> 1, part = d_part & 1;
+      const int r = q * 32 + lane, sw = (r >> 1) & 3;
+      uint8_t* qkv = sQ + hb * K::QKV1_BYTES;
+      const int nt = part ? 1 : 2;                             // 32-column tensors in this part: q, k | v
+      for (int tt = 0; tt < nt; ++tt) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + STGX_COL + (uint32_t)(tt * 32), v);
+        if (tt == nt - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&stg_empty[0]);           // this warp's rows of the part are out of TMEM
+        }
+        const int t = part ? 2 : tt;                           // 0 = q, 1 = k, 2 = v
+        const float4* bp = reinterpret_cast<const float4*>(wbias + t * D + d_h * HD);
+        uint8_t* row = qkv + (size_t)t * K::NT * K::HT_BYTES + mt * K::HT_BYTES + r * 64;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {                          // 16-byte chunks of 8 head dimensions
+          const float4 b0 = bp[2 * c], b1 = bp[2 * c + 1];
+          *reinterpret_cast<uint4*>(row + ((c ^ sw) * 16)) = make_uint4(
+              pack_bf16(__uint_as_float(v[8 * c]) + b0.x, __uint_as_float(v[8 * c + 1]) + b0.y),
+              pack_bf16(__uint_as_float(v[8 * c + 2]) + b0.z, __uint_as_float(v[8 * c + 3]) + b0.w),
+              pack_bf16(__uint_as_float(v[8 * c + 4]) + b1.x, __uint_as_float(v[8 * c + 5]) + b1.y),
+              pack_bf16(__uint_as_float(v[8 * c + 6]) + b1.z, __uint_as_float(v[8 * c + 7]) + b1.w));
+        }
+      }
+      ++d_pc;
+      if (++d_part == 2 * K::NT) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&qkvr[hb]);                                // 128 arrivals: every row of every tile of the head is in place
+        if (warp == 12 && lane == 0) MIX_TRACE(14, (int)d_hc); // epi: head d_hc drained
+        d_part = 0; ++d_hc;
+        if (++d_h == K::HEADS) { d_h = 0; d_u += gridDim.x; }
+      }
+      return true;
+    };
     int i = 0;
     for (int u = blockIdx.x; u < total; u += gridDim.x, ++i) {
       const int e = u / upg, b = u % upg;
@@ -584,24 +722,37 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < 8; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(xl2 + ((long)(k * 128 + (threadIdx.x - 384))) * 128));
       }
-      mbar_wait(&y_full, (uint32_t)i & 1u);
+      if constexpr (K::OVL) {
+        while (!mbar_test(&y_full, (uint32_t)i & 1u)) {
+          if (!try_drain()) __nanosleep(32);
+        }
+      } else {
+        mbar_wait(&y_full, (uint32_t)i & 1u);
+      }
       tc_fence_after();
+      if (warp == 12 && lane == 0) MIX_TRACE(11, i);           // epi: y_full observed
       for (int qt = 0; qt < K::NT; ++qt) {
         float* xt = xunit + (long)(qt * 128 + q * 32) * D;     // the warp's 32 rows of this query tile
         float sum[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+        float4 xin[4], xnx[4];                                 // residual rows of this / the next 16-column step
+        if (!(ep.dbg & 2)) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) xin[it] = *reinterpret_cast<const float4*>(xt + (long)(it * 8 + rsub) * D + c4 * 4);
+        }
 #pragma unroll 1
         for (int c = 0; c < D / 16; ++c) {
-          float4 xin[4];
-          if (!(ep.dbg & 2)) {
+          if constexpr (K::OVL) { while (try_drain()) {} }     // q|k|v parts waiting in TMEM go first (at most a few per step)
+          if (!(ep.dbg & 2) && c + 1 < D / 16) {
 #pragma unroll
-            for (int it = 0; it < 4; ++it) xin[it] = *reinterpret_cast<const float4*>(xt + (long)(it * 8 + rsub) * D + c * 16 + c4 * 4);
+            for (int it = 0; it < 4; ++it) xnx[it] = *reinterpret_cast<const float4*>(xt + (long)(it * 8 + rsub) * D + (c + 1) * 16 + c4 * 4);
           }
           uint32_t v[16];
           tmem_ld16(lane_addr + Y_COL + (uint32_t)(qt * D + c * 16), v);
-          if (qt == K::NT - 1 && c == D / 16 - 1) {
+          if (c == D / 16 - 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&y_empty);              // accumulator drained: the next unit may overwrite it
+            if (lane == 0) mbar_arrive(&y_empty[qt]);          // this tile's accumulator columns are drained: the next unit may overwrite them
+            if (warp == 12 && lane == 0 && qt == K::NT - 1) MIX_TRACE(12, i);     // epi: Y drained
           }
           if (ep.dbg & 2) continue;
 #pragma unroll
@@ -620,6 +771,8 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             *reinterpret_cast<float4*>(xt + (long)rl * D + c * 16 + c4 * 4) = o;
             if (LNF) { sum[it] += (o.x + o.y) + (o.z + o.w); sq[it] += fmaf(o.x, o.x, o.y * o.y) + fmaf(o.z, o.z, o.w * o.w); }
           }
+#pragma unroll
+          for (int it = 0; it < 4; ++it) xin[it] = xnx[it];
           __syncwarp();
         }
         if (LNF && !(ep.dbg & 2)) {
@@ -652,6 +805,7 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       }
+      if (warp == 12 && lane == 0) MIX_TRACE(13, i);           // epi: unit done
     }
   }
   tc_fence_before();

@@ -44,3 +44,12 @@ print("avg ns over %d pairs: wait S %.0f | ld S %.0f | max %.0f | wait PV(prev) 
 valid_m = [p for p in range(2, 200) if t[0, p] and t[3, p]]
 dm = lambda a, b: float(np.mean([t[b, p] - t[a, p] for p in valid_m]))
 print("MMA issuer avg ns: wait s_empty + issue S %.0f | wait P %.0f | issue PV %.0f" % (dm(0, 1), dm(1, 2), dm(2, 3)))
+
+# OVL (D = 128): Y-epilogue warpgroup timeline, us relative to the first softmax stamp
+if t[11, 0]:
+    f = lambda v: "%.2f" % ((int(v) - int(t0)) / 1e3) if v else "-"
+    print("unit | y_full seen | Y drained | epilogue done ; heads drained at (4 per unit)")
+    for i in range(4):
+        print("%4d | %s | %s | %s ; %s" % (i, f(t[11, i]), f(t[12, i]), f(t[13, i]), " ".join(f(t[14, 4 * i + k]) for k in range(4))))
+    hs = [p for p in range(0, 48, 4) if t[4, p]]
+    print("softmax stream 0, first pair of each head: wait-S start / S ready:", " ".join("%s/%s" % (f(t[4, p]), f(t[5, p])) for p in hs))
