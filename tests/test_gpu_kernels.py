@@ -260,6 +260,52 @@ def test_dm_router_tensor_core_engine(name):
 
 
 @pytest.mark.parametrize("prec_name", ["fp32", "bf16"])
+@pytest.mark.parametrize("I,B,T", [(6, 3, 64), (3, 5, 64), (6, 2, 63)])
+def test_router_training_backward_matches_fp64_autograd(prec_name, I, B, T):
+    """mrnb_router_backward (il_modules/mrn.py:342,360: loss = 15 * CTC + CrossEntropy(gate, domain)) against the fp64
+    autograd of the oracle for L = sum(dgate_ctc * gate) + CE(gate, domain): EVERY parameter gradient (gate head +
+    DM_Router) and the CE loss.  bf16 = the gate-head driven tensor-core path (rank-one d_out, LayerNorm 1 folded into
+    proj_1, collapsed last Linear), incl. the T = 63 run padded to 64 frames; fp32 = the generic CUDA-core path."""
+    ops = _ops()
+    from mrn_b200 import _lib as L
+    seed = 70 + I + T
+    prec = L.PREC_BF16 if prec_name == "bf16" else L.PREC_FP32
+    tol_gate, tol_g = (2e-2, 5e-2) if prec_name == "bf16" else (1e-4, 5e-4)   # 5e-2: the bf16 router-gradient budget of test_gpu_step.py
+    sd = {k: synth.synth_tensor(seed, k, s) for k, s in synth.router_shapes(I, T=T).items()}
+    x = synth.randn(seed, "router_x", (B, I, T, 256))
+    dgc = synth.randn(seed, "dgate_ctc", (B, I)) * 0.3
+    dom = torch.tensor([(3 * b + 1) % I for b in range(B)], dtype=torch.int64)
+    sdd = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    r = O.gate_scores(sdd, O.dm_router(sdd, x.double()))
+    gate_ref = torch.softmax(r, -1)
+    ce = torch.nn.functional.cross_entropy(gate_ref, dom)           # the reference applies CE to the softmaxed gate
+    ((gate_ref * dgc.double()).sum() + ce).backward()
+    n, off = ops.router_param_offsets(I, T)
+    arena = torch.zeros(n, dtype=torch.float32)
+    for k, name in enumerate(ops.ROUTER_PARAM_NAMES):
+        arena[off[k]:off[k] + sd[name].numel()] = sd[name].reshape(-1)
+    arena = arena.cuda()
+    ws = ops.RouterWorkspace()
+    out, scores, gate, index = ops.router_forward(arena, dev(x), ws, with_backward=True, prec=prec)
+    assert np.abs(gate.cpu().numpy() - gate_ref.detach().numpy()).max() < tol_gate
+    grads = torch.full_like(arena, float("nan"))
+    # the CTC part of dL/dgate is an input of the kernel; with the GPU's own gate the two losses differ only through
+    # the (tolerated) gate deviation
+    taski = ops.router_backward(arena, dev(x), gate, dev(dgc), dom.cuda(), grads, ws, prec=prec)
+    assert abs(float(taski) - float(ce.detach())) < 1e-3
+    gc = grads.cpu()
+    assert torch.isfinite(gc).all()
+    gmax = max(float(v.grad.abs().max()) for v in sdd.values())
+    for k, pname in enumerate(ops.ROUTER_PARAM_NAMES):
+        got = gc[off[k]:off[k] + sd[pname].numel()].reshape(sd[pname].shape).double().numpy()
+        ref = sdd[pname].grad.numpy()
+        # route.bias has an analytically zero gradient (softmax shift invariance): floor the yardstick
+        scale = max(float(np.abs(ref).max()), 1e-3 * gmax)
+        err = float(np.abs(got - ref).max()) / scale
+        assert err < tol_g, (pname, err)
+
+
+@pytest.mark.parametrize("prec_name", ["fp32", "bf16"])
 @pytest.mark.parametrize("I,B", [(2, 3), (6, 2)])
 def test_dm_router_63_frames(prec_name, I, B):
     """CRNN's T = 63 (modules/model.py:322-323).  fp32: the CUDA-core engine on the unpadded problem; bf16: the tcgen05
