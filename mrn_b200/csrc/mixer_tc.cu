@@ -199,6 +199,90 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// Y epilogue of ONE 128-token query tile for the 32 rows of the calling warp (TMEM lane quarter q):
+//   x <- x + rs * (Y + b_proj) in place  [+ LayerNorm 2 -> ln_out (bf16)]
+// 16 accumulator columns of the warp's 32 rows are transposed through a 2 KiB staging tile `stg` (row-major, 16-byte
+// pieces XOR-swizzled by row) so that global accesses are 64-byte row segments: lane = (row in a group of 8, float4 of
+// the 16).  The residual rows of the next step are prefetched.  `release` (optional mbarrier) is arrived on by lane 0
+// once the tile's Y columns are out of TMEM.  Called by the Y-epilogue warpgroup (one warp per quarter, every tile) or,
+// OVL, by the softmax warps of the stream that owns the tile.
+template <int D, bool LNF, int LNU = 2>
+__device__ __forceinline__ void y_tile_epilogue(const MixParams& ep, int e, long unit, int qt, int q, int lane, uint32_t y_addr,
+                                                float* xt, float rs, float* stg, uint64_t* release) {
+  const int rsub = lane >> 2, c4 = lane & 3;
+  const float* bpj = ep.bproj + (long)e * D;
+  float sum[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+  float4 xin[4], xnx[4];                                 // residual rows of this / the next 16-column step
+  if (!(ep.dbg & 2)) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) xin[it] = *reinterpret_cast<const float4*>(xt + (long)(it * 8 + rsub) * D + c4 * 4);
+  }
+#pragma unroll 1
+  for (int c = 0; c < D / 16; ++c) {
+    if (!(ep.dbg & 2) && c + 1 < D / 16) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it) xnx[it] = *reinterpret_cast<const float4*>(xt + (long)(it * 8 + rsub) * D + (c + 1) * 16 + c4 * 4);
+    }
+    uint32_t v[16];
+    tmem_ld16(y_addr + (uint32_t)(c * 16), v);
+    if (c == D / 16 - 1) {
+      tc_fence_before();
+      __syncwarp();
+      if (release && lane == 0) mbar_arrive(release);    // this tile's accumulator columns are drained
+    }
+    if (ep.dbg & 2) continue;
+#pragma unroll
+    for (int pc = 0; pc < 4; ++pc)
+      *reinterpret_cast<float4*>(stg + lane * 16 + ((pc ^ (lane & 3)) * 4)) =
+          make_float4(__uint_as_float(v[4 * pc]), __uint_as_float(v[4 * pc + 1]), __uint_as_float(v[4 * pc + 2]), __uint_as_float(v[4 * pc + 3]));
+    __syncwarp();
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bpj + c * 16 + c4 * 4));
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int rl = it * 8 + rsub;
+      const float4 a = *reinterpret_cast<const float4*>(stg + rl * 16 + ((c4 ^ (rl & 3)) * 4));
+      float4 o;
+      o.x = fmaf(a.x + b4.x, rs, xin[it].x); o.y = fmaf(a.y + b4.y, rs, xin[it].y);
+      o.z = fmaf(a.z + b4.z, rs, xin[it].z); o.w = fmaf(a.w + b4.w, rs, xin[it].w);
+      *reinterpret_cast<float4*>(xt + (long)rl * D + c * 16 + c4 * 4) = o;
+      if (LNF) { sum[it] += (o.x + o.y) + (o.z + o.w); sq[it] += fmaf(o.x, o.x, o.y * o.y) + fmaf(o.z, o.z, o.w * o.w); }
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) xin[it] = xnx[it];
+    __syncwarp();
+  }
+  if (LNF && !(ep.dbg & (2 | 32))) {
+    // row statistics: the four lanes of a row hold its partial sums; second pass over the rows just written
+    // (the warp's own stores: L1 / L2 hits) -> LayerNorm 2 in bf16
+    const float* gam = ep.ln_gamma + (long)e * D;
+    const float* bet = ep.ln_beta + (long)e * D;
+    float mean[4], rstd[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      float s1 = sum[it], s2 = sq[it];
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+      mean[it] = s1 * (1.0f / D);
+      rstd[it] = rsqrtf(fmaxf(s2 * (1.0f / D) - mean[it] * mean[it], 0.f) + ep.ln_eps);
+    }
+    __nv_bfloat16* lt = ep.ln_out + ((long)unit * (32768 / D) + qt * 128 + q * 32) * D;
+    // LNU steps unrolled: LNU x 4 independent 16-byte loads of the just-written rows in flight (they come back from L2)
+#pragma unroll LNU
+    for (int c = 0; c < D / 16; ++c) {
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(gam + c * 16 + c4 * 4));
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(bet + c * 16 + c4 * 4));
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rl = it * 8 + rsub;
+        const float4 xv = *reinterpret_cast<const float4*>(xt + (long)rl * D + c * 16 + c4 * 4);
+        *reinterpret_cast<uint2*>(lt + (long)rl * D + c * 16 + c4 * 4) = make_uint2(
+            pack_bf16((xv.x - mean[it]) * rstd[it] * g4.x + t4.x, (xv.y - mean[it]) * rstd[it] * g4.y + t4.y),
+            pack_bf16((xv.z - mean[it]) * rstd[it] * g4.z + t4.z, (xv.w - mean[it]) * rstd[it] * g4.w + t4.w));
+      }
+    }
+  }
+}
+
 template <int D, bool LOCAL, bool LNF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWq,
@@ -218,7 +302,7 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* sStg = sWp + 2 * K::WP_BYTES;
   float* sBias = reinterpret_cast<float*>(sStg + K::STG_BYTES);   // OVL: [4 drain warps][3 * D]
   __shared__ __align__(8) uint64_t a_full, a_empty, wq_full, wq_empty, wp_full[2], wp_empty[2], stg_full[2], stg_empty[2], qkv_ready,
-      s_full[2], s_empty[2], p_full[2], o_full[2], so_full[2], so_empty[2], y_full, y_empty[4], st1_done, qkvr[2], qkvf[2];
+      s_full[2], s_empty[2], p_full[2], o_full[2], so_full[2], so_empty[2], y_full, y_empty[4], st1_done, qkvr[2], qkvf[2], yd[2];
   __shared__ uint32_t tmem_base_sh;
   __shared__ float ln_part[2][4][2][32];
 
@@ -230,7 +314,7 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int b = 0; b < 2; ++b) {
       mbar_init(&wp_full[b], 1); mbar_init(&wp_empty[b], 2);
       mbar_init(&stg_full[b], 1); mbar_init(&stg_empty[b], K::OVL ? 4 : EPI_WARPS);
-      mbar_init(&qkvr[b], 128); mbar_init(&qkvf[b], 2);
+      mbar_init(&qkvr[b], 128); mbar_init(&qkvf[b], 2); mbar_init(&yd[b], 1);
       mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 128); mbar_init(&p_full[b], 128); mbar_init(&o_full[b], 1);
       mbar_init(&so_full[b], 128); mbar_init(&so_empty[b], 1);
     }
@@ -423,14 +507,16 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 // Y[qt] (+)= O_h Wproj[:, h*32 : h*32+32]^T
                 mbar_wait(&so_full[s], qc & 1u);
                 tc_fence_after();
-                // first head: the previous unit's epilogue must have drained THIS tile's Y columns (released tile by tile)
-                if (h == 0) { mbar_wait(&y_empty[qt], ((uint32_t)i & 1u) ^ 1u); tc_fence_after(); }
+                // first head: the previous unit's epilogue must have drained THIS tile's Y columns (released tile by tile).
+                // OVL: the stream's own softmax warps run that epilogue before they hand over this head output
+                if (!K::OVL && h == 0) { mbar_wait(&y_empty[qt], ((uint32_t)i & 1u) ^ 1u); tc_fence_after(); }
                 const uint64_t od = make_desc(smem_u32(sP + s * K::P_TILE), 512, 4);
                 const uint64_t wd = make_desc(smem_u32(sWp + buf * K::WP_BYTES), 512, 4);
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k)
                   umma_bf16(tmem_base + Y_COL + (uint32_t)(qt * D), od + (uint64_t)(k * 2), wd + (uint64_t)(k * 2), idesc_y, (h | k) != 0);
                 umma_commit(&so_empty[s]);
+                if (K::OVL && h == K::HEADS - 1) umma_commit(&yd[s]);    // Y of this stream's tile is complete for the unit
                 ++qc;
               }
               if (!has_next) break;
@@ -441,7 +527,7 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (s == 1) umma_commit(&st1_done);
           if constexpr (K::OVL) umma_commit(&qkvf[buf]);      // this stream has retired the head: its q/k/v buffer may be refilled
         }
-        umma_commit(&y_full);
+        if (!K::OVL) umma_commit(&y_full);
       }
     }
   } else if (warp >= 4 && warp < 12) {
@@ -462,6 +548,13 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int i = 0;
     for (int u = blockIdx.x; u < total; u += gridDim.x, ++i) {
       const int e = u / upg, b = u % upg;
+      if constexpr (K::OVL) {
+        // the residual rows of this stream's tile (64 KiB) start their trip from HBM to L2 now; they are needed by the
+        // Y epilogue after the last head
+        const char* xl2 = reinterpret_cast<const char*>(ep.x + (long)e * ep.x_gs + (long)b * K::N * D + (long)(ch * 128) * D);
+#pragma unroll
+        for (int k = 0; k < D / 32; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(xl2 + (long)(k * 128 + q * 32 + lane) * 128));
+      }
       for (int h = 0; h < K::HEADS; ++h, ++hc) {
         if constexpr (!K::OVL) {
         // ---- phase 1 (all eight warps): staging columns -> (+bias, q scaled) -> bf16 -> 64B-swizzled K-major head tiles
@@ -636,6 +729,19 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           mbar_arrive(&so_full[ch]);
+          if constexpr (K::OVL) {
+            if (h == K::HEADS - 1) {
+              // OVL: Y epilogue of this stream's own tile, right after the unit's last proj MMA (the Y-epilogue warpgroup is
+              // busy draining q|k|v of the next heads).  Staging = the 4 KiB of the P tile this warp itself writes: free once
+              // that proj MMA (the last reader of the tile buffer) has retired, which yd signals too.
+              mbar_wait(&yd[ch], (uint32_t)i & 1u);
+              tc_fence_after();
+              const float rs = ep.rowscale ? ep.rowscale[(long)e * ep.rs_gs + b] : 1.0f;
+              float* xt = ep.x + (long)e * ep.x_gs + (long)b * K::N * D + (long)(qt * 128 + q * 32) * D;
+              y_tile_epilogue<D, LNF, 8>(ep, e, u, qt, q, lane, lane_addr + Y_COL + (uint32_t)(qt * D), xt, rs, stg, nullptr);
+              tc_fence_before();
+            }
+          }
         }
       }
 
@@ -709,12 +815,17 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       return true;
     };
+    if constexpr (K::OVL) {
+      // OVL: the attention streams run the Y epilogue of their own tile; this warpgroup only drains q|k|v parts
+      while (d_u < total) {
+        if (!try_drain()) __nanosleep(64);
+      }
+    } else {
     int i = 0;
     for (int u = blockIdx.x; u < total; u += gridDim.x, ++i) {
       const int e = u / upg, b = u % upg;
       const float rs = ep.rowscale ? ep.rowscale[(long)e * ep.rs_gs + b] : 1.0f;
       float* xunit = ep.x + (long)e * ep.x_gs + (long)b * K::N * D;
-      const float* bpj = ep.bproj + (long)e * D;
       {
         // this warpgroup is idle until the unit's last proj MMA retires: start the trip of its residual rows (128 KiB)
         // from HBM to L2 now
@@ -722,90 +833,17 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < 8; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(xl2 + ((long)(k * 128 + (threadIdx.x - 384))) * 128));
       }
-      if constexpr (K::OVL) {
-        while (!mbar_test(&y_full, (uint32_t)i & 1u)) {
-          if (!try_drain()) __nanosleep(32);
-        }
-      } else {
-        mbar_wait(&y_full, (uint32_t)i & 1u);
-      }
+      mbar_wait(&y_full, (uint32_t)i & 1u);
       tc_fence_after();
       if (warp == 12 && lane == 0) MIX_TRACE(11, i);           // epi: y_full observed
       for (int qt = 0; qt < K::NT; ++qt) {
-        float* xt = xunit + (long)(qt * 128 + q * 32) * D;     // the warp's 32 rows of this query tile
-        float sum[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
-        float4 xin[4], xnx[4];                                 // residual rows of this / the next 16-column step
-        if (!(ep.dbg & 2)) {
-#pragma unroll
-          for (int it = 0; it < 4; ++it) xin[it] = *reinterpret_cast<const float4*>(xt + (long)(it * 8 + rsub) * D + c4 * 4);
-        }
-#pragma unroll 1
-        for (int c = 0; c < D / 16; ++c) {
-          if constexpr (K::OVL) { while (try_drain()) {} }     // q|k|v parts waiting in TMEM go first (at most a few per step)
-          if (!(ep.dbg & 2) && c + 1 < D / 16) {
-#pragma unroll
-            for (int it = 0; it < 4; ++it) xnx[it] = *reinterpret_cast<const float4*>(xt + (long)(it * 8 + rsub) * D + (c + 1) * 16 + c4 * 4);
-          }
-          uint32_t v[16];
-          tmem_ld16(lane_addr + Y_COL + (uint32_t)(qt * D + c * 16), v);
-          if (c == D / 16 - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&y_empty[qt]);          // this tile's accumulator columns are drained: the next unit may overwrite them
-            if (warp == 12 && lane == 0 && qt == K::NT - 1) MIX_TRACE(12, i);     // epi: Y drained
-          }
-          if (ep.dbg & 2) continue;
-#pragma unroll
-          for (int pc = 0; pc < 4; ++pc)
-            *reinterpret_cast<float4*>(stg + lane * 16 + ((pc ^ (lane & 3)) * 4)) =
-                make_float4(__uint_as_float(v[4 * pc]), __uint_as_float(v[4 * pc + 1]), __uint_as_float(v[4 * pc + 2]), __uint_as_float(v[4 * pc + 3]));
-          __syncwarp();
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bpj + c * 16 + c4 * 4));
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int rl = it * 8 + rsub;
-            const float4 a = *reinterpret_cast<const float4*>(stg + rl * 16 + ((c4 ^ (rl & 3)) * 4));
-            float4 o;
-            o.x = fmaf(a.x + b4.x, rs, xin[it].x); o.y = fmaf(a.y + b4.y, rs, xin[it].y);
-            o.z = fmaf(a.z + b4.z, rs, xin[it].z); o.w = fmaf(a.w + b4.w, rs, xin[it].w);
-            *reinterpret_cast<float4*>(xt + (long)rl * D + c * 16 + c4 * 4) = o;
-            if (LNF) { sum[it] += (o.x + o.y) + (o.z + o.w); sq[it] += fmaf(o.x, o.x, o.y * o.y) + fmaf(o.z, o.z, o.w * o.w); }
-          }
-#pragma unroll
-          for (int it = 0; it < 4; ++it) xin[it] = xnx[it];
-          __syncwarp();
-        }
-        if (LNF && !(ep.dbg & 2)) {
-          // row statistics: the four lanes of a row hold its partial sums; second pass over the rows just written
-          // (the warp's own stores: L1 / L2 hits) -> LayerNorm 2 in bf16
-          const float* gam = ep.ln_gamma + (long)e * D;
-          const float* bet = ep.ln_beta + (long)e * D;
-          float mean[4], rstd[4];
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            float s1 = sum[it], s2 = sq[it];
-            s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-            mean[it] = s1 * (1.0f / D);
-            rstd[it] = rsqrtf(fmaxf(s2 * (1.0f / D) - mean[it] * mean[it], 0.f) + ep.ln_eps);
-          }
-          __nv_bfloat16* lt = ep.ln_out + ((long)u * K::N + qt * 128 + q * 32) * D;
-#pragma unroll 1
-          for (int c = 0; c < D / 16; ++c) {
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(gam + c * 16 + c4 * 4));
-            const float4 t4 = __ldg(reinterpret_cast<const float4*>(bet + c * 16 + c4 * 4));
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int rl = it * 8 + rsub;
-              const float4 xv = *reinterpret_cast<const float4*>(xt + (long)rl * D + c * 16 + c4 * 4);
-              *reinterpret_cast<uint2*>(lt + (long)rl * D + c * 16 + c4 * 4) = make_uint2(
-                  pack_bf16((xv.x - mean[it]) * rstd[it] * g4.x + t4.x, (xv.y - mean[it]) * rstd[it] * g4.y + t4.y),
-                  pack_bf16((xv.z - mean[it]) * rstd[it] * g4.z + t4.z, (xv.w - mean[it]) * rstd[it] * g4.w + t4.w));
-            }
-          }
-        }
+        // Y is handed back tile by tile (y_empty[qt]): the next unit's first proj MMA of a tile only waits for that tile
+        y_tile_epilogue<D, LNF>(ep, e, u, qt, q, lane, lane_addr + Y_COL + (uint32_t)(qt * D), xunit + (long)(qt * 128 + q * 32) * D,
+                                rs, stg, &y_empty[qt]);
+        if (warp == 12 && lane == 0 && qt == K::NT - 1) MIX_TRACE(12, i);     // epi: Y drained (+ LayerNorm of the last tile)
       }
       if (warp == 12 && lane == 0) MIX_TRACE(13, i);           // epi: unit done
+    }
     }
   }
   tc_fence_before();
