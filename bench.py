@@ -554,6 +554,33 @@ def run_ours(args):
                                      % (args.arch.upper(), B))
         if args.sweep:
             out["sweep"] = infer_sweep(learner, [int(x) for x in args.sweep.split(",") if x], dev)
+        if world == 1 and not args.no_parity_probe and args.arch == "svtr":
+            # decode parity on a bounded sample: routed expert, greedy-decoded ids and confidence of the first 16 crops
+            # against the fp32 CPU oracle (north_star: identical decoded indices except exact-tie arg-max cases, counted)
+            from oracle import mrn_oracle as O
+            ns = min(16, B)
+            torch.set_num_threads(os.cpu_count() or 1)
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                ref = O.mrn_forward({k: v.clone() for k, v in sd.items()}, 6, host[0][0][:ns].float(), is_train=False, bn_mode="eval")
+                k_ref, seq_ref, conf_ref = O.greedy_decode(ref["logits"])
+            r = learner.infer_batch(resident[0][0][:ns].contiguous(), "TF")
+            ids, lens, conf = r["ids"].cpu(), r["lens"].cpu(), r["conf"].cpu()
+            same, tie_like = 0, 0
+            top2 = ref["logits"].topk(2, dim=2)[0]
+            margin = (top2[..., 0] - top2[..., 1])                       # [ns, T] arg-max margin of the oracle logits
+            for b_ in range(ns):
+                got = [int(v) for v in ids[b_, :int(lens[b_])]]
+                if got == seq_ref[b_]:
+                    same += 1
+                elif float(margin[b_].min()) < 2e-2 * float(ref["logits"][b_].abs().max()):
+                    tie_like += 1                                          # a frame whose top-2 logits sit within the bf16 budget
+            out["decode_parity"] = {
+                "samples": ns, "route_identical": int((r["index"].cpu() == ref["index"]).sum()), "decoded_identical": same,
+                "mismatches_at_near_ties": tie_like, "mismatches_other": ns - same - tie_like,
+                "max_conf_abs_err": float((conf - conf_ref).abs().max()), "max_conf_ref": float(conf_ref.max()),
+                "oracle_cpu_s": round(time.perf_counter() - t0, 2),
+                "note": "fp32 CPU oracle vs the %s device path, eval-mode experts, hard route" % args.precision}
     if world == 1 and not args.no_cpu_baseline and stage0:
         cs = args.cpu_sample or 32
         v, ms, cores = cpu_stage0(cs, 2, 1, args.arch)
