@@ -354,7 +354,21 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const float rs = ep.rowscale ? ep.rowscale[(long)g * ep.rowscale_gs + m0 / ep.rows_per_scale] : 1.0f;
       float* xt = ep.x + (long)g * ep.x_gs + (long)(m0 + q * 32) * D;        // the warp's 32 rows
       const float* b2p = ep.b2 + (long)g * ep.b_gs2;
-      {
+      float* xs = sXt + (size_t)(q * 32) * D;                  // this warp's rows of the staged tile (D <= 128)
+      if constexpr (LNF && K::XT_BYTES > 0) {
+        // idle until the tile's last P W2 MMA retires: the residual rows (32 x D fp32) travel HBM -> shared memory now
+        // (cp.async, swizzled like the LayerNorm tile they will be overwritten into), so that neither pass below waits
+        // for a global load -- the ncu source view put both passes on long-scoreboard stalls of those loads
+#pragma unroll
+        for (int c = 0; c < D / 16; ++c)
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rl = it * 8 + rsub;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(xs + rl * D + (((c * 4 + c4) ^ (rl & 7)) * 4))),
+                         "l"(xt + (long)rl * D + c * 16 + c4 * 4) : "memory");
+          }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      } else {
         // idle until the tile's last P W2 MMA retires: start the trip of the residual rows (32 x D fp32) to L2 now
         const char* xl2 = reinterpret_cast<const char*>(xt);
 #pragma unroll
@@ -365,13 +379,26 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       __nv_bfloat16* ct = (!LNF && ep.cast_out) ? ep.cast_out + (long)g * ep.ln_gs + (long)(m0 + q * 32) * D : nullptr;
       float sum[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
-      float* xs = sXt + (size_t)(q * 32) * D;                  // this warp's rows of the staged tile (LNF)
+      constexpr bool XS = LNF && K::XT_BYTES > 0;              // residual rows staged in shared memory (LayerNorm variants:
+                                                               // without the LayerNorm the GELU warps are the bottleneck and the extra
+                                                               // shared-memory traffic cost them 151 -> 162 us at d = 64)
       float4 xin[4], xnx[4];
+      if constexpr (XS) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+      } else {
 #pragma unroll
-      for (int it = 0; it < 4; ++it) xin[it] = *reinterpret_cast<const float4*>(xt + (long)(it * 8 + rsub) * D + c4 * 4);
+        for (int it = 0; it < 4; ++it) xin[it] = *reinterpret_cast<const float4*>(xt + (long)(it * 8 + rsub) * D + c4 * 4);
+      }
 #pragma unroll 1
       for (int c = 0; c < D / 16; ++c) {
-        if (c + 1 < D / 16) {                                  // residual rows of the next 16 columns: in flight during this step
+        if constexpr (XS) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rl = it * 8 + rsub;
+            xin[it] = *reinterpret_cast<const float4*>(xs + rl * D + (((c * 4 + c4) ^ (rl & 7)) * 4));
+          }
+        } else if (c + 1 < D / 16) {                           // residual rows of the next 16 columns: in flight during this step
 #pragma unroll
           for (int it = 0; it < 4; ++it) xnx[it] = *reinterpret_cast<const float4*>(xt + (long)(it * 8 + rsub) * D + (c + 1) * 16 + c4 * 4);
         }
@@ -405,8 +432,10 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             *reinterpret_cast<uint2*>(ct + (long)rl * D + c * 16 + c4 * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
           }
         }
+        if constexpr (!XS) {
 #pragma unroll
-        for (int it = 0; it < 4; ++it) xin[it] = xnx[it];
+          for (int it = 0; it < 4; ++it) xin[it] = xnx[it];
+        }
         __syncwarp();
       }
       if (LNF) {
