@@ -233,14 +233,14 @@ __device__ __forceinline__ void y_tile_epilogue(const MixParams& ep, int e, long
     if (ep.dbg & 2) continue;
 #pragma unroll
     for (int pc = 0; pc < 4; ++pc)
-      *reinterpret_cast<float4*>(stg + lane * 16 + ((pc ^ (lane & 3)) * 4)) =
+      *reinterpret_cast<float4*>(stg + lane * 16 + ((pc ^ ((lane >> 1) & 3)) * 4)) =
           make_float4(__uint_as_float(v[4 * pc]), __uint_as_float(v[4 * pc + 1]), __uint_as_float(v[4 * pc + 2]), __uint_as_float(v[4 * pc + 3]));
     __syncwarp();
     const float4 b4 = __ldg(reinterpret_cast<const float4*>(bpj + c * 16 + c4 * 4));
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int rl = it * 8 + rsub;
-      const float4 a = *reinterpret_cast<const float4*>(stg + rl * 16 + ((c4 ^ (rl & 3)) * 4));
+      const float4 a = *reinterpret_cast<const float4*>(stg + rl * 16 + ((c4 ^ ((rl >> 1) & 3)) * 4));
       float4 o;
       o.x = fmaf(a.x + b4.x, rs, xin[it].x); o.y = fmaf(a.y + b4.y, rs, xin[it].y);
       o.z = fmaf(a.z + b4.z, rs, xin[it].z); o.w = fmaf(a.w + b4.w, rs, xin[it].w);

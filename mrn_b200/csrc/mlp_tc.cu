@@ -96,6 +96,9 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 16-byte-chunk swizzle key of row rl in the staged fp32 tiles (row pitch a multiple of 128 B): a quarter warp touches
+// rows {2k, 2k+1} x 4 consecutive chunks, so bit 2 separates the two rows and bits 0-1 the row pairs -> conflict free
+__device__ __forceinline__ int xs_key(int rl) { return ((rl & 1) << 2) | ((rl >> 1) & 3); }
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
@@ -364,7 +367,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int rl = it * 8 + rsub;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(xs + rl * D + (((c * 4 + c4) ^ (rl & 7)) * 4))),
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(xs + rl * D + (((c * 4 + c4) ^ xs_key(rl)) * 4))),
                          "l"(xt + (long)rl * D + c * 16 + c4 * 4) : "memory");
           }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -396,7 +399,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int rl = it * 8 + rsub;
-            xin[it] = *reinterpret_cast<const float4*>(xs + rl * D + (((c * 4 + c4) ^ (rl & 7)) * 4));
+            xin[it] = *reinterpret_cast<const float4*>(xs + rl * D + (((c * 4 + c4) ^ xs_key(rl)) * 4));
           }
         } else if (c + 1 < D / 16) {                           // residual rows of the next 16 columns: in flight during this step
 #pragma unroll
@@ -411,21 +414,21 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
 #pragma unroll
         for (int pc = 0; pc < 4; ++pc)
-          *reinterpret_cast<float4*>(stg + lane * 16 + ((pc ^ (lane & 3)) * 4)) =
+          *reinterpret_cast<float4*>(stg + lane * 16 + ((pc ^ ((lane >> 1) & 3)) * 4)) =
               make_float4(__uint_as_float(v[4 * pc]), __uint_as_float(v[4 * pc + 1]), __uint_as_float(v[4 * pc + 2]), __uint_as_float(v[4 * pc + 3]));
         __syncwarp();
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2p + c * 16 + c4 * 4));
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int rl = it * 8 + rsub;
-          const float4 a = *reinterpret_cast<const float4*>(stg + rl * 16 + ((c4 ^ (rl & 3)) * 4));
+          const float4 a = *reinterpret_cast<const float4*>(stg + rl * 16 + ((c4 ^ ((rl >> 1) & 3)) * 4));
           float4 o;
           o.x = fmaf(a.x + b4.x, rs, xin[it].x); o.y = fmaf(a.y + b4.y, rs, xin[it].y);
           o.z = fmaf(a.z + b4.z, rs, xin[it].z); o.w = fmaf(a.w + b4.w, rs, xin[it].w);
           *reinterpret_cast<float4*>(xt + (long)rl * D + c * 16 + c4 * 4) = o;
           if (LNF) {
             sum[it] += (o.x + o.y) + (o.z + o.w); sq[it] += fmaf(o.x, o.x, o.y * o.y) + fmaf(o.z, o.z, o.w * o.w);
-            *reinterpret_cast<float4*>(xs + rl * D + (((c * 4 + c4) ^ (rl & 7)) * 4)) = o;
+            *reinterpret_cast<float4*>(xs + rl * D + (((c * 4 + c4) ^ xs_key(rl)) * 4)) = o;
           }
           if (!LNF && ct) {
             __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
@@ -460,7 +463,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int rl = it * 8 + rsub;
-            const float4 xv = *reinterpret_cast<const float4*>(xs + rl * D + (((c * 4 + c4) ^ (rl & 7)) * 4));
+            const float4 xv = *reinterpret_cast<const float4*>(xs + rl * D + (((c * 4 + c4) ^ xs_key(rl)) * 4));
             __nv_bfloat162 h0 = __floats2bfloat162_rn((xv.x - mean[it]) * rstd[it] * g4.x + t4.x, (xv.y - mean[it]) * rstd[it] * g4.y + t4.y);
             __nv_bfloat162 h1 = __floats2bfloat162_rn((xv.z - mean[it]) * rstd[it] * g4.z + t4.z, (xv.w - mean[it]) * rstd[it] * g4.w + t4.w);
             *reinterpret_cast<uint2*>(lt + (long)rl * D + c * 16 + c4 * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
