@@ -108,9 +108,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 constexpr int ATT_THREADS = 64 + 256;
 
+// Persistent: CTA c walks the work items (query tile, head, unit) c, c + gridDim.x, ...  Barriers, TMEM and the tensor-map
+// prefetch are set up once per CTA; key blocks are numbered across items (jc) so that the K/V ring, S, P and O keep one
+// running phase each, and the Q tile is handed back through q_empty.  (One CTA per item spent more time in set-up and
+// tear-down than in the two MMAs of a 128-token unit: 195 us per launch at d = 256.)
 template <bool LOCAL>
 __global__ void __launch_bounds__(ATT_THREADS)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int N, int d) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int N, int d, int heads, int total) {
   constexpr int W = 64;            // SVTR token grid width for 32x256 crops (modules/svtr.py:348): shifts, not divisions
   extern __shared__ uint8_t smem_raw[];
   // 1 KiB alignment by OFFSET (not by integer round-trip of the pointer): the compiler keeps the shared address space,
@@ -119,22 +123,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict
   uint8_t* sQ = smem;                          // 8 KiB
   uint8_t* sKV = smem + TILE_BYTES;            // 2 slots x (K 8 KiB + V 8 KiB)
   uint8_t* sP = smem + TILE_BYTES + 4 * TILE_BYTES;   // 32 KiB, 1024-aligned (offset 40 KiB)
-  __shared__ __align__(8) uint64_t q_full, kv_full[2], kv_empty[2], s_full, s_empty, p_full, o_full;
+  __shared__ __align__(8) uint64_t q_full, q_empty, kv_full[2], kv_empty[2], s_full, s_empty, p_full, o_full;
   __shared__ uint32_t tmem_base_sh;
-  __shared__ float xch[2][2][QT];              // [parity][column half][row]: partner exchange of half-row maxima / sums
+  __shared__ float xch[3][2][QT];              // [block parity | 2 = end of item][column half][row]: partner exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, g = blockIdx.z;
-  const int nb_all = N / KT;
+  const int nqt = N / QT, nb_all = N / KT;
+  (void)W;
   // Local mixer: a 128-token block is two rows of the 64-wide token grid; rows further than 3 apart never interact,
   // so q-tile t only needs key blocks |t - j| <= 2 (CTA-uniform skip of MMAs, loads and softmax).
-  const int jb0 = LOCAL ? (qt - 2 > 0 ? qt - 2 : 0) : 0;
-  const int jb1 = LOCAL ? (qt + 3 < nb_all ? qt + 3 : nb_all) : nb_all;
-  const int nb = jb1 - jb0;
-  const long row0 = (long)g * N;
+  auto item = [&](int w, int& qt, int& h, int& g, int& jb0, int& nb) {
+    qt = w % nqt; h = (w / nqt) % heads; g = w / (nqt * heads);
+    jb0 = LOCAL ? (qt - 2 > 0 ? qt - 2 : 0) : 0;
+    const int jb1 = LOCAL ? (qt + 3 < nb_all ? qt + 3 : nb_all) : nb_all;
+    nb = jb1 - jb0;
+  };
 
   if (threadIdx.x == 0) {
-    mbar_init(&q_full, 1);
+    mbar_init(&q_full, 1); mbar_init(&q_empty, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     mbar_init(&s_full, 1); mbar_init(&s_empty, 256); mbar_init(&p_full, 256); mbar_init(&o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -151,14 +157,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(&q_full, TILE_BYTES);
-      tma_load_2d(sQ, &tm, &q_full, h * HD, (int)(row0 + qt * QT));
-      for (int j = 0; j < nb; ++j) {
-        const int s = j & 1;
-        mbar_wait(&kv_empty[s], ((uint32_t)(j >> 1) & 1u) ^ 1u);
-        mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
-        tma_load_2d(sKV + s * 2 * TILE_BYTES, &tm, &kv_full[s], d + h * HD, (int)(row0 + (jb0 + j) * KT));
-        tma_load_2d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &tm, &kv_full[s], 2 * d + h * HD, (int)(row0 + (jb0 + j) * KT));
+      uint32_t it = 0, jc = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        int qt, h, g, jb0, nb;
+        item(w, qt, h, g, jb0, nb);
+        const long row0 = (long)g * N;
+        mbar_wait(&q_empty, (it & 1u) ^ 1u);                      // every S MMA of the previous item has read its Q tile
+        mbar_expect_tx(&q_full, TILE_BYTES);
+        tma_load_2d(sQ, &tm, &q_full, h * HD, (int)(row0 + qt * QT));
+        for (int j = 0; j < nb; ++j, ++jc) {
+          const int s = jc & 1;
+          mbar_wait(&kv_empty[s], ((jc >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+          tma_load_2d(sKV + s * 2 * TILE_BYTES, &tm, &kv_full[s], d + h * HD, (int)(row0 + (jb0 + j) * KT));
+          tma_load_2d(sKV + s * 2 * TILE_BYTES + TILE_BYTES, &tm, &kv_full[s], 2 * d + h * HD, (int)(row0 + (jb0 + j) * KT));
+        }
       }
     }
   } else if (warp == 1) {
@@ -168,51 +181,84 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict
       constexpr uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
       const uint64_t qdesc = make_desc(smem_u32(sQ), 512, 4);
       const uint64_t pdesc = make_desc(smem_u32(sP), 1024, 2);
-      auto issue_s = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(&kv_full[s], (uint32_t)(j >> 1) & 1u);
+      // blocks are numbered jc across items: S(jc + 1) goes out as soon as the softmax warps have pulled S(jc) out of TMEM
+      // (for the first block of an item also: its Q tile has landed), then P(jc) V(jc)
+      auto issue_s = [&](uint32_t jc) {
+        const int s = jc & 1;
+        mbar_wait(&kv_full[s], (jc >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t kdesc = make_desc(smem_u32(sKV + s * 2 * TILE_BYTES), 512, 4);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k);
         umma_commit(&s_full);
       };
-      mbar_wait(&q_full, 0);
-      issue_s(0);
-      for (int j = 0; j < nb; ++j) {
-        if (j + 1 < nb) {
-          mbar_wait(&s_empty, (uint32_t)j & 1u);          // softmax warps have pulled S_j out of TMEM
-          issue_s(j + 1);
-        }
-        mbar_wait(&p_full, (uint32_t)j & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int s = j & 1;
-        const uint64_t vdesc = make_desc(smem_u32(sKV + s * 2 * TILE_BYTES + TILE_BYTES), 512, 4);
+      uint32_t it = 0, jc = 0;
+      int w = blockIdx.x;
+      int qt, h, g, jb0, nb = 0;
+      if (w < total) {
+        item(w, qt, h, g, jb0, nb);
+        mbar_wait(&q_full, 0);
+        issue_s(0);
+        if (nb == 1) umma_commit(&q_empty);
+      }
+      while (w < total) {
+        for (int j = 0; j < nb; ++j, ++jc) {
+          // next S of the same item goes out before P V of this block (the softmax warps then find it ready)
+          if (j + 1 < nb) {
+            mbar_wait(&s_empty, jc & 1u);
+            issue_s(jc + 1);
+            if (j + 2 == nb) umma_commit(&q_empty);               // last S of this item issued: Q is free once it retires
+          }
+          mbar_wait(&p_full, jc & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const int s = jc & 1;
+          const uint64_t vdesc = make_desc(smem_u32(sKV + s * 2 * TILE_BYTES + TILE_BYTES), 512, 4);
 #pragma unroll
-        for (int k = 0; k < KT / 16; ++k) {
-          // P: two 64-key halves of 16 KiB, +32 B per 16 keys inside the 128 B row; V: +16 key rows of 64 B
-          const uint64_t pa = pdesc + (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4);
-          const uint64_t vb = vdesc + (uint64_t)((k * 16 * 64) >> 4);
-          umma_bf16(tmem_base + O_COL, pa, vb, idesc_o, k);
+          for (int k = 0; k < KT / 16; ++k) {
+            // P: two 64-key halves of 16 KiB, +32 B per 16 keys inside the 128 B row; V: +16 key rows of 64 B
+            const uint64_t pa = pdesc + (uint64_t)(((k >> 2) * 16384 + (k & 3) * 32) >> 4);
+            const uint64_t vb = vdesc + (uint64_t)((k * 16 * 64) >> 4);
+            umma_bf16(tmem_base + O_COL, pa, vb, idesc_o, k);
+          }
+          umma_commit(&kv_empty[s]);
+          umma_commit(&o_full);
+          if (j + 1 == nb) {
+            // last block of the item: the first S of the NEXT item follows its P V (the softmax warps still have the
+            // item's normalisation and store ahead of them; p_full(jc) implies s_empty(jc))
+            const int wn = w + gridDim.x;
+            if (wn < total) {
+              int qt2, h2, g2, jb2, nb2;
+              item(wn, qt2, h2, g2, jb2, nb2);
+              mbar_wait(&q_full, (it + 1) & 1u);
+              mbar_wait(&s_empty, jc & 1u);
+              issue_s(jc + 1);
+              if (nb2 == 1) umma_commit(&q_empty);
+            }
+          }
         }
-        umma_commit(&kv_empty[s]);
-        umma_commit(&o_full);
+        w += gridDim.x; ++it;
+        if (w < total) item(w, qt, h, g, jb0, nb);
       }
     }
   } else {
     const int q = warp & 3;
     const int ch = (warp - 2) >> 2;               // 64-key half of every block / 16-dim half of O owned by this warp
     const int r = q * 32 + lane;                  // query row inside the tile == TMEM lane
-    const int n = qt * QT + r;                    // token index of this query
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int qh = n >> 6, qw = n & 63;
     const float sl2 = 0.17677669529663688110f * 1.4426950408889634f;     // 32^-0.5 * log2(e)
+    uint32_t jc = 0;                              // key blocks are numbered across items (barrier phases)
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    int qt, h, g, jb0, nb;
+    item(w, qt, h, g, jb0, nb);
+    const long row0 = (long)g * N;
+    const int n = qt * QT + r;                    // token index of this query
+    const int qh = n >> 6, qw = n & 63;
     float m = -INFINITY, l = 0.f, corr_prev = 0.f;
     float acc[HD / 2];
 #pragma unroll
     for (int j = 0; j < HD / 2; ++j) acc[j] = 0.f;
-    for (int j = 0; j < nb; ++j) {
-      mbar_wait(&s_full, (uint32_t)j & 1u);
+    for (int j = 0; j < nb; ++j, ++jc) {
+      mbar_wait(&s_full, jc & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // Local window as a 32-bit validity mask per 32-key chunk (a chunk lies inside one row of the token grid):
       // bit i set <=> |kh - qh| <= 3 and |kw0 + i - qw| <= 5.
@@ -244,9 +290,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict
 #pragma unroll
         for (int i = 0; i < 32; i += 2) bmax = max3(bmax, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
       }
-      xch[j & 1][ch][r] = bmax;
+      xch[jc & 1][ch][r] = bmax;
       pair_sync(q);                                              // the two warps of this lane quarter
-      bmax = fmaxf(bmax, xch[j & 1][ch ^ 1][r]);
+      bmax = fmaxf(bmax, xch[jc & 1][ch ^ 1][r]);
       const float mnew = fmaxf(m, bmax * sl2);
       const float mref = (mnew == -INFINITY) ? 0.f : mnew;       // nothing visible so far
       const float corr = ex2_approx(m - mref);                   // m = -inf -> 0
@@ -254,7 +300,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict
       if (j > 0) {
         // deferred accumulation of the previous block: O_{j-1} = P_{j-1} V_{j-1} had all of pass 1 to complete, and
         // its completion also frees the P tile that pass 2 below overwrites
-        mbar_wait(&o_full, (uint32_t)(j - 1) & 1u);
+        mbar_wait(&o_full, (jc - 1u) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t o[16];
         tmem_ld16(lane_addr + O_COL + (uint32_t)(ch * 16), o);
@@ -301,7 +347,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict
       corr_prev = corr;
     }
     {
-      mbar_wait(&o_full, (uint32_t)(nb - 1) & 1u);
+      mbar_wait(&o_full, (jc - 1u) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t o[16];
       tmem_ld16(lane_addr + O_COL + (uint32_t)(ch * 16), o);
@@ -309,9 +355,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict
       for (int i = 0; i < HD / 2; ++i) acc[i] = fmaf(acc[i], corr_prev, __uint_as_float(o[i]));
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
-    xch[nb & 1][ch][r] = l;
+    xch[2][ch][r] = l;
     pair_sync(q);
-    const float inv = 1.0f / (l + xch[nb & 1][ch ^ 1][r]);
+    const float inv = 1.0f / (l + xch[2][ch ^ 1][r]);
     __nv_bfloat16* op = out + (row0 + n) * d + h * HD + ch * (HD / 2);
 #pragma unroll
     for (int i = 0; i < HD / 2; i += 8) {
@@ -322,6 +368,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict
         pk[u] = *reinterpret_cast<uint32_t*>(&hb);
       }
       *reinterpret_cast<uint4*>(op + i) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+      pair_sync(q);                                                // xch[2] is rewritten by the next item
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -367,9 +415,13 @@ int mrnb_attention_tc(const void* qkv, void* out, int groups, int N, int d, int 
     cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
-  dim3 grid(N / QT, heads, groups);
-  if (local) attn_tc_kernel<true><<<grid, ATT_THREADS, smem, st>>>(tm, (__nv_bfloat16*)out, N, d);
-  else attn_tc_kernel<false><<<grid, ATT_THREADS, smem, st>>>(tm, (__nv_bfloat16*)out, N, d);
+  const long total = (long)(N / QT) * heads * groups;
+  static int n_sm = 0;
+  if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+  const long cap = 2L * n_sm;                    // two persistent CTAs per SM (2 x 256 TMEM columns, 2 x 73 KiB shared memory)
+  const int grid = (int)(total < cap ? total : cap);
+  if (local) attn_tc_kernel<true><<<grid, ATT_THREADS, smem, st>>>(tm, (__nv_bfloat16*)out, N, d, heads, (int)total);
+  else attn_tc_kernel<false><<<grid, ATT_THREADS, smem, st>>>(tm, (__nv_bfloat16*)out, N, d, heads, (int)total);
   MRNB_CHECK_LAUNCH("attn_tc_kernel");
   return MRNB_OK;
 }
