@@ -516,12 +516,15 @@ __global__ void feature_scatter_kernel(const float* __restrict__ src, float* __r
 }
 
 // First branch of a Block in tensor-core mode: the fused mixer kernel (mixer_tc.cu) or the unfused qkv GEMM / attention /
-// proj GEMM sequence.  MRNB_MIXER = 0: never fused, 1: fused for the 64- and 128-wide stages (default: at d = 256 a sample
-// is one query tile, only one softmax stream has work and the unfused sequence is a few percent faster), 2: always fused.
+// proj GEMM sequence.  MRNB_MIXER = 0: never fused, 1 (default): fused for the 64- and 128-wide stages, 2: always fused,
+// 3: fused for the 64-wide stage only.  Per launch at 1536 units (tools/mixer_bench.py, persistent attention kernel):
+// d = 64 fused 0.467 ms vs unfused 0.565; d = 128 fused 0.465 vs unfused 0.41 in isolation -- but inside the step the
+// unfused d = 128 blocks (qkv 117 + attention 229 + proj/LN 117 us) come out at the same 0.46 ms with twice the DRAM
+// traffic (step 12.05 vs 11.99 ms), so they stay fused; d = 256 fused 0.448 vs unfused 0.341: unfused.
 bool use_fused_mixer(int d) {
   static int v = -1;
   if (v < 0) { const char* e = getenv("MRNB_MIXER"); v = e ? atoi(e) : 1; }
-  return v >= 2 || (v == 1 && d <= 128);
+  return v == 2 || (v == 1 && d <= 128) || (v == 3 && d <= 64);
 }
 
 template <typename AT>
