@@ -14,6 +14,7 @@
 // 64 rows per sample (row 63 is scratch) so that every GEMM tile holds whole samples; the LSTM walks rows 0..62.
 // The LSTM recurrence is one grouped GEMM (h W_hh^T for all experts x directions) + one cell kernel per step.
 #include "common.cuh"
+#include <stdlib.h>
 #include "expert_util.cuh"
 #include "../../include/mrn_b200.h"
 
@@ -244,6 +245,13 @@ bn_relu_pool_kernel(const AT* __restrict__ x, const float* __restrict__ ss /*[I,
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
+// MRNB_LSTM_SEQ = 0 keeps one grouped GEMM launch per time step
+inline bool lstm_seq_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MRNB_LSTM_SEQ"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+
 template <typename AT>
 __global__ void lstm_cell_kernel(const float* __restrict__ gates, const AT* __restrict__ pre, float* __restrict__ cst,
                                  AT* __restrict__ hst, AT* __restrict__ rec, int I, int B, int s, unsigned total) {
@@ -462,7 +470,17 @@ int crnn_forward_t(const MrnbCrnnPack& P, const float* image, int B, int bn_batc
     const long cells = (long)2 * I * B * LH;
     // tensor-core mode with whole 128-sample tiles: the cell runs inside the epilogue of the recurrent GEMM
     const bool fused_cell = !F32 && (B % 128) == 0;
-    for (int s = 0; s < CT; ++s) {
+    bool seq_done = false;                 // steps 1 .. CT-1 already ran in the persistent cluster kernel
+    for (int s = 0; s < CT && !seq_done; ++s) {
+      if (s == 1 && fused_cell && lstm_seq_enabled()) {
+        // every remaining step of the layer in ONE launch: W_hh resident in shared memory, h exchanged inside 4-CTA clusters
+        // (gemm_tc.cu: lstm_seq_kernel).  h ping-pongs between hst (h_0 from the cell kernel above) and the unused fp32
+        // `gates` buffer.
+        const int rc = mrnb_tc_lstm_seq(P.h[pl + MRNB_CL_WHH], pre, (long)CTP * 8 * LH, (long)B * CTP * 8 * LH, rec,
+                                        (long)CTP * 2 * LH, (long)B * CTP * 2 * LH, cst, hst, gates, 2 * I, B, CT, 1, st);
+        if (rc == MRNB_OK) { seq_done = true; break; }
+        if (rc != MRNB_ERR_UNSUPPORTED) return rc;
+      }
       if (s > 0 && fused_cell) {
         MrnbTcGemm g{};
         g.A = hst; g.lda = LH; g.a_gstride = (long)B * LH;

@@ -522,6 +522,175 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---- host side ---------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent LSTM recurrence (modules/sequence_modeling.py:12-22, the nn.LSTM inside BidirectionalLSTM): every time step
+// s_first .. CT-1 of all (expert, direction) chains of one layer in ONE launch, instead of one grouped GEMM launch per
+// step (63 x ~20 us per layer, each bounded by launch + TMA + MMA + epilogue latency, not by work).
+//
+// A thread-block CLUSTER of four CTAs owns one (chain g, 128-sample tile): CTA nq of the cluster keeps the 256 gate
+// columns (64 hidden units x i,f,g,o) nq of W_hh -- [256 x 256] bf16 = 128 KiB -- resident in shared memory for the whole
+// sequence.  Per step: the eight epilogue warps copy h_{s-1} of the tile (128 x 256 bf16, written by all four CTAs in the
+// previous step, read with ld.global.cg from L2) into a 128B-swizzled K-major operand tile; one thread issues the
+// 16 tcgen05 MMAs (M128 N256 K256, accumulator in 256 TMEM columns); the epilogue applies the cell exactly as the per-step
+// kernel (MODE 1) does and writes c (fp32), h_s (bf16, ping-pong buffer) and the [fwd | bwd] output row; a hardware
+// cluster barrier (release / acquire) publishes h_s to the other three CTAs.  Nothing else crosses CTAs.
+struct LstmSeqArgs {
+  const __nv_bfloat16* pre; long pre_row, pre_e;   // [expert][sample * CTP + t][2 * 4H]
+  __nv_bfloat16* rec; long rec_row, rec_e;         // [expert][sample * CTP + t][2H]
+  float* cst;                                      // [chain][B][H]
+  __nv_bfloat16* h0; __nv_bfloat16* h1;            // hidden state ping-pong [chain][B][H]: step s reads buffer (s-1) & 1, writes s & 1
+  int B, CT, s_first;
+};
+constexpr int LSEQ_THREADS = 320;                  // warp 0: W_hh load, warp 1: TMEM + MMA issuer, warps 2..9: operand copy + cell
+constexpr int LSEQ_W_BYTES = 4 * 256 * BK * 2, LSEQ_A_BYTES = 4 * BM * BK * 2;
+constexpr int LSEQ_SMEM = 1024 + LSEQ_W_BYTES + LSEQ_A_BYTES + EPI_WARPS * 4096;
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint4 ld_cg_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(LSEQ_THREADS, 1)
+lstm_seq_kernel(const __grid_constant__ CUtensorMap tmW, const LstmSeqArgs p) {
+  constexpr int LH = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sW = smem;                                        // 4 k-blocks x [256 gate rows x 64 k]
+  uint8_t* sA = smem + LSEQ_W_BYTES;                         // 4 k-blocks x [128 samples x 64 k]
+  float* staging = reinterpret_cast<float*>(smem + LSEQ_W_BYTES + LSEQ_A_BYTES);
+  __shared__ __align__(8) uint64_t w_full, a_ready, acc_full;
+  __shared__ uint32_t tmem_base_sh;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nq = blockIdx.x & 3;                             // rank in the cluster == quarter of the gate columns
+  const int tile = blockIdx.x >> 2, m_tiles = p.B / BM;
+  const int m0 = (tile % m_tiles) * BM, g = tile / m_tiles;
+  const int e = g >> 1, dir = g & 1;
+  if (threadIdx.x == 0) {
+    mbar_init(&w_full, 1); mbar_init(&a_ready, EPI_WARPS * 32); mbar_init(&acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_sh;
+  if (warp == 0 && lane == 0) {
+    mbar_expect_tx(&w_full, LSEQ_W_BYTES);
+    for (int kb = 0; kb < 4; ++kb) tma_load_3d(sW + kb * (256 * BK * 2), &tmW, &w_full, kb * BK, nq * 256, g);
+  }
+  uint32_t it = 0;
+  for (int s = p.s_first; s < p.CT; ++s, ++it) {
+    const __nv_bfloat16* hin = ((s - 1) & 1) ? p.h1 : p.h0;
+    __nv_bfloat16* hout = (s & 1) ? p.h1 : p.h0;
+    if (warp >= 2) {
+      // h_{s-1} of the tile: 128 rows x 512 B, contiguous -> 16-byte chunk c = row * 32 + kc
+      const char* src = reinterpret_cast<const char*>(hin + ((long)g * p.B + m0) * LH);
+      constexpr int NCH = BM * 32 / (EPI_WARPS * 32);          // 16 chunks per thread: all loads in flight before the first store
+      uint4 v[NCH];
+#pragma unroll
+      for (int u = 0; u < NCH; ++u) v[u] = ld_cg_v4(src + (size_t)((threadIdx.x - 64) + u * EPI_WARPS * 32) * 16);
+#pragma unroll
+      for (int u = 0; u < NCH; ++u) {
+        const int c = (threadIdx.x - 64) + u * EPI_WARPS * 32;
+        const int row = c >> 5, kc = c & 31, kb = kc >> 3, cc = kc & 7;
+        *reinterpret_cast<uint4*>(sA + kb * A_STAGE_BYTES + row * 128 + ((cc ^ (row & 7)) << 4)) = v[u];
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&a_ready);
+    }
+    if (warp == 1 && lane == 0) {
+      if (it == 0) mbar_wait(&w_full, 0);
+      mbar_wait(&a_ready, it & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      constexpr uint32_t idesc = make_idesc(256);
+      for (int kb = 0; kb < 4; ++kb) {
+        const uint64_t ad = make_smem_desc(smem_u32(sA + kb * A_STAGE_BYTES)), bd = make_smem_desc(smem_u32(sW + kb * (256 * BK * 2)));
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(tmem_base, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+      }
+      umma_commit(&acc_full);
+    }
+    if (warp >= 2) {
+      const int ew = warp - 2, q = warp & 3, ch = ew >> 2;
+      float* stg = staging + (size_t)ew * 1024;
+      const int p8 = lane & 7, rsel = lane >> 3;
+      const int t = dir ? p.CT - 1 - s : s;                    // frame of this step for the chain's direction
+      const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 128);
+      mbar_wait(&acc_full, it & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int ps = 0; ps < 4; ++ps) {
+        const int col = nq * 256 + ch * 128 + ps * 32 + p8 * 4;  // interleaved gate column of the chain: unit j = col / 4
+        const int j = col >> 2;
+        {
+          uint32_t r[32];
+          tmem_ld32(tcol + (uint32_t)(ps * 32), r);
+#pragma unroll
+          for (int pc = 0; pc < 8; ++pc)
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((pc ^ (lane & 7)) * 4)) =
+                make_float4(__uint_as_float(r[4 * pc]), __uint_as_float(r[4 * pc + 1]), __uint_as_float(r[4 * pc + 2]), __uint_as_float(r[4 * pc + 3]));
+        }
+        __syncwarp();
+        // input pre-activations and cell states of the pass' eight rows first (independent loads, one latency), then the
+        // cells.  (Issuing them before the TMEM load, or for all four passes before the accumulator wait, spills under the
+        // 168-register allocation of this cluster kernel and measured slower.)
+        const __nv_bfloat16* prep = p.pre + (long)e * p.pre_e + (long)t * (8 * LH) + dir * 4 * LH + col;
+        uint2 pvv[8];
+        float cprev[8];
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          const int b = m0 + q * 32 + itr * 4 + rsel;
+          pvv[itr] = *reinterpret_cast<const uint2*>(prep + (long)b * p.pre_row);
+          cprev[itr] = p.cst[((long)g * p.B + b) * LH + j];
+        }
+        __nv_bfloat16* recp = p.rec + (long)e * p.rec_e + (long)t * (2 * LH) + dir * LH + j;
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          const int rl = itr * 4 + rsel;
+          const int b = m0 + q * 32 + rl;
+          float4 x = *reinterpret_cast<const float4*>(stg + rl * 32 + ((p8 ^ (rl & 7)) * 4));
+          const uint2 pv = pvv[itr];
+          const __nv_bfloat162 p01 = *reinterpret_cast<const __nv_bfloat162*>(&pv.x), p23 = *reinterpret_cast<const __nv_bfloat162*>(&pv.y);
+          x.x += __low2float(p01); x.y += __high2float(p01); x.z += __low2float(p23); x.w += __high2float(p23);
+          const long ci = ((long)g * p.B + b) * LH + j;
+          const float c = fmaf(sigmoid_fast(x.y), cprev[itr], sigmoid_fast(x.x) * tanh_fast(x.z));
+          const float h = sigmoid_fast(x.w) * tanh_fast(c);
+          p.cst[ci] = c;
+          const __nv_bfloat16 hb = __float2bfloat16_rn(h);
+          hout[ci] = hb;
+          recp[(long)b * p.rec_row] = hb;
+        }
+        __syncwarp();
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (s + 1 < p.CT) {
+        // next step's input pre-activations (128 rows x 512 B of this CTA's gate columns): HBM -> L2 while the barrier settles
+        const int tn = dir ? p.CT - 2 - s : s + 1;
+        const char* pn = reinterpret_cast<const char*>(p.pre + (long)e * p.pre_e + (long)tn * (8 * LH) + dir * 4 * LH + nq * 256);
+        const int t2 = threadIdx.x - 64;                       // 256 threads: row = t2 / 2, 256-byte half = t2 & 1 (two 128-byte lines)
+        const char* a = pn + (long)(m0 + (t2 >> 1)) * p.pre_row * 2 + (t2 & 1) * 256;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 128));
+      }
+    }
+    // h_s of all four gate-column quarters becomes visible to the cluster; the accumulator and the operand tile are free
+    cluster_sync_all();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -700,4 +869,31 @@ extern "C" int mrnb_linear_bf16(const void* A, const void* W, const float* bias,
   g.A = A; g.lda = K; g.W = W; g.ldw = K; g.bias = bias; g.out = out; g.ldo = N; g.out_f32 = out_is_f32;
   g.res = residual; g.M = M; g.N = N; g.K = K; g.groups = 1; g.gelu = act_gelu; g.rows_per_scale = 1;
   return mrnb_tc_gemm(g, stream);
+}
+
+// Persistent LSTM recurrence: steps s_first .. CT-1 of `groups` = 2 x experts chains in one cluster launch.
+// Whh: bf16 [groups][4H = 1024 (gate-interleaved)][H = 256].  Returns MRNB_ERR_UNSUPPORTED when the shape does not fit
+// (the caller falls back to one grouped GEMM per step).
+int mrnb_tc_lstm_seq(const void* Whh, const void* pre, long pre_row, long pre_e, void* rec, long rec_row, long rec_e, float* cst,
+                     void* h0, void* h1, int groups, int B, int CT, int s_first, cudaStream_t st) {
+  if (B % BM != 0 || groups <= 0 || s_first < 1 || s_first >= CT) return MRNB_ERR_UNSUPPORTED;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaFuncSetAttribute(lstm_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LSEQ_SMEM) != cudaSuccess) { cudaGetLastError(); num_sms = -1; }
+  }
+  const int grid = groups * (B / BM) * 4;
+  if (num_sms <= 0 || grid > num_sms) return MRNB_ERR_UNSUPPORTED;       // every cluster must be resident (one CTA per SM)
+  CUtensorMap tmW;
+  MRNB_TRY(make_map(&tmW, Whh, 256, 1024, groups, 256, 1024L * 256, 256));
+  LstmSeqArgs a{};
+  a.pre = (const __nv_bfloat16*)pre; a.pre_row = pre_row; a.pre_e = pre_e;
+  a.rec = (__nv_bfloat16*)rec; a.rec_row = rec_row; a.rec_e = rec_e;
+  a.cst = cst; a.h0 = (__nv_bfloat16*)h0; a.h1 = (__nv_bfloat16*)h1; a.B = B; a.CT = CT; a.s_first = s_first;
+  MrnbProfScope prof(MRNB_PROF_TCGEMM, st, 2.0 * B * 1024.0 * 256.0 * groups * (CT - s_first), 0.0);
+  lstm_seq_kernel<<<grid, LSEQ_THREADS, LSEQ_SMEM, st>>>(tmW, a);
+  MRNB_CHECK_LAUNCH("lstm_seq_kernel");
+  return MRNB_OK;
 }

@@ -66,3 +66,7 @@ struct MrnbTcGemm {
 int mrnb_tc_gemm(const MrnbTcGemm& g, cudaStream_t st);
 // out[e][m, :C_e] = A[e][m, :] . Wall[woff[e] + n, :]^T + bias[e]   for every expert e (fp32 out); H.tile_prefix / n_tiles are filled here
 int mrnb_tc_heads(const void* A, long lda, long a_gstride, const void* Wall, long w_rows, int M, int K, MrnbTcHeads H, cudaStream_t st);
+// Persistent LSTM recurrence (all steps s_first .. CT-1 of one BidirectionalLSTM layer, every chain) in one cluster launch;
+// MRNB_ERR_UNSUPPORTED = shape does not fit, fall back to one grouped GEMM per step.
+int mrnb_tc_lstm_seq(const void* Whh, const void* pre, long pre_row, long pre_e, void* rec, long rec_row, long rec_e, float* cst,
+                     void* h0, void* h1, int groups, int B, int CT, int s_first, cudaStream_t st);
