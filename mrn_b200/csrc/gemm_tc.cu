@@ -541,7 +541,8 @@ struct LstmSeqArgs {
   __nv_bfloat16* h0; __nv_bfloat16* h1;            // hidden state ping-pong [chain][B][H]: step s reads buffer (s-1) & 1, writes s & 1
   int B, CT, s_first;
 };
-constexpr int LSEQ_THREADS = 320;                  // warp 0: W_hh load, warp 1: TMEM + MMA issuer, warps 2..9: operand copy + cell
+constexpr int LSEQ_THREADS = 256;                  // eight warps: operand copy + cell; thread 0 also loads W_hh and issues the MMAs
+                                                   // (ten warps would put three on one SM sub-partition: 168 registers per thread)
 constexpr int LSEQ_W_BYTES = 4 * 256 * BK * 2, LSEQ_A_BYTES = 4 * BM * BK * 2;
 constexpr int LSEQ_SMEM = 1024 + LSEQ_W_BYTES + LSEQ_A_BYTES + EPI_WARPS * 4096;
 
@@ -562,7 +563,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmW, const LstmSeqArgs p) {
   uint8_t* sW = smem;                                        // 4 k-blocks x [256 gate rows x 64 k]
   uint8_t* sA = smem + LSEQ_W_BYTES;                         // 4 k-blocks x [128 samples x 64 k]
   float* staging = reinterpret_cast<float*>(smem + LSEQ_W_BYTES + LSEQ_A_BYTES);
-  __shared__ __align__(8) uint64_t w_full, a_ready, acc_full;
+  __shared__ __align__(8) uint64_t w_full, acc_full;
   __shared__ uint32_t tmem_base_sh;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = blockIdx.x & 3;                             // rank in the cluster == quarter of the gate columns
@@ -570,11 +571,11 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmW, const LstmSeqArgs p) {
   const int m0 = (tile % m_tiles) * BM, g = tile / m_tiles;
   const int e = g >> 1, dir = g & 1;
   if (threadIdx.x == 0) {
-    mbar_init(&w_full, 1); mbar_init(&a_ready, EPI_WARPS * 32); mbar_init(&acc_full, 1);
+    mbar_init(&w_full, 1); mbar_init(&acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
   }
-  if (warp == 1) {
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -582,7 +583,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmW, const LstmSeqArgs p) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_sh;
-  if (warp == 0 && lane == 0) {
+  if (threadIdx.x == 0) {
     mbar_expect_tx(&w_full, LSEQ_W_BYTES);
     for (int kb = 0; kb < 4; ++kb) tma_load_3d(sW + kb * (256 * BK * 2), &tmW, &w_full, kb * BK, nq * 256, g);
   }
@@ -590,25 +591,24 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmW, const LstmSeqArgs p) {
   for (int s = p.s_first; s < p.CT; ++s, ++it) {
     const __nv_bfloat16* hin = ((s - 1) & 1) ? p.h1 : p.h0;
     __nv_bfloat16* hout = (s & 1) ? p.h1 : p.h0;
-    if (warp >= 2) {
+    {
       // h_{s-1} of the tile: 128 rows x 512 B, contiguous -> 16-byte chunk c = row * 32 + kc
       const char* src = reinterpret_cast<const char*>(hin + ((long)g * p.B + m0) * LH);
       constexpr int NCH = BM * 32 / (EPI_WARPS * 32);          // 16 chunks per thread: all loads in flight before the first store
       uint4 v[NCH];
 #pragma unroll
-      for (int u = 0; u < NCH; ++u) v[u] = ld_cg_v4(src + (size_t)((threadIdx.x - 64) + u * EPI_WARPS * 32) * 16);
+      for (int u = 0; u < NCH; ++u) v[u] = ld_cg_v4(src + (size_t)(threadIdx.x + u * EPI_WARPS * 32) * 16);
 #pragma unroll
       for (int u = 0; u < NCH; ++u) {
-        const int c = (threadIdx.x - 64) + u * EPI_WARPS * 32;
+        const int c = threadIdx.x + u * EPI_WARPS * 32;
         const int row = c >> 5, kc = c & 31, kb = kc >> 3, cc = kc & 7;
         *reinterpret_cast<uint4*>(sA + kb * A_STAGE_BYTES + row * 128 + ((cc ^ (row & 7)) << 4)) = v[u];
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(&a_ready);
     }
-    if (warp == 1 && lane == 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
       if (it == 0) mbar_wait(&w_full, 0);
-      mbar_wait(&a_ready, it & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       constexpr uint32_t idesc = make_idesc(256);
       for (int kb = 0; kb < 4; ++kb) {
@@ -618,18 +618,37 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmW, const LstmSeqArgs p) {
       }
       umma_commit(&acc_full);
     }
-    if (warp >= 2) {
-      const int ew = warp - 2, q = warp & 3, ch = ew >> 2;
+    __syncwarp();
+    {
+      const int ew = warp, q = warp & 3, ch = ew >> 2;
       float* stg = staging + (size_t)ew * 1024;
       const int p8 = lane & 7, rsel = lane >> 3;
       const int t = dir ? p.CT - 1 - s : s;                    // frame of this step for the chain's direction
       const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 128);
+      // input pre-activations and cell states of a pass' eight rows are loaded one pass ahead (pass 0: before the
+      // accumulator wait, i.e. during the MMAs), so that no pass waits for a global load
+      const __nv_bfloat16* prep0 = p.pre + (long)e * p.pre_e + (long)t * (8 * LH) + dir * 4 * LH + nq * 256 + ch * 128 + p8 * 4;
+      const long crow0 = ((long)g * p.B + m0 + q * 32 + rsel) * LH + ((nq * 256 + ch * 128 + p8 * 4) >> 2);
+      uint2 pvv[8], pvn[8];
+      float cprev[8];
+#pragma unroll
+      for (int itr = 0; itr < 8; ++itr) {
+        pvv[itr] = *reinterpret_cast<const uint2*>(prep0 + (long)(m0 + q * 32 + itr * 4 + rsel) * p.pre_row);
+      }
       mbar_wait(&acc_full, it & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
       for (int ps = 0; ps < 4; ++ps) {
         const int col = nq * 256 + ch * 128 + ps * 32 + p8 * 4;  // interleaved gate column of the chain: unit j = col / 4
         const int j = col >> 2;
+        if (ps + 1 < 4) {
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr) {
+            pvn[itr] = *reinterpret_cast<const uint2*>(prep0 + (ps + 1) * 32 + (long)(m0 + q * 32 + itr * 4 + rsel) * p.pre_row);
+          }
+        }
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) cprev[itr] = p.cst[crow0 + ps * 8 + (long)itr * 4 * LH];
         {
           uint32_t r[32];
           tmem_ld32(tcol + (uint32_t)(ps * 32), r);
@@ -639,18 +658,6 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmW, const LstmSeqArgs p) {
                 make_float4(__uint_as_float(r[4 * pc]), __uint_as_float(r[4 * pc + 1]), __uint_as_float(r[4 * pc + 2]), __uint_as_float(r[4 * pc + 3]));
         }
         __syncwarp();
-        // input pre-activations and cell states of the pass' eight rows first (independent loads, one latency), then the
-        // cells.  (Issuing them before the TMEM load, or for all four passes before the accumulator wait, spills under the
-        // 168-register allocation of this cluster kernel and measured slower.)
-        const __nv_bfloat16* prep = p.pre + (long)e * p.pre_e + (long)t * (8 * LH) + dir * 4 * LH + col;
-        uint2 pvv[8];
-        float cprev[8];
-#pragma unroll
-        for (int itr = 0; itr < 8; ++itr) {
-          const int b = m0 + q * 32 + itr * 4 + rsel;
-          pvv[itr] = *reinterpret_cast<const uint2*>(prep + (long)b * p.pre_row);
-          cprev[itr] = p.cst[((long)g * p.B + b) * LH + j];
-        }
         __nv_bfloat16* recp = p.rec + (long)e * p.rec_e + (long)t * (2 * LH) + dir * LH + j;
 #pragma unroll
         for (int itr = 0; itr < 8; ++itr) {
@@ -668,6 +675,8 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmW, const LstmSeqArgs p) {
           hout[ci] = hb;
           recp[(long)b * p.rec_row] = hb;
         }
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) pvv[itr] = pvn[itr];
         __syncwarp();
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -675,7 +684,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmW, const LstmSeqArgs p) {
         // next step's input pre-activations (128 rows x 512 B of this CTA's gate columns): HBM -> L2 while the barrier settles
         const int tn = dir ? p.CT - 2 - s : s + 1;
         const char* pn = reinterpret_cast<const char*>(p.pre + (long)e * p.pre_e + (long)tn * (8 * LH) + dir * 4 * LH + nq * 256);
-        const int t2 = threadIdx.x - 64;                       // 256 threads: row = t2 / 2, 256-byte half = t2 & 1 (two 128-byte lines)
+        const int t2 = threadIdx.x;                            // 256 threads: row = t2 / 2, 256-byte half = t2 & 1 (two 128-byte lines)
         const char* a = pn + (long)(m0 + (t2 >> 1)) * p.pre_row * 2 + (t2 & 1) * 256;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 128));
@@ -686,7 +695,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmW, const LstmSeqArgs p) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
   }
 }
