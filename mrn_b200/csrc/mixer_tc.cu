@@ -29,7 +29,7 @@
 namespace {
 
 #ifndef MRNB_MIXER_OVL
-#define MRNB_MIXER_OVL 0
+#define MRNB_MIXER_OVL 1
 #endif
 constexpr int HD = 32;
 // Four warpgroups with re-balanced register budgets (setmaxnreg): WG0 = control (warp 0 TMA producer, warp 1 MMA issuer of
@@ -280,6 +280,94 @@ __device__ __forceinline__ void y_tile_epilogue(const MixParams& ep, int e, long
             pack_bf16((xv.z - mean[it]) * rstd[it] * g4.z + t4.z, (xv.w - mean[it]) * rstd[it] * g4.w + t4.w));
       }
     }
+  }
+}
+
+// The Y epilogue of the OVL variant, run by the softmax warps of the stream that owns the tile (168 registers): each
+// warp's 32 rows in passes of RG x 8 rows.  The updated residual values of a pass stay in registers (RG x 32 per thread)
+// between the x update and LayerNorm 2 -- no second pass over rows just stored -- and ALL residual loads of a pass are
+// in flight at once (the first pass' before `wait_bar`, the barrier that says Y is complete, is waited for).  The
+// accumulator columns are read once per pass (tcgen05.ld delivers all 32 lanes; the other rows are dropped); `stg` is
+// 4 KiB: two alternating 32 x 16 fp32 staging tiles, one __syncwarp per step (DBUF = false: one 2 KiB tile, two).
+// `release` (optional) is arrived on once the last pass has left TMEM.  The 64-wide stage runs it from the Y-epilogue
+// warpgroup (RG = 2: 32 registers of rows), where the second pass of `y_tile_epilogue` cost 43 of the 464 us a launch takes.
+template <int D, bool LNF, int RG, bool DBUF = true>
+__device__ __forceinline__ void y_tile_epilogue_regs(const MixParams& ep, int e, long unit, int qt, int q, int lane, uint32_t y_addr,
+                                                     float* xt, float rs, float* stg, int g_begin, int n_pass,
+                                                     uint64_t* wait_bar, uint32_t wait_parity, uint64_t* release) {
+  constexpr int NS = D / 16;
+  const int rsub = lane >> 2, c4 = lane & 3;
+  const float* bpj = ep.bproj + (long)e * D;
+  const float* gam = ep.ln_gamma + (long)e * D;
+  const float* bet = ep.ln_beta + (long)e * D;
+  __nv_bfloat16* lt = ep.ln_out + ((long)unit * (32768 / D) + qt * 128 + q * 32) * D;
+#pragma unroll 1
+  for (int ps = 0; ps < n_pass; ++ps) {
+    const int g0 = g_begin + ps * RG;                          // first 8-row group of this pass
+    float4 xo[NS][RG];
+    float* xr = xt + (long)(g0 * 8 + rsub) * D + c4 * 4;
+#pragma unroll
+    for (int c = 0; c < NS; ++c)
+#pragma unroll
+      for (int g2 = 0; g2 < RG; ++g2) xo[c][g2] = *reinterpret_cast<const float4*>(xr + g2 * 8 * D + c * 16);
+    if (ps == 0 && wait_bar) { mbar_wait(wait_bar, wait_parity); tc_fence_after(); }
+    float sum[RG], sq[RG];
+#pragma unroll
+    for (int g2 = 0; g2 < RG; ++g2) { sum[g2] = 0.f; sq[g2] = 0.f; }
+#pragma unroll
+    for (int c = 0; c < NS; ++c) {
+      uint32_t v[16];
+      tmem_ld16(y_addr + (uint32_t)(c * 16), v);
+      if (c == NS - 1 && ps == n_pass - 1 && release) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(release);
+      }
+      float* sb = stg + (DBUF ? (c & 1) * 512 : 0);
+      if (!DBUF && c > 0) __syncwarp();                        // single staging tile: the previous step's reads are done
+#pragma unroll
+      for (int pc = 0; pc < 4; ++pc)
+        *reinterpret_cast<float4*>(sb + lane * 16 + ((pc ^ ((lane >> 1) & 3)) * 4)) =
+            make_float4(__uint_as_float(v[4 * pc]), __uint_as_float(v[4 * pc + 1]), __uint_as_float(v[4 * pc + 2]), __uint_as_float(v[4 * pc + 3]));
+      __syncwarp();
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bpj + c * 16 + c4 * 4));
+#pragma unroll
+      for (int g2 = 0; g2 < RG; ++g2) {
+        const int rl = (g0 + g2) * 8 + rsub;
+        const float4 a = *reinterpret_cast<const float4*>(sb + rl * 16 + ((c4 ^ ((rl >> 1) & 3)) * 4));
+        float4 o = xo[c][g2];
+        o.x = fmaf(a.x + b4.x, rs, o.x); o.y = fmaf(a.y + b4.y, rs, o.y);
+        o.z = fmaf(a.z + b4.z, rs, o.z); o.w = fmaf(a.w + b4.w, rs, o.w);
+        *reinterpret_cast<float4*>(xr + g2 * 8 * D + c * 16) = o;
+        xo[c][g2] = o;
+        if (LNF) { sum[g2] += (o.x + o.y) + (o.z + o.w); sq[g2] += fmaf(o.x, o.x, o.y * o.y) + fmaf(o.z, o.z, o.w * o.w); }
+      }
+    }
+    if (LNF) {
+      float mean[RG], rstd[RG];
+#pragma unroll
+      for (int g2 = 0; g2 < RG; ++g2) {
+        float s1 = sum[g2], s2 = sq[g2];
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+        mean[g2] = s1 * (1.0f / D);
+        rstd[g2] = rsqrtf(fmaxf(s2 * (1.0f / D) - mean[g2] * mean[g2], 0.f) + ep.ln_eps);
+      }
+      __nv_bfloat16* lr = lt + (long)(g0 * 8 + rsub) * D + c4 * 4;
+#pragma unroll
+      for (int c = 0; c < NS; ++c) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gam + c * 16 + c4 * 4));
+        const float4 t4 = __ldg(reinterpret_cast<const float4*>(bet + c * 16 + c4 * 4));
+#pragma unroll
+        for (int g2 = 0; g2 < RG; ++g2) {
+          const float4 xv = xo[c][g2];
+          *reinterpret_cast<uint2*>(lr + g2 * 8 * D + c * 16) = make_uint2(
+              pack_bf16((xv.x - mean[g2]) * rstd[g2] * g4.x + t4.x, (xv.y - mean[g2]) * rstd[g2] * g4.y + t4.y),
+              pack_bf16((xv.z - mean[g2]) * rstd[g2] * g4.z + t4.z, (xv.w - mean[g2]) * rstd[g2] * g4.w + t4.w));
+        }
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -734,12 +822,18 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               // OVL: Y epilogue of this stream's own tile, right after the unit's last proj MMA (the Y-epilogue warpgroup is
               // busy draining q|k|v of the next heads).  Staging = the 4 KiB of the P tile this warp itself writes: free once
               // that proj MMA (the last reader of the tile buffer) has retired, which yd signals too.
-              mbar_wait(&yd[ch], (uint32_t)i & 1u);
-              tc_fence_after();
+              if (warp == 4 && lane == 0) MIX_TRACE(11, i);    // stream 0: last head output published, waiting for Y
               const float rs = ep.rowscale ? ep.rowscale[(long)e * ep.rs_gs + b] : 1.0f;
               float* xt = ep.x + (long)e * ep.x_gs + (long)b * K::N * D + (long)(qt * 128 + q * 32) * D;
-              y_tile_epilogue<D, LNF, 8>(ep, e, u, qt, q, lane, lane_addr + Y_COL + (uint32_t)(qt * D), xt, rs, stg, nullptr);
+              if (ep.dbg == 0) {
+                y_tile_epilogue_regs<D, LNF, 2>(ep, e, u, qt, q, lane, lane_addr + Y_COL + (uint32_t)(qt * D), xt, rs, stg, 0, 2, &yd[ch], (uint32_t)i & 1u, nullptr);
+              } else {
+                mbar_wait(&yd[ch], (uint32_t)i & 1u);
+                tc_fence_after();
+                y_tile_epilogue<D, LNF, 8>(ep, e, u, qt, q, lane, lane_addr + Y_COL + (uint32_t)(qt * D), xt, rs, stg, nullptr);
+              }
               tc_fence_before();
+              if (warp == 4 && lane == 0) MIX_TRACE(13, i);    // stream 0: Y epilogue of its tile done
             }
           }
         }
@@ -838,8 +932,12 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (warp == 12 && lane == 0) MIX_TRACE(11, i);           // epi: y_full observed
       for (int qt = 0; qt < K::NT; ++qt) {
         // Y is handed back tile by tile (y_empty[qt]): the next unit's first proj MMA of a tile only waits for that tile
-        y_tile_epilogue<D, LNF>(ep, e, u, qt, q, lane, lane_addr + Y_COL + (uint32_t)(qt * D), xunit + (long)(qt * 128 + q * 32) * D,
-                                rs, stg, &y_empty[qt]);
+        if constexpr (LNF)
+          y_tile_epilogue_regs<D, LNF, 2, false>(ep, e, u, qt, q, lane, lane_addr + Y_COL + (uint32_t)(qt * D),
+                                                 xunit + (long)(qt * 128 + q * 32) * D, rs, stg, 0, 2, nullptr, 0u, &y_empty[qt]);
+        else
+          y_tile_epilogue<D, LNF>(ep, e, u, qt, q, lane, lane_addr + Y_COL + (uint32_t)(qt * D), xunit + (long)(qt * 128 + q * 32) * D,
+                                  rs, stg, &y_empty[qt]);
         if (warp == 12 && lane == 0 && qt == K::NT - 1) MIX_TRACE(12, i);     // epi: Y drained (+ LayerNorm of the last tile)
       }
       if (warp == 12 && lane == 0) MIX_TRACE(13, i);           // epi: unit done
