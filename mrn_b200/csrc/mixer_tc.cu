@@ -520,6 +520,7 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       constexpr uint32_t idesc_qkv = make_idesc(96), idesc_s = make_idesc(64), idesc_o = make_idesc(HD, 1), idesc_y = make_idesc(D);
       const uint32_t s_col = s ? S1_COL : S0_COL, o_col = s ? O1_COL : O0_COL;
       uint32_t hc = 0, mc = 0, pc = 0, qc = 0;
+      bool s_early = false;                                    // OVL: the first S of the coming head is already issued
       int i = 0;
       for (int u = blockIdx.x; u < total; u += gridDim.x, ++i) {
         if (!K::OVL && s == 0) { mbar_wait(&a_full, (uint32_t)i & 1u); tc_fence_after(); }
@@ -547,23 +548,25 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           // ---- phase 2: this stream's query tiles s, s+2, ..
           const int buf = hc & 1u;
-          if constexpr (K::OVL) mbar_wait(&qkvr[buf], (hc >> 1) & 1u);      // q/k/v of this head drained into buffer hc % 2
+          if constexpr (K::OVL) { if (!s_early) mbar_wait(&qkvr[buf], (hc >> 1) & 1u); }   // q/k/v of this head drained into buffer hc % 2
           else mbar_wait(&qkv_ready, hc & 1u);
           mbar_wait(&wp_full[buf], (hc >> 1) & 1u);
           tc_fence_after();
           uint8_t* const sQh = sQ + (K::OVL ? buf * K::QKV1_BYTES : 0);
           uint8_t* const sKh = sK + (K::OVL ? buf * K::QKV1_BYTES : 0);
           uint8_t* const sVh = sV + (K::OVL ? buf * K::QKV1_BYTES : 0);
-          auto issue_s = [&](int qt, int kr) {
-            const uint64_t qd = make_desc(smem_u32(sQh + qt * K::HT_BYTES), 512, 4);
-            const uint64_t kd = make_desc(smem_u32(sKh + kr * 4096), 512, 4);
+          auto issue_s_from = [&](const uint8_t* q_, const uint8_t* k_, int qt, int kr) {
+            const uint64_t qd = make_desc(smem_u32(q_ + qt * K::HT_BYTES), 512, 4);
+            const uint64_t kd = make_desc(smem_u32(k_ + kr * 4096), 512, 4);
 #pragma unroll
             for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + s_col, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_s, k);
             umma_commit(&s_full[s]);
           };
+          auto issue_s = [&](int qt, int kr) { issue_s_from(sQh, sKh, qt, kr); };
           if (s < K::NT) {
             int qt = s, kr = kr_lo(s);
-            issue_s(qt, kr);
+            if (!s_early) issue_s(qt, kr);
+            s_early = false;
             while (true) {
               int nqt = qt, nkr = kr + 1;
               if (nkr >= kr_hi(qt)) { nqt = qt + 2; nkr = nqt < K::NT ? kr_lo(nqt) : 0; }
@@ -590,6 +593,19 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               }
               if (s == 0) MIX_TRACE(3, pc);                    // MMA0: PV issued
               ++pc;
+              if constexpr (K::OVL) {
+                // last pair of the head (one tile per stream): if q/k/v of the NEXT head (possibly of the next unit) are
+                // already drained, its first S is issued now, under the stream's O normalisation and this head's proj MMA
+                // (never blocking: a late drain must not hold back the proj MMA the Y epilogue is waiting for)
+                const bool more = !(h == K::HEADS - 1 && u + (int)gridDim.x >= total);
+                const uint32_t nb = (hc + 1u) & 1u;
+                if (!has_next && more && mbar_test(&qkvr[nb], ((hc + 1u) >> 1) & 1u)) {
+                  mbar_wait(&s_empty[s], (pc - 1u) & 1u);    // the stream has pulled the last S out of TMEM
+                  tc_fence_after();
+                  issue_s_from(sQ + nb * K::QKV1_BYTES, sK + nb * K::QKV1_BYTES, s, kr_lo(s));
+                  s_early = true;
+                }
+              }
               if (last_of_tile) {
                 // the stream has normalised the head output of this query tile into its tile buffer:
                 // Y[qt] (+)= O_h Wproj[:, h*32 : h*32+32]^T
