@@ -28,14 +28,14 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // Optional second LayerNorm (y2, bf16): y2 = LN_2(LN_1(x)) in the same pass -- the SubSample norm followed by the next
 // stage's first norm1 (modules/svtr.py:311 then :201).
-template <typename OT, int D>
+template <typename OT, int D, int RPW = 4>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x, long x_gs, OT* y, long y_gs, const float* __restrict__ gamma,
                  const float* __restrict__ beta, long rows, long rows_per_group, float eps,
                  __nv_bfloat16* __restrict__ y2 = nullptr, long y2_gs = 0, const float* __restrict__ gamma2 = nullptr,
                  const float* __restrict__ beta2 = nullptr, float eps2 = 0.f) {
   constexpr int VPT = D / 32;
-  constexpr int RPW = 4;                       // rows per warp: all loads are issued before the first reduction
+  // RPW rows per warp: all loads are issued before the first reduction
   const long row0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
   const int lane = threadIdx.x & 31;
   float v[RPW][VPT];
@@ -129,10 +129,11 @@ int launch_layernorm(const float* x, long x_gs, OT* y, long y_gs, const float* g
                      long rows_per_group, int D, float eps, cudaStream_t st) {
   const int grid = cdiv(rows, 8 * 4);
   MrnbProfScope prof(MRNB_PROF_LN, st, 0.0, (double)rows * D * (4 + sizeof(OT)));
+  // 128 / 256 wide: two rows per warp (measured 5 % faster than four in the step: 4.72 vs 4.49 TB/s; eight: 3.93)
   switch (D) {
     case 64: layernorm_kernel<OT, 64><<<grid, 256, 0, st>>>(x, x_gs, y, y_gs, gamma, beta, rows, rows_per_group, eps); break;
-    case 128: layernorm_kernel<OT, 128><<<grid, 256, 0, st>>>(x, x_gs, y, y_gs, gamma, beta, rows, rows_per_group, eps); break;
-    case 256: layernorm_kernel<OT, 256><<<grid, 256, 0, st>>>(x, x_gs, y, y_gs, gamma, beta, rows, rows_per_group, eps); break;
+    case 128: layernorm_kernel<OT, 128, 2><<<cdiv(rows, 8 * 2), 256, 0, st>>>(x, x_gs, y, y_gs, gamma, beta, rows, rows_per_group, eps); break;
+    case 256: layernorm_kernel<OT, 256, 2><<<cdiv(rows, 8 * 2), 256, 0, st>>>(x, x_gs, y, y_gs, gamma, beta, rows, rows_per_group, eps); break;
     case 512: layernorm_kernel<OT, 512><<<grid, 256, 0, st>>>(x, x_gs, y, y_gs, gamma, beta, rows, rows_per_group, eps); break;
     default: mrnb_set_error("layernorm: unsupported D=%d", D); return MRNB_ERR_UNSUPPORTED;
   }

@@ -10,3 +10,7 @@ python bench.py --mode stage0 --no-cpu-baseline > gpurun_out/r02_final_stage0_sv
 python bench.py --mode stage0 --arch crnn --no-cpu-baseline > gpurun_out/r02_final_stage0_crnn.json 2> gpurun_out/r02_final_stage0_crnn.err
 cat gpurun_out/r02_final_pytest.txt
 for f in bench infer crnn stage0_svtr stage0_crnn; do python tools/show_bench.py gpurun_out/r02_final_$f.json | head -1; done
+# sanitizer passes last: they rebuild the box's copy of the library with the 10-minute mbarrier wait guard
+TOOLS="memcheck initcheck" HEAD=6 bash tools/sanitize.sh > gpurun_out/r02_final_sanitizer.log 2>&1
+ARCH=crnn B=128 SAN_TIMEOUT=400 timeout 450 compute-sanitizer --tool memcheck --print-limit 10 python tools/sanitize_step.py 2>&1 | grep -v "^$" | tail -6 > gpurun_out/r02_final_sanitizer_crnn.log
+tail -3 gpurun_out/r02_final_sanitizer.log; tail -3 gpurun_out/r02_final_sanitizer_crnn.log

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""One small bf16 stage-1 step + one hard-routed inference call (the workload of tools/sanitize.sh)."""
+"""One small bf16 stage-1 step + one hard-routed inference call (the workload of tools/sanitize.sh).
+ARCH=crnn B=128 covers the CRNN experts, including the persistent LSTM kernel (it needs 128-sample tiles)."""
 import os
 import sys
 
@@ -11,13 +12,14 @@ from mrn_b200 import synth  # noqa: E402
 from mrn_b200.il_modules.mrn import MRN, RankLocal, FusedAdam  # noqa: E402
 from mrn_b200.modules.model import MRNNet  # noqa: E402
 
+ARCH = os.environ.get("ARCH", "svtr")
 B = int(os.environ.get("B", 4))
-opt = make_opt("bf16", 0, "svtr")
+opt = make_opt("bf16", 0, ARCH)
 net = MRNNet(opt)
 for c in CLASS_COUNTS:
     net.update_fc(opt.hidden_size, c)
     net.build_prediction(opt, c)
-net.load_state_dict(synth.ctor_state_dict(CLASS_COUNTS, 111), strict=True)
+net.load_state_dict(synth.ctor_state_dict(CLASS_COUNTS, 111, arch=ARCH), strict=True)
 net = net.cuda()
 learner = MRN(opt)
 learner.model = RankLocal(net)
