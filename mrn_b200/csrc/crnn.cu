@@ -245,11 +245,10 @@ bn_relu_pool_kernel(const AT* __restrict__ x, const float* __restrict__ ss /*[I,
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
-// MRNB_LSTM_SEQ = 0 keeps one grouped GEMM launch per time step
+// MRNB_LSTM_SEQ = 0 keeps one grouped GEMM launch per time step (read on every call: the parity test toggles it)
 inline bool lstm_seq_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("MRNB_LSTM_SEQ"); v = e ? atoi(e) : 1; }
-  return v != 0;
+  const char* e = getenv("MRNB_LSTM_SEQ");
+  return !e || atoi(e) != 0;
 }
 
 template <typename AT>

@@ -166,6 +166,38 @@ def test_crnn_bf16_mode_within_north_star_budget():
     assert rel_err(rt["logits"].cpu().numpy(), ot["logits"].numpy()) < 2e-2
 
 
+def test_crnn_persistent_lstm_kernel_matches_per_step_launches(monkeypatch):
+    """The persistent BidirectionalLSTM kernel (one 4-CTA-cluster launch per layer, W_hh resident in shared memory; taken
+    when the batch is a multiple of 128) against the per-step grouped GEMM + cell kernel path it replaces
+    (MRNB_LSTM_SEQ=0) on the same weights and batch: same MMA shapes, k-block order and cell arithmetic, so features and
+    logits must agree to bf16 rounding noise at most (identical on the boxes measured); and both stay within the bf16
+    budget of the fp32 oracle on a 4-sample slice.  modules/sequence_modeling.py:12-22."""
+    import os
+    cc, B = (37, 61), 128
+    sd = _random_init_state_dict(cc, 11)
+    img, tgt, lens, dom = synth.synth_batch(B, cc, 11)
+    net, opt = build_net(cc, sd, precision="bf16")
+    net.eval()
+    x = img.cuda()
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MRNB_LSTM_SEQ", mode)
+        assert os.environ["MRNB_LSTM_SEQ"] == mode
+        r = net.route_and_combine(x, is_train=True, want_logits=True)
+        torch.cuda.synchronize()
+        res[mode] = (r["features"].float().cpu(), r["logits"].float().cpu())
+    monkeypatch.delenv("MRNB_LSTM_SEQ")
+    f1, l1 = res["1"]
+    f0, l0 = res["0"]
+    assert torch.isfinite(f1).all() and torch.isfinite(l1).all()
+    fd, ld = float((f1 - f0).abs().max()), float((l1 - l0).abs().max())
+    print("persistent LSTM vs per-step: max |d features| %.3e, max |d logits| %.3e" % (fd, ld))
+    assert fd <= 2e-2 * float(f0.abs().max()) and ld <= 2e-2 * float(l0.abs().max())
+    with torch.no_grad():
+        o = O.mrn_forward(sd, len(cc), img[:4], True, True)
+    assert rel_err(l1[:4].numpy(), o["logits"].numpy()) < 2e-2
+
+
 def test_crnn_baseline_config0_two_tasks_batch64():
     """BASELINE.json configs[0]: CRNN-MRN forward + CTC loss, 2 tasks (Chinese + Latin class counts), batch 64,
     synthetic 32x256 crops -- the CUDA path against the CPU oracle on the same inputs."""
