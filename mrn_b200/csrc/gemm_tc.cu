@@ -112,6 +112,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Output tensor maps of the TMA-store epilogue (MODE 3: one fp32 [M, C_e] map per expert, box 32 x 32, 128B swizzle)
+struct TcOutMaps { CUtensorMap m[8]; };
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
 struct TcEpi {
   const float* bias; long bias_gs;
   void* out; long ldo; long o_gs;
@@ -126,6 +135,7 @@ struct TcEpi {
   int relu;
   MrnbTcLstm lstm;
   MrnbTcHeads heads;       // MODE 3: ragged classifier heads of all experts in one launch (+ hard-route tile skip)
+  int tma_out;             // MODE 3: output tiles leave through TMA stores (every head 16-byte aligned with ldo % 4 == 0)
 };
 
 // MODE 3 tile decode: flat tile t -> (expert e, m0, n0); returns false when the hard route sends none of the tile's samples
@@ -161,7 +171,8 @@ __device__ __forceinline__ float tanh_fast(float x) {
 
 template <int BN, bool OUT_F32, bool GELU, bool LNF, int MODE = 0>
 __global__ void __launch_bounds__(NTHREADS, LNF ? 1 : 2)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcEpi ep) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TcEpi ep,
+               const __grid_constant__ TcOutMaps tmO) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -320,6 +331,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);  // this warp's share of the accumulator is out of TMEM
+          }
+          if constexpr (MODE == 3) {
+            if (ep.tma_out) {
+              // TMA-store epilogue: + bias in the accumulator layout (thread = row: the 32 bias values of the pass are
+              // broadcast loads), the 32 x 32 fp32 tile is parked in the staging tile in the 128B-swizzled box layout
+              // (the same conflict-free XOR as below) and leaves with ONE bulk tensor store per warp and pass -- whole
+              // 128-byte lines, rows / columns beyond M / C_e clipped by the hardware, no per-thread address arithmetic
+              const int c0 = n0 + ch * CW + ps * 32;
+              if (c0 < t_N) {
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has read the tile
+                __syncwarp();
+#pragma unroll
+                for (int pc = 0; pc < 8; ++pc) {
+                  float4 b4;
+                  if (c0 + 4 * pc + 4 <= t_N) b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * pc));
+                  else {
+                    b4.x = c0 + 4 * pc < t_N ? bias[c0 + 4 * pc] : 0.f; b4.y = c0 + 4 * pc + 1 < t_N ? bias[c0 + 4 * pc + 1] : 0.f;
+                    b4.z = c0 + 4 * pc + 2 < t_N ? bias[c0 + 4 * pc + 2] : 0.f; b4.w = 0.f;
+                  }
+                  *reinterpret_cast<float4*>(stg + lane * 32 + ((pc ^ (lane & 7)) * 4)) =
+                      make_float4(__uint_as_float(r[4 * pc]) + b4.x, __uint_as_float(r[4 * pc + 1]) + b4.y,
+                                  __uint_as_float(r[4 * pc + 2]) + b4.z, __uint_as_float(r[4 * pc + 3]) + b4.w);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) tma_store_2d(&tmO.m[g], stg, c0, m0 + q * 32);
+              }
+              continue;
+            }
           }
 #pragma unroll
           for (int pc = 0; pc < 8; ++pc)
@@ -514,6 +554,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   }
+  if (MODE == 3 && warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // bulk stores of this thread are complete
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
@@ -756,6 +797,18 @@ int make_conv_map(CUtensorMap* map, const void* ptr, const MrnbTcConv& c) {
   return MRNB_OK;
 }
 
+// 2-D map over an fp32 [rows][cols] output (row pitch ld floats): box 32 x 32, 128B swizzle -- the TMA-store epilogue
+bool make_out_map(CUtensorMap* map, void* ptr, long cols, long rows, long ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn || (reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 4)) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int BN, bool OUT_F32, bool GELU, bool LNF, int MODE = 0>
 int launch_tc(const MrnbTcGemm& p, cudaStream_t st) {
   CUtensorMap tmA, tmW;
@@ -789,7 +842,8 @@ int launch_tc(const MrnbTcGemm& p, cudaStream_t st) {
   }
   const int slots = (LNF ? 1 : 2) * num_sms;                                  // persistent CTAs: two per SM (one with fused LN)
   const int grid = ep.total_tiles < slots ? ep.total_tiles : slots;
-  tc_gemm_kernel<BN, OUT_F32, GELU, LNF, MODE><<<grid, NTHREADS, smem, st>>>(tmA, tmW, ep);
+  static const TcOutMaps no_maps{};
+  tc_gemm_kernel<BN, OUT_F32, GELU, LNF, MODE><<<grid, NTHREADS, smem, st>>>(tmA, tmW, ep, no_maps);
   MRNB_CHECK_LAUNCH("tc_gemm_kernel");
   return MRNB_OK;
 }
@@ -853,6 +907,11 @@ int mrnb_tc_heads(const void* A, long lda, long a_gstride, const void* Wall, lon
   ep.M = M; ep.N = 0; ep.KB = K / BK; ep.stages = ep.KB < MAX_STAGES ? ep.KB : MAX_STAGES;
   ep.rows_per_scale = 1; ep.n_tiles = 1; ep.m_tiles = m_tiles; ep.total_tiles = H.tile_prefix[H.n_experts];
   ep.heads = H;
+  TcOutMaps maps{};
+  ep.tma_out = 1;
+  { const char* e = getenv("MRNB_HEADS_TMA"); if (e && atoi(e) == 0) ep.tma_out = 0; }
+  for (int e = 0; e < H.n_experts && ep.tma_out; ++e)
+    if (!H.bias[e] || !make_out_map(&maps.m[e], H.out[e], H.N[e], M, H.ldo[e])) ep.tma_out = 0;
   constexpr int BN_ = 128;
   const size_t smem = 1024 + (size_t)ep.stages * (A_STAGE_BYTES + BN_ * BK * 2) + STAGING_BYTES;
   static bool attr_set = false;
@@ -867,7 +926,7 @@ int mrnb_tc_heads(const void* A, long lda, long a_gstride, const void* Wall, lon
   }
   const int slots = 2 * num_sms;
   const int grid = ep.total_tiles < slots ? ep.total_tiles : slots;
-  tc_gemm_kernel<BN_, true, false, false, 3><<<grid, NTHREADS, smem, st>>>(tmA, tmW, ep);
+  tc_gemm_kernel<BN_, true, false, false, 3><<<grid, NTHREADS, smem, st>>>(tmA, tmW, ep, maps);
   MRNB_CHECK_LAUNCH("tc_gemm_kernel");
   return MRNB_OK;
 }
