@@ -233,6 +233,91 @@ conv0_kernel(const float* __restrict__ img, const float* __restrict__ w /*[I,32,
   }
 }
 
+// The same convolution with TWO vertically adjacent output rows per thread: every broadcast 16-byte weight load feeds
+// eight FMAs instead of four (the one-row kernel is co-limited by the SM's shared-memory load path: 288 LDS.128 next to
+// 1152 FFMA per thread), and the five input rows the two windows cover are loaded once (60 instead of 72 taps).
+// grid: (8 row pairs, B, I); block: 128 threads = 128 output columns.
+template <typename OT>
+__global__ void __launch_bounds__(128)
+conv0_rows2_kernel(const float* __restrict__ img, const float* __restrict__ w /*[I,32,4,3,3]*/,
+                   const float* __restrict__ bias /*[I,32]*/, OT* __restrict__ out, double* __restrict__ stats /*[I,32,2]*/,
+                   int B) {
+  const int oh0 = blockIdx.x * 2, b = blockIdx.y, e = blockIdx.z, ow = threadIdx.x;
+  __shared__ __align__(16) float sw[32 * 36];
+  __shared__ float sb[32];
+  __shared__ float red[4][32][2];
+  for (int k = threadIdx.x; k < 32 * 36; k += 128) sw[k] = w[(long)e * 32 * 36 + k];
+  if (threadIdx.x < 32) sb[threadIdx.x] = bias[e * 32 + threadIdx.x];
+  __syncthreads();
+  float in[4][5][3];                           // input rows 2 * oh0 - 1 .. 2 * oh0 + 3
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int rr = 0; rr < 5; ++rr)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ih = oh0 * 2 - 1 + rr, iw = ow * 2 - 1 + kw;
+        in[c][rr][kw] = (ih >= 0 && ih < 32 && iw >= 0 && iw < 256) ? __ldg(img + (((long)b * 4 + c) * 32 + ih) * 256 + iw) : 0.f;
+      }
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  float r0[32], r1[32];
+#pragma unroll
+  for (int oc = 0; oc < 32; ++oc) {
+    const float4* w4 = reinterpret_cast<const float4*>(sw + oc * 36);
+    float a0 = sb[oc], a1 = a0;
+#pragma unroll
+    for (int k4 = 0; k4 < 9; ++k4) {
+      const float4 wv = w4[k4];
+      const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k4 * 4 + u, c = k / 9, kh = (k % 9) / 3, kw = k % 3;
+        a0 = fmaf(in[c][kh][kw], wq[u], a0);
+        a1 = fmaf(in[c][kh + 2][kw], wq[u], a1);
+      }
+    }
+    r0[oc] = a0; r1[oc] = a1;
+  }
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    OT* o = out + ((((long)e * B + b) * 16 + oh0 + p) * 128 + ow) * 32;
+#pragma unroll
+    for (int oc0 = 0; oc0 < 32; oc0 += 8) {
+      if constexpr (sizeof(OT) == 4) {
+        *reinterpret_cast<float4*>(o + oc0) = p ? make_float4(r1[oc0], r1[oc0 + 1], r1[oc0 + 2], r1[oc0 + 3]) : make_float4(r0[oc0], r0[oc0 + 1], r0[oc0 + 2], r0[oc0 + 3]);
+        *reinterpret_cast<float4*>(o + oc0 + 4) = p ? make_float4(r1[oc0 + 4], r1[oc0 + 5], r1[oc0 + 6], r1[oc0 + 7]) : make_float4(r0[oc0 + 4], r0[oc0 + 5], r0[oc0 + 6], r0[oc0 + 7]);
+      } else {
+        uint32_t pk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          __nv_bfloat162 h = p ? __floats2bfloat162_rn(r1[oc0 + 2 * u], r1[oc0 + 2 * u + 1]) : __floats2bfloat162_rn(r0[oc0 + 2 * u], r0[oc0 + 2 * u + 1]);
+          pk[u] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(o + oc0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+  }
+  if (stats) {
+#pragma unroll
+    for (int oc0 = 0; oc0 < 32; oc0 += 8) {
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { v[u] = r0[oc0 + u] + r1[oc0 + u]; v[8 + u] = fmaf(r0[oc0 + u], r0[oc0 + u], r1[oc0 + u] * r1[oc0 + u]); }
+      const float tot = warp_reduce16(v, lane);
+      if ((lane & 1) == 0) {
+        const int idx = (lane >> 1) & 15;
+        red[wp][oc0 + (idx & 7)][idx >> 3] = tot;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const int c = threadIdx.x >> 1, k = threadIdx.x & 1;
+      const double t = (double)red[0][c][k] + (double)red[1][c][k] + (double)red[2][c][k] + (double)red[3][c][k];
+      atomicAdd(stats + ((long)e * 32 + c) * 2 + k, t);
+    }
+  }
+}
+
 // conv1: 32->64, 3x3 s2 p1 over GELU(BN(conv0)) (applied on load) -> raw NHWC [I,B,8,64,64] + BN statistics.
 // grid (8 output rows, B, I); block 256 = 64 output columns x 4 groups of 16 output channels.
 __global__ void __launch_bounds__(256)
@@ -640,8 +725,8 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
     // ---- tensor-core mode: conv0 direct (K = 36) -> bf16 raw; conv1 as an implicit GEMM fed by TMA from the padded
     // NHWC activation (K = 3 kh x 128: {kw0,kw1} and {kw2, zero} 64-element slots), BN statistics from its fp32 output.
     __nv_bfloat16* raw0 = reinterpret_cast<__nv_bfloat16*>(conv0);
-    conv0_kernel<__nv_bfloat16><<<dim3(16, B, I), 128, 0, st>>>(image, P.p[MRNB_P_CONV0_W], P.p[MRNB_P_CONV0_B], raw0,
-                                                                  bn_batch_stats ? st0 : nullptr, B);
+    conv0_rows2_kernel<__nv_bfloat16><<<dim3(8, B, I), 128, 0, st>>>(image, P.p[MRNB_P_CONV0_W], P.p[MRNB_P_CONV0_B], raw0,
+                                                                      bn_batch_stats ? st0 : nullptr, B);
     MRNB_CHECK_LAUNCH("conv0_kernel");
     bn_finalize_kernel<<<cdiv(I * 32, 128), 128, 0, st>>>(st0, P.p[MRNB_P_BN0_W], P.p[MRNB_P_BN0_B],
                                                           (float*)P.p[MRNB_P_BN0_MEAN], (float*)P.p[MRNB_P_BN0_VAR], ss0, I,
