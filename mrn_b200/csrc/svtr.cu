@@ -145,10 +145,10 @@ int launch_layernorm(const float* x, long x_gs, OT* y, long y_gs, const float* g
 int launch_layernorm2(const float* x, long x_gs, float* y, long y_gs, const float* gamma, const float* beta, float eps,
                       __nv_bfloat16* y2, long y2_gs, const float* gamma2, const float* beta2, float eps2, long rows,
                       long rows_per_group, int D, cudaStream_t st) {
-  const int grid = cdiv(rows, 8 * 4);
+  const int grid = cdiv(rows, 8 * 2);
   MrnbProfScope prof(MRNB_PROF_LN, st, 0.0, (double)rows * D * (4 + 4 + 2));
-  if (D == 128) layernorm_kernel<float, 128><<<grid, 256, 0, st>>>(x, x_gs, y, y_gs, gamma, beta, rows, rows_per_group, eps, y2, y2_gs, gamma2, beta2, eps2);
-  else if (D == 256) layernorm_kernel<float, 256><<<grid, 256, 0, st>>>(x, x_gs, y, y_gs, gamma, beta, rows, rows_per_group, eps, y2, y2_gs, gamma2, beta2, eps2);
+  if (D == 128) layernorm_kernel<float, 128, 2><<<grid, 256, 0, st>>>(x, x_gs, y, y_gs, gamma, beta, rows, rows_per_group, eps, y2, y2_gs, gamma2, beta2, eps2);
+  else if (D == 256) layernorm_kernel<float, 256, 2><<<grid, 256, 0, st>>>(x, x_gs, y, y_gs, gamma, beta, rows, rows_per_group, eps, y2, y2_gs, gamma2, beta2, eps2);
   else { mrnb_set_error("layernorm2: unsupported D=%d", D); return MRNB_ERR_UNSUPPORTED; }
   MRNB_CHECK_LAUNCH("layernorm_kernel");
   return MRNB_OK;
@@ -431,6 +431,8 @@ bn_stats_rows_kernel(const float* __restrict__ x, long rows, double* __restrict_
 }
 
 // tokens: x[e,b,n,c] = GELU(BN(conv1 raw)) + pos_embed[e,n,c]      (svtr.py:246-254,511)
+// FAST (tensor-core mode): minimax-tanh GELU (|error| 2.5e-5) -- with erff the kernel is ALU bound (3.6 TB/s)
+template <bool FAST>
 __global__ void embed_kernel(const float* __restrict__ raw, const float* __restrict__ ss1 /*[I,64,2]*/,
                              const float* __restrict__ pos /*[I,512,64]*/, float* __restrict__ x, long per_expert,
                              __nv_bfloat16* __restrict__ ln_out /* optional: LN1 of blocks1.0, [I][rows][64] */,
@@ -445,10 +447,11 @@ __global__ void embed_kernel(const float* __restrict__ raw, const float* __restr
   const float4 p = *reinterpret_cast<const float4*>(pos + ((long)e * 512 + n) * 64 + c);
   const float* ss = ss1 + (e * 64 + c) * 2;
   float4 o;
-  o.x = gelu_erf(fmaf(r.x, ss[0], ss[1])) + p.x;
-  o.y = gelu_erf(fmaf(r.y, ss[2], ss[3])) + p.y;
-  o.z = gelu_erf(fmaf(r.z, ss[4], ss[5])) + p.z;
-  o.w = gelu_erf(fmaf(r.w, ss[6], ss[7])) + p.w;
+  const float a0 = fmaf(r.x, ss[0], ss[1]), a1 = fmaf(r.y, ss[2], ss[3]), a2 = fmaf(r.z, ss[4], ss[5]), a3 = fmaf(r.w, ss[6], ss[7]);
+  o.x = (FAST ? gelu_fast(a0) : gelu_erf(a0)) + p.x;
+  o.y = (FAST ? gelu_fast(a1) : gelu_erf(a1)) + p.y;
+  o.z = (FAST ? gelu_fast(a2) : gelu_erf(a2)) + p.z;
+  o.w = (FAST ? gelu_fast(a3) : gelu_erf(a3)) + p.w;
   *reinterpret_cast<float4*>(x + off) = o;
   if (ln_out) {
     float s = (o.x + o.y) + (o.z + o.w);
@@ -775,7 +778,7 @@ int svtr_forward_t(const MrnbSvtrPack& P, const float* image, int B, int Bc, int
     const long per_expert = (long)B * 32768;
     // tensor-core mode without batch chunking: blocks1.0.norm1 is emitted here as well (one pass over the tokens)
     ln1_ready = sizeof(AT) == 2 && Bc == B;
-    embed_kernel<<<dim3(cdiv(per_expert / 4, 256), I), 256, 0, st>>>(
+    embed_kernel<sizeof(AT) == 2><<<dim3(cdiv(per_expert / 4, 256), I), 256, 0, st>>>(
         conv1, ss1, P.p[MRNB_P_POS_EMBED], xall, per_expert, ln1_ready ? reinterpret_cast<__nv_bfloat16*>(lnout) : nullptr,
         P.p[MRNB_P_BLOCK0 + MRNB_PB_NORM1_W], P.p[MRNB_P_BLOCK0 + MRNB_PB_NORM1_B], 1e-6f);
     MRNB_CHECK_LAUNCH("embed_kernel");
