@@ -24,10 +24,17 @@ sumsq_kernel(const float* __restrict__ g, long n, double* __restrict__ partial) 
   }
 }
 
+// one warp: lane l sums partial[l], partial[l + 32], ... (all loads in flight), then a fixed-order butterfly -- the order
+// of the additions never depends on timing, so the norm is deterministic (a single serial thread took 23 us here)
 __global__ void norm_finish_kernel(const double* __restrict__ partial, int n, float max_norm, float* __restrict__ norm_out,
                                    float* __restrict__ coef_out) {
+  const int lane = threadIdx.x;
   double t = 0.0;
-  for (int k = 0; k < n; ++k) t += partial[k];      // fixed order: deterministic
+#pragma unroll 4
+  for (int k = lane; k < n; k += 32) t += partial[k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (lane != 0) return;
   const float norm = (float)sqrt(t);
   if (norm_out) norm_out[0] = norm;
   const float c = max_norm / (norm + 1e-6f);        // torch.nn.utils.clip_grad_norm_
@@ -59,7 +66,7 @@ extern "C" int mrnb_clip_adam(float* params, const float* grads, float* exp_avg,
   if (blocks > 444) blocks = 444;                // 3 x 148 SMs
   sumsq_kernel<<<blocks, 256, 0, stream>>>(grads, n, partial);
   MRNB_CHECK_LAUNCH("sumsq_kernel");
-  norm_finish_kernel<<<1, 1, 0, stream>>>(partial, blocks, max_norm, norm_out, coef);
+  norm_finish_kernel<<<1, 32, 0, stream>>>(partial, blocks, max_norm, norm_out, coef);
   MRNB_CHECK_LAUNCH("norm_finish_kernel");
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2s = sqrtf(1.f - powf(beta2, (float)step));

@@ -181,6 +181,35 @@ __global__ void mul2_kernel(const float* __restrict__ a, const float* __restrict
   if (d16) store_bf16x4(d16 + i * 4, r);
 }
 
+// T == 64 (every SVTR / padded CRNN router): the 64 frames of a channel stay in registers -- one pass over y with all
+// loads in flight instead of three dependent passes
+__global__ void __launch_bounds__(RD)
+lnT_fwd64_kernel(const float* __restrict__ y, const float* __restrict__ gamma /*[64]*/, const float* __restrict__ beta,
+                 float* __restrict__ gn, __nv_bfloat16* __restrict__ gn16, float* __restrict__ stats /*[B*I, D, 2]*/, int Tv,
+                 float eps) {
+  const long bi = blockIdx.x;
+  const int c = threadIdx.x;
+  const float* yp = y + bi * 64 * RD + c;
+  float v[64];
+#pragma unroll
+  for (int t = 0; t < 64; ++t) v[t] = yp[(long)t * RD];
+  float s = 0.f;
+#pragma unroll
+  for (int t = 0; t < 64; ++t) s += t < Tv ? v[t] : 0.f;   // same summation order as the generic kernel
+  const float mean = s / Tv;
+  float q = 0.f;
+#pragma unroll
+  for (int t = 0; t < 64; ++t) { const float d = v[t] - mean; q = t < Tv ? fmaf(d, d, q) : q; }
+  const float rstd = rsqrtf(q / Tv + eps);
+  stats[(bi * RD + c) * 2] = mean; stats[(bi * RD + c) * 2 + 1] = rstd;
+#pragma unroll
+  for (int t = 0; t < 64; ++t) {
+    const float o = t < Tv ? (v[t] - mean) * rstd * __ldg(gamma + t) + __ldg(beta + t) : 0.f;
+    if (gn) gn[bi * 64 * RD + (long)t * RD + c] = o;
+    if (gn16) gn16[bi * 64 * RD + (long)t * RD + c] = __float2bfloat16_rn(o);
+  }
+}
+
 // LayerNorm over the patch axis T for every (b,i,c): block per (b,i), thread per c (ChannelDomainGating.norm)
 __global__ void __launch_bounds__(RD)
 lnT_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma /*[T]*/, const float* __restrict__ beta,
@@ -269,38 +298,64 @@ ln_rows_bwd_kernel(const float* __restrict__ xin, long ldx, const float* __restr
   float ag[8], ab[8], ac[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { ag[j] = 0.f; ab[j] = 0.f; ac[j] = 0.f; }
-  for (long row = (long)blockIdx.x * 8 + w; row < rows; row += (long)gridDim.x * 8) {
-    const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
-    float xh[8], dxh[8], pre[8];
-    float m1 = 0.f, m2 = 0.f;
+  // two rows per iteration, 16-byte loads, all of them issued before the first reduction (one row per iteration with
+  // scalar loads left the kernel latency bound: 3.0 TB/s); per-lane accumulation order over the rows is unchanged
+  const long rstep = (long)gridDim.x * 8;
+  for (long row0 = (long)blockIdx.x * 8 + w; row0 < rows; row0 += 2 * rstep) {
+    float4 xq[2][2], dq[2][2], a1q[2][2], a2q[2][2];
+    float mean[2], rstd[2];
+    bool ok[2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int idx = (j / 4) * 128 + lane * 4 + (j % 4);
-      pre[j] = xin[row * ldx + idx];
-      const float xv = GELU_IN ? (FAST ? gelu_fast(pre[j]) : gelu_erf(pre[j])) : pre[j];
-      xh[j] = (xv - mean) * rstd;
-      const float d = dyn[row * RD + idx];
-      dxh[j] = gamma ? d * gamma[idx] : d;
-      ag[j] = fmaf(d, xh[j], ag[j]); ab[j] += d;
-      m1 += dxh[j]; m2 = fmaf(dxh[j], xh[j], m2);
+    for (int u = 0; u < 2; ++u) {
+      const long row = row0 + u * rstep;
+      ok[u] = row < rows;
+      const long rr = ok[u] ? row : row0;
+      mean[u] = stats[rr * 2]; rstd[u] = stats[rr * 2 + 1];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        xq[u][c] = *reinterpret_cast<const float4*>(xin + rr * ldx + c * 128 + lane * 4);
+        dq[u][c] = *reinterpret_cast<const float4*>(dyn + rr * RD + c * 128 + lane * 4);
+        if (add1) a1q[u][c] = *reinterpret_cast<const float4*>(add1 + rr * RD + c * 128 + lane * 4);
+        if (add2) a2q[u][c] = *reinterpret_cast<const float4*>(add2 + rr * RD + c * 128 + lane * 4);
+      }
     }
-    m1 = warp_sum(m1) * (1.0f / RD); m2 = warp_sum(m2) * (1.0f / RD);
-    if (dxin || dxin16) {
-      float g[8];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!ok[u]) continue;                                    // warp-uniform
+      const long row = row0 + u * rstep;
+      const float pre[8] = {xq[u][0].x, xq[u][0].y, xq[u][0].z, xq[u][0].w, xq[u][1].x, xq[u][1].y, xq[u][1].z, xq[u][1].w};
+      const float dd[8] = {dq[u][0].x, dq[u][0].y, dq[u][0].z, dq[u][0].w, dq[u][1].x, dq[u][1].y, dq[u][1].z, dq[u][1].w};
+      float xh[8], dxh[8];
+      float m1 = 0.f, m2 = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int idx = (j / 4) * 128 + lane * 4 + (j % 4);
-        g[j] = rstd * (dxh[j] - m1 - xh[j] * m2);
-        if (GELU_IN) g[j] *= FAST ? gelu_fast_grad(pre[j]) : gelu_erf_grad(pre[j]);
-        if (add1) g[j] += add1[row * RD + idx];
-        if (add2) g[j] += add2[row * RD + idx];
-        ac[j] += g[j];
+        const float xv = GELU_IN ? (FAST ? gelu_fast(pre[j]) : gelu_erf(pre[j])) : pre[j];
+        xh[j] = (xv - mean[u]) * rstd[u];
+        const float d = dd[j];
+        dxh[j] = gamma ? d * gamma[idx] : d;
+        ag[j] = fmaf(d, xh[j], ag[j]); ab[j] += d;
+        m1 += dxh[j]; m2 = fmaf(dxh[j], xh[j], m2);
       }
+      m1 = warp_sum(m1) * (1.0f / RD); m2 = warp_sum(m2) * (1.0f / RD);
+      if (dxin || dxin16) {
+        const float e1[8] = {a1q[u][0].x, a1q[u][0].y, a1q[u][0].z, a1q[u][0].w, a1q[u][1].x, a1q[u][1].y, a1q[u][1].z, a1q[u][1].w};
+        const float e2[8] = {a2q[u][0].x, a2q[u][0].y, a2q[u][0].z, a2q[u][0].w, a2q[u][1].x, a2q[u][1].y, a2q[u][1].z, a2q[u][1].w};
+        float g[8];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const long o = row * lddx + c * 128 + lane * 4;
-        if (dxin) *reinterpret_cast<float4*>(dxin + o) = make_float4(g[c * 4], g[c * 4 + 1], g[c * 4 + 2], g[c * 4 + 3]);
-        if (dxin16) store_bf16x4(dxin16 + o, make_float4(g[c * 4], g[c * 4 + 1], g[c * 4 + 2], g[c * 4 + 3]));
+        for (int j = 0; j < 8; ++j) {
+          g[j] = rstd[u] * (dxh[j] - m1 - xh[j] * m2);
+          if (GELU_IN) g[j] *= FAST ? gelu_fast_grad(pre[j]) : gelu_erf_grad(pre[j]);
+          if (add1) g[j] += e1[j];
+          if (add2) g[j] += e2[j];
+          ac[j] += g[j];
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const long o = row * lddx + c * 128 + lane * 4;
+          if (dxin) *reinterpret_cast<float4*>(dxin + o) = make_float4(g[c * 4], g[c * 4 + 1], g[c * 4 + 2], g[c * 4 + 3]);
+          if (dxin16) store_bf16x4(dxin16 + o, make_float4(g[c * 4], g[c * 4 + 1], g[c * 4 + 2], g[c * 4 + 3]));
+        }
       }
     }
   }
@@ -381,29 +436,44 @@ template <int I>
 __global__ void __launch_bounds__(256)
 gate_head_fwd_kernel(const float* __restrict__ out, const float* __restrict__ Wcr, const float* __restrict__ bcr, int B,
                      int T, float* __restrict__ s) {
-  const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);      // row = b*T + t
+  // four consecutive rows per warp: every weight fragment (L1-resident, 36 KiB in all) is loaded once per four rows --
+  // with one row per warp the kernel was bound by the 72 weight loads per lane and row, not by the stream of `out`
+  constexpr int R = 4;
+  const long row0 = ((long)blockIdx.x * 8 + (threadIdx.x >> 5)) * R;      // row = b*T + t
   const int lane = threadIdx.x & 31;
-  if (row >= (long)B * T) return;
-  const long b = row / T, t = row % T;
-  float acc[I];
+  const long nrows = (long)B * T;
+  if (row0 >= nrows) return;
+  float acc[R][I];
 #pragma unroll
-  for (int j = 0; j < I; ++j) acc[j] = 0.f;
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int j = 0; j < I; ++j) acc[r][j] = 0.f;
 #pragma unroll
   for (int i = 0; i < I; ++i) {
-    const float* zp = out + ((b * I + i) * T + t) * RD + lane * 8;
-    const float4 z0 = *reinterpret_cast<const float4*>(zp), z1 = *reinterpret_cast<const float4*>(zp + 4);
+    float4 z0[R], z1[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long row = row0 + r < nrows ? row0 + r : nrows - 1;
+      const long b = row / T, t = row % T;
+      const float* zp = out + ((b * I + i) * T + t) * RD + lane * 8;
+      z0[r] = *reinterpret_cast<const float4*>(zp); z1[r] = *reinterpret_cast<const float4*>(zp + 4);
+    }
 #pragma unroll
     for (int j = 0; j < I; ++j) {
       const float* wp = Wcr + (long)j * I * RD + i * RD + lane * 8;
       const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp)), w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
-      acc[j] += z0.x * w0.x + z0.y * w0.y + z0.z * w0.z + z0.w * w0.w + z1.x * w1.x + z1.y * w1.y + z1.z * w1.z + z1.w * w1.w;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        acc[r][j] += z0[r].x * w0.x + z0[r].y * w0.y + z0[r].z * w0.z + z0[r].w * w0.w + z1[r].x * w1.x + z1[r].y * w1.y + z1[r].z * w1.z + z1[r].w * w1.w;
     }
   }
 #pragma unroll
-  for (int j = 0; j < I; ++j) {
-    const float v = warp_sum(acc[j]);
-    if (lane == 0) s[row * I + j] = v + bcr[j];
-  }
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int j = 0; j < I; ++j) {
+      const float v = warp_sum(acc[r][j]);
+      if (lane == 0 && row0 + r < nrows) s[(row0 + r) * I + j] = v + bcr[j];
+    }
 }
 
 // dWcr[j,(i,c)] += sum_(b,t) ds[(b,t),j] * out[b,i,t,c].  grid (row chunks of 128, I); thread = channel c.
@@ -432,7 +502,7 @@ gate_head_dw_kernel(const float* __restrict__ ds, const float* __restrict__ out,
 
 template <int I>
 int launch_gate_head(const float* out, const float* Wcr, const float* bcr, int B, int T, float* s, cudaStream_t st) {
-  gate_head_fwd_kernel<I><<<cdiv((long)B * T, 8), 256, 0, st>>>(out, Wcr, bcr, B, T, s);
+  gate_head_fwd_kernel<I><<<cdiv((long)B * T, 32), 256, 0, st>>>(out, Wcr, bcr, B, T, s);
   MRNB_CHECK_LAUNCH("gate_head_fwd_kernel");
   return MRNB_OK;
 }
@@ -1034,8 +1104,12 @@ int router_forward(const float* P, const float* x, const Dims& d, float* out_use
   MRNB_TRY(linear_rows(d, w.g1, w.g116, D, P + off[R_P2_W], W16 + off[R_P2_W], D, D, P + off[R_P2_B], x, w.y, D, st));
   {
     MrnbProfScope prof(MRNB_PROF_ROUTER_EW, st);
-    lnT_fwd_kernel<<<B * I, RD, 0, st>>>(w.y, P + off[R_CN_W], P + off[R_CN_B], tc ? nullptr : w.gn, tc ? w.gn16 : nullptr,
-                                         w.statsT, T, d.Tv, 1e-5f);
+    if (T == 64)
+      lnT_fwd64_kernel<<<B * I, RD, 0, st>>>(w.y, P + off[R_CN_W], P + off[R_CN_B], tc ? nullptr : w.gn, tc ? w.gn16 : nullptr,
+                                             w.statsT, d.Tv, 1e-5f);
+    else
+      lnT_fwd_kernel<<<B * I, RD, 0, st>>>(w.y, P + off[R_CN_W], P + off[R_CN_B], tc ? nullptr : w.gn, tc ? w.gn16 : nullptr,
+                                           w.statsT, T, d.Tv, 1e-5f);
     MRNB_CHECK_LAUNCH("lnT_fwd_kernel");
   }
   // g2[(b,t),(i,c)] = sum_(i',c') gn[(b,t),(i',c')] Wc[(i,c),(i',c')] + bc   (channel mixing over k = i*D+c)
