@@ -298,64 +298,38 @@ ln_rows_bwd_kernel(const float* __restrict__ xin, long ldx, const float* __restr
   float ag[8], ab[8], ac[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { ag[j] = 0.f; ab[j] = 0.f; ac[j] = 0.f; }
-  // two rows per iteration, 16-byte loads, all of them issued before the first reduction (one row per iteration with
-  // scalar loads left the kernel latency bound: 3.0 TB/s); per-lane accumulation order over the rows is unchanged
-  const long rstep = (long)gridDim.x * 8;
-  for (long row0 = (long)blockIdx.x * 8 + w; row0 < rows; row0 += 2 * rstep) {
-    float4 xq[2][2], dq[2][2], a1q[2][2], a2q[2][2];
-    float mean[2], rstd[2];
-    bool ok[2];
+  for (long row = (long)blockIdx.x * 8 + w; row < rows; row += (long)gridDim.x * 8) {
+    const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
+    float xh[8], dxh[8], pre[8];
+    float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const long row = row0 + u * rstep;
-      ok[u] = row < rows;
-      const long rr = ok[u] ? row : row0;
-      mean[u] = stats[rr * 2]; rstd[u] = stats[rr * 2 + 1];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        xq[u][c] = *reinterpret_cast<const float4*>(xin + rr * ldx + c * 128 + lane * 4);
-        dq[u][c] = *reinterpret_cast<const float4*>(dyn + rr * RD + c * 128 + lane * 4);
-        if (add1) a1q[u][c] = *reinterpret_cast<const float4*>(add1 + rr * RD + c * 128 + lane * 4);
-        if (add2) a2q[u][c] = *reinterpret_cast<const float4*>(add2 + rr * RD + c * 128 + lane * 4);
-      }
+    for (int j = 0; j < 8; ++j) {
+      const int idx = (j / 4) * 128 + lane * 4 + (j % 4);
+      pre[j] = xin[row * ldx + idx];
+      const float xv = GELU_IN ? (FAST ? gelu_fast(pre[j]) : gelu_erf(pre[j])) : pre[j];
+      xh[j] = (xv - mean) * rstd;
+      const float d = dyn[row * RD + idx];
+      dxh[j] = gamma ? d * gamma[idx] : d;
+      ag[j] = fmaf(d, xh[j], ag[j]); ab[j] += d;
+      m1 += dxh[j]; m2 = fmaf(dxh[j], xh[j], m2);
     }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (!ok[u]) continue;                                    // warp-uniform
-      const long row = row0 + u * rstep;
-      const float pre[8] = {xq[u][0].x, xq[u][0].y, xq[u][0].z, xq[u][0].w, xq[u][1].x, xq[u][1].y, xq[u][1].z, xq[u][1].w};
-      const float dd[8] = {dq[u][0].x, dq[u][0].y, dq[u][0].z, dq[u][0].w, dq[u][1].x, dq[u][1].y, dq[u][1].z, dq[u][1].w};
-      float xh[8], dxh[8];
-      float m1 = 0.f, m2 = 0.f;
+    m1 = warp_sum(m1) * (1.0f / RD); m2 = warp_sum(m2) * (1.0f / RD);
+    if (dxin || dxin16) {
+      float g[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int idx = (j / 4) * 128 + lane * 4 + (j % 4);
-        const float xv = GELU_IN ? (FAST ? gelu_fast(pre[j]) : gelu_erf(pre[j])) : pre[j];
-        xh[j] = (xv - mean[u]) * rstd[u];
-        const float d = dd[j];
-        dxh[j] = gamma ? d * gamma[idx] : d;
-        ag[j] = fmaf(d, xh[j], ag[j]); ab[j] += d;
-        m1 += dxh[j]; m2 = fmaf(dxh[j], xh[j], m2);
+        g[j] = rstd * (dxh[j] - m1 - xh[j] * m2);
+        if (GELU_IN) g[j] *= FAST ? gelu_fast_grad(pre[j]) : gelu_erf_grad(pre[j]);
+        if (add1) g[j] += add1[row * RD + idx];
+        if (add2) g[j] += add2[row * RD + idx];
+        ac[j] += g[j];
       }
-      m1 = warp_sum(m1) * (1.0f / RD); m2 = warp_sum(m2) * (1.0f / RD);
-      if (dxin || dxin16) {
-        const float e1[8] = {a1q[u][0].x, a1q[u][0].y, a1q[u][0].z, a1q[u][0].w, a1q[u][1].x, a1q[u][1].y, a1q[u][1].z, a1q[u][1].w};
-        const float e2[8] = {a2q[u][0].x, a2q[u][0].y, a2q[u][0].z, a2q[u][0].w, a2q[u][1].x, a2q[u][1].y, a2q[u][1].z, a2q[u][1].w};
-        float g[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          g[j] = rstd[u] * (dxh[j] - m1 - xh[j] * m2);
-          if (GELU_IN) g[j] *= FAST ? gelu_fast_grad(pre[j]) : gelu_erf_grad(pre[j]);
-          if (add1) g[j] += e1[j];
-          if (add2) g[j] += e2[j];
-          ac[j] += g[j];
-        }
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const long o = row * lddx + c * 128 + lane * 4;
-          if (dxin) *reinterpret_cast<float4*>(dxin + o) = make_float4(g[c * 4], g[c * 4 + 1], g[c * 4 + 2], g[c * 4 + 3]);
-          if (dxin16) store_bf16x4(dxin16 + o, make_float4(g[c * 4], g[c * 4 + 1], g[c * 4 + 2], g[c * 4 + 3]));
-        }
+      for (int c = 0; c < 2; ++c) {
+        const long o = row * lddx + c * 128 + lane * 4;
+        if (dxin) *reinterpret_cast<float4*>(dxin + o) = make_float4(g[c * 4], g[c * 4 + 1], g[c * 4 + 2], g[c * 4 + 3]);
+        if (dxin16) store_bf16x4(dxin16 + o, make_float4(g[c * 4], g[c * 4 + 1], g[c * 4 + 2], g[c * 4 + 3]));
       }
     }
   }
