@@ -867,20 +867,21 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // XOR-swizzled by row), so that global accesses are 64-byte row segments: lane = (row in a group of 8, float4 of the 16)
     float* stg = reinterpret_cast<float*>(sStg + q * 2048);
     const int rsub = lane >> 2, c4 = lane & 3;
-    // ---- OVL: this warpgroup also drains the q|k|v staging parts (one warp per TMEM lane quarter) into the q/k/v buffer of
-    // the head's parity.  Never blocking: a drain runs only when its part is complete in TMEM and (first part of a head)
-    // the target buffer has been retired by both attention streams; otherwise the warp goes back to the Y epilogue, which
-    // the attention of a later head may be waiting for (y_empty).
+    // ---- OVL: this warpgroup drains the q|k|v staging parts (one warp per TMEM lane quarter) into the q/k/v buffer of
+    // the head's parity: a drain runs when its part is complete in TMEM and (first part of a head) the target buffer has
+    // been retired by both attention streams.
     int d_u = blockIdx.x, d_h = 0, d_part = 0, d_e = -1;       // next drain: unit, head, part (2 per 128-token tile)
     uint32_t d_pc = 0, d_hc = 0;                               // staging phase counter, global head counter
     float* wbias = sBias + q * 3 * D;                          // this warp's copy of the expert's q|k|v bias
     auto try_drain = [&]() -> bool {
       if constexpr (!K::OVL) return false;
       if (d_u >= total) return false;
-      if (!mbar_test(&stg_full[0], d_pc & 1u)) return false;
+      // hardware-suspended waits: this warpgroup has nothing else to do, and a polling loop (test + nanosleep) was 20 %
+      // of the kernel's executed instructions, issued on the sub-partitions the softmax warps need
+      mbar_wait(&stg_full[0], d_pc & 1u);
       const int hb = d_hc & 1u;
       if (d_part == 0) {
-        if (!mbar_test(&qkvf[hb], ((d_hc >> 1) & 1u) ^ 1u)) return false;
+        mbar_wait(&qkvf[hb], ((d_hc >> 1) & 1u) ^ 1u);
         const int e = d_u / upg;
         if (e != d_e) {
           __syncwarp();
@@ -927,9 +928,7 @@ mixer_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     };
     if constexpr (K::OVL) {
       // OVL: the attention streams run the Y epilogue of their own tile; this warpgroup only drains q|k|v parts
-      while (d_u < total) {
-        if (!try_drain()) __nanosleep(64);
-      }
+      while (d_u < total) try_drain();
     } else {
     int i = 0;
     for (int u = blockIdx.x; u < total; u += gridDim.x, ++i) {
