@@ -418,6 +418,23 @@ class MRN(object):
             p.requires_grad = False
         self.net.model[-1].eval()
 
+    def model_eval_and_train(self, taski):
+        """il_modules/mrn.py:45-50 (only reached from the reference's commented-out call sites; kept for interface
+        parity): everything in train mode, then the experts of the earlier tasks in eval mode."""
+        self.model.train()
+        self.net.model[-1].train()
+        for i in range(taski if taski >= 1 else 0):
+            self.net.model[i].eval()
+
+    def freeze_step1(self, taski):
+        """il_modules/mrn.py:289-295 (dead code in the reference's MRN loop, mirrored for completeness): modes as in
+        `model_eval_and_train`, then the newest expert frozen and in eval mode."""
+        self.model_eval_and_train(taski)
+        self.model.train()
+        for p in self.net.model[-1].parameters():
+            p.requires_grad = False
+        self.net.model[-1].eval()
+
     def train_step_stage1(self, image, labels_index, labels_length, indexs, drop_scales=None):
         """One router-training iteration (il_modules/mrn.py:338-371) entirely on the device.
         image [B,4,32,256] fp32, labels_index [B,25] int64 (pad 1), labels_length [B] int32, indexs [B] int64.

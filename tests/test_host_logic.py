@@ -219,3 +219,25 @@ def test_rehearsal_memory_index_bookkeeping():
     for taski in (1, 2):
         big.build_rehearsal_memory(loader, taski)
     assert [ix.size for ix in loader.calls[-1][2]] == [5000, 5000]             # memory_num >= 5000: per task, never trimmed
+
+
+def test_model_eval_and_train_and_freeze_step1_set_the_reference_modes():
+    """il_modules/mrn.py:45-50, 289-295: earlier experts eval, newest expert train; freeze_step1 then calls model.train()
+    again -- the earlier experts are back in TRAIN mode, the reference's quirk the stage-1 step reproduces -- and freezes
+    the newest expert in eval mode while the router modules stay trainable."""
+    from mrn_b200.il_modules.mrn import MRN
+    from mrn_b200.modules.model import MRNNet
+    opt = make_opt()
+    net = MRNNet(opt)
+    for c in (12, 20):
+        net.update_fc(256, c); net.build_prediction(opt, c)
+    learner = MRN.__new__(MRN)                      # host logic only: no device
+    learner.opt = opt
+    learner.model = net
+    net.eval()
+    learner.model_eval_and_train(1)
+    assert net.training and net.model[1].training and not net.model[0].training
+    learner.freeze_step1(1)
+    assert net.training and net.model[0].training and not net.model[1].training
+    assert all(not p.requires_grad for p in net.model[1].parameters())
+    assert any(p.requires_grad for n, p in net.named_parameters() if not n.startswith("model."))
