@@ -10,16 +10,23 @@
 // proj GEMM) through a [M,3D] tensor.
 //
 // A unit = one sample of one expert = N = 32768 / D tokens (512 / 256 / 128), NT = N / 128 query tiles, D / 32 heads.
-// Shared memory holds A of the whole unit (64 KiB), q/k/v of ONE head for all tokens (3 x N x 64 B), one probability
-// tile, one head-output tile and the weights of the current head.  TMEM (512 columns):
+// TMEM (512 columns):
 //     [0,256)   Y = proj accumulator of the whole unit (NT tiles x D columns), accumulated over heads by the MMA itself
-//     [256,384) S = q k^T of one (query tile, key block)
-//     [384,416) O = P v of one key block                   [416,512) staging of one 128-token q|k|v tile
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = softmax / epilogue (two per TMEM
-// lane quarter: 64-key / 16-dim halves).  Per head: phase 1 = q|k|v tiles (MMA -> TMEM -> bf16 -> swizzled smem),
-// phase 2 = attention over the (query tile, key block) pairs with S(p+1) issued while the softmax of pair p runs, head
-// output -> smem -> proj MMA accumulating into Y.  After the last head the epilogue adds bias, DropPath scale and the
-// fp32 residual, stores x in place and emits LN2.
+//     [256,320) / [320,384)  S = q k^T of one (query tile, 64-key block), one per softmax stream
+//     [384,416) / [416,448)  O = P v of the stream's query tile
+//     [448,512) OVL: staging of the q|k / v parts of one 128-token tile (the non-OVL staging aliases the S / O columns)
+// 512 threads in four warpgroups with their own register budgets (setmaxnreg): control (warp 0 TMA producer, warps 1 / 2
+// MMA issuers of the two streams, warp 3 OVL q|k|v issuer), two softmax streams of four warps (one query row per
+// thread), and a fourth warpgroup that is the Y epilogue (64-wide stage) or the q|k|v drain (OVL).
+//   64-wide stage: A of the whole unit resident in smem (64 KiB); per head phase 1 = q|k|v of all tiles (MMA -> TMEM ->
+//     all eight softmax warps -> bf16 swizzled smem), phase 2 = attention, stream s on query tiles s, s + 2, with S(p+1)
+//     issued while the softmax of pair p runs; head output -> smem -> proj MMA into Y; the epilogue warpgroup adds bias,
+//     DropPath scale and the fp32 residual, stores x in place and emits LN2 while the next unit is already running.
+//   128-wide stage (MRNB_MIXER_OVL): q/k/v double buffered by head parity, A streamed one tile at a time; the q|k|v GEMM
+//     and drain of head h+1 run under the attention of head h; each stream runs the Y epilogue of its own tile; the first
+//     S of the next head is issued behind the last P V of the current one.
+// Shared memory: A, q/k/v of one (OVL: two) head(s) for all tokens (3 x N x 64 B each), one probability / head-output
+// tile per stream, the q|k|v and proj weights of the current head(s), epilogue staging.
 #include "common.cuh"
 #include "mixer_tc.h"
 #include <cuda.h>
